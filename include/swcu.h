@@ -1,0 +1,259 @@
+/*
+ * swcu.h — C-ABI of the B200 draw path that stands in for SwiftShader's
+ * DrawCall::run (src/Device/Renderer.cpp:551-598) and everything below it.
+ *
+ * Boundary: the reference hands each draw from
+ * sw::Renderer::draw (src/Device/Renderer.hpp:211-213, Renderer.cpp:183-490) to
+ * three JIT'd routines per batch/cluster.  That is too fine for a GPU, so the
+ * cut is one level up: ONE call per draw (swcu_draw), plus the equivalents of
+ * Renderer::synchronize (Renderer.cpp:664-671) and of the memory the draw
+ * reads/writes (vk::DeviceMemory is host malloc memory in the reference; here
+ * each registered host range gets a device-resident shadow in HBM).
+ *
+ * Every pointer inside swcu_draw_desc is a HOST address, exactly the address
+ * the reference stores in sw::DrawData (Renderer.hpp:58-113), sw::Stream
+ * (src/Device/Stream.hpp:22-32) and sw::Mipmap::buffer
+ * (src/Device/Sampler.hpp:25-39).  The library translates it to the device
+ * shadow of the registered range that contains it.
+ *
+ * Plain C, POD only, no C++/torch types.  Enum-valued fields carry the Vulkan
+ * enum value verbatim (VkFormat, VkCompareOp, VkBlendFactor, ...), so the host
+ * shim can copy pipeline state through without translation.
+ *
+ * Unsupported state is a hard error (SWCU_E_UNSUPPORTED); there is no CPU
+ * fallback (north_star).
+ */
+#ifndef SWCU_H
+#define SWCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWCU_OK 0
+#define SWCU_E_UNSUPPORTED (-1) /* state outside the implemented subset (reference: UNSUPPORTED(), Debug.hpp:139) */
+#define SWCU_E_INVALID (-2)     /* malformed argument / unregistered pointer */
+#define SWCU_E_CUDA (-3)        /* CUDA runtime error, see swcu_last_error */
+#define SWCU_E_NOMEM (-4)
+
+#define SWCU_MAX_INPUTS 16         /* vertex input locations (reference: MAX_INTERFACE_COMPONENTS/4 = 32) */
+#define SWCU_MAX_SAMPLED_IMAGES 4  /* combined image samplers visible to the fragment shader */
+#define SWCU_MIPMAP_LEVELS 15      /* sw::MIPMAP_LEVELS, src/Device/Config.hpp */
+#define SWCU_MAX_VARYING_COMPONENTS 16
+
+typedef struct swcu_ctx swcu_ctx;
+
+/* sw::Stream (src/Device/Stream.hpp:22-32) + DrawData::input/stride/robustnessSize (Renderer.hpp:63-65). */
+typedef struct swcu_vertex_input
+{
+	const void *buffer;      /* host address of the first vertex's attribute (binding base + binding offset + attribute offset) */
+	uint32_t robustnessSize; /* bytes available from `buffer` (robustBufferAccess clamp, VertexRoutine.cpp:192-207); 0 = unchecked */
+	uint32_t vertexStride;
+	uint32_t format;         /* VkFormat; VK_FORMAT_UNDEFINED (0) = unused location */
+	uint32_t reserved;
+} swcu_vertex_input;
+
+/* One level of sw::Mipmap (src/Device/Sampler.hpp:25-39). */
+typedef struct swcu_mip_level
+{
+	const void *buffer; /* host address of texel (0,0) */
+	uint32_t width;
+	uint32_t height;
+	uint32_t pitchP;    /* row pitch in texels */
+	uint32_t reserved;
+} swcu_mip_level;
+
+/* sw::Texture + vk::SamplerState as written by vkUpdateDescriptorSets
+ * (src/Vulkan/VkDescriptorSetLayout.cpp:299-336,466-503; src/Vulkan/VkSampler.hpp:29-63). */
+typedef struct swcu_sampled_image
+{
+	uint32_t set;
+	uint32_t binding;
+	uint32_t format;     /* VkFormat of the image view */
+	uint32_t levelCount; /* levels in the view; level[] beyond it replicate the last (VkDescriptorSetLayout.cpp:470) */
+	swcu_mip_level level[SWCU_MIPMAP_LEVELS];
+	uint32_t magFilter;  /* VkFilter */
+	uint32_t minFilter;
+	uint32_t mipmapMode; /* VkSamplerMipmapMode */
+	uint32_t addressModeU; /* VkSamplerAddressMode */
+	uint32_t addressModeV;
+	float mipLodBias;
+	float minLod;
+	float maxLod;
+	uint32_t anisotropyEnable;
+	uint32_t compareEnable;
+	uint32_t unnormalizedCoordinates;
+	uint32_t reserved;
+} swcu_sampled_image;
+
+/* VkStencilOpState as consumed by PixelProcessor::Stencil::set (PixelProcessor.hpp:122-147). */
+typedef struct swcu_stencil_face
+{
+	uint32_t failOp; /* VkStencilOp */
+	uint32_t passOp;
+	uint32_t depthFailOp;
+	uint32_t compareOp; /* VkCompareOp */
+	uint32_t compareMask;
+	uint32_t writeMask;
+	uint32_t reference;
+} swcu_stencil_face;
+
+/* DrawData::{color,depth,stencil}Buffer/PitchB/SliceB (Renderer.hpp:90-98); layout per SURVEY §8a-R15:
+ * linear rows, MSAA sample q is a whole slice at +q*sliceB. */
+typedef struct swcu_attachment
+{
+	void *buffer;    /* host address of pixel (0,0) of sample 0; NULL = no attachment */
+	uint32_t format; /* VkFormat */
+	int32_t pitchB;
+	int32_t sliceB;
+	uint32_t width;  /* extent of the attachment in pixels (bounds for tile staging) */
+	uint32_t height;
+	uint32_t reserved;
+} swcu_attachment;
+
+typedef struct swcu_rect
+{
+	int32_t x, y;
+	uint32_t width, height;
+} swcu_rect;
+
+/* Flattened arguments + gathered state of sw::Renderer::draw (Renderer.cpp:183-490). */
+typedef struct swcu_draw_desc
+{
+	uint32_t structSize; /* sizeof(swcu_draw_desc), ABI check */
+
+	/* --- input assembly: Renderer::draw(count, baseVertex, indexBuffer), DrawCall::processVertices (Renderer.cpp:600-628) */
+	uint32_t topology;            /* VkPrimitiveTopology */
+	uint32_t provokingVertexMode; /* VkProvokingVertexModeEXT (0 = FIRST, reference default Context.hpp:329) */
+	uint32_t indexType;           /* 0 = non-indexed, 2 = uint16, 4 = uint32 (bytes per index) */
+	const void *indexBuffer;      /* host address of the first index of this draw (NULL when non-indexed) */
+	uint32_t primitiveCount;      /* number of triangles (Renderer::draw `count`) */
+	int32_t baseVertex;           /* added to every index (firstVertex for non-indexed draws) */
+	swcu_vertex_input input[SWCU_MAX_INPUTS];
+
+	/* --- shaders: SpirvShader::insns of the two stages (narrow translator) */
+	const uint32_t *vertexShader;
+	uint32_t vertexShaderWords;
+	uint32_t fragmentShaderWords;
+	const uint32_t *fragmentShader;
+
+	/* --- pre-rasterization state (Renderer.cpp:300-345, SetupProcessor.cpp:58-104) */
+	float viewportX, viewportY, viewportWidth, viewportHeight, viewportMinDepth, viewportMaxDepth;
+	swcu_rect scissor;
+	swcu_rect renderArea;
+	uint32_t cullMode;  /* VkCullModeFlags */
+	uint32_t frontFace; /* VkFrontFace */
+	uint32_t depthClipEnable; /* reference default true */
+	float depthBiasConstant, depthBiasSlope, depthBiasClamp;
+
+	/* --- multisampling */
+	uint32_t sampleCount; /* 1 or 4 */
+	uint32_t sampleMask;
+
+	/* --- depth / stencil (PixelProcessor.cpp:74-140) */
+	uint32_t depthTestEnable;
+	uint32_t depthWriteEnable;
+	uint32_t depthCompareOp; /* VkCompareOp */
+	uint32_t stencilTestEnable;
+	swcu_stencil_face front;
+	swcu_stencil_face back;
+
+	/* --- colour output: blend state BEFORE folding; the library folds it like
+	 *     FragmentOutputInterfaceState::getBlendState (src/Device/Context.cpp:1090-1270). */
+	uint32_t blendEnable;
+	uint32_t srcColorBlendFactor, dstColorBlendFactor, colorBlendOp; /* VkBlendFactor / VkBlendOp */
+	uint32_t srcAlphaBlendFactor, dstAlphaBlendFactor, alphaBlendOp;
+	uint32_t colorWriteMask; /* VkColorComponentFlags */
+	float blendConstants[4];
+
+	/* --- attachments */
+	swcu_attachment color;
+	swcu_attachment depth;
+	swcu_attachment stencil;
+
+	/* --- descriptors visible to the fragment shader */
+	uint32_t sampledImageCount;
+	uint32_t reserved0;
+	swcu_sampled_image sampledImage[SWCU_MAX_SAMPLED_IMAGES];
+} swcu_draw_desc;
+
+/* What the narrow SPIR-V translator extracted from one module (for tests and caching). */
+#define SWCU_SRC_INPUT 0 /* value = location*4 + component of a stage input */
+#define SWCU_SRC_CONST 1 /* value = IEEE-754 bits of a float constant */
+#define SWCU_SRC_TEXEL 2 /* fragment only: value = component of the OpImageSampleImplicitLod result */
+typedef struct swcu_shader_operand
+{
+	uint32_t kind;
+	uint32_t value;
+} swcu_shader_operand;
+
+typedef struct swcu_shader_info
+{
+	uint32_t stage;                /* 0 = vertex, 4 = fragment (SpvExecutionModel) */
+	uint32_t outputMask;           /* vertex: bit i set if varying component i is written; fragment: components of location 0 written */
+	swcu_shader_operand position[4];                           /* vertex: gl_Position.xyzw */
+	swcu_shader_operand output[SWCU_MAX_VARYING_COMPONENTS];   /* vertex: varyings (location*4+component); fragment: output[0..3] = colour location 0 */
+	uint32_t inputMask;            /* stage inputs read (bit = location*4+component) */
+	uint32_t flatMask;             /* fragment: inputs decorated Flat */
+	uint32_t noPerspectiveMask;    /* fragment: inputs decorated NoPerspective */
+	uint32_t usesTexture;          /* fragment: 1 if a combined image sampler is sampled */
+	uint32_t textureSet, textureBinding;
+	swcu_shader_operand texCoord[2]; /* fragment: u, v operands of the sample */
+} swcu_shader_info;
+
+/* Counters for bench / tests. */
+typedef struct swcu_stats
+{
+	uint64_t draws;
+	uint64_t kernelLaunches;   /* kernels of this library launched since create/reset */
+	uint64_t primitives;
+	uint64_t h2dBytes;
+	uint64_t d2hBytes;
+} swcu_stats;
+
+/* ---- lifetime ---- */
+int swcu_create(swcu_ctx **out, int device_ordinal);
+void swcu_destroy(swcu_ctx *ctx);
+const char *swcu_last_error(swcu_ctx *ctx); /* ctx may be NULL: last error of a failed swcu_create / translate */
+
+/* ---- memory: device shadows of host ranges (stands in for vk::DeviceMemory, src/Vulkan/VkDeviceMemory.cpp) ---- */
+int swcu_mem_register(swcu_ctx *ctx, const void *host_base, size_t bytes);
+int swcu_mem_unregister(swcu_ctx *ctx, const void *host_base);
+int swcu_mem_upload(swcu_ctx *ctx, const void *host_ptr, size_t bytes);   /* host -> shadow, async on the context stream */
+int swcu_mem_download(swcu_ctx *ctx, void *host_ptr, size_t bytes);       /* shadow -> host, async; complete after swcu_sync */
+void *swcu_mem_device_ptr(swcu_ctx *ctx, const void *host_ptr);           /* device address of the shadow (for NCCL plumbing); NULL if unregistered */
+
+/* ---- the hot path ---- */
+int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc); /* replaces DrawCall::run; asynchronous */
+int swcu_sync(swcu_ctx *ctx);                             /* replaces Renderer::synchronize (Renderer.cpp:664-671) */
+
+/* ---- the steps either side of the draw, on the resident shadows ---- */
+/* Blitter::fastClear (src/Device/Blitter.cpp:170-325) for RGBA8 / D32F / S8: fills `samples` slices. */
+int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t samples, const swcu_rect *area, const void *value /* 4 bytes (1 for S8) */);
+/* Blitter::fastResolve (Blitter.cpp:2079-2205): 4x RGBA8 -> 1x, avg(avg(s0,s1),avg(s2,s3)) with (a+b+1)>>1. */
+int swcu_resolve(swcu_ctx *ctx, const swcu_attachment *src, uint32_t samples, const swcu_attachment *dst);
+
+/* ---- narrow SPIR-V translator (host-only, no GPU needed) ---- */
+int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_shader_info *out, char *err, size_t errlen);
+
+/* ---- plumbing for measurement and multi-GPU ---- */
+int swcu_set_stream(swcu_ctx *ctx, void *cuda_stream); /* use an external cudaStream_t (e.g. torch's current stream); NULL = own stream */
+int swcu_timer_begin(swcu_ctx *ctx);                   /* cudaEventRecord on the context stream */
+int swcu_timer_end(swcu_ctx *ctx, float *elapsed_ms);  /* records, synchronises, returns elapsed ms */
+int swcu_get_stats(swcu_ctx *ctx, swcu_stats *out);
+int swcu_reset_stats(swcu_ctx *ctx);
+/* Per-kernel device time of the LAST swcu_draw when profiling is on (events around every launch).
+ * names/ms arrays of capacity n; returns number of kernels written. */
+int swcu_set_profiling(swcu_ctx *ctx, int enable);
+int swcu_last_draw_kernels(swcu_ctx *ctx, const char **names, float *ms, int n);
+/* Tuning knob for tests: force the binned path even for tiny draws (default: direct mode below a threshold). */
+int swcu_set_option(swcu_ctx *ctx, const char *name, int value);
+const char *swcu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWCU_H */

@@ -1,0 +1,186 @@
+"""Python binding of the CPU oracle (oracle/libswref.so) and of the reference harness (oracle/_ref/refrender).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing under swiftshader_b200/ imports this module.
+
+The oracle does not parse SPIR-V: the meaning of each fixture shader is written down by hand in SHADER_SPECS
+(from the GLSL in /root/reference/tests/VulkanBenchmarks/TriangleBenchmarks.cpp:56-81,109-140,168-198 and
+SURVEY.md §9.2), so that the product's translator (csrc/spirv_subset.cpp) is checked against an independent
+statement of what the shader does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+from swiftshader_b200 import capi
+from swiftshader_b200.scene import Scene
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libswref.so")
+REF_ICD = os.path.join(_HERE, "_ref", "libvk_swiftshader.so")
+REFRENDER = os.path.join(_HERE, "_ref", "refrender")
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE, "libswref.so"])
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = C.CDLL(LIB_PATH)
+        L.swref_draw.argtypes = [C.POINTER(capi.DrawDesc), C.POINTER(capi.ShaderInfo), C.POINTER(capi.ShaderInfo)]
+        L.swref_clear.argtypes = [C.POINTER(capi.Attachment), C.c_uint32, C.POINTER(capi.Rect), C.c_void_p]
+        L.swref_resolve.argtypes = [C.POINTER(capi.Attachment), C.c_uint32, C.POINTER(capi.Attachment)]
+        L.swref_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _f32bits(x: float) -> int:
+    return struct.unpack("<I", struct.pack("<f", x))[0]
+
+
+def _inp(loc: int, comp: int):
+    return (capi.SRC_INPUT, loc * 4 + comp)
+
+
+def _const(x: float):
+    return (capi.SRC_CONST, _f32bits(x))
+
+
+def _texel(c: int):
+    return (capi.SRC_TEXEL, c)
+
+
+def _vs(position, outputs: dict) -> capi.ShaderInfo:
+    s = capi.ShaderInfo()
+    s.stage = 0
+    inmask = 0
+    for i, (k, v) in enumerate(position):
+        s.position[i] = capi.ShaderOperand(k, v)
+        if k == capi.SRC_INPUT:
+            inmask |= 1 << v
+    for comp, (k, v) in outputs.items():
+        s.output[comp] = capi.ShaderOperand(k, v)
+        s.outputMask |= 1 << comp
+        if k == capi.SRC_INPUT:
+            inmask |= 1 << v
+    s.inputMask = inmask
+    return s
+
+
+def _fs(colour, tex=None) -> capi.ShaderInfo:
+    s = capi.ShaderInfo()
+    s.stage = 4
+    inmask = 0
+    for i, (k, v) in enumerate(colour):
+        s.output[i] = capi.ShaderOperand(k, v)
+        s.outputMask |= 1 << i
+        if k == capi.SRC_INPUT:
+            inmask |= 1 << v
+    if tex is not None:
+        (set_, binding, u, v) = tex
+        s.usesTexture, s.textureSet, s.textureBinding = 1, set_, binding
+        for i, (k, val) in enumerate((u, v)):
+            s.texCoord[i] = capi.ShaderOperand(k, val)
+            if k == capi.SRC_INPUT:
+                inmask |= 1 << val
+    s.inputMask = inmask
+    return s
+
+
+# Hand-written meaning of each fixture shader (NOT derived from the SPIR-V).
+SHADER_SPECS = {
+    # gl_Position = vec4(inPos.xyz, 1.0)
+    "vs_pos3": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)], {}),
+    # outColor(loc0).rgb = inColor(loc1).rgb
+    "vs_pos3_col3": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)],
+                                {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2)}),
+    # outTexCoord(loc0).xy = inTexCoord(loc1).xy
+    "vs_pos3_uv2": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)], {0: _inp(1, 0), 1: _inp(1, 1)}),
+    # gl_Position = inPos (vec4); outCol = inCol (vec4)
+    "vs_pos4_col4": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _inp(0, 3)],
+                                {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2), 3: _inp(1, 3)}),
+    "fs_white": lambda: _fs([_const(1.0)] * 4),
+    "fs_col3": lambda: _fs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)]),
+    "fs_col4": lambda: _fs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _inp(0, 3)]),
+    "fs_tex_uv2": lambda: _fs([_texel(0), _texel(1), _texel(2), _texel(3)], tex=(0, 0, _inp(0, 0), _inp(0, 1))),
+    "fs_tex_col4": lambda: _fs([_texel(0), _texel(1), _texel(2), _texel(3)], tex=(0, 0, _inp(0, 0), _inp(0, 1))),
+}
+
+
+def shader_spec(name: str) -> capi.ShaderInfo:
+    return SHADER_SPECS[name]()
+
+
+def render_oracle(scene: Scene, att: dict | None = None, render_area=None) -> dict:
+    """Render every draw of the scene with the C restatement, in order, into host numpy attachments."""
+    L = lib()
+    att = att if att is not None else scene.alloc_attachments()
+    for dr in scene.draws:
+        keep: list = []
+        d = scene.build_desc(dr, att, keep, render_area)
+        vs, fs = shader_spec(dr.vs), shader_spec(dr.fs)
+        rc = L.swref_draw(C.byref(d), C.byref(vs), C.byref(fs))
+        if rc != 0:
+            raise RuntimeError(f"swref_draw failed: {rc}")
+    return att
+
+
+def resolve_oracle(scene: Scene, att: dict) -> np.ndarray:
+    H2, W = scene.padded_height(), scene.width
+    out = np.zeros((H2, W, 4), dtype=np.uint8)
+    src = capi.Attachment(att["color"].ctypes.data, scene.colorFormat, W * 4, H2 * W * 4, W, scene.height, 0)
+    dst = capi.Attachment(out.ctypes.data, scene.colorFormat, W * 4, H2 * W * 4, W, scene.height, 0)
+    rc = lib().swref_resolve(C.byref(src), scene.samples, C.byref(dst))
+    if rc != 0:
+        raise RuntimeError(f"swref_resolve failed: {rc}")
+    return out
+
+
+def reference_available() -> bool:
+    return os.path.exists(REF_ICD) and os.path.exists(REFRENDER)
+
+
+def render_reference(scene: Scene, time_frames: int = 0, threads: int | None = None) -> dict:
+    """Render the scene with the REFERENCE ICD (oracle/_ref).  Returns colour (resolved when multisampled),
+    depth/stencil when single-sampled, and the timing JSON when time_frames > 0."""
+    if not reference_available():
+        raise RuntimeError("reference ICD not built (oracle/build_ref.sh); only available where /root/reference is")
+    with tempfile.TemporaryDirectory() as td:
+        sp, op = os.path.join(td, "scene.bin"), os.path.join(td, "out.bin")
+        scene.write_ref_scene(sp)
+        if threads is not None:  # docs/RuntimeConfiguration.md:9-22 — SwiftShader.ini is read from the CWD
+            with open(os.path.join(td, "SwiftShader.ini"), "w") as f:
+                f.write(f"[Processor]\nThreadCount={threads}\n")
+        cmd = [REFRENDER, REF_ICD, sp, op]
+        if time_frames:
+            cmd += ["--time", str(time_frames)]
+        res = subprocess.run(cmd, cwd=td, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"refrender failed ({res.returncode}): {res.stderr[-2000:]}")
+        raw = open(op, "rb").read()
+    magic, W, H, hasD, hasS, samples = struct.unpack_from("<6I", raw, 0)
+    assert magic == 0x4F525753 and W == scene.width and H == scene.height
+    off = 24
+    out = {"color": np.frombuffer(raw, np.uint8, W * H * 4, off).reshape(H, W, 4).copy()}
+    off += W * H * 4
+    if hasD:
+        out["depth"] = np.frombuffer(raw, np.float32, W * H, off).reshape(H, W).copy()
+        off += W * H * 4
+    if hasS:
+        out["stencil"] = np.frombuffer(raw, np.uint8, W * H, off).reshape(H, W).copy()
+    if time_frames:
+        out["timing"] = json.loads(res.stdout.strip().splitlines()[-1])
+    return out

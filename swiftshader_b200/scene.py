@@ -1,0 +1,425 @@
+"""Scenes: the inputs of a draw (vertex/index/texture bytes + pipeline state) and their flattening into
+``swcu_draw_desc`` — the Python-side counterpart of what ``sw::Renderer::draw`` gathers
+(/root/reference/src/Device/Renderer.cpp:183-490) and of the reference test harness
+(tests/VulkanWrapper/DrawTester.cpp:62-102,205-406).
+
+Nothing here computes pixels.  ``Scene.write_ref_scene`` serialises the same inputs for oracle/refrender.cpp
+(the harness that drives the reference ICD); ``Device.render`` sends them through the C-ABI to the CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import capi, spirv
+
+# ---- Vulkan enum values (vulkan_core.h) ----
+FMT_R8G8B8A8_UNORM = 37
+FMT_B8G8R8A8_UNORM = 44
+FMT_R32_SFLOAT, FMT_R32G32_SFLOAT, FMT_R32G32B32_SFLOAT, FMT_R32G32B32A32_SFLOAT = 100, 103, 106, 109
+FMT_D32_SFLOAT = 126
+FMT_S8_UINT = 127
+FLOAT_FORMATS = {1: FMT_R32_SFLOAT, 2: FMT_R32G32_SFLOAT, 3: FMT_R32G32B32_SFLOAT, 4: FMT_R32G32B32A32_SFLOAT}
+TOPO_TRIANGLE_LIST, TOPO_TRIANGLE_STRIP, TOPO_TRIANGLE_FAN = 3, 4, 5
+CMP_NEVER, CMP_LESS, CMP_EQUAL, CMP_LESS_OR_EQUAL, CMP_GREATER, CMP_NOT_EQUAL, CMP_GREATER_OR_EQUAL, CMP_ALWAYS = range(8)
+SOP_KEEP, SOP_ZERO, SOP_REPLACE, SOP_INC_CLAMP, SOP_DEC_CLAMP, SOP_INVERT, SOP_INC_WRAP, SOP_DEC_WRAP = range(8)
+(BF_ZERO, BF_ONE, BF_SRC_COLOR, BF_ONE_MINUS_SRC_COLOR, BF_DST_COLOR, BF_ONE_MINUS_DST_COLOR, BF_SRC_ALPHA,
+ BF_ONE_MINUS_SRC_ALPHA, BF_DST_ALPHA, BF_ONE_MINUS_DST_ALPHA, BF_CONSTANT_COLOR, BF_ONE_MINUS_CONSTANT_COLOR,
+ BF_CONSTANT_ALPHA, BF_ONE_MINUS_CONSTANT_ALPHA, BF_SRC_ALPHA_SATURATE) = range(15)
+BOP_ADD, BOP_SUBTRACT, BOP_REVERSE_SUBTRACT, BOP_MIN, BOP_MAX = range(5)
+CULL_NONE, CULL_FRONT, CULL_BACK = 0, 1, 2
+FRONT_CCW, FRONT_CW = 0, 1
+FILTER_NEAREST, FILTER_LINEAR = 0, 1
+MIPMAP_NEAREST, MIPMAP_LINEAR = 0, 1
+ADDR_REPEAT, ADDR_MIRRORED_REPEAT, ADDR_CLAMP_TO_EDGE = 0, 1, 2
+
+
+@dataclass
+class StencilFace:
+    failOp: int = SOP_KEEP
+    passOp: int = SOP_KEEP
+    depthFailOp: int = SOP_KEEP
+    compareOp: int = CMP_ALWAYS
+    compareMask: int = 0xFF
+    writeMask: int = 0xFF
+    reference: int = 0
+
+    def tuple(self):
+        return (self.failOp, self.passOp, self.depthFailOp, self.compareOp, self.compareMask, self.writeMask, self.reference)
+
+
+@dataclass
+class Texture:
+    """RGBA8 2-D texture with a mip chain + sampler state (vk::SamplerState, src/Vulkan/VkSampler.hpp:29-63)."""
+    levels: list  # list of (h, w, 4) uint8 arrays, level 0 first
+    magFilter: int = FILTER_LINEAR
+    minFilter: int = FILTER_LINEAR
+    mipmapMode: int = MIPMAP_LINEAR
+    addressModeU: int = ADDR_REPEAT
+    addressModeV: int = ADDR_REPEAT
+    mipLodBias: float = 0.0
+    minLod: float = 0.0
+    maxLod: float = 0.0
+    set: int = 0
+    binding: int = 0
+
+    def packed(self) -> np.ndarray:
+        """All levels back to back, tightly packed (the layout both the ICD upload and our desc use)."""
+        return np.concatenate([np.ascontiguousarray(l, dtype=np.uint8).reshape(-1) for l in self.levels])
+
+    @staticmethod
+    def box_chain(level0: np.ndarray) -> list:
+        """Full mip chain by 2x2 box filtering (host-side, like an application would upload)."""
+        levels = [np.ascontiguousarray(level0, dtype=np.uint8)]
+        while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+            a = levels[-1].astype(np.uint32)
+            h, w = a.shape[:2]
+            h2, w2 = max(1, h // 2), max(1, w // 2)
+            a = a[: h2 * 2 if h > 1 else 1, : w2 * 2 if w > 1 else 1]
+            if h > 1:
+                a = a[0::2] + a[1::2]
+            else:
+                a = a * 2
+            if w > 1:
+                a = a[:, 0::2] + a[:, 1::2]
+            else:
+                a = a * 2
+            levels.append(((a + 2) // 4).astype(np.uint8))
+        return levels
+
+
+@dataclass
+class Draw:
+    vertices: np.ndarray  # (N, k) float32, interleaved
+    attribs: list  # [(location, components, float_offset)]
+    vs: str
+    fs: str
+    indices: Optional[np.ndarray] = None  # uint16 / uint32, or None
+    topology: int = TOPO_TRIANGLE_LIST
+    count: Optional[int] = None  # vertex/index count (default: all)
+    first: int = 0  # firstIndex / firstVertex
+    vertexOffset: int = 0
+    viewport: Optional[tuple] = None  # (x, y, w, h, minDepth, maxDepth); default full FB
+    scissor: Optional[tuple] = None  # (x, y, w, h)
+    cullMode: int = CULL_NONE
+    frontFace: int = FRONT_CCW
+    depthTest: bool = False
+    depthWrite: bool = False
+    depthCompareOp: int = CMP_LESS_OR_EQUAL
+    stencilTest: bool = False
+    front: StencilFace = field(default_factory=StencilFace)
+    back: StencilFace = field(default_factory=StencilFace)
+    depthBias: tuple = (0.0, 0.0, 0.0)  # constant, clamp, slope
+    blend: bool = False
+    srcColor: int = BF_SRC_ALPHA
+    dstColor: int = BF_ONE_MINUS_SRC_ALPHA
+    colorOp: int = BOP_ADD
+    srcAlpha: int = BF_ONE
+    dstAlpha: int = BF_ZERO
+    alphaOp: int = BOP_ADD
+    colorWriteMask: int = 0xF
+    blendConstants: tuple = (0.0, 0.0, 0.0, 0.0)
+    sampleMask: int = 0xFFFFFFFF
+    texture: Optional[Texture] = None
+
+    def vertex_count(self) -> int:
+        if self.count is not None:
+            return self.count
+        return len(self.indices) if self.indices is not None else self.vertices.shape[0]
+
+    def primitive_count(self) -> int:
+        n = self.vertex_count()
+        if self.topology == TOPO_TRIANGLE_LIST:
+            return n // 3
+        return max(0, n - 2)
+
+
+@dataclass
+class Scene:
+    width: int
+    height: int
+    draws: list
+    samples: int = 1
+    colorFormat: int = FMT_R8G8B8A8_UNORM
+    hasDepth: bool = False
+    hasStencil: bool = False
+    clearColor: tuple = (0.0, 0.0, 0.0, 0.0)
+    clearDepth: float = 1.0
+    clearStencil: int = 0
+
+    # ---- attachments (linear rows, height padded to even, sample q = slice q) ----
+    def padded_height(self) -> int:
+        return (self.height + 1) & ~1
+
+    def clear_color_bytes(self) -> np.ndarray:
+        """UNORM8 pack of the clear colour as Blitter::clear does (round-to-nearest of c*255)."""
+        c = np.clip(np.array(self.clearColor, dtype=np.float32), 0, 1)
+        b = np.rint(c * np.float32(255.0)).astype(np.uint8)
+        if self.colorFormat == FMT_B8G8R8A8_UNORM:
+            b = b[[2, 1, 0, 3]]
+        return b
+
+    def alloc_attachments(self) -> dict:
+        H2, W, S = self.padded_height(), self.width, self.samples
+        att = {"color": np.empty((S, H2, W, 4), dtype=np.uint8)}
+        att["color"][:] = self.clear_color_bytes()
+        if self.hasDepth:
+            att["depth"] = np.full((S, H2, W), self.clearDepth, dtype=np.float32)
+        if self.hasStencil:
+            att["stencil"] = np.full((S, H2, W), self.clearStencil & 0xFF, dtype=np.uint8)
+        return att
+
+    # ---- flattening into the C-ABI descriptor ----
+    def build_desc(self, draw: Draw, att: dict, keep: list, render_area: Optional[tuple] = None,
+                   dev: Optional[list] = None) -> capi.DrawDesc:
+        """Fill a swcu_draw_desc with HOST addresses of numpy buffers. ``keep`` receives every array that must
+        stay alive while the descriptor is in use; ``dev`` the subset the device reads (needs a shadow)."""
+        dev = dev if dev is not None else []
+        d = capi.DrawDesc()
+        d.structSize = C.sizeof(capi.DrawDesc)
+        d.topology = draw.topology
+        d.provokingVertexMode = 0
+        verts = np.ascontiguousarray(draw.vertices, dtype=np.float32)
+        keep.append(verts)
+        dev.append(verts)
+        stride = verts.shape[1] * 4
+        nverts = draw.vertex_count()
+        if draw.indices is not None:
+            idx = np.ascontiguousarray(draw.indices)
+            assert idx.dtype in (np.uint16, np.uint32)
+            keep.append(idx)
+            dev.append(idx)
+            d.indexType = idx.dtype.itemsize
+            d.indexBuffer = idx.ctypes.data + draw.first * idx.dtype.itemsize
+            d.baseVertex = draw.vertexOffset
+        else:
+            d.indexType = 0
+            d.indexBuffer = None
+            d.baseVertex = draw.first
+        if draw.topology == TOPO_TRIANGLE_LIST:
+            d.primitiveCount = nverts // 3
+        else:
+            d.primitiveCount = max(0, nverts - 2)
+        for (loc, comps, off) in draw.attribs:
+            vi = d.input[loc]
+            vi.buffer = verts.ctypes.data + off * 4
+            vi.robustnessSize = max(0, verts.nbytes - off * 4)
+            vi.vertexStride = stride
+            vi.format = FLOAT_FORMATS[comps]
+        vs, fs = spirv.shader(draw.vs), spirv.shader(draw.fs)
+        keep += [vs, fs]
+        d.vertexShader, d.vertexShaderWords = vs.ctypes.data, len(vs)
+        d.fragmentShader, d.fragmentShaderWords = fs.ctypes.data, len(fs)
+        vp = draw.viewport or (0.0, 0.0, float(self.width), float(self.height), 0.0, 1.0)
+        (d.viewportX, d.viewportY, d.viewportWidth, d.viewportHeight, d.viewportMinDepth, d.viewportMaxDepth) = vp
+        sc = draw.scissor or (0, 0, self.width, self.height)
+        d.scissor = capi.Rect(*sc)
+        d.renderArea = capi.Rect(*(render_area or (0, 0, self.width, self.height)))
+        d.cullMode, d.frontFace, d.depthClipEnable = draw.cullMode, draw.frontFace, 1
+        d.depthBiasConstant, d.depthBiasClamp, d.depthBiasSlope = draw.depthBias
+        d.sampleCount, d.sampleMask = self.samples, draw.sampleMask & ((1 << self.samples) - 1) if self.samples > 1 else 1
+        d.depthTestEnable, d.depthWriteEnable, d.depthCompareOp = int(draw.depthTest), int(draw.depthWrite), draw.depthCompareOp
+        d.stencilTestEnable = int(draw.stencilTest)
+        d.front = capi.StencilFace(*draw.front.tuple())
+        d.back = capi.StencilFace(*draw.back.tuple())
+        d.blendEnable = int(draw.blend)
+        d.srcColorBlendFactor, d.dstColorBlendFactor, d.colorBlendOp = draw.srcColor, draw.dstColor, draw.colorOp
+        d.srcAlphaBlendFactor, d.dstAlphaBlendFactor, d.alphaBlendOp = draw.srcAlpha, draw.dstAlpha, draw.alphaOp
+        d.colorWriteMask = draw.colorWriteMask
+        d.blendConstants = (C.c_float * 4)(*draw.blendConstants)
+        H2, W = self.padded_height(), self.width
+        col = att["color"]
+        d.color = capi.Attachment(col.ctypes.data, self.colorFormat, W * 4, H2 * W * 4, W, self.height, 0)
+        if "depth" in att:
+            d.depth = capi.Attachment(att["depth"].ctypes.data, FMT_D32_SFLOAT, W * 4, H2 * W * 4, W, self.height, 0)
+        if "stencil" in att:
+            d.stencil = capi.Attachment(att["stencil"].ctypes.data, FMT_S8_UINT, W, H2 * W, W, self.height, 0)
+        if draw.texture is not None:
+            t = draw.texture
+            packed = t.packed()
+            keep.append(packed)
+            dev.append(packed)
+            si = d.sampledImage[0]
+            si.set, si.binding, si.format, si.levelCount = t.set, t.binding, FMT_R8G8B8A8_UNORM, len(t.levels)
+            off = 0
+            for l in range(capi.MIPMAP_LEVELS):
+                ll = min(l, len(t.levels) - 1)
+                if l < len(t.levels):
+                    cur = off
+                    off += t.levels[l].shape[0] * t.levels[l].shape[1] * 4
+                    last = cur
+                h, w = t.levels[ll].shape[:2]
+                si.level[l] = capi.MipLevel(packed.ctypes.data + (cur if l < len(t.levels) else last), w, h, w, 0)
+            si.magFilter, si.minFilter, si.mipmapMode = t.magFilter, t.minFilter, t.mipmapMode
+            si.addressModeU, si.addressModeV = t.addressModeU, t.addressModeV
+            si.mipLodBias, si.minLod, si.maxLod = t.mipLodBias, t.minLod, t.maxLod
+            d.sampledImageCount = 1
+        return d
+
+    # ---- serialisation for oracle/refrender.cpp (oracle/scene_format.h) ----
+    def write_ref_scene(self, path: str) -> None:
+        blobs: list = []
+
+        def blob(a) -> int:
+            blobs.append(np.ascontiguousarray(a).view(np.uint8).reshape(-1))
+            return len(blobs) - 1
+
+        recs = []
+        for dr in self.draws:
+            verts = np.ascontiguousarray(dr.vertices, dtype=np.float32)
+            r = struct.pack("<IIIIi", dr.topology, 0 if dr.indices is None else dr.indices.dtype.itemsize,
+                            dr.vertex_count(), dr.first, dr.vertexOffset)
+            r += struct.pack("<IIII", blob(spirv.shader(dr.vs)), blob(spirv.shader(dr.fs)), blob(verts),
+                             blob(dr.indices) if dr.indices is not None else 0)
+            r += struct.pack("<II", verts.shape[1] * 4, len(dr.attribs))
+            for i in range(8):
+                if i < len(dr.attribs):
+                    loc, comps, off = dr.attribs[i]
+                    r += struct.pack("<III", loc, FLOAT_FORMATS[comps], off * 4)
+                else:
+                    r += struct.pack("<III", 0, 0, 0)
+            vp = dr.viewport or (0.0, 0.0, float(self.width), float(self.height), 0.0, 1.0)
+            sc = dr.scissor or (0, 0, self.width, self.height)
+            r += struct.pack("<6f4i", *vp, *sc)
+            r += struct.pack("<IIIIII", dr.cullMode, dr.frontFace, int(dr.depthTest), int(dr.depthWrite), dr.depthCompareOp,
+                             int(dr.stencilTest))
+            r += struct.pack("<7I7I", *dr.front.tuple(), *dr.back.tuple())
+            r += struct.pack("<Ifff", int(any(v != 0.0 for v in dr.depthBias)), *dr.depthBias)
+            r += struct.pack("<8I4fI", int(dr.blend), dr.srcColor, dr.dstColor, dr.colorOp, dr.srcAlpha, dr.dstAlpha, dr.alphaOp,
+                             dr.colorWriteMask, *dr.blendConstants, dr.sampleMask & 0xFFFFFFFF)
+            t = dr.texture
+            if t is not None:
+                r += struct.pack("<5I5I3f2I", 1, blob(t.packed()), t.levels[0].shape[1], t.levels[0].shape[0], len(t.levels),
+                                 t.magFilter, t.minFilter, t.mipmapMode, t.addressModeU, t.addressModeV,
+                                 t.mipLodBias, t.minLod, t.maxLod, t.set, t.binding)
+            else:
+                r += struct.pack("<5I5I3f2I", 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0, 0)
+            recs.append(r)
+        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 2, self.width, self.height, self.samples, self.colorFormat,
+                          int(self.hasDepth), int(self.hasStencil), *self.clearColor, self.clearDepth, self.clearStencil,
+                          len(recs), len(blobs))
+        off = len(hdr) + sum(len(r) for r in recs) + 16 * len(blobs)
+        table = b""
+        for b in blobs:
+            off = (off + 15) & ~15
+            table += struct.pack("<QQ", off, b.nbytes)
+            off += b.nbytes
+        with open(path, "wb") as f:
+            f.write(hdr)
+            for r in recs:
+                f.write(r)
+            f.write(table)
+            pos = len(hdr) + sum(len(r) for r in recs) + len(table)
+            for b in blobs:
+                pad = ((pos + 15) & ~15) - pos
+                f.write(b"\0" * pad)
+                pos += pad
+                f.write(b.tobytes())
+                pos += b.nbytes
+
+
+def resolve_host(color: np.ndarray) -> np.ndarray:
+    """Shape helper only (no pixel math): the 1x view of a 1-sample attachment."""
+    return color[0]
+
+
+class Device:
+    """One CUDA context of the C-ABI (``swcu_ctx``): the Python stand-in for the shim a maintainer would put in
+    ``DrawCall::run``.  Holds the device shadows of every host buffer it has seen."""
+
+    def __init__(self, ordinal: int = 0):
+        self.lib = capi.lib()
+        self.ctx = C.c_void_p()
+        rc = self.lib.swcu_create(C.byref(self.ctx), ordinal)
+        if rc != capi.OK:
+            raise capi.SwcuError(rc, (self.lib.swcu_last_error(None) or b"").decode())
+        self._registered: dict = {}
+
+    def close(self):
+        if self.ctx:
+            self.lib.swcu_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != capi.OK:
+            raise capi.SwcuError(rc, (self.lib.swcu_last_error(self.ctx) or b"").decode())
+
+    # memory
+    def register(self, arr: np.ndarray, upload: bool = True):
+        key = arr.ctypes.data
+        if key not in self._registered:
+            self.check(self.lib.swcu_mem_register(self.ctx, key, arr.nbytes))
+            self._registered[key] = arr
+        if upload:
+            self.check(self.lib.swcu_mem_upload(self.ctx, key, arr.nbytes))
+
+    def unregister(self, arr: np.ndarray):
+        key = arr.ctypes.data
+        if key in self._registered:
+            self.check(self.lib.swcu_mem_unregister(self.ctx, key))
+            del self._registered[key]
+
+    def download(self, arr: np.ndarray):
+        self.check(self.lib.swcu_mem_download(self.ctx, arr.ctypes.data, arr.nbytes))
+
+    def device_ptr(self, arr: np.ndarray) -> int:
+        return self.lib.swcu_mem_device_ptr(self.ctx, arr.ctypes.data) or 0
+
+    def sync(self):
+        self.check(self.lib.swcu_sync(self.ctx))
+
+    def draw(self, desc: capi.DrawDesc):
+        self.check(self.lib.swcu_draw(self.ctx, C.byref(desc)))
+
+    def set_option(self, name: str, value: int):
+        self.check(self.lib.swcu_set_option(self.ctx, name.encode(), value))
+
+    def stats(self) -> capi.Stats:
+        s = capi.Stats()
+        self.check(self.lib.swcu_get_stats(self.ctx, C.byref(s)))
+        return s
+
+    def resolve(self, scene: Scene, att: dict) -> np.ndarray:
+        """Blitter::fastResolve on the device shadows; returns the 1x image."""
+        H2, W = scene.padded_height(), scene.width
+        out = np.zeros((1, H2, W, 4), dtype=np.uint8)
+        self.register(out, upload=True)
+        src = capi.Attachment(att["color"].ctypes.data, scene.colorFormat, W * 4, H2 * W * 4, W, scene.height, 0)
+        dst = capi.Attachment(out.ctypes.data, scene.colorFormat, W * 4, H2 * W * 4, W, scene.height, 0)
+        self.check(self.lib.swcu_resolve(self.ctx, C.byref(src), scene.samples, C.byref(dst)))
+        self.download(out)
+        self.sync()
+        self.unregister(out)
+        return out[0]
+
+    def render(self, scene: Scene, att: Optional[dict] = None, render_area: Optional[tuple] = None) -> dict:
+        """Upload inputs, issue every draw of the scene through swcu_draw, read the attachments back."""
+        att = att if att is not None else scene.alloc_attachments()
+        keep: list = []
+        dev: list = []
+        descs = [scene.build_desc(dr, att, keep, render_area, dev) for dr in scene.draws]
+        bufs, seen = [], set()
+        for b in list(att.values()) + dev:
+            if b.ctypes.data not in seen:
+                seen.add(b.ctypes.data)
+                bufs.append(b)
+        for b in bufs:
+            self.register(b)
+        for d in descs:
+            self.draw(d)
+        for a in att.values():
+            self.download(a)
+        self.sync()
+        for b in bufs:
+            self.unregister(b)
+        return att
