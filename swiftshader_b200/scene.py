@@ -156,9 +156,10 @@ class Scene:
         return (self.height + 1) & ~1
 
     def clear_color_bytes(self) -> np.ndarray:
-        """UNORM8 pack of the clear colour as Blitter::clear does (round-to-nearest of c*255)."""
+        """UNORM8 pack of the clear colour as Blitter::fastClear does: (uint32_t)(255 * c + 0.5f)
+        (/root/reference/src/Device/Blitter.cpp:217-229)."""
         c = np.clip(np.array(self.clearColor, dtype=np.float32), 0, 1)
-        b = np.rint(c * np.float32(255.0)).astype(np.uint8)
+        b = (np.float32(255.0) * c + np.float32(0.5)).astype(np.float32).astype(np.uint32).astype(np.uint8)
         if self.colorFormat == FMT_B8G8R8A8_UNORM:
             b = b[[2, 1, 0, 3]]
         return b

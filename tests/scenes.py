@@ -1,0 +1,331 @@
+"""Seeded scene generators shared by the golden generator (tests/golden/gen_golden.py), the CPU tests
+(oracle vs reference goldens) and the GPU tests (CUDA vs oracle).  Every family is deterministic in its seed.
+
+The families follow SURVEY.md §8c ("which goldens"): sub-pixel coverage sweeps incl. clipped triangles, cull
+modes, the 8 depth compare ops, stencil op matrix, blend-factor matrix, sampler sweeps over filters / address
+modes / LODs, 4x MSAA coverage + resolve, index/topology variants, scissor / render-area, and the three
+VulkanBenchmarks triangles (tests/VulkanBenchmarks/TriangleBenchmarks.cpp:48-52,100-104,159-163).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from swiftshader_b200.scene import *  # noqa: F401,F403
+from swiftshader_b200.scene import Draw, Scene, StencilFace, Texture
+
+CELL = 64  # sub-viewport size
+
+
+def _tri_kind(rng, kind: int):
+    if kind == 0:
+        p = rng.uniform(-1.6, 1.6, (3, 2))  # big, crosses the frustum sides
+    elif kind == 1:
+        c = rng.uniform(-0.9, 0.9, 2)
+        p = c + rng.uniform(-0.08, 0.08, (3, 2))  # small
+    elif kind == 2:
+        p = np.round(rng.uniform(-1, 1, (3, 2)) * 32) / 32  # vertices exactly on pixel corners
+    elif kind == 3:
+        p = (np.round(rng.uniform(-1, 1, (3, 2)) * 32) + 0.5) / 32  # exactly on pixel centres
+    elif kind == 4:
+        c = rng.uniform(-0.9, 0.9, 2)
+        p = c + rng.uniform(-0.02, 0.02, (3, 2))  # tiny / sliver
+    else:
+        p = rng.uniform(-0.95, 0.95, (3, 2))  # medium, inside
+    return p
+
+
+def _verts(rng, p, persp: bool, colour=None, z=None):
+    """(3, 8) float32: clip-space vec4 position + vec4 attribute."""
+    w = rng.uniform(0.5, 2.0, 3) if persp else np.ones(3)
+    z = rng.uniform(0.1, 0.9, 3) if z is None else z
+    v = np.zeros((3, 8), dtype=np.float32)
+    v[:, 0] = (p[:, 0] * w).astype(np.float32)
+    v[:, 1] = (p[:, 1] * w).astype(np.float32)
+    v[:, 2] = (z * w).astype(np.float32)
+    v[:, 3] = w.astype(np.float32)
+    v[:, 4:8] = 1.0 if colour is None else colour
+    return v
+
+
+P4C4 = [(0, 4, 0), (1, 4, 4)]
+
+
+def _grid_scene(draw_fn, n=16, **scene_kw) -> Scene:
+    """n draws, each confined to its own CELL x CELL viewport+scissor of a square framebuffer."""
+    g = int(np.ceil(np.sqrt(n)))
+    draws = []
+    for i in range(n):
+        vx, vy = (i % g) * CELL, (i // g) * CELL
+        d = draw_fn(i)
+        d.viewport = (float(vx), float(vy), float(CELL), float(CELL), 0.0, 1.0)
+        d.scissor = (vx, vy, CELL, CELL)
+        draws.append(d)
+    return Scene(g * CELL, g * CELL, draws, **scene_kw)
+
+
+# ------------------------------------------------------------------ families ----
+def coverage(seed: int) -> Scene:
+    """16 white triangles of mixed kinds; 1/3 with perspective w. Pins R3+R4+R5+R6 coverage incl. the clipper."""
+    rng = np.random.default_rng(1000 + seed)
+
+    def mk(i):
+        p = _tri_kind(rng, (seed + i) % 5)
+        return Draw(_verts(rng, p, persp=(i % 3 == 0)), P4C4, "vs_pos4_col4", "fs_col4")
+
+    return _grid_scene(mk)
+
+
+def zclip(seed: int) -> Scene:
+    """Triangles crossing the near (z<0) and far (z>w) planes, with coloured varyings and depth."""
+    rng = np.random.default_rng(2000 + seed)
+
+    def mk(i):
+        p = _tri_kind(rng, 5 if i % 2 else 0)
+        z = rng.uniform(-0.6, 1.6, 3)
+        return Draw(_verts(rng, p, persp=(i % 2 == 0), colour=rng.uniform(0, 1, (3, 4)), z=z), P4C4, "vs_pos4_col4", "fs_col4",
+                    depthTest=True, depthWrite=True)
+
+    return _grid_scene(mk, hasDepth=True, clearDepth=1.0)
+
+
+def cull(seed: int) -> Scene:
+    rng = np.random.default_rng(3000 + seed)
+    mode = [CULL_NONE, CULL_FRONT, CULL_BACK, CULL_FRONT | CULL_BACK][seed % 4]
+    ff = [FRONT_CCW, FRONT_CW][(seed // 4) % 2]
+
+    def mk(i):
+        p = _tri_kind(rng, 5)
+        return Draw(_verts(rng, p, persp=(i % 4 == 0)), P4C4, "vs_pos4_col4", "fs_col4", cullMode=mode, frontFace=ff)
+
+    return _grid_scene(mk)
+
+
+def _layers(rng, n, persp=True, kinds=(5, 0, 1)):
+    """n random coloured triangles in ONE draw (tests in-order RMW within a draw)."""
+    vs = [_verts(rng, _tri_kind(rng, kinds[i % len(kinds)]), persp and i % 2 == 0, colour=rng.uniform(0, 1, (3, 4))) for i in range(n)]
+    return np.concatenate(vs, axis=0)
+
+
+def depth_ops(seed: int) -> Scene:
+    """Two draws of overlapping triangles; second uses compare op seed%8. Pins R7/R8 (+ interpolation R5vi/R6/R11)."""
+    rng = np.random.default_rng(4000 + seed)
+    op = seed % 8
+    d1 = Draw(_layers(rng, 6), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, depthCompareOp=CMP_LESS_OR_EQUAL)
+    d2 = Draw(_layers(rng, 6), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=(seed % 3 != 0), depthCompareOp=op)
+    return Scene(CELL, CELL, [d1, d2], hasDepth=True, clearDepth=0.6, clearColor=(0.1, 0.2, 0.3, 1.0))
+
+
+_BLEND_MATRIX = [
+    (BF_SRC_ALPHA, BF_ONE_MINUS_SRC_ALPHA, BOP_ADD, BF_ONE, BF_ZERO, BOP_ADD),
+    (BF_ONE, BF_ONE, BOP_ADD, BF_ONE, BF_ONE, BOP_ADD),
+    (BF_SRC_ALPHA, BF_ONE, BOP_ADD, BF_SRC_ALPHA, BF_ONE_MINUS_SRC_ALPHA, BOP_ADD),
+    (BF_DST_COLOR, BF_ZERO, BOP_ADD, BF_DST_ALPHA, BF_ZERO, BOP_ADD),
+    (BF_ONE_MINUS_DST_COLOR, BF_SRC_COLOR, BOP_ADD, BF_ONE_MINUS_DST_ALPHA, BF_SRC_ALPHA, BOP_ADD),
+    (BF_ONE, BF_ONE_MINUS_SRC_COLOR, BOP_ADD, BF_ONE, BF_ONE_MINUS_SRC_ALPHA, BOP_ADD),
+    (BF_SRC_ALPHA_SATURATE, BF_ONE, BOP_ADD, BF_SRC_ALPHA_SATURATE, BF_ONE, BOP_ADD),
+    (BF_CONSTANT_COLOR, BF_ONE_MINUS_CONSTANT_COLOR, BOP_ADD, BF_CONSTANT_ALPHA, BF_ONE_MINUS_CONSTANT_ALPHA, BOP_ADD),
+    (BF_SRC_ALPHA, BF_ONE_MINUS_SRC_ALPHA, BOP_SUBTRACT, BF_ONE, BF_ONE, BOP_SUBTRACT),
+    (BF_SRC_ALPHA, BF_ONE, BOP_REVERSE_SUBTRACT, BF_ONE, BF_ONE, BOP_REVERSE_SUBTRACT),
+    (BF_ONE, BF_ONE, BOP_MIN, BF_ONE, BF_ONE, BOP_MIN),
+    (BF_ZERO, BF_ZERO, BOP_MAX, BF_SRC_ALPHA, BF_DST_ALPHA, BOP_MAX),
+    (BF_ZERO, BF_ONE, BOP_ADD, BF_ONE, BF_ZERO, BOP_ADD),      # colour folds to DST, alpha to SRC
+    (BF_ONE, BF_ZERO, BOP_ADD, BF_ZERO, BF_ONE, BOP_ADD),      # colour folds to SRC, alpha to DST
+    (BF_ZERO, BF_ZERO, BOP_ADD, BF_ZERO, BF_ZERO, BOP_ADD),    # both fold to ZERO
+    (BF_ZERO, BF_ONE, BOP_ADD, BF_ZERO, BF_ONE, BOP_ADD),      # both DST: colour write disabled
+    (BF_ZERO, BF_SRC_COLOR, BOP_SUBTRACT, BF_ZERO, BF_ONE, BOP_REVERSE_SUBTRACT),
+    (BF_DST_ALPHA, BF_ONE_MINUS_DST_ALPHA, BOP_ADD, BF_ONE_MINUS_SRC_COLOR, BF_DST_COLOR, BOP_ADD),
+]
+
+
+def blend(seed: int) -> Scene:
+    """Blend-factor matrix on RGBA8 with overlapping triangles in one draw (R10/R11 + ordering)."""
+    rng = np.random.default_rng(5000 + seed)
+    (sc, dc, co, sa, da, ao) = _BLEND_MATRIX[seed % len(_BLEND_MATRIX)]
+    wm = 0xF if seed % 5 else 0x5
+    d = Draw(_layers(rng, 8), P4C4, "vs_pos4_col4", "fs_col4", blend=True, srcColor=sc, dstColor=dc, colorOp=co,
+             srcAlpha=sa, dstAlpha=da, alphaOp=ao, colorWriteMask=wm, blendConstants=(0.25, 0.5, 0.75, 0.4))
+    fmt = FMT_B8G8R8A8_UNORM if seed % 7 == 3 else FMT_R8G8B8A8_UNORM
+    return Scene(CELL, CELL, [d], clearColor=(0.3, 0.6, 0.2, 0.5), colorFormat=fmt)
+
+
+def stencil(seed: int) -> Scene:
+    """Stencil compare ops x ops, front/back by winding, masks; with and without depth test (R9)."""
+    rng = np.random.default_rng(6000 + seed)
+    ops = [SOP_KEEP, SOP_ZERO, SOP_REPLACE, SOP_INC_CLAMP, SOP_DEC_CLAMP, SOP_INVERT, SOP_INC_WRAP, SOP_DEC_WRAP]
+
+    def face(k):
+        return StencilFace(failOp=ops[(seed + k) % 8], passOp=ops[(seed * 3 + k + 1) % 8], depthFailOp=ops[(seed * 5 + k + 2) % 8],
+                           compareOp=(seed + 2 * k) % 8, compareMask=[0xFF, 0x0F, 0xF3][(seed + k) % 3],
+                           writeMask=[0xFF, 0xFF, 0x3C][(seed // 2 + k) % 3], reference=(37 * seed + 11 * k + 1) & 0xFF)
+
+    use_depth = seed % 2 == 0
+    # first draw lays down a stencil pattern (ALWAYS / INC_WRAP), second exercises the matrix
+    d1 = Draw(_layers(rng, 6, persp=False), P4C4, "vs_pos4_col4", "fs_col4", stencilTest=True,
+              front=StencilFace(passOp=SOP_INC_WRAP, compareOp=CMP_ALWAYS), back=StencilFace(passOp=SOP_DEC_WRAP, compareOp=CMP_ALWAYS),
+              depthTest=use_depth, depthWrite=use_depth)
+    d2 = Draw(_layers(rng, 8, persp=False), P4C4, "vs_pos4_col4", "fs_col4", stencilTest=True, front=face(0), back=face(1),
+              depthTest=use_depth, depthWrite=use_depth, depthCompareOp=CMP_LESS)
+    return Scene(CELL, CELL, [d1, d2], hasDepth=True, hasStencil=True, clearDepth=0.7, clearStencil=(seed * 29) & 0xFF)
+
+
+def _rand_tex(rng, w, h, levels):
+    out = []
+    for l in range(levels):
+        out.append(rng.integers(0, 256, (max(1, h >> l), max(1, w >> l), 4), dtype=np.uint8))
+    return out
+
+
+def texture(seed: int) -> Scene:
+    """Sampler sweep: uv in [-4,5], filters, mip modes, address modes, LOD bias, independent random mip levels (R14)."""
+    rng = np.random.default_rng(7000 + seed)
+    variants = [
+        dict(w=16, h=16, levels=1, maxLod=0.0),                                   # the benchmark's case
+        dict(w=64, h=32, levels=1, maxLod=0.0),
+        dict(w=64, h=64, levels=7, maxLod=6.0),                                   # trilinear, full chain
+        dict(w=64, h=64, levels=7, maxLod=6.0, mipmapMode=MIPMAP_NEAREST),
+        dict(w=32, h=64, levels=4, maxLod=3.0, mipLodBias=0.75),
+        dict(w=64, h=64, levels=7, maxLod=6.0, magFilter=FILTER_NEAREST, minFilter=FILTER_NEAREST),
+        dict(w=64, h=64, levels=7, maxLod=4.5, minLod=1.25),
+        dict(w=32, h=32, levels=6, maxLod=5.0, addressModeU=ADDR_CLAMP_TO_EDGE, addressModeV=ADDR_MIRRORED_REPEAT),
+        dict(w=32, h=32, levels=1, maxLod=0.0, addressModeU=ADDR_MIRRORED_REPEAT, addressModeV=ADDR_CLAMP_TO_EDGE),
+        dict(w=16, h=16, levels=1, maxLod=0.0, magFilter=FILTER_NEAREST, minFilter=FILTER_NEAREST, mipmapMode=MIPMAP_NEAREST),
+    ]
+    v = dict(variants[seed % len(variants)])
+    tex = Texture(_rand_tex(rng, v.pop("w"), v.pop("h"), v.pop("levels")), **v)
+    tris = []
+    for i in range(3):
+        p = _tri_kind(rng, [5, 0, 1][i])
+        uvscale = [1.0, 6.0, 30.0][(seed + i) % 3]  # magnified ... strongly minified
+        col = np.zeros((3, 4))
+        col[:, :2] = rng.uniform(-4, 5, (3, 2)) * (uvscale / 9.0)
+        tris.append(_verts(rng, p, persp=(i != 1), colour=col))
+    d = Draw(np.concatenate(tris), P4C4, "vs_pos4_col4", "fs_tex_col4", texture=tex)
+    return Scene(CELL, CELL, [d])
+
+
+def msaa(seed: int) -> Scene:
+    """4x MSAA: per-sample coverage (R5 iv), resolve; odd seeds add depth test + blending."""
+    rng = np.random.default_rng(8000 + seed)
+    if seed % 2 == 0:
+        def mk(i):
+            kind = (seed // 2 + i) % 5
+            p = _tri_kind(rng, kind)
+            if i % 4 == 3:
+                p = np.round(p * 32 * 8) / (32 * 8)  # vertices on the 1/8-pixel sample grid
+            return Draw(_verts(rng, p, persp=(i % 3 == 0)), P4C4, "vs_pos4_col4", "fs_col4")
+        return _grid_scene(mk, samples=4)
+    d = Draw(_layers(rng, 10), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, blend=True)
+    return Scene(CELL, CELL, [d], samples=4, hasDepth=True, clearDepth=1.0, clearColor=(0.2, 0.2, 0.2, 1.0))
+
+
+def topology(seed: int) -> Scene:
+    """Indexed (u16/u32) lists, strips and fans, firstIndex / vertexOffset (R2 setBatchIndices)."""
+    rng = np.random.default_rng(9000 + seed)
+    n = 24
+    pts = rng.uniform(-0.95, 0.95, (n, 2))
+    v = np.zeros((n, 8), dtype=np.float32)
+    v[:, 0:2] = pts
+    v[:, 2] = rng.uniform(0.1, 0.9, n)
+    v[:, 3] = 1.0
+    v[:, 4:8] = rng.uniform(0, 1, (n, 4))
+    kind = seed % 6
+    kw = {}
+    if kind == 0:
+        idx, topo = rng.integers(0, n, 30).astype(np.uint16), TOPO_TRIANGLE_LIST
+    elif kind == 1:
+        idx, topo = rng.integers(0, n - 4, 33).astype(np.uint32), TOPO_TRIANGLE_LIST
+        kw = dict(first=3, count=27, vertexOffset=4)
+    elif kind == 2:
+        idx, topo = None, TOPO_TRIANGLE_STRIP
+    elif kind == 3:
+        idx, topo = None, TOPO_TRIANGLE_FAN
+    elif kind == 4:
+        idx, topo = rng.integers(0, n, 12).astype(np.uint16), TOPO_TRIANGLE_STRIP
+    else:
+        idx, topo = None, TOPO_TRIANGLE_LIST
+        kw = dict(first=3, count=18)
+    # flat-ish fans/strips get culled differently: exercise cull with strips' alternating winding
+    d = Draw(v, P4C4, "vs_pos4_col4", "fs_col4", indices=idx, topology=topo, cullMode=[CULL_NONE, CULL_BACK][seed % 2],
+             depthTest=True, depthWrite=True, **kw)
+    return Scene(CELL, CELL, [d], hasDepth=True)
+
+
+def scissor(seed: int) -> Scene:
+    """Scissor smaller than the viewport, viewport offset/non-square, depth range != [0,1], depth bias."""
+    rng = np.random.default_rng(10000 + seed)
+    W, H = 96, 80
+    vp = [(0.0, 0.0, 96.0, 80.0, 0.0, 1.0), (8.0, 4.0, 70.0, 60.0, 0.2, 0.9), (-10.0, -6.0, 120.0, 100.0, 0.0, 1.0), (5.5, 3.25, 64.5, 48.75, 1.0, 0.0)][seed % 4]
+    sc = [(10, 7, 50, 41), (0, 0, 96, 80), (33, 20, 17, 55), (1, 1, 94, 78)][(seed // 2) % 4]
+    bias = [(0.0, 0.0, 0.0), (2.0, 0.0, 1.5), (-3.0, -1e-6, 0.0), (4.0, 1e-7, 2.0)][seed % 4]
+    d1 = Draw(_layers(rng, 8), P4C4, "vs_pos4_col4", "fs_col4", viewport=vp, scissor=sc, depthTest=True, depthWrite=True, depthBias=bias,
+              depthCompareOp=CMP_LESS if vp[4] <= vp[5] else CMP_GREATER)
+    return Scene(W, H, [d1], hasDepth=True, clearDepth=1.0 if vp[4] <= vp[5] else 0.0)
+
+
+def _checker16():
+    """The benchmark's 16x16 checkerboard (TriangleBenchmarks.cpp:219-241)."""
+    rgb = [0xFFFF0000, 0xFF00FF00, 0xFF0000FF]
+    data = np.zeros(256, dtype=np.uint32)
+    k = 0
+    for i in range(16):
+        for j in range(16):
+            if ((i ^ j) & 1) == 0:
+                data[i + 16 * j] = rgb[k % 3]
+                k += 1
+    return data.view(np.uint8).reshape(16, 16, 4)
+
+
+def benchmark(which: int, width=1280, height=720, samples=1) -> Scene:
+    """The three VulkanBenchmarks triangles. Defaults mirror the reference harness (1280x720 swapchain,
+    tests/VulkanWrapper/DrawTester.hpp:135; clear (0.5,0.5,0.5,1), DrawTester.cpp:325-406; no depth attachment)."""
+    clear = (0.5, 0.5, 0.5, 1.0)
+    if which == 0:  # TriangleSolidColor
+        v = np.array([[1, 1, .5], [-1, 1, .5], [0, -1, .5]], dtype=np.float32)
+        d = Draw(v, [(0, 3, 0)], "vs_pos3", "fs_white")
+    elif which == 1:  # TriangleInterpolateColor
+        v = np.array([[1, 1, .05, 1, 0, 0], [-1, 1, .5, 0, 1, 0], [0, -1, .5, 0, 0, 1]], dtype=np.float32)
+        d = Draw(v, [(0, 3, 0), (1, 3, 3)], "vs_pos3_col3", "fs_col3")
+    else:  # TriangleSampleTexture
+        v = np.array([[1, 1, .5, 1, 0], [-1, 1, .5, 0, 1], [0, -1, .5, 0, 0]], dtype=np.float32)
+        d = Draw(v, [(0, 3, 0), (1, 2, 3)], "vs_pos3_uv2", "fs_tex_uv2", texture=Texture([_checker16()], maxLod=0.0))
+    return Scene(width, height, [d], samples=samples, clearColor=clear)
+
+
+FAMILIES = {
+    # name: (generator, number of seeds)
+    "coverage": (coverage, 40),
+    "zclip": (zclip, 6),
+    "cull": (cull, 8),
+    "depth_ops": (depth_ops, 16),
+    "blend": (blend, 36),
+    "stencil": (stencil, 24),
+    "texture": (texture, 30),
+    "msaa": (msaa, 16),
+    "topology": (topology, 12),
+    "scissor": (scissor, 8),
+}
+
+
+def all_cases():
+    for fam, (gen, n) in FAMILIES.items():
+        for s in range(n):
+            yield f"{fam}_{s}", gen(s)
+    for w in range(3):
+        yield f"benchmark_{w}_720p", benchmark(w)
+    yield "benchmark_0_720p_msaa", benchmark(0, samples=4)
+    yield "benchmark_2_720p_msaa", benchmark(2, samples=4)
+
+
+def outputs(scene: Scene, att: dict, resolved=None) -> dict:
+    """Canonical output arrays for comparison with the reference: unpadded colour (resolved if MSAA), depth, stencil."""
+    H = scene.height
+    out = {}
+    if scene.samples > 1:
+        out["color"] = np.ascontiguousarray(resolved[:H])
+    else:
+        out["color"] = np.ascontiguousarray(att["color"][0, :H])
+        if "depth" in att:
+            out["depth"] = np.ascontiguousarray(att["depth"][0, :H])
+        if "stencil" in att:
+            out["stencil"] = np.ascontiguousarray(att["stencil"][0, :H])
+    return out
