@@ -1,0 +1,786 @@
+// draw.cu — host side of the C-ABI in include/swcu.h: the context (device shadows of host memory, work buffers,
+// stream), the state gathering of sw::Renderer::draw (reference: src/Device/Renderer.cpp:183-490) and the kernel
+// sequence that replaces DrawCall::run (Renderer.cpp:551-662).  No torch types, no CPU rendering fallback.
+#include "kernels.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_lastError;
+
+struct DevBuf
+{
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+struct Shadow
+{
+	uintptr_t host = 0;
+	size_t bytes = 0;
+	unsigned char *dev = nullptr;
+	bool pinned = false;
+};
+
+struct KernelTime
+{
+	const char *name;
+	cudaEvent_t e0, e1;
+};
+
+struct swcu_ctx
+{
+	int device = 0;
+	cudaStream_t stream = nullptr, ownStream = nullptr;
+	std::map<uintptr_t, Shadow> mem;
+	std::string err;
+	DevBuf triRecords, spans, bigList, tileCount, pairOffset, keys, vals, keys2, vals2, tileBegin, tileEnd, cubTemp, counters;
+	DrawCounters *hostCounters = nullptr; // pinned
+	swcu_stats stats{};
+	cudaEvent_t t0 = nullptr, t1 = nullptr;
+	std::map<uint64_t, swcu_shader_info> shaderCache;
+	int optForceBinned = 0, optDirectMax = 64, optPinHost = 1;
+	int profiling = 0;
+	std::vector<KernelTime> lastKernels;
+	std::vector<cudaEvent_t> eventPool;
+	size_t eventsUsed = 0;
+};
+
+static int fail(swcu_ctx *ctx, int code, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	if(ctx) ctx->err = buf;
+	g_lastError = buf;
+	return code;
+}
+
+#define CU(call)                                                                                              \
+	do {                                                                                                      \
+		cudaError_t _e = (call);                                                                              \
+		if(_e != cudaSuccess) return fail(ctx, SWCU_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+	} while(0)
+
+static int ensure(swcu_ctx *ctx, DevBuf &b, size_t bytes)
+{
+	if(bytes <= b.cap) return SWCU_OK;
+	size_t want = std::max(bytes, b.cap + b.cap / 2);
+	want = (want + 255) & ~(size_t)255;
+	if(b.p)
+	{
+		CU(cudaStreamSynchronize(ctx->stream)); // earlier launches may still read the old block
+		CU(cudaFree(b.p));
+		b.p = nullptr;
+		b.cap = 0;
+	}
+	cudaError_t e = cudaMalloc(&b.p, want);
+	if(e != cudaSuccess) { cudaGetLastError(); return fail(ctx, SWCU_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+	b.cap = want;
+	return SWCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int swcu_create(swcu_ctx **out, int device_ordinal)
+{
+	if(!out) return fail(nullptr, SWCU_E_INVALID, "swcu_create: null out");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if(e != cudaSuccess || count == 0)
+	{
+		cudaGetLastError();
+		return fail(nullptr, SWCU_E_CUDA, "no CUDA device available (%s); the draw path has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count 0");
+	}
+	if(device_ordinal < 0 || device_ordinal >= count) return fail(nullptr, SWCU_E_INVALID, "device ordinal %d out of range (0..%d)", device_ordinal, count - 1);
+	swcu_ctx *ctx = new swcu_ctx();
+	ctx->device = device_ordinal;
+	auto bail = [&](const char *what, cudaError_t err) {
+		int rc = fail(nullptr, SWCU_E_CUDA, "%s: %s", what, cudaGetErrorString(err));
+		delete ctx;
+		return rc;
+	};
+	if((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
+	if((e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+	ctx->stream = ctx->ownStream;
+	if((e = cudaEventCreate(&ctx->t0)) != cudaSuccess) return bail("cudaEventCreate", e);
+	if((e = cudaEventCreate(&ctx->t1)) != cudaSuccess) return bail("cudaEventCreate", e);
+	if((e = cudaMallocHost((void **)&ctx->hostCounters, sizeof(DrawCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
+	*out = ctx;
+	return SWCU_OK;
+}
+
+extern "C" void swcu_destroy(swcu_ctx *ctx)
+{
+	if(!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for(auto &kv : ctx->mem)
+	{
+		if(kv.second.pinned) cudaHostUnregister((void *)kv.second.host);
+		cudaFree(kv.second.dev);
+	}
+	DevBuf *bufs[] = { &ctx->triRecords, &ctx->spans, &ctx->bigList, &ctx->tileCount, &ctx->pairOffset, &ctx->keys, &ctx->vals,
+		               &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->counters };
+	for(DevBuf *b : bufs) cudaFree(b->p);
+	for(cudaEvent_t ev : ctx->eventPool) cudaEventDestroy(ev);
+	if(ctx->hostCounters) cudaFreeHost(ctx->hostCounters);
+	if(ctx->t0) cudaEventDestroy(ctx->t0);
+	if(ctx->t1) cudaEventDestroy(ctx->t1);
+	if(ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
+	cudaGetLastError();
+	delete ctx;
+}
+
+extern "C" const char *swcu_last_error(swcu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_lastError.c_str(); }
+extern "C" const char *swcu_version(void) { return "swcuda 0.1 (sm_100a draw path: setup / spans / tile binning / tile raster)"; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// memory shadows
+// ------------------------------------------------------------------------------------------------------------------
+static Shadow *find_shadow(swcu_ctx *ctx, const void *p, size_t bytes)
+{
+	const uintptr_t a = (uintptr_t)p;
+	auto it = ctx->mem.upper_bound(a);
+	if(it == ctx->mem.begin()) return nullptr;
+	--it;
+	Shadow &s = it->second;
+	if(a < s.host || a + bytes > s.host + s.bytes) return nullptr;
+	return &s;
+}
+
+static unsigned char *dev_ptr(swcu_ctx *ctx, const void *p, size_t bytes = 1)
+{
+	Shadow *s = find_shadow(ctx, p, bytes);
+	return s ? s->dev + ((uintptr_t)p - s->host) : nullptr;
+}
+
+extern "C" int swcu_mem_register(swcu_ctx *ctx, const void *host_base, size_t bytes)
+{
+	if(!ctx || !host_base || !bytes) return fail(ctx, SWCU_E_INVALID, "swcu_mem_register: bad arguments");
+	CU(cudaSetDevice(ctx->device));
+	const uintptr_t a = (uintptr_t)host_base;
+	auto it = ctx->mem.upper_bound(a + bytes - 1);
+	if(it != ctx->mem.begin())
+	{
+		--it;
+		if(it->second.host + it->second.bytes > a) return fail(ctx, SWCU_E_INVALID, "swcu_mem_register: range overlaps a registered range");
+	}
+	Shadow s;
+	s.host = a;
+	s.bytes = bytes;
+	cudaError_t e = cudaMalloc((void **)&s.dev, (bytes + 255) & ~(size_t)255);
+	if(e != cudaSuccess) { cudaGetLastError(); return fail(ctx, SWCU_E_NOMEM, "cudaMalloc(%zu) for a shadow failed: %s", bytes, cudaGetErrorString(e)); }
+	if(ctx->optPinHost)
+	{
+		// page-lock the host range so uploads/downloads are true async DMA; best effort (fails on read-only mappings)
+		e = cudaHostRegister((void *)host_base, bytes, cudaHostRegisterDefault);
+		if(e == cudaSuccess) s.pinned = true; else cudaGetLastError();
+	}
+	ctx->mem[a] = s;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_mem_unregister(swcu_ctx *ctx, const void *host_base)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	auto it = ctx->mem.find((uintptr_t)host_base);
+	if(it == ctx->mem.end()) return fail(ctx, SWCU_E_INVALID, "swcu_mem_unregister: %p is not a registered base", host_base);
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	if(it->second.pinned) cudaHostUnregister((void *)it->second.host);
+	cudaFree(it->second.dev);
+	ctx->mem.erase(it);
+	return SWCU_OK;
+}
+
+extern "C" int swcu_mem_upload(swcu_ctx *ctx, const void *host_ptr, size_t bytes)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	unsigned char *d = dev_ptr(ctx, host_ptr, bytes);
+	if(!d) return fail(ctx, SWCU_E_INVALID, "swcu_mem_upload: [%p,+%zu) is not inside a registered range", host_ptr, bytes);
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaMemcpyAsync(d, host_ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->stats.h2dBytes += bytes;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_mem_download(swcu_ctx *ctx, void *host_ptr, size_t bytes)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	unsigned char *d = dev_ptr(ctx, host_ptr, bytes);
+	if(!d) return fail(ctx, SWCU_E_INVALID, "swcu_mem_download: [%p,+%zu) is not inside a registered range", host_ptr, bytes);
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaMemcpyAsync(host_ptr, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	ctx->stats.d2hBytes += bytes;
+	return SWCU_OK;
+}
+
+extern "C" void *swcu_mem_device_ptr(swcu_ctx *ctx, const void *host_ptr) { return ctx ? dev_ptr(ctx, host_ptr) : nullptr; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// plumbing
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int swcu_sync(swcu_ctx *ctx)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	return SWCU_OK;
+}
+
+extern "C" int swcu_set_stream(swcu_ctx *ctx, void *cuda_stream)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->ownStream;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_timer_begin(swcu_ctx *ctx)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaEventRecord(ctx->t0, ctx->stream));
+	return SWCU_OK;
+}
+
+extern "C" int swcu_timer_end(swcu_ctx *ctx, float *elapsed_ms)
+{
+	if(!ctx || !elapsed_ms) return SWCU_E_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaEventRecord(ctx->t1, ctx->stream));
+	CU(cudaEventSynchronize(ctx->t1));
+	CU(cudaEventElapsedTime(elapsed_ms, ctx->t0, ctx->t1));
+	return SWCU_OK;
+}
+
+extern "C" int swcu_get_stats(swcu_ctx *ctx, swcu_stats *out)
+{
+	if(!ctx || !out) return SWCU_E_INVALID;
+	*out = ctx->stats;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_reset_stats(swcu_ctx *ctx)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	ctx->stats = swcu_stats{};
+	return SWCU_OK;
+}
+
+extern "C" int swcu_set_profiling(swcu_ctx *ctx, int enable)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	ctx->profiling = enable;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_last_draw_kernels(swcu_ctx *ctx, const char **names, float *ms, int n)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	int k = 0;
+	for(const KernelTime &t : ctx->lastKernels)
+	{
+		if(k >= n) break;
+		float v = 0;
+		cudaEventElapsedTime(&v, t.e0, t.e1);
+		names[k] = t.name;
+		ms[k] = v;
+		k++;
+	}
+	return k;
+}
+
+extern "C" int swcu_set_option(swcu_ctx *ctx, const char *name, int value)
+{
+	if(!ctx || !name) return SWCU_E_INVALID;
+	if(!strcmp(name, "force_binned")) ctx->optForceBinned = value;
+	else if(!strcmp(name, "direct_max")) ctx->optDirectMax = value;
+	else if(!strcmp(name, "pin_host")) ctx->optPinHost = value;
+	else return fail(ctx, SWCU_E_INVALID, "unknown option '%s'", name);
+	return SWCU_OK;
+}
+
+// kernel launch bookkeeping: counts OUR kernels and, when profiling, brackets each with events
+struct LaunchScope
+{
+	swcu_ctx *ctx;
+	KernelTime kt{};
+	bool timed = false;
+	LaunchScope(swcu_ctx *c, const char *name) : ctx(c)
+	{
+		ctx->stats.kernelLaunches++;
+		if(ctx->profiling)
+		{
+			auto get = [&]() {
+				if(ctx->eventsUsed == ctx->eventPool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->eventPool.push_back(e); }
+				return ctx->eventPool[ctx->eventsUsed++];
+			};
+			kt.name = name; kt.e0 = get(); kt.e1 = get();
+			cudaEventRecord(kt.e0, ctx->stream);
+			timed = true;
+		}
+	}
+	~LaunchScope()
+	{
+		if(timed) { cudaEventRecord(kt.e1, ctx->stream); ctx->lastKernels.push_back(kt); }
+	}
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// state gathering (Renderer::draw) and the kernel sequence (DrawCall::run)
+// ------------------------------------------------------------------------------------------------------------------
+static uint64_t fnv1a(const uint32_t *w, uint32_t n)
+{
+	uint64_t h = 1469598103934665603ull;
+	for(uint32_t i = 0; i < n; i++) { h ^= w[i]; h *= 1099511628211ull; }
+	return h ^ n;
+}
+
+static int get_shader(swcu_ctx *ctx, const uint32_t *code, uint32_t words, uint32_t stage, swcu_shader_info *out)
+{
+	if(!code || !words) return fail(ctx, SWCU_E_INVALID, "missing %s shader", stage ? "fragment" : "vertex");
+	const uint64_t key = fnv1a(code, words);
+	auto it = ctx->shaderCache.find(key);
+	if(it == ctx->shaderCache.end())
+	{
+		swcu_shader_info info;
+		char err[256];
+		int rc = swcu_shader_translate(code, words, &info, err, sizeof(err));
+		if(rc != SWCU_OK) return fail(ctx, rc, "%s shader rejected by the SPIR-V subset translator: %s", stage ? "fragment" : "vertex", err);
+		it = ctx->shaderCache.emplace(key, info).first;
+	}
+	*out = it->second;
+	if(out->stage != stage) return fail(ctx, SWCU_E_INVALID, "shader stage mismatch (expected %u, module is %u)", stage, out->stage);
+	return SWCU_OK;
+}
+
+// Context.cpp:1165-1270 (operation folding) and :1272-1300 (factor folding) for UNORM targets
+static int fold_blend_op(int op, int sf, int df)
+{
+	switch(op)
+	{
+	case BOP_ADD:
+		if(sf == BF_ZERO) { if(df == BF_ZERO) return BOP_ZERO_EXT; if(df == BF_ONE) return BOP_DST_EXT; }
+		else if(sf == BF_ONE) { if(df == BF_ZERO) return BOP_SRC_EXT; }
+		break;
+	case BOP_SUBTRACT:
+		if(sf == BF_ZERO) return BOP_ZERO_EXT;
+		else if(sf == BF_ONE) { if(df == BF_ZERO) return BOP_SRC_EXT; }
+		break;
+	case BOP_REVERSE_SUBTRACT:
+		if(sf == BF_ZERO) { if(df == BF_ZERO) return BOP_ZERO_EXT; if(df == BF_ONE) return BOP_DST_EXT; }
+		else { if(df == BF_ZERO) return BOP_ZERO_EXT; }
+		break;
+	}
+	return op;
+}
+static int fold_blend_factor(int op, int f) { return (op == BOP_MIN || op == BOP_MAX) ? BF_ONE : f; }
+static int kop(int op)
+{
+	switch(op)
+	{
+	case BOP_ADD: return KOP_ADD;
+	case BOP_SUBTRACT: return KOP_SUB;
+	case BOP_REVERSE_SUBTRACT: return KOP_RSUB;
+	case BOP_MIN: return KOP_MIN;
+	case BOP_MAX: return KOP_MAX;
+	case BOP_SRC_EXT: return KOP_SRC;
+	case BOP_DST_EXT: return KOP_DST;
+	case BOP_ZERO_EXT: return KOP_ZERO;
+	}
+	return -1;
+}
+
+static int clampi_h(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); } // NaN -> 1 like min(max()) chain is irrelevant here
+
+static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
+{
+	memset(&d, 0, sizeof(d));
+	if(desc->structSize != sizeof(swcu_draw_desc)) return fail(ctx, SWCU_E_INVALID, "swcu_draw_desc.structSize %u != %zu", desc->structSize, sizeof(swcu_draw_desc));
+	if(desc->topology != TOPO_TRIANGLE_LIST && desc->topology != TOPO_TRIANGLE_STRIP && desc->topology != TOPO_TRIANGLE_FAN)
+		return fail(ctx, SWCU_E_UNSUPPORTED, "topology %u outside the subset (triangle list/strip/fan)", desc->topology);
+	if(desc->sampleCount != 1 && desc->sampleCount != 4) return fail(ctx, SWCU_E_UNSUPPORTED, "sample count %u unsupported (1 or 4)", desc->sampleCount);
+	if(desc->indexType != 0 && desc->indexType != 2 && desc->indexType != 4) return fail(ctx, SWCU_E_UNSUPPORTED, "index type %u unsupported", desc->indexType);
+	if(desc->provokingVertexMode > 1) return fail(ctx, SWCU_E_INVALID, "bad provoking vertex mode");
+	if(desc->color.buffer && desc->color.format != VKF_R8G8B8A8_UNORM && desc->color.format != VKF_B8G8R8A8_UNORM)
+		return fail(ctx, SWCU_E_UNSUPPORTED, "colour format %u unsupported (R8G8B8A8_UNORM, B8G8R8A8_UNORM)", desc->color.format);
+	if(desc->depth.buffer && desc->depth.format != VKF_D32_SFLOAT) return fail(ctx, SWCU_E_UNSUPPORTED, "depth format %u unsupported (D32_SFLOAT)", desc->depth.format);
+	if(desc->stencil.buffer && desc->stencil.format != VKF_S8_UINT) return fail(ctx, SWCU_E_UNSUPPORTED, "stencil format %u unsupported (S8_UINT)", desc->stencil.format);
+	if(!desc->color.buffer && !desc->depth.buffer && !desc->stencil.buffer) return fail(ctx, SWCU_E_INVALID, "draw without attachments");
+
+	swcu_shader_info vs, fs;
+	int rc = get_shader(ctx, desc->vertexShader, desc->vertexShaderWords, 0, &vs);
+	if(rc) return rc;
+	rc = get_shader(ctx, desc->fragmentShader, desc->fragmentShaderWords, 4, &fs);
+	if(rc) return rc;
+
+	{ // Renderer.cpp:300-331
+		const float W = 0.5f * desc->viewportWidth, H = 0.5f * desc->viewportHeight;
+		const float X0 = desc->viewportX + W, Y0 = desc->viewportY + H;
+		d.WxF = W * 256.0f; d.HxF = H * 256.0f;
+		volatile float x0f = X0 * 256.0f, y0f = Y0 * 256.0f; // no contraction into an FMA
+		d.X0xF = x0f - 128.0f; d.Y0xF = y0f - 128.0f;
+		d.depthRange = desc->viewportMaxDepth - desc->viewportMinDepth;
+		d.depthNear = desc->viewportMinDepth;
+	}
+	{ // Renderer.cpp:333-345
+		const int x0 = desc->renderArea.x, y0 = desc->renderArea.y;
+		const int x1 = x0 + (int)desc->renderArea.width, y1 = y0 + (int)desc->renderArea.height;
+		d.scX0 = clampi_h(desc->scissor.x, x0, x1);
+		d.scX1 = clampi_h(desc->scissor.x + (int)desc->scissor.width, x0, x1);
+		d.scY0 = clampi_h(desc->scissor.y, y0, y1);
+		d.scY1 = clampi_h(desc->scissor.y + (int)desc->scissor.height, y0, y1);
+	}
+	d.ms = (int)desc->sampleCount;
+	d.sampleMask = d.ms > 1 ? (desc->sampleMask & 0xF) : 1u;
+
+	// ---- input assembly ----
+	d.indexType = desc->indexType;
+	d.topology = desc->topology;
+	d.provokingFirst = desc->provokingVertexMode == 0;
+	d.primCount = desc->primitiveCount;
+	d.baseVertex = desc->baseVertex;
+	if(desc->indexType)
+	{
+		d.indexBuffer = dev_ptr(ctx, desc->indexBuffer);
+		if(!d.indexBuffer) return fail(ctx, SWCU_E_INVALID, "index buffer %p is not inside a registered range", desc->indexBuffer);
+	}
+	d.vsInputMask = 0;
+	for(int l = 0; l < SWCU_MAX_INPUTS; l++)
+	{
+		if(!(vs.inputMask & (0xFu << (4 * l)))) continue;
+		const swcu_vertex_input &in = desc->input[l];
+		KVertexInput &k = d.input[l];
+		switch(in.format)
+		{
+		case VKF_R32_SFLOAT: k.ncomp = 1; break;
+		case VKF_R32G32_SFLOAT: k.ncomp = 2; break;
+		case VKF_R32G32B32_SFLOAT: k.ncomp = 3; break;
+		case VKF_R32G32B32A32_SFLOAT: k.ncomp = 4; break;
+		case VKF_UNDEFINED: k.ncomp = 0; break;
+		default: return fail(ctx, SWCU_E_UNSUPPORTED, "vertex input %d: format %u unsupported (R32..R32G32B32A32_SFLOAT)", l, in.format);
+		}
+		if(k.ncomp)
+		{
+			k.buffer = dev_ptr(ctx, in.buffer);
+			if(!k.buffer) return fail(ctx, SWCU_E_INVALID, "vertex input %d: buffer %p is not inside a registered range", l, in.buffer);
+			k.robustnessSize = in.robustnessSize;
+			k.stride = in.vertexStride;
+		}
+		d.vsInputMask |= 1u << l;
+	}
+
+	// ---- shader routing ----
+	auto kopd = [](const swcu_shader_operand &o) { KOperand k; k.kind = o.kind == SWCU_SRC_CONST ? OPK_CONST : (o.kind == SWCU_SRC_INPUT ? OPK_INPUT : OPK_TEXEL); k.value = o.value; return k; };
+	for(int k = 0; k < 4; k++) d.vsPos[k] = kopd(vs.position[k]);
+	int packed[SWCU_MAX_VARYING_COMPONENTS];
+	d.nvar = 0;
+	for(int c = 0; c < SWCU_MAX_VARYING_COMPONENTS; c++)
+	{
+		packed[c] = -1;
+		if(!((fs.inputMask >> c) & 1)) continue;
+		if(d.nvar >= SWCU_MAXV) return fail(ctx, SWCU_E_UNSUPPORTED, "fragment shader reads more than %d interpolated components", SWCU_MAXV);
+		packed[c] = d.nvar;
+		if((vs.outputMask >> c) & 1) d.varSrc[d.nvar] = kopd(vs.output[c]);
+		else { d.varSrc[d.nvar].kind = OPK_CONST; d.varSrc[d.nvar].value = 0; }
+		if((fs.flatMask >> c) & 1) d.flatMask |= 1u << d.nvar;
+		if((fs.noPerspectiveMask >> c) & 1) d.noPerspMask |= 1u << d.nvar;
+		d.nvar++;
+	}
+	auto fsop = [&](const swcu_shader_operand &o) { KOperand k = kopd(o); if(k.kind == OPK_INPUT) k.value = (uint32_t)packed[o.value]; return k; };
+	for(int ch = 0; ch < 4; ch++)
+	{
+		if((fs.outputMask >> ch) & 1) d.fsOut[ch] = fsop(fs.output[ch]);
+		else { d.fsOut[ch].kind = OPK_CONST; d.fsOut[ch].value = 0; }
+	}
+	d.usesTexture = fs.usesTexture;
+	if(fs.usesTexture)
+	{
+		d.texCoord[0] = fsop(fs.texCoord[0]);
+		d.texCoord[1] = fsop(fs.texCoord[1]);
+		const swcu_sampled_image *t = nullptr;
+		for(uint32_t s = 0; s < desc->sampledImageCount && s < SWCU_MAX_SAMPLED_IMAGES; s++)
+			if(desc->sampledImage[s].set == fs.textureSet && desc->sampledImage[s].binding == fs.textureBinding) t = &desc->sampledImage[s];
+		if(!t) return fail(ctx, SWCU_E_INVALID, "no sampled image bound at set %u binding %u", fs.textureSet, fs.textureBinding);
+		if(t->format != VKF_R8G8B8A8_UNORM) return fail(ctx, SWCU_E_UNSUPPORTED, "sampled image format %u unsupported (R8G8B8A8_UNORM)", t->format);
+		if(t->anisotropyEnable || t->compareEnable || t->unnormalizedCoordinates) return fail(ctx, SWCU_E_UNSUPPORTED, "sampler state outside the subset (anisotropy / compare / unnormalized)");
+		if(t->addressModeU > ADDR_CLAMP_TO_EDGE || t->addressModeV > ADDR_CLAMP_TO_EDGE) return fail(ctx, SWCU_E_UNSUPPORTED, "sampler address mode outside the subset (REPEAT, MIRRORED_REPEAT, CLAMP_TO_EDGE)");
+		if(t->magFilter > FILTER_LINEAR || t->minFilter > FILTER_LINEAR || t->mipmapMode > MIPMAP_MODE_LINEAR) return fail(ctx, SWCU_E_UNSUPPORTED, "sampler filter outside the subset");
+		if(t->levelCount < 1 || t->levelCount > SWCU_MIPMAP_LEVELS) return fail(ctx, SWCU_E_INVALID, "bad mip level count %u", t->levelCount);
+		d.texLevels = t->levelCount;
+		for(int l = 0; l < SWCU_MIPMAP_LEVELS; l++)
+		{
+			const swcu_mip_level &m = t->level[std::min<int>(l, (int)t->levelCount - 1)];
+			if(m.width == 0 || m.height == 0 || m.width > 32768 || m.height > 32768) return fail(ctx, SWCU_E_INVALID, "bad mip level %d extent", l);
+			d.mip[l].buffer = dev_ptr(ctx, m.buffer, (size_t)m.pitchP * (m.height - 1) * 4 + (size_t)m.width * 4);
+			if(!d.mip[l].buffer) return fail(ctx, SWCU_E_INVALID, "mip level %d buffer %p is not inside a registered range", l, m.buffer);
+			d.mip[l].width = m.width; d.mip[l].height = m.height; d.mip[l].pitchP = m.pitchP;
+		}
+		d.magFilter = t->magFilter; d.minFilter = t->minFilter; d.mipmapMode = t->mipmapMode;
+		d.addressU = t->addressModeU; d.addressV = t->addressModeV;
+		d.mipLodBias = t->mipLodBias; d.minLod = t->minLod; d.maxLod = t->maxLod;
+	}
+
+	// ---- setup state ----
+	d.cullMode = desc->cullMode; d.frontFace = desc->frontFace; d.depthClipEnable = desc->depthClipEnable;
+	d.depthBiasConstant = desc->depthBiasConstant; d.depthBiasSlope = desc->depthBiasSlope; d.depthBiasClamp = desc->depthBiasClamp;
+	d.depthBiasEnable = desc->depthBiasConstant != 0.0f || desc->depthBiasSlope != 0.0f;
+
+	// ---- pixel state ----
+	d.depthTestActive = desc->depthTestEnable && desc->depth.buffer;
+	d.depthWriteEnable = d.depthTestActive && desc->depthWriteEnable;
+	if(desc->depthCompareOp > CMP_ALWAYS) return fail(ctx, SWCU_E_INVALID, "bad depth compare op");
+	d.depthCompareOp = desc->depthCompareOp;
+	d.stencilActive = desc->stencilTestEnable && desc->stencil.buffer;
+	auto face = [](const swcu_stencil_face &s) { KStencilFace k; k.failOp = s.failOp; k.passOp = s.passOp; k.depthFailOp = s.depthFailOp; k.compareOp = s.compareOp; k.compareMask = s.compareMask & 0xFF; k.writeMask = s.writeMask & 0xFF; k.reference = s.reference & 0xFF; k.pad = 0; return k; };
+	d.front = face(desc->front); d.back = face(desc->back);
+	if(d.stencilActive)
+	{
+		const swcu_stencil_face *f2[2] = { &desc->front, &desc->back };
+		for(const swcu_stencil_face *s : f2)
+			if(s->failOp > SOP_DEC_WRAP || s->passOp > SOP_DEC_WRAP || s->depthFailOp > SOP_DEC_WRAP || s->compareOp > CMP_ALWAYS) return fail(ctx, SWCU_E_INVALID, "bad stencil state");
+		const bool allKeep = desc->front.passOp == SOP_KEEP && desc->front.depthFailOp == SOP_KEEP && desc->front.failOp == SOP_KEEP &&
+		                     desc->back.passOp == SOP_KEEP && desc->back.depthFailOp == SOP_KEEP && desc->back.failOp == SOP_KEEP;
+		const bool writeEnabled = (desc->front.writeMask & 0xFF) != 0 || (desc->back.writeMask & 0xFF) != 0;
+		d.stencilWrite = !allKeep && writeEnabled;
+	}
+	{ // Context.cpp:1090-1147
+		const int cop = fold_blend_op((int)desc->colorBlendOp, (int)desc->srcColorBlendFactor, (int)desc->dstColorBlendFactor);
+		const int aop = fold_blend_op((int)desc->alphaBlendOp, (int)desc->srcAlphaBlendFactor, (int)desc->dstAlphaBlendFactor);
+		d.colorWriteMask = desc->color.buffer ? (desc->colorWriteMask & 0xF) : 0;
+		if(desc->blendEnable && cop == BOP_DST_EXT && aop == BOP_DST_EXT) d.colorWriteMask = 0;
+		d.blendEnable = desc->blendEnable && d.colorWriteMask && (cop != BOP_SRC_EXT || aop != BOP_SRC_EXT);
+		if(d.blendEnable)
+		{
+			if(kop(cop) < 0 || kop(aop) < 0) return fail(ctx, SWCU_E_UNSUPPORTED, "blend op %d/%d outside the subset (ADD, SUBTRACT, REVERSE_SUBTRACT, MIN, MAX)", (int)desc->colorBlendOp, (int)desc->alphaBlendOp);
+			if(desc->srcColorBlendFactor > BF_SRC_ALPHA_SATURATE || desc->dstColorBlendFactor > BF_SRC_ALPHA_SATURATE ||
+			   desc->srcAlphaBlendFactor > BF_SRC_ALPHA_SATURATE || desc->dstAlphaBlendFactor > BF_SRC_ALPHA_SATURATE)
+				return fail(ctx, SWCU_E_UNSUPPORTED, "blend factor outside the subset (dual-source factors)");
+			d.op = (uint32_t)kop(cop); d.opA = (uint32_t)kop(aop);
+			d.srcF = (uint32_t)fold_blend_factor((int)desc->colorBlendOp, (int)desc->srcColorBlendFactor);
+			d.dstF = (uint32_t)fold_blend_factor((int)desc->colorBlendOp, (int)desc->dstColorBlendFactor);
+			d.srcFA = (uint32_t)fold_blend_factor((int)desc->alphaBlendOp, (int)desc->srcAlphaBlendFactor);
+			d.dstFA = (uint32_t)fold_blend_factor((int)desc->alphaBlendOp, (int)desc->dstAlphaBlendFactor);
+		}
+		for(int k = 0; k < 4; k++) d.blendConstant[k] = clamp01(desc->blendConstants[k]);
+		d.bgr = desc->color.format == VKF_B8G8R8A8_UNORM;
+	}
+
+	// ---- attachments ----
+	const swcu_attachment *any = desc->color.buffer ? &desc->color : (desc->depth.buffer ? &desc->depth : &desc->stencil);
+	d.fbWidth = (int)any->width; d.fbHeight = (int)any->height;
+	if(d.fbWidth <= 0 || d.fbHeight <= 0 || d.fbWidth > 8192 || d.fbHeight > 8192) return fail(ctx, SWCU_E_UNSUPPORTED, "framebuffer extent %dx%d outside 1..8192 (OUTLINE_RESOLUTION, Config.hpp:20)", d.fbWidth, d.fbHeight);
+	auto att = [&](const swcu_attachment &a, int bpp, unsigned char *&buf, int &pitch, int &slice, const char *what) -> int {
+		if(!a.buffer) return SWCU_OK;
+		if((int)a.width != d.fbWidth || (int)a.height != d.fbHeight) return fail(ctx, SWCU_E_INVALID, "%s attachment extent differs from the framebuffer", what);
+		const size_t need = (size_t)(d.ms - 1) * a.sliceB + (size_t)(a.height - 1) * a.pitchB + (size_t)a.width * bpp;
+		buf = dev_ptr(ctx, a.buffer, need);
+		if(!buf) return fail(ctx, SWCU_E_INVALID, "%s attachment %p (+%zu) is not inside a registered range", what, a.buffer, need);
+		pitch = a.pitchB; slice = a.sliceB;
+		return SWCU_OK;
+	};
+	if((rc = att(desc->color, 4, d.colorBuf, d.colorPitchB, d.colorSliceB, "colour"))) return rc;
+	if((rc = att(desc->depth, 4, d.depthBuf, d.depthPitchB, d.depthSliceB, "depth"))) return rc;
+	if((rc = att(desc->stencil, 1, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, "stencil"))) return rc;
+	d.scX0 = clampi_h(d.scX0, 0, d.fbWidth); d.scX1 = clampi_h(d.scX1, 0, d.fbWidth);
+	d.scY0 = clampi_h(d.scY0, 0, d.fbHeight); d.scY1 = clampi_h(d.scY1, 0, d.fbHeight);
+
+	d.tilesX = (d.fbWidth + SWCU_TILE_W - 1) / SWCU_TILE_W;
+	d.tilesY = (d.fbHeight + SWCU_TILE_H - 1) / SWCU_TILE_H;
+	d.tileX0 = d.scX0 / SWCU_TILE_W; d.tileY0 = d.scY0 / SWCU_TILE_H;
+	d.tileX1 = (d.scX1 + SWCU_TILE_W - 1) / SWCU_TILE_W; d.tileY1 = (d.scY1 + SWCU_TILE_H - 1) / SWCU_TILE_H;
+	d.triStride = swcu_tri_stride(d.nvar);
+	return SWCU_OK;
+}
+
+__global__ void k_pair_total(const uint32_t *pairOffset, const uint32_t *tileCount, uint32_t n, DrawCounters *c)
+{
+	c->pairTotal = (unsigned long long)pairOffset[n - 1] + tileCount[n - 1];
+}
+
+template<int MS>
+static void launch_tile(swcu_ctx *ctx, const DrawConst &d, dim3 grid)
+{
+	LaunchScope ls(ctx, MS == 4 ? "k_tile<4>" : "k_tile<1>");
+	k_tile<MS><<<grid, TILE_THREADS, 0, ctx->stream>>>(d, (const uint32_t *)ctx->tileBegin.p, (const uint32_t *)ctx->tileEnd.p, (const uint32_t *)ctx->vals.p);
+}
+
+extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
+{
+	if(!ctx || !desc) return fail(ctx, SWCU_E_INVALID, "swcu_draw: null argument");
+	CU(cudaSetDevice(ctx->device));
+	DrawConst d;
+	int rc = build_const(ctx, desc, d);
+	if(rc) return rc;
+	ctx->stats.draws++;
+	ctx->stats.primitives += d.primCount;
+	if(ctx->profiling) { ctx->lastKernels.clear(); ctx->eventsUsed = 0; }
+	if(d.primCount == 0 || d.scX0 >= d.scX1 || d.scY0 >= d.scY1) return SWCU_OK;
+	if((unsigned long long)d.primCount * d.triStride > (1ull << 36)) return fail(ctx, SWCU_E_NOMEM, "draw too large");
+
+	const uint32_t n = d.primCount;
+	d.direct = (!ctx->optForceBinned && (int)n <= ctx->optDirectMax) ? 1u : 0u;
+	if((rc = ensure(ctx, ctx->triRecords, (size_t)n * d.triStride))) return rc;
+	if((rc = ensure(ctx, ctx->tileCount, (size_t)n * 4))) return rc;
+	if((rc = ensure(ctx, ctx->counters, sizeof(DrawCounters)))) return rc;
+	const size_t scRows = (size_t)(d.scY1 - d.scY0);
+	size_t spanWant, bigWant;
+	if(d.direct) { spanWant = (size_t)n * d.ms * scRows; bigWant = n; }
+	else
+	{
+		spanWant = std::max<size_t>(ctx->spans.cap / 4, std::max<size_t>((size_t)n * d.ms * 8, 1u << 20));
+		bigWant = std::max<size_t>(ctx->bigList.cap / sizeof(BigTri), 1u << 14);
+	}
+	const dim3 tileGrid((unsigned)(d.tileX1 - d.tileX0), (unsigned)(d.tileY1 - d.tileY0));
+	const uint32_t numTiles = (uint32_t)(d.tilesX * d.tilesY);
+
+	for(int attempt = 0;; attempt++)
+	{
+		if((rc = ensure(ctx, ctx->spans, spanWant * 4))) return rc;
+		if((rc = ensure(ctx, ctx->bigList, bigWant * sizeof(BigTri)))) return rc;
+		d.triRecords = (unsigned char *)ctx->triRecords.p;
+		d.tileCount = (uint32_t *)ctx->tileCount.p;
+		d.counters = (DrawCounters *)ctx->counters.p;
+		d.spans = (uint32_t *)ctx->spans.p;
+		d.spanCapacity = std::min<unsigned long long>(ctx->spans.cap / 4, 0xFFFFFFFFull);
+		d.bigList = (BigTri *)ctx->bigList.p;
+		d.bigCapacity = (uint32_t)std::min<size_t>(ctx->bigList.cap / sizeof(BigTri), 0x7FFFFFFFu);
+		CU(cudaMemsetAsync(d.counters, 0, sizeof(DrawCounters), ctx->stream));
+		{
+			LaunchScope ls(ctx, "k_setup");
+			k_setup<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d);
+		}
+		if(d.direct) break;
+
+		// ---- binning: pair offsets, totals back to the host (the one sync of a binned draw) ----
+		if((rc = ensure(ctx, ctx->pairOffset, (size_t)n * 4))) return rc;
+		size_t tempBytes = 0;
+		CU(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, (const uint32_t *)d.tileCount, (uint32_t *)ctx->pairOffset.p, (int)n, ctx->stream));
+		if((rc = ensure(ctx, ctx->cubTemp, tempBytes))) return rc;
+		tempBytes = ctx->cubTemp.cap;
+		CU(cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tempBytes, (const uint32_t *)d.tileCount, (uint32_t *)ctx->pairOffset.p, (int)n, ctx->stream));
+		{
+			LaunchScope ls(ctx, "k_pair_total");
+			k_pair_total<<<1, 1, 0, ctx->stream>>>((const uint32_t *)ctx->pairOffset.p, d.tileCount, n, d.counters);
+		}
+		CU(cudaMemcpyAsync(ctx->hostCounters, d.counters, sizeof(DrawCounters), cudaMemcpyDeviceToHost, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
+		const DrawCounters hc = *ctx->hostCounters;
+		if(hc.overflow)
+		{
+			if(attempt >= 2) return fail(ctx, SWCU_E_NOMEM, "work buffers still too small after growing (spans %llu, big %llu)", hc.spanCursor, hc.bigSlots);
+			if(hc.spanCursor > 0xFFFFFFF0ull) return fail(ctx, SWCU_E_NOMEM, "span table of %llu rows exceeds the 32-bit index space", hc.spanCursor);
+			spanWant = std::max<size_t>(spanWant, (size_t)hc.spanCursor + 1024);
+			bigWant = std::max<size_t>(bigWant, (size_t)hc.bigSlots + 64);
+			continue;
+		}
+		if(hc.pairTotal > 0x7FFFFFF0ull) return fail(ctx, SWCU_E_NOMEM, "%llu (tile, triangle) pairs exceed the 31-bit index space", hc.pairTotal);
+		const uint32_t pairs = (uint32_t)hc.pairTotal;
+		if(pairs == 0) return SWCU_OK;
+		if((rc = ensure(ctx, ctx->keys, (size_t)pairs * 4))) return rc;
+		if((rc = ensure(ctx, ctx->vals, (size_t)pairs * 4))) return rc;
+		if((rc = ensure(ctx, ctx->keys2, (size_t)pairs * 4))) return rc;
+		if((rc = ensure(ctx, ctx->vals2, (size_t)pairs * 4))) return rc;
+		if((rc = ensure(ctx, ctx->tileBegin, (size_t)numTiles * 4))) return rc;
+		if((rc = ensure(ctx, ctx->tileEnd, (size_t)numTiles * 4))) return rc;
+		{
+			LaunchScope ls(ctx, "k_emit");
+			k_emit<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d, (const uint32_t *)ctx->pairOffset.p, (uint32_t *)ctx->keys.p, (uint32_t *)ctx->vals.p);
+		}
+		if(hc.bigSlots)
+		{
+			LaunchScope ls(ctx, "k_big");
+			const unsigned gx = (unsigned)std::min<unsigned long long>(hc.bigSlots, 4096);
+			const unsigned gy = hc.bigSlots < 64 ? 16 : 1;
+			k_big<<<dim3(gx, gy), 256, 0, ctx->stream>>>(d, (const uint32_t *)ctx->pairOffset.p, (uint32_t *)ctx->keys.p, (uint32_t *)ctx->vals.p);
+		}
+		// stable sort by tile: per-tile lists keep API order
+		int bits = 1;
+		while((1u << bits) <= numTiles) bits++;
+		cub::DoubleBuffer<uint32_t> kb((uint32_t *)ctx->keys.p, (uint32_t *)ctx->keys2.p), vb((uint32_t *)ctx->vals.p, (uint32_t *)ctx->vals2.p);
+		tempBytes = 0;
+		CU(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, kb, vb, (int)pairs, 0, bits, ctx->stream));
+		if((rc = ensure(ctx, ctx->cubTemp, tempBytes))) return rc;
+		tempBytes = ctx->cubTemp.cap;
+		CU(cub::DeviceRadixSort::SortPairs(ctx->cubTemp.p, tempBytes, kb, vb, (int)pairs, 0, bits, ctx->stream));
+		if(kb.Current() != (uint32_t *)ctx->keys.p) { std::swap(ctx->keys, ctx->keys2); }
+		if(vb.Current() != (uint32_t *)ctx->vals.p) { std::swap(ctx->vals, ctx->vals2); }
+		CU(cudaMemsetAsync(ctx->tileBegin.p, 0, (size_t)numTiles * 4, ctx->stream));
+		CU(cudaMemsetAsync(ctx->tileEnd.p, 0, (size_t)numTiles * 4, ctx->stream));
+		{
+			LaunchScope ls(ctx, "k_tile_ranges");
+			k_tile_ranges<<<(pairs + 255) / 256, 256, 0, ctx->stream>>>((const uint32_t *)ctx->keys.p, pairs, numTiles, (uint32_t *)ctx->tileBegin.p, (uint32_t *)ctx->tileEnd.p);
+		}
+		break;
+	}
+	if(d.direct)
+	{
+		LaunchScope ls(ctx, "k_big");
+		k_big<<<dim3(std::min<uint32_t>(n, 64u), 1), 256, 0, ctx->stream>>>(d, nullptr, nullptr, nullptr);
+	}
+	if(d.ms == 4) launch_tile<4>(ctx, d, tileGrid); else launch_tile<1>(ctx, d, tileGrid);
+	CU(cudaGetLastError());
+	return SWCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// clear / resolve on the resident shadows
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t samples, const swcu_rect *area, const void *value)
+{
+	if(!ctx || !att || !area || !value || !att->buffer) return fail(ctx, SWCU_E_INVALID, "swcu_clear: null argument");
+	int bpp;
+	switch(att->format)
+	{
+	case VKF_R8G8B8A8_UNORM: case VKF_B8G8R8A8_UNORM: case VKF_D32_SFLOAT: bpp = 4; break;
+	case VKF_S8_UINT: bpp = 1; break;
+	default: return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_clear: format %u unsupported", att->format);
+	}
+	if(samples < 1 || area->x < 0 || area->y < 0 || area->x + area->width > att->width || area->y + area->height > att->height)
+		return fail(ctx, SWCU_E_INVALID, "swcu_clear: area outside the attachment");
+	if(area->width == 0 || area->height == 0) return SWCU_OK;
+	CU(cudaSetDevice(ctx->device));
+	const size_t need = (size_t)(samples - 1) * att->sliceB + (size_t)(att->height - 1) * att->pitchB + (size_t)att->width * bpp;
+	unsigned char *base = dev_ptr(ctx, att->buffer, need);
+	if(!base) return fail(ctx, SWCU_E_INVALID, "swcu_clear: attachment is not inside a registered range");
+	uint32_t v = 0;
+	memcpy(&v, value, (size_t)bpp);
+	LaunchScope ls(ctx, "k_clear");
+	k_clear<<<dim3((area->width + 255) / 256, area->height), 256, 0, ctx->stream>>>(base, att->pitchB, att->sliceB, bpp, area->x, area->y, (int)area->width, (int)area->height, (int)samples, v);
+	CU(cudaGetLastError());
+	return SWCU_OK;
+}
+
+extern "C" int swcu_resolve(swcu_ctx *ctx, const swcu_attachment *src, uint32_t samples, const swcu_attachment *dst)
+{
+	if(!ctx || !src || !dst || !src->buffer || !dst->buffer) return fail(ctx, SWCU_E_INVALID, "swcu_resolve: null argument");
+	if(samples != 4) return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_resolve: only 4x -> 1x");
+	if(src->format != dst->format || (src->format != VKF_R8G8B8A8_UNORM && src->format != VKF_B8G8R8A8_UNORM)) return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_resolve: format unsupported");
+	if(src->width != dst->width || src->height != dst->height) return fail(ctx, SWCU_E_INVALID, "swcu_resolve: extent mismatch");
+	CU(cudaSetDevice(ctx->device));
+	unsigned char *s = dev_ptr(ctx, src->buffer, (size_t)3 * src->sliceB + (size_t)(src->height - 1) * src->pitchB + (size_t)src->width * 4);
+	unsigned char *t = dev_ptr(ctx, dst->buffer, (size_t)(dst->height - 1) * dst->pitchB + (size_t)dst->width * 4);
+	if(!s || !t) return fail(ctx, SWCU_E_INVALID, "swcu_resolve: attachment is not inside a registered range");
+	LaunchScope ls(ctx, "k_resolve4");
+	k_resolve4<<<dim3((src->width + 255) / 256, src->height), 256, 0, ctx->stream>>>(s, src->pitchB, src->sliceB, t, dst->pitchB, (int)src->width, (int)src->height);
+	CU(cudaGetLastError());
+	return SWCU_OK;
+}

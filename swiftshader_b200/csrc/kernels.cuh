@@ -1,0 +1,1267 @@
+// kernels.cuh — the sm_100a kernels of the draw path.
+//
+//   k_setup   one thread per triangle: index fetch (Renderer.cpp:50-145), vertex stage + clip flags + projection
+//             (VertexRoutine.cpp:116-154,570-610), trivial reject / Sutherland-Hodgman clip (Renderer.cpp:733-776,
+//             Clipper.cpp), cull / row range / plane equations (SetupRoutine.cpp:36-548) and — for small triangles —
+//             the per-row spans (SetupRoutine.cpp:550-621).
+//   k_big     one CTA per large triangle: spans in closed form, one (row, sample) per thread, and its tile pairs.
+//   k_emit    (tile, triangle) pairs of the small triangles; sorted by tile with a stable radix sort => per-tile
+//             triangle lists in API order (the ordering contract of Renderer.cpp:573-576,652-661).
+//   k_tile    one CTA per 32x16 screen tile: stages colour/depth/stencil of the tile in shared memory, every lane owns one
+//             2x2 quad, walks the tile's triangles in order and runs QuadRasterizer coverage + PixelRoutine::quad
+//             (depth/stencil test, interpolation, shader routing, sampler, blend, format write), then writes the tile
+//             back with 128-bit stores.
+//
+// Float discipline: compiled with -fmad=false -ftz=true -prec-div=true -prec-sqrt=true; every
+// product/sum is a single rounded op and __fmaf_rn appears only where the reference writes MulAdd().
+#pragma once
+
+#include "swcu_internal.h"
+
+#include <cuda_runtime.h>
+
+#define DEVI __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------------------------------
+// small helpers (Reactor semantics on x86: LLVMReactor.cpp:135-138,2694-2703)
+// ------------------------------------------------------------------------------------------------------------------
+DEVI int round_int(float x) { return (x != x) ? (int)0x80000000 : __float2int_rn(x); } // cvtps2dq: NaN -> indefinite
+DEVI int trunc_int(float x) { return (x != x) ? (int)0x80000000 : __float2int_rz(x); } // cvttps2dq
+DEVI int round_int_clamped(float x) { float c = x < 2147483520.0f ? x : 2147483520.0f; return round_int(c); }
+DEVI float sse_max(float a, float b) { return a > b ? a : b; } // maxps: second operand unless strictly greater
+DEVI float sse_min(float a, float b) { return a < b ? a : b; }
+DEVI float fmul(float a, float b) { return __fmul_rn(a, b); }
+DEVI float fadd(float a, float b) { return __fadd_rn(a, b); }
+DEVI float fsub(float a, float b) { return __fsub_rn(a, b); }
+DEVI float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+DEVI int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__constant__ float c_SampleX[4] = { 0.375f - 0.5f, 0.875f - 0.5f, 0.125f - 0.5f, 0.625f - 0.5f }; // Constants.cpp:291-297
+__constant__ float c_SampleY[4] = { 0.125f - 0.5f, 0.375f - 0.5f, 0.625f - 0.5f, 0.875f - 0.5f };
+__constant__ int c_Xf[4] = { -32, 96, -96, 32 }; // Constants.hpp:26-52 (8-bit sub-pixel precision)
+__constant__ int c_Yf[4] = { -96, -32, 32, 96 };
+
+// ------------------------------------------------------------------------------------------------------------------
+// vertex stage
+// ------------------------------------------------------------------------------------------------------------------
+DEVI uint32_t fetch_index(const DrawConst &d, uint32_t i)
+{
+	if(d.indexType == 2) return ((const uint16_t *)d.indexBuffer)[i];
+	if(d.indexType == 4) return ((const uint32_t *)d.indexBuffer)[i];
+	return i;
+}
+
+// setBatchIndices, Renderer.cpp:50-145 (triangle list / strip / fan, provoking-vertex rotation)
+DEVI void triangle_indices(const DrawConst &d, uint32_t i, uint32_t idx[3])
+{
+	const uint32_t pf = d.provokingFirst;
+	if(d.topology == TOPO_TRIANGLE_STRIP)
+	{
+		idx[0] = fetch_index(d, i + (pf ? 0 : 2));
+		idx[1] = fetch_index(d, i + (i & 1) + (pf ? 1 : 0));
+		idx[2] = fetch_index(d, i + (~i & 1) + (pf ? 1 : 0));
+	}
+	else if(d.topology == TOPO_TRIANGLE_FAN)
+	{
+		uint32_t a = fetch_index(d, i + 1), b = fetch_index(d, i + 2), c = fetch_index(d, 0);
+		if(pf) { idx[0] = a; idx[1] = b; idx[2] = c; }
+		else { idx[2] = a; idx[0] = b; idx[1] = c; }
+	}
+	else
+	{
+		idx[0] = fetch_index(d, 3 * i + (pf ? 0 : 2));
+		idx[1] = fetch_index(d, 3 * i + (pf ? 1 : 0));
+		idx[2] = fetch_index(d, 3 * i + (pf ? 2 : 1));
+	}
+}
+
+// VertexRoutine::readStream (VertexRoutine.cpp:173-245) for R32..R32G32B32A32_SFLOAT, one component
+DEVI float read_attr(const DrawConst &d, uint32_t code, uint32_t index)
+{
+	const KVertexInput &in = d.input[code >> 2];
+	const uint32_t c = code & 3;
+	const float def = c == 3 ? 1.0f : 0.0f;
+	if(c >= in.ncomp) return def;
+	uint32_t offset = (index + (uint32_t)d.baseVertex) * in.stride;
+	if(in.robustnessSize)
+	{
+		uint32_t o = offset < in.robustnessSize ? offset : in.robustnessSize;
+		if(o + in.ncomp * 4 > in.robustnessSize) return 0.0f;
+	}
+	return __ldg((const float *)(in.buffer + offset) + c);
+}
+
+DEVI float vs_operand(const DrawConst &d, const KOperand &op, uint32_t index)
+{
+	return op.kind == OPK_CONST ? __uint_as_float(op.value) : read_attr(d, op.value, index);
+}
+
+struct VOut
+{
+	float px, py, pz, pw; // clip-space position
+	int flags;
+	int X, Y;      // projected, 24.8
+	float zp, rhw; // projected.z, projected.w
+};
+
+DEVI void process_vertex(const DrawConst &d, uint32_t index, VOut &v)
+{
+	const float px = vs_operand(d, d.vsPos[0], index), py = vs_operand(d, d.vsPos[1], index);
+	const float pz = vs_operand(d, d.vsPos[2], index), pw = vs_operand(d, d.vsPos[3], index);
+	v.px = px; v.py = py; v.pz = pz; v.pw = pw;
+	int f = 0; // computeClipFlags, VertexRoutine.cpp:128-152
+	if(pw < px) f |= CLIP_RIGHT;
+	if(pw < py) f |= CLIP_TOP;
+	if(!(-pw <= px)) f |= CLIP_LEFT;
+	if(!(-pw <= py)) f |= CLIP_BOTTOM;
+	if(d.depthClipEnable)
+	{
+		if(pw < pz) f |= CLIP_FAR;
+		if(!(0.0f <= pz)) f |= CLIP_NEAR;
+	}
+	if(fabsf(px) <= 3.40282347e38f && fabsf(py) <= 3.40282347e38f && fabsf(pz) <= 3.40282347e38f) f |= CLIP_FINITE;
+	v.flags = f;
+	uint32_t wb = __float_as_uint(pw); // VertexRoutine.cpp:599-606
+	if(pw == 0.0f) wb |= 0x3F800000u;
+	const float w = __uint_as_float(wb);
+	const float rhw = fdiv(1.0f, w);
+	v.X = round_int_clamped(fadd(d.X0xF, fmul(fmul(px, rhw), d.WxF)));
+	v.Y = round_int_clamped(fadd(d.Y0xF, fmul(fmul(py, rhw), d.HxF)));
+	v.zp = fmul(pz, rhw);
+	v.rhw = rhw;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// clipper (Clipper.cpp:22-30 clipEdge, :32-265 planes, :271-299 Clip)
+// ------------------------------------------------------------------------------------------------------------------
+DEVI float4 clip_edge(float4 Vi, float4 Vj, float di, float dj)
+{
+	const float D = fdiv(1.0f, fsub(dj, di));
+	float4 o;
+	o.x = fmul(fsub(fmul(dj, Vi.x), fmul(di, Vj.x)), D);
+	o.y = fmul(fsub(fmul(dj, Vi.y), fmul(di, Vj.y)), D);
+	o.z = fmul(fsub(fmul(dj, Vi.z), fmul(di, Vj.z)), D);
+	o.w = fmul(fsub(fmul(dj, Vi.w), fmul(di, Vj.w)), D);
+	return o;
+}
+
+DEVI float plane_dist(int plane, float4 v)
+{
+	switch(plane)
+	{
+	case CLIP_NEAR: return v.z;
+	case CLIP_FAR: return fsub(v.w, v.z);
+	case CLIP_LEFT: return fadd(v.w, v.x);
+	case CLIP_RIGHT: return fsub(v.w, v.x);
+	case CLIP_TOP: return fsub(v.w, v.y);
+	default: return fadd(v.w, v.y);
+	}
+}
+
+// returns the vertex count (0 if clipped away); P has room for 16
+__device__ __noinline__ int clip_polygon(float4 *P, int n, int flagsOr)
+{
+	const int order[6] = { CLIP_NEAR, CLIP_FAR, CLIP_LEFT, CLIP_RIGHT, CLIP_TOP, CLIP_BOTTOM };
+	float4 T[16];
+	for(int k = 0; k < 6; k++)
+	{
+		if(n < 3) break;
+		if(!(flagsOr & order[k])) continue;
+		int t = 0;
+		for(int i = 0; i < n; i++)
+		{
+			int j = i == n - 1 ? 0 : i + 1;
+			float di = plane_dist(order[k], P[i]);
+			float dj = plane_dist(order[k], P[j]);
+			if(di >= 0)
+			{
+				T[t++] = P[i];
+				if(dj < 0) T[t++] = clip_edge(P[i], P[j], di, dj);
+			}
+			else if(dj > 0) T[t++] = clip_edge(P[j], P[i], dj, di);
+		}
+		for(int i = 0; i < t; i++) P[i] = T[i];
+		n = t;
+	}
+	return n >= 3 ? n : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// spans
+// ------------------------------------------------------------------------------------------------------------------
+// SetupRoutine::edge (SetupRoutine.cpp:550-621), row-stepping form for triangles of a few rows.  Writes the clamped x
+// of every row of the edge inside [rowMin,rowMax) into the left or right half of the span entries.
+DEVI void edge_small(const DrawConst &d, uint32_t *spans, int rowMin, int stride, int q, int Xa, int Ya, int Xb, int Yb)
+{
+	if(Ya == Yb) return;
+	const bool swap = Yb < Ya;
+	const int X1 = swap ? Xb : Xa, X2 = swap ? Xa : Xb;
+	const int Y1 = swap ? Yb : Ya, Y2 = swap ? Ya : Yb;
+	const int y1 = (Y1 + 255) >> 8, y2 = (Y2 + 255) >> 8;
+	const int yMin = max(y1, d.scY0), yMax = min(y2, d.scY1);
+	if(!(yMin < yMax)) return;
+	const int DX12 = X2 - X1, DY12 = Y2 - Y1;
+	const int FDX12 = DX12 << 8, FDY12 = DY12 << 8;
+	int X = DX12 * ((y1 << 8) - Y1) + (X1 & 255) * DY12;
+	int x = (X1 >> 8) + X / FDY12;
+	int dd = X % FDY12;
+	int ceil = -dd >> 31;
+	x -= ceil;
+	dd -= ceil & FDY12;
+	int Q = FDX12 / FDY12;
+	int R = FDX12 % FDY12;
+	int floor = R >> 31;
+	Q += floor;
+	R += floor & FDY12;
+	unsigned short *half = (unsigned short *)spans + (swap ? 1 : 0);
+	for(int y = y1; y < yMax; y++)
+	{
+		if(y >= yMin) half[2 * ((y - rowMin) * stride + q)] = (unsigned short)clampi(x, d.scX0, d.scX1);
+		x += Q;
+		dd += R;
+		int overflow = -dd >> 31;
+		dd -= FDY12 & overflow;
+		x -= overflow;
+	}
+}
+
+// The same edge in closed form (SURVEY §9.1 "edges"): x(y) = (X1>>8) + ceil((DX*(256y - Y1) + (X1&255)*DY) / (256*DY)).
+// Returns true if the edge owns row y; *right tells which half it writes.
+DEVI bool edge_at_row(const DrawConst &d, int Xa, int Ya, int Xb, int Yb, int y, bool &right, int &xo)
+{
+	if(Ya == Yb) return false;
+	const bool swap = Yb < Ya;
+	const int X1 = swap ? Xb : Xa, X2 = swap ? Xa : Xb;
+	const int Y1 = swap ? Yb : Ya, Y2 = swap ? Ya : Yb;
+	const int y1 = (Y1 + 255) >> 8, y2 = (Y2 + 255) >> 8;
+	if(y < max(y1, d.scY0) || y >= min(y2, d.scY1)) return false;
+	const long long DX = X2 - X1, DY = Y2 - Y1;
+	const long long N = DX * (256ll * y - Y1) + (long long)(X1 & 255) * DY;
+	const long long D = 256ll * DY;
+	long long qv = N / D;
+	if(N % D > 0) qv += 1; // ceiling
+	xo = clampi((X1 >> 8) + (int)qv, d.scX0, d.scX1);
+	right = swap;
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_setup
+// ------------------------------------------------------------------------------------------------------------------
+DEVI void rot1(bool c, int &a, int &b, int &e) { if(c) { int t = a; a = b; b = e; e = t; } }
+DEVI void rot2(bool c, int &a, int &b, int &e) { if(c) { int t = e; e = b; b = a; a = t; } }
+
+// warp-aggregated bump allocation: one atomic per warp instead of one per triangle (all 32 lanes must call)
+DEVI unsigned long long warp_alloc(unsigned long long *cursor, uint32_t count)
+{
+	const int lane = threadIdx.x & 31;
+	uint32_t incl = count;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if(lane >= o) incl += t;
+	}
+	const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+	unsigned long long base = 0;
+	if(lane == 31 && total) base = atomicAdd(cursor, (unsigned long long)total);
+	base = __shfl_sync(0xFFFFFFFFu, base, 31);
+	return base + (incl - count);
+}
+
+__global__ void __launch_bounds__(128) k_setup(const __grid_constant__ DrawConst d)
+{
+	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x; // grid is padded to whole warps; inactive lanes just allocate 0
+	const bool live = tri < d.primCount;
+	const bool msaa = d.ms > 1;
+	uint32_t nTiles = 0;
+	bool visible = false;
+	uint32_t idx[3] = { 0, 0, 0 };
+	VOut v[3];
+	int PX[SWCU_POLY_MAX], PY[SWCU_POLY_MAX];
+	int n = 3, dir = 1;
+	bool frontFacing = false;
+	int yMin = 0, yMax = 0, pxMin = 0, pxMax = 0;
+	if(live)
+	{
+		do
+		{
+			triangle_indices(d, tri, idx);
+			process_vertex(d, idx[0], v[0]);
+			process_vertex(d, idx[1], v[1]);
+			process_vertex(d, idx[2], v[2]);
+
+			// setupSolidTriangles, Renderer.cpp:749-757
+			if((v[0].flags & v[1].flags & v[2].flags) != CLIP_FINITE) break;
+			const int flagsOr = v[0].flags | v[1].flags | v[2].flags;
+			PX[0] = v[0].X; PX[1] = v[1].X; PX[2] = v[2].X;
+			PY[0] = v[0].Y; PY[1] = v[1].Y; PY[2] = v[2].Y;
+
+			// culling, SetupRoutine.cpp:73-115 (on the original three vertices)
+			{
+				const float x0 = (float)v[0].X, x1 = (float)v[1].X, x2 = (float)v[2].X;
+				const float y0 = (float)v[0].Y, y1 = (float)v[1].Y, y2 = (float)v[2].Y;
+				float A = fadd(fadd(fmul(fsub(y0, y2), x1), fmul(fsub(y2, y1), x0)), fmul(fsub(y1, y0), x2));
+				const int s = (int)(__float_as_uint(v[0].pw) ^ __float_as_uint(v[1].pw) ^ __float_as_uint(v[2].pw));
+				if(s < 0) A = -A;
+				frontFacing = d.frontFace == FRONT_FACE_CCW ? (A >= 0.0f) : (A <= 0.0f);
+				if((d.cullMode & CULL_FRONT) && frontFacing) break;
+				if((d.cullMode & CULL_BACK) && !frontFacing) break;
+				if(!(A > 0.0f)) dir = 0;
+			}
+
+			if(flagsOr != CLIP_FINITE && (flagsOr & CLIP_FRUSTUM))
+			{
+				float4 P[16];
+				P[0] = make_float4(v[0].px, v[0].py, v[0].pz, v[0].pw);
+				P[1] = make_float4(v[1].px, v[1].py, v[1].pz, v[1].pw);
+				P[2] = make_float4(v[2].px, v[2].py, v[2].pz, v[2].pw);
+				n = clip_polygon(P, 3, flagsOr);
+				if(n == 0) break;
+				for(int i = 0; i < n; i++) // re-projection, SetupRoutine.cpp:125-145
+				{
+					const float rhw = P[i].w != 0.0f ? fdiv(1.0f, P[i].w) : 1.0f;
+					PX[i] = round_int(fadd(d.X0xF, fmul(fmul(P[i].x, rhw), d.WxF)));
+					PY[i] = round_int(fadd(d.Y0xF, fmul(fmul(P[i].y, rhw), d.HxF)));
+				}
+			}
+
+			int minY = PY[0], maxY = PY[0], minX = PX[0], maxX = PX[0];
+			for(int i = 1; i < n; i++)
+			{
+				minY = min(minY, PY[i]); maxY = max(maxY, PY[i]);
+				minX = min(minX, PX[i]); maxX = max(maxX, PX[i]);
+			}
+			yMin = msaa ? (minY + 159) >> 8 : (minY + 255) >> 8; // SetupRoutine.cpp:147-186
+			yMax = msaa ? (maxY + 351) >> 8 : (maxY + 255) >> 8;
+			yMin = max(yMin, d.scY0);
+			yMax = min(yMax, d.scY1);
+			if(yMin >= yMax) break;
+			// conservative pixel-x bounds of the spans (left = ceil of an edge x >= minX; right <= ceil(maxX))
+			const int margin = msaa ? 96 : 0;
+			pxMin = clampi((minX - margin + 255) >> 8, d.scX0, d.scX1);
+			pxMax = clampi((maxX + margin + 255) >> 8, d.scX0, d.scX1);
+			if(pxMin >= pxMax) break;
+			visible = true;
+		} while(0);
+	}
+
+	// ---- span-table and big-list allocation, one atomic per warp ----
+	const int rows = visible ? yMax - yMin : 0;
+	const uint32_t count = (uint32_t)(rows * d.ms);
+	bool big = false;
+	if(visible)
+	{
+		const int tx0 = pxMin / SWCU_TILE_W, tx1 = (pxMax - 1) / SWCU_TILE_W;
+		const int ty0 = yMin / SWCU_TILE_H, ty1 = (yMax - 1) / SWCU_TILE_H;
+		nTiles = (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
+		big = rows > SWCU_SMALL_ROWS || nTiles > SWCU_SMALL_TILES;
+	}
+	const unsigned long long base = warp_alloc(&d.counters->spanCursor, count);
+	const unsigned long long slot = warp_alloc(&d.counters->bigSlots, big ? 1u : 0u);
+	const uint32_t nvis = __popc(__ballot_sync(0xFFFFFFFFu, visible));
+	if((threadIdx.x & 31) == 0 && nvis) atomicAdd(&d.counters->visible, nvis);
+	if(!live) return;
+	unsigned char *rec = d.triRecords + (size_t)tri * d.triStride;
+	if(visible && base + count > d.spanCapacity) { atomicOr(&d.counters->overflow, 1u); visible = false; }
+	if(visible && big && slot >= d.bigCapacity) { atomicOr(&d.counters->overflow, 2u); visible = false; }
+	if(!visible)
+	{
+		*(uint4 *)rec = make_uint4(0, 0, 0, 0); // empty bounds: never a candidate
+		d.tileCount[tri] = 0;
+		return;
+	}
+	d.tileCount[tri] = nTiles;
+
+	if(big)
+	{
+		BigTri &b = d.bigList[slot];
+		b.tri = tri; b.spanBase = (uint32_t)base; b.n = n; b.dir = dir;
+		b.yMin = yMin; b.yMax = yMax; b.pxMin = pxMin; b.pxMax = pxMax;
+		for(int i = 0; i < n; i++) { b.X[i] = PX[i]; b.Y[i] = PY[i]; }
+	}
+	else
+	{
+		uint32_t *sp = d.spans + base;
+		for(uint32_t i = 0; i < count; i++) sp[i] = 0; // MSAA pre-fill: empty span (SetupRoutine.cpp:214-225)
+		PX[n] = PX[0]; PY[n] = PY[0];
+		for(int q = 0; q < d.ms; q++)
+		{
+			const int ox = msaa ? c_Xf[q] : 0, oy = msaa ? c_Yf[q] : 0;
+			for(int i = 0; i < n; i++)
+				edge_small(d, sp, yMin, d.ms, q, PX[i + 1 - dir] - ox, PY[i + 1 - dir] - oy, PX[i + dir] - ox, PY[i + dir] - oy);
+		}
+	}
+
+	// ---- vertex sort (SetupRoutine.cpp:271-294): only changes float rounding of the planes ----
+	int i0 = 0, i1 = 1, i2 = 2;
+	{
+		const float y0 = v[0].py, y1 = v[1].py, y2 = v[2].py;
+		const float ym = sse_min(sse_min(y0, y1), y2);
+		rot1(ym == y1, i0, i1, i2);
+		rot2(ym == y2, i0, i1, i2);
+	}
+	{
+		const float w0 = v[i0].pw, w1 = v[i1].pw, w2 = v[i2].pw;
+		const float wm = sse_max(sse_max(w0, w1), w2);
+		rot1(wm == w1, i0, i1, i2);
+		rot2(wm == w2, i0, i1, i2);
+	}
+	const VOut v0 = v[i0], v1 = v[i1], v2 = v[i2];
+	const float w0 = v0.pw, w1 = v1.pw, w2 = v2.pw;
+	const float rhw0 = v0.rhw;
+	const float rsub = 1.0f / 256.0f;
+	const float x0 = fmul((float)v0.X, rsub), y0 = fmul((float)v0.Y, rsub);
+	const int dX1 = v1.X - v0.X, dY1 = v1.Y - v0.Y, dX2 = v2.X - v0.X, dY2 = v2.Y - v0.Y;
+	const float x1 = fmul(fmul(w1, rsub), (float)dX1), y1 = fmul(fmul(w1, rsub), (float)dY1);
+	const float x2 = fmul(fmul(w2, rsub), (float)dX2), y2 = fmul(fmul(w2, rsub), (float)dY2);
+	const float a = fsub(fmul(x1, y2), fmul(x2, y1));
+	float M00 = 0, M01 = 0, M02 = rhw0, M10 = 0, M11 = 0, M20 = 0, M21 = 0;
+	if(a != 0.0f)
+	{
+		const float A = fdiv(1.0f, a);
+		const float D = fmul(A, rhw0);
+		M00 = fmul(fsub(fmul(y1, w2), fmul(y2, w1)), D);
+		M01 = fmul(fsub(fmul(x2, w1), fmul(x1, w2)), D);
+		M10 = fmul(y2, A);
+		M11 = fmul(-x2, A);
+		M20 = fmul(-y1, A);
+		M21 = fmul(x1, A);
+	}
+	float *f = (float *)(rec + TRI_HEADER_BYTES);
+	f[0] = x0; f[1] = y0;
+	f[3] = fadd(fadd(M00, M10), M20);
+	f[4] = fadd(fadd(M01, M11), M21);
+	f[5] = fadd(fadd(M02, 0.0f), 0.0f);
+	float zBias = 0.0f;
+	if(d.depthTestActive)
+	{
+		const float z0 = v0.zp;
+		const float z1 = fsub(v1.zp, z0), z2 = fsub(v2.zp, z0);
+		const float px1 = fmul((float)dX1, rsub), py1 = fmul((float)dY1, rsub), px2 = fmul((float)dX2, rsub), py2 = fmul((float)dY2, rsub);
+		const float D = fdiv(d.depthRange, fsub(fmul(px1, py2), fmul(px2, py1)));
+		const float A = fmul(fsub(fmul(py2, z1), fmul(py1, z2)), D);
+		const float B = fmul(fsub(fmul(px1, z2), fmul(px2, z1)), D);
+		const float C = fadd(fmul(z0, d.depthRange), d.depthNear);
+		f[6] = A; f[7] = B; f[8] = C;
+		const bool applyConst = d.depthBiasConstant != 0.0f, applySlope = d.depthBiasSlope != 0.0f;
+		float bias = 0.0f; // SetupRoutine.cpp:417-475, floating-point depth buffer branch
+		if(applyConst)
+		{
+			const float Z1 = fadd(fmul(z1, d.depthRange), d.depthNear);
+			const float Z2 = fadd(fmul(z2, d.depthRange), d.depthNear);
+			const int e0 = (int)(__float_as_uint(C) & 0x7F800000u), e1 = (int)(__float_as_uint(Z1) & 0x7F800000u), e2 = (int)(__float_as_uint(Z2) & 0x7F800000u);
+			const int e = max(max(e0, e1), e2);
+			const float r = fmul(__uint_as_float((uint32_t)e), 1.0f / (1 << 23));
+			bias = fmul(r, d.depthBiasConstant);
+		}
+		if(applySlope) bias = fadd(bias, fmul(sse_max(fabsf(A), fabsf(B)), d.depthBiasSlope));
+		if(applyConst || applySlope)
+		{
+			if(d.depthBiasClamp != 0.0f)
+			{
+				const float c = d.depthBiasClamp;
+				bias = c > 0.0f ? sse_min(bias, c) : sse_max(bias, c);
+			}
+			zBias = bias;
+		}
+	}
+	else { f[6] = 0; f[7] = 0; f[8] = 0; }
+	f[2] = zBias;
+	// setupGradient, SetupRoutine.cpp:514-548
+	const uint32_t vi0 = i0 == 0 ? idx[0] : (i0 == 1 ? idx[1] : idx[2]);
+	const uint32_t vi1 = i1 == 0 ? idx[0] : (i1 == 1 ? idx[1] : idx[2]);
+	const uint32_t vi2 = i2 == 0 ? idx[0] : (i2 == 1 ? idx[1] : idx[2]);
+	for(int k = 0; k < d.nvar; k++)
+	{
+		float *P = f + TRI_FLOATS_FIXED + 3 * k;
+		if((d.flatMask >> k) & 1)
+		{
+			P[0] = 0; P[1] = 0; P[2] = vs_operand(d, d.varSrc[k], idx[0]); // provoking vertex = Triangle.v0
+			continue;
+		}
+		float a0 = vs_operand(d, d.varSrc[k], vi0), a1 = vs_operand(d, d.varSrc[k], vi1), a2 = vs_operand(d, d.varSrc[k], vi2);
+		if((d.noPerspMask >> k) & 1) { a0 = fmul(a0, w0); a1 = fmul(a1, w1); a2 = fmul(a2, w2); }
+		P[0] = fadd(fadd(fmul(a0, M00), fmul(a1, M10)), fmul(a2, M20));
+		P[1] = fadd(fadd(fmul(a0, M01), fmul(a1, M11)), fmul(a2, M21));
+		P[2] = fadd(fadd(fmul(a0, M02), fmul(a1, 0.0f)), fmul(a2, 0.0f));
+	}
+	uint4 hdr;
+	hdr.x = (uint32_t)pxMin | ((uint32_t)pxMax << 16);
+	hdr.y = (uint32_t)yMin | ((uint32_t)yMax << 16);
+	hdr.z = (uint32_t)base;
+	hdr.w = frontFacing ? 1u : 0u;
+	*(uint4 *)rec = hdr;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_big: spans (and tile pairs) of the large triangles
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_big(const __grid_constant__ DrawConst d, const uint32_t *pairOffset, uint32_t *keys, uint32_t *vals)
+{
+	const uint32_t nbig = (uint32_t)min(d.counters->bigSlots, (unsigned long long)d.bigCapacity);
+	for(uint32_t e = blockIdx.x; e < nbig; e += gridDim.x)
+	{
+		const BigTri &b = d.bigList[e];
+		const int n = b.n, dir = b.dir;
+		const bool msaa = d.ms > 1;
+		if(blockIdx.y == 0)
+		{
+			const int total = (b.yMax - b.yMin) * d.ms;
+			for(int r = threadIdx.x; r < total; r += blockDim.x)
+			{
+				const int y = b.yMin + r / d.ms, q = r % d.ms;
+				const int ox = msaa ? c_Xf[q] : 0, oy = msaa ? c_Yf[q] : 0;
+				int L = 0, R = 0;
+				for(int i = 0; i < n; i++) // in edge order: the last writer wins, like the reference's span table
+				{
+					const int ia = i + 1 - dir, ib = i + dir;
+					const int a = ia == n ? 0 : ia, bb = ib == n ? 0 : ib;
+					bool right; int x;
+					if(edge_at_row(d, b.X[a] - ox, b.Y[a] - oy, b.X[bb] - ox, b.Y[bb] - oy, y, right, x)) { if(right) R = x; else L = x; }
+				}
+				d.spans[b.spanBase + r] = (uint32_t)L | ((uint32_t)R << 16);
+			}
+		}
+		if(keys)
+		{
+			// tiles of the bounding box; a tile all of whose pixel centres lie strictly outside one edge is dropped
+			const int tx0 = b.pxMin / SWCU_TILE_W, tx1 = (b.pxMax - 1) / SWCU_TILE_W;
+			const int ty0 = b.yMin / SWCU_TILE_H, ty1 = (b.yMax - 1) / SWCU_TILE_H;
+			const int tw = tx1 - tx0 + 1, total = tw * (ty1 - ty0 + 1);
+			long long area2 = 0;
+			for(int i = 0; i < n; i++)
+			{
+				const int j = i + 1 == n ? 0 : i + 1;
+				area2 += (long long)b.X[i] * b.Y[j] - (long long)b.X[j] * b.Y[i];
+			}
+			const long long sgn = area2 > 0 ? 1 : (area2 < 0 ? -1 : 0);
+			const int m = msaa ? 96 : 0;
+			const uint32_t off = pairOffset[b.tri];
+			for(int t = blockIdx.y * blockDim.x + threadIdx.x; t < total; t += blockDim.x * gridDim.y)
+			{
+				const int tx = tx0 + t % tw, ty = ty0 + t / tw;
+				// pixel centres of the tile in 24.8 (centre of pixel x is X = 256x), widened by the sample offsets
+				const long long cx0 = 256ll * max(tx * SWCU_TILE_W, b.pxMin) - m, cx1 = 256ll * (min(tx * SWCU_TILE_W + SWCU_TILE_W, b.pxMax) - 1) + m;
+				const long long cy0 = 256ll * max(ty * SWCU_TILE_H, b.yMin) - m, cy1 = 256ll * (min(ty * SWCU_TILE_H + SWCU_TILE_H, b.yMax) - 1) + m;
+				bool outside = false;
+				if(sgn != 0)
+					for(int i = 0; i < n && !outside; i++)
+					{
+						const int j = i + 1 == n ? 0 : i + 1;
+						const long long ex = b.X[j] - b.X[i], ey = b.Y[j] - b.Y[i];
+						const long long slack = 4 * (llabs(ex) + llabs(ey)) + 1024; // rounding of re-projected clip vertices
+						// E(P) = ex*(Py - Yi) - ey*(Px - Xi); inside when sgn*E >= 0
+						const long long e00 = sgn * (ex * (cy0 - b.Y[i]) - ey * (cx0 - b.X[i]));
+						const long long e10 = sgn * (ex * (cy0 - b.Y[i]) - ey * (cx1 - b.X[i]));
+						const long long e01 = sgn * (ex * (cy1 - b.Y[i]) - ey * (cx0 - b.X[i]));
+						const long long e11 = sgn * (ex * (cy1 - b.Y[i]) - ey * (cx1 - b.X[i]));
+						outside = e00 < -slack && e10 < -slack && e01 < -slack && e11 < -slack;
+					}
+				keys[off + t] = outside ? (uint32_t)(d.tilesX * d.tilesY) : (uint32_t)(ty * d.tilesX + tx); // numTiles = "no tile", sorts last
+				vals[off + t] = b.tri;
+			}
+		}
+	}
+}
+
+// (tile, triangle) pairs of the small triangles
+__global__ void __launch_bounds__(256) k_emit(const __grid_constant__ DrawConst d, const uint32_t *pairOffset, uint32_t *keys, uint32_t *vals)
+{
+	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+	if(tri >= d.primCount) return;
+	const uint32_t nT = d.tileCount[tri];
+	if(nT == 0) return;
+	const uint4 hdr = *(const uint4 *)(d.triRecords + (size_t)tri * d.triStride);
+	const int pxMin = hdr.x & 0xFFFF, pxMax = hdr.x >> 16, yMin = hdr.y & 0xFFFF, yMax = hdr.y >> 16;
+	const int rows = yMax - yMin;
+	if(rows > SWCU_SMALL_ROWS || nT > SWCU_SMALL_TILES) return; // big: k_big emits
+	const int tx0 = pxMin / SWCU_TILE_W, tx1 = (pxMax - 1) / SWCU_TILE_W;
+	const int ty0 = yMin / SWCU_TILE_H, ty1 = (yMax - 1) / SWCU_TILE_H;
+	uint32_t o = pairOffset[tri];
+	for(int ty = ty0; ty <= ty1; ty++)
+		for(int tx = tx0; tx <= tx1; tx++)
+		{
+			keys[o] = (uint32_t)(ty * d.tilesX + tx);
+			vals[o] = tri;
+			o++;
+		}
+}
+
+// start/end of every tile's run in the sorted pair array
+__global__ void k_tile_ranges(const uint32_t *keys, uint32_t n, uint32_t numTiles, uint32_t *tileBegin, uint32_t *tileEnd)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	const uint32_t k = keys[i];
+	if(k >= numTiles) return;
+	if(i == 0 || keys[i - 1] != k) tileBegin[k] = i;
+	if(i + 1 == n || keys[i + 1] != k) tileEnd[k] = i + 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// sampler (SamplerCore.cpp 16-bit fixed-point path :173-198) — RGBA8, 2D, normalised coordinates
+// ------------------------------------------------------------------------------------------------------------------
+DEVI uint32_t mulhi16(uint32_t a, uint32_t b) { return (a * b) >> 16; } // on values < 65536
+
+DEVI uint32_t tex_address(float u, uint32_t mode) // SamplerCore::address :2399-2435
+{
+	if(mode == ADDR_CLAMP_TO_EDGE)
+	{
+		const float c = sse_min(sse_max(u, 0.0f), 65535.0f / 65536.0f);
+		return (uint32_t)trunc_int(fmul(c, 65536.0f)) & 0xFFFF;
+	}
+	int convert = trunc_int(fmul(u, 65536.0f));
+	if(mode == ADDR_MIRRORED_REPEAT)
+	{
+		const int mirror = (int)((uint32_t)convert << 15) >> 31;
+		convert ^= mirror;
+	}
+	return (uint32_t)convert & 0xFFFF;
+}
+
+DEVI uint32_t offset_sample(uint32_t uvw, uint32_t half, bool wrap, int count) // :278-313
+{
+	if(wrap) return (count < 0 ? uvw - half : uvw + half) & 0xFFFF;
+	if(count < 0) return uvw < half ? 0u : uvw - half;
+	const uint32_t s = uvw + half;
+	return s > 0xFFFF ? 0xFFFFu : s;
+}
+
+DEVI uint32_t load_texel(const KMip &m, uint32_t x, uint32_t y) { return __ldg((const uint32_t *)m.buffer + (x + y * m.pitchP)); }
+
+// one tap set of one mip level; out[c] are 16-bit channel values
+DEVI void sample_level(const DrawConst &d, int level, float u, float v, bool linear, uint32_t out[4])
+{
+	level = clampi(level, 0, SWCU_MIPMAP_LEVELS - 1);
+	const int l = level < (int)d.texLevels ? level : (int)d.texLevels - 1; // VkDescriptorSetLayout.cpp:470
+	const KMip &m = d.mip[l];
+	const uint32_t W = m.width & 0xFFFF, H = m.height & 0xFFFF;
+	const uint32_t uu = tex_address(u, d.addressU), vv = tex_address(v, d.addressV);
+	if(!linear)
+	{
+		const uint32_t t = load_texel(m, mulhi16(uu, W), mulhi16(vv, H));
+#pragma unroll
+		for(int c = 0; c < 4; c++) out[c] = ((t >> (8 * c)) & 0xFF) << 8;
+		return;
+	}
+	const uint32_t uHalf = (0x8000u / m.width) & 0xFFFF, vHalf = (0x8000u / m.height) & 0xFFFF;
+	const bool wrapU = d.addressU == ADDR_REPEAT, wrapV = d.addressV == ADDR_REPEAT;
+	const uint32_t u0 = offset_sample(uu, uHalf, wrapU, -1), u1 = offset_sample(uu, uHalf, wrapU, +1);
+	const uint32_t v0 = offset_sample(vv, vHalf, wrapV, -1), v1 = offset_sample(vv, vHalf, wrapV, +1);
+	const uint32_t x0 = mulhi16(u0, W), x1 = mulhi16(u1, W), y0 = mulhi16(v0, H), y1 = mulhi16(v1, H);
+	const uint32_t t00 = load_texel(m, x0, y0), t10 = load_texel(m, x1, y0), t01 = load_texel(m, x0, y1), t11 = load_texel(m, x1, y1);
+	const uint32_t f0u = (u0 * W) & 0xFFFF, f0v = (v0 * H) & 0xFFFF;
+	const uint32_t f1u = ~f0u & 0xFFFF, f1v = ~f0v & 0xFFFF;
+	const uint32_t f0u0v = mulhi16(f0u, f0v), f1u0v = mulhi16(f1u, f0v), f0u1v = mulhi16(f0u, f1v), f1u1v = mulhi16(f1u, f1v);
+#pragma unroll
+	for(int c = 0; c < 4; c++)
+	{
+		const uint32_t c00 = mulhi16(((t00 >> (8 * c)) & 0xFF) << 8, f1u1v);
+		const uint32_t c10 = mulhi16(((t10 >> (8 * c)) & 0xFF) << 8, f0u1v);
+		const uint32_t c01 = mulhi16(((t01 >> (8 * c)) & 0xFF) << 8, f1u0v);
+		const uint32_t c11 = mulhi16(((t11 >> (8 * c)) & 0xFF) << 8, f0u0v);
+		out[c] = (((c00 + c10) & 0xFFFF) + ((c01 + c11) & 0xFFFF)) & 0xFFFF;
+	}
+}
+
+// the zero-offset 4-tap variant the reference runs when min and mag filters differ and the point filter is selected
+DEVI void sample_level_split_point(const DrawConst &d, int ilod, float u, float v, uint32_t out[4])
+{
+	const int l = ilod < (int)d.texLevels ? (ilod < 0 ? 0 : ilod) : (int)d.texLevels - 1;
+	const KMip &m = d.mip[l];
+	const uint32_t W = m.width & 0xFFFF, H = m.height & 0xFFFF;
+	const uint32_t uu = tex_address(u, d.addressU), vv = tex_address(v, d.addressV);
+	const uint32_t t = load_texel(m, mulhi16(uu, W), mulhi16(vv, H));
+	const uint32_t f0u = (uu * W) & 0xFFFF, f0v = (vv * H) & 0xFFFF, f1u = ~f0u & 0xFFFF, f1v = ~f0v & 0xFFFF;
+	const uint32_t w00 = mulhi16(f1u, f1v), w10 = mulhi16(f0u, f1v), w01 = mulhi16(f1u, f0v), w11 = mulhi16(f0u, f0v);
+#pragma unroll
+	for(int c = 0; c < 4; c++)
+	{
+		const uint32_t tx = ((t >> (8 * c)) & 0xFF) << 8;
+		out[c] = (((mulhi16(tx, w00) + mulhi16(tx, w10)) & 0xFFFF) + ((mulhi16(tx, w01) + mulhi16(tx, w11)) & 0xFFFF)) & 0xFFFF;
+	}
+}
+
+struct LodState
+{
+	float lod;
+	int ilod;
+	bool linear, split;
+};
+
+// computeLod2D :1376-1422 + log2sqrt :1333-1341 + selectMipmap :2357-2379; u/v of quad lanes 0,1,2
+DEVI LodState compute_lod(const DrawConst &d, float u0, float u1, float u2, float v0, float v1, float v2)
+{
+	LodState s;
+	s.split = d.magFilter != d.minFilter;
+	bool filterLinear = s.split ? false : d.magFilter == FILTER_LINEAR;
+	float minLod = d.minLod, maxLod = d.maxLod;
+	if(d.texLevels == 1 && !s.split) { minLod = 0.0f; maxLod = 0.0f; }
+	float lod;
+	if(minLod == maxLod) lod = minLod;
+	else
+	{
+		const float Wf = (float)d.mip[0].width, Hf = (float)d.mip[0].height;
+		const float dUdx = fmul(fsub(u1, u0), Wf), dUdy = fmul(fsub(u2, u0), Wf);
+		const float dVdx = fmul(fsub(v1, v0), Hf), dVdy = fmul(fsub(v2, v0), Hf);
+		const float sx = fadd(fmul(dUdx, dUdx), fmul(dVdx, dVdx)), sy = fadd(fmul(dUdy, dUdy), fmul(dVdy, dVdy));
+		lod = sse_max(sx, sy);
+		lod = fmul(lod, lod);
+		lod = fsub((float)(int)__float_as_uint(lod), (float)0x3F800000);
+		lod = fmul(lod, __uint_as_float(0x33000000u));
+		lod = fadd(lod, d.mipLodBias);
+		lod = sse_max(lod, minLod);
+		lod = sse_min(lod, maxLod);
+	}
+	s.linear = filterLinear;
+	if(s.split)
+	{
+		const bool minLinear = d.minFilter == FILTER_LINEAR;
+		s.linear = minLinear ? !(lod <= 0.0f) : (lod <= 0.0f);
+	}
+	s.lod = lod;
+	s.ilod = d.mipmapMode == MIPMAP_MODE_NEAREST ? round_int(lod) : trunc_int(lod);
+	return s;
+}
+
+DEVI void sample_texture(const DrawConst &d, const LodState &s, float u, float v, float out[4])
+{
+	uint32_t c[4];
+	if(s.split && !s.linear) sample_level_split_point(d, s.ilod, u, v, c);
+	else sample_level(d, s.ilod, u, v, s.linear, c);
+	if(d.mipmapMode == MIPMAP_MODE_LINEAR) // sampleFilter :324-373
+	{
+		uint32_t cc[4];
+		sample_level(d, s.ilod + 1, u, v, s.linear, cc);
+		const uint32_t utri = (uint32_t)trunc_int(fmul(s.lod, 65536.0f)) & 0xFFFF;
+		const uint32_t inv = ~utri & 0xFFFF;
+#pragma unroll
+		for(int ch = 0; ch < 4; ch++) c[ch] = (mulhi16(c[ch], inv) + mulhi16(cc[ch], utri)) & 0xFFFF;
+	}
+#pragma unroll
+	for(int ch = 0; ch < 4; ch++) out[ch] = fmul((float)c[ch], 1.0f / 0xFF00);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// pixel helpers (PixelRoutine.cpp)
+// ------------------------------------------------------------------------------------------------------------------
+DEVI bool stencil_compare(uint32_t op, uint32_t value, uint32_t refMasked) // :406-449
+{
+	switch(op)
+	{
+	case CMP_ALWAYS: return true;
+	case CMP_NEVER: return false;
+	case CMP_LESS: return refMasked < value;
+	case CMP_EQUAL: return refMasked == value;
+	case CMP_NOT_EQUAL: return refMasked != value;
+	case CMP_LESS_OR_EQUAL: return refMasked <= value;
+	case CMP_GREATER: return refMasked > value;
+	default: return refMasked >= value;
+	}
+}
+
+DEVI uint32_t stencil_op(uint32_t op, uint32_t v, uint32_t ref) // :870-902
+{
+	switch(op)
+	{
+	case SOP_KEEP: return v;
+	case SOP_ZERO: return 0;
+	case SOP_REPLACE: return ref;
+	case SOP_INC_CLAMP: return v == 0xFF ? 0xFF : v + 1;
+	case SOP_DEC_CLAMP: return v == 0 ? 0 : v - 1;
+	case SOP_INVERT: return ~v & 0xFF;
+	case SOP_INC_WRAP: return (v + 1) & 0xFF;
+	default: return (v - 1) & 0xFF;
+	}
+}
+
+DEVI bool depth_compare(uint32_t op, float zValue, float Z) // :533-553 (SSE predicate semantics incl. NaN)
+{
+	switch(op)
+	{
+	case CMP_ALWAYS: return true;
+	case CMP_NEVER: return false;
+	case CMP_EQUAL: return zValue == Z;
+	case CMP_NOT_EQUAL: return zValue != Z;
+	case CMP_LESS: return !(zValue <= Z);
+	case CMP_GREATER_OR_EQUAL: return zValue <= Z;
+	case CMP_LESS_OR_EQUAL: return !(zValue < Z);
+	default: return zValue < Z;
+	}
+}
+
+DEVI float blend_factor_rgb(const DrawConst &d, uint32_t f, int ch, const float s[4], const float dst[4]) // :1225-1393
+{
+	switch(f)
+	{
+	case BF_ZERO: return 0.0f;
+	case BF_ONE: return 1.0f;
+	case BF_SRC_COLOR: return s[ch];
+	case BF_ONE_MINUS_SRC_COLOR: return fsub(1.0f, s[ch]);
+	case BF_DST_COLOR: return dst[ch];
+	case BF_ONE_MINUS_DST_COLOR: return fsub(1.0f, dst[ch]);
+	case BF_SRC_ALPHA: return s[3];
+	case BF_ONE_MINUS_SRC_ALPHA: return fsub(1.0f, s[3]);
+	case BF_DST_ALPHA: return dst[3];
+	case BF_ONE_MINUS_DST_ALPHA: return fsub(1.0f, dst[3]);
+	case BF_SRC_ALPHA_SATURATE: return sse_min(fsub(1.0f, dst[3]), s[3]);
+	case BF_CONSTANT_COLOR: return d.blendConstant[ch];
+	case BF_CONSTANT_ALPHA: return d.blendConstant[3];
+	case BF_ONE_MINUS_CONSTANT_COLOR: return fsub(1.0f, d.blendConstant[ch]);
+	case BF_ONE_MINUS_CONSTANT_ALPHA: return fsub(1.0f, d.blendConstant[3]);
+	}
+	return 0.0f;
+}
+
+DEVI float blend_factor_a(const DrawConst &d, uint32_t f, const float s[4], const float dst[4])
+{
+	switch(f)
+	{
+	case BF_ZERO: return 0.0f;
+	case BF_ONE: return 1.0f;
+	case BF_SRC_COLOR: case BF_SRC_ALPHA: return s[3];
+	case BF_ONE_MINUS_SRC_COLOR: case BF_ONE_MINUS_SRC_ALPHA: return fsub(1.0f, s[3]);
+	case BF_DST_COLOR: case BF_DST_ALPHA: return dst[3];
+	case BF_ONE_MINUS_DST_COLOR: case BF_ONE_MINUS_DST_ALPHA: return fsub(1.0f, dst[3]);
+	case BF_SRC_ALPHA_SATURATE: return 1.0f;
+	case BF_CONSTANT_COLOR: case BF_CONSTANT_ALPHA: return d.blendConstant[3];
+	case BF_ONE_MINUS_CONSTANT_COLOR: case BF_ONE_MINUS_CONSTANT_ALPHA: return fsub(1.0f, d.blendConstant[3]);
+	}
+	return 0.0f;
+}
+
+DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1849-1958
+{
+	switch(op)
+	{
+	case KOP_ADD: return fadd(fmul(s, sf), fmul(dd, df));
+	case KOP_SUB: return fsub(fmul(s, sf), fmul(dd, df));
+	case KOP_RSUB: return fsub(fmul(dd, df), fmul(s, sf));
+	case KOP_MIN: return sse_min(s, dd);
+	case KOP_MAX: return sse_max(s, dd);
+	case KOP_SRC: return s;
+	case KOP_DST: return dd;
+	default: return 0.0f;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_tile
+// ------------------------------------------------------------------------------------------------------------------
+#define TILE_THREADS (SWCU_TILE_WARPS * 32)
+#define CAND_QUEUE 64
+
+template<int MS>
+struct TileSmem
+{
+	uint32_t color[MS][SWCU_TILE_H][SWCU_TILE_W];
+	float depth[MS][SWCU_TILE_H][SWCU_TILE_W];
+	unsigned char stencil[MS][SWCU_TILE_H][SWCU_TILE_W];
+	uint32_t cand[SWCU_TILE_WARPS][CAND_QUEUE];
+	int dirty;
+};
+
+// cooperative tile <-> framebuffer copy with 128-bit accesses where the layout allows it
+template<int MS, typename T, bool STORE>
+DEVI void tile_copy(T (*sm)[SWCU_TILE_H][SWCU_TILE_W], unsigned char *base, int pitchB, int sliceB, int tileX, int tileY, int fbW, int fbH)
+{
+	constexpr int ROWB = SWCU_TILE_W * (int)sizeof(T);
+	constexpr int VEC = 16;
+	constexpr int VPR = ROWB / VEC;
+	const bool vecOk = ((size_t)base % VEC == 0) && (pitchB % VEC == 0) && (sliceB % VEC == 0) && ((fbW * (int)sizeof(T)) % VEC == 0);
+	const int x0B = tileX * (int)sizeof(T);
+	if(vecOk)
+	{
+		for(int i = threadIdx.x; i < MS * SWCU_TILE_H * VPR; i += TILE_THREADS)
+		{
+			const int q = i / (SWCU_TILE_H * VPR), r = (i / VPR) % SWCU_TILE_H, c = i % VPR;
+			const int y = tileY + r, xB = x0B + c * VEC;
+			if(y >= fbH || xB >= fbW * (int)sizeof(T)) continue;
+			uint4 *g = (uint4 *)(base + (size_t)q * sliceB + (size_t)y * pitchB + xB);
+			uint4 *s = (uint4 *)((unsigned char *)&sm[q][r][0] + c * VEC);
+			if(STORE) *g = *s; else *s = *g;
+		}
+	}
+	else
+	{
+		for(int i = threadIdx.x; i < MS * SWCU_TILE_H * SWCU_TILE_W; i += TILE_THREADS)
+		{
+			const int q = i / (SWCU_TILE_H * SWCU_TILE_W), r = (i / SWCU_TILE_W) % SWCU_TILE_H, c = i % SWCU_TILE_W;
+			const int y = tileY + r, x = tileX + c;
+			if(y >= fbH || x >= fbW) continue;
+			T *g = (T *)(base + (size_t)q * sliceB + (size_t)y * pitchB) + x;
+			if(STORE) *g = sm[q][r][c]; else sm[q][r][c] = *g;
+		}
+	}
+}
+
+template<int MS>
+__global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ DrawConst d, const uint32_t *tileBegin, const uint32_t *tileEnd, const uint32_t *triList)
+{
+	constexpr int BPC = 4 * MS;        // coverage bits per candidate: 4 pixels x MS samples
+	constexpr int NC = MS == 4 ? 16 : 32; // candidates per pass
+	constexpr int NW = NC * BPC / 32;  // mask words per lane
+	constexpr int CPW = 32 / BPC;      // candidates per word
+
+	__shared__ __align__(16) TileSmem<MS> sm;
+
+	const int tx = d.tileX0 + blockIdx.x, ty = d.tileY0 + blockIdx.y;
+	const int tileId = ty * d.tilesX + tx;
+	uint32_t begin, end;
+	if(d.direct) { begin = 0; end = d.primCount; }
+	else { begin = tileBegin[tileId]; end = tileEnd[tileId]; }
+	if(begin >= end) return;
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int tileX = tx * SWCU_TILE_W, tileY = ty * SWCU_TILE_H;
+	const int rx = tileX + (warp % (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_W; // this warp's region
+	const int ry = tileY + (warp / (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_H;
+	const int qx0 = rx + 2 * (lane & 7), qy0 = ry + 2 * (lane >> 3);               // this lane's quad
+	const int lx0 = qx0 - tileX, ly0 = qy0 - tileY;
+
+	if(threadIdx.x == 0) sm.dirty = 0;
+	// ---- stage the tile ----
+	if(d.colorBuf) tile_copy<MS, uint32_t, false>(sm.color, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	if(d.depthTestActive) tile_copy<MS, float, false>(sm.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	if(d.stencilActive) tile_copy<MS, unsigned char, false>(sm.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	__syncthreads();
+
+	uint32_t *cand = sm.cand[warp];
+	int ncand = 0;
+	uint32_t pos = begin;
+	bool dirty = false;
+	const bool biasOn = d.depthBiasEnable != 0;
+	const bool colorOn = d.colorWriteMask != 0 && d.colorBuf != nullptr;
+
+	while(pos < end || ncand > 0)
+	{
+		// ---- gather candidates whose bounds touch this warp's region (in list order) ----
+		while(ncand < NC && pos < end)
+		{
+			const uint32_t i = pos + lane;
+			bool hit = false;
+			uint32_t tri = 0;
+			if(i < end)
+			{
+				tri = d.direct ? i : __ldg(triList + i);
+				const uint2 h = __ldg((const uint2 *)(d.triRecords + (size_t)tri * d.triStride));
+				const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+				hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
+			}
+			const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+			if(hit) cand[ncand + __popc(ballot & ((1u << lane) - 1))] = tri;
+			ncand += __popc(ballot);
+			pos += 32;
+		}
+		__syncwarp();
+		const int n = min(ncand, NC);
+		if(n == 0) break;
+
+		// ---- coverage bits of my quad for each candidate (QuadRasterizer.cpp:181-206 against the span rows) ----
+		uint32_t m[NW];
+#pragma unroll
+		for(int k = 0; k < NW; k++) m[k] = 0;
+#pragma unroll
+		for(int c = 0; c < NC; c++)
+		{
+			if(c < n)
+			{
+				const uint32_t tri = cand[c];
+				const uint4 h = __ldg((const uint4 *)(d.triRecords + (size_t)tri * d.triStride));
+				const int yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+				uint32_t bits = 0;
+#pragma unroll
+				for(int iy = 0; iy < 2; iy++)
+				{
+					const int y = qy0 + iy;
+					if(y >= yMin && y < yMax)
+					{
+						const uint32_t *sp = d.spans + h.z + (uint32_t)(y - yMin) * MS;
+						uint32_t s[MS];
+						if(MS == 4) { const uint4 t = __ldg((const uint4 *)sp); s[0] = t.x; s[1] = t.y; s[2] = t.z; s[3] = t.w; }
+						else s[0] = __ldg(sp);
+#pragma unroll
+						for(int q = 0; q < MS; q++)
+						{
+							const int L = s[q] & 0xFFFF, R = s[q] >> 16;
+#pragma unroll
+							for(int ix = 0; ix < 2; ix++)
+							{
+								const int x = qx0 + ix;
+								if(x >= L && x < R && ((d.sampleMask >> q) & 1)) bits |= 1u << ((iy * 2 + ix) * MS + q);
+							}
+						}
+					}
+				}
+				m[c / CPW] |= bits << ((c % CPW) * BPC);
+			}
+		}
+
+		// ---- walk my (triangle, pixel, sample) items in order ----
+		uint32_t curTri = 0xFFFFFFFFu;
+		int curPx = -1;
+		float P[36]; // x0 y0 zBias wA wB wC zA zB zC V[nvar][3] (TRI_FLOATS_FIXED + 3*SWCU_MAXV = 33, padded to float4s)
+		uint32_t triFlags = 0;
+		float rgba[4] = { 0, 0, 0, 0 };
+		float xf = 0, yf = 0;
+		LodState lodState;
+		lodState.lod = 0; lodState.ilod = 0; lodState.linear = false; lodState.split = false;
+		for(;;)
+		{
+			int wi = -1;
+			uint32_t wv = 0;
+#pragma unroll
+			for(int k = NW - 1; k >= 0; k--)
+				if(m[k]) { wi = k; wv = m[k]; }
+			if(wi < 0) break;
+			const int b = __ffs(wv) - 1;
+#pragma unroll
+			for(int k = 0; k < NW; k++)
+				if(k == wi) m[k] = wv & (wv - 1);
+			const int idx = wi * 32 + b;
+			const int c = idx / BPC, r = idx % BPC, i = r / MS, q = r % MS;
+			const uint32_t tri = cand[c];
+			const int ix = i & 1, iy = i >> 1;
+			const int x = qx0 + ix, y = qy0 + iy;
+
+			if(tri != curTri)
+			{
+				const unsigned char *rec = d.triRecords + (size_t)tri * d.triStride;
+				triFlags = __ldg((const uint32_t *)rec + 3);
+				const float4 *pf = (const float4 *)(rec + TRI_HEADER_BYTES);
+				const int nf4 = (TRI_FLOATS_FIXED + 3 * d.nvar + 3) / 4;
+#pragma unroll
+				for(int k = 0; k < (TRI_FLOATS_FIXED + 3 * SWCU_MAXV + 3) / 4; k++)
+					if(k < nf4)
+					{
+						const float4 t = __ldg(pf + k);
+						P[4 * k] = t.x; P[4 * k + 1] = t.y; P[4 * k + 2] = t.z; P[4 * k + 3] = t.w;
+					}
+				curTri = tri;
+				curPx = -1;
+				if(d.usesTexture)
+				{
+					// implicit LOD from quad lanes 0,1,2 (helper pixels included), SamplerCore.cpp:1376-1422
+					float uu[3], vv[3];
+#pragma unroll
+					for(int k = 0; k < 3; k++)
+					{
+						const float xk = fsub((float)(qx0 + (k & 1)), P[0]), yk = fsub((float)(qy0 + (k >> 1)), P[1]);
+						const float w = __fmaf_rn(xk, P[3], fadd(P[5], fmul(yk, P[4])));
+						const float rhw = fdiv(1.0f, w);
+						float tc[2];
+#pragma unroll
+						for(int t = 0; t < 2; t++)
+						{
+							const KOperand &o = d.texCoord[t];
+							float val = __uint_as_float(o.value);
+							if(o.kind != OPK_CONST)
+							{
+#pragma unroll
+								for(int kk = 0; kk < SWCU_MAXV; kk++)
+									if(kk == (int)o.value)
+									{
+										const float *V = P + TRI_FLOATS_FIXED + 3 * kk;
+										if((d.flatMask >> kk) & 1) val = V[2];
+										else
+										{
+											val = __fmaf_rn(xk, V[0], fadd(V[2], fmul(yk, V[1])));
+											if(!((d.noPerspMask >> kk) & 1)) val = fmul(val, rhw);
+										}
+									}
+							}
+							tc[t] = val;
+						}
+						uu[k] = tc[0]; vv[k] = tc[1];
+					}
+					lodState = compute_lod(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]);
+				}
+			}
+			if(i != curPx)
+			{
+				// ---- interpolate + run the routed fragment shader for pixel i (PixelRoutine.cpp:196-261, PixelProgram.cpp:138-241) ----
+				curPx = i;
+				xf = fsub((float)x, P[0]);
+				yf = fsub((float)y, P[1]);
+				const float w = __fmaf_rn(xf, P[3], fadd(P[5], fmul(yf, P[4])));
+				const float rhw = fdiv(1.0f, w);
+				float var[SWCU_MAXV];
+#pragma unroll
+				for(int k = 0; k < SWCU_MAXV; k++)
+				{
+					var[k] = 0.0f;
+					if(k < d.nvar)
+					{
+						const float *V = P + TRI_FLOATS_FIXED + 3 * k;
+						if((d.flatMask >> k) & 1) var[k] = V[2];
+						else
+						{
+							float val = __fmaf_rn(xf, V[0], fadd(V[2], fmul(yf, V[1])));
+							if(!((d.noPerspMask >> k) & 1)) val = fmul(val, rhw);
+							var[k] = val;
+						}
+					}
+				}
+				float texel[4] = { 0, 0, 0, 0 };
+				if(d.usesTexture)
+				{
+					float tc[2];
+#pragma unroll
+					for(int t = 0; t < 2; t++)
+					{
+						const KOperand &o = d.texCoord[t];
+						float val = __uint_as_float(o.value);
+						if(o.kind != OPK_CONST)
+						{
+#pragma unroll
+							for(int k = 0; k < SWCU_MAXV; k++)
+								if(k == (int)o.value) val = var[k];
+						}
+						tc[t] = val;
+					}
+					sample_texture(d, lodState, tc[0], tc[1], texel);
+				}
+#pragma unroll
+				for(int ch = 0; ch < 4; ch++)
+				{
+					const KOperand &o = d.fsOut[ch];
+					float val;
+					if(o.kind == OPK_CONST) val = __uint_as_float(o.value);
+					else if(o.kind == OPK_TEXEL)
+					{
+						val = texel[0];
+#pragma unroll
+						for(int k = 1; k < 4; k++)
+							if(k == (int)o.value) val = texel[k];
+					}
+					else
+					{
+						val = var[0];
+#pragma unroll
+						for(int k = 1; k < SWCU_MAXV; k++)
+							if(k == (int)o.value) val = var[k];
+					}
+					rgba[ch] = sse_min(sse_max(val, 0.0f), 1.0f); // PixelProgram::clampColor :286-364
+				}
+			}
+
+			// ---- per-sample: stencil test, depth test, depth write, blend + colour write, stencil write ----
+			const int lx = lx0 + ix, ly = ly0 + iy;
+			bool sPass = true;
+			uint32_t sValue = 0;
+			const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
+			if(d.stencilActive)
+			{
+				sValue = sm.stencil[q][ly][lx];
+				sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
+			}
+			bool zPass = true;
+			float z = 0.0f;
+			if(d.depthTestActive)
+			{
+				float yy = yf, xx = xf;
+				if(MS > 1) { yy = fadd(yy, c_SampleY[q]); xx = fsub(xx, c_SampleX[q]); }
+				z = __fmaf_rn(xx, P[6], fadd(P[8], fmul(yy, P[7])));
+				if(biasOn) z = fadd(z, P[2]);
+				z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
+				zPass = depth_compare(d.depthCompareOp, sm.depth[q][ly][lx], z);
+			}
+			const bool pass = zPass && sPass; // zMask (& sMask); without depth test this is cMask & sMask
+			if(pass)
+			{
+				if(d.depthTestActive && d.depthWriteEnable) { sm.depth[q][ly][lx] = z; dirty = true; }
+				if(colorOn)
+				{
+					uint32_t px = sm.color[q][ly][lx];
+					float o[4];
+					if(d.blendEnable)
+					{
+						float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
+#pragma unroll
+						for(int ch = 0; ch < 4; ch++)
+						{
+							const uint32_t bsel = (px >> (8 * ((d.bgr && ch < 3) ? 2 - ch : ch))) & 0xFF;
+							dst[ch] = fmul((float)(bsel * 257), 1.0f / 0xFFFF);
+						}
+#pragma unroll
+						for(int ch = 0; ch < 3; ch++)
+							o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
+						o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
+					}
+					else { o[0] = rgba[0]; o[1] = rgba[1]; o[2] = rgba[2]; o[3] = rgba[3]; }
+#pragma unroll
+					for(int ch = 0; ch < 4; ch++) // writeColor :1981-1992, :2603-2655
+					{
+						if(!((d.colorWriteMask >> ch) & 1)) continue;
+						const float cl = sse_min(sse_max(o[ch], 0.0f), 1.0f);
+						const uint32_t v = (uint32_t)clampi(round_int(fmul(cl, 255.0f)), 0, 255);
+						const int sh = 8 * ((d.bgr && ch < 3) ? 2 - ch : ch);
+						px = (px & ~(0xFFu << sh)) | (v << sh);
+					}
+					sm.color[q][ly][lx] = px;
+					dirty = true;
+				}
+			}
+			if(d.stencilWrite) // writeStencil :754-817
+			{
+				const uint32_t ref = face.reference & 0xFF;
+				uint32_t nv;
+				if(!sPass) nv = stencil_op(face.failOp, sValue, ref);
+				else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
+				else nv = stencil_op(face.passOp, sValue, ref);
+				const uint32_t wm = face.writeMask & 0xFF;
+				sm.stencil[q][ly][lx] = (unsigned char)((nv & wm) | (sValue & ~wm));
+				dirty = true;
+			}
+		}
+		__syncwarp();
+		// keep the candidates that did not fit this pass
+		const int rest = ncand - n;
+		uint32_t keep0 = 0, keep1 = 0;
+		if(lane < rest) keep0 = cand[n + lane];
+		if(lane + 32 < rest) keep1 = cand[n + lane + 32];
+		__syncwarp();
+		if(lane < rest) cand[lane] = keep0;
+		if(lane + 32 < rest) cand[lane + 32] = keep1;
+		ncand = rest;
+		__syncwarp();
+	}
+
+	if(__any_sync(0xFFFFFFFFu, dirty) && lane == 0) sm.dirty = 1;
+	__syncthreads();
+	if(!sm.dirty) return;
+	if(colorOn) tile_copy<MS, uint32_t, true>(sm.color, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	if(d.depthTestActive && d.depthWriteEnable) tile_copy<MS, float, true>(sm.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	if(d.stencilWrite) tile_copy<MS, unsigned char, true>(sm.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the steps either side of the draw
+// ------------------------------------------------------------------------------------------------------------------
+// Blitter::fastClear (Blitter.cpp:170-325): rectangle fill of every sample slice; bpp 4 or 1
+__global__ void k_clear(unsigned char *base, int pitchB, int sliceB, int bpp, int x0, int y0, int w, int h, int samples, uint32_t value)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if(x >= w || y >= h) return;
+	for(int q = 0; q < samples; q++)
+	{
+		unsigned char *row = base + (size_t)q * sliceB + (size_t)(y0 + y) * pitchB;
+		if(bpp == 4) ((uint32_t *)row)[x0 + x] = value;
+		else row[x0 + x] = (unsigned char)value;
+	}
+}
+
+// Blitter::fastResolve (Blitter.cpp:2079-2205): RGBA8 4x -> 1x, avg(avg(s0,s1),avg(s2,s3)) with pavgb = (a+b+1)>>1
+DEVI uint32_t pavgb4(uint32_t a, uint32_t b) { return __vavgu4(a, b); }
+__global__ void k_resolve4(const unsigned char *src, int srcPitchB, int srcSliceB, unsigned char *dst, int dstPitchB, int w, int h)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if(x >= w || y >= h) return;
+	const size_t o = (size_t)y * srcPitchB + 4 * (size_t)x;
+	const uint32_t s0 = *(const uint32_t *)(src + o), s1 = *(const uint32_t *)(src + o + srcSliceB);
+	const uint32_t s2 = *(const uint32_t *)(src + o + 2 * (size_t)srcSliceB), s3 = *(const uint32_t *)(src + o + 3 * (size_t)srcSliceB);
+	*(uint32_t *)(dst + (size_t)y * dstPitchB + 4 * (size_t)x) = pavgb4(pavgb4(s0, s1), pavgb4(s2, s3));
+}

@@ -1,0 +1,183 @@
+// swcu_internal.h — structures shared by the host side (draw.cu, context.cpp) and the kernels (kernels.cuh).
+//
+// The draw path replaces DrawCall::run and everything below it (reference: src/Device/Renderer.cpp:551-662).
+// Per draw the host folds the pipeline state exactly like sw::Renderer::draw (Renderer.cpp:183-490) into one
+// DrawConst that is passed BY VALUE as a __grid_constant__ kernel parameter; all pointers inside are DEVICE
+// addresses of the registered shadows.
+#pragma once
+
+#include "../../include/swcu.h"
+
+#include <stdint.h>
+
+// ---- Vulkan enum values used on this path (vulkan_core.h) ----
+enum
+{
+	VKF_UNDEFINED = 0,
+	VKF_R8G8B8A8_UNORM = 37,
+	VKF_B8G8R8A8_UNORM = 44,
+	VKF_R32_SFLOAT = 100,
+	VKF_R32G32_SFLOAT = 103,
+	VKF_R32G32B32_SFLOAT = 106,
+	VKF_R32G32B32A32_SFLOAT = 109,
+	VKF_D32_SFLOAT = 126,
+	VKF_S8_UINT = 127,
+};
+enum { TOPO_TRIANGLE_LIST = 3, TOPO_TRIANGLE_STRIP = 4, TOPO_TRIANGLE_FAN = 5 };
+enum { CMP_NEVER, CMP_LESS, CMP_EQUAL, CMP_LESS_OR_EQUAL, CMP_GREATER, CMP_NOT_EQUAL, CMP_GREATER_OR_EQUAL, CMP_ALWAYS };
+enum { SOP_KEEP, SOP_ZERO, SOP_REPLACE, SOP_INC_CLAMP, SOP_DEC_CLAMP, SOP_INVERT, SOP_INC_WRAP, SOP_DEC_WRAP };
+enum
+{
+	BF_ZERO, BF_ONE, BF_SRC_COLOR, BF_ONE_MINUS_SRC_COLOR, BF_DST_COLOR, BF_ONE_MINUS_DST_COLOR,
+	BF_SRC_ALPHA, BF_ONE_MINUS_SRC_ALPHA, BF_DST_ALPHA, BF_ONE_MINUS_DST_ALPHA,
+	BF_CONSTANT_COLOR, BF_ONE_MINUS_CONSTANT_COLOR, BF_CONSTANT_ALPHA, BF_ONE_MINUS_CONSTANT_ALPHA,
+	BF_SRC_ALPHA_SATURATE
+};
+enum { BOP_ADD, BOP_SUBTRACT, BOP_REVERSE_SUBTRACT, BOP_MIN, BOP_MAX,
+	   BOP_ZERO_EXT = 1000148000, BOP_SRC_EXT = 1000148001, BOP_DST_EXT = 1000148002 };
+// compact blend-op codes used inside the kernels
+enum { KOP_ADD, KOP_SUB, KOP_RSUB, KOP_MIN, KOP_MAX, KOP_ZERO, KOP_SRC, KOP_DST };
+enum { CULL_FRONT = 1, CULL_BACK = 2 };
+enum { FRONT_FACE_CCW = 0, FRONT_FACE_CW = 1 };
+enum { FILTER_NEAREST = 0, FILTER_LINEAR = 1 };
+enum { MIPMAP_MODE_NEAREST = 0, MIPMAP_MODE_LINEAR = 1 };
+enum { ADDR_REPEAT = 0, ADDR_MIRRORED_REPEAT = 1, ADDR_CLAMP_TO_EDGE = 2 };
+
+// Device/Clipper.hpp:28-41
+enum { CLIP_RIGHT = 1, CLIP_TOP = 2, CLIP_FAR = 4, CLIP_LEFT = 8, CLIP_BOTTOM = 16, CLIP_NEAR = 32, CLIP_FINITE = 128 };
+#define CLIP_FRUSTUM (CLIP_RIGHT | CLIP_TOP | CLIP_FAR | CLIP_LEFT | CLIP_BOTTOM | CLIP_NEAR)
+
+#define SWCU_MAXV 8          // interpolants (float components) the CUDA path carries per triangle
+#define SWCU_TILE_W 32       // screen tile staged in shared memory by one CTA
+#define SWCU_TILE_H 16
+#define SWCU_REGION_W 16     // sub-tile owned by one warp: 8x4 quads, one 2x2 quad per lane
+#define SWCU_REGION_H 8
+#define SWCU_TILE_WARPS ((SWCU_TILE_W / SWCU_REGION_W) * (SWCU_TILE_H / SWCU_REGION_H))
+#define SWCU_SMALL_ROWS 16   // triangles up to this many rows get their spans from the setup thread itself
+#define SWCU_SMALL_TILES 8   // ... and emit their (tile, triangle) pairs from the emit thread
+#define SWCU_POLY_MAX 10     // 3 + 6 clip planes (+1 wrap slot)
+#define SWCU_INVALID_TILE 0xFFFFFFFFu
+
+// operand kinds after routing (device side)
+enum { OPK_CONST = 0, OPK_INPUT = 1, OPK_TEXEL = 2 };
+
+struct KOperand
+{
+	uint32_t kind;  // OPK_*
+	uint32_t value; // CONST: float bits; INPUT: vertex stage = location*4+component, fragment stage = packed interpolant index; TEXEL: channel
+};
+
+struct KVertexInput
+{
+	const unsigned char *buffer;
+	uint32_t robustnessSize;
+	uint32_t stride;
+	uint32_t ncomp; // 0 = unused -> (0,0,0,1)
+	uint32_t pad;
+};
+
+struct KMip
+{
+	const unsigned char *buffer;
+	uint32_t width, height, pitchP, pad;
+};
+
+struct KStencilFace
+{
+	uint32_t failOp, passOp, depthFailOp, compareOp, compareMask, writeMask, reference, pad;
+};
+
+// One big-triangle work item (triangles taller than SWCU_SMALL_ROWS or wider than SWCU_SMALL_TILES tiles):
+// spans and tile pairs are produced by a CTA instead of the setup thread.
+struct BigTri
+{
+	uint32_t tri;
+	uint32_t spanBase;
+	int32_t n, dir;
+	int32_t yMin, yMax;
+	int32_t pxMin, pxMax;
+	int32_t X[SWCU_POLY_MAX], Y[SWCU_POLY_MAX];
+};
+
+// Per-draw device counters (one struct in device memory, zeroed per draw)
+struct DrawCounters
+{
+	unsigned long long spanCursor; // entries allocated from the span table
+	unsigned long long bigSlots;   // entries appended to the big list
+	uint32_t overflow;             // bit0: span table, bit1: big list
+	uint32_t visible;              // triangles that survived setup
+	unsigned long long pairTotal;  // number of (tile, triangle) pairs, written after the scan
+};
+
+struct DrawConst
+{
+	// ---- DrawData scalars (Renderer.hpp:58-113, Renderer.cpp:300-345) ----
+	float WxF, HxF, X0xF, Y0xF, depthRange, depthNear;
+	int32_t scX0, scX1, scY0, scY1;
+	int32_t ms; // 1 or 4
+	uint32_t sampleMask;
+
+	// ---- input assembly ----
+	const void *indexBuffer;
+	uint32_t indexType, topology, provokingFirst, primCount;
+	int32_t baseVertex;
+	uint32_t vsInputMask; // locations read by the vertex shader
+	KVertexInput input[SWCU_MAX_INPUTS];
+
+	// ---- shader routing (output of the SPIR-V subset translator) ----
+	KOperand vsPos[4];
+	int32_t nvar;                // packed interpolants = fragment inputs actually read
+	KOperand varSrc[SWCU_MAXV];  // vertex-stage operand that produces interpolant k
+	uint32_t flatMask, noPerspMask; // over packed interpolant index
+	KOperand fsOut[4];
+	uint32_t usesTexture;
+	KOperand texCoord[2];
+
+	// ---- setup state ----
+	uint32_t cullMode, frontFace, depthClipEnable;
+	float depthBiasConstant, depthBiasSlope, depthBiasClamp;
+	uint32_t depthBiasEnable;
+
+	// ---- pixel state (PixelProcessor.cpp:74-140, Context.cpp:1090-1312 folded) ----
+	uint32_t depthTestActive, depthWriteEnable, depthCompareOp;
+	uint32_t stencilActive, stencilWrite;
+	KStencilFace front, back;
+	uint32_t blendEnable, srcF, dstF, op, srcFA, dstFA, opA; // op/opA are KOP_*
+	uint32_t colorWriteMask;
+	float blendConstant[4]; // clamped to [0,1] (UNORM target)
+	uint32_t bgr;
+
+	// ---- attachments (device addresses) ----
+	unsigned char *colorBuf, *depthBuf, *stencilBuf;
+	int32_t colorPitchB, colorSliceB, depthPitchB, depthSliceB, stencilPitchB, stencilSliceB;
+	int32_t fbWidth, fbHeight;
+
+	// ---- sampled image (SamplerCore state, SpirvShaderSampling.cpp:49-128) ----
+	KMip mip[SWCU_MIPMAP_LEVELS];
+	uint32_t texLevels;
+	uint32_t magFilter, minFilter, mipmapMode, addressU, addressV;
+	float mipLodBias, minLod, maxLod;
+
+	// ---- work buffers ----
+	unsigned char *triRecords; // primCount records of triStride bytes
+	uint32_t triStride;
+	uint32_t *spans;           // {u16 left, u16 right} per (row, sample)
+	unsigned long long spanCapacity;
+	BigTri *bigList;
+	uint32_t bigCapacity;
+	uint32_t *tileCount;       // per triangle: number of (tile, triangle) pairs it will emit
+	DrawCounters *counters;
+	int32_t tilesX, tilesY;    // tile grid of the framebuffer
+	int32_t tileX0, tileY0, tileX1, tileY1; // tile range touched by the scissor (exclusive upper)
+	uint32_t direct;           // 1: no binning, every tile CTA walks all triangles
+};
+
+// TriRecord layout (triStride bytes, 16-byte aligned):
+//   uint16 pxMin, pxMax, yMin, yMax;   pixel bounds (x exclusive upper, y exclusive upper); yMin>=yMax => invisible
+//   uint32 spanBase;                   first span entry: index = spanBase + (y - yMin) * ms + q
+//   uint32 flags;                      bit0 = clockwiseMask (front facing), Primitive.hpp:60
+//   float  x0, y0, zBias, wA, wB, wC, zA, zB, zC;   Primitive::{x0,y0,zBias,w,z}
+//   float  V[nvar][3];                 Primitive::V planes {A,B,C}
+#define TRI_HEADER_BYTES 16
+#define TRI_FLOATS_FIXED 9
+static inline uint32_t swcu_tri_stride(int nvar) { return (uint32_t)((TRI_HEADER_BYTES + 4 * (TRI_FLOATS_FIXED + 3 * nvar) + 15) & ~15); }
