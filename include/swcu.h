@@ -221,6 +221,9 @@ const char *swcu_last_error(swcu_ctx *ctx); /* ctx may be NULL: last error of a 
 
 /* ---- memory: device shadows of host ranges (stands in for vk::DeviceMemory, src/Vulkan/VkDeviceMemory.cpp) ---- */
 int swcu_mem_register(swcu_ctx *ctx, const void *host_base, size_t bytes);
+/* Adopt an existing DEVICE allocation (e.g. an NCCL buffer owned by the caller): pointers into it are used as they are,
+ * nothing is allocated, copied or freed by the library.  Unregister with swcu_mem_unregister(ctx, device_base). */
+int swcu_mem_register_device(swcu_ctx *ctx, void *device_base, size_t bytes);
 int swcu_mem_unregister(swcu_ctx *ctx, const void *host_base);
 int swcu_mem_upload(swcu_ctx *ctx, const void *host_ptr, size_t bytes);   /* host -> shadow, async on the context stream */
 int swcu_mem_download(swcu_ctx *ctx, void *host_ptr, size_t bytes);       /* shadow -> host, async; complete after swcu_sync */

@@ -9,7 +9,7 @@
 // The ICD is dlopen'ed and every entry point is resolved through the exported vkGetInstanceProcAddr
 // (like tests/VulkanWrapper/VulkanTester.cpp:201-231), so no Vulkan loader is needed.
 //
-// usage: refrender <libvk_swiftshader.so> <scene.bin> <out.bin> [--time N]
+// usage: refrender <libvk_swiftshader.so> <scene.bin> <out.bin> [--time N] [--warmup W]
 #define VK_NO_PROTOTYPES
 #include <vulkan/vulkan.h>
 
@@ -110,9 +110,10 @@ int main(int argc, char **argv)
 		fprintf(stderr, "usage: refrender <icd.so> <scene.bin> <out.bin> [--time N]\n");
 		return 1;
 	}
-	int timing = 0;
+	int timing = 0, warmup = 1;
 	for(int i = 4; i + 1 < argc; i++)
 		if(!strcmp(argv[i], "--time")) timing = atoi(argv[i + 1]);
+		else if(!strcmp(argv[i], "--warmup")) warmup = atoi(argv[i + 1]);
 
 	// ---- scene ----
 	FILE *fi = fopen(argv[2], "rb");
@@ -477,8 +478,11 @@ int main(int argc, char **argv)
 	{
 		record(cmd[1], 1, false);
 		si.pCommandBuffers = &cmd[1];
-		CHECK(vkQueueSubmit(queue, 1, &si, VK_NULL_HANDLE)); // warm-up: JIT of the LOAD-pass routines
-		CHECK(vkQueueWaitIdle(queue));
+		for(int i = 0; i < (warmup < 1 ? 1 : warmup); i++) // warm-up: JIT of the LOAD-pass routines
+		{
+			CHECK(vkQueueSubmit(queue, 1, &si, VK_NULL_HANDLE));
+			CHECK(vkQueueWaitIdle(queue));
+		}
 		std::vector<double> ts;
 		for(int i = 0; i < timing; i++)
 		{

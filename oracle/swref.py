@@ -107,6 +107,9 @@ SHADER_SPECS = {
     # outColor(loc0).rgb = inColor(loc1).rgb
     "vs_pos3_col3": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)],
                                 {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2)}),
+    # outColor(loc0) = inColor(loc1) (vec4)
+    "vs_pos3_col4": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)],
+                                {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2), 3: _inp(1, 3)}),
     # outTexCoord(loc0).xy = inTexCoord(loc1).xy
     "vs_pos3_uv2": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)], {0: _inp(1, 0), 1: _inp(1, 1)}),
     # gl_Position = inPos (vec4); outCol = inCol (vec4)
@@ -153,7 +156,7 @@ def reference_available() -> bool:
     return os.path.exists(REF_ICD) and os.path.exists(REFRENDER)
 
 
-def render_reference(scene: Scene, time_frames: int = 0, threads: int | None = None) -> dict:
+def render_reference(scene: Scene, time_frames: int = 0, threads: int | None = None, warmup: int = 1) -> dict:
     """Render the scene with the REFERENCE ICD (oracle/_ref).  Returns colour (resolved when multisampled),
     depth/stencil when single-sampled, and the timing JSON when time_frames > 0."""
     if not reference_available():
@@ -166,7 +169,7 @@ def render_reference(scene: Scene, time_frames: int = 0, threads: int | None = N
                 f.write(f"[Processor]\nThreadCount={threads}\n")
         cmd = [REFRENDER, REF_ICD, sp, op]
         if time_frames:
-            cmd += ["--time", str(time_frames)]
+            cmd += ["--time", str(time_frames), "--warmup", str(warmup)]
         res = subprocess.run(cmd, cwd=td, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"refrender failed ({res.returncode}): {res.stderr[-2000:]}")

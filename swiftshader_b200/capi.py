@@ -98,7 +98,7 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "swcu_create", "swcu_destroy", "swcu_last_error",
-    "swcu_mem_register", "swcu_mem_unregister", "swcu_mem_upload", "swcu_mem_download", "swcu_mem_device_ptr",
+    "swcu_mem_register", "swcu_mem_register_device", "swcu_mem_unregister", "swcu_mem_upload", "swcu_mem_download", "swcu_mem_device_ptr",
     "swcu_draw", "swcu_sync", "swcu_clear", "swcu_resolve", "swcu_shader_translate",
     "swcu_set_stream", "swcu_timer_begin", "swcu_timer_end", "swcu_get_stats", "swcu_reset_stats",
     "swcu_set_profiling", "swcu_last_draw_kernels", "swcu_set_option", "swcu_version",
@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
     L.swcu_last_error.argtypes = [vp]
     L.swcu_last_error.restype = C.c_char_p
     L.swcu_mem_register.argtypes = [vp, vp, sz]
+    L.swcu_mem_register_device.argtypes = [vp, vp, sz]
     L.swcu_mem_unregister.argtypes = [vp, vp]
     L.swcu_mem_upload.argtypes = [vp, vp, sz]
     L.swcu_mem_download.argtypes = [vp, vp, sz]

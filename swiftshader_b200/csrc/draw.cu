@@ -28,6 +28,7 @@ struct Shadow
 	size_t bytes = 0;
 	unsigned char *dev = nullptr;
 	bool pinned = false;
+	bool external = false; // caller-owned device memory (swcu_mem_register_device): identity mapping
 };
 
 struct KernelTime
@@ -130,7 +131,7 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 	for(auto &kv : ctx->mem)
 	{
 		if(kv.second.pinned) cudaHostUnregister((void *)kv.second.host);
-		cudaFree(kv.second.dev);
+		if(!kv.second.external) cudaFree(kv.second.dev);
 	}
 	DevBuf *bufs[] = { &ctx->triRecords, &ctx->spans, &ctx->bigList, &ctx->tileCount, &ctx->pairOffset, &ctx->keys, &ctx->vals,
 		               &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->counters };
@@ -193,6 +194,25 @@ extern "C" int swcu_mem_register(swcu_ctx *ctx, const void *host_base, size_t by
 	return SWCU_OK;
 }
 
+extern "C" int swcu_mem_register_device(swcu_ctx *ctx, void *device_base, size_t bytes)
+{
+	if(!ctx || !device_base || !bytes) return fail(ctx, SWCU_E_INVALID, "swcu_mem_register_device: bad arguments");
+	const uintptr_t a = (uintptr_t)device_base;
+	auto it = ctx->mem.upper_bound(a + bytes - 1);
+	if(it != ctx->mem.begin())
+	{
+		--it;
+		if(it->second.host + it->second.bytes > a) return fail(ctx, SWCU_E_INVALID, "swcu_mem_register_device: range overlaps a registered range");
+	}
+	Shadow s;
+	s.host = a;
+	s.bytes = bytes;
+	s.dev = (unsigned char *)device_base;
+	s.external = true;
+	ctx->mem[a] = s;
+	return SWCU_OK;
+}
+
 extern "C" int swcu_mem_unregister(swcu_ctx *ctx, const void *host_base)
 {
 	if(!ctx) return SWCU_E_INVALID;
@@ -201,7 +221,7 @@ extern "C" int swcu_mem_unregister(swcu_ctx *ctx, const void *host_base)
 	CU(cudaSetDevice(ctx->device));
 	CU(cudaStreamSynchronize(ctx->stream));
 	if(it->second.pinned) cudaHostUnregister((void *)it->second.host);
-	cudaFree(it->second.dev);
+	if(!it->second.external) cudaFree(it->second.dev);
 	ctx->mem.erase(it);
 	return SWCU_OK;
 }
@@ -211,6 +231,7 @@ extern "C" int swcu_mem_upload(swcu_ctx *ctx, const void *host_ptr, size_t bytes
 	if(!ctx) return SWCU_E_INVALID;
 	unsigned char *d = dev_ptr(ctx, host_ptr, bytes);
 	if(!d) return fail(ctx, SWCU_E_INVALID, "swcu_mem_upload: [%p,+%zu) is not inside a registered range", host_ptr, bytes);
+	if(d == (const unsigned char *)host_ptr) return fail(ctx, SWCU_E_INVALID, "swcu_mem_upload: %p is caller-owned device memory", host_ptr);
 	CU(cudaSetDevice(ctx->device));
 	CU(cudaMemcpyAsync(d, host_ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	ctx->stats.h2dBytes += bytes;
@@ -222,6 +243,7 @@ extern "C" int swcu_mem_download(swcu_ctx *ctx, void *host_ptr, size_t bytes)
 	if(!ctx) return SWCU_E_INVALID;
 	unsigned char *d = dev_ptr(ctx, host_ptr, bytes);
 	if(!d) return fail(ctx, SWCU_E_INVALID, "swcu_mem_download: [%p,+%zu) is not inside a registered range", host_ptr, bytes);
+	if(d == (unsigned char *)host_ptr) return fail(ctx, SWCU_E_INVALID, "swcu_mem_download: %p is caller-owned device memory", host_ptr);
 	CU(cudaSetDevice(ctx->device));
 	CU(cudaMemcpyAsync(host_ptr, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	ctx->stats.d2hBytes += bytes;

@@ -382,6 +382,24 @@ class Device:
     def draw(self, desc: capi.DrawDesc):
         self.check(self.lib.swcu_draw(self.ctx, C.byref(desc)))
 
+    def upload(self, arr: np.ndarray):
+        self.check(self.lib.swcu_mem_upload(self.ctx, arr.ctypes.data, arr.nbytes))
+
+    def set_stream(self, cuda_stream: int):
+        self.check(self.lib.swcu_set_stream(self.ctx, cuda_stream))
+
+    def reset_stats(self):
+        self.check(self.lib.swcu_reset_stats(self.ctx))
+
+    def set_profiling(self, on: bool):
+        self.check(self.lib.swcu_set_profiling(self.ctx, int(on)))
+
+    def last_draw_kernels(self) -> list:
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = self.lib.swcu_last_draw_kernels(self.ctx, names, ms, 64)
+        return [(names[i].decode(), float(ms[i])) for i in range(max(n, 0))]
+
     def set_option(self, name: str, value: int):
         self.check(self.lib.swcu_set_option(self.ctx, name.encode(), value))
 
@@ -424,3 +442,98 @@ class Device:
         for b in bufs:
             self.unregister(b)
         return att
+
+
+class Frame:
+    """One scene kept resident on a Device: buffers are registered once (device shadows allocated, host side page-locked),
+    then ``upload_inputs`` / ``clear`` / ``draw`` / ``resolve`` / ``download`` can be issued any number of times.  This is
+    the steady-state shape of a render loop behind ``sw::Renderer::draw`` (inputs uploaded at vkQueueSubmit, attachments
+    resident across frames)."""
+
+    def __init__(self, dev: Device, scene: Scene, render_area: Optional[tuple] = None):
+        self.dev, self.scene = dev, scene
+        self.att = scene.alloc_attachments()
+        H2, W = scene.padded_height(), scene.width
+        self.resolved = np.zeros((1, H2, W, 4), dtype=np.uint8) if scene.samples > 1 else None
+        self.keep: list = []
+        self.inputs: list = []
+        self.descs = [scene.build_desc(dr, self.att, self.keep, render_area, self.inputs) for dr in scene.draws]
+        seen = set()
+        self.inputs = [b for b in self.inputs if not (b.ctypes.data in seen or seen.add(b.ctypes.data))]
+        self.bufs = list(self.att.values()) + self.inputs + ([self.resolved] if self.resolved is not None else [])
+        for b in self.bufs:
+            dev.register(b, upload=False)
+        self.render_area = render_area or (0, 0, scene.width, scene.height)
+
+    def input_bytes(self) -> int:
+        return int(sum(b.nbytes for b in self.inputs))
+
+    def upload_inputs(self):
+        for b in self.inputs:
+            self.dev.upload(b)
+
+    def upload_attachments(self):
+        for b in self.att.values():
+            self.dev.upload(b)
+
+    def _attachment(self, key: str) -> capi.Attachment:
+        H2, W, sc = self.scene.padded_height(), self.scene.width, self.scene
+        if key == "color":
+            return capi.Attachment(self.att["color"].ctypes.data, sc.colorFormat, W * 4, H2 * W * 4, W, sc.height, 0)
+        if key == "depth":
+            return capi.Attachment(self.att["depth"].ctypes.data, FMT_D32_SFLOAT, W * 4, H2 * W * 4, W, sc.height, 0)
+        if key == "stencil":
+            return capi.Attachment(self.att["stencil"].ctypes.data, FMT_S8_UINT, W, H2 * W, W, sc.height, 0)
+        return capi.Attachment(self.resolved.ctypes.data, sc.colorFormat, W * 4, H2 * W * 4, W, sc.height, 0)
+
+    def clear(self):
+        """Attachment load-op CLEAR on the device (Blitter::fastClear), whole framebuffer."""
+        sc = self.scene
+        area = capi.Rect(0, 0, sc.width, sc.height)
+        col = sc.clear_color_bytes().copy()
+        a = self._attachment("color")
+        self.dev.check(self.dev.lib.swcu_clear(self.dev.ctx, C.byref(a), sc.samples, C.byref(area), col.ctypes.data))
+        if "depth" in self.att:
+            z = np.array([sc.clearDepth], dtype=np.float32)
+            a = self._attachment("depth")
+            self.dev.check(self.dev.lib.swcu_clear(self.dev.ctx, C.byref(a), sc.samples, C.byref(area), z.ctypes.data))
+        if "stencil" in self.att:
+            s = np.array([sc.clearStencil & 0xFF, 0, 0, 0], dtype=np.uint8)
+            a = self._attachment("stencil")
+            self.dev.check(self.dev.lib.swcu_clear(self.dev.ctx, C.byref(a), sc.samples, C.byref(area), s.ctypes.data))
+
+    def draw(self):
+        for d in self.descs:
+            self.dev.draw(d)
+
+    def resolve(self):
+        if self.resolved is None:
+            return
+        src, dst = self._attachment("color"), self._attachment("resolved")
+        self.dev.check(self.dev.lib.swcu_resolve(self.dev.ctx, C.byref(src), self.scene.samples, C.byref(dst)))
+
+    def final_image(self) -> np.ndarray:
+        """Host array that holds the presentable 1x image after download_final()."""
+        return self.resolved[0] if self.resolved is not None else self.att["color"][0]
+
+    def download_final(self, rows: Optional[tuple] = None):
+        img = self.final_image()
+        if rows is None:
+            self.dev.download(img)
+        else:
+            self.dev.download(img[rows[0]:rows[1]])
+
+    def download_all(self):
+        for b in self.att.values():
+            self.dev.download(b)
+        if self.resolved is not None:
+            self.dev.download(self.resolved)
+
+    def final_device_ptr(self) -> int:
+        return self.dev.device_ptr(self.final_image())
+
+    def close(self):
+        self.dev.sync()
+        for b in self.bufs:
+            self.dev.unregister(b)
+        self.bufs = []

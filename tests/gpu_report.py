@@ -34,8 +34,6 @@ def main():
                 entry = {}
                 for k in want:
                     a, b = got[k], want[k]
-                    diff = np.argwhere(a.view(np.uint8).reshape(a.shape + (-1,)).reshape(a.shape[0], a.shape[1], a.shape[2], -1).any(axis=-1)
-                                       != b.view(np.uint8).reshape(a.shape[0], a.shape[1], a.shape[2], -1).any(axis=-1)) if False else None
                     ne = a.view(np.uint8).reshape(a.shape[0], a.shape[1], a.shape[2], -1) != b.view(np.uint8).reshape(a.shape[0], a.shape[1], a.shape[2], -1)
                     px = np.argwhere(ne.any(axis=-1))
                     if len(px):

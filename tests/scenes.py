@@ -314,6 +314,10 @@ def all_cases():
         yield f"benchmark_{w}_720p", benchmark(w)
     yield "benchmark_0_720p_msaa", benchmark(0, samples=4)
     yield "benchmark_2_720p_msaa", benchmark(2, samples=4)
+    # reduced-size instances of the five BASELINE.json workloads (same generators and state as bench.py runs at full size)
+    from swiftshader_b200 import workloads
+    for w in ("c1", "c2", "c3", "c4", "c5"):
+        yield f"workload_{w}", workloads.small(w).scene
 
 
 def outputs(scene: Scene, att: dict, resolved=None) -> dict:

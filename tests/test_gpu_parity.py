@@ -24,8 +24,21 @@ def sha(a):
 
 
 def cuda_outputs(device, scene):
-    att = device.render(scene)
-    res = device.resolve(scene, att) if scene.samples > 1 else None
+    """Host-cleared attachments uploaded to the device shadows, every draw through swcu_draw, the end-of-pass resolve on
+    the device, everything read back."""
+    from swiftshader_b200.scene import Frame
+    fr = Frame(device, scene)
+    try:
+        fr.upload_inputs()
+        fr.upload_attachments()
+        fr.draw()
+        fr.resolve()
+        fr.download_all()
+        device.sync()
+        att = {k: v.copy() for k, v in fr.att.items()}
+        res = fr.resolved[0].copy() if fr.resolved is not None else None
+    finally:
+        fr.close()
     return att, scenes.outputs(scene, att, res)
 
 
