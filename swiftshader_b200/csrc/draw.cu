@@ -513,31 +513,34 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	// ---- shader routing ----
 	auto kopd = [](const swcu_shader_operand &o) { KOperand k; k.kind = o.kind == SWCU_SRC_CONST ? OPK_CONST : (o.kind == SWCU_SRC_INPUT ? OPK_INPUT : OPK_TEXEL); k.value = o.value; return k; };
 	for(int k = 0; k < 4; k++) d.vsPos[k] = kopd(vs.position[k]);
-	int packed[SWCU_MAX_VARYING_COMPONENTS];
-	d.nvar = 0;
-	for(int c = 0; c < SWCU_MAX_VARYING_COMPONENTS; c++)
-	{
-		packed[c] = -1;
-		if(!((fs.inputMask >> c) & 1)) continue;
-		if(d.nvar >= SWCU_MAXV) return fail(ctx, SWCU_E_UNSUPPORTED, "fragment shader reads more than %d interpolated components", SWCU_MAXV);
-		packed[c] = d.nvar;
-		if((vs.outputMask >> c) & 1) d.varSrc[d.nvar] = kopd(vs.output[c]);
-		else { d.varSrc[d.nvar].kind = OPK_CONST; d.varSrc[d.nvar].value = 0; }
-		if((fs.flatMask >> c) & 1) d.flatMask |= 1u << d.nvar;
-		if((fs.noPerspectiveMask >> c) & 1) d.noPerspMask |= 1u << d.nvar;
-		d.nvar++;
-	}
-	auto fsop = [&](const swcu_shader_operand &o) { KOperand k = kopd(o); if(k.kind == OPK_INPUT) k.value = (uint32_t)packed[o.value]; return k; };
+	// a fragment-stage operand that reads an interpolated input becomes a plane slot fed by the vertex stage
+	auto slot_from = [&](const swcu_shader_operand &o, int slot) {
+		if(o.kind == SWCU_SRC_CONST) { d.slotSrc[slot].kind = OPK_CONST; d.slotSrc[slot].value = o.value; d.slotMode[slot] = IM_FLAT; return; }
+		const uint32_t c = o.value; // location*4 + component of the fragment input
+		if((vs.outputMask >> c) & 1) d.slotSrc[slot] = kopd(vs.output[c]);
+		else { d.slotSrc[slot].kind = OPK_CONST; d.slotSrc[slot].value = 0; } // never written by the vertex stage
+		d.slotMode[slot] = ((fs.flatMask >> c) & 1) ? IM_FLAT : (((fs.noPerspectiveMask >> c) & 1) ? IM_NOPERSP : IM_PERSP);
+	};
+	bool anySlot = false;
 	for(int ch = 0; ch < 4; ch++)
 	{
-		if((fs.outputMask >> ch) & 1) d.fsOut[ch] = fsop(fs.output[ch]);
-		else { d.fsOut[ch].kind = OPK_CONST; d.fsOut[ch].value = 0; }
+		d.slotSrc[ch].kind = OPK_CONST; d.slotSrc[ch].value = 0; d.slotMode[ch] = IM_FLAT;
+		const swcu_shader_operand &o = fs.output[ch];
+		if(!((fs.outputMask >> ch) & 1)) { d.chanKind[ch] = CK_CONST; d.chanValue[ch] = 0; }
+		else if(o.kind == SWCU_SRC_CONST) { d.chanKind[ch] = CK_CONST; d.chanValue[ch] = o.value; }
+		else if(o.kind == SWCU_SRC_TEXEL) { d.chanKind[ch] = CK_TEXEL; d.chanValue[ch] = o.value & 3; }
+		else { d.chanKind[ch] = CK_SLOT; d.chanValue[ch] = (uint32_t)ch; slot_from(o, ch); anySlot = true; }
 	}
+	d.shaderClass = fs.usesTexture ? (anySlot ? SH_GENERIC : SH_TEX) : (anySlot ? SH_VARY : SH_CONST);
+	d.nslots = d.shaderClass == SH_CONST ? 0 : d.shaderClass == SH_VARY ? 4 : d.shaderClass == SH_TEX ? 2 : 6;
+	d.uvSlot = d.shaderClass == SH_TEX ? 0 : 4;
 	d.usesTexture = fs.usesTexture;
 	if(fs.usesTexture)
 	{
-		d.texCoord[0] = fsop(fs.texCoord[0]);
-		d.texCoord[1] = fsop(fs.texCoord[1]);
+		if(d.shaderClass == SH_TEX) // slots [0,4) do not exist in this class: move the (unused) colour slots out of the way
+			for(int k = 0; k < 2; k++) { d.slotSrc[k].kind = OPK_CONST; d.slotSrc[k].value = 0; d.slotMode[k] = IM_FLAT; }
+		slot_from(fs.texCoord[0], d.uvSlot);
+		slot_from(fs.texCoord[1], d.uvSlot + 1);
 		const swcu_sampled_image *t = nullptr;
 		for(uint32_t s = 0; s < desc->sampledImageCount && s < SWCU_MAX_SAMPLED_IMAGES; s++)
 			if(desc->sampledImage[s].set == fs.textureSet && desc->sampledImage[s].binding == fs.textureBinding) t = &desc->sampledImage[s];
@@ -604,6 +607,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		}
 		for(int k = 0; k < 4; k++) d.blendConstant[k] = clamp01(desc->blendConstants[k]);
 		d.bgr = desc->color.format == VKF_B8G8R8A8_UNORM;
+		d.blendClass = !d.blendEnable ? BL_OFF : ((d.srcF == BF_SRC_ALPHA && d.dstF == BF_ONE_MINUS_SRC_ALPHA && d.op == KOP_ADD && d.opA == KOP_SRC && d.colorWriteMask == 0xF) ? BL_SRC_ALPHA : BL_GENERIC);
 	}
 
 	// ---- attachments ----
@@ -629,7 +633,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	d.tilesY = (d.fbHeight + SWCU_TILE_H - 1) / SWCU_TILE_H;
 	d.tileX0 = d.scX0 / SWCU_TILE_W; d.tileY0 = d.scY0 / SWCU_TILE_H;
 	d.tileX1 = (d.scX1 + SWCU_TILE_W - 1) / SWCU_TILE_W; d.tileY1 = (d.scY1 + SWCU_TILE_H - 1) / SWCU_TILE_H;
-	d.triStride = swcu_tri_stride(d.nvar);
+	d.triStride = swcu_tri_stride(d.nslots);
 	return SWCU_OK;
 }
 
@@ -638,11 +642,32 @@ __global__ void k_pair_total(const uint32_t *pairOffset, const uint32_t *tileCou
 	c->pairTotal = (unsigned long long)pairOffset[n - 1] + tileCount[n - 1];
 }
 
+template<int MS, int SH, int BL>
+static void launch_tile3(swcu_ctx *ctx, const DrawConst &d, dim3 grid)
+{
+	LaunchScope ls(ctx, MS == 4 ? "k_tile<4>" : "k_tile<1>");
+	k_tile<MS, SH, BL><<<grid, TILE_THREADS, 0, ctx->stream>>>(d, (const uint32_t *)ctx->tileBegin.p, (const uint32_t *)ctx->tileEnd.p, (const uint32_t *)ctx->vals.p);
+}
+template<int MS, int SH>
+static void launch_tile2(swcu_ctx *ctx, const DrawConst &d, dim3 grid)
+{
+	switch(d.blendClass)
+	{
+	case BL_OFF: launch_tile3<MS, SH, BL_OFF>(ctx, d, grid); break;
+	case BL_SRC_ALPHA: launch_tile3<MS, SH, BL_SRC_ALPHA>(ctx, d, grid); break;
+	default: launch_tile3<MS, SH, BL_GENERIC>(ctx, d, grid); break;
+	}
+}
 template<int MS>
 static void launch_tile(swcu_ctx *ctx, const DrawConst &d, dim3 grid)
 {
-	LaunchScope ls(ctx, MS == 4 ? "k_tile<4>" : "k_tile<1>");
-	k_tile<MS><<<grid, TILE_THREADS, 0, ctx->stream>>>(d, (const uint32_t *)ctx->tileBegin.p, (const uint32_t *)ctx->tileEnd.p, (const uint32_t *)ctx->vals.p);
+	switch(d.shaderClass)
+	{
+	case SH_CONST: launch_tile2<MS, SH_CONST>(ctx, d, grid); break;
+	case SH_VARY: launch_tile2<MS, SH_VARY>(ctx, d, grid); break;
+	case SH_TEX: launch_tile2<MS, SH_TEX>(ctx, d, grid); break;
+	default: launch_tile2<MS, SH_GENERIC>(ctx, d, grid); break;
+	}
 }
 
 extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)

@@ -472,16 +472,17 @@ __global__ void __launch_bounds__(128) k_setup(const __grid_constant__ DrawConst
 	const uint32_t vi0 = i0 == 0 ? idx[0] : (i0 == 1 ? idx[1] : idx[2]);
 	const uint32_t vi1 = i1 == 0 ? idx[0] : (i1 == 1 ? idx[1] : idx[2]);
 	const uint32_t vi2 = i2 == 0 ? idx[0] : (i2 == 1 ? idx[1] : idx[2]);
-	for(int k = 0; k < d.nvar; k++)
+	for(int k = 0; k < d.nslots; k++)
 	{
 		float *P = f + TRI_FLOATS_FIXED + 3 * k;
-		if((d.flatMask >> k) & 1)
+		const uint32_t mode = d.slotMode[k];
+		if(mode == IM_FLAT)
 		{
-			P[0] = 0; P[1] = 0; P[2] = vs_operand(d, d.varSrc[k], idx[0]); // provoking vertex = Triangle.v0
+			P[0] = 0; P[1] = 0; P[2] = vs_operand(d, d.slotSrc[k], idx[0]); // provoking vertex = Triangle.v0 (or a constant)
 			continue;
 		}
-		float a0 = vs_operand(d, d.varSrc[k], vi0), a1 = vs_operand(d, d.varSrc[k], vi1), a2 = vs_operand(d, d.varSrc[k], vi2);
-		if((d.noPerspMask >> k) & 1) { a0 = fmul(a0, w0); a1 = fmul(a1, w1); a2 = fmul(a2, w2); }
+		float a0 = vs_operand(d, d.slotSrc[k], vi0), a1 = vs_operand(d, d.slotSrc[k], vi1), a2 = vs_operand(d, d.slotSrc[k], vi2);
+		if(mode == IM_NOPERSP) { a0 = fmul(a0, w0); a1 = fmul(a1, w1); a2 = fmul(a2, w2); }
 		P[0] = fadd(fadd(fmul(a0, M00), fmul(a1, M10)), fmul(a2, M20));
 		P[1] = fadd(fadd(fmul(a0, M01), fmul(a1, M11)), fmul(a2, M21));
 		P[2] = fadd(fadd(fmul(a0, M02), fmul(a1, 0.0f)), fmul(a2, 0.0f));
@@ -847,18 +848,35 @@ DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_tile
+// k_tile — one CTA per 32x16 screen tile
+//
+//   * the tile's colour / depth / stencil planes live in shared memory for the whole triangle list;
+//   * the list is consumed in chunks: the CTA stages the chunk's triangle records and the span rows that cross the tile
+//     in shared memory with coalesced 128-bit loads (one global round trip per chunk instead of one per pixel);
+//   * every warp owns a 16x8 region, every lane one 2x2 quad of it; a warp ballots the chunk's bounding boxes
+//     against its region, computes per-lane coverage bits (4 pixels x MS samples) from the staged span rows, and each
+//     lane then walks ITS OWN covered (triangle, pixel, sample) items in API order — lanes do not wait for each other's
+//     triangles, which is what keeps small-triangle meshes from serialising on the slowest quad;
+//   * specialised on <samples, fragment shader class, blend class>; depth / stencil state is warp-uniform at run time.
 // ------------------------------------------------------------------------------------------------------------------
 #define TILE_THREADS (SWCU_TILE_WARPS * 32)
-#define CAND_QUEUE 64
 
-template<int MS>
+template<int SH> struct ShaderSlots { static constexpr int N = SH == SH_CONST ? 0 : SH == SH_VARY ? 4 : SH == SH_TEX ? 2 : 6; };
+
+template<int MS, int SH>
 struct TileSmem
 {
+	static constexpr int CH = MS == 4 ? 32 : 64;                                   // triangles staged per chunk
+	static constexpr int NF4 = (TRI_FLOATS_FIXED + 3 * ShaderSlots<SH>::N + 3) / 4; // float4s of plane data per record
 	uint32_t color[MS][SWCU_TILE_H][SWCU_TILE_W];
 	float depth[MS][SWCU_TILE_H][SWCU_TILE_W];
+	uint4 hdr[CH];
+	float4 planes[CH][NF4];
+	uint32_t span[CH][SWCU_TILE_H][MS];
+	unsigned short bits[SWCU_TILE_WARPS][32][32]; // [batch slot][lane]
 	unsigned char stencil[MS][SWCU_TILE_H][SWCU_TILE_W];
-	uint32_t cand[SWCU_TILE_WARPS][CAND_QUEUE];
+	uint32_t tri[CH];
+	unsigned char candIdx[SWCU_TILE_WARPS][32];
 	int dirty;
 };
 
@@ -896,15 +914,24 @@ DEVI void tile_copy(T (*sm)[SWCU_TILE_H][SWCU_TILE_W], unsigned char *base, int 
 	}
 }
 
-template<int MS>
+// P(x, y) of one plane slot: QuadRasterizer::interpolate (QuadRasterizer.cpp:235-250) on top of the row constant
+// D = C + y*B (:158-163, unfused) — MulAdd(x, A, D) is the one fused op — then * rhw for perspective-correct slots.
+DEVI float interp_slot(float A, float B, float C, uint32_t mode, float xf, float yf, float rhw)
+{
+	if(mode == IM_FLAT) return C;
+	float t = __fmaf_rn(xf, A, fadd(C, fmul(yf, B)));
+	if(mode == IM_PERSP) t = fmul(t, rhw);
+	return t;
+}
+
+template<int MS, int SH, int BL>
 __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ DrawConst d, const uint32_t *tileBegin, const uint32_t *tileEnd, const uint32_t *triList)
 {
-	constexpr int BPC = 4 * MS;        // coverage bits per candidate: 4 pixels x MS samples
-	constexpr int NC = MS == 4 ? 16 : 32; // candidates per pass
-	constexpr int NW = NC * BPC / 32;  // mask words per lane
-	constexpr int CPW = 32 / BPC;      // candidates per word
-
-	__shared__ __align__(16) TileSmem<MS> sm;
+	using SM = TileSmem<MS, SH>;
+	constexpr int CH = SM::CH, NF4 = SM::NF4, NSLOT = ShaderSlots<SH>::N;
+	constexpr bool TEX = SH == SH_TEX || SH == SH_GENERIC;
+	constexpr int UV = SH == SH_TEX ? 0 : 4;
+	__shared__ __align__(16) SM sm;
 
 	const int tx = d.tileX0 + blockIdx.x, ty = d.tileY0 + blockIdx.y;
 	const int tileId = ty * d.tilesX + tx;
@@ -921,318 +948,296 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 	const int lx0 = qx0 - tileX, ly0 = qy0 - tileY;
 
 	if(threadIdx.x == 0) sm.dirty = 0;
-	// ---- stage the tile ----
-	if(d.colorBuf) tile_copy<MS, uint32_t, false>(sm.color, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	// ---- stage the tile (made visible by the first chunk barrier) ----
+	const bool colorOn = d.colorWriteMask != 0 && d.colorBuf != nullptr;
+	if(colorOn) tile_copy<MS, uint32_t, false>(sm.color, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 	if(d.depthTestActive) tile_copy<MS, float, false>(sm.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 	if(d.stencilActive) tile_copy<MS, unsigned char, false>(sm.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-	__syncthreads();
 
-	uint32_t *cand = sm.cand[warp];
-	int ncand = 0;
-	uint32_t pos = begin;
 	bool dirty = false;
 	const bool biasOn = d.depthBiasEnable != 0;
-	const bool colorOn = d.colorWriteMask != 0 && d.colorBuf != nullptr;
+	uint32_t wmask32 = 0; // byte lanes of the packed pixel the draw may write
+#pragma unroll
+	for(int ch = 0; ch < 4; ch++)
+		if((d.colorWriteMask >> ch) & 1) wmask32 |= 0xFFu << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
 
-	while(pos < end || ncand > 0)
+	for(uint32_t pos = begin; pos < end; pos += CH)
 	{
-		// ---- gather candidates whose bounds touch this warp's region (in list order) ----
-		while(ncand < NC && pos < end)
+		const int n = (int)min((uint32_t)CH, end - pos);
+		// ---- A: triangle ids of the chunk ----
+		if((int)threadIdx.x < n) sm.tri[threadIdx.x] = d.direct ? pos + threadIdx.x : __ldg(triList + pos + threadIdx.x);
+		__syncthreads();
+		// ---- B: records (header + planes), consecutive threads read consecutive 16-byte pieces of a record ----
+		for(int i = threadIdx.x; i < n * (1 + NF4); i += TILE_THREADS)
 		{
-			const uint32_t i = pos + lane;
+			const int c = i / (1 + NF4), j = i % (1 + NF4);
+			const float4 v = __ldg((const float4 *)(d.triRecords + (size_t)sm.tri[c] * d.triStride) + j);
+			if(j == 0) sm.hdr[c] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+			else sm.planes[c][j - 1] = v;
+		}
+		__syncthreads();
+		// ---- C: the span rows of every chunk triangle that cross this tile (empty span outside the triangle's rows) ----
+		for(int i = threadIdx.x; i < n * SWCU_TILE_H; i += TILE_THREADS)
+		{
+			const int c = i / SWCU_TILE_H, r = i % SWCU_TILE_H;
+			const uint4 h = sm.hdr[c];
+			const int y = tileY + r, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+			const bool in = y >= yMin && y < yMax;
+			const uint32_t *sp = d.spans + h.z + (uint32_t)(y - yMin) * MS;
+			if(MS == 4) *(uint4 *)&sm.span[c][r][0] = in ? __ldg((const uint4 *)sp) : make_uint4(0, 0, 0, 0);
+			else sm.span[c][r][0] = in ? __ldg(sp) : 0u;
+		}
+		__syncthreads();
+
+		// ---- D: per warp: candidates of my region, in list order ----
+		uint32_t mlo, mhi = 0;
+		{
 			bool hit = false;
-			uint32_t tri = 0;
-			if(i < end)
+			if(lane < n)
 			{
-				tri = d.direct ? i : __ldg(triList + i);
-				const uint2 h = __ldg((const uint2 *)(d.triRecords + (size_t)tri * d.triStride));
+				const uint4 h = sm.hdr[lane];
 				const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
 				hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
 			}
-			const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-			if(hit) cand[ncand + __popc(ballot & ((1u << lane) - 1))] = tri;
-			ncand += __popc(ballot);
-			pos += 32;
-		}
-		__syncwarp();
-		const int n = min(ncand, NC);
-		if(n == 0) break;
-
-		// ---- coverage bits of my quad for each candidate (QuadRasterizer.cpp:181-206 against the span rows) ----
-		uint32_t m[NW];
-#pragma unroll
-		for(int k = 0; k < NW; k++) m[k] = 0;
-#pragma unroll
-		for(int c = 0; c < NC; c++)
-		{
-			if(c < n)
+			mlo = __ballot_sync(0xFFFFFFFFu, hit);
+			if(CH > 32)
 			{
-				const uint32_t tri = cand[c];
-				const uint4 h = __ldg((const uint4 *)(d.triRecords + (size_t)tri * d.triStride));
-				const int yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+				hit = false;
+				if(lane + 32 < n)
+				{
+					const uint4 h = sm.hdr[lane + 32];
+					const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+					hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
+				}
+				mhi = __ballot_sync(0xFFFFFFFFu, hit);
+			}
+		}
+		while(mlo | mhi)
+		{
+			// ---- coverage bits of my quad for up to 32 candidates (QuadRasterizer.cpp:181-206 on the staged span rows) ----
+			int nb = 0;
+			while((mlo | mhi) && nb < 32)
+			{
+				int c;
+				if(mlo) { c = __ffs(mlo) - 1; mlo &= mlo - 1; }
+				else { c = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
 				uint32_t bits = 0;
 #pragma unroll
 				for(int iy = 0; iy < 2; iy++)
 				{
-					const int y = qy0 + iy;
-					if(y >= yMin && y < yMax)
+					uint32_t sp[MS];
+					if(MS == 4) { const uint4 t = *(const uint4 *)&sm.span[c][ly0 + iy][0]; sp[0] = t.x; sp[1] = t.y; sp[2] = t.z; sp[3] = t.w; }
+					else sp[0] = sm.span[c][ly0 + iy][0];
+#pragma unroll
+					for(int q = 0; q < MS; q++)
 					{
-						const uint32_t *sp = d.spans + h.z + (uint32_t)(y - yMin) * MS;
-						uint32_t s[MS];
-						if(MS == 4) { const uint4 t = __ldg((const uint4 *)sp); s[0] = t.x; s[1] = t.y; s[2] = t.z; s[3] = t.w; }
-						else s[0] = __ldg(sp);
+						const int L = sp[q] & 0xFFFF, R = sp[q] >> 16;
 #pragma unroll
-						for(int q = 0; q < MS; q++)
+						for(int ix = 0; ix < 2; ix++)
 						{
-							const int L = s[q] & 0xFFFF, R = s[q] >> 16;
-#pragma unroll
-							for(int ix = 0; ix < 2; ix++)
-							{
-								const int x = qx0 + ix;
-								if(x >= L && x < R && ((d.sampleMask >> q) & 1)) bits |= 1u << ((iy * 2 + ix) * MS + q);
-							}
+							const int x = qx0 + ix;
+							if(x >= L && x < R) bits |= 1u << ((iy * 2 + ix) * MS + q);
 						}
 					}
 				}
-				m[c / CPW] |= bits << ((c % CPW) * BPC);
+				if(MS == 4) bits &= d.sampleMask * 0x1111u; // sample q masked out for all four pixels
+				sm.bits[warp][nb][lane] = (unsigned short)bits;
+				if(lane == 0) sm.candIdx[warp][nb] = (unsigned char)c;
+				nb++;
 			}
-		}
+			__syncwarp();
 
-		// ---- walk my (triangle, pixel, sample) items in order ----
-		uint32_t curTri = 0xFFFFFFFFu;
-		int curPx = -1;
-		float P[36]; // x0 y0 zBias wA wB wC zA zB zC V[nvar][3] (TRI_FLOATS_FIXED + 3*SWCU_MAXV = 33, padded to float4s)
-		uint32_t triFlags = 0;
-		float rgba[4] = { 0, 0, 0, 0 };
-		float xf = 0, yf = 0;
-		LodState lodState;
-		lodState.lod = 0; lodState.ilod = 0; lodState.linear = false; lodState.split = false;
-		for(;;)
-		{
-			int wi = -1;
-			uint32_t wv = 0;
-#pragma unroll
-			for(int k = NW - 1; k >= 0; k--)
-				if(m[k]) { wi = k; wv = m[k]; }
-			if(wi < 0) break;
-			const int b = __ffs(wv) - 1;
-#pragma unroll
-			for(int k = 0; k < NW; k++)
-				if(k == wi) m[k] = wv & (wv - 1);
-			const int idx = wi * 32 + b;
-			const int c = idx / BPC, r = idx % BPC, i = r / MS, q = r % MS;
-			const uint32_t tri = cand[c];
-			const int ix = i & 1, iy = i >> 1;
-			const int x = qx0 + ix, y = qy0 + iy;
-
-			if(tri != curTri)
+			// ---- walk my (triangle, pixel, sample) items in order ----
+			int k = -1;
+			uint32_t cur = 0;
+			int curPx = -1;
+			float x0 = 0, y0 = 0, zBias = 0, wA = 0, wB = 0, wC = 0, zA = 0, zB = 0, zC = 0;
+			float S[NSLOT > 0 ? NSLOT : 1][3];
+			uint32_t triFlags = 0;
+			float rgba[4] = { 0, 0, 0, 0 };
+			uint32_t packed = 0;
+			float xf = 0, yf = 0;
+			LodState lodState;
+			lodState.lod = 0; lodState.ilod = 0; lodState.linear = false; lodState.split = false;
+			for(;;)
 			{
-				const unsigned char *rec = d.triRecords + (size_t)tri * d.triStride;
-				triFlags = __ldg((const uint32_t *)rec + 3);
-				const float4 *pf = (const float4 *)(rec + TRI_HEADER_BYTES);
-				const int nf4 = (TRI_FLOATS_FIXED + 3 * d.nvar + 3) / 4;
-#pragma unroll
-				for(int k = 0; k < (TRI_FLOATS_FIXED + 3 * SWCU_MAXV + 3) / 4; k++)
-					if(k < nf4)
-					{
-						const float4 t = __ldg(pf + k);
-						P[4 * k] = t.x; P[4 * k + 1] = t.y; P[4 * k + 2] = t.z; P[4 * k + 3] = t.w;
-					}
-				curTri = tri;
-				curPx = -1;
-				if(d.usesTexture)
+				if(cur == 0)
 				{
-					// implicit LOD from quad lanes 0,1,2 (helper pixels included), SamplerCore.cpp:1376-1422
-					float uu[3], vv[3];
-#pragma unroll
-					for(int k = 0; k < 3; k++)
+					do
 					{
-						const float xk = fsub((float)(qx0 + (k & 1)), P[0]), yk = fsub((float)(qy0 + (k >> 1)), P[1]);
-						const float w = __fmaf_rn(xk, P[3], fadd(P[5], fmul(yk, P[4])));
-						const float rhw = fdiv(1.0f, w);
-						float tc[2];
+						if(++k >= nb) break;
+						cur = sm.bits[warp][k][lane];
+					} while(cur == 0);
+					if(k >= nb) break;
+					// ---- new triangle: planes from the staged record ----
+					const int c = sm.candIdx[warp][k];
+					triFlags = sm.hdr[c].w;
+					float pf[NF4 * 4];
 #pragma unroll
-						for(int t = 0; t < 2; t++)
+					for(int j = 0; j < NF4; j++)
+					{
+						const float4 t = sm.planes[c][j];
+						pf[4 * j] = t.x; pf[4 * j + 1] = t.y; pf[4 * j + 2] = t.z; pf[4 * j + 3] = t.w;
+					}
+					x0 = pf[0]; y0 = pf[1]; zBias = pf[2]; wA = pf[3]; wB = pf[4]; wC = pf[5]; zA = pf[6]; zB = pf[7]; zC = pf[8];
+#pragma unroll
+					for(int s = 0; s < NSLOT; s++) { S[s][0] = pf[9 + 3 * s]; S[s][1] = pf[10 + 3 * s]; S[s][2] = pf[11 + 3 * s]; }
+					curPx = -1;
+					if(TEX)
+					{
+						// implicit LOD from quad lanes 0,1,2 (helper pixels included), SamplerCore.cpp:1376-1422
+						float uu[3], vv[3];
+#pragma unroll
+						for(int t = 0; t < 3; t++)
 						{
-							const KOperand &o = d.texCoord[t];
-							float val = __uint_as_float(o.value);
-							if(o.kind != OPK_CONST)
-							{
-#pragma unroll
-								for(int kk = 0; kk < SWCU_MAXV; kk++)
-									if(kk == (int)o.value)
-									{
-										const float *V = P + TRI_FLOATS_FIXED + 3 * kk;
-										if((d.flatMask >> kk) & 1) val = V[2];
-										else
-										{
-											val = __fmaf_rn(xk, V[0], fadd(V[2], fmul(yk, V[1])));
-											if(!((d.noPerspMask >> kk) & 1)) val = fmul(val, rhw);
-										}
-									}
-							}
-							tc[t] = val;
+							const float xk = fsub((float)(qx0 + (t & 1)), x0), yk = fsub((float)(qy0 + (t >> 1)), y0);
+							const float w = __fmaf_rn(xk, wA, fadd(wC, fmul(yk, wB)));
+							const float rhw = fdiv(1.0f, w);
+							uu[t] = interp_slot(S[UV][0], S[UV][1], S[UV][2], d.slotMode[UV], xk, yk, rhw);
+							vv[t] = interp_slot(S[UV + 1][0], S[UV + 1][1], S[UV + 1][2], d.slotMode[UV + 1], xk, yk, rhw);
 						}
-						uu[k] = tc[0]; vv[k] = tc[1];
+						lodState = compute_lod(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]);
 					}
-					lodState = compute_lod(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]);
 				}
-			}
-			if(i != curPx)
-			{
-				// ---- interpolate + run the routed fragment shader for pixel i (PixelRoutine.cpp:196-261, PixelProgram.cpp:138-241) ----
-				curPx = i;
-				xf = fsub((float)x, P[0]);
-				yf = fsub((float)y, P[1]);
-				const float w = __fmaf_rn(xf, P[3], fadd(P[5], fmul(yf, P[4])));
-				const float rhw = fdiv(1.0f, w);
-				float var[SWCU_MAXV];
-#pragma unroll
-				for(int k = 0; k < SWCU_MAXV; k++)
+				const int b = __ffs(cur) - 1;
+				cur &= cur - 1;
+				const int i = b / MS, q = b % MS;
+				const int ix = i & 1, iy = i >> 1;
+				if(i != curPx)
 				{
-					var[k] = 0.0f;
-					if(k < d.nvar)
+					// ---- interpolate + routed fragment shader for pixel i (PixelRoutine.cpp:196-261, PixelProgram.cpp:138-241) ----
+					curPx = i;
+					xf = fsub((float)(qx0 + ix), x0);
+					yf = fsub((float)(qy0 + iy), y0);
+					float rhw = 1.0f;
+					if(SH != SH_CONST)
 					{
-						const float *V = P + TRI_FLOATS_FIXED + 3 * k;
-						if((d.flatMask >> k) & 1) var[k] = V[2];
+						const float w = __fmaf_rn(xf, wA, fadd(wC, fmul(yf, wB)));
+						rhw = fdiv(1.0f, w);
+					}
+					float texel[4] = { 0, 0, 0, 0 };
+					if(TEX)
+					{
+						const float u = interp_slot(S[UV][0], S[UV][1], S[UV][2], d.slotMode[UV], xf, yf, rhw);
+						const float v = interp_slot(S[UV + 1][0], S[UV + 1][1], S[UV + 1][2], d.slotMode[UV + 1], xf, yf, rhw);
+						sample_texture(d, lodState, u, v, texel);
+					}
+#pragma unroll
+					for(int ch = 0; ch < 4; ch++)
+					{
+						float val;
+						const uint32_t kind = d.chanKind[ch];
+						if(kind == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
+						else if(TEX && kind == CK_TEXEL)
+						{
+							const uint32_t t = d.chanValue[ch];
+							val = t == 0 ? texel[0] : t == 1 ? texel[1] : t == 2 ? texel[2] : texel[3];
+						}
+						else if(SH == SH_VARY || SH == SH_GENERIC) val = interp_slot(S[ch][0], S[ch][1], S[ch][2], d.slotMode[ch], xf, yf, rhw);
+						else val = 0.0f;
+						rgba[ch] = sse_min(sse_max(val, 0.0f), 1.0f); // PixelProgram::clampColor :286-364
+					}
+					if(BL == BL_OFF)
+					{
+						packed = 0;
+#pragma unroll
+						for(int ch = 0; ch < 4; ch++) // writeColor :1981-1992
+						{
+							const uint32_t v = (uint32_t)clampi(round_int(fmul(rgba[ch], 255.0f)), 0, 255);
+							packed |= v << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
+						}
+					}
+				}
+
+				// ---- per-sample: stencil test, depth test, depth write, blend + colour write, stencil write ----
+				const int lx = lx0 + ix, ly = ly0 + iy;
+				bool sPass = true;
+				uint32_t sValue = 0;
+				if(d.stencilActive)
+				{
+					const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
+					sValue = sm.stencil[q][ly][lx];
+					sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
+				}
+				bool zPass = true;
+				float z = 0.0f;
+				if(d.depthTestActive)
+				{
+					float yy = yf, xx = xf;
+					if(MS > 1) { yy = fadd(yy, c_SampleY[q]); xx = fsub(xx, c_SampleX[q]); }
+					z = __fmaf_rn(xx, zA, fadd(zC, fmul(yy, zB)));
+					if(biasOn) z = fadd(z, zBias);
+					z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
+					zPass = depth_compare(d.depthCompareOp, sm.depth[q][ly][lx], z);
+				}
+				if(zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
+				{
+					if(d.depthWriteEnable) { sm.depth[q][ly][lx] = z; dirty = true; }
+					if(colorOn)
+					{
+						uint32_t px = sm.color[q][ly][lx];
+						if(BL == BL_OFF) px = (px & ~wmask32) | (packed & wmask32);
 						else
 						{
-							float val = __fmaf_rn(xf, V[0], fadd(V[2], fmul(yf, V[1])));
-							if(!((d.noPerspMask >> k) & 1)) val = fmul(val, rhw);
-							var[k] = val;
+							float o[4];
+							float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
+#pragma unroll
+							for(int ch = 0; ch < 4; ch++)
+							{
+								const uint32_t bsel = (px >> (8 * ((d.bgr && ch < 3) ? 2 - ch : ch))) & 0xFF;
+								dst[ch] = fmul((float)(bsel * 257), 1.0f / 0xFFFF);
+							}
+							if(BL == BL_SRC_ALPHA)
+							{
+								const float sa = rgba[3], da = fsub(1.0f, rgba[3]);
+#pragma unroll
+								for(int ch = 0; ch < 3; ch++) o[ch] = fadd(fmul(rgba[ch], sa), fmul(dst[ch], da));
+								o[3] = rgba[3];
+							}
+							else
+							{
+#pragma unroll
+								for(int ch = 0; ch < 3; ch++)
+									o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
+								o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
+							}
+							uint32_t pk = 0;
+#pragma unroll
+							for(int ch = 0; ch < 4; ch++) // writeColor :1981-1992, :2603-2655
+							{
+								const float cl = sse_min(sse_max(o[ch], 0.0f), 1.0f);
+								const uint32_t v = (uint32_t)clampi(round_int(fmul(cl, 255.0f)), 0, 255);
+								pk |= v << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
+							}
+							px = (px & ~wmask32) | (pk & wmask32);
 						}
+						sm.color[q][ly][lx] = px;
+						dirty = true;
 					}
 				}
-				float texel[4] = { 0, 0, 0, 0 };
-				if(d.usesTexture)
+				if(d.stencilWrite) // writeStencil :754-817
 				{
-					float tc[2];
-#pragma unroll
-					for(int t = 0; t < 2; t++)
-					{
-						const KOperand &o = d.texCoord[t];
-						float val = __uint_as_float(o.value);
-						if(o.kind != OPK_CONST)
-						{
-#pragma unroll
-							for(int k = 0; k < SWCU_MAXV; k++)
-								if(k == (int)o.value) val = var[k];
-						}
-						tc[t] = val;
-					}
-					sample_texture(d, lodState, tc[0], tc[1], texel);
-				}
-#pragma unroll
-				for(int ch = 0; ch < 4; ch++)
-				{
-					const KOperand &o = d.fsOut[ch];
-					float val;
-					if(o.kind == OPK_CONST) val = __uint_as_float(o.value);
-					else if(o.kind == OPK_TEXEL)
-					{
-						val = texel[0];
-#pragma unroll
-						for(int k = 1; k < 4; k++)
-							if(k == (int)o.value) val = texel[k];
-					}
-					else
-					{
-						val = var[0];
-#pragma unroll
-						for(int k = 1; k < SWCU_MAXV; k++)
-							if(k == (int)o.value) val = var[k];
-					}
-					rgba[ch] = sse_min(sse_max(val, 0.0f), 1.0f); // PixelProgram::clampColor :286-364
-				}
-			}
-
-			// ---- per-sample: stencil test, depth test, depth write, blend + colour write, stencil write ----
-			const int lx = lx0 + ix, ly = ly0 + iy;
-			bool sPass = true;
-			uint32_t sValue = 0;
-			const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
-			if(d.stencilActive)
-			{
-				sValue = sm.stencil[q][ly][lx];
-				sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
-			}
-			bool zPass = true;
-			float z = 0.0f;
-			if(d.depthTestActive)
-			{
-				float yy = yf, xx = xf;
-				if(MS > 1) { yy = fadd(yy, c_SampleY[q]); xx = fsub(xx, c_SampleX[q]); }
-				z = __fmaf_rn(xx, P[6], fadd(P[8], fmul(yy, P[7])));
-				if(biasOn) z = fadd(z, P[2]);
-				z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
-				zPass = depth_compare(d.depthCompareOp, sm.depth[q][ly][lx], z);
-			}
-			const bool pass = zPass && sPass; // zMask (& sMask); without depth test this is cMask & sMask
-			if(pass)
-			{
-				if(d.depthTestActive && d.depthWriteEnable) { sm.depth[q][ly][lx] = z; dirty = true; }
-				if(colorOn)
-				{
-					uint32_t px = sm.color[q][ly][lx];
-					float o[4];
-					if(d.blendEnable)
-					{
-						float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
-#pragma unroll
-						for(int ch = 0; ch < 4; ch++)
-						{
-							const uint32_t bsel = (px >> (8 * ((d.bgr && ch < 3) ? 2 - ch : ch))) & 0xFF;
-							dst[ch] = fmul((float)(bsel * 257), 1.0f / 0xFFFF);
-						}
-#pragma unroll
-						for(int ch = 0; ch < 3; ch++)
-							o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
-						o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
-					}
-					else { o[0] = rgba[0]; o[1] = rgba[1]; o[2] = rgba[2]; o[3] = rgba[3]; }
-#pragma unroll
-					for(int ch = 0; ch < 4; ch++) // writeColor :1981-1992, :2603-2655
-					{
-						if(!((d.colorWriteMask >> ch) & 1)) continue;
-						const float cl = sse_min(sse_max(o[ch], 0.0f), 1.0f);
-						const uint32_t v = (uint32_t)clampi(round_int(fmul(cl, 255.0f)), 0, 255);
-						const int sh = 8 * ((d.bgr && ch < 3) ? 2 - ch : ch);
-						px = (px & ~(0xFFu << sh)) | (v << sh);
-					}
-					sm.color[q][ly][lx] = px;
+					const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
+					const uint32_t ref = face.reference & 0xFF;
+					uint32_t nv;
+					if(!sPass) nv = stencil_op(face.failOp, sValue, ref);
+					else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
+					else nv = stencil_op(face.passOp, sValue, ref);
+					const uint32_t wm = face.writeMask & 0xFF;
+					sm.stencil[q][ly][lx] = (unsigned char)((nv & wm) | (sValue & ~wm));
 					dirty = true;
 				}
 			}
-			if(d.stencilWrite) // writeStencil :754-817
-			{
-				const uint32_t ref = face.reference & 0xFF;
-				uint32_t nv;
-				if(!sPass) nv = stencil_op(face.failOp, sValue, ref);
-				else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
-				else nv = stencil_op(face.passOp, sValue, ref);
-				const uint32_t wm = face.writeMask & 0xFF;
-				sm.stencil[q][ly][lx] = (unsigned char)((nv & wm) | (sValue & ~wm));
-				dirty = true;
-			}
+			__syncwarp();
 		}
-		__syncwarp();
-		// keep the candidates that did not fit this pass
-		const int rest = ncand - n;
-		uint32_t keep0 = 0, keep1 = 0;
-		if(lane < rest) keep0 = cand[n + lane];
-		if(lane + 32 < rest) keep1 = cand[n + lane + 32];
-		__syncwarp();
-		if(lane < rest) cand[lane] = keep0;
-		if(lane + 32 < rest) cand[lane + 32] = keep1;
-		ncand = rest;
-		__syncwarp();
+		__syncthreads(); // the staging buffers are reused by the next chunk
 	}
 
 	if(__any_sync(0xFFFFFFFFu, dirty) && lane == 0) sm.dirty = 1;
 	__syncthreads();
 	if(!sm.dirty) return;
 	if(colorOn) tile_copy<MS, uint32_t, true>(sm.color, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-	if(d.depthTestActive && d.depthWriteEnable) tile_copy<MS, float, true>(sm.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	if(d.depthWriteEnable) tile_copy<MS, float, true>(sm.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 	if(d.stencilWrite) tile_copy<MS, unsigned char, true>(sm.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 }
 

@@ -47,7 +47,7 @@ enum { ADDR_REPEAT = 0, ADDR_MIRRORED_REPEAT = 1, ADDR_CLAMP_TO_EDGE = 2 };
 enum { CLIP_RIGHT = 1, CLIP_TOP = 2, CLIP_FAR = 4, CLIP_LEFT = 8, CLIP_BOTTOM = 16, CLIP_NEAR = 32, CLIP_FINITE = 128 };
 #define CLIP_FRUSTUM (CLIP_RIGHT | CLIP_TOP | CLIP_FAR | CLIP_LEFT | CLIP_BOTTOM | CLIP_NEAR)
 
-#define SWCU_MAXV 8          // interpolants (float components) the CUDA path carries per triangle
+#define SWCU_MAXSLOTS 6      // plane-equation slots per triangle: 4 colour channels + (u, v)
 #define SWCU_TILE_W 32       // screen tile staged in shared memory by one CTA
 #define SWCU_TILE_H 16
 #define SWCU_REGION_W 16     // sub-tile owned by one warp: 8x4 quads, one 2x2 quad per lane
@@ -60,6 +60,13 @@ enum { CLIP_RIGHT = 1, CLIP_TOP = 2, CLIP_FAR = 4, CLIP_LEFT = 8, CLIP_BOTTOM = 
 
 // operand kinds after routing (device side)
 enum { OPK_CONST = 0, OPK_INPUT = 1, OPK_TEXEL = 2 };
+// fragment shader classes the tile kernel is specialised on
+enum { SH_CONST = 0, SH_VARY = 1, SH_TEX = 2, SH_GENERIC = 3 };
+// interpolation mode of a plane slot (SpirvShader.hpp:761-782: Flat / NoPerspective; default = perspective)
+enum { IM_PERSP = 0, IM_NOPERSP = 1, IM_FLAT = 2 };
+enum { CK_CONST = 0, CK_SLOT = 1, CK_TEXEL = 2 };
+// blend classes
+enum { BL_OFF = 0, BL_SRC_ALPHA = 1, BL_GENERIC = 2 };
 
 struct KOperand
 {
@@ -124,14 +131,19 @@ struct DrawConst
 	uint32_t vsInputMask; // locations read by the vertex shader
 	KVertexInput input[SWCU_MAX_INPUTS];
 
-	// ---- shader routing (output of the SPIR-V subset translator) ----
+	// ---- shader routing (output of the SPIR-V subset translator), resolved to per-triangle plane slots ----
+	// The fragment shaders of the subset are pure routing, so k_setup evaluates the vertex-stage operand of every value
+	// the fragment stage consumes and writes one plane equation per SLOT: slots [0,4) are the colour channels of
+	// output 0 (shaderClass VARY/GENERIC), the last two are the texture coordinate (TEX/GENERIC).
 	KOperand vsPos[4];
-	int32_t nvar;                // packed interpolants = fragment inputs actually read
-	KOperand varSrc[SWCU_MAXV];  // vertex-stage operand that produces interpolant k
-	uint32_t flatMask, noPerspMask; // over packed interpolant index
-	KOperand fsOut[4];
+	uint32_t shaderClass;        // SH_*
+	int32_t nslots;
+	KOperand slotSrc[SWCU_MAXSLOTS];  // vertex-stage operand feeding the slot (CONST or INPUT)
+	uint32_t slotMode[SWCU_MAXSLOTS]; // IM_*
+	uint32_t chanKind[4];        // CK_* : where colour channel ch comes from
+	uint32_t chanValue[4];       // CK_CONST: float bits; CK_SLOT: slot index; CK_TEXEL: texel component
 	uint32_t usesTexture;
-	KOperand texCoord[2];
+	int32_t uvSlot;              // first of the two texcoord slots
 
 	// ---- setup state ----
 	uint32_t cullMode, frontFace, depthClipEnable;
@@ -170,6 +182,7 @@ struct DrawConst
 	int32_t tilesX, tilesY;    // tile grid of the framebuffer
 	int32_t tileX0, tileY0, tileX1, tileY1; // tile range touched by the scissor (exclusive upper)
 	uint32_t direct;           // 1: no binning, every tile CTA walks all triangles
+	uint32_t blendClass;       // BL_*
 };
 
 // TriRecord layout (triStride bytes, 16-byte aligned):
@@ -177,7 +190,7 @@ struct DrawConst
 //   uint32 spanBase;                   first span entry: index = spanBase + (y - yMin) * ms + q
 //   uint32 flags;                      bit0 = clockwiseMask (front facing), Primitive.hpp:60
 //   float  x0, y0, zBias, wA, wB, wC, zA, zB, zC;   Primitive::{x0,y0,zBias,w,z}
-//   float  V[nvar][3];                 Primitive::V planes {A,B,C}
+//   float  V[nslots][3];               Primitive::V planes {A,B,C} of the routed slots
 #define TRI_HEADER_BYTES 16
 #define TRI_FLOATS_FIXED 9
-static inline uint32_t swcu_tri_stride(int nvar) { return (uint32_t)((TRI_HEADER_BYTES + 4 * (TRI_FLOATS_FIXED + 3 * nvar) + 15) & ~15); }
+static inline uint32_t swcu_tri_stride(int nslots) { return (uint32_t)((TRI_HEADER_BYTES + 4 * (TRI_FLOATS_FIXED + 3 * nslots) + 15) & ~15); }
