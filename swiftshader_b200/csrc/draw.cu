@@ -485,46 +485,48 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		d.indexBuffer = dev_ptr(ctx, desc->indexBuffer);
 		if(!d.indexBuffer) return fail(ctx, SWCU_E_INVALID, "index buffer %p is not inside a registered range", desc->indexBuffer);
 	}
-	d.vsInputMask = 0;
-	for(int l = 0; l < SWCU_MAX_INPUTS; l++)
-	{
-		if(!(vs.inputMask & (0xFu << (4 * l)))) continue;
+	// vertex-stage scalars: component c of stream l, or a constant (VertexRoutine::readStream, VertexRoutine.cpp:173-245)
+	int vsrcErr = SWCU_OK;
+	auto vsrc = [&](const swcu_shader_operand &o) -> KVSrc {
+		KVSrc k;
+		k.ptr = nullptr; k.stride = 0; k.limit = 0xFFFFFFFFu; k.constant = 0.0f; k.pad = 0;
+		if(o.kind == SWCU_SRC_CONST) { memcpy(&k.constant, &o.value, 4); return k; }
+		const uint32_t l = o.value >> 2, c = o.value & 3;
 		const swcu_vertex_input &in = desc->input[l];
-		KVertexInput &k = d.input[l];
+		uint32_t ncomp;
 		switch(in.format)
 		{
-		case VKF_R32_SFLOAT: k.ncomp = 1; break;
-		case VKF_R32G32_SFLOAT: k.ncomp = 2; break;
-		case VKF_R32G32B32_SFLOAT: k.ncomp = 3; break;
-		case VKF_R32G32B32A32_SFLOAT: k.ncomp = 4; break;
-		case VKF_UNDEFINED: k.ncomp = 0; break;
-		default: return fail(ctx, SWCU_E_UNSUPPORTED, "vertex input %d: format %u unsupported (R32..R32G32B32A32_SFLOAT)", l, in.format);
+		case VKF_R32_SFLOAT: ncomp = 1; break;
+		case VKF_R32G32_SFLOAT: ncomp = 2; break;
+		case VKF_R32G32B32_SFLOAT: ncomp = 3; break;
+		case VKF_R32G32B32A32_SFLOAT: ncomp = 4; break;
+		case VKF_UNDEFINED: ncomp = 0; break;
+		default: vsrcErr = fail(ctx, SWCU_E_UNSUPPORTED, "vertex input %u: format %u unsupported (R32..R32G32B32A32_SFLOAT)", l, in.format); return k;
 		}
-		if(k.ncomp)
-		{
-			k.buffer = dev_ptr(ctx, in.buffer);
-			if(!k.buffer) return fail(ctx, SWCU_E_INVALID, "vertex input %d: buffer %p is not inside a registered range", l, in.buffer);
-			k.robustnessSize = in.robustnessSize;
-			k.stride = in.vertexStride;
-		}
-		d.vsInputMask |= 1u << l;
-	}
+		if(c >= ncomp) { k.constant = c == 3 ? 1.0f : 0.0f; return k; } // missing components read (0,0,0,1)
+		if(in.robustnessSize && in.robustnessSize < ncomp * 4) return k;    // every fetch is out of bounds: 0
+		unsigned char *base = dev_ptr(ctx, in.buffer);
+		if(!base) { vsrcErr = fail(ctx, SWCU_E_INVALID, "vertex input %u: buffer %p is not inside a registered range", l, in.buffer); return k; }
+		k.ptr = base + 4 * c;
+		k.stride = in.vertexStride;
+		k.limit = in.robustnessSize ? in.robustnessSize - ncomp * 4 : 0xFFFFFFFFu;
+		return k;
+	};
 
 	// ---- shader routing ----
-	auto kopd = [](const swcu_shader_operand &o) { KOperand k; k.kind = o.kind == SWCU_SRC_CONST ? OPK_CONST : (o.kind == SWCU_SRC_INPUT ? OPK_INPUT : OPK_TEXEL); k.value = o.value; return k; };
-	for(int k = 0; k < 4; k++) d.vsPos[k] = kopd(vs.position[k]);
+	for(int k = 0; k < 4; k++) d.vsPos[k] = vsrc(vs.position[k]);
+	const swcu_shader_operand opZero = { SWCU_SRC_CONST, 0 };
 	// a fragment-stage operand that reads an interpolated input becomes a plane slot fed by the vertex stage
 	auto slot_from = [&](const swcu_shader_operand &o, int slot) {
-		if(o.kind == SWCU_SRC_CONST) { d.slotSrc[slot].kind = OPK_CONST; d.slotSrc[slot].value = o.value; d.slotMode[slot] = IM_FLAT; return; }
+		if(o.kind == SWCU_SRC_CONST) { d.slotSrc[slot] = vsrc(o); d.slotMode[slot] = IM_FLAT; return; }
 		const uint32_t c = o.value; // location*4 + component of the fragment input
-		if((vs.outputMask >> c) & 1) d.slotSrc[slot] = kopd(vs.output[c]);
-		else { d.slotSrc[slot].kind = OPK_CONST; d.slotSrc[slot].value = 0; } // never written by the vertex stage
+		d.slotSrc[slot] = vsrc(((vs.outputMask >> c) & 1) ? vs.output[c] : opZero); // never written by the vertex stage: 0
 		d.slotMode[slot] = ((fs.flatMask >> c) & 1) ? IM_FLAT : (((fs.noPerspectiveMask >> c) & 1) ? IM_NOPERSP : IM_PERSP);
 	};
 	bool anySlot = false;
 	for(int ch = 0; ch < 4; ch++)
 	{
-		d.slotSrc[ch].kind = OPK_CONST; d.slotSrc[ch].value = 0; d.slotMode[ch] = IM_FLAT;
+		d.slotSrc[ch] = vsrc(opZero); d.slotMode[ch] = IM_FLAT;
 		const swcu_shader_operand &o = fs.output[ch];
 		if(!((fs.outputMask >> ch) & 1)) { d.chanKind[ch] = CK_CONST; d.chanValue[ch] = 0; }
 		else if(o.kind == SWCU_SRC_CONST) { d.chanKind[ch] = CK_CONST; d.chanValue[ch] = o.value; }
@@ -538,7 +540,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	if(fs.usesTexture)
 	{
 		if(d.shaderClass == SH_TEX) // slots [0,4) do not exist in this class: move the (unused) colour slots out of the way
-			for(int k = 0; k < 2; k++) { d.slotSrc[k].kind = OPK_CONST; d.slotSrc[k].value = 0; d.slotMode[k] = IM_FLAT; }
+			for(int k = 0; k < 2; k++) { d.slotSrc[k] = vsrc(opZero); d.slotMode[k] = IM_FLAT; }
 		slot_from(fs.texCoord[0], d.uvSlot);
 		slot_from(fs.texCoord[1], d.uvSlot + 1);
 		const swcu_sampled_image *t = nullptr;
@@ -633,7 +635,8 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	d.tilesY = (d.fbHeight + SWCU_TILE_H - 1) / SWCU_TILE_H;
 	d.tileX0 = d.scX0 / SWCU_TILE_W; d.tileY0 = d.scY0 / SWCU_TILE_H;
 	d.tileX1 = (d.scX1 + SWCU_TILE_W - 1) / SWCU_TILE_W; d.tileY1 = (d.scY1 + SWCU_TILE_H - 1) / SWCU_TILE_H;
-	d.triStride = swcu_tri_stride(d.nslots);
+	d.triStride = swcu_tri_stride(d.nslots, d.ms);
+	if(vsrcErr) return vsrcErr;
 	return SWCU_OK;
 }
 
@@ -713,7 +716,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		CU(cudaMemsetAsync(d.counters, 0, sizeof(DrawCounters), ctx->stream));
 		{
 			LaunchScope ls(ctx, "k_setup");
-			k_setup<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d);
+			k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(d);
 		}
 		if(d.direct) break;
 

@@ -75,25 +75,14 @@ DEVI void triangle_indices(const DrawConst &d, uint32_t i, uint32_t idx[3])
 	}
 }
 
-// VertexRoutine::readStream (VertexRoutine.cpp:173-245) for R32..R32G32B32A32_SFLOAT, one component
-DEVI float read_attr(const DrawConst &d, uint32_t code, uint32_t index)
+// one scalar of the vertex stage: shader constant / format default, or a component of an attribute stream with the
+// robustBufferAccess clamp (VertexRoutine::readStream, VertexRoutine.cpp:173-245; offsets wrap in 32 bits like the reference)
+DEVI float vs_operand(const DrawConst &d, const KVSrc &src, uint32_t index)
 {
-	const KVertexInput &in = d.input[code >> 2];
-	const uint32_t c = code & 3;
-	const float def = c == 3 ? 1.0f : 0.0f;
-	if(c >= in.ncomp) return def;
-	uint32_t offset = (index + (uint32_t)d.baseVertex) * in.stride;
-	if(in.robustnessSize)
-	{
-		uint32_t o = offset < in.robustnessSize ? offset : in.robustnessSize;
-		if(o + in.ncomp * 4 > in.robustnessSize) return 0.0f;
-	}
-	return __ldg((const float *)(in.buffer + offset) + c);
-}
-
-DEVI float vs_operand(const DrawConst &d, const KOperand &op, uint32_t index)
-{
-	return op.kind == OPK_CONST ? __uint_as_float(op.value) : read_attr(d, op.value, index);
+	if(!src.ptr) return src.constant;
+	const uint32_t offset = (index + (uint32_t)d.baseVertex) * src.stride;
+	if(offset > src.limit) return 0.0f;
+	return __ldg((const float *)(src.ptr + offset));
 }
 
 struct VOut
@@ -190,8 +179,10 @@ __device__ __noinline__ int clip_polygon(float4 *P, int n, int flagsOr)
 // spans
 // ------------------------------------------------------------------------------------------------------------------
 // SetupRoutine::edge (SetupRoutine.cpp:550-621), row-stepping form for triangles of a few rows.  Writes the clamped x
-// of every row of the edge inside [rowMin,rowMax) into the left or right half of the span entries.
-DEVI void edge_small(const DrawConst &d, uint32_t *spans, int rowMin, int stride, int q, int Xa, int Ya, int Xb, int Yb)
+// of every row of the edge inside [rowMin, rowMin + SWCU_SMALL_ROWS) into the left or right half of the span entries;
+// `rows` is this thread's column of the shared scratch: entry e lives at rows[e * SETUP_THREADS].
+#define SETUP_THREADS 128
+DEVI void edge_small(const DrawConst &d, uint32_t *rows, int rowMin, int stride, int q, int Xa, int Ya, int Xb, int Yb)
 {
 	if(Ya == Yb) return;
 	const bool swap = Yb < Ya;
@@ -213,10 +204,14 @@ DEVI void edge_small(const DrawConst &d, uint32_t *spans, int rowMin, int stride
 	int floor = R >> 31;
 	Q += floor;
 	R += floor & FDY12;
-	unsigned short *half = (unsigned short *)spans + (swap ? 1 : 0);
 	for(int y = y1; y < yMax; y++)
 	{
-		if(y >= yMin) half[2 * ((y - rowMin) * stride + q)] = (unsigned short)clampi(x, d.scX0, d.scX1);
+		if(y >= yMin)
+		{
+			uint32_t *e = rows + ((y - rowMin) * stride + q) * SETUP_THREADS;
+			const uint32_t c = (uint32_t)clampi(x, d.scX0, d.scX1);
+			*e = swap ? ((*e & 0x0000FFFFu) | (c << 16)) : ((*e & 0xFFFF0000u) | c);
+		}
 		x += Q;
 		dd += R;
 		int overflow = -dd >> 31;
@@ -269,8 +264,9 @@ DEVI unsigned long long warp_alloc(unsigned long long *cursor, uint32_t count)
 	return base + (incl - count);
 }
 
-__global__ void __launch_bounds__(128) k_setup(const __grid_constant__ DrawConst d)
+__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ DrawConst d)
 {
+	__shared__ uint32_t s_rows[SWCU_SMALL_ROWS * 4][SETUP_THREADS];
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x; // grid is padded to whole warps; inactive lanes just allocate 0
 	const bool live = tri < d.primCount;
 	const bool msaa = d.ms > 1;
@@ -346,9 +342,8 @@ __global__ void __launch_bounds__(128) k_setup(const __grid_constant__ DrawConst
 		} while(0);
 	}
 
-	// ---- span-table and big-list allocation, one atomic per warp ----
+	// ---- span-table and big-list allocation for the big triangles, one atomic per warp ----
 	const int rows = visible ? yMax - yMin : 0;
-	const uint32_t count = (uint32_t)(rows * d.ms);
 	bool big = false;
 	if(visible)
 	{
@@ -357,14 +352,19 @@ __global__ void __launch_bounds__(128) k_setup(const __grid_constant__ DrawConst
 		nTiles = (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
 		big = rows > SWCU_SMALL_ROWS || nTiles > SWCU_SMALL_TILES;
 	}
-	const unsigned long long base = warp_alloc(&d.counters->spanCursor, count);
-	const unsigned long long slot = warp_alloc(&d.counters->bigSlots, big ? 1u : 0u);
+	const uint32_t count = big ? (uint32_t)(rows * d.ms) : 0u;
+	unsigned long long base = 0, slot = 0;
+	if(__any_sync(0xFFFFFFFFu, big))
+	{
+		base = warp_alloc(&d.counters->spanCursor, count);
+		slot = warp_alloc(&d.counters->bigSlots, big ? 1u : 0u);
+	}
 	const uint32_t nvis = __popc(__ballot_sync(0xFFFFFFFFu, visible));
 	if((threadIdx.x & 31) == 0 && nvis) atomicAdd(&d.counters->visible, nvis);
 	if(!live) return;
 	unsigned char *rec = d.triRecords + (size_t)tri * d.triStride;
-	if(visible && base + count > d.spanCapacity) { atomicOr(&d.counters->overflow, 1u); visible = false; }
-	if(visible && big && slot >= d.bigCapacity) { atomicOr(&d.counters->overflow, 2u); visible = false; }
+	if(big && base + count > d.spanCapacity) { atomicOr(&d.counters->overflow, 1u); visible = false; }
+	if(big && slot >= d.bigCapacity) { atomicOr(&d.counters->overflow, 2u); visible = false; }
 	if(!visible)
 	{
 		*(uint4 *)rec = make_uint4(0, 0, 0, 0); // empty bounds: never a candidate
@@ -382,15 +382,23 @@ __global__ void __launch_bounds__(128) k_setup(const __grid_constant__ DrawConst
 	}
 	else
 	{
-		uint32_t *sp = d.spans + base;
-		for(uint32_t i = 0; i < count; i++) sp[i] = 0; // MSAA pre-fill: empty span (SetupRoutine.cpp:214-225)
+		// span rows of the small triangle, built in a shared scratch column and stored inline in its record
+		uint32_t *col = &s_rows[0][threadIdx.x];
+		const int ne = rows * d.ms;
+		for(int i = 0; i < ne; i++) col[i * SETUP_THREADS] = 0; // MSAA pre-fill: empty span (SetupRoutine.cpp:214-225)
 		PX[n] = PX[0]; PY[n] = PY[0];
 		for(int q = 0; q < d.ms; q++)
 		{
 			const int ox = msaa ? c_Xf[q] : 0, oy = msaa ? c_Yf[q] : 0;
 			for(int i = 0; i < n; i++)
-				edge_small(d, sp, yMin, d.ms, q, PX[i + 1 - dir] - ox, PY[i + 1 - dir] - oy, PX[i + dir] - ox, PY[i + dir] - oy);
+				edge_small(d, col, yMin, d.ms, q, PX[i + 1 - dir] - ox, PY[i + 1 - dir] - oy, PX[i + dir] - ox, PY[i + dir] - oy);
 		}
+		uint32_t *out = (uint32_t *)(rec + d.triStride) - SWCU_SMALL_ROWS * d.ms;
+		if(d.ms == 4)
+			for(int r = 0; r < rows; r++)
+				((uint4 *)out)[r] = make_uint4(col[(4 * r) * SETUP_THREADS], col[(4 * r + 1) * SETUP_THREADS], col[(4 * r + 2) * SETUP_THREADS], col[(4 * r + 3) * SETUP_THREADS]);
+		else
+			for(int r = 0; r < rows; r++) out[r] = col[r * SETUP_THREADS];
 	}
 
 	// ---- vertex sort (SetupRoutine.cpp:271-294): only changes float rounding of the planes ----
@@ -491,7 +499,7 @@ __global__ void __launch_bounds__(128) k_setup(const __grid_constant__ DrawConst
 	hdr.x = (uint32_t)pxMin | ((uint32_t)pxMax << 16);
 	hdr.y = (uint32_t)yMin | ((uint32_t)yMax << 16);
 	hdr.z = (uint32_t)base;
-	hdr.w = frontFacing ? 1u : 0u;
+	hdr.w = (frontFacing ? 1u : 0u) | (big ? 2u : 0u);
 	*(uint4 *)rec = hdr;
 }
 
@@ -575,8 +583,7 @@ __global__ void __launch_bounds__(256) k_emit(const __grid_constant__ DrawConst 
 	if(nT == 0) return;
 	const uint4 hdr = *(const uint4 *)(d.triRecords + (size_t)tri * d.triStride);
 	const int pxMin = hdr.x & 0xFFFF, pxMax = hdr.x >> 16, yMin = hdr.y & 0xFFFF, yMax = hdr.y >> 16;
-	const int rows = yMax - yMin;
-	if(rows > SWCU_SMALL_ROWS || nT > SWCU_SMALL_TILES) return; // big: k_big emits
+	if(hdr.w & 2u) return; // big: k_big emits
 	const int tx0 = pxMin / SWCU_TILE_W, tx1 = (pxMax - 1) / SWCU_TILE_W;
 	const int ty0 = yMin / SWCU_TILE_H, ty1 = (yMax - 1) / SWCU_TILE_H;
 	uint32_t o = pairOffset[tri];
@@ -851,15 +858,18 @@ DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1
 // k_tile — one CTA per 32x16 screen tile
 //
 //   * the tile's colour / depth / stencil planes live in shared memory for the whole triangle list;
-//   * the list is consumed in chunks: the CTA stages the chunk's triangle records and the span rows that cross the tile
-//     in shared memory with coalesced 128-bit loads (one global round trip per chunk instead of one per pixel);
-//   * every warp owns a 16x8 region, every lane one 2x2 quad of it; a warp ballots the chunk's bounding boxes
-//     against its region, computes per-lane coverage bits (4 pixels x MS samples) from the staged span rows, and each
-//     lane then walks ITS OWN covered (triangle, pixel, sample) items in API order — lanes do not wait for each other's
-//     triangles, which is what keeps small-triangle meshes from serialising on the slowest quad;
+//   * the list is consumed in chunks: the CTA stages the chunk's triangle records (plane equations + inline span rows)
+//     in shared memory with coalesced 128-bit loads — one global round trip per chunk instead of one per pixel;
+//   * every warp owns a 16x8 region of the tile.  It ballots the chunk's bounding boxes against the region, each lane
+//     computes the coverage bits of one 2x2 quad (4 pixels x MS samples) from the staged span rows, and the covered
+//     (triangle, pixel, sample) ITEMS of the whole region are compacted into a per-warp queue;
+//   * the queue is then consumed 32 items at a time, one item per lane, so lane utilisation does not depend on
+//     triangle size.  Items of one sample stay in API order: a lane's items are queued in list order, and items that
+//     land in the same round are serialised by __match_any_sync rank;
 //   * specialised on <samples, fragment shader class, blend class>; depth / stencil state is warp-uniform at run time.
 // ------------------------------------------------------------------------------------------------------------------
 #define TILE_THREADS (SWCU_TILE_WARPS * 32)
+#define TILE_QCAP 256 // item queue entries per warp
 
 template<int SH> struct ShaderSlots { static constexpr int N = SH == SH_CONST ? 0 : SH == SH_VARY ? 4 : SH == SH_TEX ? 2 : 6; };
 
@@ -872,8 +882,9 @@ struct TileSmem
 	float depth[MS][SWCU_TILE_H][SWCU_TILE_W];
 	uint4 hdr[CH];
 	float4 planes[CH][NF4];
-	uint32_t span[CH][SWCU_TILE_H][MS];
-	unsigned short bits[SWCU_TILE_WARPS][32][32]; // [batch slot][lane]
+	uint32_t span[CH][SWCU_TILE_H][MS];            // span rows of the chunk's triangles, by tile row
+	unsigned short bits[SWCU_TILE_WARPS][32][32];  // [batch slot][lane] coverage bits
+	unsigned short queue[SWCU_TILE_WARPS][TILE_QCAP];
 	unsigned char stencil[MS][SWCU_TILE_H][SWCU_TILE_W];
 	uint32_t tri[CH];
 	unsigned char candIdx[SWCU_TILE_WARPS][32];
@@ -928,9 +939,11 @@ template<int MS, int SH, int BL>
 __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ DrawConst d, const uint32_t *tileBegin, const uint32_t *tileEnd, const uint32_t *triList)
 {
 	using SM = TileSmem<MS, SH>;
-	constexpr int CH = SM::CH, NF4 = SM::NF4, NSLOT = ShaderSlots<SH>::N;
+	constexpr int CH = SM::CH, NF4 = SM::NF4;
 	constexpr bool TEX = SH == SH_TEX || SH == SH_GENERIC;
 	constexpr int UV = SH == SH_TEX ? 0 : 4;
+	constexpr int ROWF4 = SWCU_SMALL_ROWS * MS / 4; // 16-byte pieces of inline span rows per record
+	constexpr int PIECES = 1 + NF4 + ROWF4;
 	__shared__ __align__(16) SM sm;
 
 	const int tx = d.tileX0 + blockIdx.x, ty = d.tileY0 + blockIdx.y;
@@ -944,8 +957,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 	const int tileX = tx * SWCU_TILE_W, tileY = ty * SWCU_TILE_H;
 	const int rx = tileX + (warp % (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_W; // this warp's region
 	const int ry = tileY + (warp / (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_H;
-	const int qx0 = rx + 2 * (lane & 7), qy0 = ry + 2 * (lane >> 3);               // this lane's quad
-	const int lx0 = qx0 - tileX, ly0 = qy0 - tileY;
+	const int qx0 = rx + 2 * (lane & 7), qy0 = ry + 2 * (lane >> 3);               // the quad whose coverage this lane computes
+	const int ly0 = qy0 - tileY;
 
 	if(threadIdx.x == 0) sm.dirty = 0;
 	// ---- stage the tile (made visible by the first chunk barrier) ----
@@ -960,34 +973,74 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 #pragma unroll
 	for(int ch = 0; ch < 4; ch++)
 		if((d.colorWriteMask >> ch) & 1) wmask32 |= 0xFFu << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
+	unsigned short *queue = sm.queue[warp];
 
 	for(uint32_t pos = begin; pos < end; pos += CH)
 	{
 		const int n = (int)min((uint32_t)CH, end - pos);
-		// ---- A: triangle ids of the chunk ----
+		// ---- A: triangle ids of the chunk; span rows default to empty ----
 		if((int)threadIdx.x < n) sm.tri[threadIdx.x] = d.direct ? pos + threadIdx.x : __ldg(triList + pos + threadIdx.x);
+		for(int i = threadIdx.x; i < n * SWCU_TILE_H * MS / 4; i += TILE_THREADS) ((uint4 *)&sm.span[0][0][0])[i] = make_uint4(0, 0, 0, 0);
 		__syncthreads();
-		// ---- B: records (header + planes), consecutive threads read consecutive 16-byte pieces of a record ----
-		for(int i = threadIdx.x; i < n * (1 + NF4); i += TILE_THREADS)
+		// ---- B: records; consecutive threads read consecutive 16-byte pieces (header | planes | inline span rows) ----
+		bool anyBig = false;
+		for(int i = threadIdx.x; i < n * PIECES; i += TILE_THREADS)
 		{
-			const int c = i / (1 + NF4), j = i % (1 + NF4);
-			const float4 v = __ldg((const float4 *)(d.triRecords + (size_t)sm.tri[c] * d.triStride) + j);
-			if(j == 0) sm.hdr[c] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-			else sm.planes[c][j - 1] = v;
+			const int c = i / PIECES, j = i % PIECES;
+			const unsigned char *rec = d.triRecords + (size_t)sm.tri[c] * d.triStride;
+			if(j <= NF4)
+			{
+				const float4 v = __ldg((const float4 *)rec + j);
+				if(j == 0)
+				{
+					sm.hdr[c] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+					anyBig |= (__float_as_uint(v.w) & 2u) != 0;
+				}
+				else sm.planes[c][j - 1] = v;
+			}
+			else
+			{
+				// inline rows of a small triangle: record row rr is screen row yMin + rr
+				const uint4 v = __ldg((const uint4 *)rec + j);
+				const uint4 h = __ldg((const uint4 *)rec); // the header again (same sector as the planes another thread fetches)
+				const uint32_t flags = h.w;
+				const int yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+				if(!(flags & 2u))
+				{
+					if(MS == 4)
+					{
+						const int rr = j - 1 - NF4, r = yMin + rr - tileY;
+						if(yMin + rr < yMax && r >= 0 && r < SWCU_TILE_H) *(uint4 *)&sm.span[c][r][0] = v;
+					}
+					else
+					{
+						const uint32_t e[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+						for(int t = 0; t < 4; t++)
+						{
+							const int rr = 4 * (j - 1 - NF4) + t, r = yMin + rr - tileY;
+							if(yMin + rr < yMax && r >= 0 && r < SWCU_TILE_H) sm.span[c][r][0] = e[t];
+						}
+					}
+				}
+			}
 		}
-		__syncthreads();
-		// ---- C: the span rows of every chunk triangle that cross this tile (empty span outside the triangle's rows) ----
-		for(int i = threadIdx.x; i < n * SWCU_TILE_H; i += TILE_THREADS)
+		// ---- C: rows of the big triangles come from the span table ----
+		if(__syncthreads_or(anyBig))
 		{
-			const int c = i / SWCU_TILE_H, r = i % SWCU_TILE_H;
-			const uint4 h = sm.hdr[c];
-			const int y = tileY + r, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
-			const bool in = y >= yMin && y < yMax;
-			const uint32_t *sp = d.spans + h.z + (uint32_t)(y - yMin) * MS;
-			if(MS == 4) *(uint4 *)&sm.span[c][r][0] = in ? __ldg((const uint4 *)sp) : make_uint4(0, 0, 0, 0);
-			else sm.span[c][r][0] = in ? __ldg(sp) : 0u;
+			for(int i = threadIdx.x; i < n * SWCU_TILE_H; i += TILE_THREADS)
+			{
+				const int c = i / SWCU_TILE_H, r = i % SWCU_TILE_H;
+				const uint4 h = sm.hdr[c];
+				if(!(h.w & 2u)) continue;
+				const int y = tileY + r, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+				if(y < yMin || y >= yMax) continue;
+				const uint32_t *sp = d.spans + h.z + (uint32_t)(y - yMin) * MS;
+				if(MS == 4) *(uint4 *)&sm.span[c][r][0] = __ldg((const uint4 *)sp);
+				else sm.span[c][r][0] = __ldg(sp);
+			}
+			__syncthreads();
 		}
-		__syncthreads();
 
 		// ---- D: per warp: candidates of my region, in list order ----
 		uint32_t mlo, mhi = 0;
@@ -1016,6 +1069,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 		{
 			// ---- coverage bits of my quad for up to 32 candidates (QuadRasterizer.cpp:181-206 on the staged span rows) ----
 			int nb = 0;
+			uint32_t myCount = 0;
 			while((mlo | mhi) && nb < 32)
 			{
 				int c;
@@ -1042,193 +1096,190 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 				}
 				if(MS == 4) bits &= d.sampleMask * 0x1111u; // sample q masked out for all four pixels
 				sm.bits[warp][nb][lane] = (unsigned short)bits;
+				myCount += __popc(bits);
 				if(lane == 0) sm.candIdx[warp][nb] = (unsigned char)c;
 				nb++;
 			}
-			__syncwarp();
-
-			// ---- walk my (triangle, pixel, sample) items in order ----
-			int k = -1;
-			uint32_t cur = 0;
-			int curPx = -1;
-			float x0 = 0, y0 = 0, zBias = 0, wA = 0, wB = 0, wC = 0, zA = 0, zB = 0, zC = 0;
-			float S[NSLOT > 0 ? NSLOT : 1][3];
-			uint32_t triFlags = 0;
-			float rgba[4] = { 0, 0, 0, 0 };
-			uint32_t packed = 0;
-			float xf = 0, yf = 0;
-			LodState lodState;
-			lodState.lod = 0; lodState.ilod = 0; lodState.linear = false; lodState.split = false;
-			for(;;)
+			// ---- compact the region's items into the queue: lane-major, each lane's items in list order ----
+			uint32_t incl = myCount;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1)
 			{
-				if(cur == 0)
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+				if(lane >= o) incl += t;
+			}
+			const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+			const uint32_t first = incl - myCount;
+			__syncwarp();
+			for(uint32_t win = 0; win < total; win += TILE_QCAP)
+			{
+				if(first < win + TILE_QCAP && first + myCount > win)
 				{
-					do
+					uint32_t g = first;
+					for(int k = 0; k < nb && g < win + TILE_QCAP; k++)
 					{
-						if(++k >= nb) break;
-						cur = sm.bits[warp][k][lane];
-					} while(cur == 0);
-					if(k >= nb) break;
-					// ---- new triangle: planes from the staged record ----
-					const int c = sm.candIdx[warp][k];
-					triFlags = sm.hdr[c].w;
-					float pf[NF4 * 4];
-#pragma unroll
-					for(int j = 0; j < NF4; j++)
-					{
-						const float4 t = sm.planes[c][j];
-						pf[4 * j] = t.x; pf[4 * j + 1] = t.y; pf[4 * j + 2] = t.z; pf[4 * j + 3] = t.w;
-					}
-					x0 = pf[0]; y0 = pf[1]; zBias = pf[2]; wA = pf[3]; wB = pf[4]; wC = pf[5]; zA = pf[6]; zB = pf[7]; zC = pf[8];
-#pragma unroll
-					for(int s = 0; s < NSLOT; s++) { S[s][0] = pf[9 + 3 * s]; S[s][1] = pf[10 + 3 * s]; S[s][2] = pf[11 + 3 * s]; }
-					curPx = -1;
-					if(TEX)
-					{
-						// implicit LOD from quad lanes 0,1,2 (helper pixels included), SamplerCore.cpp:1376-1422
-						float uu[3], vv[3];
-#pragma unroll
-						for(int t = 0; t < 3; t++)
+						uint32_t b = sm.bits[warp][k][lane];
+						while(b)
 						{
-							const float xk = fsub((float)(qx0 + (t & 1)), x0), yk = fsub((float)(qy0 + (t >> 1)), y0);
-							const float w = __fmaf_rn(xk, wA, fadd(wC, fmul(yk, wB)));
-							const float rhw = fdiv(1.0f, w);
-							uu[t] = interp_slot(S[UV][0], S[UV][1], S[UV][2], d.slotMode[UV], xk, yk, rhw);
-							vv[t] = interp_slot(S[UV + 1][0], S[UV + 1][1], S[UV + 1][2], d.slotMode[UV + 1], xk, yk, rhw);
-						}
-						lodState = compute_lod(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]);
-					}
-				}
-				const int b = __ffs(cur) - 1;
-				cur &= cur - 1;
-				const int i = b / MS, q = b % MS;
-				const int ix = i & 1, iy = i >> 1;
-				if(i != curPx)
-				{
-					// ---- interpolate + routed fragment shader for pixel i (PixelRoutine.cpp:196-261, PixelProgram.cpp:138-241) ----
-					curPx = i;
-					xf = fsub((float)(qx0 + ix), x0);
-					yf = fsub((float)(qy0 + iy), y0);
-					float rhw = 1.0f;
-					if(SH != SH_CONST)
-					{
-						const float w = __fmaf_rn(xf, wA, fadd(wC, fmul(yf, wB)));
-						rhw = fdiv(1.0f, w);
-					}
-					float texel[4] = { 0, 0, 0, 0 };
-					if(TEX)
-					{
-						const float u = interp_slot(S[UV][0], S[UV][1], S[UV][2], d.slotMode[UV], xf, yf, rhw);
-						const float v = interp_slot(S[UV + 1][0], S[UV + 1][1], S[UV + 1][2], d.slotMode[UV + 1], xf, yf, rhw);
-						sample_texture(d, lodState, u, v, texel);
-					}
-#pragma unroll
-					for(int ch = 0; ch < 4; ch++)
-					{
-						float val;
-						const uint32_t kind = d.chanKind[ch];
-						if(kind == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
-						else if(TEX && kind == CK_TEXEL)
-						{
-							const uint32_t t = d.chanValue[ch];
-							val = t == 0 ? texel[0] : t == 1 ? texel[1] : t == 2 ? texel[2] : texel[3];
-						}
-						else if(SH == SH_VARY || SH == SH_GENERIC) val = interp_slot(S[ch][0], S[ch][1], S[ch][2], d.slotMode[ch], xf, yf, rhw);
-						else val = 0.0f;
-						rgba[ch] = sse_min(sse_max(val, 0.0f), 1.0f); // PixelProgram::clampColor :286-364
-					}
-					if(BL == BL_OFF)
-					{
-						packed = 0;
-#pragma unroll
-						for(int ch = 0; ch < 4; ch++) // writeColor :1981-1992
-						{
-							const uint32_t v = (uint32_t)clampi(round_int(fmul(rgba[ch], 255.0f)), 0, 255);
-							packed |= v << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
+							const int bit = __ffs(b) - 1;
+							b &= b - 1;
+							if(g >= win && g < win + TILE_QCAP) queue[g - win] = (unsigned short)((k << 9) | (bit << 5) | lane);
+							g++;
 						}
 					}
 				}
-
-				// ---- per-sample: stencil test, depth test, depth write, blend + colour write, stencil write ----
-				const int lx = lx0 + ix, ly = ly0 + iy;
-				bool sPass = true;
-				uint32_t sValue = 0;
-				if(d.stencilActive)
+				__syncwarp();
+				const int cnt = (int)min((uint32_t)TILE_QCAP, total - win);
+				for(int base = 0; base < cnt; base += 32)
 				{
-					const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
-					sValue = sm.stencil[q][ly][lx];
-					sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
-				}
-				bool zPass = true;
-				float z = 0.0f;
-				if(d.depthTestActive)
-				{
-					float yy = yf, xx = xf;
-					if(MS > 1) { yy = fadd(yy, c_SampleY[q]); xx = fsub(xx, c_SampleX[q]); }
-					z = __fmaf_rn(xx, zA, fadd(zC, fmul(yy, zB)));
-					if(biasOn) z = fadd(z, zBias);
-					z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
-					zPass = depth_compare(d.depthCompareOp, sm.depth[q][ly][lx], z);
-				}
-				if(zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
-				{
-					if(d.depthWriteEnable) { sm.depth[q][ly][lx] = z; dirty = true; }
-					if(colorOn)
+					const int j = base + lane;
+					const bool valid = j < cnt;
+					const uint32_t e = valid ? queue[j] : 0u;
+					// items of the same (quad, pixel, sample) in this round run in queue order
+					const uint32_t key = valid ? (e & 0x1FFu) : (0x200u | lane);
+					const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+					const int rank = __popc(peers & ((1u << lane) - 1));
+					const int maxRank = __reduce_max_sync(0xFFFFFFFFu, valid ? rank : 0);
+					for(int rr = 0; rr <= maxRank; rr++)
 					{
-						uint32_t px = sm.color[q][ly][lx];
-						if(BL == BL_OFF) px = (px & ~wmask32) | (packed & wmask32);
-						else
+						if(valid && rank == rr)
 						{
-							float o[4];
-							float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
+							const int k = e >> 9, bit = (e >> 5) & 15, owner = e & 31;
+							const int i = bit / MS, q = bit % MS;
+							const int ix = i & 1, iy = i >> 1;
+							const int c = sm.candIdx[warp][k];
+							const int x = rx + 2 * (owner & 7) + ix, y = ry + 2 * (owner >> 3) + iy;
+							const int lx = x - tileX, ly = y - tileY;
+							// ---- plane equations of the triangle ----
+							float pf[NF4 * 4];
+#pragma unroll
+							for(int t = 0; t < NF4; t++)
+							{
+								const float4 v = sm.planes[c][t];
+								pf[4 * t] = v.x; pf[4 * t + 1] = v.y; pf[4 * t + 2] = v.z; pf[4 * t + 3] = v.w;
+							}
+							const float x0 = pf[0], y0 = pf[1], zBias = pf[2], wA = pf[3], wB = pf[4], wC = pf[5], zA = pf[6], zB = pf[7], zC = pf[8];
+							const float *S = pf + TRI_FLOATS_FIXED; // slot s: S[3s], S[3s+1], S[3s+2]
+							// ---- interpolate + routed fragment shader (PixelRoutine.cpp:196-261, PixelProgram.cpp:138-241) ----
+							const float xf = fsub((float)x, x0), yf = fsub((float)y, y0);
+							float rhw = 1.0f;
+							if(SH != SH_CONST) rhw = fdiv(1.0f, __fmaf_rn(xf, wA, fadd(wC, fmul(yf, wB))));
+							float texel[4] = { 0, 0, 0, 0 };
+							if(TEX)
+							{
+								// implicit LOD from lanes 0,1,2 of the pixel's quad (helper pixels included), SamplerCore.cpp:1376-1422
+								float uu[3], vv[3];
+#pragma unroll
+								for(int t = 0; t < 3; t++)
+								{
+									const float xk = fsub((float)(x - ix + (t & 1)), x0), yk = fsub((float)(y - iy + (t >> 1)), y0);
+									const float rk = fdiv(1.0f, __fmaf_rn(xk, wA, fadd(wC, fmul(yk, wB))));
+									uu[t] = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], d.slotMode[UV], xk, yk, rk);
+									vv[t] = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], d.slotMode[UV + 1], xk, yk, rk);
+								}
+								const LodState lodState = compute_lod(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]);
+								const float u = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], d.slotMode[UV], xf, yf, rhw);
+								const float v = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], d.slotMode[UV + 1], xf, yf, rhw);
+								sample_texture(d, lodState, u, v, texel);
+							}
+							float rgba[4];
 #pragma unroll
 							for(int ch = 0; ch < 4; ch++)
 							{
-								const uint32_t bsel = (px >> (8 * ((d.bgr && ch < 3) ? 2 - ch : ch))) & 0xFF;
-								dst[ch] = fmul((float)(bsel * 257), 1.0f / 0xFFFF);
+								float val;
+								const uint32_t kind = d.chanKind[ch];
+								if(kind == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
+								else if(TEX && kind == CK_TEXEL)
+								{
+									const uint32_t t = d.chanValue[ch];
+									val = t == 0 ? texel[0] : t == 1 ? texel[1] : t == 2 ? texel[2] : texel[3];
+								}
+								else if(SH == SH_VARY || SH == SH_GENERIC) val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], d.slotMode[ch], xf, yf, rhw);
+								else val = 0.0f;
+								rgba[ch] = sse_min(sse_max(val, 0.0f), 1.0f); // PixelProgram::clampColor :286-364
 							}
-							if(BL == BL_SRC_ALPHA)
+
+							// ---- stencil test, depth test, depth write, blend + colour write, stencil write ----
+							bool sPass = true;
+							uint32_t sValue = 0;
+							const uint32_t triFlags = sm.hdr[c].w;
+							if(d.stencilActive)
 							{
-								const float sa = rgba[3], da = fsub(1.0f, rgba[3]);
-#pragma unroll
-								for(int ch = 0; ch < 3; ch++) o[ch] = fadd(fmul(rgba[ch], sa), fmul(dst[ch], da));
-								o[3] = rgba[3];
+								const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
+								sValue = sm.stencil[q][ly][lx];
+								sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
 							}
-							else
+							bool zPass = true;
+							float z = 0.0f;
+							if(d.depthTestActive)
 							{
-#pragma unroll
-								for(int ch = 0; ch < 3; ch++)
-									o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
-								o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
+								float yy = yf, xx = xf;
+								if(MS > 1) { yy = fadd(yy, c_SampleY[q]); xx = fsub(xx, c_SampleX[q]); }
+								z = __fmaf_rn(xx, zA, fadd(zC, fmul(yy, zB)));
+								if(biasOn) z = fadd(z, zBias);
+								z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
+								zPass = depth_compare(d.depthCompareOp, sm.depth[q][ly][lx], z);
 							}
-							uint32_t pk = 0;
-#pragma unroll
-							for(int ch = 0; ch < 4; ch++) // writeColor :1981-1992, :2603-2655
+							if(zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
 							{
-								const float cl = sse_min(sse_max(o[ch], 0.0f), 1.0f);
-								const uint32_t v = (uint32_t)clampi(round_int(fmul(cl, 255.0f)), 0, 255);
-								pk |= v << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
+								if(d.depthWriteEnable) { sm.depth[q][ly][lx] = z; dirty = true; }
+								if(colorOn)
+								{
+									uint32_t px = sm.color[q][ly][lx];
+									float o[4] = { rgba[0], rgba[1], rgba[2], rgba[3] };
+									if(BL != BL_OFF)
+									{
+										float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
+#pragma unroll
+										for(int ch = 0; ch < 4; ch++)
+										{
+											const uint32_t bsel = (px >> (8 * ((d.bgr && ch < 3) ? 2 - ch : ch))) & 0xFF;
+											dst[ch] = fmul((float)(bsel * 257), 1.0f / 0xFFFF);
+										}
+										if(BL == BL_SRC_ALPHA)
+										{
+											const float sa = rgba[3], da = fsub(1.0f, rgba[3]);
+#pragma unroll
+											for(int ch = 0; ch < 3; ch++) o[ch] = fadd(fmul(rgba[ch], sa), fmul(dst[ch], da));
+										}
+										else
+										{
+#pragma unroll
+											for(int ch = 0; ch < 3; ch++)
+												o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
+											o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
+										}
+									}
+									uint32_t pk = 0;
+#pragma unroll
+									for(int ch = 0; ch < 4; ch++) // writeColor :1981-1992, :2603-2655
+									{
+										const float cl = sse_min(sse_max(o[ch], 0.0f), 1.0f);
+										const uint32_t v = (uint32_t)clampi(round_int(fmul(cl, 255.0f)), 0, 255);
+										pk |= v << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
+									}
+									sm.color[q][ly][lx] = (px & ~wmask32) | (pk & wmask32);
+									dirty = true;
+								}
 							}
-							px = (px & ~wmask32) | (pk & wmask32);
+							if(d.stencilWrite) // writeStencil :754-817
+							{
+								const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
+								const uint32_t ref = face.reference & 0xFF;
+								uint32_t nv;
+								if(!sPass) nv = stencil_op(face.failOp, sValue, ref);
+								else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
+								else nv = stencil_op(face.passOp, sValue, ref);
+								const uint32_t wm = face.writeMask & 0xFF;
+								sm.stencil[q][ly][lx] = (unsigned char)((nv & wm) | (sValue & ~wm));
+								dirty = true;
+							}
 						}
-						sm.color[q][ly][lx] = px;
-						dirty = true;
+						__syncwarp();
 					}
 				}
-				if(d.stencilWrite) // writeStencil :754-817
-				{
-					const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
-					const uint32_t ref = face.reference & 0xFF;
-					uint32_t nv;
-					if(!sPass) nv = stencil_op(face.failOp, sValue, ref);
-					else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
-					else nv = stencil_op(face.passOp, sValue, ref);
-					const uint32_t wm = face.writeMask & 0xFF;
-					sm.stencil[q][ly][lx] = (unsigned char)((nv & wm) | (sValue & ~wm));
-					dirty = true;
-				}
+				__syncwarp();
 			}
-			__syncwarp();
 		}
 		__syncthreads(); // the staging buffers are reused by the next chunk
 	}

@@ -53,7 +53,7 @@ enum { CLIP_RIGHT = 1, CLIP_TOP = 2, CLIP_FAR = 4, CLIP_LEFT = 8, CLIP_BOTTOM = 
 #define SWCU_REGION_W 16     // sub-tile owned by one warp: 8x4 quads, one 2x2 quad per lane
 #define SWCU_REGION_H 8
 #define SWCU_TILE_WARPS ((SWCU_TILE_W / SWCU_REGION_W) * (SWCU_TILE_H / SWCU_REGION_H))
-#define SWCU_SMALL_ROWS 16   // triangles up to this many rows get their spans from the setup thread itself
+#define SWCU_SMALL_ROWS 8    // triangles up to this many rows carry their span rows inline in the triangle record
 #define SWCU_SMALL_TILES 8   // ... and emit their (tile, triangle) pairs from the emit thread
 #define SWCU_POLY_MAX 10     // 3 + 6 clip planes (+1 wrap slot)
 #define SWCU_INVALID_TILE 0xFFFFFFFFu
@@ -74,12 +74,14 @@ struct KOperand
 	uint32_t value; // CONST: float bits; INPUT: vertex stage = location*4+component, fragment stage = packed interpolant index; TEXEL: channel
 };
 
-struct KVertexInput
+// One scalar the vertex stage produces, resolved on the host to "constant" or "component c of attribute stream l"
+// (VertexRoutine::readStream, VertexRoutine.cpp:173-245, for R32..R32G32B32A32_SFLOAT streams).
+struct KVSrc
 {
-	const unsigned char *buffer;
-	uint32_t robustnessSize;
+	const unsigned char *ptr; // attribute base + 4*component; nullptr => constant
 	uint32_t stride;
-	uint32_t ncomp; // 0 = unused -> (0,0,0,1)
+	uint32_t limit;           // robustBufferAccess: fetch yields 0 when byte offset > limit (0xFFFFFFFF = unchecked)
+	float constant;           // value when ptr == nullptr (shader constant, or the (0,0,0,1) default of a short format)
 	uint32_t pad;
 };
 
@@ -128,17 +130,15 @@ struct DrawConst
 	const void *indexBuffer;
 	uint32_t indexType, topology, provokingFirst, primCount;
 	int32_t baseVertex;
-	uint32_t vsInputMask; // locations read by the vertex shader
-	KVertexInput input[SWCU_MAX_INPUTS];
 
 	// ---- shader routing (output of the SPIR-V subset translator), resolved to per-triangle plane slots ----
 	// The fragment shaders of the subset are pure routing, so k_setup evaluates the vertex-stage operand of every value
 	// the fragment stage consumes and writes one plane equation per SLOT: slots [0,4) are the colour channels of
 	// output 0 (shaderClass VARY/GENERIC), the last two are the texture coordinate (TEX/GENERIC).
-	KOperand vsPos[4];
+	KVSrc vsPos[4];
 	uint32_t shaderClass;        // SH_*
 	int32_t nslots;
-	KOperand slotSrc[SWCU_MAXSLOTS];  // vertex-stage operand feeding the slot (CONST or INPUT)
+	KVSrc slotSrc[SWCU_MAXSLOTS];     // vertex-stage scalar feeding the slot
 	uint32_t slotMode[SWCU_MAXSLOTS]; // IM_*
 	uint32_t chanKind[4];        // CK_* : where colour channel ch comes from
 	uint32_t chanValue[4];       // CK_CONST: float bits; CK_SLOT: slot index; CK_TEXEL: texel component
@@ -187,10 +187,12 @@ struct DrawConst
 
 // TriRecord layout (triStride bytes, 16-byte aligned):
 //   uint16 pxMin, pxMax, yMin, yMax;   pixel bounds (x exclusive upper, y exclusive upper); yMin>=yMax => invisible
-//   uint32 spanBase;                   first span entry: index = spanBase + (y - yMin) * ms + q
-//   uint32 flags;                      bit0 = clockwiseMask (front facing), Primitive.hpp:60
+//   uint32 spanBase;                   big triangles: first entry in the span table, index = spanBase + (y - yMin) * ms + q
+//   uint32 flags;                      bit0 = clockwiseMask (front facing, Primitive.hpp:60); bit1 = big (rows in the span table)
 //   float  x0, y0, zBias, wA, wB, wC, zA, zB, zC;   Primitive::{x0,y0,zBias,w,z}
-//   float  V[nslots][3];               Primitive::V planes {A,B,C} of the routed slots
+//   float  V[nslots][3];               Primitive::V planes {A,B,C} of the routed slots   (padded to a multiple of 16 bytes)
+//   uint32 rows[SWCU_SMALL_ROWS][ms];  small triangles: span {u16 left, u16 right} of row yMin + r, sample q  (Primitive::outline)
 #define TRI_HEADER_BYTES 16
 #define TRI_FLOATS_FIXED 9
-static inline uint32_t swcu_tri_stride(int nslots) { return (uint32_t)((TRI_HEADER_BYTES + 4 * (TRI_FLOATS_FIXED + 3 * nslots) + 15) & ~15); }
+static inline uint32_t swcu_tri_plane_f4(int nslots) { return (uint32_t)((TRI_FLOATS_FIXED + 3 * nslots + 3) / 4); }
+static inline uint32_t swcu_tri_stride(int nslots, int ms) { return TRI_HEADER_BYTES + 16 * swcu_tri_plane_f4(nslots) + 4 * SWCU_SMALL_ROWS * (uint32_t)ms; }
