@@ -53,6 +53,9 @@ struct swcu_ctx
 	std::vector<KernelTime> lastKernels;
 	std::vector<cudaEvent_t> eventPool;
 	size_t eventsUsed = 0;
+	int optTma = 1;
+	void *encodeTiled = nullptr; // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda link dependency)
+	std::map<std::vector<uint64_t>, CUtensorMap> mapCache;
 };
 
 static int fail(swcu_ctx *ctx, int code, const char *fmt, ...)
@@ -335,6 +338,7 @@ extern "C" int swcu_set_option(swcu_ctx *ctx, const char *name, int value)
 	if(!strcmp(name, "force_binned")) ctx->optForceBinned = value;
 	else if(!strcmp(name, "direct_max")) ctx->optDirectMax = value;
 	else if(!strcmp(name, "pin_host")) ctx->optPinHost = value;
+	else if(!strcmp(name, "tma")) ctx->optTma = value;
 	else return fail(ctx, SWCU_E_INVALID, "unknown option '%s'", name);
 	return SWCU_OK;
 }
@@ -645,31 +649,73 @@ __global__ void k_pair_total(const uint32_t *pairOffset, const uint32_t *tileCou
 	c->pairTotal = (unsigned long long)pairOffset[n - 1] + tileCount[n - 1];
 }
 
+// ---- TMA descriptors of the attachments: a 3-D tensor (x, y, sample plane) with a (tile width, tile height, samples) box ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool tma_eligible(const unsigned char *base, int pitchB, int sliceB, int bpp)
+{
+	return base && ((uintptr_t)base % 16 == 0) && pitchB > 0 && sliceB > 0 && (pitchB % 16 == 0) && (sliceB % 16 == 0) && (SWCU_TILE_W * bpp) % 16 == 0;
+}
+
+static bool get_tensor_map(swcu_ctx *ctx, CUtensorMap *out, unsigned char *base, int pitchB, int sliceB, int w, int h, int ms, int bpp)
+{
+	if(!ctx->encodeTiled)
+	{
+		cudaDriverEntryPointQueryResult q;
+		void *fn = nullptr;
+		if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+		{
+			cudaGetLastError();
+			return false;
+		}
+		ctx->encodeTiled = fn;
+	}
+	const std::vector<uint64_t> key = { (uint64_t)(uintptr_t)base, (uint64_t)pitchB, (uint64_t)sliceB, (uint64_t)w, (uint64_t)h, (uint64_t)ms, (uint64_t)bpp };
+	auto it = ctx->mapCache.find(key);
+	if(it == ctx->mapCache.end())
+	{
+		CUtensorMap m;
+		const cuuint64_t dims[3] = { (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)ms };
+		const cuuint64_t strides[2] = { (cuuint64_t)pitchB, (cuuint64_t)sliceB };
+		const cuuint32_t box[3] = { SWCU_TILE_W, SWCU_TILE_H, (cuuint32_t)ms };
+		const cuuint32_t estr[3] = { 1, 1, 1 };
+		CUresult r = ((EncodeTiledFn)ctx->encodeTiled)(&m, bpp == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+		                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if(r != CUDA_SUCCESS) return false;
+		if(ctx->mapCache.size() > 256) ctx->mapCache.clear();
+		it = ctx->mapCache.emplace(key, m).first;
+	}
+	*out = it->second;
+	return true;
+}
+
 template<int MS, int SH, int BL>
-static void launch_tile3(swcu_ctx *ctx, const DrawConst &d, dim3 grid)
+static void launch_tile3(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps, dim3 grid)
 {
 	LaunchScope ls(ctx, MS == 4 ? "k_tile<4>" : "k_tile<1>");
-	k_tile<MS, SH, BL><<<grid, TILE_THREADS, 0, ctx->stream>>>(d, (const uint32_t *)ctx->tileBegin.p, (const uint32_t *)ctx->tileEnd.p, (const uint32_t *)ctx->vals.p);
+	const int smem = TileLayout<MS, SH>::total(d.depthTestActive != 0, d.stencilActive != 0);
+	k_tile<MS, SH, BL><<<grid, TILE_THREADS, smem, ctx->stream>>>(d, maps, (const uint32_t *)ctx->tileBegin.p, (const uint32_t *)ctx->tileEnd.p, (const uint32_t *)ctx->vals.p);
 }
 template<int MS, int SH>
-static void launch_tile2(swcu_ctx *ctx, const DrawConst &d, dim3 grid)
+static void launch_tile2(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps, dim3 grid)
 {
 	switch(d.blendClass)
 	{
-	case BL_OFF: launch_tile3<MS, SH, BL_OFF>(ctx, d, grid); break;
-	case BL_SRC_ALPHA: launch_tile3<MS, SH, BL_SRC_ALPHA>(ctx, d, grid); break;
-	default: launch_tile3<MS, SH, BL_GENERIC>(ctx, d, grid); break;
+	case BL_OFF: launch_tile3<MS, SH, BL_OFF>(ctx, d, maps, grid); break;
+	case BL_SRC_ALPHA: launch_tile3<MS, SH, BL_SRC_ALPHA>(ctx, d, maps, grid); break;
+	default: launch_tile3<MS, SH, BL_GENERIC>(ctx, d, maps, grid); break;
 	}
 }
 template<int MS>
-static void launch_tile(swcu_ctx *ctx, const DrawConst &d, dim3 grid)
+static void launch_tile(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps, dim3 grid)
 {
 	switch(d.shaderClass)
 	{
-	case SH_CONST: launch_tile2<MS, SH_CONST>(ctx, d, grid); break;
-	case SH_VARY: launch_tile2<MS, SH_VARY>(ctx, d, grid); break;
-	case SH_TEX: launch_tile2<MS, SH_TEX>(ctx, d, grid); break;
-	default: launch_tile2<MS, SH_GENERIC>(ctx, d, grid); break;
+	case SH_CONST: launch_tile2<MS, SH_CONST>(ctx, d, maps, grid); break;
+	case SH_VARY: launch_tile2<MS, SH_VARY>(ctx, d, maps, grid); break;
+	case SH_TEX: launch_tile2<MS, SH_TEX>(ctx, d, maps, grid); break;
+	default: launch_tile2<MS, SH_GENERIC>(ctx, d, maps, grid); break;
 	}
 }
 
@@ -786,7 +832,21 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		LaunchScope ls(ctx, "k_big");
 		k_big<<<dim3(std::min<uint32_t>(n, 64u), 1), 256, 0, ctx->stream>>>(d, nullptr, nullptr, nullptr);
 	}
-	if(d.ms == 4) launch_tile<4>(ctx, d, tileGrid); else launch_tile<1>(ctx, d, tileGrid);
+	// ---- tensor maps of the attachments the tile kernel stages ----
+	TileMaps maps;
+	memset(&maps, 0, sizeof(maps));
+	{
+		const bool colorOn = d.colorWriteMask != 0 && d.colorBuf;
+		bool ok = ctx->optTma != 0;
+		if(ok && colorOn) ok = tma_eligible(d.colorBuf, d.colorPitchB, d.colorSliceB, 4);
+		if(ok && d.depthTestActive) ok = tma_eligible(d.depthBuf, d.depthPitchB, d.depthSliceB, 4);
+		if(ok && d.stencilActive) ok = tma_eligible(d.stencilBuf, d.stencilPitchB, d.stencilSliceB, 1);
+		if(ok && colorOn) ok = get_tensor_map(ctx, &maps.color, d.colorBuf, d.colorPitchB, d.colorSliceB, d.fbWidth, d.fbHeight, d.ms, 4);
+		if(ok && d.depthTestActive) ok = get_tensor_map(ctx, &maps.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, d.fbWidth, d.fbHeight, d.ms, 4);
+		if(ok && d.stencilActive) ok = get_tensor_map(ctx, &maps.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, d.fbWidth, d.fbHeight, d.ms, 1);
+		d.useTma = ok ? 1u : 0u;
+	}
+	if(d.ms == 4) launch_tile<4>(ctx, d, maps, tileGrid); else launch_tile<1>(ctx, d, maps, tileGrid);
 	CU(cudaGetLastError());
 	return SWCU_OK;
 }

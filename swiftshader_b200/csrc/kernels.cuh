@@ -18,6 +18,7 @@
 
 #include "swcu_internal.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #define DEVI __device__ __forceinline__
@@ -855,17 +856,19 @@ DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_tile — one CTA per 32x16 screen tile
+// k_tile — one CTA per 32x16 screen tile, one warp per 16x8 region of it
 //
-//   * the tile's colour / depth / stencil planes live in shared memory for the whole triangle list;
-//   * the list is consumed in chunks: the CTA stages the chunk's triangle records (plane equations + inline span rows)
-//     in shared memory with coalesced 128-bit loads — one global round trip per chunk instead of one per pixel;
-//   * every warp owns a 16x8 region of the tile.  It ballots the chunk's bounding boxes against the region, each lane
-//     computes the coverage bits of one 2x2 quad (4 pixels x MS samples) from the staged span rows, and the covered
-//     (triangle, pixel, sample) ITEMS of the whole region are compacted into a per-warp queue;
-//   * the queue is then consumed 32 items at a time, one item per lane, so lane utilisation does not depend on
-//     triangle size.  Items of one sample stay in API order: a lane's items are queued in list order, and items that
-//     land in the same round are serialised by __match_any_sync rank;
+//   * the tile's colour / depth / stencil planes are staged in shared memory by ONE TMA load per attachment
+//     (cp.async.bulk.tensor.3d: x, y, sample plane) that overlaps the first list scan, stay there for the tile's whole
+//     triangle list, and go back with one TMA store per attachment (fallback: cooperative 128-bit copies when the
+//     attachment's pitch / base address do not satisfy the tensor-map alignment rules);
+//   * the four warps are INDEPENDENT inside the list loop (no CTA barriers): each warp scans the tile's list 32 entries
+//     at a time, ballots the bounding boxes against its region, and stages the candidates' plane equations and the span
+//     rows that cross the region in its own shared-memory area with coalesced 128-bit loads;
+//   * each lane computes the coverage bits of one 2x2 quad (4 pixels x MS samples) from the staged span rows, the covered
+//     (triangle, pixel, sample) ITEMS of the region are compacted into a per-warp queue and consumed 32 at a time, one
+//     item per lane, so lane utilisation does not depend on triangle size.  Items of one sample stay in API order: a
+//     lane's items are queued in list order, and items landing in the same round are serialised by __match_any_sync rank;
 //   * specialised on <samples, fragment shader class, blend class>; depth / stencil state is warp-uniform at run time.
 // ------------------------------------------------------------------------------------------------------------------
 #define TILE_THREADS (SWCU_TILE_WARPS * 32)
@@ -873,27 +876,55 @@ DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1
 
 template<int SH> struct ShaderSlots { static constexpr int N = SH == SH_CONST ? 0 : SH == SH_VARY ? 4 : SH == SH_TEX ? 2 : 6; };
 
-template<int MS, int SH>
-struct TileSmem
+// ---- TMA / mbarrier primitives (PTX ISA 8.x, sm_90+) ----
+DEVI uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DEVI void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+DEVI void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+DEVI bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
-	static constexpr int CH = MS == 4 ? 32 : 64;                                   // triangles staged per chunk
+	uint32_t ok;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+DEVI void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+DEVI void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+	             ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+DEVI void tma_store_3d(const CUtensorMap *map, const void *src, int x, int y, int z)
+{
+	asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+DEVI void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+DEVI void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// shared-memory layout of one tile CTA (dynamic shared memory; the host computes the same size)
+template<int MS, int SH>
+struct TileLayout
+{
+	static constexpr int NB = MS == 4 ? 16 : 32;                                   // candidates staged per warp batch
 	static constexpr int NF4 = (TRI_FLOATS_FIXED + 3 * ShaderSlots<SH>::N + 3) / 4; // float4s of plane data per record
-	uint32_t color[MS][SWCU_TILE_H][SWCU_TILE_W];
-	float depth[MS][SWCU_TILE_H][SWCU_TILE_W];
-	uint4 hdr[CH];
-	float4 planes[CH][NF4];
-	uint32_t span[CH][SWCU_TILE_H][MS];            // span rows of the chunk's triangles, by tile row
-	unsigned short bits[SWCU_TILE_WARPS][32][32];  // [batch slot][lane] coverage bits
-	unsigned short queue[SWCU_TILE_WARPS][TILE_QCAP];
-	unsigned char stencil[MS][SWCU_TILE_H][SWCU_TILE_W];
-	uint32_t tri[CH];
-	unsigned char candIdx[SWCU_TILE_WARPS][32];
-	int dirty;
+	static constexpr int PLANE_B = SWCU_TILE_W * SWCU_TILE_H * 4 * MS;              // colour or depth tile
+	static constexpr int STENCIL_B = SWCU_TILE_W * SWCU_TILE_H * MS;
+	// per-warp area
+	static constexpr int W_HDR = 0;                                  // uint4 hdr[NB]
+	static constexpr int W_PLANES = W_HDR + 16 * NB;                 // float4 planes[NB][NF4]
+	static constexpr int W_ROWS = W_PLANES + 16 * NB * NF4;          // uint32 rows[NB][REGION_H][MS]
+	static constexpr int W_BITS = W_ROWS + 4 * NB * SWCU_REGION_H * MS; // uint16 bits[NB][32]
+	static constexpr int W_QUEUE = W_BITS + 2 * NB * 32;             // uint16 queue[QCAP]
+	static constexpr int W_TRI = W_QUEUE + 2 * TILE_QCAP;            // uint32 tri[NB]
+	static constexpr int W_BYTES = (W_TRI + 4 * NB + 127) & ~127;
+	static constexpr int HEAD_B = 128;                               // mbarrier + dirty flag
+	__host__ __device__ static int total(bool depth, bool stencil)
+	{
+		return HEAD_B + PLANE_B + (depth ? PLANE_B : 0) + (stencil ? ((STENCIL_B + 127) & ~127) : 0) + SWCU_TILE_WARPS * W_BYTES;
+	}
 };
 
-// cooperative tile <-> framebuffer copy with 128-bit accesses where the layout allows it
+// cooperative tile <-> framebuffer copy with 128-bit accesses where the layout allows it (TMA-ineligible attachments)
 template<int MS, typename T, bool STORE>
-DEVI void tile_copy(T (*sm)[SWCU_TILE_H][SWCU_TILE_W], unsigned char *base, int pitchB, int sliceB, int tileX, int tileY, int fbW, int fbH)
+DEVI void tile_copy(T *sm, unsigned char *base, int pitchB, int sliceB, int tileX, int tileY, int fbW, int fbH)
 {
 	constexpr int ROWB = SWCU_TILE_W * (int)sizeof(T);
 	constexpr int VEC = 16;
@@ -908,7 +939,7 @@ DEVI void tile_copy(T (*sm)[SWCU_TILE_H][SWCU_TILE_W], unsigned char *base, int 
 			const int y = tileY + r, xB = x0B + c * VEC;
 			if(y >= fbH || xB >= fbW * (int)sizeof(T)) continue;
 			uint4 *g = (uint4 *)(base + (size_t)q * sliceB + (size_t)y * pitchB + xB);
-			uint4 *s = (uint4 *)((unsigned char *)&sm[q][r][0] + c * VEC);
+			uint4 *s = (uint4 *)((unsigned char *)(sm + (q * SWCU_TILE_H + r) * SWCU_TILE_W) + c * VEC);
 			if(STORE) *g = *s; else *s = *g;
 		}
 	}
@@ -920,7 +951,8 @@ DEVI void tile_copy(T (*sm)[SWCU_TILE_H][SWCU_TILE_W], unsigned char *base, int 
 			const int y = tileY + r, x = tileX + c;
 			if(y >= fbH || x >= fbW) continue;
 			T *g = (T *)(base + (size_t)q * sliceB + (size_t)y * pitchB) + x;
-			if(STORE) *g = sm[q][r][c]; else sm[q][r][c] = *g;
+			T *s = sm + (q * SWCU_TILE_H + r) * SWCU_TILE_W + c;
+			if(STORE) *g = *s; else *s = *g;
 		}
 	}
 }
@@ -935,16 +967,21 @@ DEVI float interp_slot(float A, float B, float C, uint32_t mode, float xf, float
 	return t;
 }
 
-template<int MS, int SH, int BL>
-__global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ DrawConst d, const uint32_t *tileBegin, const uint32_t *tileEnd, const uint32_t *triList)
+struct TileMaps
 {
-	using SM = TileSmem<MS, SH>;
-	constexpr int CH = SM::CH, NF4 = SM::NF4;
+	CUtensorMap color, depth, stencil;
+};
+
+template<int MS, int SH, int BL>
+__global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ DrawConst d, const __grid_constant__ TileMaps maps,
+                                                        const uint32_t *tileBegin, const uint32_t *tileEnd, const uint32_t *triList)
+{
+	using L = TileLayout<MS, SH>;
+	constexpr int NB = L::NB, NF4 = L::NF4;
 	constexpr bool TEX = SH == SH_TEX || SH == SH_GENERIC;
 	constexpr int UV = SH == SH_TEX ? 0 : 4;
-	constexpr int ROWF4 = SWCU_SMALL_ROWS * MS / 4; // 16-byte pieces of inline span rows per record
-	constexpr int PIECES = 1 + NF4 + ROWF4;
-	__shared__ __align__(16) SM sm;
+	constexpr int TP = SWCU_TILE_W * SWCU_TILE_H; // pixels per sample plane of the tile
+	extern __shared__ __align__(128) unsigned char smem[];
 
 	const int tx = d.tileX0 + blockIdx.x, ty = d.tileY0 + blockIdx.y;
 	const int tileId = ty * d.tilesX + tx;
@@ -953,19 +990,59 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 	else { begin = tileBegin[tileId]; end = tileEnd[tileId]; }
 	if(begin >= end) return;
 
+	const bool colorOn = d.colorWriteMask != 0 && d.colorBuf != nullptr;
+	uint64_t *bar = (uint64_t *)smem;
+	int *dirtyFlag = (int *)(smem + 8);
+	uint32_t *smColor = (uint32_t *)(smem + L::HEAD_B);
+	float *smDepth = (float *)(smem + L::HEAD_B + L::PLANE_B);
+	unsigned char *smStencil = smem + L::HEAD_B + L::PLANE_B + (d.depthTestActive ? L::PLANE_B : 0);
+	unsigned char *warpBase = smStencil + (d.stencilActive ? ((L::STENCIL_B + 127) & ~127) : 0);
+
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int tileX = tx * SWCU_TILE_W, tileY = ty * SWCU_TILE_H;
 	const int rx = tileX + (warp % (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_W; // this warp's region
 	const int ry = tileY + (warp / (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_H;
-	const int qx0 = rx + 2 * (lane & 7), qy0 = ry + 2 * (lane >> 3);               // the quad whose coverage this lane computes
-	const int ly0 = qy0 - tileY;
+	const int qx0 = rx + 2 * (lane & 7);     // the quad whose coverage this lane computes
+	const int qr0 = 2 * (lane >> 3);         // its first row inside the region
 
-	if(threadIdx.x == 0) sm.dirty = 0;
-	// ---- stage the tile (made visible by the first chunk barrier) ----
-	const bool colorOn = d.colorWriteMask != 0 && d.colorBuf != nullptr;
-	if(colorOn) tile_copy<MS, uint32_t, false>(sm.color, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-	if(d.depthTestActive) tile_copy<MS, float, false>(sm.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-	if(d.stencilActive) tile_copy<MS, unsigned char, false>(sm.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	unsigned char *wa = warpBase + warp * L::W_BYTES;
+	uint4 *wHdr = (uint4 *)(wa + L::W_HDR);
+	float4 *wPlanes = (float4 *)(wa + L::W_PLANES);
+	uint32_t *wRows = (uint32_t *)(wa + L::W_ROWS);
+	unsigned short *wBits = (unsigned short *)(wa + L::W_BITS);
+	unsigned short *queue = (unsigned short *)(wa + L::W_QUEUE);
+	uint32_t *wTri = (uint32_t *)(wa + L::W_TRI);
+
+	// ---- stage the tile: TMA when the attachments allow it ----
+	if(threadIdx.x == 0)
+	{
+		*dirtyFlag = 0;
+		if(d.useTma)
+		{
+			mbar_init(bar, 1);
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+	}
+	__syncthreads();
+	if(d.useTma)
+	{
+		if(threadIdx.x == 0)
+		{
+			const uint32_t bytes = (colorOn ? L::PLANE_B : 0) + (d.depthTestActive ? L::PLANE_B : 0) + (d.stencilActive ? L::STENCIL_B : 0);
+			mbar_expect_tx(bar, bytes);
+			if(colorOn) tma_load_3d(smColor, &maps.color, bar, tileX, tileY, 0);
+			if(d.depthTestActive) tma_load_3d(smDepth, &maps.depth, bar, tileX, tileY, 0);
+			if(d.stencilActive) tma_load_3d(smStencil, &maps.stencil, bar, tileX, tileY, 0);
+		}
+	}
+	else
+	{
+		if(colorOn) tile_copy<MS, uint32_t, false>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		if(d.depthTestActive) tile_copy<MS, float, false>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		if(d.stencilActive) tile_copy<MS, unsigned char, false>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		__syncthreads();
+	}
+	bool tileReady = !d.useTma;
 
 	bool dirty = false;
 	const bool biasOn = d.depthBiasEnable != 0;
@@ -973,132 +1050,79 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 #pragma unroll
 	for(int ch = 0; ch < 4; ch++)
 		if((d.colorWriteMask >> ch) & 1) wmask32 |= 0xFFu << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
-	unsigned short *queue = sm.queue[warp];
 
-	for(uint32_t pos = begin; pos < end; pos += CH)
+	for(uint32_t pos = begin; pos < end; pos += 32)
 	{
-		const int n = (int)min((uint32_t)CH, end - pos);
-		// ---- A: triangle ids of the chunk; span rows default to empty ----
-		if((int)threadIdx.x < n) sm.tri[threadIdx.x] = d.direct ? pos + threadIdx.x : __ldg(triList + pos + threadIdx.x);
-		for(int i = threadIdx.x; i < n * SWCU_TILE_H * MS / 4; i += TILE_THREADS) ((uint4 *)&sm.span[0][0][0])[i] = make_uint4(0, 0, 0, 0);
-		__syncthreads();
-		// ---- B: records; consecutive threads read consecutive 16-byte pieces (header | planes | inline span rows) ----
-		bool anyBig = false;
-		for(int i = threadIdx.x; i < n * PIECES; i += TILE_THREADS)
+		// ---- scan 32 list entries: which of them touch my region? ----
+		const uint32_t li = pos + lane;
+		uint32_t tri = 0;
+		uint4 h = make_uint4(0, 0, 0, 0);
+		bool hit = false;
+		if(li < end)
 		{
-			const int c = i / PIECES, j = i % PIECES;
-			const unsigned char *rec = d.triRecords + (size_t)sm.tri[c] * d.triStride;
-			if(j <= NF4)
-			{
-				const float4 v = __ldg((const float4 *)rec + j);
-				if(j == 0)
-				{
-					sm.hdr[c] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
-					anyBig |= (__float_as_uint(v.w) & 2u) != 0;
-				}
-				else sm.planes[c][j - 1] = v;
-			}
-			else
-			{
-				// inline rows of a small triangle: record row rr is screen row yMin + rr
-				const uint4 v = __ldg((const uint4 *)rec + j);
-				const uint4 h = __ldg((const uint4 *)rec); // the header again (same sector as the planes another thread fetches)
-				const uint32_t flags = h.w;
-				const int yMin = h.y & 0xFFFF, yMax = h.y >> 16;
-				if(!(flags & 2u))
-				{
-					if(MS == 4)
-					{
-						const int rr = j - 1 - NF4, r = yMin + rr - tileY;
-						if(yMin + rr < yMax && r >= 0 && r < SWCU_TILE_H) *(uint4 *)&sm.span[c][r][0] = v;
-					}
-					else
-					{
-						const uint32_t e[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-						for(int t = 0; t < 4; t++)
-						{
-							const int rr = 4 * (j - 1 - NF4) + t, r = yMin + rr - tileY;
-							if(yMin + rr < yMax && r >= 0 && r < SWCU_TILE_H) sm.span[c][r][0] = e[t];
-						}
-					}
-				}
-			}
+			tri = d.direct ? li : __ldg(triList + li);
+			h = __ldg((const uint4 *)(d.triRecords + (size_t)tri * d.triStride));
+			const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+			hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
 		}
-		// ---- C: rows of the big triangles come from the span table ----
-		if(__syncthreads_or(anyBig))
+		uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+		while(m)
 		{
-			for(int i = threadIdx.x; i < n * SWCU_TILE_H; i += TILE_THREADS)
+			// ---- take the next NB candidates (list order) and stage their plane equations + region span rows ----
+			const int rank = __popc(m & ((1u << lane) - 1));
+			const bool mine = hit && ((m >> lane) & 1) && rank < NB;
+			const int nb = min(__popc(m), NB);
+			if(mine) { wHdr[rank] = h; wTri[rank] = tri; }
+			m &= ~__ballot_sync(0xFFFFFFFFu, mine);
+			__syncwarp();
+			for(int i = lane; i < nb * NF4; i += 32)
 			{
-				const int c = i / SWCU_TILE_H, r = i % SWCU_TILE_H;
-				const uint4 h = sm.hdr[c];
-				if(!(h.w & 2u)) continue;
-				const int y = tileY + r, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
-				if(y < yMin || y >= yMax) continue;
-				const uint32_t *sp = d.spans + h.z + (uint32_t)(y - yMin) * MS;
-				if(MS == 4) *(uint4 *)&sm.span[c][r][0] = __ldg((const uint4 *)sp);
-				else sm.span[c][r][0] = __ldg(sp);
+				const int s = i / NF4, j = i % NF4;
+				wPlanes[i] = __ldg((const float4 *)(d.triRecords + (size_t)wTri[s] * d.triStride + TRI_HEADER_BYTES) + j);
 			}
-			__syncthreads();
-		}
+			for(int i = lane; i < nb * SWCU_REGION_H; i += 32)
+			{
+				const int s = i / SWCU_REGION_H, r = i % SWCU_REGION_H;
+				const uint4 hh = wHdr[s];
+				const int y = ry + r, yMin = hh.y & 0xFFFF, yMax = hh.y >> 16;
+				uint4 v = make_uint4(0, 0, 0, 0); // empty span outside the triangle's rows
+				if(y >= yMin && y < yMax)
+				{
+					const uint32_t *src = (hh.w & 2u) ? d.spans + hh.z + (uint32_t)(y - yMin) * MS // big: span table
+					                                  : (const uint32_t *)(d.triRecords + (size_t)wTri[s] * d.triStride + TRI_HEADER_BYTES + 16 * NF4) + (y - yMin) * MS;
+					if(MS == 4) v = __ldg((const uint4 *)src); else v.x = __ldg(src);
+				}
+				if(MS == 4) *(uint4 *)(wRows + i * 4) = v; else wRows[i] = v.x;
+			}
+			__syncwarp();
 
-		// ---- D: per warp: candidates of my region, in list order ----
-		uint32_t mlo, mhi = 0;
-		{
-			bool hit = false;
-			if(lane < n)
-			{
-				const uint4 h = sm.hdr[lane];
-				const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
-				hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
-			}
-			mlo = __ballot_sync(0xFFFFFFFFu, hit);
-			if(CH > 32)
-			{
-				hit = false;
-				if(lane + 32 < n)
-				{
-					const uint4 h = sm.hdr[lane + 32];
-					const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
-					hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
-				}
-				mhi = __ballot_sync(0xFFFFFFFFu, hit);
-			}
-		}
-		while(mlo | mhi)
-		{
-			// ---- coverage bits of my quad for up to 32 candidates (QuadRasterizer.cpp:181-206 on the staged span rows) ----
-			int nb = 0;
+			// ---- coverage bits of my quad for every candidate (QuadRasterizer.cpp:181-206 on the staged span rows) ----
 			uint32_t myCount = 0;
-			while((mlo | mhi) && nb < 32)
+			for(int s = 0; s < nb; s++)
 			{
-				int c;
-				if(mlo) { c = __ffs(mlo) - 1; mlo &= mlo - 1; }
-				else { c = 32 + __ffs(mhi) - 1; mhi &= mhi - 1; }
 				uint32_t bits = 0;
 #pragma unroll
 				for(int iy = 0; iy < 2; iy++)
 				{
 					uint32_t sp[MS];
-					if(MS == 4) { const uint4 t = *(const uint4 *)&sm.span[c][ly0 + iy][0]; sp[0] = t.x; sp[1] = t.y; sp[2] = t.z; sp[3] = t.w; }
-					else sp[0] = sm.span[c][ly0 + iy][0];
+					const uint32_t *row = wRows + (s * SWCU_REGION_H + qr0 + iy) * MS;
+					if(MS == 4) { const uint4 t = *(const uint4 *)row; sp[0] = t.x; sp[1] = t.y; sp[2] = t.z; sp[3] = t.w; }
+					else sp[0] = row[0];
 #pragma unroll
 					for(int q = 0; q < MS; q++)
 					{
-						const int L = sp[q] & 0xFFFF, R = sp[q] >> 16;
+						const int Lx = sp[q] & 0xFFFF, Rx = sp[q] >> 16;
 #pragma unroll
 						for(int ix = 0; ix < 2; ix++)
 						{
 							const int x = qx0 + ix;
-							if(x >= L && x < R) bits |= 1u << ((iy * 2 + ix) * MS + q);
+							if(x >= Lx && x < Rx) bits |= 1u << ((iy * 2 + ix) * MS + q);
 						}
 					}
 				}
 				if(MS == 4) bits &= d.sampleMask * 0x1111u; // sample q masked out for all four pixels
-				sm.bits[warp][nb][lane] = (unsigned short)bits;
+				wBits[s * 32 + lane] = (unsigned short)bits;
 				myCount += __popc(bits);
-				if(lane == 0) sm.candIdx[warp][nb] = (unsigned char)c;
-				nb++;
 			}
 			// ---- compact the region's items into the queue: lane-major, each lane's items in list order ----
 			uint32_t incl = myCount;
@@ -1110,7 +1134,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 			}
 			const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
 			const uint32_t first = incl - myCount;
-			__syncwarp();
+			if(total && !tileReady)
+			{
+				while(!mbar_try_wait(bar, 0)) {} // the TMA loads of the tile have landed
+				tileReady = true;
+			}
 			for(uint32_t win = 0; win < total; win += TILE_QCAP)
 			{
 				if(first < win + TILE_QCAP && first + myCount > win)
@@ -1118,7 +1146,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 					uint32_t g = first;
 					for(int k = 0; k < nb && g < win + TILE_QCAP; k++)
 					{
-						uint32_t b = sm.bits[warp][k][lane];
+						uint32_t b = wBits[k * 32 + lane];
 						while(b)
 						{
 							const int bit = __ffs(b) - 1;
@@ -1138,24 +1166,23 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 					// items of the same (quad, pixel, sample) in this round run in queue order
 					const uint32_t key = valid ? (e & 0x1FFu) : (0x200u | lane);
 					const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-					const int rank = __popc(peers & ((1u << lane) - 1));
-					const int maxRank = __reduce_max_sync(0xFFFFFFFFu, valid ? rank : 0);
+					const int prank = __popc(peers & ((1u << lane) - 1));
+					const int maxRank = __reduce_max_sync(0xFFFFFFFFu, valid ? prank : 0);
 					for(int rr = 0; rr <= maxRank; rr++)
 					{
-						if(valid && rank == rr)
+						if(valid && prank == rr)
 						{
 							const int k = e >> 9, bit = (e >> 5) & 15, owner = e & 31;
 							const int i = bit / MS, q = bit % MS;
 							const int ix = i & 1, iy = i >> 1;
-							const int c = sm.candIdx[warp][k];
 							const int x = rx + 2 * (owner & 7) + ix, y = ry + 2 * (owner >> 3) + iy;
-							const int lx = x - tileX, ly = y - tileY;
+							const int pi = q * TP + (y - tileY) * SWCU_TILE_W + (x - tileX); // index inside the staged planes
 							// ---- plane equations of the triangle ----
 							float pf[NF4 * 4];
 #pragma unroll
 							for(int t = 0; t < NF4; t++)
 							{
-								const float4 v = sm.planes[c][t];
+								const float4 v = wPlanes[k * NF4 + t];
 								pf[4 * t] = v.x; pf[4 * t + 1] = v.y; pf[4 * t + 2] = v.z; pf[4 * t + 3] = v.w;
 							}
 							const float x0 = pf[0], y0 = pf[1], zBias = pf[2], wA = pf[3], wB = pf[4], wC = pf[5], zA = pf[6], zB = pf[7], zC = pf[8];
@@ -1202,11 +1229,11 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 							// ---- stencil test, depth test, depth write, blend + colour write, stencil write ----
 							bool sPass = true;
 							uint32_t sValue = 0;
-							const uint32_t triFlags = sm.hdr[c].w;
+							const uint32_t triFlags = wHdr[k].w;
 							if(d.stencilActive)
 							{
 								const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
-								sValue = sm.stencil[q][ly][lx];
+								sValue = smStencil[pi];
 								sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
 							}
 							bool zPass = true;
@@ -1218,14 +1245,14 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 								z = __fmaf_rn(xx, zA, fadd(zC, fmul(yy, zB)));
 								if(biasOn) z = fadd(z, zBias);
 								z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
-								zPass = depth_compare(d.depthCompareOp, sm.depth[q][ly][lx], z);
+								zPass = depth_compare(d.depthCompareOp, smDepth[pi], z);
 							}
 							if(zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
 							{
-								if(d.depthWriteEnable) { sm.depth[q][ly][lx] = z; dirty = true; }
+								if(d.depthWriteEnable) { smDepth[pi] = z; dirty = true; }
 								if(colorOn)
 								{
-									uint32_t px = sm.color[q][ly][lx];
+									const uint32_t px = smColor[pi];
 									float o[4] = { rgba[0], rgba[1], rgba[2], rgba[3] };
 									if(BL != BL_OFF)
 									{
@@ -1258,7 +1285,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 										const uint32_t v = (uint32_t)clampi(round_int(fmul(cl, 255.0f)), 0, 255);
 										pk |= v << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
 									}
-									sm.color[q][ly][lx] = (px & ~wmask32) | (pk & wmask32);
+									smColor[pi] = (px & ~wmask32) | (pk & wmask32);
 									dirty = true;
 								}
 							}
@@ -1271,7 +1298,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 								else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
 								else nv = stencil_op(face.passOp, sValue, ref);
 								const uint32_t wm = face.writeMask & 0xFF;
-								sm.stencil[q][ly][lx] = (unsigned char)((nv & wm) | (sValue & ~wm));
+								smStencil[pi] = (unsigned char)((nv & wm) | (sValue & ~wm));
 								dirty = true;
 							}
 						}
@@ -1280,16 +1307,34 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 				}
 				__syncwarp();
 			}
+			__syncwarp(); // the staging area is reused by the next batch
 		}
-		__syncthreads(); // the staging buffers are reused by the next chunk
 	}
 
-	if(__any_sync(0xFFFFFFFFu, dirty) && lane == 0) sm.dirty = 1;
+	if(!tileReady)
+		while(!mbar_try_wait(bar, 0)) {} // never leave with a bulk copy into this CTA's shared memory still in flight
+	if(__any_sync(0xFFFFFFFFu, dirty) && lane == 0) *dirtyFlag = 1;
 	__syncthreads();
-	if(!sm.dirty) return;
-	if(colorOn) tile_copy<MS, uint32_t, true>(sm.color, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-	if(d.depthWriteEnable) tile_copy<MS, float, true>(sm.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-	if(d.stencilWrite) tile_copy<MS, unsigned char, true>(sm.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	if(!*dirtyFlag) return;
+	if(d.useTma)
+	{
+		fence_proxy_async(); // generic-proxy writes of the tile -> visible to the async proxy
+		__syncthreads();
+		if(threadIdx.x == 0)
+		{
+			if(colorOn) tma_store_3d(&maps.color, smColor, tileX, tileY, 0);
+			if(d.depthWriteEnable) tma_store_3d(&maps.depth, smDepth, tileX, tileY, 0);
+			if(d.stencilWrite) tma_store_3d(&maps.stencil, smStencil, tileX, tileY, 0);
+			tma_commit();
+			tma_wait_read0();
+		}
+	}
+	else
+	{
+		if(colorOn) tile_copy<MS, uint32_t, true>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		if(d.depthWriteEnable) tile_copy<MS, float, true>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		if(d.stencilWrite) tile_copy<MS, unsigned char, true>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------------------

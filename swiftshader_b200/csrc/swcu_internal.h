@@ -183,6 +183,7 @@ struct DrawConst
 	int32_t tileX0, tileY0, tileX1, tileY1; // tile range touched by the scissor (exclusive upper)
 	uint32_t direct;           // 1: no binning, every tile CTA walks all triangles
 	uint32_t blendClass;       // BL_*
+	uint32_t useTma;           // attachments satisfy the tensor-map alignment rules: stage the tile with TMA
 };
 
 // TriRecord layout (triStride bytes, 16-byte aligned):
