@@ -911,9 +911,10 @@ struct TileLayout
 	static constexpr int W_HDR = 0;                                  // uint4 hdr[NB]
 	static constexpr int W_PLANES = W_HDR + 16 * NB;                 // float4 planes[NB][NF4]
 	static constexpr int W_ROWS = W_PLANES + 16 * NB * NF4;          // uint32 rows[NB][REGION_H][MS]
-	static constexpr int W_BITS = W_ROWS + 4 * NB * SWCU_REGION_H * MS; // uint16 bits[NB][32]
-	static constexpr int W_QUEUE = W_BITS + 2 * NB * 32;             // uint16 queue[QCAP]
-	static constexpr int W_TRI = W_QUEUE + 2 * TILE_QCAP;            // uint32 tri[NB]
+	static constexpr int MAXPAIRS = NB * (MS == 4 ? 32 : SWCU_REGION_H);     // (candidate, region row, sample) pairs with coverage
+	static constexpr int W_PAIRS = W_ROWS + 4 * NB * SWCU_REGION_H * MS;     // uint32 pairs[MAXPAIRS]: cand << 21 | code << 16 | x-mask
+	static constexpr int W_PSUM = W_PAIRS + 4 * MAXPAIRS;                    // uint16 psum[MAXPAIRS + 1]: items before pair p
+	static constexpr int W_TRI = (W_PSUM + 2 * (MAXPAIRS + 1) + 3) & ~3;     // uint32 tri[NB]
 	static constexpr int W_BYTES = (W_TRI + 4 * NB + 127) & ~127;
 	static constexpr int HEAD_B = 128;                               // mbarrier + dirty flag
 	__host__ __device__ static int total(bool depth, bool stencil)
@@ -1002,15 +1003,17 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 	const int tileX = tx * SWCU_TILE_W, tileY = ty * SWCU_TILE_H;
 	const int rx = tileX + (warp % (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_W; // this warp's region
 	const int ry = tileY + (warp / (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_H;
-	const int qx0 = rx + 2 * (lane & 7);     // the quad whose coverage this lane computes
-	const int qr0 = 2 * (lane >> 3);         // its first row inside the region
+	// coverage is computed per (region row, sample): MS == 4: lane = row * 4 + sample; MS == 1: lane = sub * 8 + row, four candidates at a time
+	const int covRow = MS == 4 ? lane >> 2 : lane & 7;
+	const int covQ = MS == 4 ? lane & 3 : 0;
+	const bool covOn = MS == 4 ? ((d.sampleMask >> covQ) & 1) != 0 : true;
 
 	unsigned char *wa = warpBase + warp * L::W_BYTES;
 	uint4 *wHdr = (uint4 *)(wa + L::W_HDR);
 	float4 *wPlanes = (float4 *)(wa + L::W_PLANES);
 	uint32_t *wRows = (uint32_t *)(wa + L::W_ROWS);
-	unsigned short *wBits = (unsigned short *)(wa + L::W_BITS);
-	unsigned short *queue = (unsigned short *)(wa + L::W_QUEUE);
+	uint32_t *wPairs = (uint32_t *)(wa + L::W_PAIRS);
+	unsigned short *wPsum = (unsigned short *)(wa + L::W_PSUM);
 	uint32_t *wTri = (uint32_t *)(wa + L::W_TRI);
 
 	// ---- stage the tile: TMA when the attachments allow it ----
@@ -1096,75 +1099,70 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 			}
 			__syncwarp();
 
-			// ---- coverage bits of my quad for every candidate (QuadRasterizer.cpp:181-206 on the staged span rows) ----
-			uint32_t myCount = 0;
-			for(int s = 0; s < nb; s++)
+			// ---- coverage (QuadRasterizer.cpp:181-206): one lane per (region row, sample) turns the span [left, right) into a
+			//      16-bit x-mask of the row; (candidate, row, sample) pairs with coverage are compacted in candidate order ----
+			int P = 0;
+			constexpr int CPI = MS == 4 ? 1 : 4; // candidates per iteration
+			for(int s0 = 0; s0 < nb; s0 += CPI)
 			{
-				uint32_t bits = 0;
-#pragma unroll
-				for(int iy = 0; iy < 2; iy++)
+				const int s = MS == 4 ? s0 : s0 + (lane >> 3);
+				uint32_t mask = 0;
+				if(s < nb && covOn)
 				{
-					uint32_t sp[MS];
-					const uint32_t *row = wRows + (s * SWCU_REGION_H + qr0 + iy) * MS;
-					if(MS == 4) { const uint4 t = *(const uint4 *)row; sp[0] = t.x; sp[1] = t.y; sp[2] = t.z; sp[3] = t.w; }
-					else sp[0] = row[0];
-#pragma unroll
-					for(int q = 0; q < MS; q++)
-					{
-						const int Lx = sp[q] & 0xFFFF, Rx = sp[q] >> 16;
-#pragma unroll
-						for(int ix = 0; ix < 2; ix++)
-						{
-							const int x = qx0 + ix;
-							if(x >= Lx && x < Rx) bits |= 1u << ((iy * 2 + ix) * MS + q);
-						}
-					}
+					const uint32_t sp = wRows[(s * SWCU_REGION_H + covRow) * MS + covQ];
+					const int a = clampi((int)(sp & 0xFFFF) - rx, 0, 16), e = clampi((int)(sp >> 16) - rx, 0, 16);
+					if(e > a) mask = ((1u << e) - 1u) & ~((1u << a) - 1u);
 				}
-				if(MS == 4) bits &= d.sampleMask * 0x1111u; // sample q masked out for all four pixels
-				wBits[s * 32 + lane] = (unsigned short)bits;
-				myCount += __popc(bits);
+				const uint32_t nz = __ballot_sync(0xFFFFFFFFu, mask != 0);
+				if(mask) wPairs[P + __popc(nz & ((1u << lane) - 1))] = ((uint32_t)s << 21) | ((uint32_t)(MS == 4 ? lane : covRow) << 16) | mask;
+				P += __popc(nz);
 			}
-			// ---- compact the region's items into the queue: lane-major, each lane's items in list order ----
-			uint32_t incl = myCount;
-#pragma unroll
-			for(int o = 1; o < 32; o <<= 1)
+			__syncwarp();
+			// ---- items before each pair (exclusive prefix sum of the mask popcounts) ----
+			uint32_t total = 0;
+			for(int p0 = 0; p0 < P; p0 += 32)
 			{
-				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-				if(lane >= o) incl += t;
+				const int p = p0 + lane;
+				const uint32_t c = p < P ? __popc(wPairs[p] & 0xFFFFu) : 0u;
+				uint32_t incl = c;
+#pragma unroll
+				for(int o = 1; o < 32; o <<= 1)
+				{
+					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+					if(lane >= o) incl += t;
+				}
+				if(p < P) wPsum[p] = (unsigned short)(total + incl - c);
+				total += __shfl_sync(0xFFFFFFFFu, incl, 31);
 			}
-			const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-			const uint32_t first = incl - myCount;
+			if(lane == 0) wPsum[P] = (unsigned short)total;
+			__syncwarp();
 			if(total && !tileReady)
 			{
 				while(!mbar_try_wait(bar, 0)) {} // the TMA loads of the tile have landed
 				tileReady = true;
 			}
-			for(uint32_t win = 0; win < total; win += TILE_QCAP)
+			// ---- consume the items 32 at a time, one per lane ----
 			{
-				if(first < win + TILE_QCAP && first + myCount > win)
+				for(uint32_t base = 0; base < total; base += 32)
 				{
-					uint32_t g = first;
-					for(int k = 0; k < nb && g < win + TILE_QCAP; k++)
+					const uint32_t g = base + lane;
+					const bool valid = g < total;
+					uint32_t e = 0;
+					int bit = 0;
+					if(valid)
 					{
-						uint32_t b = wBits[k * 32 + lane];
-						while(b)
+						int lo = 0, hi = P; // largest p with psum[p] <= g
+						while(hi - lo > 1)
 						{
-							const int bit = __ffs(b) - 1;
-							b &= b - 1;
-							if(g >= win && g < win + TILE_QCAP) queue[g - win] = (unsigned short)((k << 9) | (bit << 5) | lane);
-							g++;
+							const int mid = (lo + hi) >> 1;
+							if(wPsum[mid] <= g) lo = mid; else hi = mid;
 						}
+						e = wPairs[lo];
+						bit = __fns(e & 0xFFFFu, 0, (int)(g - wPsum[lo]) + 1);
 					}
-				}
-				__syncwarp();
-				const int cnt = (int)min((uint32_t)TILE_QCAP, total - win);
-				for(int base = 0; base < cnt; base += 32)
-				{
-					const int j = base + lane;
-					const bool valid = j < cnt;
-					const uint32_t e = valid ? queue[j] : 0u;
 					// items of the same (quad, pixel, sample) in this round run in queue order
-					const uint32_t key = valid ? (e & 0x1FFu) : (0x200u | lane);
+					const uint32_t code = (e >> 16) & 31;
+					const uint32_t key = valid ? ((code << 4) | (uint32_t)bit) : (0x200u | lane); // one key per sample of the region
 					const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
 					const int prank = __popc(peers & ((1u << lane) - 1));
 					const int maxRank = __reduce_max_sync(0xFFFFFFFFu, valid ? prank : 0);
@@ -1172,10 +1170,10 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 					{
 						if(valid && prank == rr)
 						{
-							const int k = e >> 9, bit = (e >> 5) & 15, owner = e & 31;
-							const int i = bit / MS, q = bit % MS;
-							const int ix = i & 1, iy = i >> 1;
-							const int x = rx + 2 * (owner & 7) + ix, y = ry + 2 * (owner >> 3) + iy;
+							const int k = e >> 21;
+							const int q = MS == 4 ? (int)(code & 3) : 0;
+							const int x = rx + bit, y = ry + (MS == 4 ? (int)(code >> 2) : (int)code);
+							const int ix = x & 1, iy = y & 1;
 							const int pi = q * TP + (y - tileY) * SWCU_TILE_W + (x - tileX); // index inside the staged planes
 							// ---- plane equations of the triangle ----
 							float pf[NF4 * 4];
