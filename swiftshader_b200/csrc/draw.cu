@@ -564,6 +564,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 			d.mip[l].buffer = dev_ptr(ctx, m.buffer, (size_t)m.pitchP * (m.height - 1) * 4 + (size_t)m.width * 4);
 			if(!d.mip[l].buffer) return fail(ctx, SWCU_E_INVALID, "mip level %d buffer %p is not inside a registered range", l, m.buffer);
 			d.mip[l].width = m.width; d.mip[l].height = m.height; d.mip[l].pitchP = m.pitchP;
+			d.mip[l].half = ((0x8000u / m.width) & 0xFFFFu) | (((0x8000u / m.height) & 0xFFFFu) << 16);
 		}
 		d.magFilter = t->magFilter; d.minFilter = t->minFilter; d.mipmapMode = t->mipmapMode;
 		d.addressU = t->addressModeU; d.addressV = t->addressModeV;

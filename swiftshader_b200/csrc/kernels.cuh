@@ -654,7 +654,7 @@ DEVI void sample_level(const DrawConst &d, int level, float u, float v, bool lin
 		for(int c = 0; c < 4; c++) out[c] = ((t >> (8 * c)) & 0xFF) << 8;
 		return;
 	}
-	const uint32_t uHalf = (0x8000u / m.width) & 0xFFFF, vHalf = (0x8000u / m.height) & 0xFFFF;
+	const uint32_t uHalf = m.half & 0xFFFF, vHalf = m.half >> 16; // 0x8000 / extent, VkDescriptorSetLayout.cpp:315
 	const bool wrapU = d.addressU == ADDR_REPEAT, wrapV = d.addressV == ADDR_REPEAT;
 	const uint32_t u0 = offset_sample(uu, uHalf, wrapU, -1), u1 = offset_sample(uu, uHalf, wrapU, +1);
 	const uint32_t v0 = offset_sample(vv, vHalf, wrapV, -1), v1 = offset_sample(vv, vHalf, wrapV, +1);
@@ -1054,29 +1054,44 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 	for(int ch = 0; ch < 4; ch++)
 		if((d.colorWriteMask >> ch) & 1) wmask32 |= 0xFFu << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
 
-	for(uint32_t pos = begin; pos < end; pos += 32)
+	int ns = 0;        // candidates staged so far for the next batch
+	uint32_t pend = 0; // lanes whose scanned hit is not staged yet
+	uint32_t tri = 0;
+	uint4 h = make_uint4(0, 0, 0, 0);
+	for(uint32_t pos = begin;;)
 	{
-		// ---- scan 32 list entries: which of them touch my region? ----
-		const uint32_t li = pos + lane;
-		uint32_t tri = 0;
-		uint4 h = make_uint4(0, 0, 0, 0);
-		bool hit = false;
-		if(li < end)
+		if(!pend && pos < end)
 		{
-			tri = d.direct ? li : __ldg(triList + li);
-			h = __ldg((const uint4 *)(d.triRecords + (size_t)tri * d.triStride));
-			const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
-			hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
+			// ---- scan 32 list entries: which of them touch my region? ----
+			const uint32_t li = pos + lane;
+			bool hit = false;
+			if(li < end)
+			{
+				tri = d.direct ? li : __ldg(triList + li);
+				h = __ldg((const uint4 *)(d.triRecords + (size_t)tri * d.triStride));
+				const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+				hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
+			}
+			pend = __ballot_sync(0xFFFFFFFFu, hit);
+			pos += 32;
 		}
-		uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-		while(m)
+		if(pend)
 		{
-			// ---- take the next NB candidates (list order) and stage their plane equations + region span rows ----
-			const int rank = __popc(m & ((1u << lane) - 1));
-			const bool mine = hit && ((m >> lane) & 1) && rank < NB;
-			const int nb = min(__popc(m), NB);
-			if(mine) { wHdr[rank] = h; wTri[rank] = tri; }
-			m &= ~__ballot_sync(0xFFFFFFFFu, mine);
+			// ---- hits go to the free slots of the batch, in list order; the rest wait for the next batch ----
+			const int rank = __popc(pend & ((1u << lane) - 1));
+			const int take = min(__popc(pend), NB - ns);
+			const bool mine = ((pend >> lane) & 1) && rank < take;
+			if(mine) { wHdr[ns + rank] = h; wTri[ns + rank] = tri; }
+			pend &= ~__ballot_sync(0xFFFFFFFFu, mine);
+			ns += take;
+		}
+		const bool listDone = pend == 0 && pos >= end;
+		if(ns < NB && !listDone) continue;
+		if(ns == 0) break;
+		{
+			// ---- stage the batch: plane equations + the span rows that cross my region ----
+			const int nb = ns;
+			ns = 0;
 			__syncwarp();
 			for(int i = lane; i < nb * NF4; i += 32)
 			{
@@ -1143,22 +1158,25 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 			}
 			// ---- consume the items 32 at a time, one per lane ----
 			{
+				int cursor = 0; // pair that holds item `base`
 				for(uint32_t base = 0; base < total; base += 32)
 				{
 					const uint32_t g = base + lane;
 					const bool valid = g < total;
+					// a round of 32 consecutive items spans at most 32 pairs (every pair has >= 1 item): lane j looks at the end
+					// of pair cursor + j; the ends that fall inside the round mark where the next pairs start
+					const int pj = cursor + lane;
+					const uint32_t endj = pj < P ? wPsum[pj + 1] : 0xFFFFFFFFu;
+					const uint32_t rel = endj - base;
+					const uint32_t starts = __reduce_or_sync(0xFFFFFFFFu, (pj < P && rel < 32u) ? (1u << rel) : 0u);
+					const int myPair = cursor + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+					cursor += __popc(__ballot_sync(0xFFFFFFFFu, pj < P && rel <= 32u));
 					uint32_t e = 0;
 					int bit = 0;
 					if(valid)
 					{
-						int lo = 0, hi = P; // largest p with psum[p] <= g
-						while(hi - lo > 1)
-						{
-							const int mid = (lo + hi) >> 1;
-							if(wPsum[mid] <= g) lo = mid; else hi = mid;
-						}
-						e = wPairs[lo];
-						bit = __fns(e & 0xFFFFu, 0, (int)(g - wPsum[lo]) + 1);
+						e = wPairs[myPair];
+						bit = (__ffs(e & 0xFFFFu) - 1) + (int)(g - wPsum[myPair]); // the x-mask is one run of ones
 					}
 					// items of the same (quad, pixel, sample) in this round run in queue order
 					const uint32_t code = (e >> 16) & 31;
@@ -1280,7 +1298,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 									for(int ch = 0; ch < 4; ch++) // writeColor :1981-1992, :2603-2655
 									{
 										const float cl = sse_min(sse_max(o[ch], 0.0f), 1.0f);
-										const uint32_t v = (uint32_t)clampi(round_int(fmul(cl, 255.0f)), 0, 255);
+										const uint32_t v = (uint32_t)__float2int_rn(fmul(cl, 255.0f)); // cl in [0,1] (NaN already folded to 0)
 										pk |= v << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
 									}
 									smColor[pi] = (px & ~wmask32) | (pk & wmask32);
@@ -1307,6 +1325,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 			}
 			__syncwarp(); // the staging area is reused by the next batch
 		}
+		if(listDone) break;
 	}
 
 	if(!tileReady)

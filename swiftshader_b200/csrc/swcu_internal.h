@@ -88,7 +88,8 @@ struct KVSrc
 struct KMip
 {
 	const unsigned char *buffer;
-	uint32_t width, height, pitchP, pad;
+	uint32_t width, height, pitchP;
+	uint32_t half; // (0x8000 / width) | (0x8000 / height) << 16: the half-texel offsets of Mipmap::uHalf/vHalf (Sampler.hpp:25-39)
 };
 
 struct KStencilFace
