@@ -43,7 +43,7 @@ struct swcu_ctx
 	cudaStream_t stream = nullptr, ownStream = nullptr;
 	std::map<uintptr_t, Shadow> mem;
 	std::string err;
-	DevBuf triRecords, spans, bigList, tileCount, pairOffset, keys, vals, keys2, vals2, tileBegin, tileEnd, cubTemp, counters;
+	DevBuf triRecords, spans, bigList, tileCount, pairOffset, keys, vals, keys2, vals2, tileBegin, tileEnd, cubTemp, counters, zeroPage;
 	DrawCounters *hostCounters = nullptr; // pinned
 	swcu_stats stats{};
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -137,7 +137,7 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 		if(!kv.second.external) cudaFree(kv.second.dev);
 	}
 	DevBuf *bufs[] = { &ctx->triRecords, &ctx->spans, &ctx->bigList, &ctx->tileCount, &ctx->pairOffset, &ctx->keys, &ctx->vals,
-		               &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->counters };
+		               &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->counters, &ctx->zeroPage };
 	for(DevBuf *b : bufs) cudaFree(b->p);
 	for(cudaEvent_t ev : ctx->eventPool) cudaEventDestroy(ev);
 	if(ctx->hostCounters) cudaFreeHost(ctx->hostCounters);
@@ -738,6 +738,11 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	if((rc = ensure(ctx, ctx->triRecords, (size_t)n * d.triStride))) return rc;
 	if((rc = ensure(ctx, ctx->tileCount, (size_t)n * 4))) return rc;
 	if((rc = ensure(ctx, ctx->counters, sizeof(DrawCounters)))) return rc;
+	if(!ctx->zeroPage.p)
+	{
+		if((rc = ensure(ctx, ctx->zeroPage, 256))) return rc;
+		CU(cudaMemsetAsync(ctx->zeroPage.p, 0, 256, ctx->stream));
+	}
 	const size_t scRows = (size_t)(d.scY1 - d.scY0);
 	size_t spanWant, bigWant;
 	if(d.direct) { spanWant = (size_t)n * d.ms * scRows; bigWant = n; }
@@ -756,6 +761,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		d.triRecords = (unsigned char *)ctx->triRecords.p;
 		d.tileCount = (uint32_t *)ctx->tileCount.p;
 		d.counters = (DrawCounters *)ctx->counters.p;
+		d.zeroPage = ctx->zeroPage.p;
 		d.spans = (uint32_t *)ctx->spans.p;
 		d.spanCapacity = std::min<unsigned long long>(ctx->spans.cap / 4, 0xFFFFFFFFull);
 		d.bigList = (BigTri *)ctx->bigList.p;

@@ -80,10 +80,13 @@ DEVI void triangle_indices(const DrawConst &d, uint32_t i, uint32_t idx[3])
 // robustBufferAccess clamp (VertexRoutine::readStream, VertexRoutine.cpp:173-245; offsets wrap in 32 bits like the reference)
 DEVI float vs_operand(const DrawConst &d, const KVSrc &src, uint32_t index)
 {
-	if(!src.ptr) return src.constant;
+	// branch-free: the load is always issued (from a scratch address when the value is a constant or out of bounds), so the
+	// compiler can batch every attribute fetch of a triangle into one round trip
 	const uint32_t offset = (index + (uint32_t)d.baseVertex) * src.stride;
-	if(offset > src.limit) return 0.0f;
-	return __ldg((const float *)(src.ptr + offset));
+	const bool ok = src.ptr != nullptr && offset <= src.limit;
+	const float *p = ok ? (const float *)(src.ptr + offset) : (const float *)d.zeroPage;
+	const float v = __ldg(p);
+	return ok ? v : (src.ptr ? 0.0f : src.constant);
 }
 
 struct VOut
@@ -94,10 +97,8 @@ struct VOut
 	float zp, rhw; // projected.z, projected.w
 };
 
-DEVI void process_vertex(const DrawConst &d, uint32_t index, VOut &v)
+DEVI void process_vertex(const DrawConst &d, float px, float py, float pz, float pw, VOut &v)
 {
-	const float px = vs_operand(d, d.vsPos[0], index), py = vs_operand(d, d.vsPos[1], index);
-	const float pz = vs_operand(d, d.vsPos[2], index), pw = vs_operand(d, d.vsPos[3], index);
 	v.px = px; v.py = py; v.pz = pz; v.pw = pw;
 	int f = 0; // computeClipFlags, VertexRoutine.cpp:128-152
 	if(pw < px) f |= CLIP_RIGHT;
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 	bool visible = false;
 	uint32_t idx[3] = { 0, 0, 0 };
 	VOut v[3];
+	float sv[3][SWCU_MAXSLOTS]; // slot sources at the three vertices
 	int PX[SWCU_POLY_MAX], PY[SWCU_POLY_MAX];
 	int n = 3, dir = 1;
 	bool frontFacing = false;
@@ -284,9 +286,19 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 		do
 		{
 			triangle_indices(d, tri, idx);
-			process_vertex(d, idx[0], v[0]);
-			process_vertex(d, idx[1], v[1]);
-			process_vertex(d, idx[2], v[2]);
+			// every attribute the two stages consume, for the three vertices, fetched up front
+			float pos[3][4];
+#pragma unroll
+			for(int a = 0; a < 3; a++)
+#pragma unroll
+				for(int c = 0; c < 4; c++) pos[a][c] = vs_operand(d, d.vsPos[c], idx[a]);
+#pragma unroll
+			for(int a = 0; a < 3; a++)
+#pragma unroll
+				for(int k = 0; k < SWCU_MAXSLOTS; k++) sv[a][k] = k < d.nslots ? vs_operand(d, d.slotSrc[k], idx[a]) : 0.0f;
+			process_vertex(d, pos[0][0], pos[0][1], pos[0][2], pos[0][3], v[0]);
+			process_vertex(d, pos[1][0], pos[1][1], pos[1][2], pos[1][3], v[1]);
+			process_vertex(d, pos[2][0], pos[2][1], pos[2][2], pos[2][3], v[2]);
 
 			// setupSolidTriangles, Renderer.cpp:749-757
 			if((v[0].flags & v[1].flags & v[2].flags) != CLIP_FINITE) break;
@@ -478,19 +490,20 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 	else { f[6] = 0; f[7] = 0; f[8] = 0; }
 	f[2] = zBias;
 	// setupGradient, SetupRoutine.cpp:514-548
-	const uint32_t vi0 = i0 == 0 ? idx[0] : (i0 == 1 ? idx[1] : idx[2]);
-	const uint32_t vi1 = i1 == 0 ? idx[0] : (i1 == 1 ? idx[1] : idx[2]);
-	const uint32_t vi2 = i2 == 0 ? idx[0] : (i2 == 1 ? idx[1] : idx[2]);
-	for(int k = 0; k < d.nslots; k++)
+#pragma unroll
+	for(int k = 0; k < SWCU_MAXSLOTS; k++)
 	{
+		if(k >= d.nslots) break;
 		float *P = f + TRI_FLOATS_FIXED + 3 * k;
 		const uint32_t mode = d.slotMode[k];
 		if(mode == IM_FLAT)
 		{
-			P[0] = 0; P[1] = 0; P[2] = vs_operand(d, d.slotSrc[k], idx[0]); // provoking vertex = Triangle.v0 (or a constant)
+			P[0] = 0; P[1] = 0; P[2] = sv[0][k]; // provoking vertex = Triangle.v0 (or a constant)
 			continue;
 		}
-		float a0 = vs_operand(d, d.slotSrc[k], vi0), a1 = vs_operand(d, d.slotSrc[k], vi1), a2 = vs_operand(d, d.slotSrc[k], vi2);
+		float a0 = i0 == 0 ? sv[0][k] : (i0 == 1 ? sv[1][k] : sv[2][k]);
+		float a1 = i1 == 0 ? sv[0][k] : (i1 == 1 ? sv[1][k] : sv[2][k]);
+		float a2 = i2 == 0 ? sv[0][k] : (i2 == 1 ? sv[1][k] : sv[2][k]);
 		if(mode == IM_NOPERSP) { a0 = fmul(a0, w0); a1 = fmul(a1, w1); a2 = fmul(a2, w2); }
 		P[0] = fadd(fadd(fmul(a0, M00), fmul(a1, M10)), fmul(a2, M20));
 		P[1] = fadd(fadd(fmul(a0, M01), fmul(a1, M11)), fmul(a2, M21));

@@ -180,6 +180,7 @@ struct DrawConst
 	uint32_t bigCapacity;
 	uint32_t *tileCount;       // per triangle: number of (tile, triangle) pairs it will emit
 	DrawCounters *counters;
+	const void *zeroPage;      // 256 readable bytes: target of the discarded loads of branch-free attribute fetches
 	int32_t tilesX, tilesY;    // tile grid of the framebuffer
 	int32_t tileX0, tileY0, tileX1, tileY1; // tile range touched by the scissor (exclusive upper)
 	uint32_t direct;           // 1: no binning, every tile CTA walks all triangles
