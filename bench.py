@@ -142,7 +142,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from swiftshader_b200 import workloads
+    from swiftshader_b200 import bands, workloads
     from swiftshader_b200.scene import Device, Frame
     from swiftshader_b200 import capi
     import ctypes as C
@@ -158,10 +158,8 @@ def main():
     wl = workloads.WORKLOADS[args.workload]()
     sc = wl.scene
     H, W = sc.height, sc.width
-    if H % (2 * N):
-        raise SystemExit(f"framebuffer height {H} does not split into {N} even bands")
-    band = (rank * H // N, (rank + 1) * H // N)
-    area = (0, band[0], W, band[1] - band[0])
+    band = bands.band_rows(H, N, rank)
+    area = bands.render_area(W, H, N, rank)
 
     dev = Device(local_rank)
     stream = torch.cuda.Stream()
@@ -186,14 +184,13 @@ def main():
     full = None
     if N > 1:
         full = torch.as_tensor(_DevArr(frame.final_device_ptr(), H * pitch), device=f"cuda:{local_rank}")
-        mine = full[band[0] * pitch: band[1] * pitch]
 
     def step():
         frame.draw()
         if dst_b is not None:
             dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(dst_b)))
         if N > 1:
-            dist.all_gather_into_tensor(full, mine)  # in place: my band is already at its slot
+            bands.gather_bands(full, H, pitch, N, rank)  # NCCL all-gather, in place: my band is already at its slot
 
     def barrier():
         if N > 1:

@@ -1,0 +1,58 @@
+"""Run under torchrun on N GPUs: every rank renders its band of the reduced-size workloads through the CUDA path, the bands
+are all-gathered over NCCL, and rank 0 compares the assembled frame with the CPU oracle's full-frame render (bit-exact).
+  python -m torch.distributed.run --nproc-per-node N tests/multi_gpu_check.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import swref  # noqa: E402
+from swiftshader_b200 import bands, workloads  # noqa: E402
+from swiftshader_b200.scene import Device, Frame  # noqa: E402
+
+
+class _DevArr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = Device(local)
+    stream = torch.cuda.Stream()
+    dev.set_stream(stream.cuda_stream)
+    bad = 0
+    for name in ("c4", "c5", "c2"):
+        sc = workloads.small(name).scene
+        H, W = sc.height, sc.width
+        if H % (2 * world):
+            continue
+        fr = Frame(dev, sc, render_area=bands.render_area(W, H, world, rank))
+        with torch.cuda.stream(stream):
+            fr.upload_inputs(); fr.clear(); fr.draw(); fr.resolve()
+            full = torch.as_tensor(_DevArr(fr.final_device_ptr(), H * W * 4), device=f"cuda:{local}")
+            bands.gather_bands(full, H, W * 4, world, rank)
+            torch.cuda.synchronize()
+            got = full.cpu().numpy().reshape(H, W, 4)
+        fr.close()
+        if rank == 0:
+            want = swref.render_oracle(sc)
+            ref = swref.resolve_oracle(sc, want) if sc.samples > 1 else want["color"][0]
+            ok = np.array_equal(got, ref[:H])
+            print(f"multi_gpu_check {name} world={world}: {'ok' if ok else 'MISMATCH'}", flush=True)
+            bad += 0 if ok else 1
+    dev.close()
+    dist.destroy_process_group()
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
