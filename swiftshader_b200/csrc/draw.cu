@@ -569,6 +569,8 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		d.magFilter = t->magFilter; d.minFilter = t->minFilter; d.mipmapMode = t->mipmapMode;
 		d.addressU = t->addressModeU; d.addressV = t->addressModeV;
 		d.mipLodBias = t->mipLodBias; d.minLod = t->minLod; d.maxLod = t->maxLod;
+		d.texFast = t->magFilter == FILTER_LINEAR && t->minFilter == FILTER_LINEAR && t->mipmapMode == MIPMAP_MODE_LINEAR &&
+		            t->addressModeU == ADDR_REPEAT && t->addressModeV == ADDR_REPEAT;
 	}
 
 	// ---- setup state ----

@@ -26,8 +26,8 @@
 // ------------------------------------------------------------------------------------------------------------------
 // small helpers (Reactor semantics on x86: LLVMReactor.cpp:135-138,2694-2703)
 // ------------------------------------------------------------------------------------------------------------------
-DEVI int round_int(float x) { return (x != x) ? (int)0x80000000 : __float2int_rn(x); } // cvtps2dq: NaN -> indefinite
-DEVI int trunc_int(float x) { return (x != x) ? (int)0x80000000 : __float2int_rz(x); } // cvttps2dq
+DEVI int round_int(float x) { return !(x < 2147483648.0f) ? (int)0x80000000 : __float2int_rn(x); } // cvtps2dq: NaN / overflow -> "integer indefinite"
+DEVI int trunc_int(float x) { return !(x < 2147483648.0f) ? (int)0x80000000 : __float2int_rz(x); } // cvttps2dq
 DEVI int round_int_clamped(float x) { float c = x < 2147483520.0f ? x : 2147483520.0f; return round_int(c); }
 DEVI float sse_max(float a, float b) { return a > b ? a : b; } // maxps: second operand unless strictly greater
 DEVI float sse_min(float a, float b) { return a < b ? a : b; }
@@ -652,15 +652,17 @@ DEVI uint32_t offset_sample(uint32_t uvw, uint32_t half, bool wrap, int count) /
 
 DEVI uint32_t load_texel(const KMip &m, uint32_t x, uint32_t y) { return __ldg((const uint32_t *)m.buffer + (x + y * m.pitchP)); }
 
-// one tap set of one mip level; out[c] are 16-bit channel values
+// one tap set of one mip level; out[c] are 16-bit channel values.  FAST = REPEAT/REPEAT addressing + linear filter (the
+// benchmark sampler): same arithmetic with the state tests folded away.
+template<bool FAST>
 DEVI void sample_level(const DrawConst &d, int level, float u, float v, bool linear, uint32_t out[4])
 {
 	level = clampi(level, 0, SWCU_MIPMAP_LEVELS - 1);
 	const int l = level < (int)d.texLevels ? level : (int)d.texLevels - 1; // VkDescriptorSetLayout.cpp:470
 	const KMip &m = d.mip[l];
 	const uint32_t W = m.width & 0xFFFF, H = m.height & 0xFFFF;
-	const uint32_t uu = tex_address(u, d.addressU), vv = tex_address(v, d.addressV);
-	if(!linear)
+	const uint32_t uu = tex_address(u, FAST ? (uint32_t)ADDR_REPEAT : d.addressU), vv = tex_address(v, FAST ? (uint32_t)ADDR_REPEAT : d.addressV);
+	if(!FAST && !linear)
 	{
 		const uint32_t t = load_texel(m, mulhi16(uu, W), mulhi16(vv, H));
 #pragma unroll
@@ -668,21 +670,24 @@ DEVI void sample_level(const DrawConst &d, int level, float u, float v, bool lin
 		return;
 	}
 	const uint32_t uHalf = m.half & 0xFFFF, vHalf = m.half >> 16; // 0x8000 / extent, VkDescriptorSetLayout.cpp:315
-	const bool wrapU = d.addressU == ADDR_REPEAT, wrapV = d.addressV == ADDR_REPEAT;
+	const bool wrapU = FAST || d.addressU == ADDR_REPEAT, wrapV = FAST || d.addressV == ADDR_REPEAT;
 	const uint32_t u0 = offset_sample(uu, uHalf, wrapU, -1), u1 = offset_sample(uu, uHalf, wrapU, +1);
 	const uint32_t v0 = offset_sample(vv, vHalf, wrapV, -1), v1 = offset_sample(vv, vHalf, wrapV, +1);
 	const uint32_t x0 = mulhi16(u0, W), x1 = mulhi16(u1, W), y0 = mulhi16(v0, H), y1 = mulhi16(v1, H);
-	const uint32_t t00 = load_texel(m, x0, y0), t10 = load_texel(m, x1, y0), t01 = load_texel(m, x0, y1), t11 = load_texel(m, x1, y1);
+	const uint32_t *base = (const uint32_t *)m.buffer;
+	const uint32_t r0 = y0 * m.pitchP, r1 = y1 * m.pitchP;
+	const uint32_t t00 = __ldg(base + r0 + x0), t10 = __ldg(base + r0 + x1), t01 = __ldg(base + r1 + x0), t11 = __ldg(base + r1 + x1);
 	const uint32_t f0u = (u0 * W) & 0xFFFF, f0v = (v0 * H) & 0xFFFF;
 	const uint32_t f1u = ~f0u & 0xFFFF, f1v = ~f0v & 0xFFFF;
 	const uint32_t f0u0v = mulhi16(f0u, f0v), f1u0v = mulhi16(f1u, f0v), f0u1v = mulhi16(f0u, f1v), f1u1v = mulhi16(f1u, f1v);
 #pragma unroll
 	for(int c = 0; c < 4; c++)
 	{
-		const uint32_t c00 = mulhi16(((t00 >> (8 * c)) & 0xFF) << 8, f1u1v);
-		const uint32_t c10 = mulhi16(((t10 >> (8 * c)) & 0xFF) << 8, f0u1v);
-		const uint32_t c01 = mulhi16(((t01 >> (8 * c)) & 0xFF) << 8, f1u0v);
-		const uint32_t c11 = mulhi16(((t11 >> (8 * c)) & 0xFF) << 8, f0u0v);
+		// mulhi(b << 8, w) == (b * w) >> 8 for a byte b and a 16-bit weight w
+		const uint32_t c00 = (__byte_perm(t00, 0, 0x4440 + c) * f1u1v) >> 8;
+		const uint32_t c10 = (__byte_perm(t10, 0, 0x4440 + c) * f0u1v) >> 8;
+		const uint32_t c01 = (__byte_perm(t01, 0, 0x4440 + c) * f1u0v) >> 8;
+		const uint32_t c11 = (__byte_perm(t11, 0, 0x4440 + c) * f0u0v) >> 8;
 		out[c] = (((c00 + c10) & 0xFFFF) + ((c01 + c11) & 0xFFFF)) & 0xFFFF;
 	}
 }
@@ -713,11 +718,12 @@ struct LodState
 };
 
 // computeLod2D :1376-1422 + log2sqrt :1333-1341 + selectMipmap :2357-2379; u/v of quad lanes 0,1,2
+template<bool FAST>
 DEVI LodState compute_lod(const DrawConst &d, float u0, float u1, float u2, float v0, float v1, float v2)
 {
 	LodState s;
-	s.split = d.magFilter != d.minFilter;
-	bool filterLinear = s.split ? false : d.magFilter == FILTER_LINEAR;
+	s.split = FAST ? false : d.magFilter != d.minFilter;
+	bool filterLinear = FAST ? true : (s.split ? false : d.magFilter == FILTER_LINEAR);
 	float minLod = d.minLod, maxLod = d.maxLod;
 	if(d.texLevels == 1 && !s.split) { minLod = 0.0f; maxLod = 0.0f; }
 	float lod;
@@ -743,19 +749,20 @@ DEVI LodState compute_lod(const DrawConst &d, float u0, float u1, float u2, floa
 		s.linear = minLinear ? !(lod <= 0.0f) : (lod <= 0.0f);
 	}
 	s.lod = lod;
-	s.ilod = d.mipmapMode == MIPMAP_MODE_NEAREST ? round_int(lod) : trunc_int(lod);
+	s.ilod = (!FAST && d.mipmapMode == MIPMAP_MODE_NEAREST) ? round_int(lod) : trunc_int(lod);
 	return s;
 }
 
+template<bool FAST>
 DEVI void sample_texture(const DrawConst &d, const LodState &s, float u, float v, float out[4])
 {
 	uint32_t c[4];
-	if(s.split && !s.linear) sample_level_split_point(d, s.ilod, u, v, c);
-	else sample_level(d, s.ilod, u, v, s.linear, c);
-	if(d.mipmapMode == MIPMAP_MODE_LINEAR) // sampleFilter :324-373
+	if(!FAST && s.split && !s.linear) sample_level_split_point(d, s.ilod, u, v, c);
+	else sample_level<FAST>(d, s.ilod, u, v, s.linear, c);
+	if(FAST || d.mipmapMode == MIPMAP_MODE_LINEAR) // sampleFilter :324-373
 	{
 		uint32_t cc[4];
-		sample_level(d, s.ilod + 1, u, v, s.linear, cc);
+		sample_level<FAST>(d, s.ilod + 1, u, v, s.linear, cc);
 		const uint32_t utri = (uint32_t)trunc_int(fmul(s.lod, 65536.0f)) & 0xFFFF;
 		const uint32_t inv = ~utri & 0xFFFF;
 #pragma unroll
@@ -1130,6 +1137,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 			// ---- coverage (QuadRasterizer.cpp:181-206): one lane per (region row, sample) turns the span [left, right) into a
 			//      16-bit x-mask of the row; (candidate, row, sample) pairs with coverage are compacted in candidate order ----
 			int P = 0;
+			uint32_t accMask = 0, overlap = 0; // does any sample of the region receive two fragments in this batch?
 			constexpr int CPI = MS == 4 ? 1 : 4; // candidates per iteration
 			for(int s0 = 0; s0 < nb; s0 += CPI)
 			{
@@ -1141,10 +1149,24 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 					const int a = clampi((int)(sp & 0xFFFF) - rx, 0, 16), e = clampi((int)(sp >> 16) - rx, 0, 16);
 					if(e > a) mask = ((1u << e) - 1u) & ~((1u << a) - 1u);
 				}
+				overlap |= accMask & mask;
+				accMask |= mask;
 				const uint32_t nz = __ballot_sync(0xFFFFFFFFu, mask != 0);
 				if(mask) wPairs[P + __popc(nz & ((1u << lane) - 1))] = ((uint32_t)s << 21) | ((uint32_t)(MS == 4 ? lane : covRow) << 16) | mask;
 				P += __popc(nz);
 			}
+			if(MS == 1)
+			{
+				// four candidates per iteration share a row: fold the per-lane accumulators of the four sub-streams
+#pragma unroll
+				for(int o = 8; o < 32; o <<= 1)
+				{
+					const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, accMask, o);
+					overlap |= accMask & other;
+					accMask |= other;
+				}
+			}
+			const bool conflicts = __any_sync(0xFFFFFFFFu, overlap != 0);
 			__syncwarp();
 			// ---- items before each pair (exclusive prefix sum of the mask popcounts) ----
 			uint32_t total = 0;
@@ -1194,9 +1216,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 					// items of the same (quad, pixel, sample) in this round run in queue order
 					const uint32_t code = (e >> 16) & 31;
 					const uint32_t key = valid ? ((code << 4) | (uint32_t)bit) : (0x200u | lane); // one key per sample of the region
-					const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-					const int prank = __popc(peers & ((1u << lane) - 1));
-					const int maxRank = __reduce_max_sync(0xFFFFFFFFu, valid ? prank : 0);
+					int prank = 0, maxRank = 0;
+					if(conflicts) // overlapping triangles in this batch: same-sample items of a round run in list order
+					{
+						const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+						prank = __popc(peers & ((1u << lane) - 1));
+						maxRank = __reduce_max_sync(0xFFFFFFFFu, valid ? prank : 0);
+					}
 					for(int rr = 0; rr <= maxRank; rr++)
 					{
 						if(valid && prank == rr)
@@ -1233,10 +1259,10 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 									uu[t] = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], d.slotMode[UV], xk, yk, rk);
 									vv[t] = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], d.slotMode[UV + 1], xk, yk, rk);
 								}
-								const LodState lodState = compute_lod(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]);
 								const float u = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], d.slotMode[UV], xf, yf, rhw);
 								const float v = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], d.slotMode[UV + 1], xf, yf, rhw);
-								sample_texture(d, lodState, u, v, texel);
+								if(d.texFast) sample_texture<true>(d, compute_lod<true>(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]), u, v, texel);
+								else sample_texture<false>(d, compute_lod<false>(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]), u, v, texel);
 							}
 							float rgba[4];
 #pragma unroll

@@ -170,6 +170,7 @@ struct DrawConst
 	uint32_t texLevels;
 	uint32_t magFilter, minFilter, mipmapMode, addressU, addressV;
 	float mipLodBias, minLod, maxLod;
+	uint32_t texFast; // REPEAT/REPEAT, LINEAR/LINEAR, MIPMAP_LINEAR: the benchmark sampler, state tests folded away
 
 	// ---- work buffers ----
 	unsigned char *triRecords; // primCount records of triStride bytes
