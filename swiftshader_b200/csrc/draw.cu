@@ -54,6 +54,7 @@ struct swcu_ctx
 	std::vector<cudaEvent_t> eventPool;
 	size_t eventsUsed = 0;
 	int optTma = 1;
+	int optFastState = 1;
 	void *encodeTiled = nullptr; // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda link dependency)
 	std::map<std::vector<uint64_t>, CUtensorMap> mapCache;
 };
@@ -339,6 +340,7 @@ extern "C" int swcu_set_option(swcu_ctx *ctx, const char *name, int value)
 	else if(!strcmp(name, "direct_max")) ctx->optDirectMax = value;
 	else if(!strcmp(name, "pin_host")) ctx->optPinHost = value;
 	else if(!strcmp(name, "tma")) ctx->optTma = value;
+	else if(!strcmp(name, "fast_state")) ctx->optFastState = value;
 	else return fail(ctx, SWCU_E_INVALID, "unknown option '%s'", name);
 	return SWCU_OK;
 }
@@ -693,12 +695,45 @@ static bool get_tensor_map(swcu_ctx *ctx, CUtensorMap *out, unsigned char *base,
 	return true;
 }
 
-template<int MS, int SH, int BL>
-static void launch_tile3(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps, dim3 grid)
+template<int MS, int SH, int BL, bool FS>
+static void launch_tile4(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps, dim3 grid)
 {
 	LaunchScope ls(ctx, MS == 4 ? "k_tile<4>" : "k_tile<1>");
 	const int smem = TileLayout<MS, SH>::total(d.depthTestActive != 0, d.stencilActive != 0);
-	k_tile<MS, SH, BL><<<grid, TILE_THREADS, smem, ctx->stream>>>(d, maps, (const uint32_t *)ctx->tileBegin.p, (const uint32_t *)ctx->tileEnd.p, (const uint32_t *)ctx->vals.p);
+	if(MS == 4)
+	{
+		// 8 CTAs of 4x MSAA colour + depth tiles need ~224 KB of the SM's shared memory: ask for the largest carve-out
+		static bool once = false;
+		if(!once) { cudaFuncSetAttribute(k_tile<MS, SH, BL, FS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); once = true; }
+	}
+	k_tile<MS, SH, BL, FS><<<grid, TILE_THREADS, smem, ctx->stream>>>(d, maps, (const uint32_t *)ctx->tileBegin.p, (const uint32_t *)ctx->tileEnd.p, (const uint32_t *)ctx->vals.p);
+}
+
+// The common fixed-function state the FS instantiations of k_tile assume (see kernels.cuh); anything else runs the
+// instantiation that decodes the state at run time.
+static bool fast_state(const swcu_ctx *ctx, const DrawConst &d)
+{
+	if(!ctx->optFastState) return false;
+	if(d.stencilActive || d.stencilWrite || !d.colorBuf || d.colorWriteMask != 0xFu || d.bgr || d.depthBiasEnable) return false;
+	if(d.depthTestActive && d.depthCompareOp != CMP_LESS && d.depthCompareOp != CMP_LESS_OR_EQUAL) return false;
+	if(d.ms == 4 && (d.sampleMask & 0xFu) != 0xFu) return false;
+	if(d.blendClass == BL_GENERIC || d.shaderClass == SH_GENERIC) return false;
+	for(int ch = 0; ch < 4; ch++)
+	{
+		const uint32_t kind = d.chanKind[ch];
+		if(d.shaderClass == SH_CONST && kind != CK_CONST) return false;
+		if(d.shaderClass == SH_VARY && !(kind == CK_CONST || (kind == CK_SLOT && d.slotMode[ch] == IM_PERSP))) return false;
+		if(d.shaderClass == SH_TEX && !(kind == CK_TEXEL && d.chanValue[ch] == (uint32_t)ch)) return false;
+	}
+	if(d.shaderClass == SH_TEX && (d.slotMode[d.uvSlot] != IM_PERSP || d.slotMode[d.uvSlot + 1] != IM_PERSP)) return false;
+	return true;
+}
+
+template<int MS, int SH, int BL>
+static void launch_tile3(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps, dim3 grid)
+{
+	if(SH != SH_GENERIC && BL != BL_GENERIC && fast_state(ctx, d)) launch_tile4<MS, SH, BL, (SH != SH_GENERIC && BL != BL_GENERIC)>(ctx, d, maps, grid);
+	else launch_tile4<MS, SH, BL, false>(ctx, d, maps, grid);
 }
 template<int MS, int SH>
 static void launch_tile2(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps, dim3 grid)
@@ -771,7 +806,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		CU(cudaMemsetAsync(d.counters, 0, sizeof(DrawCounters), ctx->stream));
 		{
 			LaunchScope ls(ctx, "k_setup");
-			k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, 0, ctx->stream>>>(d);
+			k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4, ctx->stream>>>(d);
 		}
 		if(d.direct) break;
 

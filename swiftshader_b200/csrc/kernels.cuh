@@ -180,45 +180,57 @@ __device__ __noinline__ int clip_polygon(float4 *P, int n, int flagsOr)
 // ------------------------------------------------------------------------------------------------------------------
 // spans
 // ------------------------------------------------------------------------------------------------------------------
-// SetupRoutine::edge (SetupRoutine.cpp:550-621), row-stepping form for triangles of a few rows.  Writes the clamped x
-// of every row of the edge inside [rowMin, rowMin + SWCU_SMALL_ROWS) into the left or right half of the span entries;
-// `rows` is this thread's column of the shared scratch: entry e lives at rows[e * SETUP_THREADS].
+// SetupRoutine::edge (SetupRoutine.cpp:550-621), row-stepping form for triangles of a few rows.
+//
+// The reference runs the DDA once per (edge, sample) with two integer divisions each.  Here the per-edge step
+// (Q, R) = floor-divmod(DX, DY) is computed once for all samples (the sample offset moves both end points, so DX, DY do
+// not change), and the divisions are done as a float estimate fixed up with the exact integer remainder — the result is
+// the exact quotient for every int32 input (the fix-up loops run 0 or 1 times for screen-sized operands).
 #define SETUP_THREADS 128
-DEVI void edge_small(const DrawConst &d, uint32_t *rows, int rowMin, int stride, int q, int Xa, int Ya, int Xb, int Yb)
+DEVI int floor_div(int n, int d, int &rem) // d > 0; returns floor(n / d), rem = n - q*d in [0, d)
+{
+	int q = __float2int_rd(__fdividef((float)n, (float)d));
+	int r = n - q * d;
+	while(r < 0) { r += d; q--; }
+	while(r >= d) { r -= d; q++; }
+	rem = r;
+	return q;
+}
+
+// One edge a->b of a small triangle / clipped polygon, all samples.  Writes the clamped x of every row of the edge inside
+// [rowMin, rowMin + SWCU_SMALL_ROWS) into the left or right half of the span entries; `rows` is this thread's column of
+// the shared scratch: entry e lives at rows[e * SETUP_THREADS].
+template<int MS>
+DEVI void edge_small(const DrawConst &d, uint32_t *rows, int rowMin, int Xa, int Ya, int Xb, int Yb)
 {
 	if(Ya == Yb) return;
 	const bool swap = Yb < Ya;
 	const int X1 = swap ? Xb : Xa, X2 = swap ? Xa : Xb;
 	const int Y1 = swap ? Yb : Ya, Y2 = swap ? Ya : Yb;
-	const int y1 = (Y1 + 255) >> 8, y2 = (Y2 + 255) >> 8;
-	const int yMin = max(y1, d.scY0), yMax = min(y2, d.scY1);
-	if(!(yMin < yMax)) return;
-	const int DX12 = X2 - X1, DY12 = Y2 - Y1;
-	const int FDX12 = DX12 << 8, FDY12 = DY12 << 8;
-	int X = DX12 * ((y1 << 8) - Y1) + (X1 & 255) * DY12;
-	int x = (X1 >> 8) + X / FDY12;
-	int dd = X % FDY12;
-	int ceil = -dd >> 31;
-	x -= ceil;
-	dd -= ceil & FDY12;
-	int Q = FDX12 / FDY12;
-	int R = FDX12 % FDY12;
-	int floor = R >> 31;
-	Q += floor;
-	R += floor & FDY12;
-	for(int y = y1; y < yMax; y++)
+	const int DX = X2 - X1, DY = Y2 - Y1, FDY = DY << 8;
+	int R;
+	const int Q = floor_div(DX, DY, R); // == floor-divmod(DX << 8, DY << 8) with the remainder scaled by 256
+	R <<= 8;
+	unsigned short *half = (unsigned short *)rows + (swap ? 1 : 0);
+#pragma unroll
+	for(int q = 0; q < MS; q++)
 	{
-		if(y >= yMin)
+		const int X1q = X1 - (MS > 1 ? c_Xf[q] : 0), Y1q = Y1 - (MS > 1 ? c_Yf[q] : 0), Y2q = Y2 - (MS > 1 ? c_Yf[q] : 0);
+		const int y1 = (Y1q + 255) >> 8, y2 = (Y2q + 255) >> 8;
+		const int yMin = max(y1, d.scY0), yMax = min(y2, d.scY1);
+		if(!(yMin < yMax)) continue;
+		// x(y1) = (X1 >> 8) + ceil(N / FDY), dd = N - ceil * FDY in (-FDY, 0]
+		const int N = DX * ((y1 << 8) - Y1q) + (X1q & 255) * DY;
+		int dd;
+		int x = (X1q >> 8) + floor_div(N, FDY, dd);
+		if(dd > 0) { x++; dd -= FDY; }
+		for(int y = y1; y < yMax; y++)
 		{
-			uint32_t *e = rows + ((y - rowMin) * stride + q) * SETUP_THREADS;
-			const uint32_t c = (uint32_t)clampi(x, d.scX0, d.scX1);
-			*e = swap ? ((*e & 0x0000FFFFu) | (c << 16)) : ((*e & 0xFFFF0000u) | c);
+			if(y >= yMin) half[2 * (((y - rowMin) * MS + q) * SETUP_THREADS)] = (unsigned short)clampi(x, d.scX0, d.scX1);
+			x += Q;
+			dd += R;
+			if(dd > 0) { dd -= FDY; x++; }
 		}
-		x += Q;
-		dd += R;
-		int overflow = -dd >> 31;
-		dd -= FDY12 & overflow;
-		x -= overflow;
 	}
 }
 
@@ -266,19 +278,25 @@ DEVI unsigned long long warp_alloc(unsigned long long *cursor, uint32_t count)
 	return base + (incl - count);
 }
 
+DEVI int sel3(int i, int a0, int a1, int a2) { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
+DEVI float sel3(int i, float a0, float a1, float a2) { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
+
+// The unclipped triangle lives in registers only (three named vertices, selects instead of indexed arrays); the clipped
+// polygon — rare — goes through local-memory arrays.
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ DrawConst d)
 {
-	__shared__ uint32_t s_rows[SWCU_SMALL_ROWS * 4][SETUP_THREADS];
+	extern __shared__ uint32_t s_rows[]; // [SWCU_SMALL_ROWS * ms][SETUP_THREADS]: one scratch column of span rows per thread
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x; // grid is padded to whole warps; inactive lanes just allocate 0
 	const bool live = tri < d.primCount;
 	const bool msaa = d.ms > 1;
 	uint32_t nTiles = 0;
 	bool visible = false;
 	uint32_t idx[3] = { 0, 0, 0 };
-	VOut v[3];
+	VOut va, vb, vc;
 	float sv[3][SWCU_MAXSLOTS]; // slot sources at the three vertices
-	int PX[SWCU_POLY_MAX], PY[SWCU_POLY_MAX];
+	int PX[SWCU_POLY_MAX], PY[SWCU_POLY_MAX]; // clipped polygons only
 	int n = 3, dir = 1;
+	bool clipped = false;
 	bool frontFacing = false;
 	int yMin = 0, yMax = 0, pxMin = 0, pxMax = 0;
 	if(live)
@@ -296,22 +314,20 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 			for(int a = 0; a < 3; a++)
 #pragma unroll
 				for(int k = 0; k < SWCU_MAXSLOTS; k++) sv[a][k] = k < d.nslots ? vs_operand(d, d.slotSrc[k], idx[a]) : 0.0f;
-			process_vertex(d, pos[0][0], pos[0][1], pos[0][2], pos[0][3], v[0]);
-			process_vertex(d, pos[1][0], pos[1][1], pos[1][2], pos[1][3], v[1]);
-			process_vertex(d, pos[2][0], pos[2][1], pos[2][2], pos[2][3], v[2]);
+			process_vertex(d, pos[0][0], pos[0][1], pos[0][2], pos[0][3], va);
+			process_vertex(d, pos[1][0], pos[1][1], pos[1][2], pos[1][3], vb);
+			process_vertex(d, pos[2][0], pos[2][1], pos[2][2], pos[2][3], vc);
 
 			// setupSolidTriangles, Renderer.cpp:749-757
-			if((v[0].flags & v[1].flags & v[2].flags) != CLIP_FINITE) break;
-			const int flagsOr = v[0].flags | v[1].flags | v[2].flags;
-			PX[0] = v[0].X; PX[1] = v[1].X; PX[2] = v[2].X;
-			PY[0] = v[0].Y; PY[1] = v[1].Y; PY[2] = v[2].Y;
+			if((va.flags & vb.flags & vc.flags) != CLIP_FINITE) break;
+			const int flagsOr = va.flags | vb.flags | vc.flags;
 
 			// culling, SetupRoutine.cpp:73-115 (on the original three vertices)
 			{
-				const float x0 = (float)v[0].X, x1 = (float)v[1].X, x2 = (float)v[2].X;
-				const float y0 = (float)v[0].Y, y1 = (float)v[1].Y, y2 = (float)v[2].Y;
+				const float x0 = (float)va.X, x1 = (float)vb.X, x2 = (float)vc.X;
+				const float y0 = (float)va.Y, y1 = (float)vb.Y, y2 = (float)vc.Y;
 				float A = fadd(fadd(fmul(fsub(y0, y2), x1), fmul(fsub(y2, y1), x0)), fmul(fsub(y1, y0), x2));
-				const int s = (int)(__float_as_uint(v[0].pw) ^ __float_as_uint(v[1].pw) ^ __float_as_uint(v[2].pw));
+				const int s = (int)(__float_as_uint(va.pw) ^ __float_as_uint(vb.pw) ^ __float_as_uint(vc.pw));
 				if(s < 0) A = -A;
 				frontFacing = d.frontFace == FRONT_FACE_CCW ? (A >= 0.0f) : (A <= 0.0f);
 				if((d.cullMode & CULL_FRONT) && frontFacing) break;
@@ -319,27 +335,29 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 				if(!(A > 0.0f)) dir = 0;
 			}
 
+			int minY = min(min(va.Y, vb.Y), vc.Y), maxY = max(max(va.Y, vb.Y), vc.Y);
+			int minX = min(min(va.X, vb.X), vc.X), maxX = max(max(va.X, vb.X), vc.X);
 			if(flagsOr != CLIP_FINITE && (flagsOr & CLIP_FRUSTUM))
 			{
 				float4 P[16];
-				P[0] = make_float4(v[0].px, v[0].py, v[0].pz, v[0].pw);
-				P[1] = make_float4(v[1].px, v[1].py, v[1].pz, v[1].pw);
-				P[2] = make_float4(v[2].px, v[2].py, v[2].pz, v[2].pw);
+				P[0] = make_float4(va.px, va.py, va.pz, va.pw);
+				P[1] = make_float4(vb.px, vb.py, vb.pz, vb.pw);
+				P[2] = make_float4(vc.px, vc.py, vc.pz, vc.pw);
 				n = clip_polygon(P, 3, flagsOr);
 				if(n == 0) break;
+				clipped = true;
 				for(int i = 0; i < n; i++) // re-projection, SetupRoutine.cpp:125-145
 				{
 					const float rhw = P[i].w != 0.0f ? fdiv(1.0f, P[i].w) : 1.0f;
 					PX[i] = round_int(fadd(d.X0xF, fmul(fmul(P[i].x, rhw), d.WxF)));
 					PY[i] = round_int(fadd(d.Y0xF, fmul(fmul(P[i].y, rhw), d.HxF)));
 				}
-			}
-
-			int minY = PY[0], maxY = PY[0], minX = PX[0], maxX = PX[0];
-			for(int i = 1; i < n; i++)
-			{
-				minY = min(minY, PY[i]); maxY = max(maxY, PY[i]);
-				minX = min(minX, PX[i]); maxX = max(maxX, PX[i]);
+				minY = maxY = PY[0]; minX = maxX = PX[0];
+				for(int i = 1; i < n; i++)
+				{
+					minY = min(minY, PY[i]); maxY = max(maxY, PY[i]);
+					minX = min(minX, PX[i]); maxX = max(maxX, PX[i]);
+				}
 			}
 			yMin = msaa ? (minY + 159) >> 8 : (minY + 255) >> 8; // SetupRoutine.cpp:147-186
 			yMax = msaa ? (maxY + 351) >> 8 : (maxY + 255) >> 8;
@@ -391,49 +409,64 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 		BigTri &b = d.bigList[slot];
 		b.tri = tri; b.spanBase = (uint32_t)base; b.n = n; b.dir = dir;
 		b.yMin = yMin; b.yMax = yMax; b.pxMin = pxMin; b.pxMax = pxMax;
-		for(int i = 0; i < n; i++) { b.X[i] = PX[i]; b.Y[i] = PY[i]; }
+		if(clipped)
+			for(int i = 0; i < n; i++) { b.X[i] = PX[i]; b.Y[i] = PY[i]; }
+		else
+		{
+			b.X[0] = va.X; b.X[1] = vb.X; b.X[2] = vc.X;
+			b.Y[0] = va.Y; b.Y[1] = vb.Y; b.Y[2] = vc.Y;
+		}
 	}
 	else
 	{
 		// span rows of the small triangle, built in a shared scratch column and stored inline in its record
-		uint32_t *col = &s_rows[0][threadIdx.x];
-		const int ne = rows * d.ms;
-		for(int i = 0; i < ne; i++) col[i * SETUP_THREADS] = 0; // MSAA pre-fill: empty span (SetupRoutine.cpp:214-225)
-		PX[n] = PX[0]; PY[n] = PY[0];
-		for(int q = 0; q < d.ms; q++)
+		uint32_t *col = s_rows + threadIdx.x;
+		// every row of the record is written (rows outside the triangle as empty spans): whole 32-byte sectors reach L2, so
+		// evicting them needs no fill from DRAM.  Empty = {0, 0}, also the MSAA pre-fill (SetupRoutine.cpp:214-225)
+		for(int i = 0; i < SWCU_SMALL_ROWS * d.ms; i++) col[i * SETUP_THREADS] = 0;
+		if(clipped) { PX[n] = PX[0]; PY[n] = PY[0]; }
+		for(int i = 0; i < n; i++)
 		{
-			const int ox = msaa ? c_Xf[q] : 0, oy = msaa ? c_Yf[q] : 0;
-			for(int i = 0; i < n; i++)
-				edge_small(d, col, yMin, d.ms, q, PX[i + 1 - dir] - ox, PY[i + 1 - dir] - oy, PX[i + dir] - ox, PY[i + dir] - oy);
+			// edge i runs from vertex i to vertex i + 1 (reversed when the winding is reversed)
+			int Xs, Ys, Xe, Ye;
+			if(clipped) { Xs = PX[i]; Ys = PY[i]; Xe = PX[i + 1]; Ye = PY[i + 1]; }
+			else
+			{
+				Xs = sel3(i, va.X, vb.X, vc.X); Ys = sel3(i, va.Y, vb.Y, vc.Y);
+				Xe = sel3(i, vb.X, vc.X, va.X); Ye = sel3(i, vb.Y, vc.Y, va.Y);
+			}
+			const int Xa = dir ? Xs : Xe, Ya = dir ? Ys : Ye, Xb = dir ? Xe : Xs, Yb = dir ? Ye : Ys;
+			if(msaa) edge_small<4>(d, col, yMin, Xa, Ya, Xb, Yb);
+			else edge_small<1>(d, col, yMin, Xa, Ya, Xb, Yb);
 		}
 		uint32_t *out = (uint32_t *)(rec + d.triStride) - SWCU_SMALL_ROWS * d.ms;
-		if(d.ms == 4)
-			for(int r = 0; r < rows; r++)
+#pragma unroll
+		for(int r = 0; r < SWCU_SMALL_ROWS; r++)
+			if(r < 2 * d.ms)
 				((uint4 *)out)[r] = make_uint4(col[(4 * r) * SETUP_THREADS], col[(4 * r + 1) * SETUP_THREADS], col[(4 * r + 2) * SETUP_THREADS], col[(4 * r + 3) * SETUP_THREADS]);
-		else
-			for(int r = 0; r < rows; r++) out[r] = col[r * SETUP_THREADS];
 	}
 
 	// ---- vertex sort (SetupRoutine.cpp:271-294): only changes float rounding of the planes ----
 	int i0 = 0, i1 = 1, i2 = 2;
 	{
-		const float y0 = v[0].py, y1 = v[1].py, y2 = v[2].py;
+		const float y0 = va.py, y1 = vb.py, y2 = vc.py;
 		const float ym = sse_min(sse_min(y0, y1), y2);
 		rot1(ym == y1, i0, i1, i2);
 		rot2(ym == y2, i0, i1, i2);
 	}
 	{
-		const float w0 = v[i0].pw, w1 = v[i1].pw, w2 = v[i2].pw;
+		const float w0 = sel3(i0, va.pw, vb.pw, vc.pw), w1 = sel3(i1, va.pw, vb.pw, vc.pw), w2 = sel3(i2, va.pw, vb.pw, vc.pw);
 		const float wm = sse_max(sse_max(w0, w1), w2);
 		rot1(wm == w1, i0, i1, i2);
 		rot2(wm == w2, i0, i1, i2);
 	}
-	const VOut v0 = v[i0], v1 = v[i1], v2 = v[i2];
-	const float w0 = v0.pw, w1 = v1.pw, w2 = v2.pw;
-	const float rhw0 = v0.rhw;
+	const float w0 = sel3(i0, va.pw, vb.pw, vc.pw), w1 = sel3(i1, va.pw, vb.pw, vc.pw), w2 = sel3(i2, va.pw, vb.pw, vc.pw);
+	const int X0 = sel3(i0, va.X, vb.X, vc.X), X1 = sel3(i1, va.X, vb.X, vc.X), X2 = sel3(i2, va.X, vb.X, vc.X);
+	const int Y0 = sel3(i0, va.Y, vb.Y, vc.Y), Y1 = sel3(i1, va.Y, vb.Y, vc.Y), Y2 = sel3(i2, va.Y, vb.Y, vc.Y);
+	const float rhw0 = sel3(i0, va.rhw, vb.rhw, vc.rhw);
 	const float rsub = 1.0f / 256.0f;
-	const float x0 = fmul((float)v0.X, rsub), y0 = fmul((float)v0.Y, rsub);
-	const int dX1 = v1.X - v0.X, dY1 = v1.Y - v0.Y, dX2 = v2.X - v0.X, dY2 = v2.Y - v0.Y;
+	const float x0 = fmul((float)X0, rsub), y0 = fmul((float)Y0, rsub);
+	const int dX1 = X1 - X0, dY1 = Y1 - Y0, dX2 = X2 - X0, dY2 = Y2 - Y0;
 	const float x1 = fmul(fmul(w1, rsub), (float)dX1), y1 = fmul(fmul(w1, rsub), (float)dY1);
 	const float x2 = fmul(fmul(w2, rsub), (float)dX2), y2 = fmul(fmul(w2, rsub), (float)dY2);
 	const float a = fsub(fmul(x1, y2), fmul(x2, y1));
@@ -450,21 +483,37 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 		M21 = fmul(x1, A);
 	}
 	float *f = (float *)(rec + TRI_HEADER_BYTES);
-	f[0] = x0; f[1] = y0;
-	f[3] = fadd(fadd(M00, M10), M20);
-	f[4] = fadd(fadd(M01, M11), M21);
-	f[5] = fadd(fadd(M02, 0.0f), 0.0f);
+	float F[TRI_FLOATS_FIXED + 3 * SWCU_MAXSLOTS + 3]; // the plane block, stored with 128-bit writes below
+#pragma unroll
+	for(int i = 0; i < TRI_FLOATS_FIXED + 3 * SWCU_MAXSLOTS + 3; i++) F[i] = 0.0f;
+	F[0] = x0; F[1] = y0;
+	F[3] = fadd(fadd(M00, M10), M20);
+	F[4] = fadd(fadd(M01, M11), M21);
+	F[5] = fadd(fadd(M02, 0.0f), 0.0f);
+	// The last float of the block is spare for every slot count in use (9 + 3n = 9, 15, 21, 27).  It carries 1/w when the w
+	// plane is constant (wA == wB == 0: MulAdd(x, 0, wC + y * 0) == wC at every pixel, bit for bit), so the tile kernel can
+	// skip the per-fragment division (PixelRoutine.cpp:196-199); 0 = "not constant".
+	float rhwConst = 0.0f;
+	if(F[3] == 0.0f && F[4] == 0.0f && F[5] != 0.0f)
+	{
+		const float r = fdiv(1.0f, F[5]);
+		if(r != 0.0f && fabsf(r) <= 3.40282347e38f) rhwConst = r;
+	}
+	const int nf4 = (TRI_FLOATS_FIXED + 3 * d.nslots + 3) >> 2;
+	// 128-bit stores of the block, each issued as soon as its four floats are final (keeps the live range of F short)
+	auto put = [&](int j) { ((float4 *)f)[j] = make_float4(F[4 * j], F[4 * j + 1], F[4 * j + 2], j == nf4 - 1 ? rhwConst : F[4 * j + 3]); };
 	float zBias = 0.0f;
 	if(d.depthTestActive)
 	{
-		const float z0 = v0.zp;
-		const float z1 = fsub(v1.zp, z0), z2 = fsub(v2.zp, z0);
+		const float zp0 = sel3(i0, va.zp, vb.zp, vc.zp), zp1 = sel3(i1, va.zp, vb.zp, vc.zp), zp2 = sel3(i2, va.zp, vb.zp, vc.zp);
+		const float z0 = zp0;
+		const float z1 = fsub(zp1, z0), z2 = fsub(zp2, z0);
 		const float px1 = fmul((float)dX1, rsub), py1 = fmul((float)dY1, rsub), px2 = fmul((float)dX2, rsub), py2 = fmul((float)dY2, rsub);
 		const float D = fdiv(d.depthRange, fsub(fmul(px1, py2), fmul(px2, py1)));
 		const float A = fmul(fsub(fmul(py2, z1), fmul(py1, z2)), D);
 		const float B = fmul(fsub(fmul(px1, z2), fmul(px2, z1)), D);
 		const float C = fadd(fmul(z0, d.depthRange), d.depthNear);
-		f[6] = A; f[7] = B; f[8] = C;
+		F[6] = A; F[7] = B; F[8] = C;
 		const bool applyConst = d.depthBiasConstant != 0.0f, applySlope = d.depthBiasSlope != 0.0f;
 		float bias = 0.0f; // SetupRoutine.cpp:417-475, floating-point depth buffer branch
 		if(applyConst)
@@ -487,28 +536,39 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 			zBias = bias;
 		}
 	}
-	else { f[6] = 0; f[7] = 0; f[8] = 0; }
-	f[2] = zBias;
+	F[2] = zBias;
+	put(0);
+	put(1);
 	// setupGradient, SetupRoutine.cpp:514-548
 #pragma unroll
 	for(int k = 0; k < SWCU_MAXSLOTS; k++)
 	{
 		if(k >= d.nslots) break;
-		float *P = f + TRI_FLOATS_FIXED + 3 * k;
+		float *P = F + TRI_FLOATS_FIXED + 3 * k;
 		const uint32_t mode = d.slotMode[k];
 		if(mode == IM_FLAT)
 		{
 			P[0] = 0; P[1] = 0; P[2] = sv[0][k]; // provoking vertex = Triangle.v0 (or a constant)
-			continue;
 		}
-		float a0 = i0 == 0 ? sv[0][k] : (i0 == 1 ? sv[1][k] : sv[2][k]);
-		float a1 = i1 == 0 ? sv[0][k] : (i1 == 1 ? sv[1][k] : sv[2][k]);
-		float a2 = i2 == 0 ? sv[0][k] : (i2 == 1 ? sv[1][k] : sv[2][k]);
-		if(mode == IM_NOPERSP) { a0 = fmul(a0, w0); a1 = fmul(a1, w1); a2 = fmul(a2, w2); }
-		P[0] = fadd(fadd(fmul(a0, M00), fmul(a1, M10)), fmul(a2, M20));
-		P[1] = fadd(fadd(fmul(a0, M01), fmul(a1, M11)), fmul(a2, M21));
-		P[2] = fadd(fadd(fmul(a0, M02), fmul(a1, 0.0f)), fmul(a2, 0.0f));
+		else
+		{
+			float a0 = sel3(i0, sv[0][k], sv[1][k], sv[2][k]);
+			float a1 = sel3(i1, sv[0][k], sv[1][k], sv[2][k]);
+			float a2 = sel3(i2, sv[0][k], sv[1][k], sv[2][k]);
+			if(mode == IM_NOPERSP) { a0 = fmul(a0, w0); a1 = fmul(a1, w1); a2 = fmul(a2, w2); }
+			P[0] = fadd(fadd(fmul(a0, M00), fmul(a1, M10)), fmul(a2, M20));
+			P[1] = fadd(fadd(fmul(a0, M01), fmul(a1, M11)), fmul(a2, M21));
+			P[2] = fadd(fadd(fmul(a0, M02), fmul(a1, 0.0f)), fmul(a2, 0.0f));
+		}
+		// floats up to index 11 + 3k are final: store the float4s this slot completed
+#pragma unroll
+		for(int j = 2; j < (TRI_FLOATS_FIXED + 3 * SWCU_MAXSLOTS + 3) / 4; j++)
+			if(4 * j + 3 <= 11 + 3 * k && 4 * j + 3 > 8 + 3 * k) put(j);
 	}
+	// the float4 that holds the padding (and rhwConst) is still open
+#pragma unroll
+	for(int j = 2; j < (TRI_FLOATS_FIXED + 3 * SWCU_MAXSLOTS + 3) / 4; j++)
+		if(j < nf4 && 4 * j + 3 > 8 + 3 * d.nslots) put(j);
 	uint4 hdr;
 	hdr.x = (uint32_t)pxMin | ((uint32_t)pxMax << 16);
 	hdr.y = (uint32_t)yMin | ((uint32_t)yMax << 16);
@@ -892,7 +952,6 @@ DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1
 //   * specialised on <samples, fragment shader class, blend class>; depth / stencil state is warp-uniform at run time.
 // ------------------------------------------------------------------------------------------------------------------
 #define TILE_THREADS (SWCU_TILE_WARPS * 32)
-#define TILE_QCAP 256 // item queue entries per warp
 
 template<int SH> struct ShaderSlots { static constexpr int N = SH == SH_CONST ? 0 : SH == SH_VARY ? 4 : SH == SH_TEX ? 2 : 6; };
 
@@ -927,21 +986,40 @@ struct TileLayout
 	static constexpr int NF4 = (TRI_FLOATS_FIXED + 3 * ShaderSlots<SH>::N + 3) / 4; // float4s of plane data per record
 	static constexpr int PLANE_B = SWCU_TILE_W * SWCU_TILE_H * 4 * MS;              // colour or depth tile
 	static constexpr int STENCIL_B = SWCU_TILE_W * SWCU_TILE_H * MS;
+	// A batch is bounded three ways when it is formed: NB candidates, PCAP (candidate, region row, sample) pairs and ICAP
+	// covered samples (both from the bounding boxes, before any span is read), so the per-warp area stays small enough for
+	// 8 CTAs per SM with the 4x MSAA colour + depth tile.
+	static constexpr int PCAP = MS == 4 ? 224 : 256;
+	static constexpr int ICAP = MS == 4 ? 1536 : 2048;
 	// per-warp area
-	static constexpr int W_HDR = 0;                                  // uint4 hdr[NB]
+	static constexpr int W_HDR = 0;                                  // uint4 hdr[NB]: {span rows pointer (lo, hi), yMin | rows << 14 | flags << 28, triangle}
 	static constexpr int W_PLANES = W_HDR + 16 * NB;                 // float4 planes[NB][NF4]
-	static constexpr int W_ROWS = W_PLANES + 16 * NB * NF4;          // uint32 rows[NB][REGION_H][MS]
-	static constexpr int MAXPAIRS = NB * (MS == 4 ? 32 : SWCU_REGION_H);     // (candidate, region row, sample) pairs with coverage
-	static constexpr int W_PAIRS = W_ROWS + 4 * NB * SWCU_REGION_H * MS;     // uint32 pairs[MAXPAIRS]: cand << 21 | code << 16 | x-mask
-	static constexpr int W_PSUM = W_PAIRS + 4 * MAXPAIRS;                    // uint16 psum[MAXPAIRS + 1]: items before pair p
-	static constexpr int W_TRI = (W_PSUM + 2 * (MAXPAIRS + 1) + 3) & ~3;     // uint32 tri[NB]
-	static constexpr int W_BYTES = (W_TRI + 4 * NB + 127) & ~127;
+	static constexpr int W_PAIRS = W_PLANES + 16 * NB * NF4;         // uint32 pairs[PCAP]: start << 18 | cand << 13 | code << 8 | x0 << 4 | (n - 1)
+	static constexpr int W_BITS = W_PAIRS + 4 * PCAP;                // uint32 bits[ICAP / 32]: bit i set <=> a pair starts at item i
+	static constexpr int W_BYTES = (W_BITS + ICAP / 8 + 15) & ~15;
 	static constexpr int HEAD_B = 128;                               // mbarrier + dirty flag
 	__host__ __device__ static int total(bool depth, bool stencil)
 	{
 		return HEAD_B + PLANE_B + (depth ? PLANE_B : 0) + (stencil ? ((STENCIL_B + 127) & ~127) : 0) + SWCU_TILE_WARPS * W_BYTES;
 	}
 };
+
+DEVI void cp_async16(void *dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory"); }
+DEVI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DEVI void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// writeColor for the RGBA8 family (PixelRoutine.cpp:1981-1992, :2603-2655): RoundInt(clamp(c, 0, 1) * 255) per channel,
+// packed with saturation.  The float clamp is folded into the integer saturation: values above 1 round to >= 255, negative
+// ones to <= 0 and NaN converts to 0, exactly what min(max(c, 0), 1) gives before the conversion.
+DEVI uint32_t pack_unorm8(float b0, float b1, float b2, float b3)
+{
+	const int i0 = __float2int_rn(fmul(b0, 255.0f)), i1 = __float2int_rn(fmul(b1, 255.0f));
+	const int i2 = __float2int_rn(fmul(b2, 255.0f)), i3 = __float2int_rn(fmul(b3, 255.0f));
+	uint32_t hi, pk;
+	asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(i3), "r"(i2), "r"(0));
+	asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(pk) : "r"(i1), "r"(i0), "r"(hi));
+	return pk;
+}
 
 // cooperative tile <-> framebuffer copy with 128-bit accesses where the layout allows it (TMA-ineligible attachments)
 template<int MS, typename T, bool STORE>
@@ -993,12 +1071,17 @@ struct TileMaps
 	CUtensorMap color, depth, stencil;
 };
 
-template<int MS, int SH, int BL>
-__global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ DrawConst d, const __grid_constant__ TileMaps maps,
-                                                        const uint32_t *tileBegin, const uint32_t *tileEnd, const uint32_t *triList)
+// FS ("fast state"): the host has checked the common fixed-function state — no stencil, full colour write mask, RGBA byte
+// order, no depth bias, full sample mask, depth test off or LESS / LESS_OR_EQUAL, perspective slots routed one to one —
+// so none of it is decoded per fragment.  FS == false is the same code with every state read at run time.
+template<int MS, int SH, int BL, bool FS>
+__global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __grid_constant__ DrawConst d, const __grid_constant__ TileMaps maps,
+                                                                         const uint32_t *tileBegin, const uint32_t *tileEnd, const uint32_t *triList)
 {
 	using L = TileLayout<MS, SH>;
-	constexpr int NB = L::NB, NF4 = L::NF4;
+	constexpr int NB = L::NB, NF4 = L::NF4, PCAP = L::PCAP, ICAP = L::ICAP;
+	constexpr int CPI = MS == 4 ? 1 : 4;  // candidates per coverage iteration
+	constexpr int NITER = NB / CPI;
 	constexpr bool TEX = SH == SH_TEX || SH == SH_GENERIC;
 	constexpr int UV = SH == SH_TEX ? 0 : 4;
 	constexpr int TP = SWCU_TILE_W * SWCU_TILE_H; // pixels per sample plane of the tile
@@ -1011,7 +1094,7 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 	else { begin = tileBegin[tileId]; end = tileEnd[tileId]; }
 	if(begin >= end) return;
 
-	const bool colorOn = d.colorWriteMask != 0 && d.colorBuf != nullptr;
+	const bool colorOn = FS ? true : (d.colorWriteMask != 0 && d.colorBuf != nullptr);
 	uint64_t *bar = (uint64_t *)smem;
 	int *dirtyFlag = (int *)(smem + 8);
 	uint32_t *smColor = (uint32_t *)(smem + L::HEAD_B);
@@ -1020,21 +1103,23 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 	unsigned char *warpBase = smStencil + (d.stencilActive ? ((L::STENCIL_B + 127) & ~127) : 0);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t laneLt = (1u << lane) - 1u, laneLe = (2u << lane) - 1u;
 	const int tileX = tx * SWCU_TILE_W, tileY = ty * SWCU_TILE_H;
 	const int rx = tileX + (warp % (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_W; // this warp's region
 	const int ry = tileY + (warp / (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_H;
+	const int regionPi = (ry - tileY) * SWCU_TILE_W + (rx - tileX); // index of the region's first pixel inside a staged plane
 	// coverage is computed per (region row, sample): MS == 4: lane = row * 4 + sample; MS == 1: lane = sub * 8 + row, four candidates at a time
 	const int covRow = MS == 4 ? lane >> 2 : lane & 7;
 	const int covQ = MS == 4 ? lane & 3 : 0;
-	const bool covOn = MS == 4 ? ((d.sampleMask >> covQ) & 1) != 0 : true;
+	const bool covOn = (MS == 4 && !FS) ? ((d.sampleMask >> covQ) & 1) != 0 : true;
+	const int covOff = (ry + covRow) * MS + covQ; // my entry in a span table that starts at row 0
+	const uint32_t covCode = MS == 4 ? (uint32_t)lane : (uint32_t)covRow;
 
 	unsigned char *wa = warpBase + warp * L::W_BYTES;
 	uint4 *wHdr = (uint4 *)(wa + L::W_HDR);
 	float4 *wPlanes = (float4 *)(wa + L::W_PLANES);
-	uint32_t *wRows = (uint32_t *)(wa + L::W_ROWS);
 	uint32_t *wPairs = (uint32_t *)(wa + L::W_PAIRS);
-	unsigned short *wPsum = (unsigned short *)(wa + L::W_PSUM);
-	uint32_t *wTri = (uint32_t *)(wa + L::W_TRI);
+	uint32_t *wBits = (uint32_t *)(wa + L::W_BITS);
 
 	// ---- stage the tile: TMA when the attachments allow it ----
 	if(threadIdx.x == 0)
@@ -1068,92 +1153,149 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 	bool tileReady = !d.useTma;
 
 	bool dirty = false;
-	const bool biasOn = d.depthBiasEnable != 0;
-	uint32_t wmask32 = 0; // byte lanes of the packed pixel the draw may write
+	const bool biasOn = FS ? false : d.depthBiasEnable != 0;
+	const bool bgr = FS ? false : d.bgr != 0;
+	uint32_t wmask32 = FS ? 0xFFFFFFFFu : 0u; // byte lanes of the packed pixel the draw may write
+	if(!FS)
+	{
 #pragma unroll
-	for(int ch = 0; ch < 4; ch++)
-		if((d.colorWriteMask >> ch) & 1) wmask32 |= 0xFFu << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
+		for(int ch = 0; ch < 4; ch++)
+			if((d.colorWriteMask >> ch) & 1) wmask32 |= 0xFFu << (8 * ((bgr && ch < 3) ? 2 - ch : ch));
+	}
 
-	int ns = 0;        // candidates staged so far for the next batch
-	uint32_t pend = 0; // lanes whose scanned hit is not staged yet
-	uint32_t tri = 0;
-	uint4 h = make_uint4(0, 0, 0, 0);
+	// ---- list scan with one block of look-ahead: the headers of the next 32 entries are in flight while this block is used ----
+	uint32_t triN = 0;
+	uint4 hN = make_uint4(0, 0, 0, 0);
+	{
+		const uint32_t li = begin + lane;
+		if(li < end)
+		{
+			triN = d.direct ? li : __ldg(triList + li);
+			hN = __ldg((const uint4 *)(d.triRecords + (size_t)triN * d.triStride));
+		}
+	}
+	int ns = 0;             // candidates staged so far for the next batch
+	uint32_t accU = 0;      // their pair bound << 16 | item bound
+	uint32_t pend = 0;      // lanes whose scanned hit is not staged yet
+	uint32_t tri = 0, hy = 0, myU = 0;
+	const unsigned char *hrows = nullptr;
 	for(uint32_t pos = begin;;)
 	{
 		if(!pend && pos < end)
 		{
-			// ---- scan 32 list entries: which of them touch my region? ----
-			const uint32_t li = pos + lane;
+			// ---- which of these 32 list entries touch my region? ----
 			bool hit = false;
-			if(li < end)
+			if(pos + lane < end)
 			{
-				tri = d.direct ? li : __ldg(triList + li);
-				h = __ldg((const uint4 *)(d.triRecords + (size_t)tri * d.triStride));
-				const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.y & 0xFFFF, yMax = h.y >> 16;
+				const int pxMin = hN.x & 0xFFFF, pxMax = hN.x >> 16, yMin = hN.y & 0xFFFF, yMax = hN.y >> 16;
 				hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
+				if(hit)
+				{
+					tri = triN;
+					hy = (uint32_t)yMin | ((uint32_t)(yMax - yMin) << 14) | ((hN.w & 3u) << 28);
+					// span rows of the triangle, rebased so that entry (y * MS + q) is row y: the span table for big triangles,
+					// the rows inlined in the record otherwise
+					hrows = (hN.w & 2u) ? (const unsigned char *)(d.spans + hN.z) : d.triRecords + (size_t)triN * d.triStride + TRI_HEADER_BYTES + 16 * NF4;
+					hrows -= (size_t)yMin * (MS * 4);
+					// bounds of what the candidate can add to a batch: one pair per (row, sample) of its rows inside the region, and
+					// at most its column range inside the region per pair (the pixel bounds cover every span, see k_setup)
+					const int rowsIn = min(yMax, ry + SWCU_REGION_H) - max(yMin, ry);
+					const int colsIn = min(pxMax, rx + SWCU_REGION_W) - max(pxMin, rx);
+					myU = ((uint32_t)(rowsIn * MS) << 16) | (uint32_t)(rowsIn * MS * colsIn);
+				}
 			}
 			pend = __ballot_sync(0xFFFFFFFFu, hit);
 			pos += 32;
+			const uint32_t li = pos + lane;
+			if(li < end)
+			{
+				triN = d.direct ? li : __ldg(triList + li);
+				hN = __ldg((const uint4 *)(d.triRecords + (size_t)triN * d.triStride));
+			}
 		}
+		bool full = false;
 		if(pend)
 		{
-			// ---- hits go to the free slots of the batch, in list order; the rest wait for the next batch ----
-			const int rank = __popc(pend & ((1u << lane) - 1));
-			const int take = min(__popc(pend), NB - ns);
-			const bool mine = ((pend >> lane) & 1) && rank < take;
-			if(mine) { wHdr[ns + rank] = h; wTri[ns + rank] = tri; }
-			pend &= ~__ballot_sync(0xFFFFFFFFu, mine);
-			ns += take;
+			// ---- hits join the batch in list order while it has room (slots, pairs, items); the rest wait for the next batch ----
+			const bool mineP = (pend >> lane) & 1;
+			uint32_t incl = mineP ? myU : 0u;
+#pragma unroll
+			for(int o = 1; o < 32; o <<= 1)
+			{
+				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+				if(lane >= o) incl += t;
+			}
+			const int rank = __popc(pend & laneLt);
+			const uint32_t sum = accU + incl;
+			const bool admit = mineP && ns + rank < NB && (sum >> 16) <= (uint32_t)PCAP && (sum & 0xFFFFu) <= (uint32_t)ICAP;
+			const uint32_t adm = __ballot_sync(0xFFFFFFFFu, admit);
+			if(admit) wHdr[ns + rank] = make_uint4((uint32_t)(uintptr_t)hrows, (uint32_t)((uintptr_t)hrows >> 32), hy, tri);
+			if(adm)
+			{
+				accU += __shfl_sync(0xFFFFFFFFu, incl, 31 - __clz(adm)); // admitted lanes are a prefix of the pending ones
+				ns += __popc(adm);
+				pend &= ~adm;
+			}
+			full = pend != 0;
 		}
 		const bool listDone = pend == 0 && pos >= end;
-		if(ns < NB && !listDone) continue;
+		if(!full && ns < NB && !listDone) continue;
 		if(ns == 0) break;
 		{
-			// ---- stage the batch: plane equations + the span rows that cross my region ----
 			const int nb = ns;
 			ns = 0;
+			accU = 0;
 			__syncwarp();
+			// ---- plane equations of the batch -> shared memory, asynchronously (needed only when the items are consumed) ----
 			for(int i = lane; i < nb * NF4; i += 32)
 			{
-				const int s = i / NF4, j = i % NF4;
-				wPlanes[i] = __ldg((const float4 *)(d.triRecords + (size_t)wTri[s] * d.triStride + TRI_HEADER_BYTES) + j);
+				const int s = i / NF4, j = i - s * NF4;
+				cp_async16(wPlanes + i, d.triRecords + (size_t)wHdr[s].w * d.triStride + TRI_HEADER_BYTES + 16 * j);
 			}
-			for(int i = lane; i < nb * SWCU_REGION_H; i += 32)
+			cp_async_commit();
+			// ---- the span of my (region row, sample) in every candidate, all loads in flight together ----
+			uint32_t sp[NITER];
+#pragma unroll
+			for(int it = 0; it < NITER; it++)
 			{
-				const int s = i / SWCU_REGION_H, r = i % SWCU_REGION_H;
-				const uint4 hh = wHdr[s];
-				const int y = ry + r, yMin = hh.y & 0xFFFF, yMax = hh.y >> 16;
-				uint4 v = make_uint4(0, 0, 0, 0); // empty span outside the triangle's rows
-				if(y >= yMin && y < yMax)
+				sp[it] = 0; // empty span outside the triangle's rows
+				if(it * CPI < nb)
 				{
-					const uint32_t *src = (hh.w & 2u) ? d.spans + hh.z + (uint32_t)(y - yMin) * MS // big: span table
-					                                  : (const uint32_t *)(d.triRecords + (size_t)wTri[s] * d.triStride + TRI_HEADER_BYTES + 16 * NF4) + (y - yMin) * MS;
-					if(MS == 4) v = __ldg((const uint4 *)src); else v.x = __ldg(src);
+					const int s = MS == 4 ? it : it * CPI + (lane >> 3);
+					if(s < nb && covOn)
+					{
+						const uint4 hh = wHdr[s];
+						const uint32_t rel = (uint32_t)(ry + covRow) - (hh.z & 0x3FFFu);
+						if(rel < ((hh.z >> 14) & 0x3FFFu))
+							sp[it] = __ldg((const uint32_t *)(((uintptr_t)hh.y << 32) | hh.x) + covOff);
+					}
 				}
-				if(MS == 4) *(uint4 *)(wRows + i * 4) = v; else wRows[i] = v.x;
 			}
-			__syncwarp();
+			// zero the start marks while the loads fly (the previous batch's rounds ended with a __syncwarp)
+#pragma unroll
+			for(int i = 0; i < (ICAP / 32 + 31) / 32; i++)
+				if(lane + 32 * i < ICAP / 32) wBits[lane + 32 * i] = 0;
 
-			// ---- coverage (QuadRasterizer.cpp:181-206): one lane per (region row, sample) turns the span [left, right) into a
-			//      16-bit x-mask of the row; (candidate, row, sample) pairs with coverage are compacted in candidate order ----
+			// ---- coverage (QuadRasterizer.cpp:181-206): the span [left, right) clipped to the region's 16 columns is a run of
+			//      n pixels from x0; (candidate, row, sample) pairs with coverage are compacted in candidate order ----
 			int P = 0;
 			uint32_t accMask = 0, overlap = 0; // does any sample of the region receive two fragments in this batch?
-			constexpr int CPI = MS == 4 ? 1 : 4; // candidates per iteration
-			for(int s0 = 0; s0 < nb; s0 += CPI)
+#pragma unroll
+			for(int it = 0; it < NITER; it++)
 			{
-				const int s = MS == 4 ? s0 : s0 + (lane >> 3);
-				uint32_t mask = 0;
-				if(s < nb && covOn)
+				if(it * CPI < nb)
 				{
-					const uint32_t sp = wRows[(s * SWCU_REGION_H + covRow) * MS + covQ];
-					const int a = clampi((int)(sp & 0xFFFF) - rx, 0, 16), e = clampi((int)(sp >> 16) - rx, 0, 16);
-					if(e > a) mask = ((1u << e) - 1u) & ~((1u << a) - 1u);
+					const int s = MS == 4 ? it : it * CPI + (lane >> 3);
+					const int a = clampi((int)(sp[it] & 0xFFFF) - rx, 0, 16), e = clampi((int)(sp[it] >> 16) - rx, 0, 16);
+					const int n = e - a;
+					const bool has = n > 0;
+					const uint32_t mask = has ? (((1u << n) - 1u) << a) : 0u;
+					overlap |= accMask & mask;
+					accMask |= mask;
+					const uint32_t nz = __ballot_sync(0xFFFFFFFFu, has);
+					if(has) wPairs[P + __popc(nz & laneLt)] = ((uint32_t)s << 13) | (covCode << 8) | ((uint32_t)a << 4) | (uint32_t)(n - 1);
+					P += __popc(nz);
 				}
-				overlap |= accMask & mask;
-				accMask |= mask;
-				const uint32_t nz = __ballot_sync(0xFFFFFFFFu, mask != 0);
-				if(mask) wPairs[P + __popc(nz & ((1u << lane) - 1))] = ((uint32_t)s << 21) | ((uint32_t)(MS == 4 ? lane : covRow) << 16) | mask;
-				P += __popc(nz);
 			}
 			if(MS == 1)
 			{
@@ -1168,12 +1310,13 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 			}
 			const bool conflicts = __any_sync(0xFFFFFFFFu, overlap != 0);
 			__syncwarp();
-			// ---- items before each pair (exclusive prefix sum of the mask popcounts) ----
+			// ---- first item of each pair (exclusive prefix sum of the run lengths), stored in the pair word and as a mark bit ----
 			uint32_t total = 0;
 			for(int p0 = 0; p0 < P; p0 += 32)
 			{
 				const int p = p0 + lane;
-				const uint32_t c = p < P ? __popc(wPairs[p] & 0xFFFFu) : 0u;
+				const uint32_t w = p < P ? wPairs[p] : 0u;
+				const uint32_t c = p < P ? (w & 15u) + 1u : 0u;
 				uint32_t incl = c;
 #pragma unroll
 				for(int o = 1; o < 32; o <<= 1)
@@ -1181,10 +1324,16 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
 					if(lane >= o) incl += t;
 				}
-				if(p < P) wPsum[p] = (unsigned short)(total + incl - c);
+				if(p < P)
+				{
+					const uint32_t start = total + incl - c;
+					wPairs[p] = w | (start << 18);
+					if(start < (uint32_t)ICAP) atomicOr(wBits + (start >> 5), 1u << (start & 31));
+				}
 				total += __shfl_sync(0xFFFFFFFFu, incl, 31);
 			}
-			if(lane == 0) wPsum[P] = (unsigned short)total;
+			if(total > (uint32_t)ICAP) __trap(); // the pixel bounds of a record did not cover its spans
+			cp_async_wait_all();
 			__syncwarp();
 			if(total && !tileReady)
 			{
@@ -1193,45 +1342,36 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 			}
 			// ---- consume the items 32 at a time, one per lane ----
 			{
-				int cursor = 0; // pair that holds item `base`
+				int cursor = 0; // pairs that start before this round
 				for(uint32_t base = 0; base < total; base += 32)
 				{
 					const uint32_t g = base + lane;
 					const bool valid = g < total;
-					// a round of 32 consecutive items spans at most 32 pairs (every pair has >= 1 item): lane j looks at the end
-					// of pair cursor + j; the ends that fall inside the round mark where the next pairs start
-					const int pj = cursor + lane;
-					const uint32_t endj = pj < P ? wPsum[pj + 1] : 0xFFFFFFFFu;
-					const uint32_t rel = endj - base;
-					const uint32_t starts = __reduce_or_sync(0xFFFFFFFFu, (pj < P && rel < 32u) ? (1u << rel) : 0u);
-					const int myPair = cursor + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
-					cursor += __popc(__ballot_sync(0xFFFFFFFFu, pj < P && rel <= 32u));
-					uint32_t e = 0;
-					int bit = 0;
-					if(valid)
-					{
-						e = wPairs[myPair];
-						bit = (__ffs(e & 0xFFFFu) - 1) + (int)(g - wPsum[myPair]); // the x-mask is one run of ones
-					}
-					// items of the same (quad, pixel, sample) in this round run in queue order
-					const uint32_t code = (e >> 16) & 31;
+					const uint32_t starts = wBits[base >> 5];
+					const int myPair = cursor + __popc(starts & laneLe) - 1; // the last pair that starts at or before my item
+					cursor += __popc(starts);
+					const uint32_t e = wPairs[myPair];
+					const int bit = (int)((e >> 4) & 15u) + (int)(g - (e >> 18));
+					const uint32_t code = (e >> 8) & 31u;
+					// items of the same (pixel, sample) in this round run in queue order
 					const uint32_t key = valid ? ((code << 4) | (uint32_t)bit) : (0x200u | lane); // one key per sample of the region
 					int prank = 0, maxRank = 0;
 					if(conflicts) // overlapping triangles in this batch: same-sample items of a round run in list order
 					{
 						const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-						prank = __popc(peers & ((1u << lane) - 1));
+						prank = __popc(peers & laneLt);
 						maxRank = __reduce_max_sync(0xFFFFFFFFu, valid ? prank : 0);
 					}
 					for(int rr = 0; rr <= maxRank; rr++)
 					{
 						if(valid && prank == rr)
 						{
-							const int k = e >> 21;
+							const int k = (e >> 13) & 31;
 							const int q = MS == 4 ? (int)(code & 3) : 0;
-							const int x = rx + bit, y = ry + (MS == 4 ? (int)(code >> 2) : (int)code);
+							const int row = MS == 4 ? (int)(code >> 2) : (int)code;
+							const int x = rx + bit, y = ry + row;
 							const int ix = x & 1, iy = y & 1;
-							const int pi = q * TP + (y - tileY) * SWCU_TILE_W + (x - tileX); // index inside the staged planes
+							const int pi = q * TP + regionPi + row * SWCU_TILE_W + bit; // index inside the staged planes
 							// ---- plane equations of the triangle ----
 							float pf[NF4 * 4];
 #pragma unroll
@@ -1244,23 +1384,25 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 							const float *S = pf + TRI_FLOATS_FIXED; // slot s: S[3s], S[3s+1], S[3s+2]
 							// ---- interpolate + routed fragment shader (PixelRoutine.cpp:196-261, PixelProgram.cpp:138-241) ----
 							const float xf = fsub((float)x, x0), yf = fsub((float)y, y0);
+							const float rhwConst = pf[NF4 * 4 - 1]; // 1/w of a constant w plane (k_setup), 0 otherwise
 							float rhw = 1.0f;
-							if(SH != SH_CONST) rhw = fdiv(1.0f, __fmaf_rn(xf, wA, fadd(wC, fmul(yf, wB))));
+							if(SH != SH_CONST) rhw = rhwConst != 0.0f ? rhwConst : fdiv(1.0f, __fmaf_rn(xf, wA, fadd(wC, fmul(yf, wB))));
 							float texel[4] = { 0, 0, 0, 0 };
 							if(TEX)
 							{
 								// implicit LOD from lanes 0,1,2 of the pixel's quad (helper pixels included), SamplerCore.cpp:1376-1422
+								const uint32_t modeU = FS ? (uint32_t)IM_PERSP : d.slotMode[UV], modeV = FS ? (uint32_t)IM_PERSP : d.slotMode[UV + 1];
 								float uu[3], vv[3];
 #pragma unroll
 								for(int t = 0; t < 3; t++)
 								{
 									const float xk = fsub((float)(x - ix + (t & 1)), x0), yk = fsub((float)(y - iy + (t >> 1)), y0);
-									const float rk = fdiv(1.0f, __fmaf_rn(xk, wA, fadd(wC, fmul(yk, wB))));
-									uu[t] = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], d.slotMode[UV], xk, yk, rk);
-									vv[t] = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], d.slotMode[UV + 1], xk, yk, rk);
+									const float rk = rhwConst != 0.0f ? rhwConst : fdiv(1.0f, __fmaf_rn(xk, wA, fadd(wC, fmul(yk, wB))));
+									uu[t] = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], modeU, xk, yk, rk);
+									vv[t] = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], modeV, xk, yk, rk);
 								}
-								const float u = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], d.slotMode[UV], xf, yf, rhw);
-								const float v = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], d.slotMode[UV + 1], xf, yf, rhw);
+								const float u = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], modeU, xf, yf, rhw);
+								const float v = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], modeV, xf, yf, rhw);
 								if(d.texFast) sample_texture<true>(d, compute_lod<true>(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]), u, v, texel);
 								else sample_texture<false>(d, compute_lod<false>(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]), u, v, texel);
 							}
@@ -1269,25 +1411,40 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 							for(int ch = 0; ch < 4; ch++)
 							{
 								float val;
-								const uint32_t kind = d.chanKind[ch];
-								if(kind == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
-								else if(TEX && kind == CK_TEXEL)
+								if(FS)
 								{
-									const uint32_t t = d.chanValue[ch];
-									val = t == 0 ? texel[0] : t == 1 ? texel[1] : t == 2 ? texel[2] : texel[3];
+									// routing checked on the host: constant shader -> constants; texture shader -> texel channel ch;
+									// varying shader -> slot ch, or a constant (e.g. alpha = 1)
+									if(SH == SH_CONST) val = __uint_as_float(d.chanValue[ch]);
+									else if(SH == SH_TEX) val = texel[ch];
+									else
+									{
+										val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], IM_PERSP, xf, yf, rhw);
+										if(d.chanKind[ch] == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
+									}
 								}
-								else if(SH == SH_VARY || SH == SH_GENERIC) val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], d.slotMode[ch], xf, yf, rhw);
-								else val = 0.0f;
+								else
+								{
+									const uint32_t kind = d.chanKind[ch];
+									if(kind == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
+									else if(TEX && kind == CK_TEXEL)
+									{
+										const uint32_t t = d.chanValue[ch];
+										val = t == 0 ? texel[0] : t == 1 ? texel[1] : t == 2 ? texel[2] : texel[3];
+									}
+									else if(SH == SH_VARY || SH == SH_GENERIC) val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], d.slotMode[ch], xf, yf, rhw);
+									else val = 0.0f;
+								}
 								rgba[ch] = sse_min(sse_max(val, 0.0f), 1.0f); // PixelProgram::clampColor :286-364
 							}
 
 							// ---- stencil test, depth test, depth write, blend + colour write, stencil write ----
 							bool sPass = true;
 							uint32_t sValue = 0;
-							const uint32_t triFlags = wHdr[k].w;
-							if(d.stencilActive)
+							const uint32_t frontFacing = FS ? 1u : (wHdr[k].z >> 28) & 1u;
+							if(!FS && d.stencilActive)
 							{
-								const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
+								const KStencilFace &face = frontFacing ? d.front : d.back;
 								sValue = smStencil[pi];
 								sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
 							}
@@ -1296,11 +1453,20 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 							if(d.depthTestActive)
 							{
 								float yy = yf, xx = xf;
-								if(MS > 1) { yy = fadd(yy, c_SampleY[q]); xx = fsub(xx, c_SampleX[q]); }
+								if(MS > 1)
+								{
+									// sample position relative to the pixel centre (Constants.cpp:291-297), in eighths: Y = 2q - 3, X = {-1, 3, -3, 1}
+									const float sy = fmul((float)(2 * q - 3), 0.125f);
+									const float sx = fmul((float)(int)(signed char)(0x01FD03FFu >> (8 * q)), 0.125f);
+									yy = fadd(yy, sy);
+									xx = fsub(xx, sx);
+								}
 								z = __fmaf_rn(xx, zA, fadd(zC, fmul(yy, zB)));
 								if(biasOn) z = fadd(z, zBias);
 								z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
-								zPass = depth_compare(d.depthCompareOp, smDepth[pi], z);
+								const float zValue = smDepth[pi];
+								if(FS) zPass = d.depthCompareOp == CMP_LESS ? !(zValue <= z) : !(zValue < z); // LESS / LESS_OR_EQUAL (:533-553)
+								else zPass = depth_compare(d.depthCompareOp, zValue, z);
 							}
 							if(zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
 							{
@@ -1315,8 +1481,8 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 #pragma unroll
 										for(int ch = 0; ch < 4; ch++)
 										{
-											const uint32_t bsel = (px >> (8 * ((d.bgr && ch < 3) ? 2 - ch : ch))) & 0xFF;
-											dst[ch] = fmul((float)(bsel * 257), 1.0f / 0xFFFF);
+											const uint32_t byte = (bgr && ch < 3) ? 2 - ch : ch;
+											dst[ch] = fmul((float)__byte_perm(px, 0, 0x4400u | byte | (byte << 4)), 1.0f / 0xFFFF); // b * 257 == b << 8 | b
 										}
 										if(BL == BL_SRC_ALPHA)
 										{
@@ -1332,21 +1498,14 @@ __global__ void __launch_bounds__(TILE_THREADS) k_tile(const __grid_constant__ D
 											o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
 										}
 									}
-									uint32_t pk = 0;
-#pragma unroll
-									for(int ch = 0; ch < 4; ch++) // writeColor :1981-1992, :2603-2655
-									{
-										const float cl = sse_min(sse_max(o[ch], 0.0f), 1.0f);
-										const uint32_t v = (uint32_t)__float2int_rn(fmul(cl, 255.0f)); // cl in [0,1] (NaN already folded to 0)
-										pk |= v << (8 * ((d.bgr && ch < 3) ? 2 - ch : ch));
-									}
+									const uint32_t pk = bgr ? pack_unorm8(o[2], o[1], o[0], o[3]) : pack_unorm8(o[0], o[1], o[2], o[3]);
 									smColor[pi] = (px & ~wmask32) | (pk & wmask32);
 									dirty = true;
 								}
 							}
-							if(d.stencilWrite) // writeStencil :754-817
+							if(!FS && d.stencilWrite) // writeStencil :754-817
 							{
-								const KStencilFace &face = (triFlags & 1) ? d.front : d.back;
+								const KStencilFace &face = frontFacing ? d.front : d.back;
 								const uint32_t ref = face.reference & 0xFF;
 								uint32_t nv;
 								if(!sPass) nv = stencil_op(face.failOp, sValue, ref);

@@ -42,15 +42,23 @@ def cuda_outputs(device, scene):
     return att, scenes.outputs(scene, att, res)
 
 
-@pytest.mark.parametrize("binned", [0, 1], ids=["direct", "binned"])
+# direct: no binning; binned: forced through the sort; generic: binned, with the fast-state instantiations of the tile
+# kernel switched off, so every scene also runs the instantiation that decodes the fixed-function state at run time
+MODES = {"direct": (0, 1), "binned": (1, 1), "generic": (1, 0)}
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_cuda_matches_reference_golden_and_oracle(device, name, binned):
+def test_cuda_matches_reference_golden_and_oracle(device, name, mode):
     scene = CASES[name]
+    binned, fast = MODES[mode]
     device.set_option("force_binned", binned)
+    device.set_option("fast_state", fast)
     try:
         att, out = cuda_outputs(device, scene)
     finally:
         device.set_option("force_binned", 0)
+        device.set_option("fast_state", 1)
     for k, h in HASHES[name].items():
         if sha(out[k]) != h:
             # value-level diagnosis against the oracle (which is pinned to the same goldens on the CPU side)
