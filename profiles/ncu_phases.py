@@ -1,23 +1,38 @@
 #!/usr/bin/env python
 """Per-phase instruction totals of one kernel from an ncu source page (cuda,sass view), SASS rows de-duplicated by address.
-usage: python profiles/ncu_phases.py x.csv <kernel substring> name:lo-hi [...]   (line ranges of kernels.cuh)"""
+Phases are delimited by marker substrings searched in kernels.cuh, so the tool follows
+the code as it moves (the file on disk, or $KERNELS_CUH, must be the profiled version).  usage: python profiles/ncu_phases.py x.csv <kernel substring> [warps]"""
 import csv
 import sys
 
+MARKERS = [  # (phase, substring of the first line of the phase), in file order
+    ("helpers", "small helpers (Reactor semantics"),
+    ("sampler", "DEVI uint32_t mulhi16"),
+    ("pixhelp", "DEVI bool stencil_compare"),
+    ("tile-prolog", "FS (\"fast state\")"),
+    ("scan", "list scan with one block of look-ahead"),
+    ("admit", "hits join the batch in list order"),
+    ("planes-stage", "plane equations of the batch -> shared memory"),
+    ("coverage-L", "coverage (QuadRasterizer.cpp:181-206), one candidate per lane"),
+    ("scan-place", "where do my pairs and items start"),
+    ("coverage", "coverage (QuadRasterizer.cpp:181-206)"),
+    ("psum", "first item of each pair"),
+    ("item-find", "consume the items 32 at a time"),
+    ("item-planes", "plane equations of the triangle ----"),
+    ("item-shade", "interpolate + routed fragment shader"),
+    ("item-tests", "stencil test, depth test, depth write"),
+    ("item-blend", "const uint32_t px = smColor[pi];"),
+    ("item-stencilw", "writeStencil :754-817"),
+    ("tile-epilog", "never leave with a bulk copy"),
+    ("after", "the steps either side of the draw"),
+]
 rows = list(csv.reader(open(sys.argv[1])))
 kern = sys.argv[2]
-ranges = []
-for a in sys.argv[3:]:
-    n, r = a.split(":")
-    lo, hi = r.split("-")
-    ranges.append((n, int(lo), int(hi)))
-hdr = next(r for r in rows if r and r[0] == "Line No")
-ci = {}
-for i, n in enumerate(hdr):
-    ci.setdefault(n, i)
+warps = float(sys.argv[3]) if len(sys.argv) > 3 else 0
+hdr, ci = None, {}
 seen = {}
-fn = sec = None
-cur = None
+srcline = {}
+fn = sec = cur = None
 for r in rows:
     if r and r[0] == "File Path":
         sec = r[1].split("/")[-1]
@@ -25,10 +40,17 @@ for r in rows:
     if r and r[0] == "Function Name":
         fn = r[1]
         continue
-    if len(r) < len(hdr) or r[0] == "Line No":
+    if r and r[0] == "Line No":  # every section has its own header (the column count varies)
+        hdr, ci = r, {}
+        for i, n in enumerate(hdr):
+            ci.setdefault(n, i)
+        continue
+    if hdr is None or len(r) < len(hdr):
         continue
     if r[0]:
         cur = (sec, int(r[0]))
+        if sec == "kernels.cuh":
+            srcline[int(r[0])] = r[1]
         continue
     if fn is None or kern not in fn or r[2] in ("", "..."):
         continue
@@ -37,21 +59,36 @@ for r in rows:
         smp = float(r[ci["# Samples"]] or 0)
     except ValueError:
         continue
-    seen.setdefault(r[2], (cur, inst, smp, r[3].strip()))
-agg = {n: [0.0, 0.0, 0] for n, _, _ in ranges}
-agg["other"] = [0.0, 0.0, 0]
-for addr, ((sec, ln), inst, smp, txt) in seen.items():
-    name = "other"
-    if sec == "kernels.cuh":
-        for n, lo, hi in ranges:
-            if lo <= ln <= hi:
-                name = n
-                break
-    agg[name][0] += inst
-    agg[name][1] += smp
-    agg[name][2] += 1
+    seen.setdefault(r[2], (cur, inst, smp))
+import os
+SRC = os.environ.get("KERNELS_CUH", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "swiftshader_b200", "csrc", "kernels.cuh"))
+srcline = {i + 1: l for i, l in enumerate(open(SRC).read().splitlines())}  # must be the profiled version of the file
+starts = []
+for name, sub in MARKERS:
+    ln = next((l for l in sorted(srcline) if sub in srcline[l]), None)
+    if ln is not None:
+        starts.append((ln, name))
+starts.sort()
+def phase(sec, ln):
+    if sec != "kernels.cuh":
+        return "intrinsics"
+    name = "head"
+    for l, n in starts:
+        if ln >= l:
+            name = n
+    return name
+agg = {}
+for addr, ((sec, ln), inst, smp) in seen.items():
+    a = agg.setdefault(phase(sec, ln), [0.0, 0.0, 0])
+    a[0] += inst
+    a[1] += smp
+    a[2] += 1
 ti = sum(v[0] for v in agg.values()) or 1
 ts = sum(v[1] for v in agg.values()) or 1
 print(f"{kern}: {ti:.4e} warp-instructions, {ts:.0f} samples, {len(seen)} SASS instructions")
-for n, (i, s, c) in agg.items():
-    print(f"{n:12s} {100 * i / ti:5.1f}% inst  {100 * s / ts:5.1f}% samples  ({i:.3e} warp-inst, {c} SASS)")
+order = ["head"] + [n for _, n in starts] + ["intrinsics"]
+for n in order:
+    if n in agg:
+        i, s, c = agg[n]
+        per = f"  {i / warps:7.0f}/warp" if warps else ""
+        print(f"{n:14s} {100 * i / ti:5.1f}% inst  {100 * s / ts:5.1f}% samples  ({i:.3e} warp-inst, {c} SASS){per}")

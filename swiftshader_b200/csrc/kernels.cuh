@@ -989,14 +989,15 @@ struct TileLayout
 	// A batch is bounded three ways when it is formed: NB candidates, PCAP (candidate, region row, sample) pairs and ICAP
 	// covered samples (both from the bounding boxes, before any span is read), so the per-warp area stays small enough for
 	// 8 CTAs per SM with the 4x MSAA colour + depth tile.
-	static constexpr int PCAP = MS == 4 ? 224 : 256;
+	static constexpr int PCAP = MS == 4 ? 208 : 256;
 	static constexpr int ICAP = MS == 4 ? 1536 : 2048;
 	// per-warp area
 	static constexpr int W_HDR = 0;                                  // uint4 hdr[NB]: {span rows pointer (lo, hi), yMin | rows << 14 | flags << 28, triangle}
 	static constexpr int W_PLANES = W_HDR + 16 * NB;                 // float4 planes[NB][NF4]
 	static constexpr int W_PAIRS = W_PLANES + 16 * NB * NF4;         // uint32 pairs[PCAP]: start << 18 | cand << 13 | code << 8 | x0 << 4 | (n - 1)
 	static constexpr int W_BITS = W_PAIRS + 4 * PCAP;                // uint32 bits[ICAP / 32]: bit i set <=> a pair starts at item i
-	static constexpr int W_BYTES = (W_BITS + ICAP / 8 + 15) & ~15;
+	static constexpr int W_COV = W_BITS + ICAP / 8;                  // uint32 cov[16]: samples of the region covered by the current range (conflict test)
+	static constexpr int W_BYTES = (W_COV + 64 + 15) & ~15;
 	static constexpr int HEAD_B = 128;                               // mbarrier + dirty flag
 	__host__ __device__ static int total(bool depth, bool stencil)
 	{
@@ -1080,8 +1081,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 {
 	using L = TileLayout<MS, SH>;
 	constexpr int NB = L::NB, NF4 = L::NF4, PCAP = L::PCAP, ICAP = L::ICAP;
-	constexpr int CPI = MS == 4 ? 1 : 4;  // candidates per coverage iteration
-	constexpr int NITER = NB / CPI;
+	constexpr int LPC = MS == 4 ? 2 : 1;                 // lanes per candidate in the coverage step
+	constexpr int RPL = SWCU_REGION_H / LPC;              // region rows per lane
+	static_assert(NB * LPC == 32, "one batch fills the warp");
 	constexpr bool TEX = SH == SH_TEX || SH == SH_GENERIC;
 	constexpr int UV = SH == SH_TEX ? 0 : 4;
 	constexpr int TP = SWCU_TILE_W * SWCU_TILE_H; // pixels per sample plane of the tile
@@ -1108,18 +1110,13 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 	const int rx = tileX + (warp % (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_W; // this warp's region
 	const int ry = tileY + (warp / (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_H;
 	const int regionPi = (ry - tileY) * SWCU_TILE_W + (rx - tileX); // index of the region's first pixel inside a staged plane
-	// coverage is computed per (region row, sample): MS == 4: lane = row * 4 + sample; MS == 1: lane = sub * 8 + row, four candidates at a time
-	const int covRow = MS == 4 ? lane >> 2 : lane & 7;
-	const int covQ = MS == 4 ? lane & 3 : 0;
-	const bool covOn = (MS == 4 && !FS) ? ((d.sampleMask >> covQ) & 1) != 0 : true;
-	const int covOff = (ry + covRow) * MS + covQ; // my entry in a span table that starts at row 0
-	const uint32_t covCode = MS == 4 ? (uint32_t)lane : (uint32_t)covRow;
 
 	unsigned char *wa = warpBase + warp * L::W_BYTES;
 	uint4 *wHdr = (uint4 *)(wa + L::W_HDR);
 	float4 *wPlanes = (float4 *)(wa + L::W_PLANES);
 	uint32_t *wPairs = (uint32_t *)(wa + L::W_PAIRS);
 	uint32_t *wBits = (uint32_t *)(wa + L::W_BITS);
+	uint32_t *wCov = (uint32_t *)(wa + L::W_COV);
 
 	// ---- stage the tile: TMA when the attachments allow it ----
 	if(threadIdx.x == 0)
@@ -1175,9 +1172,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 		}
 	}
 	int ns = 0;             // candidates staged so far for the next batch
-	uint32_t accU = 0;      // their pair bound << 16 | item bound
 	uint32_t pend = 0;      // lanes whose scanned hit is not staged yet
-	uint32_t tri = 0, hy = 0, myU = 0;
+	uint32_t tri = 0, hy = 0;
 	const unsigned char *hrows = nullptr;
 	for(uint32_t pos = begin;;)
 	{
@@ -1197,11 +1193,6 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 					// the rows inlined in the record otherwise
 					hrows = (hN.w & 2u) ? (const unsigned char *)(d.spans + hN.z) : d.triRecords + (size_t)triN * d.triStride + TRI_HEADER_BYTES + 16 * NF4;
 					hrows -= (size_t)yMin * (MS * 4);
-					// bounds of what the candidate can add to a batch: one pair per (row, sample) of its rows inside the region, and
-					// at most its column range inside the region per pair (the pixel bounds cover every span, see k_setup)
-					const int rowsIn = min(yMax, ry + SWCU_REGION_H) - max(yMin, ry);
-					const int colsIn = min(pxMax, rx + SWCU_REGION_W) - max(pxMin, rx);
-					myU = ((uint32_t)(rowsIn * MS) << 16) | (uint32_t)(rowsIn * MS * colsIn);
 				}
 			}
 			pend = __ballot_sync(0xFFFFFFFFu, hit);
@@ -1213,38 +1204,22 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 				hN = __ldg((const uint4 *)(d.triRecords + (size_t)triN * d.triStride));
 			}
 		}
-		bool full = false;
 		if(pend)
 		{
-			// ---- hits join the batch in list order while it has room (slots, pairs, items); the rest wait for the next batch ----
-			const bool mineP = (pend >> lane) & 1;
-			uint32_t incl = mineP ? myU : 0u;
-#pragma unroll
-			for(int o = 1; o < 32; o <<= 1)
-			{
-				const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-				if(lane >= o) incl += t;
-			}
+			// ---- hits go to the free slots of the batch, in list order; the rest wait for the next batch ----
 			const int rank = __popc(pend & laneLt);
-			const uint32_t sum = accU + incl;
-			const bool admit = mineP && ns + rank < NB && (sum >> 16) <= (uint32_t)PCAP && (sum & 0xFFFFu) <= (uint32_t)ICAP;
-			const uint32_t adm = __ballot_sync(0xFFFFFFFFu, admit);
-			if(admit) wHdr[ns + rank] = make_uint4((uint32_t)(uintptr_t)hrows, (uint32_t)((uintptr_t)hrows >> 32), hy, tri);
-			if(adm)
-			{
-				accU += __shfl_sync(0xFFFFFFFFu, incl, 31 - __clz(adm)); // admitted lanes are a prefix of the pending ones
-				ns += __popc(adm);
-				pend &= ~adm;
-			}
-			full = pend != 0;
+			const int take = min(__popc(pend), NB - ns);
+			const bool mine = ((pend >> lane) & 1) && rank < take;
+			if(mine) wHdr[ns + rank] = make_uint4((uint32_t)(uintptr_t)hrows, (uint32_t)((uintptr_t)hrows >> 32), hy, tri);
+			pend &= ~__ballot_sync(0xFFFFFFFFu, mine);
+			ns += take;
 		}
 		const bool listDone = pend == 0 && pos >= end;
-		if(!full && ns < NB && !listDone) continue;
+		if(ns < NB && !listDone) continue;
 		if(ns == 0) break;
 		{
 			const int nb = ns;
 			ns = 0;
-			accU = 0;
 			__syncwarp();
 			// ---- plane equations of the batch -> shared memory, asynchronously (needed only when the items are consumed) ----
 			for(int i = lane; i < nb * NF4; i += 32)
@@ -1253,86 +1228,118 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 				cp_async16(wPlanes + i, d.triRecords + (size_t)wHdr[s].w * d.triStride + TRI_HEADER_BYTES + 16 * j);
 			}
 			cp_async_commit();
-			// ---- the span of my (region row, sample) in every candidate, all loads in flight together ----
-			uint32_t sp[NITER];
-#pragma unroll
-			for(int it = 0; it < NITER; it++)
+
+			// ---- coverage (QuadRasterizer.cpp:181-206), one candidate per lane (MS == 1) or per lane pair (MS == 4: rows 0-3 and
+			//      4-7 of the region): the lane reads its rows' spans, clips [left, right) to the region's 16 columns — a run of
+			//      n pixels from x0 — and keeps the non-empty (row, sample) pairs packed in registers.  A warp scan over the lanes
+			//      then places the pairs and their first items, so the lanes write the pair words (and the start marks) directly;
+			//      no per-candidate warp iteration, no second pass over the pairs.  A range [c0, c1) of the batch whose pairs
+			//      and items fit the shared-memory areas is taken at a time (normally the whole batch) ----
+			for(int c0 = 0; c0 < nb;)
 			{
-				sp[it] = 0; // empty span outside the triangle's rows
-				if(it * CPI < nb)
+			int c1;
+			uint32_t total;
+			bool conflicts = false; // does any sample of the region receive two fragments in this range?
+			{
+				const int cand = c0 + lane / LPC;
+				const int rowBase = (lane % LPC) * RPL; // first region row of this lane
+				const bool active = cand < nb;
+				uint4 hh = make_uint4(0, 0, 0, 0);
+				if(active) hh = wHdr[cand];
+				const unsigned char *rowsPtr = (const unsigned char *)(((uintptr_t)hh.y << 32) | hh.x);
+				const uint32_t yMin = hh.z & 0x3FFFu, nrows = (hh.z >> 14) & 0x3FFFu;
+				uint32_t sp[RPL][MS];
+#pragma unroll
+				for(int r = 0; r < RPL; r++)
 				{
-					const int s = MS == 4 ? it : it * CPI + (lane >> 3);
-					if(s < nb && covOn)
+					const uint32_t y = (uint32_t)(ry + rowBase + r);
+					const bool in = active && (y - yMin) < nrows;
+					if(MS == 4)
 					{
-						const uint4 hh = wHdr[s];
-						const uint32_t rel = (uint32_t)(ry + covRow) - (hh.z & 0x3FFFu);
-						if(rel < ((hh.z >> 14) & 0x3FFFu))
-							sp[it] = __ldg((const uint32_t *)(((uintptr_t)hh.y << 32) | hh.x) + covOff);
+						uint4 v = make_uint4(0, 0, 0, 0); // empty spans outside the triangle's rows
+						if(in) v = __ldg((const uint4 *)(rowsPtr + (size_t)y * 16));
+						sp[r][0] = v.x; sp[r][MS > 1 ? 1 : 0] = v.y; sp[r][MS > 1 ? 2 : 0] = v.z; sp[r][MS > 1 ? 3 : 0] = v.w;
+					}
+					else
+					{
+						sp[r][0] = 0;
+						if(in) sp[r][0] = __ldg((const uint32_t *)(rowsPtr + (size_t)y * 4));
 					}
 				}
-			}
-			// zero the start marks while the loads fly (the previous batch's rounds ended with a __syncwarp)
+				// zero the start marks while the loads fly (the previous rounds ended with a __syncwarp)
 #pragma unroll
-			for(int i = 0; i < (ICAP / 32 + 31) / 32; i++)
-				if(lane + 32 * i < ICAP / 32) wBits[lane + 32 * i] = 0;
-
-			// ---- coverage (QuadRasterizer.cpp:181-206): the span [left, right) clipped to the region's 16 columns is a run of
-			//      n pixels from x0; (candidate, row, sample) pairs with coverage are compacted in candidate order ----
-			int P = 0;
-			uint32_t accMask = 0, overlap = 0; // does any sample of the region receive two fragments in this batch?
+				for(int i = 0; i < (ICAP / 32 + 31) / 32; i++)
+					if(lane + 32 * i < ICAP / 32) wBits[lane + 32 * i] = 0;
+				if(lane < 16) wCov[lane] = 0;
+				uint32_t runs[RPL * MS / 4]; // per pair: x0 << 4 | (n - 1), four pairs per register
+				uint32_t valid = 0, items = 0;
 #pragma unroll
-			for(int it = 0; it < NITER; it++)
-			{
-				if(it * CPI < nb)
+				for(int j = 0; j < RPL * MS; j++)
 				{
-					const int s = MS == 4 ? it : it * CPI + (lane >> 3);
-					const int a = clampi((int)(sp[it] & 0xFFFF) - rx, 0, 16), e = clampi((int)(sp[it] >> 16) - rx, 0, 16);
+					const int r = j / MS, q = j % MS;
+					uint32_t v = sp[r][q];
+					if(MS == 4 && !FS && !((d.sampleMask >> q) & 1)) v = 0;
+					const int a = clampi((int)(v & 0xFFFF) - rx, 0, 16), e = clampi((int)(v >> 16) - rx, 0, 16);
 					const int n = e - a;
 					const bool has = n > 0;
-					const uint32_t mask = has ? (((1u << n) - 1u) << a) : 0u;
-					overlap |= accMask & mask;
-					accMask |= mask;
-					const uint32_t nz = __ballot_sync(0xFFFFFFFFu, has);
-					if(has) wPairs[P + __popc(nz & laneLt)] = ((uint32_t)s << 13) | (covCode << 8) | ((uint32_t)a << 4) | (uint32_t)(n - 1);
-					P += __popc(nz);
+					const uint32_t run = has ? (((uint32_t)a << 4) | (uint32_t)(n - 1)) : 0u;
+					if(j % 4 == 0) runs[j / 4] = run; else runs[j / 4] |= run << (8 * (j % 4));
+					if(has) { valid |= 1u << j; items += (uint32_t)n; }
 				}
-			}
-			if(MS == 1)
-			{
-				// four candidates per iteration share a row: fold the per-lane accumulators of the four sub-streams
-#pragma unroll
-				for(int o = 8; o < 32; o <<= 1)
-				{
-					const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, accMask, o);
-					overlap |= accMask & other;
-					accMask |= other;
-				}
-			}
-			const bool conflicts = __any_sync(0xFFFFFFFFu, overlap != 0);
-			__syncwarp();
-			// ---- first item of each pair (exclusive prefix sum of the run lengths), stored in the pair word and as a mark bit ----
-			uint32_t total = 0;
-			for(int p0 = 0; p0 < P; p0 += 32)
-			{
-				const int p = p0 + lane;
-				const uint32_t w = p < P ? wPairs[p] : 0u;
-				const uint32_t c = p < P ? (w & 15u) + 1u : 0u;
-				uint32_t incl = c;
+				// ---- where do my pairs and items start?  (inclusive scan of pairs << 16 | items over the lanes) ----
+				const uint32_t mineU = ((uint32_t)__popc(valid) << 16) | items;
+				uint32_t incl = mineU;
 #pragma unroll
 				for(int o = 1; o < 32; o <<= 1)
 				{
 					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
 					if(lane >= o) incl += t;
 				}
-				if(p < P)
+				// a candidate is taken whole: the sums at its last lane must fit
+				const uint32_t inclC = LPC == 1 ? incl : __shfl_sync(0xFFFFFFFFu, incl, lane | (LPC - 1));
+				const bool fits = active && (inclC >> 16) <= (uint32_t)PCAP && (inclC & 0xFFFFu) <= (uint32_t)ICAP;
+				const uint32_t fitMask = __ballot_sync(0xFFFFFFFFu, fits); // a prefix of the lanes, never empty (one candidate always fits)
+				const int lastLane = 31 - __clz(fitMask);
+				const uint32_t sums = __shfl_sync(0xFFFFFFFFu, incl, lastLane);
+				total = sums & 0xFFFFu;
+				c1 = c0 + (lastLane + 1) / LPC;
+				__syncwarp(); // start marks zeroed
+				if(fits)
 				{
-					const uint32_t start = total + incl - c;
-					wPairs[p] = w | (start << 18);
-					if(start < (uint32_t)ICAP) atomicOr(wBits + (start >> 5), 1u << (start & 31));
+					uint32_t pairIdx = (incl - mineU) >> 16, start = (incl - mineU) & 0xFFFFu;
+					const uint32_t word0 = ((uint32_t)cand << 13) | (MS == 4 ? (uint32_t)rowBase << 10 : 0u);
+#pragma unroll
+					for(int j = 0; j < RPL * MS; j++)
+					{
+						if((valid >> j) & 1)
+						{
+							const uint32_t run = (runs[j / 4] >> (8 * (j % 4))) & 0xFFu;
+							// code (bits 8-12) = region row << 2 | sample for MS == 4 (j = r * 4 + q, the lane's first row comes in
+							// through word0), region row for MS == 1 (j = r)
+							wPairs[pairIdx] = (start << 18) | (word0 + ((uint32_t)j << 8)) | run;
+							atomicOr(wBits + (start >> 5), 1u << (start & 31));
+							pairIdx++;
+							start += (run & 15u) + 1u;
+						}
+					}
 				}
-				total += __shfl_sync(0xFFFFFFFFu, incl, 31);
+				__syncwarp();
+				// ---- two fragments on one sample?  Every pair ORs its run into a bitmap of the region's samples; a bit that was
+				//      already set means an earlier (or later) pair covers the sample too.  One candidate alone cannot overlap itself ----
+				if(c1 - c0 > 1)
+				{
+					const uint32_t P = sums >> 16;
+					uint32_t ov = 0;
+					for(uint32_t p = lane; p < P; p += 32)
+					{
+						const uint32_t w = wPairs[p];
+						const uint32_t code = (w >> 8) & 31u;
+						const uint32_t m = ((2u << (w & 15u)) - 1u) << (((w >> 4) & 15u) + 16u * (code & 1u));
+						ov |= atomicOr(wCov + (code >> 1), m) & m;
+					}
+					conflicts = __any_sync(0xFFFFFFFFu, ov != 0);
+				}
 			}
-			if(total > (uint32_t)ICAP) __trap(); // the pixel bounds of a record did not cover its spans
 			cp_async_wait_all();
 			__syncwarp();
 			if(total && !tileReady)
@@ -1356,11 +1363,11 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 					// items of the same (pixel, sample) in this round run in queue order
 					const uint32_t key = valid ? ((code << 4) | (uint32_t)bit) : (0x200u | lane); // one key per sample of the region
 					int prank = 0, maxRank = 0;
-					if(conflicts) // overlapping triangles in this batch: same-sample items of a round run in list order
+					if(conflicts) // overlapping triangles in this range: same-sample items of a round run in list order
 					{
 						const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
 						prank = __popc(peers & laneLt);
-						maxRank = __reduce_max_sync(0xFFFFFFFFu, valid ? prank : 0);
+						maxRank = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(valid ? prank : 0));
 					}
 					for(int rr = 0; rr <= maxRank; rr++)
 					{
@@ -1521,7 +1528,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 				}
 				__syncwarp();
 			}
-			__syncwarp(); // the staging area is reused by the next batch
+			__syncwarp(); // the pair / mark areas are reused by the next range
+			c0 = c1;
+			}
 		}
 		if(listDone) break;
 	}
