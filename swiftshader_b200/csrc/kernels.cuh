@@ -1270,9 +1270,15 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 #pragma unroll
 				for(int i = 0; i < (ICAP / 32 + 31) / 32; i++)
 					if(lane + 32 * i < ICAP / 32) wBits[lane + 32 * i] = 0;
-				if(lane < 16) wCov[lane] = 0;
+				if(MS == 4 && lane < 16) wCov[lane] = 0;
 				uint32_t runs[RPL * MS / 4]; // per pair: x0 << 4 | (n - 1), four pairs per register
 				uint32_t valid = 0, items = 0;
+				uint32_t cw[MS == 1 ? RPL / 2 : 1]; // MS == 1: my candidate's coverage of the region, two rows per word
+				if(MS == 1)
+				{
+#pragma unroll
+					for(int i = 0; i < RPL / 2; i++) cw[i] = 0;
+				}
 #pragma unroll
 				for(int j = 0; j < RPL * MS; j++)
 				{
@@ -1285,6 +1291,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 					const uint32_t run = has ? (((uint32_t)a << 4) | (uint32_t)(n - 1)) : 0u;
 					if(j % 4 == 0) runs[j / 4] = run; else runs[j / 4] |= run << (8 * (j % 4));
 					if(has) { valid |= 1u << j; items += (uint32_t)n; }
+					if(MS == 1) cw[j / 2 < RPL / 2 ? j / 2 : 0] |= (has ? ((1u << n) - 1u) << a : 0u) << (16 * (j & 1));
 				}
 				// ---- where do my pairs and items start?  (inclusive scan of pairs << 16 | items over the lanes) ----
 				const uint32_t mineU = ((uint32_t)__popc(valid) << 16) | items;
@@ -1328,16 +1335,29 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 				//      already set means an earlier (or later) pair covers the sample too.  One candidate alone cannot overlap itself ----
 				if(c1 - c0 > 1)
 				{
-					const uint32_t P = sums >> 16;
-					uint32_t ov = 0;
-					for(uint32_t p = lane; p < P; p += 32)
+					if(MS == 1)
 					{
-						const uint32_t w = wPairs[p];
-						const uint32_t code = (w >> 8) & 31u;
-						const uint32_t m = ((2u << (w & 15u)) - 1u) << (((w >> 4) & 15u) + 16u * (code & 1u));
-						ov |= atomicOr(wCov + (code >> 1), m) & m;
+						// one candidate per lane, all lanes see the same eight rows: the samples covered by the range are the OR of the
+						// lanes' words; fewer of them than items means some sample is covered twice
+						uint32_t covered = 0;
+#pragma unroll
+						for(int i = 0; i < RPL / 2; i++) covered += __popc(__reduce_or_sync(0xFFFFFFFFu, fits ? cw[i] : 0u));
+						conflicts = covered != total;
 					}
-					conflicts = __any_sync(0xFFFFFFFFu, ov != 0);
+					else
+					{
+						const uint32_t P = sums >> 16;
+						uint32_t ov = 0;
+#pragma unroll 2
+						for(uint32_t p = lane; p < P; p += 32)
+						{
+							const uint32_t w = wPairs[p];
+							const uint32_t code = (w >> 8) & 31u;
+							const uint32_t m = ((2u << (w & 15u)) - 1u) << (((w >> 4) & 15u) + 16u * (code & 1u));
+							ov |= atomicOr(wCov + (code >> 1), m) & m;
+						}
+						conflicts = __any_sync(0xFFFFFFFFu, ov != 0);
+					}
 				}
 			}
 			cp_async_wait_all();
