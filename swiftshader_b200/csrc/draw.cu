@@ -5,6 +5,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -649,9 +650,14 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	return SWCU_OK;
 }
 
+struct TileRectCount
+{
+	__host__ __device__ uint32_t operator()(uint32_t r) const { return tile_rect_count(r); }
+};
+
 __global__ void k_pair_total(const uint32_t *pairOffset, const uint32_t *tileCount, uint32_t n, DrawCounters *c)
 {
-	c->pairTotal = (unsigned long long)pairOffset[n - 1] + tileCount[n - 1];
+	c->pairTotal = (unsigned long long)pairOffset[n - 1] + tile_rect_count(tileCount[n - 1]);
 }
 
 // ---- TMA descriptors of the attachments: a 3-D tensor (x, y, sample plane) with a (tile width, tile height, samples) box ----
@@ -813,10 +819,11 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		// ---- binning: pair offsets, totals back to the host (the one sync of a binned draw) ----
 		if((rc = ensure(ctx, ctx->pairOffset, (size_t)n * 4))) return rc;
 		size_t tempBytes = 0;
-		CU(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, (const uint32_t *)d.tileCount, (uint32_t *)ctx->pairOffset.p, (int)n, ctx->stream));
+		thrust::transform_iterator<TileRectCount, const uint32_t *> counts((const uint32_t *)d.tileCount, TileRectCount());
+		CU(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, counts, (uint32_t *)ctx->pairOffset.p, (int)n, ctx->stream));
 		if((rc = ensure(ctx, ctx->cubTemp, tempBytes))) return rc;
 		tempBytes = ctx->cubTemp.cap;
-		CU(cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tempBytes, (const uint32_t *)d.tileCount, (uint32_t *)ctx->pairOffset.p, (int)n, ctx->stream));
+		CU(cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tempBytes, counts, (uint32_t *)ctx->pairOffset.p, (int)n, ctx->stream));
 		{
 			LaunchScope ls(ctx, "k_pair_total");
 			k_pair_total<<<1, 1, 0, ctx->stream>>>((const uint32_t *)ctx->pairOffset.p, d.tileCount, n, d.counters);

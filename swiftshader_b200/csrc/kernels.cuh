@@ -376,12 +376,14 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 	// ---- span-table and big-list allocation for the big triangles, one atomic per warp ----
 	const int rows = visible ? yMax - yMin : 0;
 	bool big = false;
+	uint32_t tileRect = TILE_RECT_NONE; // what k_emit needs to know about this triangle (see tile_rect_count)
 	if(visible)
 	{
 		const int tx0 = pxMin / SWCU_TILE_W, tx1 = (pxMax - 1) / SWCU_TILE_W;
 		const int ty0 = yMin / SWCU_TILE_H, ty1 = (yMax - 1) / SWCU_TILE_H;
 		nTiles = (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
 		big = rows > SWCU_SMALL_ROWS || nTiles > SWCU_SMALL_TILES;
+		tileRect = big ? (TILE_RECT_BIG | nTiles) : ((uint32_t)tx0 | ((uint32_t)ty0 << 9) | ((uint32_t)(tx1 - tx0) << 19) | ((uint32_t)(ty1 - ty0) << 22));
 	}
 	const uint32_t count = big ? (uint32_t)(rows * d.ms) : 0u;
 	unsigned long long base = 0, slot = 0;
@@ -399,10 +401,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 	if(!visible)
 	{
 		*(uint4 *)rec = make_uint4(0, 0, 0, 0); // empty bounds: never a candidate
-		d.tileCount[tri] = 0;
+		d.tileCount[tri] = TILE_RECT_NONE;
 		return;
 	}
-	d.tileCount[tri] = nTiles;
+	d.tileCount[tri] = tileRect;
 
 	if(big)
 	{
@@ -648,18 +650,14 @@ __global__ void __launch_bounds__(256) k_big(const __grid_constant__ DrawConst d
 	}
 }
 
-// (tile, triangle) pairs of the small triangles
+// (tile, triangle) pairs of the small triangles, from the packed tile rectangle k_setup left for each of them
 __global__ void __launch_bounds__(256) k_emit(const __grid_constant__ DrawConst d, const uint32_t *pairOffset, uint32_t *keys, uint32_t *vals)
 {
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
 	if(tri >= d.primCount) return;
-	const uint32_t nT = d.tileCount[tri];
-	if(nT == 0) return;
-	const uint4 hdr = *(const uint4 *)(d.triRecords + (size_t)tri * d.triStride);
-	const int pxMin = hdr.x & 0xFFFF, pxMax = hdr.x >> 16, yMin = hdr.y & 0xFFFF, yMax = hdr.y >> 16;
-	if(hdr.w & 2u) return; // big: k_big emits
-	const int tx0 = pxMin / SWCU_TILE_W, tx1 = (pxMax - 1) / SWCU_TILE_W;
-	const int ty0 = yMin / SWCU_TILE_H, ty1 = (yMax - 1) / SWCU_TILE_H;
+	const uint32_t r = d.tileCount[tri];
+	if(r & TILE_RECT_BIG) return; // big: k_big emits; invisible: nothing to emit
+	const int tx0 = r & 0x1FF, ty0 = (r >> 9) & 0x3FF, tx1 = tx0 + ((r >> 19) & 7), ty1 = ty0 + ((r >> 22) & 7);
 	uint32_t o = pairOffset[tri];
 	for(int ty = ty0; ty <= ty1; ty++)
 		for(int tx = tx0; tx <= tx1; tx++)

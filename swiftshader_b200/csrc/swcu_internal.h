@@ -179,7 +179,7 @@ struct DrawConst
 	unsigned long long spanCapacity;
 	BigTri *bigList;
 	uint32_t bigCapacity;
-	uint32_t *tileCount;       // per triangle: number of (tile, triangle) pairs it will emit
+	uint32_t *tileCount;       // per triangle: packed tile rectangle / pair count (tile_rect_count)
 	DrawCounters *counters;
 	const void *zeroPage;      // 256 readable bytes: target of the discarded loads of branch-free attribute fetches
 	int32_t tilesX, tilesY;    // tile grid of the framebuffer
@@ -197,6 +197,19 @@ struct DrawConst
 //   float  V[nslots][3];               Primitive::V planes {A,B,C} of the routed slots   (padded to a multiple of 16 bytes)
 //   uint32 rows[SWCU_SMALL_ROWS][ms];  small triangles: span {u16 left, u16 right} of row yMin + r, sample q  (Primitive::outline)
 #define TRI_HEADER_BYTES 16
+
+// Per-triangle word k_setup leaves for the binning steps.  Small triangles (<= 8 rows, <= 8 tiles): the tile rectangle
+// tx0 (9 bits) | ty0 << 9 (10 bits) | (tx1 - tx0) << 19 (3 bits) | (ty1 - ty0) << 22 (3 bits) — k_emit needs nothing else.
+// Big triangles: TILE_RECT_BIG | number of tiles of the bounding box (k_big emits them).  Invisible: TILE_RECT_NONE.
+#define TILE_RECT_BIG 0x80000000u
+#define TILE_RECT_NONE 0x80000000u
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline uint32_t tile_rect_count(uint32_t r)
+{
+	return (r & TILE_RECT_BIG) ? (r & 0x7FFFFFFFu) : (((r >> 19) & 7u) + 1u) * (((r >> 22) & 7u) + 1u);
+}
 #define TRI_FLOATS_FIXED 9
 static inline uint32_t swcu_tri_plane_f4(int nslots) { return (uint32_t)((TRI_FLOATS_FIXED + 3 * nslots + 3) / 4); }
 static inline uint32_t swcu_tri_stride(int nslots, int ms) { return TRI_HEADER_BYTES + 16 * swcu_tri_plane_f4(nslots) + 4 * SWCU_SMALL_ROWS * (uint32_t)ms; }
