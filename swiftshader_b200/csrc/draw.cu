@@ -874,7 +874,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		CU(cudaMemsetAsync(ctx->tileEnd.p, 0, (size_t)numTiles * 4, ctx->stream));
 		{
 			LaunchScope ls(ctx, "k_tile_ranges");
-			k_tile_ranges<<<(pairs + 255) / 256, 256, 0, ctx->stream>>>((const uint32_t *)ctx->keys.p, pairs, numTiles, (uint32_t *)ctx->tileBegin.p, (uint32_t *)ctx->tileEnd.p);
+			k_tile_ranges<<<(pairs + 1023) / 1024, 256, 0, ctx->stream>>>((const uint32_t *)ctx->keys.p, pairs, numTiles, (uint32_t *)ctx->tileBegin.p, (uint32_t *)ctx->tileEnd.p);
 		}
 		break;
 	}

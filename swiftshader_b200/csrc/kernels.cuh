@@ -304,16 +304,13 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 		do
 		{
 			triangle_indices(d, tri, idx);
-			// every attribute the two stages consume, for the three vertices, fetched up front
+			// the positions of the three vertices, fetched together; the other attributes wait until the triangle is known to be
+			// visible (a rank of a multi-GPU frame rejects everything outside its band here)
 			float pos[3][4];
 #pragma unroll
 			for(int a = 0; a < 3; a++)
 #pragma unroll
 				for(int c = 0; c < 4; c++) pos[a][c] = vs_operand(d, d.vsPos[c], idx[a]);
-#pragma unroll
-			for(int a = 0; a < 3; a++)
-#pragma unroll
-				for(int k = 0; k < SWCU_MAXSLOTS; k++) sv[a][k] = k < d.nslots ? vs_operand(d, d.slotSrc[k], idx[a]) : 0.0f;
 			process_vertex(d, pos[0][0], pos[0][1], pos[0][2], pos[0][3], va);
 			process_vertex(d, pos[1][0], pos[1][1], pos[1][2], pos[1][3], vb);
 			process_vertex(d, pos[2][0], pos[2][1], pos[2][2], pos[2][3], vc);
@@ -405,6 +402,11 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 		return;
 	}
 	d.tileCount[tri] = tileRect;
+	// the attributes behind the plane slots (usually the same cache lines as the positions); in flight during the span work
+#pragma unroll
+	for(int a = 0; a < 3; a++)
+#pragma unroll
+		for(int k = 0; k < SWCU_MAXSLOTS; k++) sv[a][k] = k < d.nslots ? vs_operand(d, d.slotSrc[k], idx[a]) : 0.0f;
 
 	if(big)
 	{
@@ -668,15 +670,32 @@ __global__ void __launch_bounds__(256) k_emit(const __grid_constant__ DrawConst 
 		}
 }
 
-// start/end of every tile's run in the sorted pair array
+// start/end of every tile's run in the sorted pair array; four keys per thread
 __global__ void k_tile_ranges(const uint32_t *keys, uint32_t n, uint32_t numTiles, uint32_t *tileBegin, uint32_t *tileEnd)
 {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if(i >= n) return;
-	const uint32_t k = keys[i];
-	if(k >= numTiles) return;
-	if(i == 0 || keys[i - 1] != k) tileBegin[k] = i;
-	if(i + 1 == n || keys[i + 1] != k) tileEnd[k] = i + 1;
+	const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if(i0 >= n) return;
+	uint32_t k[6]; // keys i0 - 1 .. i0 + 4
+	if(i0 + 4 <= n)
+	{
+		const uint4 v = *(const uint4 *)(keys + i0);
+		k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+	}
+	else
+	{
+#pragma unroll
+		for(int j = 0; j < 4; j++) k[1 + j] = i0 + j < n ? keys[i0 + j] : 0xFFFFFFFFu;
+	}
+	k[0] = i0 > 0 ? keys[i0 - 1] : 0xFFFFFFFFu;
+	k[5] = i0 + 4 < n ? keys[i0 + 4] : 0xFFFFFFFFu;
+#pragma unroll
+	for(int j = 0; j < 4; j++)
+	{
+		const uint32_t i = i0 + j, key = k[1 + j];
+		if(i >= n || key >= numTiles) continue;
+		if(i == 0 || k[j] != key) tileBegin[key] = i;
+		if(i + 1 == n || k[2 + j] != key) tileEnd[key] = i + 1;
+	}
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1158,8 +1177,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 			if((d.colorWriteMask >> ch) & 1) wmask32 |= 0xFFu << (8 * ((bgr && ch < 3) ? 2 - ch : ch));
 	}
 
-	// ---- list scan with one block of look-ahead: the headers of the next 32 entries are in flight while this block is used ----
-	uint32_t triN = 0;
+	// ---- list scan with look-ahead: while block b of 32 list entries is used, the record headers of block b + 1 and the list
+	//      entries of block b + 2 are in flight (the header address depends on the list entry) ----
+	uint32_t triN = 0, triNN = 0;
 	uint4 hN = make_uint4(0, 0, 0, 0);
 	{
 		const uint32_t li = begin + lane;
@@ -1168,6 +1188,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 			triN = d.direct ? li : __ldg(triList + li);
 			hN = __ldg((const uint4 *)(d.triRecords + (size_t)triN * d.triStride));
 		}
+		if(li + 32 < end) triNN = d.direct ? li + 32 : __ldg(triList + li + 32);
 	}
 	int ns = 0;             // candidates staged so far for the next batch
 	uint32_t pend = 0;      // lanes whose scanned hit is not staged yet
@@ -1198,9 +1219,10 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 			const uint32_t li = pos + lane;
 			if(li < end)
 			{
-				triN = d.direct ? li : __ldg(triList + li);
+				triN = triNN;
 				hN = __ldg((const uint4 *)(d.triRecords + (size_t)triN * d.triStride));
 			}
+			if(li + 32 < end) triNN = d.direct ? li + 32 : __ldg(triList + li + 32);
 		}
 		if(pend)
 		{
