@@ -264,6 +264,13 @@ def main():
     tile_bytes = wl.tile_bytes / N
     achieved = tile_bytes / (tile_ms * 1e-3) / 1e9 if tile_ms else None
     frame_bytes = wl.algorithmic_bytes if N == 1 else None
+    traffic = None  # DRAM bytes of the dominant kernel per launch, from the committed ncu capture of this workload (if any)
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
+        if N == 1 and wl.name in tj and tj[wl.name]["kernel"] == tile_name:
+            traffic = tj[wl.name]["bytes"]
+    except (OSError, ValueError, KeyError):
+        pass
 
     if rank == 0:
         gpix = wl.covered_pixels / (ms_step * 1e-3) / 1e9
@@ -282,7 +289,7 @@ def main():
             "gpu_launches_note": "kernels of libswcuda.so launched in the timed region (excludes the CUB scan/sort kernels between them)",
             "kernels_ms": kernels,
             "roofline": {"bound": "hbm", "kernel": tile_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": tile_bytes,
                          "frame_algorithmic_bytes": frame_bytes,
                          "frame_achieved": (frame_bytes / (ms_step * 1e-3) / 1e9) if frame_bytes else None,

@@ -6,17 +6,17 @@ import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-hdr = next(r for r in rows if r and r[0] == "Line No")
-ci = {}
-for i, n in enumerate(hdr):
-    ci.setdefault(n, i)
-stalls = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
+hdr, ci, stalls = None, {}, []
 cur = None
 agg = {}
-for r in rows[rows.index(hdr) + 1:]:
-    if len(r) < len(hdr):
+for r in rows:
+    if r and r[0] == "Line No":  # every section of the export has its own header (the column count varies)
+        hdr, ci = r, {}
+        for i, n in enumerate(hdr):
+            ci.setdefault(n, i)
+        stalls = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
         continue
-    if r[0] == "Line No":
+    if hdr is None or len(r) < len(hdr):
         continue
     if r[0]:
         cur = (int(r[0]), r[1].strip())
@@ -28,10 +28,10 @@ for r in rows[rows.index(hdr) + 1:]:
     try:
         a["inst"] += float(r[ci["Instructions Executed"]] or 0)
         a["smp"] += float(r[ci["# Samples"]] or 0)
-        for s in stalls:
-            v = float(r[ci[s]] or 0)
+        for s_ in stalls:
+            v = float(r[ci[s_]] or 0)
             if v:
-                a["st"][s] = a["st"].get(s, 0) + v
+                a["st"][s_] = a["st"].get(s_, 0) + v
     except ValueError:
         pass
 ti = sum(a["inst"] for a in agg.values()) or 1

@@ -106,9 +106,15 @@ def main():
     for p in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
         name = os.path.basename(p)
         md += [f"## `ncu --set full` {name} (the .ncu-rep itself stays in gpurun_out/: too large for the history)", "", raw_metrics(p), ""]
+        wl = name[len("prof_"):-len(".ncu-rep")]
+        srccsv = os.path.join(src, f"source_{wl}.csv")
+        if os.path.exists(srccsv):
+            warps = {"c4": 64800, "c5": 259200}.get(wl, 0)
+            res = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "ncu_phases.py"), srccsv, "k_tile"] + ([str(warps)] if warps else []), capture_output=True, text=True)
+            md += ["Tile kernel by phase (warp instructions, stall samples; SASS rows de-duplicated; profiles/ncu_phases.py):", "", "```", res.stdout.strip(), "```", ""]
         md += ["Hottest CUDA lines of the tile kernel (share of warp instructions / of stall samples, top stall reasons):", "", "```",
-               hot_lines(p, "k_tile", 1).strip(), "```", ""]
-        md += ["Hottest CUDA lines of k_setup:", "", "```", hot_lines(p, "k_setup", 0, 15).strip(), "```", ""]
+               hot_lines(p, "^k_tile$", 0).strip(), "```", ""]
+        md += ["Hottest CUDA lines of k_setup:", "", "```", hot_lines(p, "^k_setup$", 0, 15).strip(), "```", ""]
     open(os.path.join(dst, "SUMMARY.md"), "w").write("\n".join(md))
     print(f"wrote {dst}/SUMMARY.md")
 

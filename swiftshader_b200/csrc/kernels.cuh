@@ -838,10 +838,12 @@ DEVI void sample_texture(const DrawConst &d, const LodState &s, float u, float v
 	else sample_level<FAST>(d, s.ilod, u, v, s.linear, c);
 	if(FAST || d.mipmapMode == MIPMAP_MODE_LINEAR) // sampleFilter :324-373
 	{
-		uint32_t cc[4];
-		sample_level<FAST>(d, s.ilod + 1, u, v, s.linear, cc);
 		const uint32_t utri = (uint32_t)trunc_int(fmul(s.lod, 65536.0f)) & 0xFFFF;
 		const uint32_t inv = ~utri & 0xFFFF;
+		// the reference always fetches level ilod + 1; with a zero weight (magnification, integer LOD) its term mulhi(cc, 0) is 0
+		// whatever the texels are, so the fetch is skipped: c = mulhi(c, 0xFFFF) + 0
+		uint32_t cc[4] = { 0, 0, 0, 0 };
+		if(utri != 0) sample_level<FAST>(d, s.ilod + 1, u, v, s.linear, cc);
 #pragma unroll
 		for(int ch = 0; ch < 4; ch++) c[ch] = (mulhi16(c[ch], inv) + mulhi16(cc[ch], utri)) & 0xFFFF;
 	}
@@ -1260,6 +1262,52 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 			int c1;
 			uint32_t total;
 			bool conflicts = false; // does any sample of the region receive two fragments in this range?
+			if(nb * SWCU_REGION_H * MS <= 32)
+			{
+				// ---- a batch of one (4x) or up to four (1x) candidates — big triangles, direct mode: one (candidate, row, sample)
+				//      per lane, pairs compacted with a ballot, first items from one warp scan ----
+				const int cand = lane / (SWCU_REGION_H * MS), row = (lane / MS) % SWCU_REGION_H, q = lane % MS;
+				uint32_t v = 0;
+				if(cand < nb && (MS == 1 || FS || ((d.sampleMask >> q) & 1)))
+				{
+					const uint4 hh = wHdr[cand];
+					const uint32_t y = (uint32_t)(ry + row);
+					if(y - (hh.z & 0x3FFFu) < ((hh.z >> 14) & 0x3FFFu))
+						v = __ldg((const uint32_t *)(((uintptr_t)hh.y << 32) | hh.x) + y * MS + q);
+				}
+#pragma unroll
+				for(int i = 0; i < (ICAP / 32 + 31) / 32; i++)
+					if(lane + 32 * i < ICAP / 32) wBits[lane + 32 * i] = 0;
+				const int a = clampi((int)(v & 0xFFFF) - rx, 0, 16), e = clampi((int)(v >> 16) - rx, 0, 16);
+				const int n = e - a;
+				const bool has = n > 0;
+				const uint32_t nz = __ballot_sync(0xFFFFFFFFu, has);
+				uint32_t incl = has ? (uint32_t)n : 0u;
+#pragma unroll
+				for(int o = 1; o < 32; o <<= 1)
+				{
+					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+					if(lane >= o) incl += t;
+				}
+				total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+				c1 = nb;
+				if(MS == 1 && nb > 1)
+				{
+					// the other candidates' runs on my row sit 8, 16 and 24 lanes away
+					const uint32_t mask = has ? ((1u << n) - 1u) << a : 0u;
+					const uint32_t others = __shfl_xor_sync(0xFFFFFFFFu, mask, 8) | __shfl_xor_sync(0xFFFFFFFFu, mask, 16) | __shfl_xor_sync(0xFFFFFFFFu, mask, 24);
+					conflicts = __any_sync(0xFFFFFFFFu, (mask & others) != 0);
+				}
+				__syncwarp(); // start marks zeroed
+				if(has)
+				{
+					const uint32_t start = incl - (uint32_t)n;
+					wPairs[__popc(nz & laneLt)] = (start << 18) | ((uint32_t)cand << 13) | ((uint32_t)(row * MS + q) << 8) | ((uint32_t)a << 4) | (uint32_t)(n - 1);
+					atomicOr(wBits + (start >> 5), 1u << (start & 31));
+				}
+				__syncwarp();
+			}
+			else
 			{
 				const int cand = c0 + lane / LPC;
 				const int rowBase = (lane % LPC) * RPL; // first region row of this lane
