@@ -842,8 +842,9 @@ DEVI void sample_texture(const DrawConst &d, const LodState &s, float u, float v
 		const uint32_t inv = ~utri & 0xFFFF;
 		// the reference always fetches level ilod + 1; with a zero weight (magnification, integer LOD) its term mulhi(cc, 0) is 0
 		// whatever the texels are, so the fetch is skipped: c = mulhi(c, 0xFFFF) + 0
+		// (decided per warp, so a mixed warp does not diverge: a fetched level with weight 0 contributes 0 all the same)
 		uint32_t cc[4] = { 0, 0, 0, 0 };
-		if(utri != 0) sample_level<FAST>(d, s.ilod + 1, u, v, s.linear, cc);
+		if(__any_sync(__activemask(), utri != 0)) sample_level<FAST>(d, s.ilod + 1, u, v, s.linear, cc);
 #pragma unroll
 		for(int ch = 0; ch < 4; ch++) c[ch] = (mulhi16(c[ch], inv) + mulhi16(cc[ch], utri)) & 0xFFFF;
 	}
