@@ -181,16 +181,42 @@ def main():
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
+    # N > 1: how the finished bands reach rank 0.  "peer" (default): the end-of-pass resolve (4x) / a band copy (1x) of every
+    # other rank stores straight into rank 0's frame over NVLink (CUDA IPC mapping), ordered by flags — no collective on the
+    # data path.  "nccl": in-place NCCL all-gather of the bands (SWCU_GATHER=nccl).
+    gather = os.environ.get("SWCU_GATHER", "peer") if N > 1 else "none"
     full = None
-    if N > 1:
+    pg = None
+    if gather == "nccl":
         full = torch.as_tensor(_DevArr(frame.final_device_ptr(), H * pitch), device=f"cuda:{local_rank}")
+    elif gather == "peer":
+        pg = bands.PeerGather(dev, frame.final_image(), H, pitch, N, rank)
+        if rank != 0:
+            peer_dst = pg.band_destination(sc.colorFormat, W)
 
-    def step():
+    def step(present=None):
         frame.draw()
+        if pg is not None and rank != 0:
+            pg.begin_frame()  # rank 0 must be done with the previous frame before its rows are overwritten
+            if dst_b is not None:
+                dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(peer_dst)))
+            else:
+                dev.check(dev.lib.swcu_copy_image(dev.ctx, C.byref(src_b), C.byref(peer_dst)))
+            pg.band_done()
+            return
         if dst_b is not None:
             dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(dst_b)))
-        if N > 1:
+        if pg is not None:
+            pg.begin_frame()
+            pg.band_done()  # the stream waits for the other ranks' bands
+            if present is not None:
+                present()
+            pg.frame_consumed()
+            return
+        if gather == "nccl":
             bands.gather_bands(full, H, pitch, N, rank)  # NCCL all-gather, in place: my band is already at its slot
+        if present is not None:
+            present()
 
     def barrier():
         if N > 1:
@@ -224,18 +250,14 @@ def main():
         # ---- end to end through the C-ABI with HOST buffers: H2D of the step's inputs and D2H of the frame inside the timed region ----
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
-            frame.upload_inputs(); step()
-            if rank == 0:
-                frame.download_final()
+            frame.upload_inputs(); step(frame.download_final if rank == 0 else None)
             dev.sync()
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             frame.upload_inputs()
-            step()
-            if rank == 0:
-                frame.download_final()
+            step(frame.download_final if rank == 0 else None)
             dev.sync()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -281,7 +303,8 @@ def main():
             "mtris_per_s": wl.triangles / (ms_step * 1e-3) / 1e6,
             "config": {"workload": wl.name, "description": wl.description, "bands": N, "band_rows": band[1] - band[0],
                        "l2": "inputs larger than L2 (framebuffer + mesh + per-triangle records > 126 MB)" if wl.algorithmic_bytes > 200e6 else "working set fits L2; steady-state frames",
-                       "step": "draw (+ resolve) (+ NCCL all-gather of bands)"},
+                       "step": "draw (+ resolve)" + ("" if N == 1 else " + bands stored into rank 0's frame over NVLink (CUDA IPC) + flags" if gather == "peer" else " + NCCL all-gather of bands"),
+                       "gather": gather},
             "clocks": clock_info,
             "e2e": {"value": wl.covered_pixels / (e2e_ms * 1e-3) / 1e9, "unit": "Gpixels/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
@@ -306,6 +329,8 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "Gpixels/s", "cores": host_threads(), "kind": "reference", "sample": f"unavailable: {e}"}
         print(json.dumps(line), flush=True)
+    if pg is not None:
+        pg.close()
     frame.close()
     dev.close()
     if N > 1:

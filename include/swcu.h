@@ -239,6 +239,20 @@ int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t samples, cons
 /* Blitter::fastResolve (Blitter.cpp:2079-2205): 4x RGBA8 -> 1x, avg(avg(s0,s1),avg(s2,s3)) with (a+b+1)>>1. */
 int swcu_resolve(swcu_ctx *ctx, const swcu_attachment *src, uint32_t samples, const swcu_attachment *dst);
 
+/* ---- multi-GPU: one process per GPU; finished bands reach the presenting GPU by stores over NVLink ----
+ * The presenting rank exports the CUDA IPC handle of its frame's shadow (and of a small flag array), the other ranks open
+ * it, adopt the mapping with swcu_mem_register_device and use addresses inside it as the destination of swcu_resolve /
+ * swcu_copy_image; swcu_signal / swcu_wait_flags order frames between the GPUs (counters that only grow). */
+int swcu_ipc_export(swcu_ctx *ctx, const void *ptr, void *handle64 /* 64 bytes out */, uint64_t *offset /* of ptr inside the exported allocation */);
+int swcu_ipc_open(swcu_ctx *ctx, const void *handle64, void **device_base);
+int swcu_ipc_close(swcu_ctx *ctx, void *device_base);
+/* rows of an RGBA8 image -> another image of the same extent (either side may be adopted peer memory) */
+int swcu_copy_image(swcu_ctx *ctx, const swcu_attachment *src, const swcu_attachment *dst);
+/* *flag = value once everything enqueued before on this context is visible system-wide (flag: registered / adopted memory) */
+int swcu_signal(swcu_ctx *ctx, void *flag, uint32_t value);
+/* the stream waits until flags[first .. first+count) >= value (wrap-around compare), count <= 64 */
+int swcu_wait_flags(swcu_ctx *ctx, const void *flags, uint32_t first, uint32_t count, uint32_t value);
+
 /* ---- narrow SPIR-V translator (host-only, no GPU needed) ---- */
 int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_shader_info *out, char *err, size_t errlen);
 

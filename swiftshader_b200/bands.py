@@ -34,3 +34,89 @@ def gather_bands(full, height: int, pitch_bytes: int, world: int, rank: int):
     mine = full[y0 * pitch_bytes: y1 * pitch_bytes]
     dist.all_gather_into_tensor(full[: height * pitch_bytes], mine)
     return full
+
+
+class PeerGather:
+    """Finished bands reach rank 0's frame by STORES OVER NVLINK, not by a collective: rank 0 exports the CUDA IPC handle of
+    its 1x frame (and of a flag array), every other rank maps it and lets its end-of-pass resolve (4x) or band copy (1x) write
+    straight into that frame; counters that only grow order the frames (flags[r] = "band r of frame f has arrived", written by
+    rank r; flags[0] = "frame f has been consumed", written by rank 0 and polled by the others over NVLink before they
+    overwrite the frame).  torch.distributed only carries the handles at start-up.
+
+    `dev` is a swiftshader_b200.scene.Device, `final_host` the numpy array that keys the 1x frame on this rank."""
+
+    def __init__(self, dev, final_host, height: int, pitch_bytes: int, world: int, rank: int):
+        import ctypes as C
+        import numpy as np
+        import torch.distributed as dist
+        self.dev, self.world, self.rank = dev, world, rank
+        self.height, self.pitch = height, pitch_bytes
+        self.frame_no = 0
+        self.peer_frame = self.peer_flags = None
+        self._opened = []
+        self.flags = np.zeros(64, dtype=np.uint32)  # rank 0's copy is the live one
+        dev.register(self.flags)
+        dev.upload(self.flags)
+        dev.sync()
+        payload = [None]
+        if rank == 0:
+            hs = []
+            for arr in (final_host, self.flags):
+                h = (C.c_ubyte * 64)()
+                off = C.c_uint64(0)
+                dev.check(dev.lib.swcu_ipc_export(dev.ctx, arr.ctypes.data, h, C.byref(off)))
+                hs.append((bytes(h), int(off.value)))
+            payload = [hs]
+        dist.broadcast_object_list(payload, src=0)
+        if rank != 0:
+            (hf, of), (hg, og) = payload[0]
+            self.peer_frame = self._open(hf) + of
+            self.peer_flags = self._open(hg) + og
+            # adopt the mappings so that addresses inside them are accepted as attachments / flags
+            dev.check(dev.lib.swcu_mem_register_device(dev.ctx, self.peer_frame, height * pitch_bytes))
+            dev.check(dev.lib.swcu_mem_register_device(dev.ctx, self.peer_flags, 64 * 4))
+        dist.barrier()
+
+    def _open(self, handle: bytes) -> int:
+        import ctypes as C
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        base = C.c_void_p()
+        self.dev.check(self.dev.lib.swcu_ipc_open(self.dev.ctx, buf, C.byref(base)))
+        self._opened.append(base.value)
+        return base.value
+
+    def band_destination(self, fmt: int, width: int):
+        """Attachment describing my band inside rank 0's frame (ranks > 0)."""
+        from . import capi
+        y0, y1 = band_rows(self.height, self.world, self.rank)
+        return capi.Attachment(self.peer_frame + y0 * self.pitch, fmt, self.pitch, 0, width, y1 - y0, 0)
+
+    def begin_frame(self):
+        """Before this rank overwrites its band of rank 0's frame: the previous frame must have been consumed."""
+        self.frame_no += 1
+        if self.rank != 0 and self.frame_no > 1:
+            self.dev.check(self.dev.lib.swcu_wait_flags(self.dev.ctx, self.peer_flags, 0, 1, self.frame_no - 1))
+
+    def band_done(self):
+        """After the band's resolve / copy has been enqueued: announce it (ranks > 0), or wait for all bands (rank 0)."""
+        if self.rank != 0:
+            self.dev.check(self.dev.lib.swcu_signal(self.dev.ctx, self.peer_flags + 4 * self.rank, self.frame_no))
+        else:
+            self.dev.check(self.dev.lib.swcu_wait_flags(self.dev.ctx, self.flags.ctypes.data, 1, self.world - 1, self.frame_no))
+
+    def frame_consumed(self):
+        """Rank 0, once whoever presents the frame is done with it (enqueued on the same stream)."""
+        if self.rank == 0:
+            self.dev.check(self.dev.lib.swcu_signal(self.dev.ctx, self.flags.ctypes.data, self.frame_no))
+
+    def close(self):
+        import torch.distributed as dist
+        self.dev.sync()
+        dist.barrier()
+        if self.rank != 0:
+            self.dev.check(self.dev.lib.swcu_mem_unregister(self.dev.ctx, self.peer_frame))
+            self.dev.check(self.dev.lib.swcu_mem_unregister(self.dev.ctx, self.peer_flags))
+            for b in self._opened:
+                self.dev.lib.swcu_ipc_close(self.dev.ctx, b)
+        self.dev.unregister(self.flags)
+        dist.barrier()

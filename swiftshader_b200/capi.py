@@ -102,6 +102,7 @@ EXPORTS = [
     "swcu_draw", "swcu_sync", "swcu_clear", "swcu_resolve", "swcu_shader_translate",
     "swcu_set_stream", "swcu_timer_begin", "swcu_timer_end", "swcu_get_stats", "swcu_reset_stats",
     "swcu_set_profiling", "swcu_last_draw_kernels", "swcu_set_option", "swcu_version",
+    "swcu_ipc_export", "swcu_ipc_open", "swcu_ipc_close", "swcu_copy_image", "swcu_signal", "swcu_wait_flags",
 ]
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -144,6 +145,12 @@ def lib() -> C.CDLL:
     L.swcu_set_profiling.argtypes = [vp, i32]
     L.swcu_last_draw_kernels.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]
     L.swcu_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.swcu_ipc_export.argtypes = [vp, vp, vp, C.POINTER(C.c_uint64)]
+    L.swcu_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.swcu_ipc_close.argtypes = [vp, vp]
+    L.swcu_copy_image.argtypes = [vp, C.POINTER(Attachment), C.POINTER(Attachment)]
+    L.swcu_signal.argtypes = [vp, vp, u32]
+    L.swcu_wait_flags.argtypes = [vp, vp, u32, u32, u32]
     L.swcu_version.argtypes = []
     L.swcu_version.restype = C.c_char_p
     for name in EXPORTS:

@@ -903,6 +903,83 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// multi-GPU plumbing: CUDA IPC handles of shadows, band copies into peer memory, flags
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int swcu_ipc_export(swcu_ctx *ctx, const void *ptr, void *handle64, uint64_t *offset)
+{
+	if(!ctx || !ptr || !handle64 || !offset) return fail(ctx, SWCU_E_INVALID, "swcu_ipc_export: null argument");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+	Shadow *s = find_shadow(ctx, ptr, 1);
+	if(!s || s->external) return fail(ctx, SWCU_E_INVALID, "swcu_ipc_export: %p is not inside a shadow owned by this context", ptr);
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, s->dev));
+	*offset = (uint64_t)((uintptr_t)ptr - s->host);
+	return SWCU_OK;
+}
+
+extern "C" int swcu_ipc_open(swcu_ctx *ctx, const void *handle64, void **device_base)
+{
+	if(!ctx || !handle64 || !device_base) return fail(ctx, SWCU_E_INVALID, "swcu_ipc_open: null argument");
+	CU(cudaSetDevice(ctx->device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, sizeof(h));
+	CU(cudaIpcOpenMemHandle(device_base, h, cudaIpcMemLazyEnablePeerAccess));
+	return SWCU_OK;
+}
+
+extern "C" int swcu_ipc_close(swcu_ctx *ctx, void *device_base)
+{
+	if(!ctx || !device_base) return SWCU_E_INVALID;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaIpcCloseMemHandle(device_base));
+	return SWCU_OK;
+}
+
+extern "C" int swcu_copy_image(swcu_ctx *ctx, const swcu_attachment *src, const swcu_attachment *dst)
+{
+	if(!ctx || !src || !dst || !src->buffer || !dst->buffer) return fail(ctx, SWCU_E_INVALID, "swcu_copy_image: null argument");
+	if(src->format != dst->format || (src->format != VKF_R8G8B8A8_UNORM && src->format != VKF_B8G8R8A8_UNORM)) return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_copy_image: format unsupported");
+	if(src->width != dst->width || src->height != dst->height) return fail(ctx, SWCU_E_INVALID, "swcu_copy_image: extent mismatch");
+	CU(cudaSetDevice(ctx->device));
+	const size_t rowB = (size_t)src->width * 4;
+	unsigned char *s = dev_ptr(ctx, src->buffer, (size_t)(src->height - 1) * src->pitchB + rowB);
+	unsigned char *t = dev_ptr(ctx, dst->buffer, (size_t)(dst->height - 1) * dst->pitchB + rowB);
+	if(!s || !t) return fail(ctx, SWCU_E_INVALID, "swcu_copy_image: image is not inside a registered range");
+	const int vec = ((uintptr_t)s % 16 == 0) && ((uintptr_t)t % 16 == 0) && (src->pitchB % 16 == 0) && (dst->pitchB % 16 == 0) && (rowB % 16 == 0);
+	const int per = vec ? 16 : 4;
+	LaunchScope ls(ctx, "k_copy_rows");
+	k_copy_rows<<<dim3((unsigned)((rowB / per + 255) / 256), src->height), 256, 0, ctx->stream>>>(s, src->pitchB, t, dst->pitchB, (int)rowB, (int)src->height, vec);
+	CU(cudaGetLastError());
+	return SWCU_OK;
+}
+
+extern "C" int swcu_signal(swcu_ctx *ctx, void *flag, uint32_t value)
+{
+	if(!ctx || !flag) return fail(ctx, SWCU_E_INVALID, "swcu_signal: null argument");
+	CU(cudaSetDevice(ctx->device));
+	unsigned char *f = dev_ptr(ctx, flag, 4);
+	if(!f) return fail(ctx, SWCU_E_INVALID, "swcu_signal: flag is not inside a registered range");
+	LaunchScope ls(ctx, "k_signal");
+	k_signal<<<1, 1, 0, ctx->stream>>>((uint32_t *)f, value);
+	CU(cudaGetLastError());
+	return SWCU_OK;
+}
+
+extern "C" int swcu_wait_flags(swcu_ctx *ctx, const void *flags, uint32_t first, uint32_t count, uint32_t value)
+{
+	if(!ctx || !flags || count > 64) return fail(ctx, SWCU_E_INVALID, "swcu_wait_flags: bad argument");
+	if(count == 0) return SWCU_OK;
+	CU(cudaSetDevice(ctx->device));
+	unsigned char *f = dev_ptr(ctx, flags, (size_t)(first + count) * 4);
+	if(!f) return fail(ctx, SWCU_E_INVALID, "swcu_wait_flags: flags are not inside a registered range");
+	LaunchScope ls(ctx, "k_wait_flags");
+	k_wait_flags<<<1, 64, 0, ctx->stream>>>((const uint32_t *)f, (int)first, (int)count, value);
+	CU(cudaGetLastError());
+	return SWCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // clear / resolve on the resident shadows
 // ------------------------------------------------------------------------------------------------------------------
 extern "C" int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t samples, const swcu_rect *area, const void *value)

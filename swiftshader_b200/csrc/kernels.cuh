@@ -1680,3 +1680,42 @@ __global__ void k_resolve4(const unsigned char *src, int srcPitchB, int srcSlice
 	const uint32_t s2 = *(const uint32_t *)(src + o + 2 * (size_t)srcSliceB), s3 = *(const uint32_t *)(src + o + 3 * (size_t)srcSliceB);
 	*(uint32_t *)(dst + (size_t)y * dstPitchB + 4 * (size_t)x) = pavgb4(pavgb4(s0, s1), pavgb4(s2, s3));
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// multi-GPU: finished bands go to the presenting GPU by stores over NVLink into its (IPC-mapped) frame, not by a collective
+// ------------------------------------------------------------------------------------------------------------------
+// rows of a 4-byte-per-pixel image -> another image (the destination may be peer memory); 16 bytes per thread when aligned
+__global__ void k_copy_rows(const unsigned char *src, int srcPitchB, unsigned char *dst, int dstPitchB, int rowBytes, int h, int vec)
+{
+	const int y = blockIdx.y;
+	if(y >= h) return;
+	const unsigned char *s = src + (size_t)y * srcPitchB;
+	unsigned char *t = dst + (size_t)y * dstPitchB;
+	if(vec)
+	{
+		const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+		if(i < rowBytes) *(uint4 *)(t + i) = *(const uint4 *)(s + i);
+	}
+	else
+	{
+		const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+		if(i < rowBytes) *(uint32_t *)(t + i) = *(const uint32_t *)(s + i);
+	}
+}
+
+// flag <- value, after everything this stream wrote before (the kernels ahead of this one) is visible system-wide
+__global__ void k_signal(uint32_t *flag, uint32_t value)
+{
+	__threadfence_system();
+	*(volatile uint32_t *)flag = value;
+}
+
+// spin until flags[first .. first + count) have all reached `value` (they only grow), then make the data they announce visible
+__global__ void k_wait_flags(const uint32_t *flags, int first, int count, uint32_t value)
+{
+	const int i = threadIdx.x;
+	if(i < count)
+		while((int32_t)(*(volatile const uint32_t *)(flags + first + i) - value) < 0) __nanosleep(100);
+	__syncthreads();
+	__threadfence_system();
+}

@@ -30,25 +30,58 @@ def main():
     stream = torch.cuda.Stream()
     dev.set_stream(stream.cuda_stream)
     bad = 0
+    import ctypes as C
+    from swiftshader_b200 import capi
     for name in ("c4", "c5", "c2"):
         sc = workloads.small(name).scene
         H, W = sc.height, sc.width
         if H % (2 * world):
             continue
-        fr = Frame(dev, sc, render_area=bands.render_area(W, H, world, rank))
-        with torch.cuda.stream(stream):
-            fr.upload_inputs(); fr.clear(); fr.draw(); fr.resolve()
-            full = torch.as_tensor(_DevArr(fr.final_device_ptr(), H * W * 4), device=f"cuda:{local}")
-            bands.gather_bands(full, H, W * 4, world, rank)
-            torch.cuda.synchronize()
-            got = full.cpu().numpy().reshape(H, W, 4)
-        fr.close()
-        if rank == 0:
-            want = swref.render_oracle(sc)
-            ref = swref.resolve_oracle(sc, want) if sc.samples > 1 else want["color"][0]
-            ok = np.array_equal(got, ref[:H])
-            print(f"multi_gpu_check {name} world={world}: {'ok' if ok else 'MISMATCH'}", flush=True)
-            bad += 0 if ok else 1
+        for mode in ("nccl", "peer"):
+            fr = Frame(dev, sc, render_area=bands.render_area(W, H, world, rank))
+            y0, y1 = bands.band_rows(H, world, rank)
+            pitch = W * 4
+            with torch.cuda.stream(stream):
+                fr.upload_inputs(); fr.clear()
+                if mode == "nccl":
+                    fr.draw(); fr.resolve()
+                    full = torch.as_tensor(_DevArr(fr.final_device_ptr(), H * W * 4), device=f"cuda:{local}")
+                    bands.gather_bands(full, H, W * 4, world, rank)
+                    torch.cuda.synchronize()
+                    got = full.cpu().numpy().reshape(H, W, 4)
+                else:
+                    # two frames, so the "previous frame consumed" handshake is exercised as well
+                    pg = bands.PeerGather(dev, fr.final_image(), H, pitch, world, rank)
+                    H2 = sc.padded_height()
+                    for _ in range(2):
+                        if sc.samples > 1:
+                            fr.clear()  # the blended 4x scene is not idempotent; its 4x attachments are private to the rank
+                        fr.draw()
+                        pg.begin_frame()
+                        if rank == 0:
+                            fr.resolve()
+                            pg.band_done()
+                            fr.download_final()
+                            pg.frame_consumed()
+                        else:
+                            dst = pg.band_destination(sc.colorFormat, W)
+                            src = capi.Attachment(fr.att["color"].ctypes.data + y0 * pitch, sc.colorFormat, pitch, H2 * pitch, W, y1 - y0, 0)
+                            if sc.samples > 1:
+                                dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src), sc.samples, C.byref(dst)))
+                            else:
+                                dev.check(dev.lib.swcu_copy_image(dev.ctx, C.byref(src), C.byref(dst)))
+                            pg.band_done()
+                    dev.sync()
+                    torch.cuda.synchronize()
+                    got = fr.final_image()[:H].copy()
+                    pg.close()
+            fr.close()
+            if rank == 0:
+                want = swref.render_oracle(sc)
+                ref = swref.resolve_oracle(sc, want) if sc.samples > 1 else want["color"][0]
+                ok = np.array_equal(got, ref[:H])
+                print(f"multi_gpu_check {name} world={world} gather={mode}: {'ok' if ok else 'MISMATCH'}", flush=True)
+                bad += 0 if ok else 1
     dev.close()
     dist.destroy_process_group()
     sys.exit(1 if bad else 0)
