@@ -59,7 +59,10 @@ def main():
                         fr.draw()
                         pg.begin_frame()
                         if rank == 0:
-                            fr.resolve()
+                            if sc.samples > 1:  # only MY band: the other rows of the frame belong to the other ranks' stores
+                                src = capi.Attachment(fr.att["color"].ctypes.data + y0 * pitch, sc.colorFormat, pitch, H2 * pitch, W, y1 - y0, 0)
+                                dst = capi.Attachment(fr.resolved.ctypes.data + y0 * pitch, sc.colorFormat, pitch, H2 * pitch, W, y1 - y0, 0)
+                                dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src), sc.samples, C.byref(dst)))
                             pg.band_done()
                             fr.download_final()
                             pg.frame_consumed()
