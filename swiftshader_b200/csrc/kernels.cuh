@@ -311,6 +311,17 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 			for(int a = 0; a < 3; a++)
 #pragma unroll
 				for(int c = 0; c < 4; c++) pos[a][c] = vs_operand(d, d.vsPos[c], idx[a]);
+			// Early band / scissor reject on an approximate projected y (fast reciprocal, 4-pixel margin): with all three w > 0 the
+			// clipped polygon stays inside the hull of the projected vertices, so a triangle whose hull misses the scissor rows
+			// cannot produce a span.  This is what a rank of a multi-GPU frame pays for a triangle outside its band.
+			if(pos[0][3] > 0.0f && pos[1][3] > 0.0f && pos[2][3] > 0.0f)
+			{
+				const float y0a = __fmaf_rn(__fdividef(pos[0][1], pos[0][3]), d.HxF, d.Y0xF);
+				const float y1a = __fmaf_rn(__fdividef(pos[1][1], pos[1][3]), d.HxF, d.Y0xF);
+				const float y2a = __fmaf_rn(__fdividef(pos[2][1], pos[2][3]), d.HxF, d.Y0xF);
+				const float ylo = fminf(fminf(y0a, y1a), y2a), yhi = fmaxf(fmaxf(y0a, y1a), y2a);
+				if(yhi + 1024.0f < (float)(d.scY0 << 8) || ylo - 1024.0f > (float)(d.scY1 << 8)) break;
+			}
 			process_vertex(d, pos[0][0], pos[0][1], pos[0][2], pos[0][3], va);
 			process_vertex(d, pos[1][0], pos[1][1], pos[1][2], pos[1][3], vb);
 			process_vertex(d, pos[2][0], pos[2][1], pos[2][2], pos[2][3], vc);
