@@ -10,7 +10,7 @@ MARKERS = [  # (phase, substring of the first line of the phase), in file order
     ("sampler", "DEVI uint32_t mulhi16"),
     ("pixhelp", "DEVI bool stencil_compare"),
     ("tile-prolog", "FS (\"fast state\")"),
-    ("scan", "list scan with one block of look-ahead"),
+    ("scan", "list scan with look-ahead"),
     ("admit", "hits join the batch in list order"),
     ("planes-stage", "plane equations of the batch -> shared memory"),
     ("coverage-L", "coverage (QuadRasterizer.cpp:181-206), one candidate per lane"),

@@ -44,6 +44,7 @@ struct swcu_ctx
 	cudaStream_t stream = nullptr, ownStream = nullptr;
 	std::map<uintptr_t, Shadow> mem;
 	std::string err;
+	DevBuf cullFlags;
 	DevBuf triRecords, spans, bigList, tileCount, pairOffset, keys, vals, keys2, vals2, tileBegin, tileEnd, cubTemp, counters, zeroPage;
 	DrawCounters *hostCounters = nullptr; // pinned
 	swcu_stats stats{};
@@ -139,7 +140,7 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 		if(!kv.second.external) cudaFree(kv.second.dev);
 	}
 	DevBuf *bufs[] = { &ctx->triRecords, &ctx->spans, &ctx->bigList, &ctx->tileCount, &ctx->pairOffset, &ctx->keys, &ctx->vals,
-		               &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->counters, &ctx->zeroPage };
+		               &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->counters, &ctx->zeroPage, &ctx->cullFlags };
 	for(DevBuf *b : bufs) cudaFree(b->p);
 	for(cudaEvent_t ev : ctx->eventPool) cudaEventDestroy(ev);
 	if(ctx->hostCounters) cudaFreeHost(ctx->hostCounters);
@@ -810,6 +811,17 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		d.bigList = (BigTri *)ctx->bigList.p;
 		d.bigCapacity = (uint32_t)std::min<size_t>(ctx->bigList.cap / sizeof(BigTri), 0x7FFFFFFFu);
 		CU(cudaMemsetAsync(d.counters, 0, sizeof(DrawCounters), ctx->stream));
+		// band mode: the scissor / render area keeps less than 3/4 of the framebuffer rows (a rank of a multi-GPU frame)
+		d.cullFlags = nullptr;
+		if(!d.direct && attempt == 0 && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
+		{
+			if((rc = ensure(ctx, ctx->cullFlags, n))) return rc;
+			LaunchScope ls(ctx, "k_cull");
+			k_cull<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d, (unsigned char *)ctx->cullFlags.p);
+			d.cullFlags = (const unsigned char *)ctx->cullFlags.p;
+		}
+		else if(!d.direct && attempt > 0 && ctx->cullFlags.p && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
+			d.cullFlags = (const unsigned char *)ctx->cullFlags.p; // flags of the first attempt are still valid
 		{
 			LaunchScope ls(ctx, "k_setup");
 			k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4, ctx->stream>>>(d);

@@ -278,6 +278,38 @@ DEVI unsigned long long warp_alloc(unsigned long long *cursor, uint32_t count)
 	return base + (incl - count);
 }
 
+// Approximate band / scissor-row reject shared by k_cull and k_setup: projected y with a fast reciprocal and a 4-pixel margin.
+// With all three w > 0 the clipped polygon stays inside the hull of the projected vertices, so a triangle whose hull misses
+// the scissor rows cannot produce a span.  Returns true if the triangle is certainly invisible.
+DEVI bool rows_missed(const DrawConst &d, float y0, float w0, float y1, float w1, float y2, float w2)
+{
+	if(!(w0 > 0.0f && w1 > 0.0f && w2 > 0.0f)) return false;
+	const float y0a = __fmaf_rn(__fdividef(y0, w0), d.HxF, d.Y0xF);
+	const float y1a = __fmaf_rn(__fdividef(y1, w1), d.HxF, d.Y0xF);
+	const float y2a = __fmaf_rn(__fdividef(y2, w2), d.HxF, d.Y0xF);
+	const float ylo = fminf(fminf(y0a, y1a), y2a), yhi = fmaxf(fmaxf(y0a, y1a), y2a);
+	return yhi + 1024.0f < (float)(d.scY0 << 8) || ylo - 1024.0f > (float)(d.scY1 << 8);
+}
+
+// Band mode (the render area covers only part of the framebuffer rows — a rank of a multi-GPU frame): a light first pass,
+// one thread per triangle at full occupancy, that only fetches y and w of the three vertices and marks the triangles whose
+// rows miss the band; k_setup then drops them on one coalesced byte load instead of a dependent index -> vertex fetch chain.
+__global__ void __launch_bounds__(256) k_cull(const __grid_constant__ DrawConst d, unsigned char *flags)
+{
+	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+	if(tri >= d.primCount) return;
+	uint32_t idx[3];
+	triangle_indices(d, tri, idx);
+	float y[3], w[3];
+#pragma unroll
+	for(int a = 0; a < 3; a++)
+	{
+		y[a] = vs_operand(d, d.vsPos[1], idx[a]);
+		w[a] = vs_operand(d, d.vsPos[3], idx[a]);
+	}
+	flags[tri] = rows_missed(d, y[0], w[0], y[1], w[1], y[2], w[2]) ? 0 : 1;
+}
+
 DEVI int sel3(int i, int a0, int a1, int a2) { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
 DEVI float sel3(int i, float a0, float a1, float a2) { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
 
@@ -292,6 +324,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 	uint32_t nTiles = 0;
 	bool visible = false;
 	uint32_t idx[3] = { 0, 0, 0 };
+	const bool precull = live && d.cullFlags != nullptr && d.cullFlags[tri] == 0; // marked by k_cull: rows outside the band
 	VOut va, vb, vc;
 	float sv[3][SWCU_MAXSLOTS]; // slot sources at the three vertices
 	int PX[SWCU_POLY_MAX], PY[SWCU_POLY_MAX]; // clipped polygons only
@@ -299,7 +332,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 	bool clipped = false;
 	bool frontFacing = false;
 	int yMin = 0, yMax = 0, pxMin = 0, pxMax = 0;
-	if(live)
+	if(live && !precull)
 	{
 		do
 		{
@@ -314,14 +347,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 			// Early band / scissor reject on an approximate projected y (fast reciprocal, 4-pixel margin): with all three w > 0 the
 			// clipped polygon stays inside the hull of the projected vertices, so a triangle whose hull misses the scissor rows
 			// cannot produce a span.  This is what a rank of a multi-GPU frame pays for a triangle outside its band.
-			if(pos[0][3] > 0.0f && pos[1][3] > 0.0f && pos[2][3] > 0.0f)
-			{
-				const float y0a = __fmaf_rn(__fdividef(pos[0][1], pos[0][3]), d.HxF, d.Y0xF);
-				const float y1a = __fmaf_rn(__fdividef(pos[1][1], pos[1][3]), d.HxF, d.Y0xF);
-				const float y2a = __fmaf_rn(__fdividef(pos[2][1], pos[2][3]), d.HxF, d.Y0xF);
-				const float ylo = fminf(fminf(y0a, y1a), y2a), yhi = fmaxf(fmaxf(y0a, y1a), y2a);
-				if(yhi + 1024.0f < (float)(d.scY0 << 8) || ylo - 1024.0f > (float)(d.scY1 << 8)) break;
-			}
+			if(rows_missed(d, pos[0][1], pos[0][3], pos[1][1], pos[1][3], pos[2][1], pos[2][3])) break;
 			process_vertex(d, pos[0][0], pos[0][1], pos[0][2], pos[0][3], va);
 			process_vertex(d, pos[1][0], pos[1][1], pos[1][2], pos[1][3], vb);
 			process_vertex(d, pos[2][0], pos[2][1], pos[2][2], pos[2][3], vc);
@@ -408,7 +434,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 	if(big && slot >= d.bigCapacity) { atomicOr(&d.counters->overflow, 2u); visible = false; }
 	if(!visible)
 	{
-		*(uint4 *)rec = make_uint4(0, 0, 0, 0); // empty bounds: never a candidate
+		// empty bounds: never a candidate.  Only the direct mode reads the header of an invisible triangle (every tile CTA walks
+		// the whole list); a binned draw never puts it in a tile list, so the 32-byte sector is not written at all.
+		if(d.direct) *(uint4 *)rec = make_uint4(0, 0, 0, 0);
 		d.tileCount[tri] = TILE_RECT_NONE;
 		return;
 	}
