@@ -893,7 +893,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	if(d.direct)
 	{
 		LaunchScope ls(ctx, "k_big");
-		k_big<<<dim3(std::min<uint32_t>(n, 64u), 1), 256, 0, ctx->stream>>>(d, nullptr, nullptr, nullptr);
+		k_big<<<dim3(std::min<uint32_t>(n, 64u), n <= 4 ? 16 : (n <= 16 ? 4 : 1)), 256, 0, ctx->stream>>>(d, nullptr, nullptr, nullptr);
 	}
 	// ---- tensor maps of the attachments the tile kernel stages ----
 	TileMaps maps;

@@ -631,10 +631,10 @@ __global__ void __launch_bounds__(256) k_big(const __grid_constant__ DrawConst d
 		const BigTri &b = d.bigList[e];
 		const int n = b.n, dir = b.dir;
 		const bool msaa = d.ms > 1;
-		if(blockIdx.y == 0)
 		{
+			// (row, sample) entries strided over the y-slices of the grid as well: a full-screen triangle gets one row per thread
 			const int total = (b.yMax - b.yMin) * d.ms;
-			for(int r = threadIdx.x; r < total; r += blockDim.x)
+			for(int r = blockIdx.y * blockDim.x + threadIdx.x; r < total; r += blockDim.x * gridDim.y)
 			{
 				const int y = b.yMin + r / d.ms, q = r % d.ms;
 				const int ox = msaa ? c_Xf[q] : 0, oy = msaa ? c_Yf[q] : 0;
