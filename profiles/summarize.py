@@ -114,7 +114,7 @@ def main():
             md += ["Tile kernel by phase (warp instructions, stall samples; SASS rows de-duplicated; profiles/ncu_phases.py):", "", "```", res.stdout.strip(), "```", ""]
         md += ["Hottest CUDA lines of the tile kernel (share of warp instructions / of stall samples, top stall reasons):", "", "```",
                hot_lines(p, "^k_tile$", 0).strip(), "```", ""]
-        md += ["Hottest CUDA lines of k_setup:", "", "```", hot_lines(p, "^k_setup$", 0, 15).strip(), "```", ""]
+        md += ["Hottest CUDA lines of k_setup:", "", "```", hot_lines(p, "^k_setup(_1x)?$", 0, 15).strip(), "```", ""]
     open(os.path.join(dst, "SUMMARY.md"), "w").write("\n".join(md))
     print(f"wrote {dst}/SUMMARY.md")
 

@@ -25,7 +25,7 @@ EOF
 done
 if [ -z "$NOPROF" ]; then
   W1=$(echo $WLS | cut -d' ' -f1)
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'^(k_tile|k_setup)$' -s 4 -c 2 -f -o "$OUT/prof_$W1" \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'^(k_tile|k_setup|k_setup_1x)$' -s 4 -c 2 -f -o "$OUT/prof_$W1" \
     python bench.py --workload $W1 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1
   ncu -i "$OUT/prof_$W1.ncu-rep" --page source --print-source cuda,sass --csv > "$OUT/source_$W1.csv" 2>/dev/null
   ncu -i "$OUT/prof_$W1.ncu-rep" --page raw --csv > "$OUT/raw_$W1.csv" 2>/dev/null

@@ -23,12 +23,12 @@ fi
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_c4.csv" \
   python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_launch.log" 2>&1
 # full capture of the tile kernel and of setup (2 launches each, after warm-up)
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'^(k_tile|k_setup)$' -s 4 -c 2 -f -o "$OUT/prof_c4" \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'^(k_tile|k_setup|k_setup_1x)$' -s 4 -c 2 -f -o "$OUT/prof_c4" \
   python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1
 ncu -i "$OUT/prof_c4.ncu-rep" --page source --print-source cuda,sass --csv > "$OUT/source_c4.csv" 2>/dev/null
 ncu -i "$OUT/prof_c4.ncu-rep" --page raw --csv > "$OUT/raw_c4.csv" 2>/dev/null
 if [ "$MODE" != "quick" ]; then
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'^(k_tile|k_setup)$' -s 4 -c 2 -f -o "$OUT/prof_c5" \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'^(k_tile|k_setup|k_setup_1x)$' -s 4 -c 2 -f -o "$OUT/prof_c5" \
   python bench.py --workload c5 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_full_c5.log" 2>&1
 ncu -i "$OUT/prof_c5.ncu-rep" --page source --print-source cuda,sass --csv > "$OUT/source_c5.csv" 2>/dev/null
 ncu -i "$OUT/prof_c5.ncu-rep" --page raw --csv > "$OUT/raw_c5.csv" 2>/dev/null

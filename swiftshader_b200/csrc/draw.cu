@@ -824,7 +824,9 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 			d.cullFlags = (const unsigned char *)ctx->cullFlags.p; // flags of the first attempt are still valid
 		{
 			LaunchScope ls(ctx, "k_setup");
-			k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4, ctx->stream>>>(d);
+			const size_t scratch = (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4;
+			if(d.ms != 1) k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ctx->stream>>>(d);
+			else k_setup_1x<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ctx->stream>>>(d);
 		}
 		if(d.direct) break;
 

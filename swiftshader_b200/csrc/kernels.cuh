@@ -187,6 +187,9 @@ __device__ __noinline__ int clip_polygon(float4 *P, int n, int flagsOr)
 // not change), and the divisions are done as a float estimate fixed up with the exact integer remainder — the result is
 // the exact quotient for every int32 input (the fix-up loops run 0 or 1 times for screen-sized operands).
 #define SETUP_THREADS 128
+#ifndef SETUP_BLOCKS_1X
+#define SETUP_BLOCKS_1X 7 // resident CTAs per SM asked of the 1x instantiation of k_setup (register cap 72)
+#endif
 DEVI int floor_div(int n, int d, int &rem) // d > 0; returns floor(n / d), rem = n - q*d in [0, d)
 {
 	int q = __float2int_rd(__fdividef((float)n, (float)d));
@@ -315,12 +318,16 @@ DEVI float sel3(int i, float a0, float a1, float a2) { return i == 0 ? a0 : (i =
 
 // The unclipped triangle lives in registers only (three named vertices, selects instead of indexed arrays); the clipped
 // polygon — rare — goes through local-memory arrays.
-__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ DrawConst d)
+// MSC = 1: the 1x instantiation (sample count folded, 7 CTAs / SM); MSC = 0: sample count read at run time (used for 4x — measured
+// faster than a folded 4x instantiation, whose natural register allocation costs a resident CTA)
+template<int MSC>
+DEVI void setup_triangle(const DrawConst &d)
 {
 	extern __shared__ uint32_t s_rows[]; // [SWCU_SMALL_ROWS * ms][SETUP_THREADS]: one scratch column of span rows per thread
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x; // grid is padded to whole warps; inactive lanes just allocate 0
 	const bool live = tri < d.primCount;
-	const bool msaa = d.ms > 1;
+	const int MS = MSC ? MSC : d.ms;
+	const bool msaa = MS > 1;
 	uint32_t nTiles = 0;
 	bool visible = false;
 	uint32_t idx[3] = { 0, 0, 0 };
@@ -419,7 +426,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 		big = rows > SWCU_SMALL_ROWS || nTiles > SWCU_SMALL_TILES;
 		tileRect = big ? (TILE_RECT_BIG | nTiles) : ((uint32_t)tx0 | ((uint32_t)ty0 << 9) | ((uint32_t)(tx1 - tx0) << 19) | ((uint32_t)(ty1 - ty0) << 22));
 	}
-	const uint32_t count = big ? (uint32_t)(rows * d.ms) : 0u;
+	const uint32_t count = big ? (uint32_t)(rows * MS) : 0u;
 	unsigned long long base = 0, slot = 0;
 	if(__any_sync(0xFFFFFFFFu, big))
 	{
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 		uint32_t *col = s_rows + threadIdx.x;
 		// every row of the record is written (rows outside the triangle as empty spans): whole 32-byte sectors reach L2, so
 		// evicting them needs no fill from DRAM.  Empty = {0, 0}, also the MSAA pre-fill (SetupRoutine.cpp:214-225)
-		for(int i = 0; i < SWCU_SMALL_ROWS * d.ms; i++) col[i * SETUP_THREADS] = 0;
+		for(int i = 0; i < SWCU_SMALL_ROWS * MS; i++) col[i * SETUP_THREADS] = 0;
 		if(clipped) { PX[n] = PX[0]; PY[n] = PY[0]; }
 		for(int i = 0; i < n; i++)
 		{
@@ -479,13 +486,14 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 				Xe = sel3(i, vb.X, vc.X, va.X); Ye = sel3(i, vb.Y, vc.Y, va.Y);
 			}
 			const int Xa = dir ? Xs : Xe, Ya = dir ? Ys : Ye, Xb = dir ? Xe : Xs, Yb = dir ? Ye : Ys;
-			if(msaa) edge_small<4>(d, col, yMin, Xa, Ya, Xb, Yb);
+			if(MSC == 1) edge_small<1>(d, col, yMin, Xa, Ya, Xb, Yb);
+			else if(msaa) edge_small<4>(d, col, yMin, Xa, Ya, Xb, Yb);
 			else edge_small<1>(d, col, yMin, Xa, Ya, Xb, Yb);
 		}
-		uint32_t *out = (uint32_t *)(rec + d.triStride) - SWCU_SMALL_ROWS * d.ms;
+		uint32_t *out = (uint32_t *)(rec + d.triStride) - SWCU_SMALL_ROWS * MS;
 #pragma unroll
 		for(int r = 0; r < SWCU_SMALL_ROWS; r++)
-			if(r < 2 * d.ms)
+			if(r < 2 * MS)
 				((uint4 *)out)[r] = make_uint4(col[(4 * r) * SETUP_THREADS], col[(4 * r + 1) * SETUP_THREADS], col[(4 * r + 2) * SETUP_THREADS], col[(4 * r + 3) * SETUP_THREADS]);
 	}
 
@@ -619,6 +627,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 	hdr.w = (frontFacing ? 1u : 0u) | (big ? 2u : 0u);
 	*(uint4 *)rec = hdr;
 }
+
+__global__ void __launch_bounds__(SETUP_THREADS, SETUP_BLOCKS_1X) k_setup_1x(const __grid_constant__ DrawConst d) { setup_triangle<1>(d); }
+__global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ DrawConst d) { setup_triangle<0>(d); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // k_big: spans (and tile pairs) of the large triangles
