@@ -194,8 +194,18 @@ def main():
     if gather == "nccl":
         full = torch.as_tensor(_DevArr(frame.final_device_ptr(), H * pitch), device=f"cuda:{local_rank}")
     elif gather == "peer":
-        pg = bands.PeerGather(dev, frame.final_image(), H, pitch, N, rank)
-        if rank != 0:
+        try:
+            pg = bands.PeerGather(dev, frame.final_image(), H, pitch, N, rank)
+            ok = 1
+        except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC not permitted in this container)
+            print(f"[bench] rank {rank}: peer delivery unavailable ({e}); falling back to the NCCL all-gather", file=sys.stderr)
+            pg, ok = None, 0
+        t_ok = torch.tensor([ok], device=f"cuda:{local_rank}")
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            pg, gather = None, "nccl"
+            full = torch.as_tensor(_DevArr(frame.final_device_ptr(), H * pitch), device=f"cuda:{local_rank}")
+        elif rank != 0:
             peer_dst = pg.band_destination(sc.colorFormat, W)
 
     def step(present=None):
