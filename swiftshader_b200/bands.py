@@ -58,23 +58,39 @@ class PeerGather:
         dev.register(self.flags)
         dev.upload(self.flags)
         dev.sync()
+        # Every step that can fail (CUDA IPC may be unavailable) is agreed on by all ranks before anyone waits for anyone:
+        # a failure raises on every rank instead of leaving the others in a collective.
         payload = [None]
         if rank == 0:
-            hs = []
-            for arr in (final_host, self.flags):
-                h = (C.c_ubyte * 64)()
-                off = C.c_uint64(0)
-                dev.check(dev.lib.swcu_ipc_export(dev.ctx, arr.ctypes.data, h, C.byref(off)))
-                hs.append((bytes(h), int(off.value)))
-            payload = [hs]
+            try:
+                hs = []
+                for arr in (final_host, self.flags):
+                    h = (C.c_ubyte * 64)()
+                    off = C.c_uint64(0)
+                    dev.check(dev.lib.swcu_ipc_export(dev.ctx, arr.ctypes.data, h, C.byref(off)))
+                    hs.append((bytes(h), int(off.value)))
+                payload = [hs]
+            except Exception as e:  # noqa: BLE001
+                payload = [f"export failed: {e}"]
         dist.broadcast_object_list(payload, src=0)
+        if isinstance(payload[0], str):
+            dev.unregister(self.flags)
+            raise RuntimeError(payload[0])
+        err = ""
         if rank != 0:
-            (hf, of), (hg, og) = payload[0]
-            self.peer_frame = self._open(hf) + of
-            self.peer_flags = self._open(hg) + og
-            # adopt the mappings so that addresses inside them are accepted as attachments / flags
-            dev.check(dev.lib.swcu_mem_register_device(dev.ctx, self.peer_frame, height * pitch_bytes))
-            dev.check(dev.lib.swcu_mem_register_device(dev.ctx, self.peer_flags, 64 * 4))
+            try:
+                (hf, of), (hg, og) = payload[0]
+                self.peer_frame = self._open(hf) + of
+                self.peer_flags = self._open(hg) + og
+                # adopt the mappings so that addresses inside them are accepted as attachments / flags
+                dev.check(dev.lib.swcu_mem_register_device(dev.ctx, self.peer_frame, height * pitch_bytes))
+                dev.check(dev.lib.swcu_mem_register_device(dev.ctx, self.peer_flags, 64 * 4))
+            except Exception as e:  # noqa: BLE001
+                err = f"rank {rank}: {e}"
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        if any(errs):
+            raise RuntimeError("peer mapping failed: " + "; ".join(e for e in errs if e))
         dist.barrier()
 
     def _open(self, handle: bytes) -> int:
