@@ -262,6 +262,37 @@ def scissor(seed: int) -> Scene:
     return Scene(W, H, [d1], hasDepth=True, clearDepth=1.0 if vp[4] <= vp[5] else 0.0)
 
 
+_OVERDRAW = [
+    # samples, n triangles, kinds, textured, depth, blend, W, H
+    (4, 3000, (1, 4, 1, 5), False, True, True, 160, 96),
+    (4, 600, (5, 0, 1, 4), False, False, True, 128, 128),
+    (4, 40, (0, 5), False, True, True, 256, 160),
+    (1, 4000, (1, 4, 1), False, False, True, 160, 96),
+    (1, 800, (5, 0, 1, 4), False, True, True, 192, 128),
+    (1, 1500, (1, 5, 4), True, True, False, 128, 96),
+    (1, 300, (0, 5, 1), True, False, True, 96, 96),
+]
+
+
+def overdraw(seed: int) -> Scene:
+    """Thousands of overlapping triangles of mixed sizes in ONE draw: per-pixel order under non-commutative blending, many
+    fragments per sample, big and pixel-sized triangles together (the density the other families do not reach)."""
+    samples, n, kinds, textured, depth, blend_on, W, H = _OVERDRAW[seed % len(_OVERDRAW)]
+    rng = np.random.default_rng(90000 + seed)
+    tris = []
+    for i in range(n):
+        p = _tri_kind(rng, kinds[i % len(kinds)])
+        col = rng.uniform(0, 1, (3, 4))
+        if textured:
+            col[:, :2] = rng.uniform(-2, 3, (3, 2))
+        tris.append(_verts(rng, p, persp=(i % 3 == 0), colour=col))
+    kw = dict(depthTest=depth, depthWrite=depth, blend=blend_on)
+    if textured:
+        kw["texture"] = Texture(_rand_tex(np.random.default_rng(5), 64, 64, 7), maxLod=6.0)
+    d = Draw(np.concatenate(tris, axis=0), P4C4, "vs_pos4_col4", "fs_tex_col4" if textured else "fs_col4", **kw)
+    return Scene(W, H, [d], samples=samples, hasDepth=depth, clearDepth=1.0, clearColor=(0.25, 0.5, 0.125, 1.0))
+
+
 def _checker16():
     """The benchmark's 16x16 checkerboard (TriangleBenchmarks.cpp:219-241)."""
     rgb = [0xFFFF0000, 0xFF00FF00, 0xFF0000FF]
@@ -303,6 +334,7 @@ FAMILIES = {
     "msaa": (msaa, 16),
     "topology": (topology, 12),
     "scissor": (scissor, 8),
+    "overdraw": (overdraw, 7),
 }
 
 
