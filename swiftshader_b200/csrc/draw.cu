@@ -44,9 +44,22 @@ struct swcu_ctx
 	cudaStream_t stream = nullptr, ownStream = nullptr;
 	std::map<uintptr_t, Shadow> mem;
 	std::string err;
-	DevBuf cullFlags;
-	DevBuf triRecords, spans, bigList, tileCount, pairOffset, keys, vals, keys2, vals2, tileBegin, tileEnd, cubTemp, counters, zeroPage;
-	DrawCounters *hostCounters = nullptr; // pinned
+	// Buffers of the setup phase (k_cull, k_setup, pair-offset scan) exist twice: the setup of draw i+1 runs on its own stream
+	// while the tile kernel of draw i is still reading the other set, so the host's wait for the pair count (the one sync of a
+	// binned draw) no longer leaves the GPU idle.
+	struct SetupSet
+	{
+		DevBuf triRecords, spans, bigList, tileCount, pairOffset, counters, cullFlags, scanTemp;
+		DrawCounters *hostCounters = nullptr; // pinned
+		cudaEvent_t tileDone = nullptr;       // recorded on the main stream after the last kernel that reads this set
+		bool tileDoneValid = false;
+	} set[2];
+	int cur = 0;
+	cudaStream_t setupStream = nullptr;
+	cudaEvent_t evUpload = nullptr; // last swcu_mem_upload / clear on the main stream (inputs of the setup phase)
+	bool evUploadValid = false;
+	int optPipeline = 1;
+	DevBuf keys, vals, keys2, vals2, tileBegin, tileEnd, cubTemp, zeroPage;
 	swcu_stats stats{};
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	std::map<uint64_t, swcu_shader_info> shaderCache;
@@ -87,6 +100,7 @@ static int ensure(swcu_ctx *ctx, DevBuf &b, size_t bytes)
 	if(b.p)
 	{
 		CU(cudaStreamSynchronize(ctx->stream)); // earlier launches may still read the old block
+		if(ctx->setupStream) CU(cudaStreamSynchronize(ctx->setupStream));
 		CU(cudaFree(b.p));
 		b.p = nullptr;
 		b.cap = 0;
@@ -124,7 +138,13 @@ extern "C" int swcu_create(swcu_ctx **out, int device_ordinal)
 	ctx->stream = ctx->ownStream;
 	if((e = cudaEventCreate(&ctx->t0)) != cudaSuccess) return bail("cudaEventCreate", e);
 	if((e = cudaEventCreate(&ctx->t1)) != cudaSuccess) return bail("cudaEventCreate", e);
-	if((e = cudaMallocHost((void **)&ctx->hostCounters, sizeof(DrawCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
+	if((e = cudaStreamCreateWithFlags(&ctx->setupStream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+	if((e = cudaEventCreateWithFlags(&ctx->evUpload, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+	for(auto &S : ctx->set)
+	{
+		if((e = cudaMallocHost((void **)&S.hostCounters, sizeof(DrawCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
+		if((e = cudaEventCreateWithFlags(&S.tileDone, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+	}
 	*out = ctx;
 	return SWCU_OK;
 }
@@ -139,11 +159,19 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 		if(kv.second.pinned) cudaHostUnregister((void *)kv.second.host);
 		if(!kv.second.external) cudaFree(kv.second.dev);
 	}
-	DevBuf *bufs[] = { &ctx->triRecords, &ctx->spans, &ctx->bigList, &ctx->tileCount, &ctx->pairOffset, &ctx->keys, &ctx->vals,
-		               &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->counters, &ctx->zeroPage, &ctx->cullFlags };
+	if(ctx->setupStream) cudaStreamSynchronize(ctx->setupStream);
+	DevBuf *bufs[] = { &ctx->keys, &ctx->vals, &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->zeroPage };
 	for(DevBuf *b : bufs) cudaFree(b->p);
+	for(auto &S : ctx->set)
+	{
+		DevBuf *sb[] = { &S.triRecords, &S.spans, &S.bigList, &S.tileCount, &S.pairOffset, &S.counters, &S.cullFlags, &S.scanTemp };
+		for(DevBuf *b : sb) cudaFree(b->p);
+		if(S.hostCounters) cudaFreeHost(S.hostCounters);
+		if(S.tileDone) cudaEventDestroy(S.tileDone);
+	}
+	if(ctx->evUpload) cudaEventDestroy(ctx->evUpload);
+	if(ctx->setupStream) cudaStreamDestroy(ctx->setupStream);
 	for(cudaEvent_t ev : ctx->eventPool) cudaEventDestroy(ev);
-	if(ctx->hostCounters) cudaFreeHost(ctx->hostCounters);
 	if(ctx->t0) cudaEventDestroy(ctx->t0);
 	if(ctx->t1) cudaEventDestroy(ctx->t1);
 	if(ctx->ownStream) cudaStreamDestroy(ctx->ownStream);
@@ -240,6 +268,8 @@ extern "C" int swcu_mem_upload(swcu_ctx *ctx, const void *host_ptr, size_t bytes
 	if(d == (const unsigned char *)host_ptr) return fail(ctx, SWCU_E_INVALID, "swcu_mem_upload: %p is caller-owned device memory", host_ptr);
 	CU(cudaSetDevice(ctx->device));
 	CU(cudaMemcpyAsync(d, host_ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CU(cudaEventRecord(ctx->evUpload, ctx->stream)); // the setup stream of a later draw waits for its inputs
+	ctx->evUploadValid = true;
 	ctx->stats.h2dBytes += bytes;
 	return SWCU_OK;
 }
@@ -265,6 +295,7 @@ extern "C" int swcu_sync(swcu_ctx *ctx)
 {
 	if(!ctx) return SWCU_E_INVALID;
 	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->setupStream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	return SWCU_OK;
 }
@@ -343,6 +374,7 @@ extern "C" int swcu_set_option(swcu_ctx *ctx, const char *name, int value)
 	else if(!strcmp(name, "pin_host")) ctx->optPinHost = value;
 	else if(!strcmp(name, "tma")) ctx->optTma = value;
 	else if(!strcmp(name, "fast_state")) ctx->optFastState = value;
+	else if(!strcmp(name, "pipeline")) ctx->optPipeline = value;
 	else return fail(ctx, SWCU_E_INVALID, "unknown option '%s'", name);
 	return SWCU_OK;
 }
@@ -353,7 +385,8 @@ struct LaunchScope
 	swcu_ctx *ctx;
 	KernelTime kt{};
 	bool timed = false;
-	LaunchScope(swcu_ctx *c, const char *name) : ctx(c)
+	cudaStream_t st;
+	LaunchScope(swcu_ctx *c, const char *name, cudaStream_t stream = nullptr) : ctx(c), st(stream ? stream : c->stream)
 	{
 		ctx->stats.kernelLaunches++;
 		if(ctx->profiling)
@@ -363,13 +396,13 @@ struct LaunchScope
 				return ctx->eventPool[ctx->eventsUsed++];
 			};
 			kt.name = name; kt.e0 = get(); kt.e1 = get();
-			cudaEventRecord(kt.e0, ctx->stream);
+			cudaEventRecord(kt.e0, st);
 			timed = true;
 		}
 	}
 	~LaunchScope()
 	{
-		if(timed) { cudaEventRecord(kt.e1, ctx->stream); ctx->lastKernels.push_back(kt); }
+		if(timed) { cudaEventRecord(kt.e1, st); ctx->lastKernels.push_back(kt); }
 	}
 };
 
@@ -492,6 +525,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	{
 		d.indexBuffer = dev_ptr(ctx, desc->indexBuffer);
 		if(!d.indexBuffer) return fail(ctx, SWCU_E_INVALID, "index buffer %p is not inside a registered range", desc->indexBuffer);
+		if(find_shadow(ctx, desc->indexBuffer, 1)->external) d.inputsExternal = 1;
 	}
 	// vertex-stage scalars: component c of stream l, or a constant (VertexRoutine::readStream, VertexRoutine.cpp:173-245)
 	int vsrcErr = SWCU_OK;
@@ -515,6 +549,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		if(in.robustnessSize && in.robustnessSize < ncomp * 4) return k;    // every fetch is out of bounds: 0
 		unsigned char *base = dev_ptr(ctx, in.buffer);
 		if(!base) { vsrcErr = fail(ctx, SWCU_E_INVALID, "vertex input %u: buffer %p is not inside a registered range", l, in.buffer); return k; }
+		if(find_shadow(ctx, in.buffer, 1)->external) d.inputsExternal = 1;
 		k.ptr = base + 4 * c;
 		k.stride = in.vertexStride;
 		k.limit = in.robustnessSize ? in.robustnessSize - ncomp * 4 : 0xFFFFFFFFu;
@@ -779,72 +814,86 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 
 	const uint32_t n = d.primCount;
 	d.direct = (!ctx->optForceBinned && (int)n <= ctx->optDirectMax) ? 1u : 0u;
-	if((rc = ensure(ctx, ctx->triRecords, (size_t)n * d.triStride))) return rc;
-	if((rc = ensure(ctx, ctx->tileCount, (size_t)n * 4))) return rc;
-	if((rc = ensure(ctx, ctx->counters, sizeof(DrawCounters)))) return rc;
+	// The setup phase of this draw uses the set the draw before the previous one used.  A binned draw runs it on the setup
+	// stream: it waits only for the inputs (last upload) and for the last reader of this set, not for the tile kernel of the
+	// previous draw, which keeps the GPU busy while the host waits for the pair count.  Direct draws, profiling mode (per-kernel
+	// events) and inputs in caller-owned device memory (whose producers the library cannot see) stay on the main stream.
+	swcu_ctx::SetupSet &S = ctx->set[ctx->cur];
+	ctx->cur ^= 1;
+	const bool pipelined = !d.direct && ctx->optPipeline && !ctx->profiling && !d.inputsExternal;
+	const cudaStream_t ss = pipelined ? ctx->setupStream : ctx->stream;
+	if(pipelined)
+	{
+		if(S.tileDoneValid) CU(cudaStreamWaitEvent(ss, S.tileDone, 0));
+		if(ctx->evUploadValid) CU(cudaStreamWaitEvent(ss, ctx->evUpload, 0));
+	}
+	if((rc = ensure(ctx, S.triRecords, (size_t)n * d.triStride))) return rc;
+	if((rc = ensure(ctx, S.tileCount, (size_t)n * 4))) return rc;
+	if((rc = ensure(ctx, S.counters, sizeof(DrawCounters)))) return rc;
 	if(!ctx->zeroPage.p)
 	{
 		if((rc = ensure(ctx, ctx->zeroPage, 256))) return rc;
 		CU(cudaMemsetAsync(ctx->zeroPage.p, 0, 256, ctx->stream));
+		CU(cudaStreamSynchronize(ctx->stream));
 	}
 	const size_t scRows = (size_t)(d.scY1 - d.scY0);
 	size_t spanWant, bigWant;
 	if(d.direct) { spanWant = (size_t)n * d.ms * scRows; bigWant = n; }
 	else
 	{
-		spanWant = std::max<size_t>(ctx->spans.cap / 4, std::max<size_t>((size_t)n * d.ms * 8, 1u << 20));
-		bigWant = std::max<size_t>(ctx->bigList.cap / sizeof(BigTri), 1u << 14);
+		spanWant = std::max<size_t>(S.spans.cap / 4, std::max<size_t>((size_t)n * d.ms * 8, 1u << 20));
+		bigWant = std::max<size_t>(S.bigList.cap / sizeof(BigTri), 1u << 14);
 	}
 	const dim3 tileGrid((unsigned)(d.tileX1 - d.tileX0), (unsigned)(d.tileY1 - d.tileY0));
 	const uint32_t numTiles = (uint32_t)(d.tilesX * d.tilesY);
 
 	for(int attempt = 0;; attempt++)
 	{
-		if((rc = ensure(ctx, ctx->spans, spanWant * 4))) return rc;
-		if((rc = ensure(ctx, ctx->bigList, bigWant * sizeof(BigTri)))) return rc;
-		d.triRecords = (unsigned char *)ctx->triRecords.p;
-		d.tileCount = (uint32_t *)ctx->tileCount.p;
-		d.counters = (DrawCounters *)ctx->counters.p;
+		if((rc = ensure(ctx, S.spans, spanWant * 4))) return rc;
+		if((rc = ensure(ctx, S.bigList, bigWant * sizeof(BigTri)))) return rc;
+		d.triRecords = (unsigned char *)S.triRecords.p;
+		d.tileCount = (uint32_t *)S.tileCount.p;
+		d.counters = (DrawCounters *)S.counters.p;
 		d.zeroPage = ctx->zeroPage.p;
-		d.spans = (uint32_t *)ctx->spans.p;
-		d.spanCapacity = std::min<unsigned long long>(ctx->spans.cap / 4, 0xFFFFFFFFull);
-		d.bigList = (BigTri *)ctx->bigList.p;
-		d.bigCapacity = (uint32_t)std::min<size_t>(ctx->bigList.cap / sizeof(BigTri), 0x7FFFFFFFu);
-		CU(cudaMemsetAsync(d.counters, 0, sizeof(DrawCounters), ctx->stream));
+		d.spans = (uint32_t *)S.spans.p;
+		d.spanCapacity = std::min<unsigned long long>(S.spans.cap / 4, 0xFFFFFFFFull);
+		d.bigList = (BigTri *)S.bigList.p;
+		d.bigCapacity = (uint32_t)std::min<size_t>(S.bigList.cap / sizeof(BigTri), 0x7FFFFFFFu);
+		CU(cudaMemsetAsync(d.counters, 0, sizeof(DrawCounters), ss));
 		// band mode: the scissor / render area keeps less than 3/4 of the framebuffer rows (a rank of a multi-GPU frame)
 		d.cullFlags = nullptr;
 		if(!d.direct && attempt == 0 && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
 		{
-			if((rc = ensure(ctx, ctx->cullFlags, n))) return rc;
-			LaunchScope ls(ctx, "k_cull");
-			k_cull<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d, (unsigned char *)ctx->cullFlags.p);
-			d.cullFlags = (const unsigned char *)ctx->cullFlags.p;
+			if((rc = ensure(ctx, S.cullFlags, n))) return rc;
+			LaunchScope ls(ctx, "k_cull", ss);
+			k_cull<<<(n + 255) / 256, 256, 0, ss>>>(d, (unsigned char *)S.cullFlags.p);
+			d.cullFlags = (const unsigned char *)S.cullFlags.p;
 		}
-		else if(!d.direct && attempt > 0 && ctx->cullFlags.p && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
-			d.cullFlags = (const unsigned char *)ctx->cullFlags.p; // flags of the first attempt are still valid
+		else if(!d.direct && attempt > 0 && S.cullFlags.p && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
+			d.cullFlags = (const unsigned char *)S.cullFlags.p; // flags of the first attempt are still valid
 		{
-			LaunchScope ls(ctx, "k_setup");
+			LaunchScope ls(ctx, "k_setup", ss);
 			const size_t scratch = (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4;
-			if(d.ms != 1) k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ctx->stream>>>(d);
-			else k_setup_1x<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ctx->stream>>>(d);
+			if(d.ms != 1) k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
+			else k_setup_1x<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
 		}
 		if(d.direct) break;
 
 		// ---- binning: pair offsets, totals back to the host (the one sync of a binned draw) ----
-		if((rc = ensure(ctx, ctx->pairOffset, (size_t)n * 4))) return rc;
+		if((rc = ensure(ctx, S.pairOffset, (size_t)n * 4))) return rc;
 		size_t tempBytes = 0;
 		thrust::transform_iterator<TileRectCount, const uint32_t *> counts((const uint32_t *)d.tileCount, TileRectCount());
-		CU(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, counts, (uint32_t *)ctx->pairOffset.p, (int)n, ctx->stream));
-		if((rc = ensure(ctx, ctx->cubTemp, tempBytes))) return rc;
-		tempBytes = ctx->cubTemp.cap;
-		CU(cub::DeviceScan::ExclusiveSum(ctx->cubTemp.p, tempBytes, counts, (uint32_t *)ctx->pairOffset.p, (int)n, ctx->stream));
+		CU(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, counts, (uint32_t *)S.pairOffset.p, (int)n, ss));
+		if((rc = ensure(ctx, S.scanTemp, tempBytes))) return rc;
+		tempBytes = S.scanTemp.cap;
+		CU(cub::DeviceScan::ExclusiveSum(S.scanTemp.p, tempBytes, counts, (uint32_t *)S.pairOffset.p, (int)n, ss));
 		{
-			LaunchScope ls(ctx, "k_pair_total");
-			k_pair_total<<<1, 1, 0, ctx->stream>>>((const uint32_t *)ctx->pairOffset.p, d.tileCount, n, d.counters);
+			LaunchScope ls(ctx, "k_pair_total", ss);
+			k_pair_total<<<1, 1, 0, ss>>>((const uint32_t *)S.pairOffset.p, d.tileCount, n, d.counters);
 		}
-		CU(cudaMemcpyAsync(ctx->hostCounters, d.counters, sizeof(DrawCounters), cudaMemcpyDeviceToHost, ctx->stream));
-		CU(cudaStreamSynchronize(ctx->stream));
-		const DrawCounters hc = *ctx->hostCounters;
+		CU(cudaMemcpyAsync(S.hostCounters, d.counters, sizeof(DrawCounters), cudaMemcpyDeviceToHost, ss));
+		CU(cudaStreamSynchronize(ss)); // the setup phase only: the main stream may still be running the previous draw's tiles
+		const DrawCounters hc = *S.hostCounters;
 		if(hc.overflow)
 		{
 			if(attempt >= 2) return fail(ctx, SWCU_E_NOMEM, "work buffers still too small after growing (spans %llu, big %llu)", hc.spanCursor, hc.bigSlots);
@@ -864,14 +913,14 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		if((rc = ensure(ctx, ctx->tileEnd, (size_t)numTiles * 4))) return rc;
 		{
 			LaunchScope ls(ctx, "k_emit");
-			k_emit<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d, (const uint32_t *)ctx->pairOffset.p, (uint32_t *)ctx->keys.p, (uint32_t *)ctx->vals.p);
+			k_emit<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d, (const uint32_t *)S.pairOffset.p, (uint32_t *)ctx->keys.p, (uint32_t *)ctx->vals.p);
 		}
 		if(hc.bigSlots)
 		{
 			LaunchScope ls(ctx, "k_big");
 			const unsigned gx = (unsigned)std::min<unsigned long long>(hc.bigSlots, 4096);
 			const unsigned gy = hc.bigSlots < 64 ? 16 : 1;
-			k_big<<<dim3(gx, gy), 256, 0, ctx->stream>>>(d, (const uint32_t *)ctx->pairOffset.p, (uint32_t *)ctx->keys.p, (uint32_t *)ctx->vals.p);
+			k_big<<<dim3(gx, gy), 256, 0, ctx->stream>>>(d, (const uint32_t *)S.pairOffset.p, (uint32_t *)ctx->keys.p, (uint32_t *)ctx->vals.p);
 		}
 		// stable sort by tile: per-tile lists keep API order
 		int bits = 1;
@@ -913,6 +962,8 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	}
 	if(d.ms == 4) launch_tile<4>(ctx, d, maps, tileGrid); else launch_tile<1>(ctx, d, maps, tileGrid);
 	CU(cudaGetLastError());
+	CU(cudaEventRecord(S.tileDone, ctx->stream)); // last reader of this set's records / spans / offsets
+	S.tileDoneValid = true;
 	return SWCU_OK;
 }
 

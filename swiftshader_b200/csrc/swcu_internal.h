@@ -180,6 +180,7 @@ struct DrawConst
 	BigTri *bigList;
 	uint32_t bigCapacity;
 	uint32_t *tileCount;       // per triangle: packed tile rectangle / pair count (tile_rect_count)
+	uint32_t inputsExternal;        // an index / vertex stream lives in caller-owned device memory (host side only)
 	const unsigned char *cullFlags; // band mode: 0 = rows outside the band (k_cull), nullptr when the pass is not run
 	DrawCounters *counters;
 	const void *zeroPage;      // 256 readable bytes: target of the discarded loads of branch-free attribute fetches
