@@ -1,16 +1,19 @@
 // kernels.cuh — the sm_100a kernels of the draw path.
 //
+//   k_cull    band mode only: marks the triangles whose rows miss the render area (a rank of a multi-GPU frame).
 //   k_setup   one thread per triangle: index fetch (Renderer.cpp:50-145), vertex stage + clip flags + projection
 //             (VertexRoutine.cpp:116-154,570-610), trivial reject / Sutherland-Hodgman clip (Renderer.cpp:733-776,
 //             Clipper.cpp), cull / row range / plane equations (SetupRoutine.cpp:36-548) and — for small triangles —
-//             the per-row spans (SetupRoutine.cpp:550-621).
+//             the per-row spans (SetupRoutine.cpp:550-621); writes one record + one packed tile rectangle per triangle.
 //   k_big     one CTA per large triangle: spans in closed form, one (row, sample) per thread, and its tile pairs.
 //   k_emit    (tile, triangle) pairs of the small triangles; sorted by tile with a stable radix sort => per-tile
 //             triangle lists in API order (the ordering contract of Renderer.cpp:573-576,652-661).
-//   k_tile    one CTA per 32x16 screen tile: stages colour/depth/stencil of the tile in shared memory, every lane owns one
-//             2x2 quad, walks the tile's triangles in order and runs QuadRasterizer coverage + PixelRoutine::quad
-//             (depth/stencil test, interpolation, shader routing, sampler, blend, format write), then writes the tile
-//             back with 128-bit stores.
+//   k_tile    one CTA per 32x16 screen tile, one warp per 16x8 region: stages colour/depth/stencil of the tile in shared
+//             memory (TMA), walks the tile's triangle list in order, turns the spans that cross the region into
+//             (candidate, row, sample) runs of covered pixels (QuadRasterizer coverage) and consumes the covered samples 32 at
+//             a time, one per lane, through PixelRoutine::quad (interpolation, shader routing, sampler, depth/stencil
+//             test, blend, format write); the tile goes back with TMA stores.
+//   k_clear, k_resolve4, k_copy_rows, k_signal, k_wait_flags   the steps either side of the draw and the multi-GPU delivery.
 //
 // Float discipline: compiled with -fmad=false -ftz=true -prec-div=true -prec-sqrt=true; every
 // product/sum is a single rounded op and __fmaf_rn appears only where the reference writes MulAdd().
@@ -1014,13 +1017,17 @@ DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1
 //     triangle list, and go back with one TMA store per attachment (fallback: cooperative 128-bit copies when the
 //     attachment's pitch / base address do not satisfy the tensor-map alignment rules);
 //   * the four warps are INDEPENDENT inside the list loop (no CTA barriers): each warp scans the tile's list 32 entries
-//     at a time, ballots the bounding boxes against its region, and stages the candidates' plane equations and the span
-//     rows that cross the region in its own shared-memory area with coalesced 128-bit loads;
-//   * each lane computes the coverage bits of one 2x2 quad (4 pixels x MS samples) from the staged span rows, the covered
-//     (triangle, pixel, sample) ITEMS of the region are compacted into a per-warp queue and consumed 32 at a time, one
-//     item per lane, so lane utilisation does not depend on triangle size.  Items of one sample stay in API order: a
-//     lane's items are queued in list order, and items landing in the same round are serialised by __match_any_sync rank;
-//   * specialised on <samples, fragment shader class, blend class>; depth / stencil state is warp-uniform at run time.
+//     at a time (headers of the next block and list entries of the block after it already in flight), ballots the bounding
+//     boxes against its region and collects a batch of candidates; their plane equations come in with cp.async;
+//   * coverage: one candidate per lane (1x) or lane pair (4x) reads its span rows, clips them to the region's 16 columns and
+//     keeps the non-empty (row, sample) runs in registers; one warp scan places every lane's pairs and first item, the
+//     pair words and one start-mark bit per pair go to shared memory.  Batches of up to 4 (1x) / 1 (4x) candidates — big
+//     triangles — take a one-(candidate, row, sample)-per-lane path instead;
+//   * the covered samples (ITEMS) are consumed 32 at a time, one per lane, so lane utilisation does not depend on triangle
+//     size: the round's mark word maps every lane to its pair.  Items of one sample stay in API order: pairs are in list
+//     order, and when two fragments of a range hit the same sample (tested once per range) the items of a round are
+//     serialised by __match_any_sync rank;
+//   * specialised on <samples, fragment shader class, blend class, fast state>; everything else is warp-uniform run-time state.
 // ------------------------------------------------------------------------------------------------------------------
 #define TILE_THREADS (SWCU_TILE_WARPS * 32)
 
