@@ -166,7 +166,10 @@ int main(int argc, char **argv)
 	// ---- attachments ----
 	const VkFormat cfmt = (VkFormat)hdr->colorFormat;
 	const bool hasDS = hdr->hasDepth || hdr->hasStencil;
-	const VkFormat dsfmt = hdr->hasStencil ? VK_FORMAT_D32_SFLOAT_S8_UINT : VK_FORMAT_D32_SFLOAT;
+	// hasDepth: 0 = none, 1 = D32_SFLOAT, 2 = D16_UNORM (without stencil)
+	const bool d16 = hdr->hasDepth == 2 && !hdr->hasStencil;
+	const VkFormat dsfmt = hdr->hasStencil ? VK_FORMAT_D32_SFLOAT_S8_UINT : (d16 ? VK_FORMAT_D16_UNORM : VK_FORMAT_D32_SFLOAT);
+	const size_t depthBpp = d16 ? 2 : 4;
 	const VkImageAspectFlags dsAspect = VK_IMAGE_ASPECT_DEPTH_BIT | (hdr->hasStencil ? VK_IMAGE_ASPECT_STENCIL_BIT : 0);
 	VkImage cimg, rimg = VK_NULL_HANDLE, dimg = VK_NULL_HANDLE;
 	VkImageView cview, rview = VK_NULL_HANDLE, dview = VK_NULL_HANDLE;
@@ -417,7 +420,7 @@ int main(int argc, char **argv)
 	void *pC, *pD = nullptr, *pS = nullptr;
 	mkBuffer((size_t)W * H * 4, VK_BUFFER_USAGE_TRANSFER_DST_BIT, rbC, pC);
 	const bool readDS = hasDS && !ms;
-	if(readDS && hdr->hasDepth) mkBuffer((size_t)W * H * 4, VK_BUFFER_USAGE_TRANSFER_DST_BIT, rbD, pD);
+	if(readDS && hdr->hasDepth) mkBuffer((size_t)W * H * depthBpp, VK_BUFFER_USAGE_TRANSFER_DST_BIT, rbD, pD);
 	if(readDS && hdr->hasStencil) mkBuffer((size_t)W * H, VK_BUFFER_USAGE_TRANSFER_DST_BIT, rbS, pS);
 
 	auto record = [&](VkCommandBuffer c, int pass, bool copy) {
@@ -467,10 +470,10 @@ int main(int argc, char **argv)
 
 	FILE *fo = fopen(argv[3], "wb");
 	if(!fo) { perror("out"); return 1; }
-	uint32_t oh[6] = { 0x4F525753u /* SWRO */, W, H, (uint32_t)(rbD != VK_NULL_HANDLE), (uint32_t)(rbS != VK_NULL_HANDLE), hdr->samples };
+	uint32_t oh[6] = { 0x4F525753u /* SWRO */, W, H, (uint32_t)(rbD != VK_NULL_HANDLE ? (d16 ? 2 : 1) : 0), (uint32_t)(rbS != VK_NULL_HANDLE), hdr->samples };
 	fwrite(oh, 4, 6, fo);
 	fwrite(pC, 1, (size_t)W * H * 4, fo);
-	if(rbD) fwrite(pD, 1, (size_t)W * H * 4, fo);
+	if(rbD) fwrite(pD, 1, (size_t)W * H * depthBpp, fo);
 	if(rbS) fwrite(pS, 1, (size_t)W * H, fo);
 	fclose(fo);
 

@@ -35,6 +35,7 @@ enum
 	FMT_R32G32_SFLOAT = 103,
 	FMT_R32G32B32_SFLOAT = 106,
 	FMT_R32G32B32A32_SFLOAT = 109,
+	FMT_D16_UNORM = 124,
 	FMT_D32_SFLOAT = 126,
 	FMT_S8_UINT = 127,
 };
@@ -463,12 +464,18 @@ static int setup_triangle(const Draw *dr, Primitive *prim, const Vertex *tv0, co
 		int applyConst = d->depthBiasConstant != 0.0f, applySlope = d->depthBiasSlope != 0.0f;
 		if(applyConst)
 		{
-			float Z0 = C;
-			float Z1 = z1 * dr->depthRange + dr->depthNear;
-			float Z2 = z2 * dr->depthRange + dr->depthNear;
-			int e0 = (int)(as_uint(Z0) & 0x7F800000u), e1 = (int)(as_uint(Z1) & 0x7F800000u), e2 = (int)(as_uint(Z2) & 0x7F800000u);
-			int e = e0 > e1 ? e0 : e1; e = e > e2 ? e : e2;
-			float r = as_float((uint32_t)e) * (1.0f / (1 << 23));
+			float r;
+			if(d->depth.format == FMT_D16_UNORM)
+				r = 1.01f / 0xFFFF; /* fixed-point depth buffer: DrawData::minimumResolvableDepthDifference, Renderer.cpp:430 */
+			else
+			{
+				float Z0 = C;
+				float Z1 = z1 * dr->depthRange + dr->depthNear;
+				float Z2 = z2 * dr->depthRange + dr->depthNear;
+				int e0 = (int)(as_uint(Z0) & 0x7F800000u), e1 = (int)(as_uint(Z1) & 0x7F800000u), e2 = (int)(as_uint(Z2) & 0x7F800000u);
+				int e = e0 > e1 ? e0 : e1; e = e > e2 ? e : e2;
+				r = as_float((uint32_t)e) * (1.0f / (1 << 23));
+			}
 			bias = r * d->depthBiasConstant;
 		}
 		if(applySlope)
@@ -920,14 +927,23 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 				if(!(d->sampleMask & (1u << q))) continue;
 				if(dr->depthTestActive)
 				{
-					float *zb = (float *)((char *)d->depth.buffer + (size_t)q * d->depth.sliceB);
+					char *zb = (char *)d->depth.buffer + (size_t)q * d->depth.sliceB;
+					const int d16 = d->depth.format == FMT_D16_UNORM;
 					int zTest = 0;
 					for(int i = 0; i < 4; i++)
 					{
-						/* clampDepth :484-492: D32F without VK_EXT_depth_range_unrestricted => [0,1] (PixelProcessor.cpp:121-136) */
+						/* clampDepth :484-492: fixed point, or D32F without VK_EXT_depth_range_unrestricted => [0,1] (PixelProcessor.cpp:121-136) */
 						z[q][i] = sse_min(sse_max(z[q][i], 0.0f), 1.0f);
 						float Z = z[q][i];
-						float zValue = *(float *)((char *)zb + (size_t)(y + (i >> 1)) * d->depth.pitchB + 4 * (size_t)(x + (i & 1)));
+						float zValue;
+						if(d16)
+						{
+							/* depthTest :508-511: Z = Min(Max(Round(z * 0xFFFF), 0), 0xFFFF), compared as floats with Float(UShort) (:466-482) */
+							Z = sse_min(sse_max(rintf(Z * 65535.0f), 0.0f), 65535.0f);
+							zValue = (float)*(uint16_t *)(zb + (size_t)(y + (i >> 1)) * d->depth.pitchB + 2 * (size_t)(x + (i & 1)));
+						}
+						else
+							zValue = *(float *)(zb + (size_t)(y + (i >> 1)) * d->depth.pitchB + 4 * (size_t)(x + (i & 1)));
 						int t;
 						switch(d->depthCompareOp)
 						{
@@ -957,7 +973,17 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 						char *zb = (char *)d->depth.buffer + (size_t)q * d->depth.sliceB;
 						for(int i = 0; i < 4; i++)
 							if(zMask[q] & (1 << i))
-								*(float *)(zb + (size_t)(y + (i >> 1)) * d->depth.pitchB + 4 * (size_t)(x + (i & 1))) = z[q][i];
+							{
+								if(d->depth.format == FMT_D16_UNORM)
+								{
+									/* writeDepth16 :687-711: UShort4(Round(z * 0xFFFF), saturate) */
+									float r = rintf(z[q][i] * 65535.0f);
+									r = r < 0.0f ? 0.0f : (r > 65535.0f ? 65535.0f : r);
+									*(uint16_t *)(zb + (size_t)(y + (i >> 1)) * d->depth.pitchB + 2 * (size_t)(x + (i & 1))) = (uint16_t)r;
+								}
+								else
+									*(float *)(zb + (size_t)(y + (i >> 1)) * d->depth.pitchB + 4 * (size_t)(x + (i & 1))) = z[q][i];
+							}
 					}
 				/* blendColor (PixelProgram.cpp:261-284) -> alphaBlend (PixelRoutine.cpp:1653-1961) -> writeColor (:1963-2655) */
 				if(dr->colorWriteMask && d->color.buffer)
@@ -1078,7 +1104,8 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 	if(!d || d->structSize != sizeof(swcu_draw_desc) || !vs || !fs) return SWCU_E_INVALID;
 	if(d->sampleCount != 1 && d->sampleCount != 4) return SWCU_E_UNSUPPORTED;
 	if(d->color.buffer && d->color.format != FMT_R8G8B8A8_UNORM && d->color.format != FMT_B8G8R8A8_UNORM) return SWCU_E_UNSUPPORTED;
-	if(d->depth.buffer && d->depth.format != FMT_D32_SFLOAT) return SWCU_E_UNSUPPORTED;
+	if(d->depth.buffer && d->depth.format != FMT_D32_SFLOAT && d->depth.format != FMT_D16_UNORM) return SWCU_E_UNSUPPORTED;
+	if(d->depth.buffer && d->depth.format == FMT_D16_UNORM && d->stencil.buffer) return SWCU_E_UNSUPPORTED; /* D16_UNORM_S8_UINT: not in the subset */
 
 	unsigned int csr = _mm_getcsr();
 	_mm_setcsr(csr | 0x8040); /* FTZ | DAZ, System/SwiftConfig.cpp:136-139 */
@@ -1157,7 +1184,7 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 /* Blitter::fastClear, Device/Blitter.cpp:170-325 — rectangle fill of every sample slice */
 int swref_clear(const swcu_attachment *att, uint32_t samples, const swcu_rect *area, const void *value)
 {
-	int bpp = att->format == FMT_S8_UINT ? 1 : 4;
+	int bpp = att->format == FMT_S8_UINT ? 1 : (att->format == FMT_D16_UNORM ? 2 : 4);
 	for(uint32_t q = 0; q < samples; q++)
 		for(uint32_t y = 0; y < area->height; y++)
 		{

@@ -179,7 +179,10 @@ def render_reference(scene: Scene, time_frames: int = 0, threads: int | None = N
     off = 24
     out = {"color": np.frombuffer(raw, np.uint8, W * H * 4, off).reshape(H, W, 4).copy()}
     off += W * H * 4
-    if hasD:
+    if hasD == 2:  # D16_UNORM
+        out["depth"] = np.frombuffer(raw, np.uint16, W * H, off).reshape(H, W).copy()
+        off += W * H * 2
+    elif hasD:
         out["depth"] = np.frombuffer(raw, np.float32, W * H, off).reshape(H, W).copy()
         off += W * H * 4
     if hasS:

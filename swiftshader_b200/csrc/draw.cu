@@ -485,7 +485,10 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	if(desc->provokingVertexMode > 1) return fail(ctx, SWCU_E_INVALID, "bad provoking vertex mode");
 	if(desc->color.buffer && desc->color.format != VKF_R8G8B8A8_UNORM && desc->color.format != VKF_B8G8R8A8_UNORM)
 		return fail(ctx, SWCU_E_UNSUPPORTED, "colour format %u unsupported (R8G8B8A8_UNORM, B8G8R8A8_UNORM)", desc->color.format);
-	if(desc->depth.buffer && desc->depth.format != VKF_D32_SFLOAT) return fail(ctx, SWCU_E_UNSUPPORTED, "depth format %u unsupported (D32_SFLOAT)", desc->depth.format);
+	if(desc->depth.buffer && desc->depth.format != VKF_D32_SFLOAT && desc->depth.format != VKF_D16_UNORM)
+		return fail(ctx, SWCU_E_UNSUPPORTED, "depth format %u unsupported (D32_SFLOAT, D16_UNORM)", desc->depth.format);
+	if(desc->depth.buffer && desc->depth.format == VKF_D16_UNORM && desc->stencil.buffer)
+		return fail(ctx, SWCU_E_UNSUPPORTED, "D16_UNORM with a stencil aspect is outside the subset");
 	if(desc->stencil.buffer && desc->stencil.format != VKF_S8_UINT) return fail(ctx, SWCU_E_UNSUPPORTED, "stencil format %u unsupported (S8_UINT)", desc->stencil.format);
 	if(!desc->color.buffer && !desc->depth.buffer && !desc->stencil.buffer) return fail(ctx, SWCU_E_INVALID, "draw without attachments");
 
@@ -672,7 +675,8 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		return SWCU_OK;
 	};
 	if((rc = att(desc->color, 4, d.colorBuf, d.colorPitchB, d.colorSliceB, "colour"))) return rc;
-	if((rc = att(desc->depth, 4, d.depthBuf, d.depthPitchB, d.depthSliceB, "depth"))) return rc;
+	d.depth16 = desc->depth.buffer && desc->depth.format == VKF_D16_UNORM;
+	if((rc = att(desc->depth, d.depth16 ? 2 : 4, d.depthBuf, d.depthPitchB, d.depthSliceB, "depth"))) return rc;
 	if((rc = att(desc->stencil, 1, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, "stencil"))) return rc;
 	d.scX0 = clampi_h(d.scX0, 0, d.fbWidth); d.scX1 = clampi_h(d.scX1, 0, d.fbWidth);
 	d.scY0 = clampi_h(d.scY0, 0, d.fbHeight); d.scY1 = clampi_h(d.scY1, 0, d.fbHeight);
@@ -727,7 +731,7 @@ static bool get_tensor_map(swcu_ctx *ctx, CUtensorMap *out, unsigned char *base,
 		const cuuint64_t strides[2] = { (cuuint64_t)pitchB, (cuuint64_t)sliceB };
 		const cuuint32_t box[3] = { SWCU_TILE_W, SWCU_TILE_H, (cuuint32_t)ms };
 		const cuuint32_t estr[3] = { 1, 1, 1 };
-		CUresult r = ((EncodeTiledFn)ctx->encodeTiled)(&m, bpp == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+		CUresult r = ((EncodeTiledFn)ctx->encodeTiled)(&m, bpp == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : (bpp == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8), 3, base, dims, strides, box, estr,
 		                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 		if(r != CUDA_SUCCESS) return false;
 		if(ctx->mapCache.size() > 256) ctx->mapCache.clear();
@@ -756,7 +760,7 @@ static void launch_tile4(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps
 static bool fast_state(const swcu_ctx *ctx, const DrawConst &d)
 {
 	if(!ctx->optFastState) return false;
-	if(d.stencilActive || d.stencilWrite || !d.colorBuf || d.colorWriteMask != 0xFu || d.bgr || d.depthBiasEnable) return false;
+	if(d.stencilActive || d.stencilWrite || !d.colorBuf || d.colorWriteMask != 0xFu || d.bgr || d.depthBiasEnable || d.depth16) return false;
 	if(d.depthTestActive && d.depthCompareOp != CMP_LESS && d.depthCompareOp != CMP_LESS_OR_EQUAL) return false;
 	if(d.ms == 4 && (d.sampleMask & 0xFu) != 0xFu) return false;
 	if(d.blendClass == BL_GENERIC || d.shaderClass == SH_GENERIC) return false;
@@ -953,10 +957,10 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		const bool colorOn = d.colorWriteMask != 0 && d.colorBuf;
 		bool ok = ctx->optTma != 0;
 		if(ok && colorOn) ok = tma_eligible(d.colorBuf, d.colorPitchB, d.colorSliceB, 4);
-		if(ok && d.depthTestActive) ok = tma_eligible(d.depthBuf, d.depthPitchB, d.depthSliceB, 4);
+		if(ok && d.depthTestActive) ok = tma_eligible(d.depthBuf, d.depthPitchB, d.depthSliceB, d.depth16 ? 2 : 4);
 		if(ok && d.stencilActive) ok = tma_eligible(d.stencilBuf, d.stencilPitchB, d.stencilSliceB, 1);
 		if(ok && colorOn) ok = get_tensor_map(ctx, &maps.color, d.colorBuf, d.colorPitchB, d.colorSliceB, d.fbWidth, d.fbHeight, d.ms, 4);
-		if(ok && d.depthTestActive) ok = get_tensor_map(ctx, &maps.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, d.fbWidth, d.fbHeight, d.ms, 4);
+		if(ok && d.depthTestActive) ok = get_tensor_map(ctx, &maps.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, d.fbWidth, d.fbHeight, d.ms, d.depth16 ? 2 : 4);
 		if(ok && d.stencilActive) ok = get_tensor_map(ctx, &maps.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, d.fbWidth, d.fbHeight, d.ms, 1);
 		d.useTma = ok ? 1u : 0u;
 	}
@@ -1054,6 +1058,7 @@ extern "C" int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t sa
 	switch(att->format)
 	{
 	case VKF_R8G8B8A8_UNORM: case VKF_B8G8R8A8_UNORM: case VKF_D32_SFLOAT: bpp = 4; break;
+	case VKF_D16_UNORM: bpp = 2; break;
 	case VKF_S8_UINT: bpp = 1; break;
 	default: return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_clear: format %u unsupported", att->format);
 	}

@@ -576,7 +576,8 @@ DEVI void setup_triangle(const DrawConst &d)
 			const float Z2 = fadd(fmul(z2, d.depthRange), d.depthNear);
 			const int e0 = (int)(__float_as_uint(C) & 0x7F800000u), e1 = (int)(__float_as_uint(Z1) & 0x7F800000u), e2 = (int)(__float_as_uint(Z2) & 0x7F800000u);
 			const int e = max(max(e0, e1), e2);
-			const float r = fmul(__uint_as_float((uint32_t)e), 1.0f / (1 << 23));
+			// fixed-point depth buffer: the constant minimum resolvable difference of Renderer.cpp:430
+			const float r = d.depth16 ? 1.01f / 0xFFFF : fmul(__uint_as_float((uint32_t)e), 1.0f / (1 << 23));
 			bias = fmul(r, d.depthBiasConstant);
 		}
 		if(applySlope) bias = fadd(bias, fmul(sse_max(fabsf(A), fabsf(B)), d.depthBiasSlope));
@@ -1211,7 +1212,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 	{
 		if(threadIdx.x == 0)
 		{
-			const uint32_t bytes = (colorOn ? L::PLANE_B : 0) + (d.depthTestActive ? L::PLANE_B : 0) + (d.stencilActive ? L::STENCIL_B : 0);
+			const uint32_t bytes = (colorOn ? L::PLANE_B : 0) + (d.depthTestActive ? (d.depth16 ? L::PLANE_B / 2 : L::PLANE_B) : 0) + (d.stencilActive ? L::STENCIL_B : 0);
 			mbar_expect_tx(bar, bytes);
 			if(colorOn) tma_load_3d(smColor, &maps.color, bar, tileX, tileY, 0);
 			if(d.depthTestActive) tma_load_3d(smDepth, &maps.depth, bar, tileX, tileY, 0);
@@ -1221,7 +1222,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 	else
 	{
 		if(colorOn) tile_copy<MS, uint32_t, false>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		if(d.depthTestActive) tile_copy<MS, float, false>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		if(d.depthTestActive && d.depth16) tile_copy<MS, unsigned short, false>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		else if(d.depthTestActive) tile_copy<MS, float, false>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 		if(d.stencilActive) tile_copy<MS, unsigned char, false>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 		__syncthreads();
 	}
@@ -1618,13 +1620,28 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 								z = __fmaf_rn(xx, zA, fadd(zC, fmul(yy, zB)));
 								if(biasOn) z = fadd(z, zBias);
 								z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
-								const float zValue = smDepth[pi];
-								if(FS) zPass = d.depthCompareOp == CMP_LESS ? !(zValue <= z) : !(zValue < z); // LESS / LESS_OR_EQUAL (:533-553)
-								else zPass = depth_compare(d.depthCompareOp, zValue, z);
+								if(!FS && d.depth16)
+								{
+									// D16_UNORM (:466-482, :508-511): Z = Min(Max(Round(z * 0xFFFF), 0), 0xFFFF) against Float(UShort), as floats;
+									// the value written (:687-711, saturating UShort of Round(z * 0xFFFF)) is that same Z
+									z = sse_min(sse_max(rintf(fmul(z, 65535.0f)), 0.0f), 65535.0f);
+									zPass = depth_compare(d.depthCompareOp, (float)((const unsigned short *)smDepth)[pi], z);
+								}
+								else
+								{
+									const float zValue = smDepth[pi];
+									if(FS) zPass = d.depthCompareOp == CMP_LESS ? !(zValue <= z) : !(zValue < z); // LESS / LESS_OR_EQUAL (:533-553)
+									else zPass = depth_compare(d.depthCompareOp, zValue, z);
+								}
 							}
 							if(zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
 							{
-								if(d.depthWriteEnable) { smDepth[pi] = z; dirty = true; }
+								if(d.depthWriteEnable)
+								{
+									if(!FS && d.depth16) ((unsigned short *)smDepth)[pi] = (unsigned short)z;
+									else smDepth[pi] = z;
+									dirty = true;
+								}
 								if(colorOn)
 								{
 									const uint32_t px = smColor[pi];
@@ -1703,7 +1720,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 	else
 	{
 		if(colorOn) tile_copy<MS, uint32_t, true>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		if(d.depthWriteEnable) tile_copy<MS, float, true>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		if(d.depthWriteEnable && d.depth16) tile_copy<MS, unsigned short, true>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		else if(d.depthWriteEnable) tile_copy<MS, float, true>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 		if(d.stencilWrite) tile_copy<MS, unsigned char, true>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 	}
 }
@@ -1721,6 +1739,7 @@ __global__ void k_clear(unsigned char *base, int pitchB, int sliceB, int bpp, in
 	{
 		unsigned char *row = base + (size_t)q * sliceB + (size_t)(y0 + y) * pitchB;
 		if(bpp == 4) ((uint32_t *)row)[x0 + x] = value;
+		else if(bpp == 2) ((unsigned short *)row)[x0 + x] = (unsigned short)value;
 		else row[x0 + x] = (unsigned char)value;
 	}
 }

@@ -20,6 +20,7 @@ enum
 	VKF_R32G32_SFLOAT = 103,
 	VKF_R32G32B32_SFLOAT = 106,
 	VKF_R32G32B32A32_SFLOAT = 109,
+	VKF_D16_UNORM = 124,
 	VKF_D32_SFLOAT = 126,
 	VKF_S8_UINT = 127,
 };
@@ -153,6 +154,7 @@ struct DrawConst
 
 	// ---- pixel state (PixelProcessor.cpp:74-140, Context.cpp:1090-1312 folded) ----
 	uint32_t depthTestActive, depthWriteEnable, depthCompareOp;
+	uint32_t depth16; // D16_UNORM depth buffer: quantised compare / saturating write (PixelRoutine.cpp:466-482,508-511,687-711)
 	uint32_t stencilActive, stencilWrite;
 	KStencilFace front, back;
 	uint32_t blendEnable, srcF, dstF, op, srcFA, dstFA, opA; // op/opA are KOP_*

@@ -22,6 +22,7 @@ FMT_R8G8B8A8_UNORM = 37
 FMT_B8G8R8A8_UNORM = 44
 FMT_R32_SFLOAT, FMT_R32G32_SFLOAT, FMT_R32G32B32_SFLOAT, FMT_R32G32B32A32_SFLOAT = 100, 103, 106, 109
 FMT_D32_SFLOAT = 126
+FMT_D16_UNORM = 124
 FMT_S8_UINT = 127
 FLOAT_FORMATS = {1: FMT_R32_SFLOAT, 2: FMT_R32G32_SFLOAT, 3: FMT_R32G32B32_SFLOAT, 4: FMT_R32G32B32A32_SFLOAT}
 TOPO_TRIANGLE_LIST, TOPO_TRIANGLE_STRIP, TOPO_TRIANGLE_FAN = 3, 4, 5
@@ -147,6 +148,7 @@ class Scene:
     colorFormat: int = FMT_R8G8B8A8_UNORM
     hasDepth: bool = False
     hasStencil: bool = False
+    depthFormat: int = FMT_D32_SFLOAT  # or FMT_D16_UNORM (then no stencil)
     clearColor: tuple = (0.0, 0.0, 0.0, 0.0)
     clearDepth: float = 1.0
     clearStencil: int = 0
@@ -168,7 +170,12 @@ class Scene:
         H2, W, S = self.padded_height(), self.width, self.samples
         att = {"color": np.empty((S, H2, W, 4), dtype=np.uint8)}
         att["color"][:] = self.clear_color_bytes()
-        if self.hasDepth:
+        if self.hasDepth and self.depthFormat == FMT_D16_UNORM:
+            # D16 is not a fastClear format: the generic blit scales by 0xFFFF, clamps and stores UShort(RoundInt(x))
+            # (/root/reference/src/Device/Blitter.cpp:1085-1087), i.e. round-to-nearest-even
+            z16 = np.uint16(np.rint(np.float32(65535.0) * np.float32(min(max(self.clearDepth, 0.0), 1.0))))
+            att["depth"] = np.full((S, H2, W), z16, dtype=np.uint16)
+        elif self.hasDepth:
             att["depth"] = np.full((S, H2, W), self.clearDepth, dtype=np.float32)
         if self.hasStencil:
             att["stencil"] = np.full((S, H2, W), self.clearStencil & 0xFF, dtype=np.uint8)
@@ -236,7 +243,8 @@ class Scene:
         col = att["color"]
         d.color = capi.Attachment(col.ctypes.data, self.colorFormat, W * 4, H2 * W * 4, W, self.height, 0)
         if "depth" in att:
-            d.depth = capi.Attachment(att["depth"].ctypes.data, FMT_D32_SFLOAT, W * 4, H2 * W * 4, W, self.height, 0)
+            zb = att["depth"].dtype.itemsize
+            d.depth = capi.Attachment(att["depth"].ctypes.data, self.depthFormat, W * zb, H2 * W * zb, W, self.height, 0)
         if "stencil" in att:
             d.stencil = capi.Attachment(att["stencil"].ctypes.data, FMT_S8_UINT, W, H2 * W, W, self.height, 0)
         if draw.texture is not None:
@@ -301,7 +309,7 @@ class Scene:
                 r += struct.pack("<5I5I3f2I", 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0, 0)
             recs.append(r)
         hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 2, self.width, self.height, self.samples, self.colorFormat,
-                          int(self.hasDepth), int(self.hasStencil), *self.clearColor, self.clearDepth, self.clearStencil,
+                          (2 if self.depthFormat == FMT_D16_UNORM else 1) if self.hasDepth else 0, int(self.hasStencil), *self.clearColor, self.clearDepth, self.clearStencil,
                           len(recs), len(blobs))
         off = len(hdr) + sum(len(r) for r in recs) + 16 * len(blobs)
         table = b""
@@ -481,7 +489,8 @@ class Frame:
         if key == "color":
             return capi.Attachment(self.att["color"].ctypes.data, sc.colorFormat, W * 4, H2 * W * 4, W, sc.height, 0)
         if key == "depth":
-            return capi.Attachment(self.att["depth"].ctypes.data, FMT_D32_SFLOAT, W * 4, H2 * W * 4, W, sc.height, 0)
+            zb = self.att["depth"].dtype.itemsize
+            return capi.Attachment(self.att["depth"].ctypes.data, sc.depthFormat, W * zb, H2 * W * zb, W, sc.height, 0)
         if key == "stencil":
             return capi.Attachment(self.att["stencil"].ctypes.data, FMT_S8_UINT, W, H2 * W, W, sc.height, 0)
         return capi.Attachment(self.resolved.ctypes.data, sc.colorFormat, W * 4, H2 * W * 4, W, sc.height, 0)
@@ -494,7 +503,10 @@ class Frame:
         a = self._attachment("color")
         self.dev.check(self.dev.lib.swcu_clear(self.dev.ctx, C.byref(a), sc.samples, C.byref(area), col.ctypes.data))
         if "depth" in self.att:
-            z = np.array([sc.clearDepth], dtype=np.float32)
+            if sc.depthFormat == FMT_D16_UNORM:  # same value as the host-side clear of alloc_attachments
+                z = np.array([np.rint(np.float32(65535.0) * np.float32(min(max(sc.clearDepth, 0.0), 1.0)))], dtype=np.uint16)
+            else:
+                z = np.array([sc.clearDepth], dtype=np.float32)
             a = self._attachment("depth")
             self.dev.check(self.dev.lib.swcu_clear(self.dev.ctx, C.byref(a), sc.samples, C.byref(area), z.ctypes.data))
         if "stencil" in self.att:

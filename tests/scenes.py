@@ -115,6 +115,32 @@ def depth_ops(seed: int) -> Scene:
     return Scene(CELL, CELL, [d1, d2], hasDepth=True, clearDepth=0.6, clearColor=(0.1, 0.2, 0.3, 1.0))
 
 
+def depth16(seed: int) -> Scene:
+    """D16_UNORM depth buffer (PixelRoutine.cpp:466-482,508-511,687-711): the 8 compare ops on the quantised value, depth
+    write with saturating round, the fixed-point constant depth bias (r = 1.01 / 0xFFFF), 4x MSAA, dense overdraw."""
+    rng = np.random.default_rng(4500 + seed)
+    kw = dict(hasDepth=True, depthFormat=FMT_D16_UNORM, clearColor=(0.1, 0.2, 0.3, 1.0))
+    if seed < 8:
+        d1 = Draw(_layers(rng, 6), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, depthCompareOp=CMP_LESS_OR_EQUAL)
+        d2 = Draw(_layers(rng, 6), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=(seed % 3 != 0), depthCompareOp=seed % 8)
+        return Scene(CELL, CELL, [d1, d2], clearDepth=0.6, **kw)
+    if seed == 8:  # constant + slope bias, with and without clamp
+        d1 = Draw(_layers(rng, 5), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, depthBias=(3.0, 0.0, 1.5))
+        d2 = Draw(_layers(rng, 5), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, depthCompareOp=CMP_LESS, depthBias=(-40.0, -0.0004, 2.0))
+        return Scene(CELL, CELL, [d1, d2], clearDepth=1.0, **kw)
+    if seed == 9:  # 4x MSAA + blend
+        d = Draw(_layers(rng, 10), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, blend=True)
+        return Scene(CELL, CELL, [d], samples=4, clearDepth=1.0, **kw)
+    if seed == 10:  # many small triangles, binned path
+        tris = [_verts(rng, _tri_kind(rng, (1, 4, 5)[i % 3]), persp=(i % 3 == 0), colour=rng.uniform(0, 1, (3, 4))) for i in range(1200)]
+        d = Draw(np.concatenate(tris), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, depthCompareOp=CMP_LESS)
+        return Scene(128, 96, [d], clearDepth=1.0, **kw)
+    # z outside [0,1] through the viewport depth range: clamped before the quantisation
+    d = Draw(_layers(rng, 8), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, depthCompareOp=CMP_GREATER,
+             viewport=(0.0, 0.0, float(CELL), float(CELL), -0.25, 1.5))
+    return Scene(CELL, CELL, [d], clearDepth=0.0, **kw)
+
+
 _BLEND_MATRIX = [
     (BF_SRC_ALPHA, BF_ONE_MINUS_SRC_ALPHA, BOP_ADD, BF_ONE, BF_ZERO, BOP_ADD),
     (BF_ONE, BF_ONE, BOP_ADD, BF_ONE, BF_ONE, BOP_ADD),
@@ -335,6 +361,7 @@ FAMILIES = {
     "topology": (topology, 12),
     "scissor": (scissor, 8),
     "overdraw": (overdraw, 7),
+    "depth16": (depth16, 12),
 }
 
 

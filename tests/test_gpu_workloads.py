@@ -97,6 +97,27 @@ def test_device_clear_and_resolve_match_oracle(device):
     assert np.array_equal(got["resolved"][0], swref.resolve_oracle(sc, want))
 
 
+def test_d16_device_clear_and_unaligned_pitch(device):
+    """D16_UNORM: the device-side clear (2-byte fill) and a framebuffer whose row pitch does not satisfy the tensor-map rules
+    (cooperative 16-bit tile copies instead of TMA), both against the oracle."""
+    for sc in (scenes.depth16(0), scenes.depth16(8)):
+        got = _render_frame(device, sc)
+        want = swref.render_oracle(sc)
+        for k in want:
+            assert np.array_equal(got[k].view(np.uint8), want[k].view(np.uint8)), k
+    base = scenes.depth16(10)
+    sc = scenes.Scene(100, 70, base.draws, hasDepth=True, depthFormat=scenes.FMT_D16_UNORM, clearDepth=1.0, clearColor=(0.1, 0.2, 0.3, 1.0))
+    for binned in (0, 1):
+        device.set_option("force_binned", binned)
+        try:
+            got = _render_frame(device, sc)
+        finally:
+            device.set_option("force_binned", 0)
+        want = swref.render_oracle(sc)
+        for k in want:
+            assert np.array_equal(got[k].view(np.uint8), want[k].view(np.uint8)), (k, binned)
+
+
 def test_unsupported_state_is_a_hard_error(device):
     from swiftshader_b200 import capi
     sc = scenes.benchmark(1, 64, 64)
