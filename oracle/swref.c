@@ -30,7 +30,9 @@ enum
 {
 	FMT_UNDEFINED = 0,
 	FMT_R8G8B8A8_UNORM = 37,
+	FMT_R8G8B8A8_SRGB = 43,
 	FMT_B8G8R8A8_UNORM = 44,
+	FMT_B8G8R8A8_SRGB = 50,
 	FMT_R32_SFLOAT = 100,
 	FMT_R32G32_SFLOAT = 103,
 	FMT_R32G32B32_SFLOAT = 106,
@@ -690,6 +692,45 @@ static uint8_t stencil_op(int op, uint8_t v, uint8_t ref)
 	}
 }
 
+/* Pow<Mediump> = Exp2(y * Log2(x)) with the relaxed-precision polynomials of ShaderCore.cpp:352-382 (Exp2), :412-436 (Log2),
+ * :472-477 (Pow); MulAdd is an FMA on every AVX2 host, Float(Int) is cvtdq2ps, Int(Float) truncates. */
+static float log2_mediump(float x)
+{
+	int32_t im = (int32_t)as_uint(x);
+	float y = fmaf((float)im, 1.0f / (1 << 23), -127.0f);
+	if(im == 0x7F800000) y = as_float(as_uint(y) | 0x7F800000u);
+	float m = (float)(im & 0x007FFFFF);
+	const float a = 2.8017103e-22f, b = -8.373131e-15f, c = 5.0615534e-8f;
+	float f = fmaf(fmaf(a, m, b), m, c);
+	return fmaf(f, m, y);
+}
+static float exp2_mediump(float x)
+{
+	float x0 = sse_min(x, 128.0f);
+	x0 = sse_max(x0, as_float(0xC2FDFFFFu));
+	float xi = floorf(x0);
+	float f = x0 - xi;
+	const float a = 7.8145574e-2f, b = 2.2617357e-1f, c = -3.0444314e-1f;
+	float r = fmaf(fmaf(a, f, b), f, c);
+	float y = fmaf(r, f, x0);
+	int32_t i = trunc_int(fmaf((float)(1 << 23), y, (float)(127 << 23)));
+	return as_float((uint32_t)i);
+}
+static float pow_mediump(float x, float y) { return exp2_mediump(log2_mediump(x) * y); }
+/* ShaderCore.cpp:673-689 */
+static float linear_to_srgb(float c)
+{
+	float lc = c * 12.92f;
+	float ec = fmaf(1.055f, pow_mediump(c, 1.0f / 2.4f), -0.055f);
+	return c < 0.0031308f ? lc : ec;
+}
+static float srgb_to_linear(float c)
+{
+	float lc = c * (1.0f / 12.92f);
+	float ec = pow_mediump(fmaf(c, 1.0f / 1.055f, 0.055f / 1.055f), 2.4f);
+	return c < 0.04045f ? lc : ec;
+}
+
 static float blend_factor(const Draw *dr, int f, int ch, const float s[4], const float dst[4])
 {
 	/* PixelRoutine.cpp:1225-1393; ch 0..2 = RGB path, 3 = alpha path */
@@ -776,7 +817,8 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 	const int ms = dr->ms;
 	int yMin = prim->yMin & ~1; /* clusterCount = 1: QuadRasterizer.cpp:46-49 */
 	const int yMax = prim->yMax;
-	const int bgr = d->color.format == FMT_B8G8R8A8_UNORM;
+	const int bgr = d->color.format == FMT_B8G8R8A8_UNORM || d->color.format == FMT_B8G8R8A8_SRGB;
+	const int srgb = d->color.format == FMT_R8G8B8A8_SRGB || d->color.format == FMT_B8G8R8A8_SRGB;
 
 	for(int y = yMin; y < yMax; y += 2)
 	{
@@ -1006,6 +1048,7 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 								{
 									uint8_t b = px[bgr && ch < 3 ? 2 - ch : ch];
 									dst[ch] = (float)(uint16_t)(b * 257) * (1.0f / 0xFFFF);
+									if(srgb && ch < 3) dst[ch] = srgb_to_linear(dst[ch]); /* :1821-1826 */
 								}
 								for(int ch = 0; ch < 3; ch++)
 								{
@@ -1020,6 +1063,8 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 								}
 							}
 							else memcpy(out, c[i], sizeof(out));
+							if(srgb) /* writeColor :1965-1970 */
+								for(int ch = 0; ch < 3; ch++) out[ch] = linear_to_srgb(out[ch]);
 							for(int ch = 0; ch < 4; ch++)
 							{
 								if(!((dr->colorWriteMask >> ch) & 1)) continue;
@@ -1103,7 +1148,10 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 {
 	if(!d || d->structSize != sizeof(swcu_draw_desc) || !vs || !fs) return SWCU_E_INVALID;
 	if(d->sampleCount != 1 && d->sampleCount != 4) return SWCU_E_UNSUPPORTED;
-	if(d->color.buffer && d->color.format != FMT_R8G8B8A8_UNORM && d->color.format != FMT_B8G8R8A8_UNORM) return SWCU_E_UNSUPPORTED;
+	if(d->color.buffer && d->color.format != FMT_R8G8B8A8_UNORM && d->color.format != FMT_B8G8R8A8_UNORM &&
+	   d->color.format != FMT_R8G8B8A8_SRGB && d->color.format != FMT_B8G8R8A8_SRGB) return SWCU_E_UNSUPPORTED;
+	if(d->color.buffer && (d->color.format == FMT_R8G8B8A8_SRGB || d->color.format == FMT_B8G8R8A8_SRGB) && d->sampleCount > 1)
+		return SWCU_E_UNSUPPORTED; /* the sRGB resolve is not Blitter::fastResolve: outside the subset */
 	if(d->depth.buffer && d->depth.format != FMT_D32_SFLOAT && d->depth.format != FMT_D16_UNORM) return SWCU_E_UNSUPPORTED;
 	if(d->depth.buffer && d->depth.format == FMT_D16_UNORM && d->stencil.buffer) return SWCU_E_UNSUPPORTED; /* D16_UNORM_S8_UINT: not in the subset */
 

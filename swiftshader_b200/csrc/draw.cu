@@ -483,8 +483,10 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	if(desc->sampleCount != 1 && desc->sampleCount != 4) return fail(ctx, SWCU_E_UNSUPPORTED, "sample count %u unsupported (1 or 4)", desc->sampleCount);
 	if(desc->indexType != 0 && desc->indexType != 2 && desc->indexType != 4) return fail(ctx, SWCU_E_UNSUPPORTED, "index type %u unsupported", desc->indexType);
 	if(desc->provokingVertexMode > 1) return fail(ctx, SWCU_E_INVALID, "bad provoking vertex mode");
-	if(desc->color.buffer && desc->color.format != VKF_R8G8B8A8_UNORM && desc->color.format != VKF_B8G8R8A8_UNORM)
-		return fail(ctx, SWCU_E_UNSUPPORTED, "colour format %u unsupported (R8G8B8A8_UNORM, B8G8R8A8_UNORM)", desc->color.format);
+	const bool srgbTarget = desc->color.buffer && (desc->color.format == VKF_R8G8B8A8_SRGB || desc->color.format == VKF_B8G8R8A8_SRGB);
+	if(srgbTarget && desc->sampleCount > 1) return fail(ctx, SWCU_E_UNSUPPORTED, "multisampled sRGB colour targets are outside the subset (their resolve is not Blitter::fastResolve)");
+	if(desc->color.buffer && !srgbTarget && desc->color.format != VKF_R8G8B8A8_UNORM && desc->color.format != VKF_B8G8R8A8_UNORM)
+		return fail(ctx, SWCU_E_UNSUPPORTED, "colour format %u unsupported (R8G8B8A8 / B8G8R8A8, UNORM or SRGB)", desc->color.format);
 	if(desc->depth.buffer && desc->depth.format != VKF_D32_SFLOAT && desc->depth.format != VKF_D16_UNORM)
 		return fail(ctx, SWCU_E_UNSUPPORTED, "depth format %u unsupported (D32_SFLOAT, D16_UNORM)", desc->depth.format);
 	if(desc->depth.buffer && desc->depth.format == VKF_D16_UNORM && desc->stencil.buffer)
@@ -657,7 +659,8 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 			d.dstFA = (uint32_t)fold_blend_factor((int)desc->alphaBlendOp, (int)desc->dstAlphaBlendFactor);
 		}
 		for(int k = 0; k < 4; k++) d.blendConstant[k] = clamp01(desc->blendConstants[k]);
-		d.bgr = desc->color.format == VKF_B8G8R8A8_UNORM;
+		d.bgr = desc->color.format == VKF_B8G8R8A8_UNORM || desc->color.format == VKF_B8G8R8A8_SRGB;
+		d.srgb = srgbTarget ? 1u : 0u;
 		d.blendClass = !d.blendEnable ? BL_OFF : ((d.srcF == BF_SRC_ALPHA && d.dstF == BF_ONE_MINUS_SRC_ALPHA && d.op == KOP_ADD && d.opA == KOP_SRC && d.colorWriteMask == 0xF) ? BL_SRC_ALPHA : BL_GENERIC);
 	}
 
@@ -760,7 +763,7 @@ static void launch_tile4(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps
 static bool fast_state(const swcu_ctx *ctx, const DrawConst &d)
 {
 	if(!ctx->optFastState) return false;
-	if(d.stencilActive || d.stencilWrite || !d.colorBuf || d.colorWriteMask != 0xFu || d.bgr || d.depthBiasEnable || d.depth16) return false;
+	if(d.stencilActive || d.stencilWrite || !d.colorBuf || d.colorWriteMask != 0xFu || d.bgr || d.srgb || d.depthBiasEnable || d.depth16) return false;
 	if(d.depthTestActive && d.depthCompareOp != CMP_LESS && d.depthCompareOp != CMP_LESS_OR_EQUAL) return false;
 	if(d.ms == 4 && (d.sampleMask & 0xFu) != 0xFu) return false;
 	if(d.blendClass == BL_GENERIC || d.shaderClass == SH_GENERIC) return false;
@@ -1057,7 +1060,7 @@ extern "C" int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t sa
 	int bpp;
 	switch(att->format)
 	{
-	case VKF_R8G8B8A8_UNORM: case VKF_B8G8R8A8_UNORM: case VKF_D32_SFLOAT: bpp = 4; break;
+	case VKF_R8G8B8A8_UNORM: case VKF_B8G8R8A8_UNORM: case VKF_R8G8B8A8_SRGB: case VKF_B8G8R8A8_SRGB: case VKF_D32_SFLOAT: bpp = 4; break;
 	case VKF_D16_UNORM: bpp = 2; break;
 	case VKF_S8_UINT: bpp = 1; break;
 	default: return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_clear: format %u unsupported", att->format);

@@ -995,6 +995,40 @@ DEVI float blend_factor_a(const DrawConst &d, uint32_t f, const float s[4], cons
 	return 0.0f;
 }
 
+// sRGB colour targets.  Pow<Mediump> = Exp2(y * Log2(x)) with the relaxed-precision polynomials of ShaderCore.cpp:352-382 (Exp2),
+// :412-436 (Log2), :472-477 (Pow); MulAdd is an FMA, Float(Int) rounds to nearest, Int(Float) truncates.
+DEVI float log2_mediump(float x)
+{
+	const int im = (int)__float_as_uint(x);
+	float y = __fmaf_rn((float)im, 1.0f / (1 << 23), -127.0f);
+	if(im == 0x7F800000) y = __uint_as_float(__float_as_uint(y) | 0x7F800000u);
+	const float m = (float)(im & 0x007FFFFF);
+	const float f = __fmaf_rn(__fmaf_rn(2.8017103e-22f, m, -8.373131e-15f), m, 5.0615534e-8f);
+	return __fmaf_rn(f, m, y);
+}
+DEVI float exp2_mediump(float x)
+{
+	float x0 = sse_min(x, 128.0f);
+	x0 = sse_max(x0, __uint_as_float(0xC2FDFFFFu));
+	const float f = fsub(x0, floorf(x0));
+	const float r = __fmaf_rn(__fmaf_rn(7.8145574e-2f, f, 2.2617357e-1f), f, -3.0444314e-1f);
+	const float y = __fmaf_rn(r, f, x0);
+	return __uint_as_float((uint32_t)trunc_int(__fmaf_rn((float)(1 << 23), y, (float)(127 << 23))));
+}
+DEVI float pow_mediump(float x, float y) { return exp2_mediump(fmul(log2_mediump(x), y)); }
+DEVI float linear_to_srgb(float c) // ShaderCore.cpp:673-680
+{
+	const float lc = fmul(c, 12.92f);
+	const float ec = __fmaf_rn(1.055f, pow_mediump(c, 1.0f / 2.4f), -0.055f);
+	return c < 0.0031308f ? lc : ec;
+}
+DEVI float srgb_to_linear(float c) // ShaderCore.cpp:682-689
+{
+	const float lc = fmul(c, 1.0f / 12.92f);
+	const float ec = pow_mediump(__fmaf_rn(c, 1.0f / 1.055f, 0.055f / 1.055f), 2.4f);
+	return c < 0.04045f ? lc : ec;
+}
+
 DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1849-1958
 {
 	switch(op)
@@ -1654,6 +1688,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 										{
 											const uint32_t byte = (bgr && ch < 3) ? 2 - ch : ch;
 											dst[ch] = fmul((float)__byte_perm(px, 0, 0x4400u | byte | (byte << 4)), 1.0f / 0xFFFF); // b * 257 == b << 8 | b
+											if(!FS && d.srgb && ch < 3) dst[ch] = srgb_to_linear(dst[ch]);
 										}
 										if(BL == BL_SRC_ALPHA)
 										{
@@ -1668,6 +1703,11 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 												o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
 											o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
 										}
+									}
+									if(!FS && d.srgb)
+									{
+#pragma unroll
+										for(int ch = 0; ch < 3; ch++) o[ch] = linear_to_srgb(o[ch]);
 									}
 									const uint32_t pk = bgr ? pack_unorm8(o[2], o[1], o[0], o[3]) : pack_unorm8(o[0], o[1], o[2], o[3]);
 									smColor[pi] = (px & ~wmask32) | (pk & wmask32);

@@ -15,7 +15,9 @@ enum
 {
 	VKF_UNDEFINED = 0,
 	VKF_R8G8B8A8_UNORM = 37,
+	VKF_R8G8B8A8_SRGB = 43,
 	VKF_B8G8R8A8_UNORM = 44,
+	VKF_B8G8R8A8_SRGB = 50,
 	VKF_R32_SFLOAT = 100,
 	VKF_R32G32_SFLOAT = 103,
 	VKF_R32G32B32_SFLOAT = 106,
@@ -161,6 +163,7 @@ struct DrawConst
 	uint32_t colorWriteMask;
 	float blendConstant[4]; // clamped to [0,1] (UNORM target)
 	uint32_t bgr;
+	uint32_t srgb; // sRGB colour target: encode before the pack, decode the destination when blending (PixelRoutine.cpp:1821-1826,1965-1970)
 
 	// ---- attachments (device addresses) ----
 	unsigned char *colorBuf, *depthBuf, *stencilBuf;

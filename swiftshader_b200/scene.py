@@ -21,6 +21,8 @@ from . import capi, spirv
 FMT_R8G8B8A8_UNORM = 37
 FMT_B8G8R8A8_UNORM = 44
 FMT_R32_SFLOAT, FMT_R32G32_SFLOAT, FMT_R32G32B32_SFLOAT, FMT_R32G32B32A32_SFLOAT = 100, 103, 106, 109
+FMT_R8G8B8A8_SRGB = 43
+FMT_B8G8R8A8_SRGB = 50
 FMT_D32_SFLOAT = 126
 FMT_D16_UNORM = 124
 FMT_S8_UINT = 127
@@ -162,8 +164,8 @@ class Scene:
         (/root/reference/src/Device/Blitter.cpp:217-229)."""
         c = np.clip(np.array(self.clearColor, dtype=np.float32), 0, 1)
         b = (np.float32(255.0) * c + np.float32(0.5)).astype(np.float32).astype(np.uint32).astype(np.uint8)
-        if self.colorFormat == FMT_B8G8R8A8_UNORM:
-            b = b[[2, 1, 0, 3]]
+        if self.colorFormat in (FMT_B8G8R8A8_UNORM, FMT_B8G8R8A8_SRGB):
+            b = b[[2, 1, 0, 3]]  # (sRGB targets: use clear colours of 0 / 1 only — the clear's own sRGB encode is not restated here)
         return b
 
     def alloc_attachments(self) -> dict:

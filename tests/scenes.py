@@ -141,6 +141,36 @@ def depth16(seed: int) -> Scene:
     return Scene(CELL, CELL, [d], clearDepth=0.0, **kw)
 
 
+def srgb(seed: int) -> Scene:
+    """sRGB render targets (R8G8B8A8_SRGB / B8G8R8A8_SRGB): linearToSRGB before the UNORM8 pack (PixelRoutine.cpp:1965-1970),
+    sRGBtoLinear of the destination when blending (:1821-1826), both through the relaxed-precision Pow of ShaderCore.cpp.
+    Clear colours are 0 / 1 only (their encoding is the identity)."""
+    rng = np.random.default_rng(4800 + seed)
+    fmt = FMT_B8G8R8A8_SRGB if seed % 3 == 2 else FMT_R8G8B8A8_SRGB
+    clear = [(0.0, 0.0, 0.0, 1.0), (1.0, 1.0, 1.0, 0.0), (0.0, 1.0, 0.0, 1.0), (1.0, 0.0, 1.0, 1.0)][seed % 4]
+    if seed < 4:  # opaque varying colours: every 8-bit output level of the encode gets hit
+        d = Draw(_layers(rng, 8), P4C4, "vs_pos4_col4", "fs_col4", depthTest=(seed % 2 == 1), depthWrite=(seed % 2 == 1))
+        return Scene(CELL, CELL, [d], colorFormat=fmt, clearColor=clear, hasDepth=(seed % 2 == 1))
+    if seed < 12:  # blending: decode of the destination, blend in linear space, encode
+        (sc, dc, co, sa, da, ao) = _BLEND_MATRIX[(seed * 5) % len(_BLEND_MATRIX)]
+        d = Draw(_layers(rng, 8), P4C4, "vs_pos4_col4", "fs_col4", blend=True, srcColor=sc, dstColor=dc, colorOp=co,
+                 srcAlpha=sa, dstAlpha=da, alphaOp=ao, colorWriteMask=(0xF if seed % 4 else 0xB), blendConstants=(0.25, 0.5, 0.75, 0.4))
+        return Scene(CELL, CELL, [d], colorFormat=fmt, clearColor=clear)
+    if seed == 12:  # textured
+        tex = Texture(_rand_tex(rng, 64, 64, 7), maxLod=6.0)
+        tris = []
+        for i in range(4):
+            col = np.zeros((3, 4))
+            col[:, :2] = rng.uniform(-2, 3, (3, 2))
+            tris.append(_verts(rng, _tri_kind(rng, [5, 0, 1, 5][i]), persp=(i % 2 == 0), colour=col))
+        d = Draw(np.concatenate(tris), P4C4, "vs_pos4_col4", "fs_tex_col4", texture=tex)
+        return Scene(CELL, CELL, [d], colorFormat=fmt, clearColor=clear)
+    # dense overdraw with SRC_ALPHA blending, binned path
+    tris = [_verts(rng, _tri_kind(rng, (1, 4, 5)[i % 3]), persp=(i % 3 == 0), colour=rng.uniform(0, 1, (3, 4))) for i in range(1500)]
+    d = Draw(np.concatenate(tris), P4C4, "vs_pos4_col4", "fs_col4", blend=True)
+    return Scene(128, 96, [d], colorFormat=fmt, clearColor=clear)
+
+
 _BLEND_MATRIX = [
     (BF_SRC_ALPHA, BF_ONE_MINUS_SRC_ALPHA, BOP_ADD, BF_ONE, BF_ZERO, BOP_ADD),
     (BF_ONE, BF_ONE, BOP_ADD, BF_ONE, BF_ONE, BOP_ADD),
@@ -362,6 +392,7 @@ FAMILIES = {
     "scissor": (scissor, 8),
     "overdraw": (overdraw, 7),
     "depth16": (depth16, 12),
+    "srgb": (srgb, 14),
 }
 
 
