@@ -234,7 +234,7 @@ int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc); /* replaces DrawCall::
 int swcu_sync(swcu_ctx *ctx);                             /* replaces Renderer::synchronize (Renderer.cpp:664-671) */
 
 /* ---- the steps either side of the draw, on the resident shadows ---- */
-/* Blitter::fastClear (src/Device/Blitter.cpp:170-325) for RGBA8 / D32F / S8 (and the 2-byte fill of a D16 clear): fills `samples` slices. */
+/* Blitter::fastClear (src/Device/Blitter.cpp:170-325) for RGBA8 / D32F / S8 (and the 2 / 8 / 16-byte fills of D16, RGBA16F, RGBA32F clears): fills `samples` slices. */
 int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t samples, const swcu_rect *area, const void *value /* 4 bytes (1 for S8) */);
 /* Blitter::fastResolve (Blitter.cpp:2079-2205): 4x RGBA8 -> 1x, avg(avg(s0,s1),avg(s2,s3)) with (a+b+1)>>1. */
 int swcu_resolve(swcu_ctx *ctx, const swcu_attachment *src, uint32_t samples, const swcu_attachment *dst);

@@ -418,7 +418,8 @@ int main(int argc, char **argv)
 	// ---- readback buffers ----
 	VkBuffer rbC, rbD = VK_NULL_HANDLE, rbS = VK_NULL_HANDLE;
 	void *pC, *pD = nullptr, *pS = nullptr;
-	mkBuffer((size_t)W * H * 4, VK_BUFFER_USAGE_TRANSFER_DST_BIT, rbC, pC);
+	const size_t colorBpp = cfmt == VK_FORMAT_R32G32B32A32_SFLOAT ? 16 : (cfmt == VK_FORMAT_R16G16B16A16_SFLOAT ? 8 : 4);
+	mkBuffer((size_t)W * H * colorBpp, VK_BUFFER_USAGE_TRANSFER_DST_BIT, rbC, pC);
 	const bool readDS = hasDS && !ms;
 	if(readDS && hdr->hasDepth) mkBuffer((size_t)W * H * depthBpp, VK_BUFFER_USAGE_TRANSFER_DST_BIT, rbD, pD);
 	if(readDS && hdr->hasStencil) mkBuffer((size_t)W * H, VK_BUFFER_USAGE_TRANSFER_DST_BIT, rbS, pS);
@@ -472,7 +473,7 @@ int main(int argc, char **argv)
 	if(!fo) { perror("out"); return 1; }
 	uint32_t oh[6] = { 0x4F525753u /* SWRO */, W, H, (uint32_t)(rbD != VK_NULL_HANDLE ? (d16 ? 2 : 1) : 0), (uint32_t)(rbS != VK_NULL_HANDLE), hdr->samples };
 	fwrite(oh, 4, 6, fo);
-	fwrite(pC, 1, (size_t)W * H * 4, fo);
+	fwrite(pC, 1, (size_t)W * H * colorBpp, fo);
 	if(rbD) fwrite(pD, 1, (size_t)W * H * depthBpp, fo);
 	if(rbS) fwrite(pS, 1, (size_t)W * H, fo);
 	fclose(fo);

@@ -33,6 +33,7 @@ enum
 	FMT_R8G8B8A8_SRGB = 43,
 	FMT_B8G8R8A8_UNORM = 44,
 	FMT_B8G8R8A8_SRGB = 50,
+	FMT_R16G16B16A16_SFLOAT = 97,
 	FMT_R32_SFLOAT = 100,
 	FMT_R32G32_SFLOAT = 103,
 	FMT_R32G32B32_SFLOAT = 106,
@@ -114,6 +115,7 @@ typedef struct
 	int blendEnable, srcF, dstF, op, srcFA, dstFA, opA;
 	int colorWriteMask;
 	int depthTestActive, depthWriteEnable, stencilActive;
+	int floatTarget, colorBpp; /* R32G32B32A32_SFLOAT / R16G16B16A16_SFLOAT colour attachment; bytes per pixel */
 	int numVaryings; /* packed interpolants = set bits of fs->inputMask */
 	int interpolateZ, interpolateW;
 } Draw;
@@ -731,10 +733,46 @@ static float srgb_to_linear(float c)
 	return c < 0.04045f ? lc : ec;
 }
 
+/* Reactor's scalar Half <-> Float conversions (Reactor.cpp:3744-3770, :3787-3815): round-to-nearest-even on the way down with
+ * everything above 0x47FFEFFF (incl. NaN) becoming 0x7FFF; on the way up exponent 31 is NOT special (it decodes to 2^16 * 1.m). */
+static uint16_t float_to_half(float f)
+{
+	uint32_t fp32i = as_uint(f), a = fp32i & 0x7FFFFFFFu;
+	uint16_t h = (uint16_t)((fp32i & 0x80000000u) >> 16);
+	if(a > 0x47FFEFFFu) h |= 0x7FFF;
+	else if(a < 0x38800000u)
+	{
+		int32_t mantissa = (int32_t)((a & 0x007FFFFFu) | 0x00800000u);
+		int32_t e = 113 - (int32_t)(a >> 23);
+		a = e < 24 ? (uint32_t)(mantissa >> e) : 0u;
+		h |= (uint16_t)((a + 0x00000FFFu + ((a >> 13) & 1u)) >> 13);
+	}
+	else h |= (uint16_t)((a + 0xC8000000u + 0x00000FFFu + ((a >> 13) & 1u)) >> 13);
+	return h;
+}
+static float half_to_float(uint16_t h)
+{
+	int32_t sgn = (h >> 15) & 1, e = (h >> 10) & 0x1F, m = h & 0x3FF;
+	uint32_t fp32i = (uint32_t)sgn << 31;
+	if(e == 0)
+	{
+		if(m != 0)
+		{
+			while((m & 0x400) == 0) { m <<= 1; e -= 1; }
+			fp32i |= (uint32_t)(((e + (127 - 15) + 1) << 23) | ((m & ~0x400) << 13));
+		}
+	}
+	else fp32i |= (uint32_t)(((e + (127 - 15)) << 23) | (m << 13));
+	return as_float(fp32i);
+}
+
 static float blend_factor(const Draw *dr, int f, int ch, const float s[4], const float dst[4])
 {
 	/* PixelRoutine.cpp:1225-1393; ch 0..2 = RGB path, 3 = alpha path */
-	const float *bc = dr->d->blendConstants;
+	/* blend constants: PixelProcessor::setBlendConstant keeps a [0,1]-clamped copy for UNORM targets (blendConstantU) and the
+	 * raw one for floating-point targets (blendConstantF), PixelRoutine.cpp:1203-1223 */
+	float bc[4];
+	for(int k = 0; k < 4; k++) bc[k] = dr->floatTarget ? dr->d->blendConstants[k] : sse_min(sse_max(dr->d->blendConstants[k], 0.0f), 1.0f);
 	float r;
 	if(ch < 3)
 	{
@@ -751,11 +789,10 @@ static float blend_factor(const Draw *dr, int f, int ch, const float s[4], const
 		case BF_DST_ALPHA: return dst[3];
 		case BF_ONE_MINUS_DST_ALPHA: return 1.0f - dst[3];
 		case BF_SRC_ALPHA_SATURATE: r = 1.0f - dst[3]; return sse_min(r, s[3]);
-		/* blend constants: Renderer.cpp / PixelProcessor::setBlendConstant clamps to [0,1] for UNORM (blendConstantU) */
-		case BF_CONSTANT_COLOR: return sse_min(sse_max(bc[ch], 0.0f), 1.0f);
-		case BF_CONSTANT_ALPHA: return sse_min(sse_max(bc[3], 0.0f), 1.0f);
-		case BF_ONE_MINUS_CONSTANT_COLOR: return 1.0f - sse_min(sse_max(bc[ch], 0.0f), 1.0f);
-		case BF_ONE_MINUS_CONSTANT_ALPHA: return 1.0f - sse_min(sse_max(bc[3], 0.0f), 1.0f);
+		case BF_CONSTANT_COLOR: return bc[ch];
+		case BF_CONSTANT_ALPHA: return bc[3];
+		case BF_ONE_MINUS_CONSTANT_COLOR: return 1.0f - bc[ch];
+		case BF_ONE_MINUS_CONSTANT_ALPHA: return 1.0f - bc[3];
 		}
 		return 0.0f;
 	}
@@ -768,8 +805,8 @@ static float blend_factor(const Draw *dr, int f, int ch, const float s[4], const
 	case BF_DST_COLOR: case BF_DST_ALPHA: return dst[3];
 	case BF_ONE_MINUS_DST_COLOR: case BF_ONE_MINUS_DST_ALPHA: return 1.0f - dst[3];
 	case BF_SRC_ALPHA_SATURATE: return 1.0f;
-	case BF_CONSTANT_COLOR: case BF_CONSTANT_ALPHA: return sse_min(sse_max(bc[3], 0.0f), 1.0f);
-	case BF_ONE_MINUS_CONSTANT_COLOR: case BF_ONE_MINUS_CONSTANT_ALPHA: return 1.0f - sse_min(sse_max(bc[3], 0.0f), 1.0f);
+	case BF_CONSTANT_COLOR: case BF_CONSTANT_ALPHA: return bc[3];
+	case BF_ONE_MINUS_CONSTANT_COLOR: case BF_ONE_MINUS_CONSTANT_ALPHA: return 1.0f - bc[3];
 	}
 	return 0.0f;
 }
@@ -790,7 +827,7 @@ static float blend_op(int op, float s, float sf, float dd, float df)
 }
 
 /* Context.cpp:1165-1270 */
-static int fold_blend_op(int op, int sf, int df)
+static int fold_blend_op(int op, int sf, int df, int unorm)
 {
 	switch(op)
 	{
@@ -799,12 +836,12 @@ static int fold_blend_op(int op, int sf, int df)
 		else if(sf == BF_ONE) { if(df == BF_ZERO) return BOP_SRC_EXT; }
 		break;
 	case BOP_SUBTRACT:
-		if(sf == BF_ZERO) return BOP_ZERO_EXT; /* ZERO,ZERO or negative clamped to zero (UNORM) */
+		if(sf == BF_ZERO) { if(df == BF_ZERO || unorm) return BOP_ZERO_EXT; } /* ZERO,ZERO; or negative, clamped to zero (UNORM only) */
 		else if(sf == BF_ONE) { if(df == BF_ZERO) return BOP_SRC_EXT; }
 		break;
 	case BOP_REVERSE_SUBTRACT:
 		if(sf == BF_ZERO) { if(df == BF_ZERO) return BOP_ZERO_EXT; if(df == BF_ONE) return BOP_DST_EXT; }
-		else { if(df == BF_ZERO) return BOP_ZERO_EXT; }
+		else { if(df == BF_ZERO && unorm) return BOP_ZERO_EXT; }
 		break;
 	}
 	return op;
@@ -958,8 +995,8 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 					else if(o->kind == SWCU_SRC_CONST) val = as_float(o->value);
 					else if(o->kind == SWCU_SRC_TEXEL) val = texel[i][o->value];
 					else val = in[o->value][i];
-					/* PixelProgram::clampColor :286-364 (UNORM targets) */
-					c[i][ch] = sse_min(sse_max(val, 0.0f), 1.0f);
+					/* PixelProgram::clampColor :286-364: UNORM targets only, "if the color attachment is floating-point, no clamping occurs" */
+					c[i][ch] = dr->floatTarget ? val : sse_min(sse_max(val, 0.0f), 1.0f);
 				}
 
 			/* depth test :494-574 (late) */
@@ -1038,7 +1075,7 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 						for(int i = 0; i < 4; i++)
 						{
 							if(!(xMask & (1 << i))) continue;
-							uint8_t *px = cb + (size_t)(y + (i >> 1)) * d->color.pitchB + 4 * (size_t)(x + (i & 1));
+							uint8_t *px = cb + (size_t)(y + (i >> 1)) * d->color.pitchB + (size_t)dr->colorBpp * (size_t)(x + (i & 1));
 							float out[4];
 							if(dr->blendEnable)
 							{
@@ -1046,6 +1083,8 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 								float dst[4];
 								for(int ch = 0; ch < 4; ch++)
 								{
+									if(d->color.format == FMT_R32G32B32A32_SFLOAT) { dst[ch] = ((const float *)px)[ch]; continue; }  /* :1700-1710 */
+									if(d->color.format == FMT_R16G16B16A16_SFLOAT) { dst[ch] = half_to_float(((const uint16_t *)px)[ch]); continue; } /* :1782-1801 */
 									uint8_t b = px[bgr && ch < 3 ? 2 - ch : ch];
 									dst[ch] = (float)(uint16_t)(b * 257) * (1.0f / 0xFFFF);
 									if(srgb && ch < 3) dst[ch] = srgb_to_linear(dst[ch]); /* :1821-1826 */
@@ -1068,6 +1107,8 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 							for(int ch = 0; ch < 4; ch++)
 							{
 								if(!((dr->colorWriteMask >> ch) & 1)) continue;
+								if(d->color.format == FMT_R32G32B32A32_SFLOAT) { ((float *)px)[ch] = out[ch]; continue; }                 /* :2429-2447: bits stored as they are */
+								if(d->color.format == FMT_R16G16B16A16_SFLOAT) { ((uint16_t *)px)[ch] = float_to_half(out[ch]); continue; } /* :2504-2540 */
 								float cl = sse_min(sse_max(out[ch], 0.0f), 1.0f);
 								int v = round_int(cl * 255.0f);
 								v = v < 0 ? 0 : (v > 255 ? 255 : v); /* PackUnsigned saturation */
@@ -1148,8 +1189,10 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 {
 	if(!d || d->structSize != sizeof(swcu_draw_desc) || !vs || !fs) return SWCU_E_INVALID;
 	if(d->sampleCount != 1 && d->sampleCount != 4) return SWCU_E_UNSUPPORTED;
-	if(d->color.buffer && d->color.format != FMT_R8G8B8A8_UNORM && d->color.format != FMT_B8G8R8A8_UNORM &&
+	const int floatTarget = d->color.buffer && (d->color.format == FMT_R32G32B32A32_SFLOAT || d->color.format == FMT_R16G16B16A16_SFLOAT);
+	if(d->color.buffer && !floatTarget && d->color.format != FMT_R8G8B8A8_UNORM && d->color.format != FMT_B8G8R8A8_UNORM &&
 	   d->color.format != FMT_R8G8B8A8_SRGB && d->color.format != FMT_B8G8R8A8_SRGB) return SWCU_E_UNSUPPORTED;
+	if(floatTarget && d->sampleCount > 1) return SWCU_E_UNSUPPORTED; /* no Blitter::fastResolve for float formats: outside the subset */
 	if(d->color.buffer && (d->color.format == FMT_R8G8B8A8_SRGB || d->color.format == FMT_B8G8R8A8_SRGB) && d->sampleCount > 1)
 		return SWCU_E_UNSUPPORTED; /* the sRGB resolve is not Blitter::fastResolve: outside the subset */
 	if(d->depth.buffer && d->depth.format != FMT_D32_SFLOAT && d->depth.format != FMT_D16_UNORM) return SWCU_E_UNSUPPORTED;
@@ -1181,13 +1224,15 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 	dr.ms = (int)d->sampleCount;
 	dr.enableMultiSampling = dr.ms > 1;
 	dr.depthTestActive = d->depthTestEnable && d->depth.buffer;
+	dr.floatTarget = floatTarget;
+	dr.colorBpp = d->color.format == FMT_R32G32B32A32_SFLOAT ? 16 : (d->color.format == FMT_R16G16B16A16_SFLOAT ? 8 : 4);
 	dr.depthWriteEnable = dr.depthTestActive && d->depthWriteEnable; /* FragmentState::depthWriteActive */
 	dr.stencilActive = d->stencilTestEnable && d->stencil.buffer;
 	dr.interpolateZ = dr.depthTestActive;
 	dr.interpolateW = 1;
 	{ /* Context.cpp:1090-1147, :1272-1300 */
-		int cop = fold_blend_op((int)d->colorBlendOp, (int)d->srcColorBlendFactor, (int)d->dstColorBlendFactor);
-		int aop = fold_blend_op((int)d->alphaBlendOp, (int)d->srcAlphaBlendFactor, (int)d->dstAlphaBlendFactor);
+		int cop = fold_blend_op((int)d->colorBlendOp, (int)d->srcColorBlendFactor, (int)d->dstColorBlendFactor, !dr.floatTarget);
+		int aop = fold_blend_op((int)d->alphaBlendOp, (int)d->srcAlphaBlendFactor, (int)d->dstAlphaBlendFactor, !dr.floatTarget);
 		dr.colorWriteMask = d->color.buffer ? (int)(d->colorWriteMask & 0xF) : 0;
 		if(d->blendEnable && cop == BOP_DST_EXT && aop == BOP_DST_EXT) dr.colorWriteMask = 0;
 		dr.blendEnable = d->blendEnable && dr.colorWriteMask && (cop != BOP_SRC_EXT || aop != BOP_SRC_EXT);
@@ -1232,7 +1277,7 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 /* Blitter::fastClear, Device/Blitter.cpp:170-325 — rectangle fill of every sample slice */
 int swref_clear(const swcu_attachment *att, uint32_t samples, const swcu_rect *area, const void *value)
 {
-	int bpp = att->format == FMT_S8_UINT ? 1 : (att->format == FMT_D16_UNORM ? 2 : 4);
+	int bpp = att->format == FMT_S8_UINT ? 1 : (att->format == FMT_D16_UNORM ? 2 : (att->format == FMT_R32G32B32A32_SFLOAT ? 16 : (att->format == FMT_R16G16B16A16_SFLOAT ? 8 : 4)));
 	for(uint32_t q = 0; q < samples; q++)
 		for(uint32_t y = 0; y < area->height; y++)
 		{

@@ -177,8 +177,9 @@ def render_reference(scene: Scene, time_frames: int = 0, threads: int | None = N
     magic, W, H, hasD, hasS, samples = struct.unpack_from("<6I", raw, 0)
     assert magic == 0x4F525753 and W == scene.width and H == scene.height
     off = 24
-    out = {"color": np.frombuffer(raw, np.uint8, W * H * 4, off).reshape(H, W, 4).copy()}
-    off += W * H * 4
+    cdt = scene.color_dtype()
+    out = {"color": np.frombuffer(raw, cdt, W * H * 4, off).reshape(H, W, 4).copy()}
+    off += W * H * 4 * cdt.itemsize
     if hasD == 2:  # D16_UNORM
         out["depth"] = np.frombuffer(raw, np.uint16, W * H, off).reshape(H, W).copy()
         off += W * H * 2

@@ -434,8 +434,9 @@ static int get_shader(swcu_ctx *ctx, const uint32_t *code, uint32_t words, uint3
 	return SWCU_OK;
 }
 
-// Context.cpp:1165-1270 (operation folding) and :1272-1300 (factor folding) for UNORM targets
-static int fold_blend_op(int op, int sf, int df)
+// Context.cpp:1165-1270 (operation folding) and :1272-1300 (factor folding); two SUBTRACT cases fold only for UNORM targets
+// (a negative result is clamped to zero there, kept for floating-point targets)
+static int fold_blend_op(int op, int sf, int df, bool unorm)
 {
 	switch(op)
 	{
@@ -444,12 +445,12 @@ static int fold_blend_op(int op, int sf, int df)
 		else if(sf == BF_ONE) { if(df == BF_ZERO) return BOP_SRC_EXT; }
 		break;
 	case BOP_SUBTRACT:
-		if(sf == BF_ZERO) return BOP_ZERO_EXT;
+		if(sf == BF_ZERO) { if(df == BF_ZERO || unorm) return BOP_ZERO_EXT; }
 		else if(sf == BF_ONE) { if(df == BF_ZERO) return BOP_SRC_EXT; }
 		break;
 	case BOP_REVERSE_SUBTRACT:
 		if(sf == BF_ZERO) { if(df == BF_ZERO) return BOP_ZERO_EXT; if(df == BF_ONE) return BOP_DST_EXT; }
-		else { if(df == BF_ZERO) return BOP_ZERO_EXT; }
+		else { if(df == BF_ZERO && unorm) return BOP_ZERO_EXT; }
 		break;
 	}
 	return op;
@@ -485,8 +486,11 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	if(desc->provokingVertexMode > 1) return fail(ctx, SWCU_E_INVALID, "bad provoking vertex mode");
 	const bool srgbTarget = desc->color.buffer && (desc->color.format == VKF_R8G8B8A8_SRGB || desc->color.format == VKF_B8G8R8A8_SRGB);
 	if(srgbTarget && desc->sampleCount > 1) return fail(ctx, SWCU_E_UNSUPPORTED, "multisampled sRGB colour targets are outside the subset (their resolve is not Blitter::fastResolve)");
-	if(desc->color.buffer && !srgbTarget && desc->color.format != VKF_R8G8B8A8_UNORM && desc->color.format != VKF_B8G8R8A8_UNORM)
-		return fail(ctx, SWCU_E_UNSUPPORTED, "colour format %u unsupported (R8G8B8A8 / B8G8R8A8, UNORM or SRGB)", desc->color.format);
+	const bool floatTarget = desc->color.buffer && (desc->color.format == VKF_R32G32B32A32_SFLOAT || desc->color.format == VKF_R16G16B16A16_SFLOAT);
+	if(floatTarget && desc->sampleCount > 1) return fail(ctx, SWCU_E_UNSUPPORTED, "multisampled floating-point colour targets are outside the subset (no Blitter::fastResolve)");
+	if(desc->color.buffer && !srgbTarget && !floatTarget && desc->color.format != VKF_R8G8B8A8_UNORM && desc->color.format != VKF_B8G8R8A8_UNORM)
+		return fail(ctx, SWCU_E_UNSUPPORTED, "colour format %u unsupported (R8G8B8A8 / B8G8R8A8 UNORM or SRGB, R16G16B16A16_SFLOAT, R32G32B32A32_SFLOAT)", desc->color.format);
+	d.colorEpp = desc->color.format == VKF_R32G32B32A32_SFLOAT ? 4u : (desc->color.format == VKF_R16G16B16A16_SFLOAT ? 2u : 1u);
 	if(desc->depth.buffer && desc->depth.format != VKF_D32_SFLOAT && desc->depth.format != VKF_D16_UNORM)
 		return fail(ctx, SWCU_E_UNSUPPORTED, "depth format %u unsupported (D32_SFLOAT, D16_UNORM)", desc->depth.format);
 	if(desc->depth.buffer && desc->depth.format == VKF_D16_UNORM && desc->stencil.buffer)
@@ -641,8 +645,8 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		d.stencilWrite = !allKeep && writeEnabled;
 	}
 	{ // Context.cpp:1090-1147
-		const int cop = fold_blend_op((int)desc->colorBlendOp, (int)desc->srcColorBlendFactor, (int)desc->dstColorBlendFactor);
-		const int aop = fold_blend_op((int)desc->alphaBlendOp, (int)desc->srcAlphaBlendFactor, (int)desc->dstAlphaBlendFactor);
+		const int cop = fold_blend_op((int)desc->colorBlendOp, (int)desc->srcColorBlendFactor, (int)desc->dstColorBlendFactor, !floatTarget);
+		const int aop = fold_blend_op((int)desc->alphaBlendOp, (int)desc->srcAlphaBlendFactor, (int)desc->dstAlphaBlendFactor, !floatTarget);
 		d.colorWriteMask = desc->color.buffer ? (desc->colorWriteMask & 0xF) : 0;
 		if(desc->blendEnable && cop == BOP_DST_EXT && aop == BOP_DST_EXT) d.colorWriteMask = 0;
 		d.blendEnable = desc->blendEnable && d.colorWriteMask && (cop != BOP_SRC_EXT || aop != BOP_SRC_EXT);
@@ -658,7 +662,8 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 			d.srcFA = (uint32_t)fold_blend_factor((int)desc->alphaBlendOp, (int)desc->srcAlphaBlendFactor);
 			d.dstFA = (uint32_t)fold_blend_factor((int)desc->alphaBlendOp, (int)desc->dstAlphaBlendFactor);
 		}
-		for(int k = 0; k < 4; k++) d.blendConstant[k] = clamp01(desc->blendConstants[k]);
+		// blendConstantU (clamped) for UNORM targets, blendConstantF (as given) for floating-point ones (PixelRoutine.cpp:1203-1223)
+		for(int k = 0; k < 4; k++) d.blendConstant[k] = floatTarget ? desc->blendConstants[k] : clamp01(desc->blendConstants[k]);
 		d.bgr = desc->color.format == VKF_B8G8R8A8_UNORM || desc->color.format == VKF_B8G8R8A8_SRGB;
 		d.srgb = srgbTarget ? 1u : 0u;
 		d.blendClass = !d.blendEnable ? BL_OFF : ((d.srcF == BF_SRC_ALPHA && d.dstF == BF_ONE_MINUS_SRC_ALPHA && d.op == KOP_ADD && d.opA == KOP_SRC && d.colorWriteMask == 0xF) ? BL_SRC_ALPHA : BL_GENERIC);
@@ -677,7 +682,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		pitch = a.pitchB; slice = a.sliceB;
 		return SWCU_OK;
 	};
-	if((rc = att(desc->color, 4, d.colorBuf, d.colorPitchB, d.colorSliceB, "colour"))) return rc;
+	if((rc = att(desc->color, 4 * (int)d.colorEpp, d.colorBuf, d.colorPitchB, d.colorSliceB, "colour"))) return rc;
 	d.depth16 = desc->depth.buffer && desc->depth.format == VKF_D16_UNORM;
 	if((rc = att(desc->depth, d.depth16 ? 2 : 4, d.depthBuf, d.depthPitchB, d.depthSliceB, "depth"))) return rc;
 	if((rc = att(desc->stencil, 1, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, "stencil"))) return rc;
@@ -712,7 +717,8 @@ static bool tma_eligible(const unsigned char *base, int pitchB, int sliceB, int 
 	return base && ((uintptr_t)base % 16 == 0) && pitchB > 0 && sliceB > 0 && (pitchB % 16 == 0) && (sliceB % 16 == 0) && (SWCU_TILE_W * bpp) % 16 == 0;
 }
 
-static bool get_tensor_map(swcu_ctx *ctx, CUtensorMap *out, unsigned char *base, int pitchB, int sliceB, int w, int h, int ms, int bpp)
+// epp: elements per pixel along x (floating-point colour targets are mapped as 2 or 4 32-bit words per pixel)
+static bool get_tensor_map(swcu_ctx *ctx, CUtensorMap *out, unsigned char *base, int pitchB, int sliceB, int w, int h, int ms, int bpp, int epp = 1)
 {
 	if(!ctx->encodeTiled)
 	{
@@ -725,14 +731,14 @@ static bool get_tensor_map(swcu_ctx *ctx, CUtensorMap *out, unsigned char *base,
 		}
 		ctx->encodeTiled = fn;
 	}
-	const std::vector<uint64_t> key = { (uint64_t)(uintptr_t)base, (uint64_t)pitchB, (uint64_t)sliceB, (uint64_t)w, (uint64_t)h, (uint64_t)ms, (uint64_t)bpp };
+	const std::vector<uint64_t> key = { (uint64_t)(uintptr_t)base, (uint64_t)pitchB, (uint64_t)sliceB, (uint64_t)w, (uint64_t)h, (uint64_t)ms, (uint64_t)bpp, (uint64_t)epp };
 	auto it = ctx->mapCache.find(key);
 	if(it == ctx->mapCache.end())
 	{
 		CUtensorMap m;
-		const cuuint64_t dims[3] = { (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)ms };
+		const cuuint64_t dims[3] = { (cuuint64_t)w * epp, (cuuint64_t)h, (cuuint64_t)ms };
 		const cuuint64_t strides[2] = { (cuuint64_t)pitchB, (cuuint64_t)sliceB };
-		const cuuint32_t box[3] = { SWCU_TILE_W, SWCU_TILE_H, (cuuint32_t)ms };
+		const cuuint32_t box[3] = { (cuuint32_t)(SWCU_TILE_W * epp), SWCU_TILE_H, (cuuint32_t)ms };
 		const cuuint32_t estr[3] = { 1, 1, 1 };
 		CUresult r = ((EncodeTiledFn)ctx->encodeTiled)(&m, bpp == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : (bpp == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8), 3, base, dims, strides, box, estr,
 		                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -748,7 +754,7 @@ template<int MS, int SH, int BL, bool FS>
 static void launch_tile4(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps, dim3 grid)
 {
 	LaunchScope ls(ctx, MS == 4 ? "k_tile<4>" : "k_tile<1>");
-	const int smem = TileLayout<MS, SH>::total(d.depthTestActive != 0, d.stencilActive != 0);
+	const int smem = TileLayout<MS, SH>::total(d.depthTestActive != 0, d.stencilActive != 0, FS ? 1 : (int)d.colorEpp);
 	if(MS == 4)
 	{
 		// 8 CTAs of 4x MSAA colour + depth tiles need ~224 KB of the SM's shared memory: ask for the largest carve-out
@@ -763,7 +769,7 @@ static void launch_tile4(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps
 static bool fast_state(const swcu_ctx *ctx, const DrawConst &d)
 {
 	if(!ctx->optFastState) return false;
-	if(d.stencilActive || d.stencilWrite || !d.colorBuf || d.colorWriteMask != 0xFu || d.bgr || d.srgb || d.depthBiasEnable || d.depth16) return false;
+	if(d.stencilActive || d.stencilWrite || !d.colorBuf || d.colorWriteMask != 0xFu || d.bgr || d.srgb || d.colorEpp != 1 || d.depthBiasEnable || d.depth16) return false;
 	if(d.depthTestActive && d.depthCompareOp != CMP_LESS && d.depthCompareOp != CMP_LESS_OR_EQUAL) return false;
 	if(d.ms == 4 && (d.sampleMask & 0xFu) != 0xFu) return false;
 	if(d.blendClass == BL_GENERIC || d.shaderClass == SH_GENERIC) return false;
@@ -959,10 +965,10 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	{
 		const bool colorOn = d.colorWriteMask != 0 && d.colorBuf;
 		bool ok = ctx->optTma != 0;
-		if(ok && colorOn) ok = tma_eligible(d.colorBuf, d.colorPitchB, d.colorSliceB, 4);
+		if(ok && colorOn) ok = tma_eligible(d.colorBuf, d.colorPitchB, d.colorSliceB, 4 * (int)d.colorEpp);
 		if(ok && d.depthTestActive) ok = tma_eligible(d.depthBuf, d.depthPitchB, d.depthSliceB, d.depth16 ? 2 : 4);
 		if(ok && d.stencilActive) ok = tma_eligible(d.stencilBuf, d.stencilPitchB, d.stencilSliceB, 1);
-		if(ok && colorOn) ok = get_tensor_map(ctx, &maps.color, d.colorBuf, d.colorPitchB, d.colorSliceB, d.fbWidth, d.fbHeight, d.ms, 4);
+		if(ok && colorOn) ok = get_tensor_map(ctx, &maps.color, d.colorBuf, d.colorPitchB, d.colorSliceB, d.fbWidth, d.fbHeight, d.ms, 4, (int)d.colorEpp);
 		if(ok && d.depthTestActive) ok = get_tensor_map(ctx, &maps.depth, d.depthBuf, d.depthPitchB, d.depthSliceB, d.fbWidth, d.fbHeight, d.ms, d.depth16 ? 2 : 4);
 		if(ok && d.stencilActive) ok = get_tensor_map(ctx, &maps.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, d.fbWidth, d.fbHeight, d.ms, 1);
 		d.useTma = ok ? 1u : 0u;
@@ -1062,6 +1068,8 @@ extern "C" int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t sa
 	{
 	case VKF_R8G8B8A8_UNORM: case VKF_B8G8R8A8_UNORM: case VKF_R8G8B8A8_SRGB: case VKF_B8G8R8A8_SRGB: case VKF_D32_SFLOAT: bpp = 4; break;
 	case VKF_D16_UNORM: bpp = 2; break;
+	case VKF_R16G16B16A16_SFLOAT: bpp = 8; break;
+	case VKF_R32G32B32A32_SFLOAT: bpp = 16; break;
 	case VKF_S8_UINT: bpp = 1; break;
 	default: return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_clear: format %u unsupported", att->format);
 	}
@@ -1072,7 +1080,7 @@ extern "C" int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t sa
 	const size_t need = (size_t)(samples - 1) * att->sliceB + (size_t)(att->height - 1) * att->pitchB + (size_t)att->width * bpp;
 	unsigned char *base = dev_ptr(ctx, att->buffer, need);
 	if(!base) return fail(ctx, SWCU_E_INVALID, "swcu_clear: attachment is not inside a registered range");
-	uint32_t v = 0;
+	uint4 v = make_uint4(0, 0, 0, 0);
 	memcpy(&v, value, (size_t)bpp);
 	LaunchScope ls(ctx, "k_clear");
 	k_clear<<<dim3((area->width + 255) / 256, area->height), 256, 0, ctx->stream>>>(base, att->pitchB, att->sliceB, bpp, area->x, area->y, (int)area->width, (int)area->height, (int)samples, v);

@@ -1029,6 +1029,40 @@ DEVI float srgb_to_linear(float c) // ShaderCore.cpp:682-689
 	return c < 0.04045f ? lc : ec;
 }
 
+// Reactor's scalar Half <-> Float conversions (Reactor.cpp:3744-3770, :3787-3815): round-to-nearest-even on the way down, everything
+// above 0x47FFEFFF (incl. NaN) becomes 0x7FFF; on the way up exponent 31 is NOT special (it decodes to 2^16 * 1.m).
+DEVI uint32_t float_to_half(float f)
+{
+	const uint32_t fp32i = __float_as_uint(f);
+	uint32_t a = fp32i & 0x7FFFFFFFu;
+	uint32_t h = (fp32i & 0x80000000u) >> 16;
+	if(a > 0x47FFEFFFu) h |= 0x7FFFu;
+	else if(a < 0x38800000u)
+	{
+		const int mantissa = (int)((a & 0x007FFFFFu) | 0x00800000u);
+		const int e = 113 - (int)(a >> 23);
+		a = e < 24 ? (uint32_t)(mantissa >> e) : 0u;
+		h |= ((a + 0x00000FFFu + ((a >> 13) & 1u)) >> 13) & 0xFFFFu;
+	}
+	else h |= ((a + 0xC8000000u + 0x00000FFFu + ((a >> 13) & 1u)) >> 13) & 0xFFFFu;
+	return h & 0xFFFFu;
+}
+DEVI float half_to_float(uint32_t h)
+{
+	int e = (int)(h >> 10) & 0x1F, m = (int)(h & 0x3FFu);
+	uint32_t fp32i = (h & 0x8000u) << 16;
+	if(e == 0)
+	{
+		if(m != 0)
+		{
+			while((m & 0x400) == 0) { m <<= 1; e -= 1; }
+			fp32i |= (uint32_t)(((e + (127 - 15) + 1) << 23) | ((m & ~0x400) << 13));
+		}
+	}
+	else fp32i |= (uint32_t)(((e + (127 - 15)) << 23) | (m << 13));
+	return __uint_as_float(fp32i);
+}
+
 DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1849-1958
 {
 	switch(op)
@@ -1112,9 +1146,9 @@ struct TileLayout
 	static constexpr int W_COV = W_BITS + ICAP / 8;                  // uint32 cov[16]: samples of the region covered by the current range (conflict test)
 	static constexpr int W_BYTES = (W_COV + 64 + 15) & ~15;
 	static constexpr int HEAD_B = 128;                               // mbarrier + dirty flag
-	__host__ __device__ static int total(bool depth, bool stencil)
+	__host__ __device__ static int total(bool depth, bool stencil, int colorEpp = 1)
 	{
-		return HEAD_B + PLANE_B + (depth ? PLANE_B : 0) + (stencil ? ((STENCIL_B + 127) & ~127) : 0) + SWCU_TILE_WARPS * W_BYTES;
+		return HEAD_B + PLANE_B * colorEpp + (depth ? PLANE_B : 0) + (stencil ? ((STENCIL_B + 127) & ~127) : 0) + SWCU_TILE_WARPS * W_BYTES;
 	}
 };
 
@@ -1213,8 +1247,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 	uint64_t *bar = (uint64_t *)smem;
 	int *dirtyFlag = (int *)(smem + 8);
 	uint32_t *smColor = (uint32_t *)(smem + L::HEAD_B);
-	float *smDepth = (float *)(smem + L::HEAD_B + L::PLANE_B);
-	unsigned char *smStencil = smem + L::HEAD_B + L::PLANE_B + (d.depthTestActive ? L::PLANE_B : 0);
+	const int colorEpp = FS ? 1 : (int)d.colorEpp; // 32-bit words per colour pixel (floating-point targets: 2 or 4)
+	float *smDepth = (float *)(smem + L::HEAD_B + L::PLANE_B * colorEpp);
+	unsigned char *smStencil = smem + L::HEAD_B + L::PLANE_B * colorEpp + (d.depthTestActive ? L::PLANE_B : 0);
 	unsigned char *warpBase = smStencil + (d.stencilActive ? ((L::STENCIL_B + 127) & ~127) : 0);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1246,16 +1281,18 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 	{
 		if(threadIdx.x == 0)
 		{
-			const uint32_t bytes = (colorOn ? L::PLANE_B : 0) + (d.depthTestActive ? (d.depth16 ? L::PLANE_B / 2 : L::PLANE_B) : 0) + (d.stencilActive ? L::STENCIL_B : 0);
+			const uint32_t bytes = (colorOn ? L::PLANE_B * colorEpp : 0) + (d.depthTestActive ? (d.depth16 ? L::PLANE_B / 2 : L::PLANE_B) : 0) + (d.stencilActive ? L::STENCIL_B : 0);
 			mbar_expect_tx(bar, bytes);
-			if(colorOn) tma_load_3d(smColor, &maps.color, bar, tileX, tileY, 0);
+			if(colorOn) tma_load_3d(smColor, &maps.color, bar, tileX * colorEpp, tileY, 0); // the map counts 32-bit words along x
 			if(d.depthTestActive) tma_load_3d(smDepth, &maps.depth, bar, tileX, tileY, 0);
 			if(d.stencilActive) tma_load_3d(smStencil, &maps.stencil, bar, tileX, tileY, 0);
 		}
 	}
 	else
 	{
-		if(colorOn) tile_copy<MS, uint32_t, false>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		if(colorOn && colorEpp == 4) tile_copy<MS, uint4, false>((uint4 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		else if(colorOn && colorEpp == 2) tile_copy<MS, uint2, false>((uint2 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		else if(colorOn) tile_copy<MS, uint32_t, false>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 		if(d.depthTestActive && d.depth16) tile_copy<MS, unsigned short, false>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 		else if(d.depthTestActive) tile_copy<MS, float, false>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 		if(d.stencilActive) tile_copy<MS, unsigned char, false>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
@@ -1625,7 +1662,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 									else if(SH == SH_VARY || SH == SH_GENERIC) val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], d.slotMode[ch], xf, yf, rhw);
 									else val = 0.0f;
 								}
-								rgba[ch] = sse_min(sse_max(val, 0.0f), 1.0f); // PixelProgram::clampColor :286-364
+								// PixelProgram::clampColor :286-364 — UNORM targets only ("if the color attachment is floating-point, no clamping occurs")
+								rgba[ch] = (!FS && colorEpp > 1) ? val : sse_min(sse_max(val, 0.0f), 1.0f);
 							}
 
 							// ---- stencil test, depth test, depth write, blend + colour write, stencil write ----
@@ -1678,17 +1716,36 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 								}
 								if(colorOn)
 								{
-									const uint32_t px = smColor[pi];
+									const bool floatTarget = !FS && colorEpp > 1;
+									const uint32_t px = floatTarget ? 0u : smColor[pi];
 									float o[4] = { rgba[0], rgba[1], rgba[2], rgba[3] };
 									if(BL != BL_OFF)
 									{
 										float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
-#pragma unroll
-										for(int ch = 0; ch < 4; ch++)
+										if(floatTarget)
 										{
-											const uint32_t byte = (bgr && ch < 3) ? 2 - ch : ch;
-											dst[ch] = fmul((float)__byte_perm(px, 0, 0x4400u | byte | (byte << 4)), 1.0f / 0xFFFF); // b * 257 == b << 8 | b
-											if(!FS && d.srgb && ch < 3) dst[ch] = srgb_to_linear(dst[ch]);
+											// floating-point targets: the stored value itself (:1700-1710), or Reactor's Float(Half) (:1782-1801)
+											if(colorEpp == 4)
+											{
+												const float4 t = ((const float4 *)smColor)[pi];
+												dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+											}
+											else
+											{
+												const uint2 t = ((const uint2 *)smColor)[pi];
+												dst[0] = half_to_float(t.x & 0xFFFFu); dst[1] = half_to_float(t.x >> 16);
+												dst[2] = half_to_float(t.y & 0xFFFFu); dst[3] = half_to_float(t.y >> 16);
+											}
+										}
+										else
+										{
+#pragma unroll
+											for(int ch = 0; ch < 4; ch++)
+											{
+												const uint32_t byte = (bgr && ch < 3) ? 2 - ch : ch;
+												dst[ch] = fmul((float)__byte_perm(px, 0, 0x4400u | byte | (byte << 4)), 1.0f / 0xFFFF); // b * 257 == b << 8 | b
+												if(!FS && d.srgb && ch < 3) dst[ch] = srgb_to_linear(dst[ch]);
+											}
 										}
 										if(BL == BL_SRC_ALPHA)
 										{
@@ -1709,8 +1766,30 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 #pragma unroll
 										for(int ch = 0; ch < 3; ch++) o[ch] = linear_to_srgb(o[ch]);
 									}
-									const uint32_t pk = bgr ? pack_unorm8(o[2], o[1], o[0], o[3]) : pack_unorm8(o[0], o[1], o[2], o[3]);
-									smColor[pi] = (px & ~wmask32) | (pk & wmask32);
+									if(floatTarget)
+									{
+										// masked store of the bits (:2429-2447), or of Reactor's Half(Float) (:2504-2540); no clamp, no rounding of fp32
+										const uint32_t cm = d.colorWriteMask;
+										if(colorEpp == 4)
+										{
+											float *t = (float *)smColor + 4 * pi;
+#pragma unroll
+											for(int ch = 0; ch < 4; ch++)
+												if((cm >> ch) & 1) t[ch] = o[ch];
+										}
+										else
+										{
+											unsigned short *t = (unsigned short *)smColor + 4 * pi;
+#pragma unroll
+											for(int ch = 0; ch < 4; ch++)
+												if((cm >> ch) & 1) t[ch] = (unsigned short)float_to_half(o[ch]);
+										}
+									}
+									else
+									{
+										const uint32_t pk = bgr ? pack_unorm8(o[2], o[1], o[0], o[3]) : pack_unorm8(o[0], o[1], o[2], o[3]);
+										smColor[pi] = (px & ~wmask32) | (pk & wmask32);
+									}
 									dirty = true;
 								}
 							}
@@ -1750,7 +1829,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 		__syncthreads();
 		if(threadIdx.x == 0)
 		{
-			if(colorOn) tma_store_3d(&maps.color, smColor, tileX, tileY, 0);
+			if(colorOn) tma_store_3d(&maps.color, smColor, tileX * colorEpp, tileY, 0);
 			if(d.depthWriteEnable) tma_store_3d(&maps.depth, smDepth, tileX, tileY, 0);
 			if(d.stencilWrite) tma_store_3d(&maps.stencil, smStencil, tileX, tileY, 0);
 			tma_commit();
@@ -1759,7 +1838,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 	}
 	else
 	{
-		if(colorOn) tile_copy<MS, uint32_t, true>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		if(colorOn && colorEpp == 4) tile_copy<MS, uint4, true>((uint4 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		else if(colorOn && colorEpp == 2) tile_copy<MS, uint2, true>((uint2 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		else if(colorOn) tile_copy<MS, uint32_t, true>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 		if(d.depthWriteEnable && d.depth16) tile_copy<MS, unsigned short, true>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 		else if(d.depthWriteEnable) tile_copy<MS, float, true>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
 		if(d.stencilWrite) tile_copy<MS, unsigned char, true>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
@@ -1770,7 +1851,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 // the steps either side of the draw
 // ------------------------------------------------------------------------------------------------------------------
 // Blitter::fastClear (Blitter.cpp:170-325): rectangle fill of every sample slice; bpp 4 or 1
-__global__ void k_clear(unsigned char *base, int pitchB, int sliceB, int bpp, int x0, int y0, int w, int h, int samples, uint32_t value)
+__global__ void k_clear(unsigned char *base, int pitchB, int sliceB, int bpp, int x0, int y0, int w, int h, int samples, uint4 value4)
 {
 	const int x = blockIdx.x * blockDim.x + threadIdx.x;
 	const int y = blockIdx.y;
@@ -1778,7 +1859,10 @@ __global__ void k_clear(unsigned char *base, int pitchB, int sliceB, int bpp, in
 	for(int q = 0; q < samples; q++)
 	{
 		unsigned char *row = base + (size_t)q * sliceB + (size_t)(y0 + y) * pitchB;
-		if(bpp == 4) ((uint32_t *)row)[x0 + x] = value;
+		const uint32_t value = value4.x;
+		if(bpp == 16) ((uint4 *)row)[x0 + x] = value4;
+		else if(bpp == 8) ((uint2 *)row)[x0 + x] = make_uint2(value4.x, value4.y);
+		else if(bpp == 4) ((uint32_t *)row)[x0 + x] = value;
 		else if(bpp == 2) ((unsigned short *)row)[x0 + x] = (unsigned short)value;
 		else row[x0 + x] = (unsigned char)value;
 	}

@@ -18,6 +18,7 @@ enum
 	VKF_R8G8B8A8_SRGB = 43,
 	VKF_B8G8R8A8_UNORM = 44,
 	VKF_B8G8R8A8_SRGB = 50,
+	VKF_R16G16B16A16_SFLOAT = 97,
 	VKF_R32_SFLOAT = 100,
 	VKF_R32G32_SFLOAT = 103,
 	VKF_R32G32B32_SFLOAT = 106,
@@ -163,6 +164,8 @@ struct DrawConst
 	uint32_t colorWriteMask;
 	float blendConstant[4]; // clamped to [0,1] (UNORM target)
 	uint32_t bgr;
+	uint32_t colorEpp; // 32-bit words per colour pixel: 1 (RGBA8 family), 2 (R16G16B16A16_SFLOAT), 4 (R32G32B32A32_SFLOAT); > 1 = floating-point target:
+	                   // no clamping of shader output / blend constants, Half conversions of Reactor.cpp:3744-3815, masked bit-exact stores
 	uint32_t srgb; // sRGB colour target: encode before the pack, decode the destination when blending (PixelRoutine.cpp:1821-1826,1965-1970)
 
 	// ---- attachments (device addresses) ----

@@ -21,6 +21,7 @@ from . import capi, spirv
 FMT_R8G8B8A8_UNORM = 37
 FMT_B8G8R8A8_UNORM = 44
 FMT_R32_SFLOAT, FMT_R32G32_SFLOAT, FMT_R32G32B32_SFLOAT, FMT_R32G32B32A32_SFLOAT = 100, 103, 106, 109
+FMT_R16G16B16A16_SFLOAT = 97
 FMT_R8G8B8A8_SRGB = 43
 FMT_B8G8R8A8_SRGB = 50
 FMT_D32_SFLOAT = 126
@@ -159,9 +160,20 @@ class Scene:
     def padded_height(self) -> int:
         return (self.height + 1) & ~1
 
+    def color_dtype(self) -> np.dtype:
+        """Element type of one colour channel: uint8 (RGBA8 / BGRA8, UNORM or SRGB), float16 (R16G16B16A16_SFLOAT) or float32
+        (R32G32B32A32_SFLOAT); a pixel is four of them."""
+        return np.dtype({FMT_R32G32B32A32_SFLOAT: np.float32, FMT_R16G16B16A16_SFLOAT: np.float16}.get(self.colorFormat, np.uint8))
+
+    def color_bpp(self) -> int:
+        return 4 * self.color_dtype().itemsize
+
     def clear_color_bytes(self) -> np.ndarray:
-        """UNORM8 pack of the clear colour as Blitter::fastClear does: (uint32_t)(255 * c + 0.5f)
-        (/root/reference/src/Device/Blitter.cpp:217-229)."""
+        """One pixel of the clear colour in the attachment's format.  UNORM8: the pack Blitter::fastClear does,
+        (uint32_t)(255 * c + 0.5f) (/root/reference/src/Device/Blitter.cpp:217-229); float formats: the value itself (use clear
+        colours that are exact in half precision for R16G16B16A16_SFLOAT)."""
+        if self.color_dtype() != np.uint8:
+            return np.array(self.clearColor, dtype=np.float32).astype(self.color_dtype())
         c = np.clip(np.array(self.clearColor, dtype=np.float32), 0, 1)
         b = (np.float32(255.0) * c + np.float32(0.5)).astype(np.float32).astype(np.uint32).astype(np.uint8)
         if self.colorFormat in (FMT_B8G8R8A8_UNORM, FMT_B8G8R8A8_SRGB):
@@ -170,7 +182,7 @@ class Scene:
 
     def alloc_attachments(self) -> dict:
         H2, W, S = self.padded_height(), self.width, self.samples
-        att = {"color": np.empty((S, H2, W, 4), dtype=np.uint8)}
+        att = {"color": np.empty((S, H2, W, 4), dtype=self.color_dtype())}
         att["color"][:] = self.clear_color_bytes()
         if self.hasDepth and self.depthFormat == FMT_D16_UNORM:
             # D16 is not a fastClear format: the generic blit scales by 0xFFFF, clamps and stores UShort(RoundInt(x))
@@ -243,7 +255,8 @@ class Scene:
         d.blendConstants = (C.c_float * 4)(*draw.blendConstants)
         H2, W = self.padded_height(), self.width
         col = att["color"]
-        d.color = capi.Attachment(col.ctypes.data, self.colorFormat, W * 4, H2 * W * 4, W, self.height, 0)
+        cb = self.color_bpp()
+        d.color = capi.Attachment(col.ctypes.data, self.colorFormat, W * cb, H2 * W * cb, W, self.height, 0)
         if "depth" in att:
             zb = att["depth"].dtype.itemsize
             d.depth = capi.Attachment(att["depth"].ctypes.data, self.depthFormat, W * zb, H2 * W * zb, W, self.height, 0)
@@ -488,8 +501,9 @@ class Frame:
 
     def _attachment(self, key: str) -> capi.Attachment:
         H2, W, sc = self.scene.padded_height(), self.scene.width, self.scene
+        cb = sc.color_bpp()
         if key == "color":
-            return capi.Attachment(self.att["color"].ctypes.data, sc.colorFormat, W * 4, H2 * W * 4, W, sc.height, 0)
+            return capi.Attachment(self.att["color"].ctypes.data, sc.colorFormat, W * cb, H2 * W * cb, W, sc.height, 0)
         if key == "depth":
             zb = self.att["depth"].dtype.itemsize
             return capi.Attachment(self.att["depth"].ctypes.data, sc.depthFormat, W * zb, H2 * W * zb, W, sc.height, 0)

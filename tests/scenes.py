@@ -171,6 +171,39 @@ def srgb(seed: int) -> Scene:
     return Scene(128, 96, [d], colorFormat=fmt, clearColor=clear)
 
 
+def floatrt(seed: int) -> Scene:
+    """Floating-point colour targets, R32G32B32A32_SFLOAT (even seeds) and R16G16B16A16_SFLOAT (odd): no clamping of the shader
+    output, the blend factors or the blend constants (PixelProgram.cpp:286-364, PixelRoutine.cpp:1203-1223), the un-folded
+    SUBTRACT cases (Context.cpp:1204-1243), destination read / Reactor's Half conversions (Reactor.cpp:3744-3815), masked write."""
+    rng = np.random.default_rng(5200 + seed)
+    fmt = FMT_R16G16B16A16_SFLOAT if seed % 2 else FMT_R32G32B32A32_SFLOAT
+    kw = dict(colorFormat=fmt, clearColor=(0.25, 0.5, 0.125, 1.0))
+
+    def wide(n, kinds=(5, 0, 1)):  # vertex colours outside [0, 1]
+        return np.concatenate([_verts(rng, _tri_kind(rng, kinds[i % len(kinds)]), i % 2 == 0, colour=rng.uniform(-0.75, 2.5, (3, 4))) for i in range(n)])
+    if seed < 4:
+        d = Draw(wide(8), P4C4, "vs_pos4_col4", "fs_col4", depthTest=(seed >= 2), depthWrite=(seed >= 2), colorWriteMask=(0xF if seed < 2 else 0x6))
+        return Scene(CELL, CELL, [d], hasDepth=(seed >= 2), **kw)
+    if seed < 16:
+        (sc, dc, co, sa, da, ao) = _BLEND_MATRIX[(seed * 7 + seed // 2) % len(_BLEND_MATRIX)]
+        if seed in (12, 13):  # the two SUBTRACT folds that only apply to UNORM targets
+            (sc, dc, co, sa, da, ao) = (BF_ZERO, BF_ONE, BOP_SUBTRACT, BF_SRC_ALPHA, BF_ZERO, BOP_REVERSE_SUBTRACT)
+        d = Draw(wide(8), P4C4, "vs_pos4_col4", "fs_col4", blend=True, srcColor=sc, dstColor=dc, colorOp=co, srcAlpha=sa, dstAlpha=da,
+                 alphaOp=ao, colorWriteMask=(0xF if seed % 5 else 0xD), blendConstants=(-0.25, 1.5, 0.75, 2.0))
+        return Scene(CELL, CELL, [d], **kw)
+    if seed < 18:
+        tex = Texture(_rand_tex(rng, 64, 64, 7), maxLod=6.0)
+        tris = []
+        for i in range(4):
+            col = np.zeros((3, 4))
+            col[:, :2] = rng.uniform(-2, 3, (3, 2))
+            tris.append(_verts(rng, _tri_kind(rng, [5, 0, 1, 5][i]), persp=(i % 2 == 0), colour=col))
+        d = Draw(np.concatenate(tris), P4C4, "vs_pos4_col4", "fs_tex_col4", texture=tex, blend=(seed == 17))
+        return Scene(CELL, CELL, [d], **kw)
+    d = Draw(wide(1500, (1, 4, 5)), P4C4, "vs_pos4_col4", "fs_col4", blend=True)  # dense overdraw, binned
+    return Scene(128, 96, [d], **kw)
+
+
 _BLEND_MATRIX = [
     (BF_SRC_ALPHA, BF_ONE_MINUS_SRC_ALPHA, BOP_ADD, BF_ONE, BF_ZERO, BOP_ADD),
     (BF_ONE, BF_ONE, BOP_ADD, BF_ONE, BF_ONE, BOP_ADD),
@@ -393,6 +426,7 @@ FAMILIES = {
     "overdraw": (overdraw, 7),
     "depth16": (depth16, 12),
     "srgb": (srgb, 14),
+    "floatrt": (floatrt, 20),
 }
 
 

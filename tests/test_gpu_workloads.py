@@ -121,7 +121,7 @@ def test_d16_device_clear_and_unaligned_pitch(device):
 def test_unsupported_state_is_a_hard_error(device):
     from swiftshader_b200 import capi
     sc = scenes.benchmark(1, 64, 64)
-    sc.colorFormat = 97  # R16G16B16A16_SFLOAT: outside the subset
+    sc.colorFormat = 64  # A2B10G10R10_UNORM_PACK32: outside the subset
     with pytest.raises(capi.SwcuError) as e:
         device.render(sc)
     assert e.value.code == capi.E_UNSUPPORTED
