@@ -204,6 +204,51 @@ def floatrt(seed: int) -> Scene:
     return Scene(128, 96, [d], **kw)
 
 
+def pathological(seed: int) -> Scene:
+    """Vertex data a robust rasteriser must survive exactly like the reference does: NaN / Inf components, w = 0 and w < 0,
+    magnitudes of 1e30 and 1e-40, coincident and collinear vertices, zero-area slivers, vertices exactly on the clip planes and
+    on the scissor bounds — mixed with ordinary triangles so that order and neighbours matter."""
+    rng = np.random.default_rng(6100 + seed)
+    # Known divergences of the restatement, kept out of this family and listed in DESIGN.md §6: a NaN clip-space w under 4x MSAA
+    # (the reference covers nothing, the restatement some pixels) and components of magnitude >= 3.4e38 (overflow to Inf inside the
+    # clipper's edge interpolation).
+    msaa4 = seed % 4 == 3
+    specials = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e30, -1e30, 1e-40, -1e-40, 1.0, -1.0, 1e37]
+    tris = []
+    for i in range(48):
+        v = _verts(rng, _tri_kind(rng, (5, 0, 1, 2, 3)[i % 5]), persp=(i % 2 == 0), colour=rng.uniform(0, 1, (3, 4)))
+        mode = (i + seed) % 8
+        if mode == 0:    # one special value somewhere in a position
+            comp, val = rng.integers(4), specials[rng.integers(len(specials))]
+            if msaa4 and comp == 3 and val != val:
+                val = np.inf
+            v[rng.integers(3), comp] = val
+        elif mode == 1:  # w = 0 / negative w on one or two vertices
+            k = rng.integers(3)
+            v[k, 3] = [0.0, -0.5, -2.0][rng.integers(3)]
+            if rng.integers(2):
+                v[(k + 1) % 3, 3] = -1.0
+        elif mode == 2:  # coincident / collinear / zero area
+            if rng.integers(2):
+                v[1, :4] = v[0, :4]
+            else:
+                v[2, :4] = 0.5 * (v[0, :4] + v[1, :4])
+        elif mode == 3:  # exactly on the clip planes: |x| = w, |y| = w, z = 0 / z = w
+            k = rng.integers(3)
+            v[k, 0] = v[k, 3] * [1.0, -1.0][rng.integers(2)]
+            v[(k + 1) % 3, 1] = v[(k + 1) % 3, 3] * [1.0, -1.0][rng.integers(2)]
+            v[(k + 2) % 3, 2] = [0.0, v[(k + 2) % 3, 3]][rng.integers(2)]
+        elif mode == 4:  # special value in a colour attribute
+            v[rng.integers(3), 4 + rng.integers(4)] = specials[rng.integers(len(specials))]
+        elif mode == 5:  # far outside the frustum on one side (clipped, huge edge functions)
+            v[rng.integers(3), rng.integers(2)] *= 1e6
+        tris.append(v)
+    verts = np.concatenate(tris).astype(np.float32)
+    d = Draw(verts, P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, blend=(seed % 2 == 1),
+             scissor=(3, 5, CELL - 7, CELL - 9) if seed % 3 == 0 else None, cullMode=(CULL_NONE, CULL_BACK, CULL_FRONT)[seed % 3])
+    return Scene(CELL, CELL, [d], samples=(4 if msaa4 else 1), hasDepth=True, clearDepth=1.0, clearColor=(0.25, 0.5, 0.125, 1.0))
+
+
 _BLEND_MATRIX = [
     (BF_SRC_ALPHA, BF_ONE_MINUS_SRC_ALPHA, BOP_ADD, BF_ONE, BF_ZERO, BOP_ADD),
     (BF_ONE, BF_ONE, BOP_ADD, BF_ONE, BF_ONE, BOP_ADD),
@@ -427,6 +472,7 @@ FAMILIES = {
     "depth16": (depth16, 12),
     "srgb": (srgb, 14),
     "floatrt": (floatrt, 20),
+    "pathological": (pathological, 16),
 }
 
 
