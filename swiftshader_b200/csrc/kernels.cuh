@@ -206,6 +206,41 @@ DEVI int floor_div(int n, int d, int &rem) // d > 0; returns floor(n / d), rem =
 // One edge a->b of a small triangle / clipped polygon, all samples.  Writes the clamped x of every row of the edge inside
 // [rowMin, rowMin + SWCU_SMALL_ROWS) into the left or right half of the span entries; `rows` is this thread's column of
 // the shared scratch: entry e lives at rows[e * SETUP_THREADS].
+// Operands of an edge for which the closed form of edge_at_row equals the reference's 32-bit arithmetic: screen-sized coordinates.
+// Anything else (a vertex that projected to INT_MIN because its w was -Inf or NaN, ...) goes through edge_wrapped(); k_setup
+// sends every polygon with such a coordinate to k_big.
+DEVI bool edge_is_sane(int DX, int DY) { return DY > 0 && DY < (1 << 22) && DX > -(1 << 22) && DX < (1 << 22); }
+
+// x of the edge at row y exactly as SetupRoutine::edge (SetupRoutine.cpp:550-621) computes it in wrapping 32-bit integers,
+// for ANY operands: the reference's set-up values (x0, d0, Q, R) are formed with the same wrapping operations, then its
+// row-by-row stepping (d += R; carry into x when d > 0) is closed over k = y - y1 rows in 64 bits — the step count itself can
+// be millions when a coordinate is garbage.  Returns false if the edge does not own the row.
+DEVI bool edge_wrapped(const DrawConst &d, int Xa, int Ya, int Xb, int Yb, int y, bool &right, int &xo)
+{
+	if(Ya == Yb) return false;
+	const bool swap = Yb < Ya;
+	const int X1 = swap ? Xb : Xa, X2 = swap ? Xa : Xb;
+	const int Y1 = swap ? Yb : Ya, Y2 = swap ? Ya : Yb;
+	const int y1 = (int)((uint32_t)Y1 + 255u) >> 8, y2 = (int)((uint32_t)Y2 + 255u) >> 8;
+	if(y < max(y1, d.scY0) || y >= min(y2, d.scY1)) return false;
+	const uint32_t DX12 = (uint32_t)X2 - (uint32_t)X1, DY12 = (uint32_t)Y2 - (uint32_t)Y1;
+	const int FDX12 = (int)(DX12 << 8), FDY12 = (int)(DY12 << 8);
+	if(FDY12 <= 0) return false; // the reference divides by a non-positive value here (undefined); nothing is drawn for the edge
+	const int X = (int)(DX12 * (((uint32_t)y1 << 8) - (uint32_t)Y1) + (uint32_t)(X1 & 255) * DY12);
+	int x0 = (int)((uint32_t)(X1 >> 8) + (uint32_t)(X / FDY12));
+	int d0 = X % FDY12;
+	if(d0 > 0) { x0 = (int)((uint32_t)x0 + 1u); d0 -= FDY12; } // ceiling: remainder in (-D, 0]
+	int Q = FDX12 / FDY12, R = FDX12 % FDY12;
+	if(R < 0) { Q -= 1; R += FDY12; }                          // flooring: remainder in [0, D)
+	const long long k = (long long)y - (long long)y1;
+	const long long total = (long long)d0 + k * (long long)R;
+	const long long carries = total > 0 ? (total + FDY12 - 1) / FDY12 : 0;
+	const int x = (int)(uint32_t)((unsigned long long)(long long)x0 + (unsigned long long)(k * (long long)Q) + (unsigned long long)carries);
+	xo = clampi(x, d.scX0, d.scX1);
+	right = swap;
+	return true;
+}
+
 template<int MS>
 DEVI void edge_small(const DrawConst &d, uint32_t *rows, int rowMin, int Xa, int Ya, int Xb, int Yb)
 {
@@ -213,7 +248,7 @@ DEVI void edge_small(const DrawConst &d, uint32_t *rows, int rowMin, int Xa, int
 	const bool swap = Yb < Ya;
 	const int X1 = swap ? Xb : Xa, X2 = swap ? Xa : Xb;
 	const int Y1 = swap ? Yb : Ya, Y2 = swap ? Ya : Yb;
-	const int DX = X2 - X1, DY = Y2 - Y1, FDY = DY << 8;
+	const int DX = (int)((uint32_t)X2 - (uint32_t)X1), DY = (int)((uint32_t)Y2 - (uint32_t)Y1), FDY = DY << 8;
 	int R;
 	const int Q = floor_div(DX, DY, R); // == floor-divmod(DX << 8, DY << 8) with the remainder scaled by 256
 	R <<= 8;
@@ -245,6 +280,8 @@ DEVI void edge_small(const DrawConst &d, uint32_t *rows, int rowMin, int Xa, int
 DEVI bool edge_at_row(const DrawConst &d, int Xa, int Ya, int Xb, int Yb, int y, bool &right, int &xo)
 {
 	if(Ya == Yb) return false;
+	if(!edge_is_sane((int)((uint32_t)Xb - (uint32_t)Xa), Ya < Yb ? (int)((uint32_t)Yb - (uint32_t)Ya) : (int)((uint32_t)Ya - (uint32_t)Yb)))
+		return edge_wrapped(d, Xa, Ya, Xb, Yb, y, right, xo);
 	const bool swap = Yb < Ya;
 	const int X1 = swap ? Xb : Xa, X2 = swap ? Xa : Xb;
 	const int Y1 = swap ? Yb : Ya, Y2 = swap ? Ya : Yb;
@@ -342,6 +379,7 @@ DEVI void setup_triangle(const DrawConst &d)
 	bool clipped = false;
 	bool frontFacing = false;
 	int yMin = 0, yMax = 0, pxMin = 0, pxMax = 0;
+	int minXs = 0, maxXs = 0, minYs = 0, maxYs = 0; // 24.8 bounds of the (clipped) polygon
 	if(live && !precull)
 	{
 		do
@@ -403,6 +441,7 @@ DEVI void setup_triangle(const DrawConst &d)
 					minX = min(minX, PX[i]); maxX = max(maxX, PX[i]);
 				}
 			}
+			minXs = minX; maxXs = maxX; minYs = minY; maxYs = maxY;
 			yMin = msaa ? (minY + 159) >> 8 : (minY + 255) >> 8; // SetupRoutine.cpp:147-186
 			yMax = msaa ? (maxY + 351) >> 8 : (maxY + 255) >> 8;
 			yMin = max(yMin, d.scY0);
@@ -426,7 +465,12 @@ DEVI void setup_triangle(const DrawConst &d)
 		const int tx0 = pxMin / SWCU_TILE_W, tx1 = (pxMax - 1) / SWCU_TILE_W;
 		const int ty0 = yMin / SWCU_TILE_H, ty1 = (yMax - 1) / SWCU_TILE_H;
 		nTiles = (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
-		big = rows > SWCU_SMALL_ROWS || nTiles > SWCU_SMALL_TILES;
+		// A polygon with a coordinate outside the screen range (a vertex that projected to INT_MIN because its w was -Inf or NaN,
+		// ...) also goes the big-triangle way: k_big reproduces the reference's wrapping arithmetic for such edges (edge_wrapped),
+		// which keeps that case out of the small-triangle DDA below (whose fast division assumes screen-sized operands).
+		const int lim = (1 << 21) + 4096;
+		const bool insane = minXs < -lim || maxXs > lim || minYs < -lim || maxYs > lim;
+		big = rows > SWCU_SMALL_ROWS || nTiles > SWCU_SMALL_TILES || insane;
 		tileRect = big ? (TILE_RECT_BIG | nTiles) : ((uint32_t)tx0 | ((uint32_t)ty0 << 9) | ((uint32_t)(tx1 - tx0) << 19) | ((uint32_t)(ty1 - ty0) << 22));
 	}
 	const uint32_t count = big ? (uint32_t)(rows * MS) : 0u;
@@ -475,8 +519,16 @@ DEVI void setup_triangle(const DrawConst &d)
 		// span rows of the small triangle, built in a shared scratch column and stored inline in its record
 		uint32_t *col = s_rows + threadIdx.x;
 		// every row of the record is written (rows outside the triangle as empty spans): whole 32-byte sectors reach L2, so
-		// evicting them needs no fill from DRAM.  Empty = {0, 0}, also the MSAA pre-fill (SetupRoutine.cpp:214-225)
-		for(int i = 0; i < SWCU_SMALL_ROWS * MS; i++) col[i * SETUP_THREADS] = 0;
+		// evicting them needs no fill from DRAM.
+		// MSAA pre-fill (SetupRoutine.cpp:214-225): left = right = the clamped pixel of the polygon's first vertex — an empty span,
+		// but also what a half keeps when only the other half of a row gets written (degenerate / garbage edges)
+		uint32_t fill = 0;
+		if(msaa)
+		{
+			const uint32_t x = (uint32_t)clampi((int)((uint32_t)(clipped ? PX[0] : va.X) + 255u) >> 8, d.scX0, d.scX1);
+			fill = x | (x << 16);
+		}
+		for(int i = 0; i < SWCU_SMALL_ROWS * MS; i++) col[i * SETUP_THREADS] = fill;
 		if(clipped) { PX[n] = PX[0]; PY[n] = PY[0]; }
 		for(int i = 0; i < n; i++)
 		{
@@ -654,6 +706,7 @@ __global__ void __launch_bounds__(256) k_big(const __grid_constant__ DrawConst d
 				const int y = b.yMin + r / d.ms, q = r % d.ms;
 				const int ox = msaa ? c_Xf[q] : 0, oy = msaa ? c_Yf[q] : 0;
 				int L = 0, R = 0;
+				if(msaa) L = R = clampi((int)((uint32_t)b.X[0] + 255u) >> 8, d.scX0, d.scX1); // MSAA pre-fill, SetupRoutine.cpp:214-225
 				for(int i = 0; i < n; i++) // in edge order: the last writer wins, like the reference's span table
 				{
 					const int ia = i + 1 - dir, ib = i + dir;
