@@ -277,7 +277,7 @@ int main(int argc, char **argv)
 			memcpy(p, blobPtr(d.texBlob), blobSize(d.texBlob));
 			VkImage timg;
 			VkImageView tview;
-			mkImage(d.texWidth, d.texHeight, d.texLevels, VK_SAMPLE_COUNT_1_BIT, VK_FORMAT_R8G8B8A8_UNORM,
+			mkImage(d.texWidth, d.texHeight, d.texLevels, VK_SAMPLE_COUNT_1_BIT, d.hasTexture == 2 ? VK_FORMAT_R8G8B8A8_SRGB : VK_FORMAT_R8G8B8A8_UNORM, // hasTexture: 1 = UNORM, 2 = SRGB
 			        VK_IMAGE_USAGE_SAMPLED_BIT | VK_IMAGE_USAGE_TRANSFER_DST_BIT, VK_IMAGE_ASPECT_COLOR_BIT, timg, tview);
 			VkImageMemoryBarrier b{ VK_STRUCTURE_TYPE_IMAGE_MEMORY_BARRIER };
 			b.oldLayout = VK_IMAGE_LAYOUT_UNDEFINED;

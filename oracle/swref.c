@@ -19,6 +19,7 @@
  * (System/SwiftConfig.cpp:136-139) which we set in MXCSR for the duration of a call.
  */
 #include "../include/swcu.h"
+#include "../include/swcu_srgb_lut.h"
 
 #include <immintrin.h>
 #include <math.h>
@@ -550,6 +551,14 @@ static uint16_t offset_sample(uint16_t uvw, uint16_t half, int wrap, int count)
 
 /* one bilinear (or point) tap of one mip level: sampleQuad2D :668-909, computeIndices :1593-1608,
  * sampleTexel :1781-1788 (byte b -> b<<8), bilinearInterpolate :516-575 */
+/* One 8-bit texel channel in the 16-bit sampler path: b << 8, or — RGB of an sRGB texture — the reference's start-up table
+ * sRGBtoLinearFF_FF00 (SamplerCore.cpp:1966-1977, :2670-2680; include/swcu_srgb_lut.h) */
+static const uint16_t srgb_lut[256] = { SWCU_SRGB_LUT_VALUES };
+static inline uint16_t texel16(const swcu_sampled_image *t, uint8_t b, int ch)
+{
+	return (t->format == FMT_R8G8B8A8_SRGB && ch < 3) ? srgb_lut[b] : (uint16_t)(b << 8);
+}
+
 static void sample_level(const swcu_sampled_image *t, int level, float u, float v, int linear, uint16_t out[4])
 {
 	if(level < 0) level = 0;
@@ -563,7 +572,7 @@ static void sample_level(const swcu_sampled_image *t, int level, float u, float 
 	{
 		uint32_t x = mulhi_u16(uuuu, W), y = mulhi_u16(vvvv, H);
 		const uint8_t *p = buf + 4 * (size_t)(x + y * m->pitchP);
-		for(int c = 0; c < 4; c++) out[c] = (uint16_t)(p[c] << 8);
+		for(int c = 0; c < 4; c++) out[c] = texel16(t, p[c], c);
 		return;
 	}
 	uint16_t uHalf = (uint16_t)(0x8000 / m->width), vHalf = (uint16_t)(0x8000 / m->height);
@@ -580,10 +589,10 @@ static void sample_level(const swcu_sampled_image *t, int level, float u, float 
 	uint16_t f0u0v = mulhi_u16(f0u, f0v), f1u0v = mulhi_u16(f1u, f0v), f0u1v = mulhi_u16(f0u, f1v), f1u1v = mulhi_u16(f1u, f1v);
 	for(int c = 0; c < 4; c++)
 	{
-		uint16_t c00 = mulhi_u16((uint16_t)(p00[c] << 8), f1u1v);
-		uint16_t c10 = mulhi_u16((uint16_t)(p10[c] << 8), f0u1v);
-		uint16_t c01 = mulhi_u16((uint16_t)(p01[c] << 8), f1u0v);
-		uint16_t c11 = mulhi_u16((uint16_t)(p11[c] << 8), f0u0v);
+		uint16_t c00 = mulhi_u16(texel16(t, p00[c], c), f1u1v);
+		uint16_t c10 = mulhi_u16(texel16(t, p10[c], c), f0u1v);
+		uint16_t c01 = mulhi_u16(texel16(t, p01[c], c), f1u0v);
+		uint16_t c11 = mulhi_u16(texel16(t, p11[c], c), f0u0v);
 		out[c] = (uint16_t)((uint16_t)(c00 + c10) + (uint16_t)(c01 + c11));
 	}
 }
@@ -642,7 +651,7 @@ static void sample_quad(const swcu_sampled_image *t, const float u[4], const flo
 			uint16_t w00 = mulhi_u16(f1u, f1v), w10 = mulhi_u16(f0u, f1v), w01 = mulhi_u16(f1u, f0v), w11 = mulhi_u16(f0u, f0v);
 			for(int ch = 0; ch < 4; ch++)
 			{
-				uint16_t tx = (uint16_t)(p[ch] << 8);
+				uint16_t tx = texel16(t, p[ch], ch);
 				c[ch] = (uint16_t)((uint16_t)(mulhi_u16(tx, w00) + mulhi_u16(tx, w10)) + (uint16_t)(mulhi_u16(tx, w01) + mulhi_u16(tx, w11)));
 			}
 		}

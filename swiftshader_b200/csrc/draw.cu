@@ -599,7 +599,8 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		for(uint32_t s = 0; s < desc->sampledImageCount && s < SWCU_MAX_SAMPLED_IMAGES; s++)
 			if(desc->sampledImage[s].set == fs.textureSet && desc->sampledImage[s].binding == fs.textureBinding) t = &desc->sampledImage[s];
 		if(!t) return fail(ctx, SWCU_E_INVALID, "no sampled image bound at set %u binding %u", fs.textureSet, fs.textureBinding);
-		if(t->format != VKF_R8G8B8A8_UNORM) return fail(ctx, SWCU_E_UNSUPPORTED, "sampled image format %u unsupported (R8G8B8A8_UNORM)", t->format);
+		if(t->format != VKF_R8G8B8A8_UNORM && t->format != VKF_R8G8B8A8_SRGB) return fail(ctx, SWCU_E_UNSUPPORTED, "sampled image format %u unsupported (R8G8B8A8_UNORM, R8G8B8A8_SRGB)", t->format);
+		d.texSrgb = t->format == VKF_R8G8B8A8_SRGB;
 		if(t->anisotropyEnable || t->compareEnable || t->unnormalizedCoordinates) return fail(ctx, SWCU_E_UNSUPPORTED, "sampler state outside the subset (anisotropy / compare / unnormalized)");
 		if(t->addressModeU > ADDR_CLAMP_TO_EDGE || t->addressModeV > ADDR_CLAMP_TO_EDGE) return fail(ctx, SWCU_E_UNSUPPORTED, "sampler address mode outside the subset (REPEAT, MIRRORED_REPEAT, CLAMP_TO_EDGE)");
 		if(t->magFilter > FILTER_LINEAR || t->minFilter > FILTER_LINEAR || t->mipmapMode > MIPMAP_MODE_LINEAR) return fail(ctx, SWCU_E_UNSUPPORTED, "sampler filter outside the subset");
@@ -617,7 +618,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		d.magFilter = t->magFilter; d.minFilter = t->minFilter; d.mipmapMode = t->mipmapMode;
 		d.addressU = t->addressModeU; d.addressV = t->addressModeV;
 		d.mipLodBias = t->mipLodBias; d.minLod = t->minLod; d.maxLod = t->maxLod;
-		d.texFast = t->magFilter == FILTER_LINEAR && t->minFilter == FILTER_LINEAR && t->mipmapMode == MIPMAP_MODE_LINEAR &&
+		d.texFast = !d.texSrgb && t->magFilter == FILTER_LINEAR && t->minFilter == FILTER_LINEAR && t->mipmapMode == MIPMAP_MODE_LINEAR &&
 		            t->addressModeU == ADDR_REPEAT && t->addressModeV == ADDR_REPEAT;
 	}
 

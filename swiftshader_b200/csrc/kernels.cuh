@@ -20,6 +20,7 @@
 #pragma once
 
 #include "swcu_internal.h"
+#include "../../include/swcu_srgb_lut.h"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -834,6 +835,16 @@ DEVI uint32_t offset_sample(uint32_t uvw, uint32_t half, bool wrap, int count) /
 	return s > 0xFFFF ? 0xFFFFu : s;
 }
 
+// One 8-bit texel channel in the 16-bit sampler path: b << 8, or — RGB of an sRGB image — the reference's start-up table
+// sRGBtoLinearFF_FF00 (SamplerCore.cpp:1966-1977, :2670-2680).  The table sits in global memory and is read through the
+// read-only path: 512 bytes, resident in L1, and unlike constant memory not serialised when the lanes' texels differ.
+__device__ const unsigned short g_srgbLut[256] = { SWCU_SRGB_LUT_VALUES };
+DEVI uint32_t texel16(bool srgb, uint32_t t, int c)
+{
+	const uint32_t b = __byte_perm(t, 0, 0x4440 + c);
+	return (srgb && c < 3) ? (uint32_t)__ldg(g_srgbLut + b) : b << 8;
+}
+
 DEVI uint32_t load_texel(const KMip &m, uint32_t x, uint32_t y) { return __ldg((const uint32_t *)m.buffer + (x + y * m.pitchP)); }
 
 // one tap set of one mip level; out[c] are 16-bit channel values.  FAST = REPEAT/REPEAT addressing + linear filter (the
@@ -850,7 +861,7 @@ DEVI void sample_level(const DrawConst &d, int level, float u, float v, bool lin
 	{
 		const uint32_t t = load_texel(m, mulhi16(uu, W), mulhi16(vv, H));
 #pragma unroll
-		for(int c = 0; c < 4; c++) out[c] = ((t >> (8 * c)) & 0xFF) << 8;
+		for(int c = 0; c < 4; c++) out[c] = texel16(d.texSrgb != 0, t, c); // (!FAST only)
 		return;
 	}
 	const uint32_t uHalf = m.half & 0xFFFF, vHalf = m.half >> 16; // 0x8000 / extent, VkDescriptorSetLayout.cpp:315
@@ -867,11 +878,20 @@ DEVI void sample_level(const DrawConst &d, int level, float u, float v, bool lin
 #pragma unroll
 	for(int c = 0; c < 4; c++)
 	{
-		// mulhi(b << 8, w) == (b * w) >> 8 for a byte b and a 16-bit weight w
-		const uint32_t c00 = (__byte_perm(t00, 0, 0x4440 + c) * f1u1v) >> 8;
-		const uint32_t c10 = (__byte_perm(t10, 0, 0x4440 + c) * f0u1v) >> 8;
-		const uint32_t c01 = (__byte_perm(t01, 0, 0x4440 + c) * f1u0v) >> 8;
-		const uint32_t c11 = (__byte_perm(t11, 0, 0x4440 + c) * f0u0v) >> 8;
+		uint32_t c00, c10, c01, c11;
+		if(!FAST && d.texSrgb) // the benchmark sampler (FAST) is only selected for UNORM images
+		{
+			c00 = mulhi16(texel16(true, t00, c), f1u1v); c10 = mulhi16(texel16(true, t10, c), f0u1v);
+			c01 = mulhi16(texel16(true, t01, c), f1u0v); c11 = mulhi16(texel16(true, t11, c), f0u0v);
+		}
+		else
+		{
+			// mulhi(b << 8, w) == (b * w) >> 8 for a byte b and a 16-bit weight w
+			c00 = (__byte_perm(t00, 0, 0x4440 + c) * f1u1v) >> 8;
+			c10 = (__byte_perm(t10, 0, 0x4440 + c) * f0u1v) >> 8;
+			c01 = (__byte_perm(t01, 0, 0x4440 + c) * f1u0v) >> 8;
+			c11 = (__byte_perm(t11, 0, 0x4440 + c) * f0u0v) >> 8;
+		}
 		out[c] = (((c00 + c10) & 0xFFFF) + ((c01 + c11) & 0xFFFF)) & 0xFFFF;
 	}
 }
@@ -889,7 +909,7 @@ DEVI void sample_level_split_point(const DrawConst &d, int ilod, float u, float 
 #pragma unroll
 	for(int c = 0; c < 4; c++)
 	{
-		const uint32_t tx = ((t >> (8 * c)) & 0xFF) << 8;
+		const uint32_t tx = texel16(d.texSrgb != 0, t, c);
 		out[c] = (((mulhi16(tx, w00) + mulhi16(tx, w10)) & 0xFFFF) + ((mulhi16(tx, w01) + mulhi16(tx, w11)) & 0xFFFF)) & 0xFFFF;
 	}
 }

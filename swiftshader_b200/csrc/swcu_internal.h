@@ -178,6 +178,7 @@ struct DrawConst
 	uint32_t texLevels;
 	uint32_t magFilter, minFilter, mipmapMode, addressU, addressV;
 	float mipLodBias, minLod, maxLod;
+	uint32_t texSrgb; // R8G8B8A8_SRGB image: RGB texels go through the reference's sRGBtoLinearFF_FF00 table (SamplerCore.cpp:1966-1977)
 	uint32_t texFast; // REPEAT/REPEAT, LINEAR/LINEAR, MIPMAP_LINEAR: the benchmark sampler, state tests folded away
 
 	// ---- work buffers ----

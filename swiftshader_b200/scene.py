@@ -70,6 +70,7 @@ class Texture:
     maxLod: float = 0.0
     set: int = 0
     binding: int = 0
+    srgb: bool = False  # R8G8B8A8_SRGB instead of R8G8B8A8_UNORM
 
     def packed(self) -> np.ndarray:
         """All levels back to back, tightly packed (the layout both the ICD upload and our desc use)."""
@@ -268,7 +269,7 @@ class Scene:
             keep.append(packed)
             dev.append(packed)
             si = d.sampledImage[0]
-            si.set, si.binding, si.format, si.levelCount = t.set, t.binding, FMT_R8G8B8A8_UNORM, len(t.levels)
+            si.set, si.binding, si.format, si.levelCount = t.set, t.binding, (FMT_R8G8B8A8_SRGB if t.srgb else FMT_R8G8B8A8_UNORM), len(t.levels)
             off = 0
             for l in range(capi.MIPMAP_LEVELS):
                 ll = min(l, len(t.levels) - 1)
@@ -317,7 +318,7 @@ class Scene:
                              dr.colorWriteMask, *dr.blendConstants, dr.sampleMask & 0xFFFFFFFF)
             t = dr.texture
             if t is not None:
-                r += struct.pack("<5I5I3f2I", 1, blob(t.packed()), t.levels[0].shape[1], t.levels[0].shape[0], len(t.levels),
+                r += struct.pack("<5I5I3f2I", 2 if t.srgb else 1, blob(t.packed()), t.levels[0].shape[1], t.levels[0].shape[0], len(t.levels),
                                  t.magFilter, t.minFilter, t.mipmapMode, t.addressModeU, t.addressModeV,
                                  t.mipLodBias, t.minLod, t.maxLod, t.set, t.binding)
             else:

@@ -309,9 +309,15 @@ def _rand_tex(rng, w, h, levels):
     return out
 
 
-def texture(seed: int) -> Scene:
+def srgbtex(seed: int) -> Scene:
+    """The sampler sweep of texture() on an R8G8B8A8_SRGB image: RGB texels go through the reference's sRGBtoLinearFF_FF00 table
+    before filtering (SamplerCore.cpp:1966-1977), alpha does not."""
+    return texture(seed, srgb=True)
+
+
+def texture(seed: int, srgb: bool = False) -> Scene:
     """Sampler sweep: uv in [-4,5], filters, mip modes, address modes, LOD bias, independent random mip levels (R14)."""
-    rng = np.random.default_rng(7000 + seed)
+    rng = np.random.default_rng((7700 if srgb else 7000) + seed)
     variants = [
         dict(w=16, h=16, levels=1, maxLod=0.0),                                   # the benchmark's case
         dict(w=64, h=32, levels=1, maxLod=0.0),
@@ -325,7 +331,7 @@ def texture(seed: int) -> Scene:
         dict(w=16, h=16, levels=1, maxLod=0.0, magFilter=FILTER_NEAREST, minFilter=FILTER_NEAREST, mipmapMode=MIPMAP_NEAREST),
     ]
     v = dict(variants[seed % len(variants)])
-    tex = Texture(_rand_tex(rng, v.pop("w"), v.pop("h"), v.pop("levels")), **v)
+    tex = Texture(_rand_tex(rng, v.pop("w"), v.pop("h"), v.pop("levels")), srgb=srgb, **v)
     tris = []
     for i in range(3):
         p = _tri_kind(rng, [5, 0, 1][i])
@@ -473,6 +479,7 @@ FAMILIES = {
     "srgb": (srgb, 14),
     "floatrt": (floatrt, 20),
     "pathological": (pathological, 16),
+    "srgbtex": (srgbtex, 12),
 }
 
 
