@@ -152,6 +152,7 @@ typedef struct swcu_draw_desc
 	/* --- multisampling */
 	uint32_t sampleCount; /* 1 or 4 */
 	uint32_t sampleMask;
+	uint32_t alphaToCoverageEnable; /* VkPipelineMultisampleStateCreateInfo (Context.cpp:526); thresholds of Renderer.cpp:391-410 */
 
 	/* --- depth / stencil (PixelProcessor.cpp:74-140) */
 	uint32_t depthTestEnable;
@@ -160,6 +161,8 @@ typedef struct swcu_draw_desc
 	uint32_t stencilTestEnable;
 	swcu_stencil_face front;
 	swcu_stencil_face back;
+	uint32_t depthBoundsTestEnable; /* Context.cpp:960-962; active only with a depth attachment (Context.cpp:946-949) */
+	float minDepthBounds, maxDepthBounds;
 
 	/* --- colour output: blend state BEFORE folding; the library folds it like
 	 *     FragmentOutputInterfaceState::getBlendState (src/Device/Context.cpp:1090-1270). */

@@ -159,6 +159,9 @@ int main(int argc, char **argv)
 	VkDeviceCreateInfo dci{ VK_STRUCTURE_TYPE_DEVICE_CREATE_INFO };
 	dci.queueCreateInfoCount = 1;
 	dci.pQueueCreateInfos = &qci;
+	VkPhysicalDeviceFeatures feat{};
+	feat.depthBounds = VK_TRUE;
+	dci.pEnabledFeatures = &feat;
 	CHECK(vkCreateDevice(pd, &dci, nullptr, &dev));
 	VkQueue queue;
 	vkGetDeviceQueue(dev, 0, 0, &queue);
@@ -377,11 +380,15 @@ int main(int argc, char **argv)
 		mss.rasterizationSamples = S;
 		VkSampleMask smask = d.sampleMask;
 		mss.pSampleMask = &smask;
+		mss.alphaToCoverageEnable = d.alphaToCoverageEnable;
 		VkPipelineDepthStencilStateCreateInfo ds{ VK_STRUCTURE_TYPE_PIPELINE_DEPTH_STENCIL_STATE_CREATE_INFO };
 		ds.depthTestEnable = d.depthTestEnable;
 		ds.depthWriteEnable = d.depthWriteEnable;
 		ds.depthCompareOp = (VkCompareOp)d.depthCompareOp;
 		ds.stencilTestEnable = d.stencilTestEnable;
+		ds.depthBoundsTestEnable = d.depthBoundsTestEnable;
+		ds.minDepthBounds = d.minDepthBounds;
+		ds.maxDepthBounds = d.maxDepthBounds;
 		auto face = [](const SceneStencilFace &f) {
 			VkStencilOpState s{};
 			s.failOp = (VkStencilOp)f.failOp; s.passOp = (VkStencilOp)f.passOp; s.depthFailOp = (VkStencilOp)f.depthFailOp;

@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define SCENE_MAGIC 0x43535753u /* "SWSC" */
-#define SCENE_VERSION 2u
+#define SCENE_VERSION 3u
 #define SCENE_MAX_ATTRIBS 8
 
 #pragma pack(push, 4)
@@ -56,6 +56,8 @@ typedef struct SceneDraw
 	uint32_t magFilter, minFilter, mipmapMode, addressModeU, addressModeV;
 	float mipLodBias, minLod, maxLod;
 	uint32_t texSet, texBinding;
+	uint32_t alphaToCoverageEnable, depthBoundsTestEnable;
+	float minDepthBounds, maxDepthBounds;
 } SceneDraw;
 
 typedef struct SceneBlob { uint64_t offset, size; } SceneBlob;

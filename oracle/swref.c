@@ -115,7 +115,7 @@ typedef struct
 	/* folded blend state (Device/Context.cpp:1090-1117) */
 	int blendEnable, srcF, dstF, op, srcFA, dstFA, opA;
 	int colorWriteMask;
-	int depthTestActive, depthWriteEnable, stencilActive;
+	int depthTestActive, depthWriteEnable, stencilActive, depthBoundsActive;
 	int floatTarget, colorBpp; /* R32G32B32A32_SFLOAT / R16G16B16A16_SFLOAT colour attachment; bytes per pixel */
 	int numVaryings; /* packed interpolants = set bits of fs->inputMask */
 	int interpolateZ, interpolateW;
@@ -1008,11 +1008,46 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 					c[i][ch] = dr->floatTarget ? val : sse_min(sse_max(val, 0.0f), 1.0f);
 				}
 
+			/* alphaTest (PixelProgram.cpp:243-259) -> alphaToCoverage (PixelRoutine.cpp:643-658): the clamped c[0].w against the
+			 * per-sample thresholds of Renderer.cpp:391-410, CmpNLT (a NaN alpha passes); then :319-326 */
+			if(d->alphaToCoverageEnable)
+			{
+				static const float a2c4[4] = { 0.2f, 0.4f, 0.6f, 0.8f };
+				for(int q = 0; q < ms; q++)
+				{
+					if(!(d->sampleMask & (1u << q))) continue;
+					const float thr = ms == 4 ? a2c4[q] : 0.5f;
+					int aMask = 0;
+					for(int i = 0; i < 4; i++)
+						if(!(c[i][3] < thr)) aMask |= 1 << i;
+					cMask[q] &= aMask;
+					zMask[q] &= cMask[q];
+					sMask[q] &= cMask[q];
+				}
+			}
+
 			/* depth test :494-574 (late) */
 			int depthPass = !dr->depthTestActive;
 			for(int q = 0; q < ms; q++)
 			{
 				if(!(d->sampleMask & (1u << q))) continue;
+				/* depthBoundsTest :576-641 reads the stored depth BEFORE this fragment's write (both run before writeDepth) */
+				int bTest = 0xF;
+				if(dr->depthBoundsActive)
+				{
+					const char *zb = (const char *)d->depth.buffer + (size_t)q * d->depth.sliceB;
+					bTest = 0;
+					for(int i = 0; i < 4; i++)
+					{
+						float zValue;
+						if(d->depth.format == FMT_D16_UNORM)
+							zValue = (float)*(const uint16_t *)(zb + (size_t)(y + (i >> 1)) * d->depth.pitchB + 2 * (size_t)(x + (i & 1))) * (1.0f / 0xFFFF);
+						else
+							zValue = *(const float *)(zb + (size_t)(y + (i >> 1)) * d->depth.pitchB + 4 * (size_t)(x + (i & 1)));
+						if(d->minDepthBounds <= zValue && zValue <= d->maxDepthBounds) bTest |= 1 << i;
+					}
+					if(!dr->depthTestActive) cMask[q] &= zMask[q] & bTest; /* :634-637 */
+				}
 				if(dr->depthTestActive)
 				{
 					char *zb = (char *)d->depth.buffer + (size_t)q * d->depth.sliceB;
@@ -1049,6 +1084,7 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 					zMask[q] = zTest & cMask[q];
 					if(dr->stencilActive) zMask[q] &= sMask[q];
 					if(zMask[q]) depthPass = 1;
+					zMask[q] &= cMask[q] & bTest; /* :638-641, after depthPass was taken */
 				}
 			}
 			if(depthPass)
@@ -1233,6 +1269,7 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 	dr.ms = (int)d->sampleCount;
 	dr.enableMultiSampling = dr.ms > 1;
 	dr.depthTestActive = d->depthTestEnable && d->depth.buffer;
+	dr.depthBoundsActive = d->depthBoundsTestEnable && d->depth.buffer; /* Context.cpp:946-949 */
 	dr.floatTarget = floatTarget;
 	dr.colorBpp = d->color.format == FMT_R32G32B32A32_SFLOAT ? 16 : (d->color.format == FMT_R16G16B16A16_SFLOAT ? 8 : 4);
 	dr.depthWriteEnable = dr.depthTestActive && d->depthWriteEnable; /* FragmentState::depthWriteActive */

@@ -63,9 +63,10 @@ class DrawDesc(C.Structure):
         ("scissor", Rect), ("renderArea", Rect),
         ("cullMode", C.c_uint32), ("frontFace", C.c_uint32), ("depthClipEnable", C.c_uint32),
         ("depthBiasConstant", C.c_float), ("depthBiasSlope", C.c_float), ("depthBiasClamp", C.c_float),
-        ("sampleCount", C.c_uint32), ("sampleMask", C.c_uint32),
+        ("sampleCount", C.c_uint32), ("sampleMask", C.c_uint32), ("alphaToCoverageEnable", C.c_uint32),
         ("depthTestEnable", C.c_uint32), ("depthWriteEnable", C.c_uint32), ("depthCompareOp", C.c_uint32),
         ("stencilTestEnable", C.c_uint32), ("front", StencilFace), ("back", StencilFace),
+        ("depthBoundsTestEnable", C.c_uint32), ("minDepthBounds", C.c_float), ("maxDepthBounds", C.c_float),
         ("blendEnable", C.c_uint32),
         ("srcColorBlendFactor", C.c_uint32), ("dstColorBlendFactor", C.c_uint32), ("colorBlendOp", C.c_uint32),
         ("srcAlphaBlendFactor", C.c_uint32), ("dstAlphaBlendFactor", C.c_uint32), ("alphaBlendOp", C.c_uint32),

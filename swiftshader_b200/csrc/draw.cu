@@ -632,6 +632,14 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	d.depthWriteEnable = d.depthTestActive && desc->depthWriteEnable;
 	if(desc->depthCompareOp > CMP_ALWAYS) return fail(ctx, SWCU_E_INVALID, "bad depth compare op");
 	d.depthCompareOp = desc->depthCompareOp;
+	d.alphaToCoverage = desc->alphaToCoverageEnable != 0;
+	d.depthBounds = 0;
+	if(desc->depthBoundsTestEnable && desc->depth.buffer) // FragmentState::depthBoundsTestActive, Context.cpp:946-949
+	{
+		d.depthBounds = d.depthTestActive ? 1 : 2;
+		d.minDepthBounds = desc->minDepthBounds; d.maxDepthBounds = desc->maxDepthBounds;
+		if(!d.depthTestActive) { d.depthTestActive = 1; d.depthCompareOp = CMP_ALWAYS; d.depthWriteEnable = 0; } // stage the depth plane, test nothing else
+	}
 	d.stencilActive = desc->stencilTestEnable && desc->stencil.buffer;
 	auto face = [](const swcu_stencil_face &s) { KStencilFace k; k.failOp = s.failOp; k.passOp = s.passOp; k.depthFailOp = s.depthFailOp; k.compareOp = s.compareOp; k.compareMask = s.compareMask & 0xFF; k.writeMask = s.writeMask & 0xFF; k.reference = s.reference & 0xFF; k.pad = 0; return k; };
 	d.front = face(desc->front); d.back = face(desc->back);
@@ -770,6 +778,7 @@ static void launch_tile4(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps
 static bool fast_state(const swcu_ctx *ctx, const DrawConst &d)
 {
 	if(!ctx->optFastState) return false;
+	if(d.alphaToCoverage || d.depthBounds) return false;
 	if(d.stencilActive || d.stencilWrite || !d.colorBuf || d.colorWriteMask != 0xFu || d.bgr || d.srgb || d.colorEpp != 1 || d.depthBiasEnable || d.depth16) return false;
 	if(d.depthTestActive && d.depthCompareOp != CMP_LESS && d.depthCompareOp != CMP_LESS_OR_EQUAL) return false;
 	if(d.ms == 4 && (d.sampleMask & 0xFu) != 0xFu) return false;

@@ -1749,6 +1749,10 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 								sValue = smStencil[pi];
 								sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
 							}
+							// alphaToCoverage (PixelRoutine.cpp:643-658, thresholds Renderer.cpp:391-410): CmpNLT, so a NaN alpha stays covered; a
+							// sample that loses its coverage leaves every later stage, stencil write included (:319-326)
+							bool alive = true;
+							if(!FS && d.alphaToCoverage) alive = !(rgba[3] < (MS == 4 ? (q == 0 ? 0.2f : q == 1 ? 0.4f : q == 2 ? 0.6f : 0.8f) : 0.5f));
 							bool zPass = true;
 							float z = 0.0f;
 							if(d.depthTestActive)
@@ -1778,8 +1782,17 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 									if(FS) zPass = d.depthCompareOp == CMP_LESS ? !(zValue <= z) : !(zValue < z); // LESS / LESS_OR_EQUAL (:533-553)
 									else zPass = depth_compare(d.depthCompareOp, zValue, z);
 								}
+								if(!FS && d.depthBounds)
+								{
+									// depthBoundsTest :576-641: the STORED depth (read before this fragment's write) against [min, max]; with a depth
+									// test it narrows the depth mask, so the stencil depth-fail op sees it; without one it narrows the coverage
+									const float stored = d.depth16 ? fmul((float)((const unsigned short *)smDepth)[pi], 1.0f / 0xFFFF) : smDepth[pi];
+									const bool inside = d.minDepthBounds <= stored && stored <= d.maxDepthBounds;
+									if(d.depthBounds == 2) alive = alive && inside;
+									else zPass = zPass && inside;
+								}
 							}
-							if(zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
+							if(alive && zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
 							{
 								if(d.depthWriteEnable)
 								{
@@ -1866,7 +1879,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 									dirty = true;
 								}
 							}
-							if(!FS && d.stencilWrite) // writeStencil :754-817
+							if(!FS && d.stencilWrite && alive) // writeStencil :754-817
 							{
 								const KStencilFace &face = frontFacing ? d.front : d.back;
 								const uint32_t ref = face.reference & 0xFF;

@@ -159,6 +159,10 @@ struct DrawConst
 	uint32_t depthTestActive, depthWriteEnable, depthCompareOp;
 	uint32_t depth16; // D16_UNORM depth buffer: quantised compare / saturating write (PixelRoutine.cpp:466-482,508-511,687-711)
 	uint32_t stencilActive, stencilWrite;
+	uint32_t alphaToCoverage; // c[0].w against the per-sample thresholds of Renderer.cpp:391-410 (PixelRoutine.cpp:643-658)
+	uint32_t depthBounds;     // 0 off; 1: failing samples leave the depth mask (:638-641); 2: no depth test in the reference's state, failing
+	                          //    samples leave the coverage mask (:634-637) - the depth plane is still staged, compare op forced to ALWAYS
+	float minDepthBounds, maxDepthBounds;
 	KStencilFace front, back;
 	uint32_t blendEnable, srcF, dstF, op, srcFA, dstFA, opA; // op/opA are KOP_*
 	uint32_t colorWriteMask;

@@ -129,6 +129,8 @@ class Draw:
     colorWriteMask: int = 0xF
     blendConstants: tuple = (0.0, 0.0, 0.0, 0.0)
     sampleMask: int = 0xFFFFFFFF
+    alphaToCoverage: bool = False
+    depthBounds: Optional[tuple] = None  # (min, max) enables the depth bounds test
     texture: Optional[Texture] = None
 
     def vertex_count(self) -> int:
@@ -245,6 +247,9 @@ class Scene:
         d.cullMode, d.frontFace, d.depthClipEnable = draw.cullMode, draw.frontFace, 1
         d.depthBiasConstant, d.depthBiasClamp, d.depthBiasSlope = draw.depthBias
         d.sampleCount, d.sampleMask = self.samples, draw.sampleMask & ((1 << self.samples) - 1) if self.samples > 1 else 1
+        d.alphaToCoverageEnable = int(draw.alphaToCoverage)
+        if draw.depthBounds is not None:
+            d.depthBoundsTestEnable, (d.minDepthBounds, d.maxDepthBounds) = 1, draw.depthBounds
         d.depthTestEnable, d.depthWriteEnable, d.depthCompareOp = int(draw.depthTest), int(draw.depthWrite), draw.depthCompareOp
         d.stencilTestEnable = int(draw.stencilTest)
         d.front = capi.StencilFace(*draw.front.tuple())
@@ -323,8 +328,9 @@ class Scene:
                                  t.mipLodBias, t.minLod, t.maxLod, t.set, t.binding)
             else:
                 r += struct.pack("<5I5I3f2I", 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0, 0)
+            r += struct.pack("<IIff", int(dr.alphaToCoverage), int(dr.depthBounds is not None), *(dr.depthBounds or (0.0, 1.0)))
             recs.append(r)
-        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 2, self.width, self.height, self.samples, self.colorFormat,
+        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 3, self.width, self.height, self.samples, self.colorFormat,
                           (2 if self.depthFormat == FMT_D16_UNORM else 1) if self.hasDepth else 0, int(self.hasStencil), *self.clearColor, self.clearDepth, self.clearStencil,
                           len(recs), len(blobs))
         off = len(hdr) + sum(len(r) for r in recs) + 16 * len(blobs)

@@ -271,6 +271,50 @@ _BLEND_MATRIX = [
 ]
 
 
+def fragtests(seed: int) -> Scene:
+    """alphaToCoverage (PixelRoutine.cpp:643-658 with the thresholds of Renderer.cpp:391-410: the coverage feeds the depth,
+    stencil and colour masks, :319-326) and the depth bounds test (:576-641: against the STORED depth, D32F and D16, folding into
+    the coverage mask without a depth test and into the depth mask with one, so that the stencil depth-fail op sees it)."""
+    rng = np.random.default_rng(4700 + seed)
+    col = dict(clearColor=(0.1, 0.2, 0.3, 1.0))
+
+    def layers(n, persp=True):
+        v = _layers(rng, n, persp)
+        v[:, 7] = rng.uniform(-0.1, 1.1, v.shape[0]).astype(np.float32)  # per-vertex alpha crossing every threshold
+        return v
+
+    inc = StencilFace(passOp=SOP_INC_WRAP, failOp=SOP_INVERT, depthFailOp=SOP_DEC_WRAP, compareOp=CMP_ALWAYS)
+    if seed < 8:
+        ms = 4 if seed % 2 else 1
+        kw = {}
+        if seed in (2, 3):
+            kw = dict(blend=True)
+        elif seed in (4, 5):
+            kw = dict(depthTest=True, depthWrite=True, depthCompareOp=CMP_LESS_OR_EQUAL, stencilTest=True, front=inc,
+                      back=StencilFace(passOp=SOP_REPLACE, depthFailOp=SOP_INC_CLAMP, compareOp=CMP_NOT_EQUAL, reference=3))
+        elif seed == 6:
+            kw = dict(stencilTest=True, front=inc, back=inc, colorWriteMask=0x7)
+        elif seed == 7:
+            kw = dict(sampleMask=0b1010, blend=True, depthTest=True, depthWrite=True)
+        d = Draw(layers(10), P4C4, "vs_pos4_col4", "fs_col4", alphaToCoverage=True, **kw)
+        fmt = dict(colorFormat=FMT_R16G16B16A16_SFLOAT) if seed == 2 else {}
+        return Scene(CELL, CELL, [d], samples=ms, hasDepth=True, hasStencil=seed in (4, 5, 6), clearDepth=0.8, **col, **fmt)
+    # depth bounds: a first draw lays the stored depth down, the second is bounded by it
+    k = seed - 8
+    ms = 4 if k % 4 == 3 else 1
+    lo = float(np.float32(rng.uniform(0.25, 0.45)))
+    hi = float(np.float32(lo + rng.uniform(0.1, 0.3)))
+    d1 = Draw(_layers(rng, 8), P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, depthCompareOp=CMP_LESS)
+    test = k % 2 == 0
+    kw = dict(depthTest=test, depthWrite=test and k % 3 != 0, depthCompareOp=(CMP_LESS_OR_EQUAL, CMP_GREATER, CMP_ALWAYS)[k % 3])
+    sten = k in (2, 3, 6, 7)
+    if sten:
+        kw.update(stencilTest=True, front=inc, back=StencilFace(passOp=SOP_REPLACE, depthFailOp=SOP_INVERT, compareOp=CMP_ALWAYS, reference=0x5A))
+    d2 = Draw(layers(8), P4C4, "vs_pos4_col4", "fs_col4", depthBounds=(lo, hi), blend=k % 4 == 1, alphaToCoverage=k in (5, 7), **kw)
+    fmt = dict(depthFormat=FMT_D16_UNORM) if k in (1, 4, 7) and not sten else {}
+    return Scene(CELL, CELL, [d1, d2], samples=ms, hasDepth=True, hasStencil=sten, clearDepth=float(np.float32(rng.uniform(0.3, 0.9))), **col, **fmt)
+
+
 def blend(seed: int) -> Scene:
     """Blend-factor matrix on RGBA8 with overlapping triangles in one draw (R10/R11 + ordering)."""
     rng = np.random.default_rng(5000 + seed)
@@ -480,6 +524,7 @@ FAMILIES = {
     "floatrt": (floatrt, 20),
     "pathological": (pathological, 16),
     "srgbtex": (srgbtex, 12),
+    "fragtests": (fragtests, 16),
 }
 
 
