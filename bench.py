@@ -265,18 +265,81 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item()) / args.steps
 
-        # ---- end to end through the C-ABI with HOST buffers: H2D of the step's inputs and D2H of the frame inside the timed region ----
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            frame.upload_inputs(); step(frame.download_final if rank == 0 else None)
-            dev.sync()
+        # ---- end to end through the C-ABI with HOST buffers: H2D of the step's inputs and D2H of the frame inside the timed region.
+        #      A render loop with several frames in flight, bounded by a fence per frame (a Vulkan application's per-frame vk::Fence):
+        #      the library's copy streams bring frame i+1's inputs up and frame i-1's pixels down while frame i renders ----
+        e2e_steps = max(3, min(args.steps, 10)) if N > 1 else max(6, min(args.steps, 30))
+        if gather == "nccl":
+            dev.set_option("copy_streams", 0)  # the all-gather writes the frame on the caller's stream, unseen by the library
+        if N == 1:
+            # Three stages overlap - frame i+1's inputs going up, frame i rendering, frame i-1 coming down - so the loop holds
+            # two sets of input buffers (per-frame dynamic vertex data, as an application double-buffers it) and, with MSAA,
+            # three resolve targets; a fence per frame bounds the frames in flight.
+            import dataclasses
+            alt_inputs, alt_keep = [], []
+            alt_descs = [sc.build_desc(dataclasses.replace(dr, vertices=np.array(dr.vertices, dtype=np.float32, copy=True),
+                                                           indices=None if dr.indices is None else dr.indices.copy()),
+                                       frame.att, alt_keep, area, alt_inputs) for dr in sc.draws]
+            for b in alt_inputs:
+                dev.register(b, upload=False)
+            in_sets = [(frame.inputs, frame.descs), (alt_inputs, alt_descs)]
+            outs, dsts = [frame.final_image()], [dst_b]
+            if dst_b is not None:
+                for _ in range(2):
+                    extra = np.zeros_like(frame.resolved)
+                    dev.register(extra, upload=False)
+                    outs.append(extra[0])
+                    dsts.append(band_att(extra, H2 * pitch))
+            F = len(outs)  # frames in flight (1x: the colour attachment itself is the only host-visible image)
+
+            skip = set(filter(None, os.environ.get("SWCU_E2E_SKIP", "").split(",")))  # diagnosis only: the reported e2e runs with nothing skipped
+
+            def upload_set(k):
+                if "upload" in skip:
+                    return
+                for b in in_sets[k][0]:
+                    dev.upload(b)
+
+            def e2e_frame(i):
+                upload_set((i + 1) % 2)  # next frame's inputs, behind this frame's on the upload stream
+                for d_ in in_sets[i % 2][1]:
+                    dev.draw(d_)
+                k = i % F
+                if dsts[k] is not None:
+                    dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(dsts[k])))
+                if F == 1 and i >= 1:
+                    dev.fence_wait((i - 1) % 2)  # the one host image: frame i-1 is consumed before frame i may land in it
+                if "download" not in skip:
+                    dev.download(outs[k])
+                dev.fence_signal(i % max(F, 2))
+                if F > 1 and i >= F - 1:
+                    dev.fence_wait((i - (F - 1)) % F)  # frame i-2 is on the host now
+
+            def e2e_run(n):
+                upload_set(0)  # frame 0's inputs; every frame of the loop uploads one set, so n frames move n sets
+                for i in range(n):
+                    e2e_frame(i)
+                dev.sync()
+            frames_in_flight = max(F, 2)
+        else:
+            def e2e_frame(i):
+                frame.upload_inputs()
+                step(frame.download_final if rank == 0 else None)
+                dev.fence_signal(i % 2)
+                if i >= 1:
+                    dev.fence_wait((i - 1) % 2)  # frame i-1 is on the host now
+
+            def e2e_run(n):
+                for i in range(n):
+                    e2e_frame(i)
+                dev.sync()
+            frames_in_flight = 2
+
+        e2e_run(3)
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            frame.upload_inputs()
-            step(frame.download_final if rank == 0 else None)
-            dev.sync()
+        e2e_run(e2e_steps)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], device=f"cuda:{local_rank}")
@@ -325,7 +388,7 @@ def main():
                        "gather": gather},
             "clocks": clock_info,
             "e2e": {"value": wl.covered_pixels / (e2e_ms * 1e-3) / 1e9, "unit": "Gpixels/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "frames_in_flight": frames_in_flight},
             "gpu_launches": int(st.kernelLaunches),
             "gpu_launches_note": "kernels of libswcuda.so launched in the timed region (excludes the CUB scan/sort kernels between them)",
             "kernels_ms": kernels,

@@ -228,13 +228,26 @@ int swcu_mem_register(swcu_ctx *ctx, const void *host_base, size_t bytes);
  * nothing is allocated, copied or freed by the library.  Unregister with swcu_mem_unregister(ctx, device_base). */
 int swcu_mem_register_device(swcu_ctx *ctx, void *device_base, size_t bytes);
 int swcu_mem_unregister(swcu_ctx *ctx, const void *host_base);
-int swcu_mem_upload(swcu_ctx *ctx, const void *host_ptr, size_t bytes);   /* host -> shadow, async on the context stream */
-int swcu_mem_download(swcu_ctx *ctx, void *host_ptr, size_t bytes);       /* shadow -> host, async; complete after swcu_sync */
+/* Copies are asynchronous and run on the library's two copy streams (one per DMA direction), ordered against the kernels by
+ * events: an upload is visible to every call issued after it; it waits for kernels issued earlier that touch the same shadow
+ * and for a download of it still in flight.  A download sees every call issued before it; calls issued later that overwrite
+ * the shadow wait for it.  So frame n+1's inputs go up and frame n-1's pixels come down while frame n renders.  The host
+ * may read a downloaded range after swcu_sync or after waiting for a fence signalled after the download.
+ * (option "copy_streams" = 0 puts the copies back on the context stream.) */
+int swcu_mem_upload(swcu_ctx *ctx, const void *host_ptr, size_t bytes);   /* host -> shadow */
+int swcu_mem_download(swcu_ctx *ctx, void *host_ptr, size_t bytes);       /* shadow -> host */
 void *swcu_mem_device_ptr(swcu_ctx *ctx, const void *host_ptr);           /* device address of the shadow (for NCCL plumbing); NULL if unregistered */
 
 /* ---- the hot path ---- */
 int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc); /* replaces DrawCall::run; asynchronous */
 int swcu_sync(swcu_ctx *ctx);                             /* replaces Renderer::synchronize (Renderer.cpp:664-671) */
+/* Completion of a submission without draining the device: the CountedEvent argument of sw::Renderer::draw (Renderer.cpp:184,
+ * counted up at :499-501 and done at :507-510) that vk::Fence waits on.  signal: "everything issued so far, copies included";
+ * wait: block the host on the last signal of that slot (returns at once if the slot was never signalled).  With two slots a
+ * render loop keeps two frames in flight. */
+#define SWCU_MAX_FENCES 8
+int swcu_fence_signal(swcu_ctx *ctx, uint32_t slot);
+int swcu_fence_wait(swcu_ctx *ctx, uint32_t slot);
 
 /* ---- the steps either side of the draw, on the resident shadows ---- */
 /* Blitter::fastClear (src/Device/Blitter.cpp:170-325) for RGBA8 / D32F / S8 (and the 2 / 8 / 16-byte fills of D16, RGBA16F, RGBA32F clears): fills `samples` slices. */

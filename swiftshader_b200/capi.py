@@ -104,6 +104,7 @@ EXPORTS = [
     "swcu_set_stream", "swcu_timer_begin", "swcu_timer_end", "swcu_get_stats", "swcu_reset_stats",
     "swcu_set_profiling", "swcu_last_draw_kernels", "swcu_set_option", "swcu_version",
     "swcu_ipc_export", "swcu_ipc_open", "swcu_ipc_close", "swcu_copy_image", "swcu_signal", "swcu_wait_flags",
+    "swcu_fence_signal", "swcu_fence_wait",
 ]
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -152,6 +153,8 @@ def lib() -> C.CDLL:
     L.swcu_copy_image.argtypes = [vp, C.POINTER(Attachment), C.POINTER(Attachment)]
     L.swcu_signal.argtypes = [vp, vp, u32]
     L.swcu_wait_flags.argtypes = [vp, vp, u32, u32, u32]
+    L.swcu_fence_signal.argtypes = [vp, u32]
+    L.swcu_fence_wait.argtypes = [vp, u32]
     L.swcu_version.argtypes = []
     L.swcu_version.restype = C.c_char_p
     for name in EXPORTS:

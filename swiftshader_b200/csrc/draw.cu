@@ -30,6 +30,16 @@ struct Shadow
 	unsigned char *dev = nullptr;
 	bool pinned = false;
 	bool external = false; // caller-owned device memory (swcu_mem_register_device): identity mapping
+	// copy-stream hazards: a download in flight on the download stream must finish before the shadow is overwritten (by a
+	// kernel on the main stream or by an upload); a shadow kernels of the main stream touch (attachment, sampled image,
+	// clear / resolve / copy operand) must not be overwritten by an upload before those kernels are done
+	cudaEvent_t dlEvent = nullptr;
+	bool dlPendingMain = false, dlPendingUpload = false;
+	bool mainTouched = false;
+	// the last upload into this shadow: readers wait for THIS one, not for uploads issued after it (the next frame's inputs
+	// already on their way up must not hold back the current frame)
+	cudaEvent_t upEvent = nullptr;
+	uint64_t upSeq = 0;
 };
 
 struct KernelTime
@@ -56,8 +66,18 @@ struct swcu_ctx
 	} set[2];
 	int cur = 0;
 	cudaStream_t setupStream = nullptr;
-	cudaEvent_t evUpload = nullptr; // last swcu_mem_upload / clear on the main stream (inputs of the setup phase)
-	bool evUploadValid = false;
+	// Host<->device copies run on their own two streams (one per DMA direction), so the upload of the next frame's inputs and
+	// the download of the previous frame overlap the kernels of the current one; events order them against the kernels:
+	cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
+	cudaEvent_t evUpload = nullptr;  // after the last swcu_mem_upload
+	uint64_t uploadSeq = 0, mainSawUpload = 0, setupSawUpload = 0, d2hSawUpload = 0;
+	cudaEvent_t evMark = nullptr;    // scratch: "the main stream up to here"
+	cudaEvent_t evDownload = nullptr; // after the last swcu_mem_download
+	uint64_t downloadSeq = 0, mainSawDownload = 0;
+	bool mainReadsInputs = false;    // a setup phase ran on the main stream since the last upload looked
+	cudaEvent_t fence[SWCU_MAX_FENCES] = {};
+	bool fenceValid[SWCU_MAX_FENCES] = {};
+	int optCopyStreams = 1;
 	int optPipeline = 1;
 	DevBuf keys, vals, keys2, vals2, tileBegin, tileEnd, cubTemp, zeroPage;
 	swcu_stats stats{};
@@ -140,6 +160,12 @@ extern "C" int swcu_create(swcu_ctx **out, int device_ordinal)
 	if((e = cudaEventCreate(&ctx->t1)) != cudaSuccess) return bail("cudaEventCreate", e);
 	if((e = cudaStreamCreateWithFlags(&ctx->setupStream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
 	if((e = cudaEventCreateWithFlags(&ctx->evUpload, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+	if((e = cudaEventCreateWithFlags(&ctx->evMark, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+	if((e = cudaEventCreateWithFlags(&ctx->evDownload, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+	if((e = cudaStreamCreateWithFlags(&ctx->h2dStream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+	if((e = cudaStreamCreateWithFlags(&ctx->d2hStream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+	for(auto &f : ctx->fence)
+		if((e = cudaEventCreateWithFlags(&f, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
 	for(auto &S : ctx->set)
 	{
 		if((e = cudaMallocHost((void **)&S.hostCounters, sizeof(DrawCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -154,10 +180,14 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 	if(!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	if(ctx->h2dStream) cudaStreamSynchronize(ctx->h2dStream);
+	if(ctx->d2hStream) cudaStreamSynchronize(ctx->d2hStream);
 	for(auto &kv : ctx->mem)
 	{
 		if(kv.second.pinned) cudaHostUnregister((void *)kv.second.host);
 		if(!kv.second.external) cudaFree(kv.second.dev);
+		if(kv.second.dlEvent) cudaEventDestroy(kv.second.dlEvent);
+		if(kv.second.upEvent) cudaEventDestroy(kv.second.upEvent);
 	}
 	if(ctx->setupStream) cudaStreamSynchronize(ctx->setupStream);
 	DevBuf *bufs[] = { &ctx->keys, &ctx->vals, &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->zeroPage };
@@ -170,6 +200,12 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 		if(S.tileDone) cudaEventDestroy(S.tileDone);
 	}
 	if(ctx->evUpload) cudaEventDestroy(ctx->evUpload);
+	if(ctx->evMark) cudaEventDestroy(ctx->evMark);
+	if(ctx->evDownload) cudaEventDestroy(ctx->evDownload);
+	for(auto &f : ctx->fence)
+		if(f) cudaEventDestroy(f);
+	if(ctx->h2dStream) cudaStreamDestroy(ctx->h2dStream);
+	if(ctx->d2hStream) cudaStreamDestroy(ctx->d2hStream);
 	if(ctx->setupStream) cudaStreamDestroy(ctx->setupStream);
 	for(cudaEvent_t ev : ctx->eventPool) cudaEventDestroy(ev);
 	if(ctx->t0) cudaEventDestroy(ctx->t0);
@@ -253,10 +289,54 @@ extern "C" int swcu_mem_unregister(swcu_ctx *ctx, const void *host_base)
 	auto it = ctx->mem.find((uintptr_t)host_base);
 	if(it == ctx->mem.end()) return fail(ctx, SWCU_E_INVALID, "swcu_mem_unregister: %p is not a registered base", host_base);
 	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->h2dStream));
+	CU(cudaStreamSynchronize(ctx->setupStream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaStreamSynchronize(ctx->d2hStream));
 	if(it->second.pinned) cudaHostUnregister((void *)it->second.host);
 	if(!it->second.external) cudaFree(it->second.dev);
+	if(it->second.dlEvent) cudaEventDestroy(it->second.dlEvent);
+	if(it->second.upEvent) cudaEventDestroy(it->second.upEvent);
 	ctx->mem.erase(it);
+	return SWCU_OK;
+}
+
+// ---- ordering between the copy streams and the kernel streams ----
+// a stream is about to read shadow s: its last upload must have landed (uploads complete in issue order, so a stream that has
+// waited for upload number n has seen every earlier one)
+static int see_upload(swcu_ctx *ctx, Shadow *s, cudaStream_t st, uint64_t &seen)
+{
+	if(s && s->upSeq > seen)
+	{
+		CU(cudaStreamWaitEvent(st, s->upEvent, 0));
+		seen = s->upSeq;
+	}
+	return SWCU_OK;
+}
+// ... or every upload issued so far
+static int see_uploads(swcu_ctx *ctx, cudaStream_t st, uint64_t &seen)
+{
+	if(seen != ctx->uploadSeq)
+	{
+		CU(cudaStreamWaitEvent(st, ctx->evUpload, 0));
+		seen = ctx->uploadSeq;
+	}
+	return SWCU_OK;
+}
+// the main stream is about to read or write [p, ...): later uploads wait for it, and a download of the shadow still in
+// flight finishes before a write
+static int main_touches(swcu_ctx *ctx, const void *p, bool write)
+{
+	Shadow *s = p ? find_shadow(ctx, p, 1) : nullptr;
+	if(!s) return SWCU_OK;
+	s->mainTouched = true;
+	int rc = see_upload(ctx, s, ctx->stream, ctx->mainSawUpload);
+	if(rc) return rc;
+	if(write && s->dlPendingMain)
+	{
+		CU(cudaStreamWaitEvent(ctx->stream, s->dlEvent, 0));
+		s->dlPendingMain = false;
+	}
 	return SWCU_OK;
 }
 
@@ -267,9 +347,29 @@ extern "C" int swcu_mem_upload(swcu_ctx *ctx, const void *host_ptr, size_t bytes
 	if(!d) return fail(ctx, SWCU_E_INVALID, "swcu_mem_upload: [%p,+%zu) is not inside a registered range", host_ptr, bytes);
 	if(d == (const unsigned char *)host_ptr) return fail(ctx, SWCU_E_INVALID, "swcu_mem_upload: %p is caller-owned device memory", host_ptr);
 	CU(cudaSetDevice(ctx->device));
-	CU(cudaMemcpyAsync(d, host_ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
-	CU(cudaEventRecord(ctx->evUpload, ctx->stream)); // the setup stream of a later draw waits for its inputs
-	ctx->evUploadValid = true;
+	Shadow *s = find_shadow(ctx, host_ptr, bytes);
+	const cudaStream_t st = ctx->optCopyStreams ? ctx->h2dStream : ctx->stream;
+	if(ctx->optCopyStreams)
+	{
+		// Readers of the old contents.  The setup phase of a pipelined draw has been waited for by the host (swcu_draw's one
+		// sync), so plain vertex / index streams need nothing; kernels of the main stream do.
+		if(s->mainTouched || ctx->mainReadsInputs)
+		{
+			CU(cudaEventRecord(ctx->evMark, ctx->stream));
+			CU(cudaStreamWaitEvent(st, ctx->evMark, 0));
+			ctx->mainReadsInputs = false;
+		}
+		if(s->dlPendingUpload)
+		{
+			CU(cudaStreamWaitEvent(st, s->dlEvent, 0));
+			s->dlPendingUpload = false;
+		}
+	}
+	CU(cudaMemcpyAsync(d, host_ptr, bytes, cudaMemcpyHostToDevice, st));
+	if(!s->upEvent) CU(cudaEventCreateWithFlags(&s->upEvent, cudaEventDisableTiming));
+	CU(cudaEventRecord(s->upEvent, st)); // kernels issued later that read this shadow wait for it
+	CU(cudaEventRecord(ctx->evUpload, st));
+	s->upSeq = ++ctx->uploadSeq;
 	ctx->stats.h2dBytes += bytes;
 	return SWCU_OK;
 }
@@ -281,8 +381,51 @@ extern "C" int swcu_mem_download(swcu_ctx *ctx, void *host_ptr, size_t bytes)
 	if(!d) return fail(ctx, SWCU_E_INVALID, "swcu_mem_download: [%p,+%zu) is not inside a registered range", host_ptr, bytes);
 	if(d == (unsigned char *)host_ptr) return fail(ctx, SWCU_E_INVALID, "swcu_mem_download: %p is caller-owned device memory", host_ptr);
 	CU(cudaSetDevice(ctx->device));
-	CU(cudaMemcpyAsync(host_ptr, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	ctx->stats.d2hBytes += bytes;
+	Shadow *s = find_shadow(ctx, host_ptr, bytes);
+	if(!ctx->optCopyStreams)
+	{
+		int rc = see_upload(ctx, s, ctx->stream, ctx->mainSawUpload);
+		if(rc) return rc;
+		CU(cudaMemcpyAsync(host_ptr, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		return SWCU_OK;
+	}
+	const cudaStream_t st = ctx->d2hStream;
+	CU(cudaEventRecord(ctx->evMark, ctx->stream)); // everything issued on the main stream so far has produced its pixels
+	CU(cudaStreamWaitEvent(st, ctx->evMark, 0));
+	int rc = see_upload(ctx, s, st, ctx->d2hSawUpload);
+	if(rc) return rc;
+	CU(cudaMemcpyAsync(host_ptr, d, bytes, cudaMemcpyDeviceToHost, st));
+	if(!s->dlEvent) CU(cudaEventCreateWithFlags(&s->dlEvent, cudaEventDisableTiming));
+	CU(cudaEventRecord(s->dlEvent, st));
+	s->dlPendingMain = s->dlPendingUpload = true;
+	CU(cudaEventRecord(ctx->evDownload, st));
+	ctx->downloadSeq++;
+	return SWCU_OK;
+}
+
+// Fences: the completion signal a submission hands back (the reference: the CountedEvent of sw::Renderer::draw, Renderer.cpp:184,
+// :499-510, that vk::Fence waits on).  swcu_fence_signal marks "everything issued so far, copies included"; swcu_fence_wait blocks the host on it.
+extern "C" int swcu_fence_signal(swcu_ctx *ctx, uint32_t slot)
+{
+	if(!ctx || slot >= SWCU_MAX_FENCES) return fail(ctx, SWCU_E_INVALID, "swcu_fence_signal: bad slot");
+	CU(cudaSetDevice(ctx->device));
+	const cudaStream_t st = ctx->d2hStream; // downloads are the tail of a frame: join the other streams here
+	CU(cudaEventRecord(ctx->evMark, ctx->stream));
+	CU(cudaStreamWaitEvent(st, ctx->evMark, 0));
+	int rc = see_uploads(ctx, st, ctx->d2hSawUpload);
+	if(rc) return rc;
+	CU(cudaEventRecord(ctx->fence[slot], st));
+	ctx->fenceValid[slot] = true;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_fence_wait(swcu_ctx *ctx, uint32_t slot)
+{
+	if(!ctx || slot >= SWCU_MAX_FENCES) return fail(ctx, SWCU_E_INVALID, "swcu_fence_wait: bad slot");
+	if(!ctx->fenceValid[slot]) return SWCU_OK;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaEventSynchronize(ctx->fence[slot]));
 	return SWCU_OK;
 }
 
@@ -295,8 +438,10 @@ extern "C" int swcu_sync(swcu_ctx *ctx)
 {
 	if(!ctx) return SWCU_E_INVALID;
 	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamSynchronize(ctx->h2dStream));
 	CU(cudaStreamSynchronize(ctx->setupStream));
 	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaStreamSynchronize(ctx->d2hStream));
 	return SWCU_OK;
 }
 
@@ -375,6 +520,14 @@ extern "C" int swcu_set_option(swcu_ctx *ctx, const char *name, int value)
 	else if(!strcmp(name, "tma")) ctx->optTma = value;
 	else if(!strcmp(name, "fast_state")) ctx->optFastState = value;
 	else if(!strcmp(name, "pipeline")) ctx->optPipeline = value;
+	else if(!strcmp(name, "copy_streams"))
+	{
+		// 0: copies on the main stream (needed when something the library cannot see - e.g. an NCCL collective on the caller's
+		// stream - writes a shadow that is also downloaded)
+		int rc = swcu_sync(ctx);
+		if(rc) return rc;
+		ctx->optCopyStreams = value;
+	}
 	else return fail(ctx, SWCU_E_INVALID, "unknown option '%s'", name);
 	return SWCU_OK;
 }
@@ -712,9 +865,14 @@ struct TileRectCount
 	__host__ __device__ uint32_t operator()(uint32_t r) const { return tile_rect_count(r); }
 };
 
-__global__ void k_pair_total(const uint32_t *pairOffset, const uint32_t *tileCount, uint32_t n, DrawCounters *c)
+// The totals reach the host through its mapped pinned page, written by the kernel itself: a cudaMemcpyAsync would queue in the
+// device-to-host copy engine behind a frame download that may be in flight there, and the host's one wait of a binned draw would
+// then last as long as that download.
+__global__ void k_pair_total(const uint32_t *pairOffset, const uint32_t *tileCount, uint32_t n, DrawCounters *c, DrawCounters *hostOut)
 {
 	c->pairTotal = (unsigned long long)pairOffset[n - 1] + tile_rect_count(tileCount[n - 1]);
+	*hostOut = *c;
+	__threadfence_system();
 }
 
 // ---- TMA descriptors of the attachments: a 3-D tensor (x, y, sample plane) with a (tile width, tile height, samples) box ----
@@ -848,8 +1006,19 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	if(pipelined)
 	{
 		if(S.tileDoneValid) CU(cudaStreamWaitEvent(ss, S.tileDone, 0));
-		if(ctx->evUploadValid) CU(cudaStreamWaitEvent(ss, ctx->evUpload, 0));
 	}
+	else ctx->mainReadsInputs = true; // the setup phase reads the vertex / index streams on the main stream, asynchronously
+	{
+		// the vertex / index streams the setup phase reads: wait for THEIR uploads only
+		uint64_t &seen = pipelined ? ctx->setupSawUpload : ctx->mainSawUpload;
+		for(int i = 0; i < SWCU_MAX_INPUTS; i++)
+			if(desc->input[i].buffer && (rc = see_upload(ctx, find_shadow(ctx, desc->input[i].buffer, 1), ss, seen))) return rc;
+		if(desc->indexBuffer && (rc = see_upload(ctx, find_shadow(ctx, desc->indexBuffer, 1), ss, seen))) return rc;
+	}
+	if((rc = main_touches(ctx, desc->color.buffer, true)) || (rc = main_touches(ctx, desc->depth.buffer, true)) || (rc = main_touches(ctx, desc->stencil.buffer, true))) return rc;
+	for(uint32_t t = 0; t < desc->sampledImageCount && t < SWCU_MAX_SAMPLED_IMAGES; t++)
+		for(uint32_t l = 0; l < desc->sampledImage[t].levelCount && l < SWCU_MIPMAP_LEVELS; l++)
+			if((rc = main_touches(ctx, desc->sampledImage[t].level[l].buffer, false))) return rc;
 	if((rc = ensure(ctx, S.triRecords, (size_t)n * d.triStride))) return rc;
 	if((rc = ensure(ctx, S.tileCount, (size_t)n * 4))) return rc;
 	if((rc = ensure(ctx, S.counters, sizeof(DrawCounters)))) return rc;
@@ -912,9 +1081,8 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		CU(cub::DeviceScan::ExclusiveSum(S.scanTemp.p, tempBytes, counts, (uint32_t *)S.pairOffset.p, (int)n, ss));
 		{
 			LaunchScope ls(ctx, "k_pair_total", ss);
-			k_pair_total<<<1, 1, 0, ss>>>((const uint32_t *)S.pairOffset.p, d.tileCount, n, d.counters);
+			k_pair_total<<<1, 1, 0, ss>>>((const uint32_t *)S.pairOffset.p, d.tileCount, n, d.counters, S.hostCounters);
 		}
-		CU(cudaMemcpyAsync(S.hostCounters, d.counters, sizeof(DrawCounters), cudaMemcpyDeviceToHost, ss));
 		CU(cudaStreamSynchronize(ss)); // the setup phase only: the main stream may still be running the previous draw's tiles
 		const DrawCounters hc = *S.hostCounters;
 		if(hc.overflow)
@@ -1036,6 +1204,8 @@ extern "C" int swcu_copy_image(swcu_ctx *ctx, const swcu_attachment *src, const 
 	if(!s || !t) return fail(ctx, SWCU_E_INVALID, "swcu_copy_image: image is not inside a registered range");
 	const int vec = ((uintptr_t)s % 16 == 0) && ((uintptr_t)t % 16 == 0) && (src->pitchB % 16 == 0) && (dst->pitchB % 16 == 0) && (rowB % 16 == 0);
 	const int per = vec ? 16 : 4;
+	int rc;
+	if((rc = main_touches(ctx, src->buffer, false)) || (rc = main_touches(ctx, dst->buffer, true))) return rc;
 	LaunchScope ls(ctx, "k_copy_rows");
 	k_copy_rows<<<dim3((unsigned)((rowB / per + 255) / 256), src->height), 256, 0, ctx->stream>>>(s, src->pitchB, t, dst->pitchB, (int)rowB, (int)src->height, vec);
 	CU(cudaGetLastError());
@@ -1048,6 +1218,12 @@ extern "C" int swcu_signal(swcu_ctx *ctx, void *flag, uint32_t value)
 	CU(cudaSetDevice(ctx->device));
 	unsigned char *f = dev_ptr(ctx, flag, 4);
 	if(!f) return fail(ctx, SWCU_E_INVALID, "swcu_signal: flag is not inside a registered range");
+	// a flag tells a peer that this rank's frame may be overwritten: downloads of it still in flight come first
+	if(ctx->mainSawDownload != ctx->downloadSeq)
+	{
+		CU(cudaStreamWaitEvent(ctx->stream, ctx->evDownload, 0));
+		ctx->mainSawDownload = ctx->downloadSeq;
+	}
 	LaunchScope ls(ctx, "k_signal");
 	k_signal<<<1, 1, 0, ctx->stream>>>((uint32_t *)f, value);
 	CU(cudaGetLastError());
@@ -1092,6 +1268,8 @@ extern "C" int swcu_clear(swcu_ctx *ctx, const swcu_attachment *att, uint32_t sa
 	if(!base) return fail(ctx, SWCU_E_INVALID, "swcu_clear: attachment is not inside a registered range");
 	uint4 v = make_uint4(0, 0, 0, 0);
 	memcpy(&v, value, (size_t)bpp);
+	int rc;
+	if((rc = main_touches(ctx, att->buffer, true))) return rc;
 	LaunchScope ls(ctx, "k_clear");
 	k_clear<<<dim3((area->width + 255) / 256, area->height), 256, 0, ctx->stream>>>(base, att->pitchB, att->sliceB, bpp, area->x, area->y, (int)area->width, (int)area->height, (int)samples, v);
 	CU(cudaGetLastError());
@@ -1108,6 +1286,8 @@ extern "C" int swcu_resolve(swcu_ctx *ctx, const swcu_attachment *src, uint32_t 
 	unsigned char *s = dev_ptr(ctx, src->buffer, (size_t)3 * src->sliceB + (size_t)(src->height - 1) * src->pitchB + (size_t)src->width * 4);
 	unsigned char *t = dev_ptr(ctx, dst->buffer, (size_t)(dst->height - 1) * dst->pitchB + (size_t)dst->width * 4);
 	if(!s || !t) return fail(ctx, SWCU_E_INVALID, "swcu_resolve: attachment is not inside a registered range");
+	int rc;
+	if((rc = main_touches(ctx, src->buffer, false)) || (rc = main_touches(ctx, dst->buffer, true))) return rc;
 	LaunchScope ls(ctx, "k_resolve4");
 	k_resolve4<<<dim3((src->width + 255) / 256, src->height), 256, 0, ctx->stream>>>(s, src->pitchB, src->sliceB, t, dst->pitchB, (int)src->width, (int)src->height);
 	CU(cudaGetLastError());

@@ -409,6 +409,13 @@ class Device:
     def sync(self):
         self.check(self.lib.swcu_sync(self.ctx))
 
+    def fence_signal(self, slot: int):
+        """Marks everything issued so far (copies included); ``fence_wait`` blocks the host on it without draining the device."""
+        self.check(self.lib.swcu_fence_signal(self.ctx, slot))
+
+    def fence_wait(self, slot: int):
+        self.check(self.lib.swcu_fence_wait(self.ctx, slot))
+
     def draw(self, desc: capi.DrawDesc):
         self.check(self.lib.swcu_draw(self.ctx, C.byref(desc)))
 

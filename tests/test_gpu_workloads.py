@@ -125,3 +125,86 @@ def test_unsupported_state_is_a_hard_error(device):
     with pytest.raises(capi.SwcuError) as e:
         device.render(sc)
     assert e.value.code == capi.E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("samples", [1, 4])
+def test_frames_in_flight_match_serial_frames(device, samples):
+    """The copy streams and fences of the boundary (swcu_mem_upload / swcu_mem_download / swcu_fence_*): a render loop that
+    keeps two frames in flight — new vertex data every frame, clear, draw, resolve, download — delivers exactly the frames
+    of the same loop with a full swcu_sync after every call.  Covers an upload overlapping the previous frame's tile kernel,
+    a download overlapping the next frame's clear / draw of the SAME attachment (1x) or the next resolve (4x)."""
+    from swiftshader_b200.scene import Draw, Scene
+    rng = np.random.default_rng(77)
+    tris = [scenes._verts(rng, scenes._tri_kind(rng, (5, 1, 0)[i % 3]), persp=(i % 2 == 0), colour=rng.uniform(0, 1, (3, 4))) for i in range(400)]
+    base = np.ascontiguousarray(np.concatenate(tris), dtype=np.float32)
+    d = Draw(base.copy(), scenes.P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, blend=True)
+    sc = Scene(192, 160, [d], samples=samples, hasDepth=True, clearDepth=1.0, clearColor=(0.1, 0.2, 0.3, 1.0))
+    frames = 7
+    variants = []
+    for i in range(frames):
+        v = base.copy()
+        v[:, 4:7] = np.float32(1.0) - v[:, 4:7] if i % 2 else v[:, 4:7] * np.float32(0.25 + 0.1 * i)
+        v[:, 0] += np.float32(0.02 * i) * v[:, 3]
+        variants.append(v)
+    fr = Frame(device, sc)
+    device.set_option("force_binned", 1)  # the setup phase of every draw is host-synchronised: the vertex array may be rewritten after draw()
+    try:
+        verts = fr.inputs[0]
+        assert verts.shape == base.shape
+        outs = [fr.final_image()]
+        dsts = [fr._attachment("resolved")] if samples > 1 else [None]
+        if samples > 1:
+            second = np.zeros_like(fr.resolved)
+            device.register(second, upload=False)
+            outs.append(second[0])
+            a = fr._attachment("resolved")
+            a.buffer = second.ctypes.data
+            dsts.append(a)
+        import ctypes as C
+
+        def issue(i, serial):
+            drain = device.sync if serial else (lambda: None)
+            verts[...] = variants[i]
+            fr.upload_inputs()
+            drain()
+            fr.clear()
+            drain()
+            fr.draw()
+            drain()
+            k = i % len(outs)
+            if dsts[k] is not None:
+                src = fr._attachment("color")
+                device.check(device.lib.swcu_resolve(device.ctx, C.byref(src), samples, C.byref(dsts[k])))
+                drain()
+            return k
+
+        want = []
+        for i in range(frames):
+            k = issue(i, True)
+            device.download(outs[k])
+            device.sync()
+            want.append(outs[k].copy())
+        assert any(not np.array_equal(want[0], w) for w in want[1:])
+        for o in outs:
+            o[...] = 0
+        got = [None] * frames
+        for i in range(frames):
+            k = issue(i, False)
+            if len(outs) == 1 and i >= 1:  # one host image: frame i-1 is consumed before frame i may land in it
+                device.fence_wait((i - 1) % 2)
+                got[i - 1] = outs[0].copy()
+            device.download(outs[k])
+            device.fence_signal(i % 2)
+            if len(outs) == 2 and i >= 1:
+                device.fence_wait((i - 1) % 2)
+                got[i - 1] = outs[(i - 1) % 2].copy()
+        device.fence_wait((frames - 1) % 2)
+        got[frames - 1] = outs[(frames - 1) % len(outs)].copy()
+        for i in range(frames):
+            assert np.array_equal(got[i], want[i]), f"frame {i} of the pipelined loop differs from the serial loop"
+    finally:
+        device.set_option("force_binned", 0)
+        device.sync()
+        if samples > 1:
+            device.unregister(second)
+        fr.close()
