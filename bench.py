@@ -208,8 +208,9 @@ def main():
         elif rank != 0:
             peer_dst = pg.band_destination(sc.colorFormat, W)
 
-    def step(present=None):
-        frame.draw()
+    def step(present=None, descs=None):
+        for d_ in (descs if descs is not None else frame.descs):
+            dev.draw(d_)
         if pg is not None and rank != 0:
             pg.begin_frame()  # rank 0 must be done with the previous frame before its rows are overwritten
             if dst_b is not None:
@@ -268,21 +269,27 @@ def main():
         # ---- end to end through the C-ABI with HOST buffers: H2D of the step's inputs and D2H of the frame inside the timed region.
         #      A render loop with several frames in flight, bounded by a fence per frame (a Vulkan application's per-frame vk::Fence):
         #      the library's copy streams bring frame i+1's inputs up and frame i-1's pixels down while frame i renders ----
-        e2e_steps = max(3, min(args.steps, 10)) if N > 1 else max(6, min(args.steps, 30))
+        e2e_steps = max(6, min(args.steps, 30))
         if gather == "nccl":
             dev.set_option("copy_streams", 0)  # the all-gather writes the frame on the caller's stream, unseen by the library
+        # Three stages overlap - frame i+1's inputs going up, frame i rendering, frame i-1 coming down - so the loop holds two
+        # sets of input buffers (per-frame dynamic vertex data, as an application double-buffers it) and, at N = 1 with MSAA,
+        # three resolve targets; a fence per frame bounds the frames in flight.
+        import dataclasses
+        alt_inputs, alt_keep = [], []
+        alt_descs = [sc.build_desc(dataclasses.replace(dr, vertices=np.array(dr.vertices, dtype=np.float32, copy=True),
+                                                       indices=None if dr.indices is None else dr.indices.copy()),
+                                   frame.att, alt_keep, area, alt_inputs) for dr in sc.draws]
+        for b in alt_inputs:
+            dev.register(b, upload=False)
+        in_sets = [(frame.inputs, frame.descs), (alt_inputs, alt_descs)]
+        skip = set(filter(None, os.environ.get("SWCU_E2E_SKIP", "").split(",")))  # diagnosis only: the reported e2e runs with nothing skipped
+
+        def upload_set(k):
+            for b in in_sets[k][0]:
+                dev.upload(b)
+
         if N == 1:
-            # Three stages overlap - frame i+1's inputs going up, frame i rendering, frame i-1 coming down - so the loop holds
-            # two sets of input buffers (per-frame dynamic vertex data, as an application double-buffers it) and, with MSAA,
-            # three resolve targets; a fence per frame bounds the frames in flight.
-            import dataclasses
-            alt_inputs, alt_keep = [], []
-            alt_descs = [sc.build_desc(dataclasses.replace(dr, vertices=np.array(dr.vertices, dtype=np.float32, copy=True),
-                                                           indices=None if dr.indices is None else dr.indices.copy()),
-                                       frame.att, alt_keep, area, alt_inputs) for dr in sc.draws]
-            for b in alt_inputs:
-                dev.register(b, upload=False)
-            in_sets = [(frame.inputs, frame.descs), (alt_inputs, alt_descs)]
             outs, dsts = [frame.final_image()], [dst_b]
             if dst_b is not None:
                 for _ in range(2):
@@ -291,14 +298,6 @@ def main():
                     outs.append(extra[0])
                     dsts.append(band_att(extra, H2 * pitch))
             F = len(outs)  # frames in flight (1x: the colour attachment itself is the only host-visible image)
-
-            skip = set(filter(None, os.environ.get("SWCU_E2E_SKIP", "").split(",")))  # diagnosis only: the reported e2e runs with nothing skipped
-
-            def upload_set(k):
-                if "upload" in skip:
-                    return
-                for b in in_sets[k][0]:
-                    dev.upload(b)
 
             def e2e_frame(i):
                 upload_set((i + 1) % 2)  # next frame's inputs, behind this frame's on the upload stream
@@ -314,26 +313,28 @@ def main():
                 dev.fence_signal(i % max(F, 2))
                 if F > 1 and i >= F - 1:
                     dev.fence_wait((i - (F - 1)) % F)  # frame i-2 is on the host now
-
-            def e2e_run(n):
-                upload_set(0)  # frame 0's inputs; every frame of the loop uploads one set, so n frames move n sets
-                for i in range(n):
-                    e2e_frame(i)
-                dev.sync()
             frames_in_flight = max(F, 2)
         else:
-            def e2e_frame(i):
-                frame.upload_inputs()
-                step(frame.download_final if rank == 0 else None)
-                dev.fence_signal(i % 2)
+            # rank 0's frame is the one host-visible image (the other ranks store their bands into it): frame i-1 is consumed
+            # before frame i comes down; the consumed flag leaves rank 0 from its download stream, so its next draw is not held back
+            def present(i):
                 if i >= 1:
-                    dev.fence_wait((i - 1) % 2)  # frame i-1 is on the host now
+                    dev.fence_wait((i - 1) % 2)
+                frame.download_final()
 
-            def e2e_run(n):
-                for i in range(n):
-                    e2e_frame(i)
-                dev.sync()
+            def e2e_frame(i):
+                upload_set((i + 1) % 2)
+                step((lambda: present(i)) if rank == 0 else None, in_sets[i % 2][1])
+                dev.fence_signal(i % 2)
+                if rank != 0 and i >= 1:
+                    dev.fence_wait((i - 1) % 2)
             frames_in_flight = 2
+
+        def e2e_run(n):
+            upload_set(0)  # frame 0's inputs; every frame of the loop uploads one set, so n frames move n sets
+            for i in range(n):
+                e2e_frame(i)
+            dev.sync()
 
         e2e_run(3)
         barrier()

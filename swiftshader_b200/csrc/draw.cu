@@ -1218,14 +1218,19 @@ extern "C" int swcu_signal(swcu_ctx *ctx, void *flag, uint32_t value)
 	CU(cudaSetDevice(ctx->device));
 	unsigned char *f = dev_ptr(ctx, flag, 4);
 	if(!f) return fail(ctx, SWCU_E_INVALID, "swcu_signal: flag is not inside a registered range");
-	// a flag tells a peer that this rank's frame may be overwritten: downloads of it still in flight come first
-	if(ctx->mainSawDownload != ctx->downloadSeq)
+	// A flag tells a peer that this rank's frame may be overwritten, so downloads still in flight come first.  The flag is then
+	// written from the download stream, behind them (and behind everything issued on the main stream so far): the main stream
+	// itself is not held back and goes on with the next frame's draw.
+	cudaStream_t st = ctx->stream;
+	if(ctx->optCopyStreams && ctx->mainSawDownload != ctx->downloadSeq)
 	{
-		CU(cudaStreamWaitEvent(ctx->stream, ctx->evDownload, 0));
+		st = ctx->d2hStream;
+		CU(cudaEventRecord(ctx->evMark, ctx->stream));
+		CU(cudaStreamWaitEvent(st, ctx->evMark, 0));
 		ctx->mainSawDownload = ctx->downloadSeq;
 	}
-	LaunchScope ls(ctx, "k_signal");
-	k_signal<<<1, 1, 0, ctx->stream>>>((uint32_t *)f, value);
+	LaunchScope ls(ctx, "k_signal", st);
+	k_signal<<<1, 1, 0, st>>>((uint32_t *)f, value);
 	CU(cudaGetLastError());
 	return SWCU_OK;
 }
