@@ -181,16 +181,18 @@ static void process_vertex(const Draw *dr, uint32_t index, Vertex *v)
 	for(int i = 0; i < SWCU_MAX_VARYING_COMPONENTS; i++)
 		v->v[i] = (dr->vs->outputMask >> i) & 1 ? operand(&dr->vs->output[i], inputs) : 0.0f;
 
-	/* computeClipFlags, VertexRoutine.cpp:128-152 (CmpNLE(a,b) = !(a <= b)) */
+	/* computeClipFlags, VertexRoutine.cpp:128-152.  Reactor's CmpNLE / CmpNLT / CmpNEQ are ORDERED compares in the LLVM backend
+	 * (FCmpOGT / FCmpOGE / FCmpONE, LLVMReactor.cpp:3161-3180,4479-4495), not the x86 cmpnleps they are named after: a NaN w sets
+	 * no flag, so the triangle goes to setup unclipped with the clamped projection of VertexRoutine.cpp:609-610 */
 	int f = 0;
 	if(pw < px) f |= CLIP_RIGHT;
 	if(pw < py) f |= CLIP_TOP;
-	if(!(-pw <= px)) f |= CLIP_LEFT;
-	if(!(-pw <= py)) f |= CLIP_BOTTOM;
+	if(-pw > px) f |= CLIP_LEFT;
+	if(-pw > py) f |= CLIP_BOTTOM;
 	if(d->depthClipEnable)
 	{
 		if(pw < pz) f |= CLIP_FAR;
-		if(!(0.0f <= pz)) f |= CLIP_NEAR;
+		if(0.0f > pz) f |= CLIP_NEAR;
 	}
 	if(fabsf(px) <= 3.40282347e38f && fabsf(py) <= 3.40282347e38f && fabsf(pz) <= 3.40282347e38f) f |= CLIP_FINITE;
 	v->clipFlags = f;
@@ -360,7 +362,7 @@ static int setup_triangle(const Draw *dr, Primitive *prim, const Vertex *tv0, co
 		for(int i = 0; i < n; i++)
 		{
 			f4 v = poly->P[i];
-			float rhw = v.w != 0.0f ? 1.0f / v.w : 1.0f;
+			float rhw = (v.w < 0.0f || v.w > 0.0f) ? 1.0f / v.w : 1.0f; /* Float != is FCmpONE (Reactor.cpp:3965-3968): false for NaN */
 			X[i] = round_int(dr->X0xF + v.x * rhw * dr->WxF);
 			Y[i] = round_int(dr->Y0xF + v.y * rhw * dr->HxF);
 		}
@@ -436,7 +438,7 @@ static int setup_triangle(const Draw *dr, Primitive *prim, const Vertex *tv0, co
 	float a = x1 * y2 - x2 * y1;
 	float M[3][3] = { { 0, 0, 0 }, { 0, 0, 0 }, { 0, 0, 0 } }; /* [row][x,y,z] */
 	M[0][2] = rhw0;
-	if(a != 0.0f)
+	if(a < 0.0f || a > 0.0f) /* If(a != 0.0f), FCmpONE: a NaN area leaves the zero matrix */
 	{
 		float A = 1.0f / a;
 		float D = A * rhw0;
@@ -630,7 +632,7 @@ static void sample_quad(const swcu_sampled_image *t, const float u[4], const flo
 	{
 		/* offsetSample masks the half-texel offset by the lod sign (:282-289): MIN_LINEAR_MAG_POINT: linear iff lod > 0 */
 		int minLinear = t->minFilter == FILTER_LINEAR;
-		linear = minLinear ? !(lod <= 0.0f) : (lod <= 0.0f);
+		linear = minLinear ? (lod > 0.0f) : (lod <= 0.0f); /* CmpNLE is FCmpOGT */
 		/* with the offset masked to 0 the four taps coincide and the blend weights still apply (fractions of u0 == u) */
 	}
 	int ilod;
@@ -1009,7 +1011,7 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 				}
 
 			/* alphaTest (PixelProgram.cpp:243-259) -> alphaToCoverage (PixelRoutine.cpp:643-658): the clamped c[0].w against the
-			 * per-sample thresholds of Renderer.cpp:391-410, CmpNLT (a NaN alpha passes); then :319-326 */
+			 * per-sample thresholds of Renderer.cpp:391-410; then :319-326 */
 			if(d->alphaToCoverageEnable)
 			{
 				static const float a2c4[4] = { 0.2f, 0.4f, 0.6f, 0.8f };
@@ -1019,7 +1021,7 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 					const float thr = ms == 4 ? a2c4[q] : 0.5f;
 					int aMask = 0;
 					for(int i = 0; i < 4; i++)
-						if(!(c[i][3] < thr)) aMask |= 1 << i;
+						if(c[i][3] >= thr) aMask |= 1 << i; /* CmpNLT is FCmpOGE: a NaN alpha loses its coverage */
 					cMask[q] &= aMask;
 					zMask[q] &= cMask[q];
 					sMask[q] &= cMask[q];
@@ -1073,10 +1075,10 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 						case CMP_ALWAYS: t = 1; break;
 						case CMP_NEVER: t = 0; break;
 						case CMP_EQUAL: t = zValue == Z; break;
-						case CMP_NOT_EQUAL: t = zValue != Z; break;
-						case CMP_LESS: t = !(zValue <= Z); break;
+						case CMP_NOT_EQUAL: t = zValue < Z || zValue > Z; break; /* CmpNEQ is FCmpONE */
+						case CMP_LESS: t = zValue > Z; break;            /* CmpNLE is FCmpOGT */
 						case CMP_GREATER_OR_EQUAL: t = zValue <= Z; break;
-						case CMP_LESS_OR_EQUAL: t = !(zValue < Z); break;
+						case CMP_LESS_OR_EQUAL: t = zValue >= Z; break;  /* CmpNLT is FCmpOGE */
 						default: t = zValue < Z; break; /* GREATER */
 						}
 						if(t) zTest |= 1 << i;

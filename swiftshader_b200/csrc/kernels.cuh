@@ -104,15 +104,17 @@ struct VOut
 DEVI void process_vertex(const DrawConst &d, float px, float py, float pz, float pw, VOut &v)
 {
 	v.px = px; v.py = py; v.pz = pz; v.pw = pw;
-	int f = 0; // computeClipFlags, VertexRoutine.cpp:128-152
+	// computeClipFlags, VertexRoutine.cpp:128-152.  Reactor's CmpNLE is an ORDERED greater-than (FCmpOGT, LLVMReactor.cpp:4491-4495):
+	// a NaN w sets no flag
+	int f = 0;
 	if(pw < px) f |= CLIP_RIGHT;
 	if(pw < py) f |= CLIP_TOP;
-	if(!(-pw <= px)) f |= CLIP_LEFT;
-	if(!(-pw <= py)) f |= CLIP_BOTTOM;
+	if(-pw > px) f |= CLIP_LEFT;
+	if(-pw > py) f |= CLIP_BOTTOM;
 	if(d.depthClipEnable)
 	{
 		if(pw < pz) f |= CLIP_FAR;
-		if(!(0.0f <= pz)) f |= CLIP_NEAR;
+		if(0.0f > pz) f |= CLIP_NEAR;
 	}
 	if(fabsf(px) <= 3.40282347e38f && fabsf(py) <= 3.40282347e38f && fabsf(pz) <= 3.40282347e38f) f |= CLIP_FINITE;
 	v.flags = f;
@@ -431,7 +433,7 @@ DEVI void setup_triangle(const DrawConst &d)
 				clipped = true;
 				for(int i = 0; i < n; i++) // re-projection, SetupRoutine.cpp:125-145
 				{
-					const float rhw = P[i].w != 0.0f ? fdiv(1.0f, P[i].w) : 1.0f;
+					const float rhw = (P[i].w < 0.0f || P[i].w > 0.0f) ? fdiv(1.0f, P[i].w) : 1.0f; // Float != is FCmpONE: false for NaN
 					PX[i] = round_int(fadd(d.X0xF, fmul(fmul(P[i].x, rhw), d.WxF)));
 					PY[i] = round_int(fadd(d.Y0xF, fmul(fmul(P[i].y, rhw), d.HxF)));
 				}
@@ -443,15 +445,17 @@ DEVI void setup_triangle(const DrawConst &d)
 				}
 			}
 			minXs = minX; maxXs = maxX; minYs = minY; maxYs = maxY;
-			yMin = msaa ? (minY + 159) >> 8 : (minY + 255) >> 8; // SetupRoutine.cpp:147-186
-			yMax = msaa ? (maxY + 351) >> 8 : (maxY + 255) >> 8;
+			// SetupRoutine.cpp:147-186, in the reference's wrapping 32-bit arithmetic: a vertex with a NaN w projects to the clamp
+			// value 2147483520 (RoundIntClamped), the sum wraps negative and the triangle ends here, as it does in the reference
+			yMin = (int)((uint32_t)minY + (msaa ? 159u : 255u)) >> 8;
+			yMax = (int)((uint32_t)maxY + (msaa ? 351u : 255u)) >> 8;
 			yMin = max(yMin, d.scY0);
 			yMax = min(yMax, d.scY1);
 			if(yMin >= yMax) break;
 			// conservative pixel-x bounds of the spans (left = ceil of an edge x >= minX; right <= ceil(maxX))
 			const int margin = msaa ? 96 : 0;
-			pxMin = clampi((minX - margin + 255) >> 8, d.scX0, d.scX1);
-			pxMax = clampi((maxX + margin + 255) >> 8, d.scX0, d.scX1);
+			pxMin = clampi((int)(((long long)minX - margin + 255) >> 8), d.scX0, d.scX1);
+			pxMax = clampi((int)(((long long)maxX + margin + 255) >> 8), d.scX0, d.scX1);
 			if(pxMin >= pxMax) break;
 			visible = true;
 		} while(0);
@@ -578,7 +582,7 @@ DEVI void setup_triangle(const DrawConst &d)
 	const float x2 = fmul(fmul(w2, rsub), (float)dX2), y2 = fmul(fmul(w2, rsub), (float)dY2);
 	const float a = fsub(fmul(x1, y2), fmul(x2, y1));
 	float M00 = 0, M01 = 0, M02 = rhw0, M10 = 0, M11 = 0, M20 = 0, M21 = 0;
-	if(a != 0.0f)
+	if(a < 0.0f || a > 0.0f) // If(a != 0.0f) is FCmpONE: a NaN area leaves the zero matrix
 	{
 		const float A = fdiv(1.0f, a);
 		const float D = fmul(A, rhw0);
@@ -950,7 +954,7 @@ DEVI LodState compute_lod(const DrawConst &d, float u0, float u1, float u2, floa
 	if(s.split)
 	{
 		const bool minLinear = d.minFilter == FILTER_LINEAR;
-		s.linear = minLinear ? !(lod <= 0.0f) : (lod <= 0.0f);
+		s.linear = minLinear ? (lod > 0.0f) : (lod <= 0.0f); // CmpNLE is FCmpOGT
 	}
 	s.lod = lod;
 	s.ilod = (!FAST && d.mipmapMode == MIPMAP_MODE_NEAREST) ? round_int(lod) : trunc_int(lod);
@@ -1013,17 +1017,17 @@ DEVI uint32_t stencil_op(uint32_t op, uint32_t v, uint32_t ref) // :870-902
 	}
 }
 
-DEVI bool depth_compare(uint32_t op, float zValue, float Z) // :533-553 (SSE predicate semantics incl. NaN)
+DEVI bool depth_compare(uint32_t op, float zValue, float Z) // :533-553; CmpNEQ / CmpNLE / CmpNLT are the ORDERED FCmpONE / OGT / OGE
 {
 	switch(op)
 	{
 	case CMP_ALWAYS: return true;
 	case CMP_NEVER: return false;
 	case CMP_EQUAL: return zValue == Z;
-	case CMP_NOT_EQUAL: return zValue != Z;
-	case CMP_LESS: return !(zValue <= Z);
+	case CMP_NOT_EQUAL: return zValue < Z || zValue > Z;
+	case CMP_LESS: return zValue > Z;
 	case CMP_GREATER_OR_EQUAL: return zValue <= Z;
-	case CMP_LESS_OR_EQUAL: return !(zValue < Z);
+	case CMP_LESS_OR_EQUAL: return zValue >= Z;
 	default: return zValue < Z;
 	}
 }
@@ -1749,10 +1753,10 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 								sValue = smStencil[pi];
 								sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
 							}
-							// alphaToCoverage (PixelRoutine.cpp:643-658, thresholds Renderer.cpp:391-410): CmpNLT, so a NaN alpha stays covered; a
+							// alphaToCoverage (PixelRoutine.cpp:643-658, thresholds Renderer.cpp:391-410): CmpNLT = ordered >=, a NaN alpha loses its coverage; a
 							// sample that loses its coverage leaves every later stage, stencil write included (:319-326)
 							bool alive = true;
-							if(!FS && d.alphaToCoverage) alive = !(rgba[3] < (MS == 4 ? (q == 0 ? 0.2f : q == 1 ? 0.4f : q == 2 ? 0.6f : 0.8f) : 0.5f));
+							if(!FS && d.alphaToCoverage) alive = rgba[3] >= (MS == 4 ? (q == 0 ? 0.2f : q == 1 ? 0.4f : q == 2 ? 0.6f : 0.8f) : 0.5f);
 							bool zPass = true;
 							float z = 0.0f;
 							if(d.depthTestActive)
@@ -1779,7 +1783,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 								else
 								{
 									const float zValue = smDepth[pi];
-									if(FS) zPass = d.depthCompareOp == CMP_LESS ? !(zValue <= z) : !(zValue < z); // LESS / LESS_OR_EQUAL (:533-553)
+									if(FS) zPass = d.depthCompareOp == CMP_LESS ? zValue > z : zValue >= z; // LESS / LESS_OR_EQUAL (:533-553)
 									else zPass = depth_compare(d.depthCompareOp, zValue, z);
 								}
 								if(!FS && d.depthBounds)

@@ -209,19 +209,16 @@ def pathological(seed: int) -> Scene:
     magnitudes of 1e30 and 1e-40, coincident and collinear vertices, zero-area slivers, vertices exactly on the clip planes and
     on the scissor bounds — mixed with ordinary triangles so that order and neighbours matter."""
     rng = np.random.default_rng(6100 + seed)
-    # Known divergences of the restatement, kept out of this family and listed in DESIGN.md §6: a NaN clip-space w under 4x MSAA
-    # (the reference covers nothing, the restatement some pixels) and components of magnitude >= 3.4e38 (overflow to Inf inside the
-    # clipper's edge interpolation).
+    # A NaN w is the interesting one: Reactor's CmpNLE is an ordered compare, so the vertex gets no clip flag, projects to the clamp
+    # value of RoundIntClamped and the triangle dies in the wrapping row-range arithmetic of the set-up (DESIGN.md §6).
     msaa4 = seed % 4 == 3
-    specials = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e30, -1e30, 1e-40, -1e-40, 1.0, -1.0, 1e37]
+    specials = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1e30, -1e30, 1e-40, -1e-40, 1.0, -1.0, 1e37, 3.4e38, -3.4e38, -np.nan]
     tris = []
     for i in range(48):
         v = _verts(rng, _tri_kind(rng, (5, 0, 1, 2, 3)[i % 5]), persp=(i % 2 == 0), colour=rng.uniform(0, 1, (3, 4)))
         mode = (i + seed) % 8
         if mode == 0:    # one special value somewhere in a position
             comp, val = rng.integers(4), specials[rng.integers(len(specials))]
-            if msaa4 and comp == 3 and val != val:
-                val = np.inf
             v[rng.integers(3), comp] = val
         elif mode == 1:  # w = 0 / negative w on one or two vertices
             k = rng.integers(3)
@@ -242,6 +239,11 @@ def pathological(seed: int) -> Scene:
             v[rng.integers(3), 4 + rng.integers(4)] = specials[rng.integers(len(specials))]
         elif mode == 5:  # far outside the frustum on one side (clipped, huge edge functions)
             v[rng.integers(3), rng.integers(2)] *= 1e6
+        elif mode == 6:  # NaN / infinite w on one or two vertices
+            k = rng.integers(3)
+            v[k, 3] = [np.nan, np.inf, -np.inf, -np.nan][rng.integers(4)]
+            if rng.integers(3) == 0:
+                v[(k + 1) % 3, 3] = np.nan
         tris.append(v)
     verts = np.concatenate(tris).astype(np.float32)
     d = Draw(verts, P4C4, "vs_pos4_col4", "fs_col4", depthTest=True, depthWrite=True, blend=(seed % 2 == 1),
@@ -522,7 +524,7 @@ FAMILIES = {
     "depth16": (depth16, 12),
     "srgb": (srgb, 14),
     "floatrt": (floatrt, 20),
-    "pathological": (pathological, 16),
+    "pathological": (pathological, 20),
     "srgbtex": (srgbtex, 12),
     "fragtests": (fragtests, 16),
 }
