@@ -212,6 +212,11 @@ DEVI int floor_div(int n, int d, int &rem) // d > 0; returns floor(n / d), rem =
 // Operands of an edge for which the closed form of edge_at_row equals the reference's 32-bit arithmetic: screen-sized coordinates.
 // Anything else (a vertex that projected to INT_MIN because its w was -Inf or NaN, ...) goes through edge_wrapped(); k_setup
 // sends every polygon with such a coordinate to k_big.
+DEVI bool polygon_insane(int minX, int maxX, int minY, int maxY)
+{
+	const int lim = (1 << 21) + 4096;
+	return minX < -lim || maxX > lim || minY < -lim || maxY > lim;
+}
 DEVI bool edge_is_sane(int DX, int DY) { return DY > 0 && DY < (1 << 22) && DX > -(1 << 22) && DX < (1 << 22); }
 
 // x of the edge at row y exactly as SetupRoutine::edge (SetupRoutine.cpp:550-621) computes it in wrapping 32-bit integers,
@@ -456,6 +461,10 @@ DEVI void setup_triangle(const DrawConst &d)
 			const int margin = msaa ? 96 : 0;
 			pxMin = clampi((int)(((long long)minX - margin + 255) >> 8), d.scX0, d.scX1);
 			pxMax = clampi((int)(((long long)maxX + margin + 255) >> 8), d.scX0, d.scX1);
+			// A polygon with a coordinate far outside the screen range (a vertex that projected to INT_MIN or to the clamp value
+			// because its w was -Inf or NaN, ...): the reference's edge walk wraps for it, so its spans are not bounded by the
+			// polygon's x extent - every tile column of the scissor is a candidate, and k_big must not cull tiles geometrically
+			if(polygon_insane(minX, maxX, minY, maxY)) { pxMin = d.scX0; pxMax = d.scX1; }
 			if(pxMin >= pxMax) break;
 			visible = true;
 		} while(0);
@@ -473,8 +482,7 @@ DEVI void setup_triangle(const DrawConst &d)
 		// A polygon with a coordinate outside the screen range (a vertex that projected to INT_MIN because its w was -Inf or NaN,
 		// ...) also goes the big-triangle way: k_big reproduces the reference's wrapping arithmetic for such edges (edge_wrapped),
 		// which keeps that case out of the small-triangle DDA below (whose fast division assumes screen-sized operands).
-		const int lim = (1 << 21) + 4096;
-		const bool insane = minXs < -lim || maxXs > lim || minYs < -lim || maxYs > lim;
+		const bool insane = polygon_insane(minXs, maxXs, minYs, maxYs);
 		big = rows > SWCU_SMALL_ROWS || nTiles > SWCU_SMALL_TILES || insane;
 		tileRect = big ? (TILE_RECT_BIG | nTiles) : ((uint32_t)tx0 | ((uint32_t)ty0 << 9) | ((uint32_t)(tx1 - tx0) << 19) | ((uint32_t)(ty1 - ty0) << 22));
 	}
@@ -729,12 +737,15 @@ __global__ void __launch_bounds__(256) k_big(const __grid_constant__ DrawConst d
 			const int ty0 = b.yMin / SWCU_TILE_H, ty1 = (b.yMax - 1) / SWCU_TILE_H;
 			const int tw = tx1 - tx0 + 1, total = tw * (ty1 - ty0 + 1);
 			long long area2 = 0;
+			int loX = b.X[0], hiX = b.X[0], loY = b.Y[0], hiY = b.Y[0];
 			for(int i = 0; i < n; i++)
 			{
 				const int j = i + 1 == n ? 0 : i + 1;
 				area2 += (long long)b.X[i] * b.Y[j] - (long long)b.X[j] * b.Y[i];
+				loX = min(loX, b.X[i]); hiX = max(hiX, b.X[i]); loY = min(loY, b.Y[i]); hiY = max(hiY, b.Y[i]);
 			}
-			const long long sgn = area2 > 0 ? 1 : (area2 < 0 ? -1 : 0);
+			// no geometric culling for a polygon whose edges the reference walks in wrapped arithmetic (see k_setup)
+			const long long sgn = polygon_insane(loX, hiX, loY, hiY) ? 0 : (area2 > 0 ? 1 : (area2 < 0 ? -1 : 0));
 			const int m = msaa ? 96 : 0;
 			const uint32_t off = pairOffset[b.tri];
 			for(int t = blockIdx.y * blockDim.x + threadIdx.x; t < total; t += blockDim.x * gridDim.y)
@@ -748,7 +759,7 @@ __global__ void __launch_bounds__(256) k_big(const __grid_constant__ DrawConst d
 					for(int i = 0; i < n && !outside; i++)
 					{
 						const int j = i + 1 == n ? 0 : i + 1;
-						const long long ex = b.X[j] - b.X[i], ey = b.Y[j] - b.Y[i];
+						const long long ex = (long long)b.X[j] - b.X[i], ey = (long long)b.Y[j] - b.Y[i];
 						const long long slack = 4 * (llabs(ex) + llabs(ey)) + 1024; // rounding of re-projected clip vertices
 						// E(P) = ex*(Py - Yi) - ey*(Px - Xi); inside when sgn*E >= 0
 						const long long e00 = sgn * (ex * (cy0 - b.Y[i]) - ey * (cx0 - b.X[i]));
