@@ -1,3 +1,7 @@
+"""GPU diagnosis tool: renders single triangles of the `pathological` scene family through the CUDA path (binned and direct)
+and through the CPU oracle, and prints where they differ (vertex data, bounds of the differing pixels, first values).
+Used to find the tile-candidate bug of polygons with out-of-range coordinates; edit CASES for other triangles.
+usage (GPU box): python scripts/diag_pathological.py"""
 import sys; sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
 import numpy as np, dataclasses
 import scenes
