@@ -599,6 +599,24 @@ static void sample_level(const swcu_sampled_image *t, int level, float u, float 
 	}
 }
 
+/* Min and mag filters differ and the point one is selected: offsetSample masks the half-texel offset to 0 (:282-289), the four
+ * taps coincide and the 16-bit blend weights (fractions of the un-offset coordinate) still apply - they sum to less than 1 */
+static void sample_level_split_point(const swcu_sampled_image *t, int ilod, float u, float v, uint16_t c[4])
+{
+	const swcu_mip_level *m = &t->level[ilod < (int)t->levelCount ? (ilod < 0 ? 0 : ilod) : (int)t->levelCount - 1];
+	uint16_t uu = address(u, t->addressModeU), vv = address(v, t->addressModeV);
+	uint16_t W = (uint16_t)m->width, H = (uint16_t)m->height;
+	uint32_t x = mulhi_u16(uu, W), y = mulhi_u16(vv, H);
+	const uint8_t *p = (const uint8_t *)m->buffer + 4 * (size_t)(x + y * m->pitchP);
+	uint16_t f0u = (uint16_t)(uu * W), f0v = (uint16_t)(vv * H), f1u = (uint16_t)~f0u, f1v = (uint16_t)~f0v;
+	uint16_t w00 = mulhi_u16(f1u, f1v), w10 = mulhi_u16(f0u, f1v), w01 = mulhi_u16(f1u, f0v), w11 = mulhi_u16(f0u, f0v);
+	for(int ch = 0; ch < 4; ch++)
+	{
+		uint16_t tx = texel16(t, p[ch], ch);
+		c[ch] = (uint16_t)((uint16_t)(mulhi_u16(tx, w00) + mulhi_u16(tx, w10)) + (uint16_t)(mulhi_u16(tx, w01) + mulhi_u16(tx, w11)));
+	}
+}
+
 /* sampleTexture128 :59-253 for function == Implicit; u[4], v[4] are the quad's lanes */
 static void sample_quad(const swcu_sampled_image *t, const float u[4], const float v[4], float out[4][4])
 {
@@ -641,27 +659,13 @@ static void sample_quad(const swcu_sampled_image *t, const float u[4], const flo
 	for(int k = 0; k < 4; k++)
 	{
 		uint16_t c[4];
-		if(minMagSplit && !linear)
-		{
-			/* reference still runs the 4-tap path with zero offset: weights sum to < 1; restate exactly */
-			const swcu_mip_level *m = &t->level[ilod < (int)t->levelCount ? (ilod < 0 ? 0 : ilod) : (int)t->levelCount - 1];
-			uint16_t uu = address(u[k], t->addressModeU), vv = address(v[k], t->addressModeV);
-			uint16_t W = (uint16_t)m->width, H = (uint16_t)m->height;
-			uint32_t x = mulhi_u16(uu, W), y = mulhi_u16(vv, H);
-			const uint8_t *p = (const uint8_t *)m->buffer + 4 * (size_t)(x + y * m->pitchP);
-			uint16_t f0u = (uint16_t)(uu * W), f0v = (uint16_t)(vv * H), f1u = (uint16_t)~f0u, f1v = (uint16_t)~f0v;
-			uint16_t w00 = mulhi_u16(f1u, f1v), w10 = mulhi_u16(f0u, f1v), w01 = mulhi_u16(f1u, f0v), w11 = mulhi_u16(f0u, f0v);
-			for(int ch = 0; ch < 4; ch++)
-			{
-				uint16_t tx = texel16(t, p[ch], ch);
-				c[ch] = (uint16_t)((uint16_t)(mulhi_u16(tx, w00) + mulhi_u16(tx, w10)) + (uint16_t)(mulhi_u16(tx, w01) + mulhi_u16(tx, w11)));
-			}
-		}
+		if(minMagSplit && !linear) sample_level_split_point(t, ilod, u[k], v[k], c);
 		else sample_level(t, ilod, u[k], v[k], linear, c);
 		if(t->mipmapMode == MIPMAP_MODE_LINEAR) /* sampleFilter :324-373 */
 		{
 			uint16_t cc[4];
-			sample_level(t, ilod + 1, u[k], v[k], linear, cc);
+			if(minMagSplit && !linear) sample_level_split_point(t, ilod + 1, u[k], v[k], cc); /* both levels of a trilinear fetch */
+			else sample_level(t, ilod + 1, u[k], v[k], linear, cc);
 			uint16_t utri = (uint16_t)trunc_int(lod * 65536.0f);
 			uint16_t inv = (uint16_t)~utri;
 			for(int ch = 0; ch < 4; ch++) c[ch] = (uint16_t)(mulhi_u16(c[ch], inv) + mulhi_u16(cc[ch], utri));

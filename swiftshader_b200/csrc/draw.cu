@@ -675,7 +675,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		d.scY1 = clampi_h(desc->scissor.y + (int)desc->scissor.height, y0, y1);
 	}
 	d.ms = (int)desc->sampleCount;
-	d.sampleMask = d.ms > 1 ? (desc->sampleMask & 0xF) : 1u;
+	d.sampleMask = desc->sampleMask & (d.ms > 1 ? 0xFu : 0x1u); // Context.cpp:527: bit 0 counts at one sample per pixel too
 
 	// ---- input assembly ----
 	d.indexType = desc->indexType;
@@ -990,7 +990,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	ctx->stats.draws++;
 	ctx->stats.primitives += d.primCount;
 	if(ctx->profiling) { ctx->lastKernels.clear(); ctx->eventsUsed = 0; }
-	if(d.primCount == 0 || d.scX0 >= d.scX1 || d.scY0 >= d.scY1) return SWCU_OK;
+	if(d.primCount == 0 || d.scX0 >= d.scX1 || d.scY0 >= d.scY1 || d.sampleMask == 0) return SWCU_OK; // no sample enabled: PixelRoutine.cpp:104-111
 	if((unsigned long long)d.primCount * d.triStride > (1ull << 36)) return fail(ctx, SWCU_E_NOMEM, "draw too large");
 
 	const uint32_t n = d.primCount;

@@ -987,7 +987,11 @@ DEVI void sample_texture(const DrawConst &d, const LodState &s, float u, float v
 		// minified 10 M-triangle scene 2.6 % of its tile kernel and saves the magnified 4K triangle 30 %; warp-voted variants that
 		// keep both levels' loads together were slower on both.)
 		uint32_t cc[4] = { 0, 0, 0, 0 };
-		if(utri != 0) sample_level<FAST>(d, s.ilod + 1, u, v, s.linear, cc);
+		if(utri != 0)
+		{
+			if(!FAST && s.split && !s.linear) sample_level_split_point(d, s.ilod + 1, u, v, cc); // both levels of a trilinear fetch
+			else sample_level<FAST>(d, s.ilod + 1, u, v, s.linear, cc);
+		}
 #pragma unroll
 		for(int ch = 0; ch < 4; ch++) c[ch] = (mulhi16(c[ch], inv) + mulhi16(cc[ch], utri)) & 0xFFFF;
 	}

@@ -246,7 +246,7 @@ class Scene:
         d.renderArea = capi.Rect(*(render_area or (0, 0, self.width, self.height)))
         d.cullMode, d.frontFace, d.depthClipEnable = draw.cullMode, draw.frontFace, 1
         d.depthBiasConstant, d.depthBiasClamp, d.depthBiasSlope = draw.depthBias
-        d.sampleCount, d.sampleMask = self.samples, draw.sampleMask & ((1 << self.samples) - 1) if self.samples > 1 else 1
+        d.sampleCount, d.sampleMask = self.samples, draw.sampleMask & ((1 << self.samples) - 1)
         d.alphaToCoverageEnable = int(draw.alphaToCoverage)
         if draw.depthBounds is not None:
             d.depthBoundsTestEnable, (d.minDepthBounds, d.maxDepthBounds) = 1, draw.depthBounds

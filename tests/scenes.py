@@ -389,6 +389,33 @@ def texture(seed: int, srgb: bool = False) -> Scene:
     return Scene(CELL, CELL, [d])
 
 
+def texsplit(seed: int) -> Scene:
+    """Min and mag filters that differ (FILTER_MIN_POINT_MAG_LINEAR / FILTER_MIN_LINEAR_MAG_POINT, SamplerCore.cpp:278-289): the
+    half-texel offset is masked by the sign of the LOD, so the "point" side still runs the 4-tap blend on four coinciding texels -
+    on both levels of a trilinear fetch.  Magnified, minified and mixed triangles, every mipmap mode, LOD bias and clamps."""
+    rng = np.random.default_rng(7300 + seed)
+    mag, mn = ((FILTER_LINEAR, FILTER_NEAREST), (FILTER_NEAREST, FILTER_LINEAR))[seed % 2]
+    variants = [
+        dict(w=64, h=64, levels=7, maxLod=6.0),
+        dict(w=64, h=64, levels=7, maxLod=6.0, mipmapMode=MIPMAP_NEAREST),
+        dict(w=32, h=64, levels=4, maxLod=3.0, mipLodBias=0.75),
+        dict(w=64, h=32, levels=1, maxLod=0.0),
+        dict(w=64, h=64, levels=7, maxLod=4.5, minLod=1.25, addressModeU=ADDR_CLAMP_TO_EDGE, addressModeV=ADDR_MIRRORED_REPEAT),
+        dict(w=32, h=32, levels=6, maxLod=5.0, mipLodBias=-0.5),
+    ]
+    v = dict(variants[(seed // 2) % len(variants)])
+    tex = Texture(_rand_tex(rng, v.pop("w"), v.pop("h"), v.pop("levels")), srgb=(seed % 3 == 2), magFilter=mag, minFilter=mn, **v)
+    tris = []
+    for i in range(4):
+        p = _tri_kind(rng, [5, 0, 1, 5][i])
+        uvscale = [1.0, 6.0, 30.0, 0.3][(seed + i) % 4]
+        col = np.zeros((3, 4))
+        col[:, :2] = rng.uniform(-4, 5, (3, 2)) * (uvscale / 9.0)
+        tris.append(_verts(rng, p, persp=(i % 2 == 0), colour=col))
+    d = Draw(np.concatenate(tris), P4C4, "vs_pos4_col4", "fs_tex_col4", texture=tex)
+    return Scene(CELL, CELL, [d], samples=(4 if seed % 5 == 4 else 1))
+
+
 def msaa(seed: int) -> Scene:
     """4x MSAA: per-sample coverage (R5 iv), resolve; odd seeds add depth test + blending."""
     rng = np.random.default_rng(8000 + seed)
@@ -527,6 +554,7 @@ FAMILIES = {
     "pathological": (pathological, 20),
     "srgbtex": (srgbtex, 12),
     "fragtests": (fragtests, 16),
+    "texsplit": (texsplit, 12),
 }
 
 
