@@ -47,17 +47,9 @@ def cuda_outputs(device, scene):
 MODES = {"direct": (0, 1), "binned": (1, 1), "generic": (1, 0)}
 
 
-# Families whose goldens were added after the last GPU visit of round 1 (no GPU minutes were left): the oracle is pinned on them
-# against the reference ICD on the CPU side, the CUDA path has the same change but has not run on hardware yet.  Non-strict: the
-# report shows XPASS once it does; remove the entry then.
-UNCONFIRMED_ON_HARDWARE = ("texsplit_",)
-
-
 @pytest.mark.parametrize("mode", sorted(MODES))
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_cuda_matches_reference_golden_and_oracle(device, name, mode, request):
-    if name.startswith(UNCONFIRMED_ON_HARDWARE):
-        request.node.add_marker(pytest.mark.xfail(strict=False, reason="golden added after the last GPU visit of round 1"))
+def test_cuda_matches_reference_golden_and_oracle(device, name, mode):
     scene = CASES[name]
     binned, fast = MODES[mode]
     device.set_option("force_binned", binned)
