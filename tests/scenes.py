@@ -535,6 +535,95 @@ def benchmark(which: int, width=1280, height=720, samples=1) -> Scene:
     return Scene(width, height, [d], samples=samples, clearColor=clear)
 
 
+def mixed(seed: int):
+    """One scene with every state drawn independently at random (the families tie state to seed % k): formats, sample count,
+    1-3 draws with random compare ops / stencil faces / blend equations / masks / bias / cull / scissor / viewport depth range /
+    alphaToCoverage / depth bounds / sampler state, ordinary and special-valued vertices."""
+    rng = np.random.default_rng(31000 + seed)
+    pick = lambda xs: xs[int(rng.integers(len(xs)))]  # noqa: E731
+    samples = pick([1, 1, 4])
+    colour = pick([FMT_R8G8B8A8_UNORM, FMT_B8G8R8A8_UNORM] + ([FMT_R8G8B8A8_SRGB, FMT_B8G8R8A8_SRGB, FMT_R16G16B16A16_SFLOAT, FMT_R32G32B32A32_SFLOAT] if samples == 1 else []))
+    has_stencil = bool(rng.integers(2))
+    depth_fmt = FMT_D32_SFLOAT if has_stencil else pick([FMT_D32_SFLOAT, FMT_D16_UNORM])
+    ops = [SOP_KEEP, SOP_ZERO, SOP_REPLACE, SOP_INC_CLAMP, SOP_DEC_CLAMP, SOP_INVERT, SOP_INC_WRAP, SOP_DEC_WRAP]
+    factors = list(range(15))  # VkBlendFactor 0..14
+    bops = [BOP_ADD, BOP_SUBTRACT, BOP_REVERSE_SUBTRACT, BOP_MIN, BOP_MAX]
+    draws = []
+    for _ in range(int(rng.integers(1, 4))):
+        n = int(rng.integers(3, 12))
+        tris = []
+        for i in range(n):
+            v = _verts(rng, _tri_kind(rng, int(rng.integers(6))), persp=bool(rng.integers(2)), colour=rng.uniform(-0.2, 1.2, (3, 4)))
+            if rng.integers(8) == 0:
+                v[int(rng.integers(3)), int(rng.integers(4))] = pick([np.nan, np.inf, -np.inf, 0.0, 1e30, -1e30, 3.4e38, 1e-40])
+            tris.append(v)
+        face = lambda: StencilFace(failOp=pick(ops), passOp=pick(ops), depthFailOp=pick(ops), compareOp=int(rng.integers(8)),  # noqa: E731
+                                   compareMask=pick([0xFF, 0x0F, 0xF3]), writeMask=pick([0xFF, 0x3C, 0x00]), reference=int(rng.integers(256)))
+        kw = dict(depthTest=bool(rng.integers(2)), depthWrite=bool(rng.integers(2)), depthCompareOp=int(rng.integers(8)),
+                  stencilTest=has_stencil and bool(rng.integers(2)), front=face(), back=face(),
+                  blend=bool(rng.integers(2)), srcColor=pick(factors), dstColor=pick(factors), colorOp=pick(bops),
+                  srcAlpha=pick(factors), dstAlpha=pick(factors), alphaOp=pick(bops), colorWriteMask=pick([0xF, 0xF, 0x7, 0x5, 0x8]),
+                  blendConstants=tuple(float(x) for x in rng.uniform(-0.2, 1.2, 4)), cullMode=pick([CULL_NONE, CULL_NONE, CULL_BACK, CULL_FRONT]),
+                  frontFace=int(rng.integers(2)), alphaToCoverage=rng.integers(4) == 0, sampleMask=pick([0xF, 0xF, 0x5, 0xA, 0x1]))
+        if rng.integers(3) == 0:
+            kw["depthBias"] = (float(rng.uniform(-8, 8)), pick([0.0, 0.001, -0.002]), float(rng.uniform(-2, 2)))
+        if rng.integers(4) == 0:
+            lo = float(np.float32(rng.uniform(0.1, 0.6)))
+            kw["depthBounds"] = (lo, float(np.float32(lo + rng.uniform(0.05, 0.4))))
+        if rng.integers(3) == 0:
+            x, y = int(rng.integers(0, 20)), int(rng.integers(0, 20))
+            kw["scissor"] = (x, y, int(rng.integers(8, CELL - x + 1)), int(rng.integers(8, CELL - y + 1)))
+        if rng.integers(4) == 0:
+            kw["viewport"] = (float(rng.integers(-8, 8)), float(rng.integers(-8, 8)), float(rng.integers(40, 80)), float(rng.integers(40, 80)),
+                              float(rng.uniform(-0.2, 0.4)), float(rng.uniform(0.6, 1.3)))
+        fs = "fs_col4"
+        if rng.integers(3) == 0:
+            w, h = pick([(16, 16), (64, 32), (32, 64)])
+            levels = pick([1, 1, int(np.log2(max(w, h))) + 1])
+            kw["texture"] = Texture(_rand_tex(rng, w, h, levels), srgb=bool(rng.integers(2)), magFilter=int(rng.integers(2)), minFilter=int(rng.integers(2)),
+                                    mipmapMode=int(rng.integers(2)), addressModeU=pick([ADDR_REPEAT, ADDR_CLAMP_TO_EDGE, ADDR_MIRRORED_REPEAT]),
+                                    addressModeV=pick([ADDR_REPEAT, ADDR_CLAMP_TO_EDGE, ADDR_MIRRORED_REPEAT]),
+                                    mipLodBias=pick([0.0, 0.75, -0.5]), minLod=pick([0.0, 1.25]), maxLod=float(levels - 1))
+            fs = "fs_tex_col4"
+            for v in tris:
+                v[:, 4:6] = rng.uniform(-4, 5, (3, 2)) * pick([0.1, 0.7, 3.0])
+        verts, attribs, vs = np.concatenate(tris).astype(np.float32), P4C4, "vs_pos4_col4"
+        layout = pick(["p4c4", "p4c4", "p3c3", "p3uv2", "p3"])
+        if layout != "p4c4":  # the reference benchmarks' vertex layouts: vec3 position (w = 1), vec3 colour / vec2 uv / nothing
+            with np.errstate(all="ignore"):
+                pos = verts[:, :3] / np.where(np.isfinite(verts[:, 3:4]) & (verts[:, 3:4] != 0), verts[:, 3:4], 1.0)
+            if layout == "p3c3":
+                verts, attribs, vs, fs = np.concatenate([pos, verts[:, 4:7]], axis=1), [(0, 3, 0), (1, 3, 3)], "vs_pos3_col3", "fs_col3"
+                kw.pop("texture", None)
+            elif layout == "p3uv2" and "texture" in kw:
+                verts, attribs, vs, fs = np.concatenate([pos, verts[:, 4:6]], axis=1), [(0, 3, 0), (1, 2, 3)], "vs_pos3_uv2", "fs_tex_uv2"
+            elif layout == "p3":
+                verts, attribs, vs, fs = pos, [(0, 3, 0)], "vs_pos3", "fs_white"
+                kw.pop("texture", None)
+            verts = np.ascontiguousarray(verts, dtype=np.float32)
+        nv = verts.shape[0]
+        topo = pick([TOPO_TRIANGLE_LIST, TOPO_TRIANGLE_LIST, TOPO_TRIANGLE_STRIP, TOPO_TRIANGLE_FAN])
+        if rng.integers(3) == 0:
+            kw["indices"] = rng.integers(0, nv, int(rng.integers(3, 40))).astype(pick([np.uint16, np.uint32]))
+            if rng.integers(2):
+                kw["first"] = int(rng.integers(0, 4))
+                kw["count"] = max(3, len(kw["indices"]) - kw["first"] - int(rng.integers(0, 3)))
+        elif rng.integers(3) == 0:
+            kw["first"] = int(rng.integers(0, 4))
+            kw["count"] = max(3, nv - kw["first"] - int(rng.integers(0, 3)))
+        draws.append(Draw(verts, attribs, vs, fs, topology=topo, **kw))
+    # the harness' host-side clear does not restate the clear's own sRGB encode / half rounding (scene.py clear_color_bytes)
+    if colour in (FMT_R8G8B8A8_SRGB, FMT_B8G8R8A8_SRGB):
+        clear = tuple(float(x) for x in rng.integers(0, 2, 4))
+    elif colour == FMT_R16G16B16A16_SFLOAT:
+        clear = tuple(float(x) / 8.0 for x in rng.integers(0, 9, 4))
+    else:
+        clear = tuple(float(x) for x in rng.uniform(0, 1, 4))
+    return Scene(CELL, CELL, draws, samples=samples, colorFormat=colour, hasDepth=True, depthFormat=depth_fmt, hasStencil=has_stencil,
+                 clearDepth=float(np.float32(rng.uniform(0.3, 1.0))), clearStencil=int(rng.integers(256)), clearColor=clear)
+
+
+
 FAMILIES = {
     # name: (generator, number of seeds)
     "coverage": (coverage, 40),
@@ -555,6 +644,7 @@ FAMILIES = {
     "srgbtex": (srgbtex, 12),
     "fragtests": (fragtests, 16),
     "texsplit": (texsplit, 12),
+    "mixed": (mixed, 24),
 }
 
 
