@@ -605,12 +605,12 @@ def mixed(seed: int):
         topo = pick([TOPO_TRIANGLE_LIST, TOPO_TRIANGLE_LIST, TOPO_TRIANGLE_STRIP, TOPO_TRIANGLE_FAN])
         if rng.integers(3) == 0:
             kw["indices"] = rng.integers(0, nv, int(rng.integers(3, 40))).astype(pick([np.uint16, np.uint32]))
-            if rng.integers(2):
+            if rng.integers(2) and len(kw["indices"]) >= 7:  # a sub-range that stays inside the index buffer
                 kw["first"] = int(rng.integers(0, 4))
-                kw["count"] = max(3, len(kw["indices"]) - kw["first"] - int(rng.integers(0, 3)))
-        elif rng.integers(3) == 0:
+                kw["count"] = len(kw["indices"]) - kw["first"] - int(rng.integers(0, 2))
+        elif rng.integers(3) == 0 and nv >= 7:
             kw["first"] = int(rng.integers(0, 4))
-            kw["count"] = max(3, nv - kw["first"] - int(rng.integers(0, 3)))
+            kw["count"] = nv - kw["first"] - int(rng.integers(0, 2))
         draws.append(Draw(verts, attribs, vs, fs, topology=topo, **kw))
     # the harness' host-side clear does not restate the clear's own sRGB encode / half rounding (scene.py clear_color_bytes)
     if colour in (FMT_R8G8B8A8_SRGB, FMT_B8G8R8A8_SRGB):
