@@ -685,8 +685,11 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	d.baseVertex = desc->baseVertex;
 	if(desc->indexType)
 	{
-		d.indexBuffer = dev_ptr(ctx, desc->indexBuffer);
-		if(!d.indexBuffer) return fail(ctx, SWCU_E_INVALID, "index buffer %p is not inside a registered range", desc->indexBuffer);
+		// every index the draw fetches must lie inside the registered range: the kernels do no bounds checks on the index stream
+		// (the reference reads whatever follows an index buffer that is too short; a device library must not)
+		const size_t nIdx = desc->topology == TOPO_TRIANGLE_LIST ? (size_t)desc->primitiveCount * 3 : (size_t)desc->primitiveCount + 2;
+		d.indexBuffer = desc->primitiveCount ? dev_ptr(ctx, desc->indexBuffer, nIdx * desc->indexType) : dev_ptr(ctx, desc->indexBuffer);
+		if(!d.indexBuffer) return fail(ctx, SWCU_E_INVALID, "index buffer [%p, +%zu) is not inside a registered range", desc->indexBuffer, nIdx * desc->indexType);
 		if(find_shadow(ctx, desc->indexBuffer, 1)->external) d.inputsExternal = 1;
 	}
 	// vertex-stage scalars: component c of stream l, or a constant (VertexRoutine::readStream, VertexRoutine.cpp:173-245)
