@@ -1,6 +1,8 @@
 """Run under torchrun on N GPUs: every rank renders its band of the reduced-size workloads through the CUDA path, the bands
 are all-gathered over NCCL, and rank 0 compares the assembled frame with the CPU oracle's full-frame render (bit-exact).
   python -m torch.distributed.run --nproc-per-node N tests/multi_gpu_check.py"""
+import hashlib
+import json
 import os
 import sys
 
@@ -83,6 +85,9 @@ def main():
                 want = swref.render_oracle(sc)
                 ref = swref.resolve_oracle(sc, want) if sc.samples > 1 else want["color"][0]
                 ok = np.array_equal(got, ref[:H])
+                # ... and with what the unmodified reference ICD rendered for the same scene (tests/golden/gen_workload_hashes.py)
+                want_sha = json.load(open(os.path.join(ROOT, "tests", "golden", "workload_hashes.json")))[f"small_{name}"]["hashes"]["color"]
+                ok = ok and hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == want_sha
                 print(f"multi_gpu_check {name} world={world} gather={mode}: {'ok' if ok else 'MISMATCH'}", flush=True)
                 bad += 0 if ok else 1
     dev.close()

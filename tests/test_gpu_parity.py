@@ -47,18 +47,9 @@ def cuda_outputs(device, scene):
 MODES = {"direct": (0, 1), "binned": (1, 1), "generic": (1, 0)}
 
 
-# Families whose goldens were added after the last GPU minute of round 1 was spent: the oracle is pinned on them against the
-# reference ICD on the CPU side (tests/test_oracle_golden.py); the CUDA path has not rendered them on hardware yet.  They are
-# skipped by default - an unvalidated state combination must not be able to take the rest of the GPU suite down with it - and
-# run with SWCU_RUN_UNCONFIRMED=1 (first thing to do on the next GPU visit; remove the entry once they pass).
-UNCONFIRMED_ON_HARDWARE = ("mixed_",)
-
-
 @pytest.mark.parametrize("mode", sorted(MODES))
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_cuda_matches_reference_golden_and_oracle(device, name, mode):
-    if name.startswith(UNCONFIRMED_ON_HARDWARE) and os.environ.get("SWCU_RUN_UNCONFIRMED") != "1":
-        pytest.skip("golden added after the last GPU visit of round 1; run with SWCU_RUN_UNCONFIRMED=1")
     scene = CASES[name]
     binned, fast = MODES[mode]
     device.set_option("force_binned", binned)
