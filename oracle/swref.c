@@ -1286,7 +1286,7 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 		int cop = fold_blend_op((int)d->colorBlendOp, (int)d->srcColorBlendFactor, (int)d->dstColorBlendFactor, !dr.floatTarget);
 		int aop = fold_blend_op((int)d->alphaBlendOp, (int)d->srcAlphaBlendFactor, (int)d->dstAlphaBlendFactor, !dr.floatTarget);
 		dr.colorWriteMask = d->color.buffer ? (int)(d->colorWriteMask & 0xF) : 0;
-		if(d->blendEnable && cop == BOP_DST_EXT && aop == BOP_DST_EXT) dr.colorWriteMask = 0;
+		if(cop == BOP_DST_EXT && aop == BOP_DST_EXT) dr.colorWriteMask = 0; /* colorWriteActive, Context.cpp:1304-1308: the stored factors, whether or not blending is enabled */
 		dr.blendEnable = d->blendEnable && dr.colorWriteMask && (cop != BOP_SRC_EXT || aop != BOP_SRC_EXT);
 		dr.srcF = fold_blend_factor((int)d->colorBlendOp, (int)d->srcColorBlendFactor);
 		dr.dstF = fold_blend_factor((int)d->colorBlendOp, (int)d->dstColorBlendFactor);

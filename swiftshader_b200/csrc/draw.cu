@@ -82,7 +82,8 @@ struct swcu_ctx
 	DevBuf keys, vals, keys2, vals2, tileBegin, tileEnd, cubTemp, zeroPage;
 	swcu_stats stats{};
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
-	std::map<uint64_t, swcu_shader_info> shaderCache;
+	struct CachedShader { std::vector<uint32_t> words; swcu_shader_info info; };
+	std::multimap<uint64_t, CachedShader> shaderCache; // keyed by a hash of the module, entries compared word for word on a hit
 	int optForceBinned = 0, optDirectMax = 64, optPinHost = 1;
 	int profiling = 0;
 	std::vector<KernelTime> lastKernels;
@@ -573,16 +574,20 @@ static int get_shader(swcu_ctx *ctx, const uint32_t *code, uint32_t words, uint3
 {
 	if(!code || !words) return fail(ctx, SWCU_E_INVALID, "missing %s shader", stage ? "fragment" : "vertex");
 	const uint64_t key = fnv1a(code, words);
-	auto it = ctx->shaderCache.find(key);
-	if(it == ctx->shaderCache.end())
+	auto range = ctx->shaderCache.equal_range(key);
+	auto it = range.first;
+	for(; it != range.second; ++it)
+		if(it->second.words.size() == words && !memcmp(it->second.words.data(), code, (size_t)words * 4)) break;
+	if(it == range.second)
 	{
-		swcu_shader_info info;
+		swcu_ctx::CachedShader entry;
 		char err[256];
-		int rc = swcu_shader_translate(code, words, &info, err, sizeof(err));
+		int rc = swcu_shader_translate(code, words, &entry.info, err, sizeof(err));
 		if(rc != SWCU_OK) return fail(ctx, rc, "%s shader rejected by the SPIR-V subset translator: %s", stage ? "fragment" : "vertex", err);
-		it = ctx->shaderCache.emplace(key, info).first;
+		entry.words.assign(code, code + words);
+		it = ctx->shaderCache.emplace(key, std::move(entry));
 	}
-	*out = it->second;
+	*out = it->second.info;
 	if(out->stage != stage) return fail(ctx, SWCU_E_INVALID, "shader stage mismatch (expected %u, module is %u)", stage, out->stage);
 	return SWCU_OK;
 }
@@ -813,7 +818,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		const int cop = fold_blend_op((int)desc->colorBlendOp, (int)desc->srcColorBlendFactor, (int)desc->dstColorBlendFactor, !floatTarget);
 		const int aop = fold_blend_op((int)desc->alphaBlendOp, (int)desc->srcAlphaBlendFactor, (int)desc->dstAlphaBlendFactor, !floatTarget);
 		d.colorWriteMask = desc->color.buffer ? (desc->colorWriteMask & 0xF) : 0;
-		if(desc->blendEnable && cop == BOP_DST_EXT && aop == BOP_DST_EXT) d.colorWriteMask = 0;
+		if(cop == BOP_DST_EXT && aop == BOP_DST_EXT) d.colorWriteMask = 0; // colorWriteActive (Context.cpp:1304-1308) tests the stored factors whether or not blending is enabled
 		d.blendEnable = desc->blendEnable && d.colorWriteMask && (cop != BOP_SRC_EXT || aop != BOP_SRC_EXT);
 		if(d.blendEnable)
 		{

@@ -299,7 +299,10 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			else if(pt.storage == SCInput)
 			{
 				if(d.builtin >= 0) return fail("built-in input %d outside the subset", d.builtin);
-				if(d.location < 0 || d.location >= SWCU_MAX_INPUTS) return fail("input without a supported Location");
+				// inputMask / flatMask / noPerspectiveMask are 32-bit (bit = location * 4 + component): vertex inputs at locations 0..7,
+				// fragment inputs at the locations the vertex stage can write (SWCU_MAX_VARYING_COMPONENTS / 4)
+				const int maxLoc = model == 4 ? SWCU_MAX_VARYING_COMPONENTS / 4 : 8;
+				if(d.location < 0 || d.location >= maxLoc || d.location >= SWCU_MAX_INPUTS) return fail("input without a supported Location (0..%d)", maxLoc - 1);
 				if(d.component != 0) return fail("Component decoration unsupported");
 				int n = obj.kind == Type::Float ? 1 : obj.kind == Type::Vector ? (int)obj.count : 0;
 				if(!n) return fail("input of unsupported type");
@@ -335,7 +338,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 		{
 			NEED(4); ID(a[1]); ID(a[2]);
 			const Value &s = values[a[2]];
-			if(s.kind != Value::Vec || na != 4 || (int)a[3] >= s.n) return fail("unsupported composite extract");
+			if(s.kind != Value::Vec || na != 4 || a[3] >= (uint32_t)s.n) return fail("unsupported composite extract");
 			Value v; v.kind = Value::Vec; v.n = 1; v.c[0] = s.c[a[3]];
 			values[a[1]] = v;
 			break;
@@ -345,7 +348,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			NEED(5); ID(a[1]); ID(a[2]); ID(a[3]);
 			const Value &obj = values[a[2]];
 			Value v = values[a[3]];
-			if(obj.kind != Value::Vec || obj.n != 1 || v.kind != Value::Vec || na != 5 || (int)a[4] >= v.n) return fail("unsupported composite insert");
+			if(obj.kind != Value::Vec || obj.n != 1 || v.kind != Value::Vec || na != 5 || a[4] >= (uint32_t)v.n) return fail("unsupported composite insert");
 			v.c[a[4]] = obj.c[0];
 			values[a[1]] = v;
 			break;
@@ -360,8 +363,8 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			{
 				uint32_t s = a[i];
 				if(s == 0xFFFFFFFFu) v.c[v.n++] = { SWCU_SRC_CONST, 0 };
-				else if((int)s < x.n) v.c[v.n++] = x.c[s];
-				else if((int)s < x.n + y.n) v.c[v.n++] = y.c[s - x.n];
+				else if(s < (uint32_t)x.n) v.c[v.n++] = x.c[s];
+				else if(s < (uint32_t)(x.n + y.n)) v.c[v.n++] = y.c[s - x.n];
 				else return fail("shuffle index out of range");
 			}
 			values[a[1]] = v;
@@ -450,7 +453,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 	out->stage = (uint32_t)model;
 
 	// inputs actually consumed by the results
-	auto use = [&](const swcu_shader_operand &o) { if(o.kind == SWCU_SRC_INPUT) out->inputMask |= 1u << o.value; };
+	auto use = [&](const swcu_shader_operand &o) { if(o.kind == SWCU_SRC_INPUT && o.value < 32) out->inputMask |= 1u << o.value; };
 	if(model == 0)
 	{
 		// a VS that never writes gl_Position is legal (tests/VulkanUnitTests/DrawTests.cpp:26-76) but outside the subset
@@ -477,6 +480,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			if(!varType[id] || types[varType[id]].storage != SCInput || decos[id].location < 0) continue;
 			for(int c = 0; c < 4; c++)
 			{
+				if(decos[id].location * 4 + c >= 32) continue;
 				uint32_t bit = 1u << (decos[id].location * 4 + c);
 				if(!(out->inputMask & bit)) continue;
 				if(decos[id].flat) out->flatMask |= bit;

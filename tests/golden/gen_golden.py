@@ -30,8 +30,17 @@ def sha(a: np.ndarray) -> str:
 
 def main():
     check = "--check-oracle" in sys.argv
+    # --only fam1,fam2: render only these families and MERGE them into the committed files (everything else is kept as it is)
+    only = None
+    if "--only" in sys.argv:
+        only = tuple(sys.argv[sys.argv.index("--only") + 1].split(","))
     hashes, full, seen_fam, bad = {}, {}, {}, 0
+    if only:
+        hashes = json.load(open(os.path.join(HERE, "golden_hashes.json")))
+        full = dict(np.load(os.path.join(HERE, "golden_full.npz")))
     for name, scene in scenes.all_cases():
+        if only and not name.startswith(only):
+            continue
         ref = swref.render_reference(scene)
         ref.pop("timing", None)
         hashes[name] = {k: sha(v) for k, v in ref.items()}

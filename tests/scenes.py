@@ -328,6 +328,21 @@ def blend(seed: int) -> Scene:
     return Scene(CELL, CELL, [d], clearColor=(0.3, 0.6, 0.2, 0.5), colorFormat=fmt)
 
 
+def blendoff(seed: int) -> Scene:
+    """Blend factors that fold to "keep the destination" while blending is DISABLED: FragmentOutputInterfaceState::colorWriteActive
+    (Context.cpp:1304-1308) applies the DST_EXT test to the stored factors whether or not blendEnable is set, so the colour write is
+    off (depth still written); plus the neighbouring states that must keep writing."""
+    rng = np.random.default_rng(5500 + seed)
+    eq = [(BF_ZERO, BF_ONE, BOP_ADD, BF_ZERO, BF_ONE, BOP_ADD),                            # both fold to DST: nothing written
+          (BF_ZERO, BF_ONE, BOP_REVERSE_SUBTRACT, BF_ZERO, BF_ONE, BOP_ADD),               # both fold to DST
+          (BF_ZERO, BF_ONE, BOP_ADD, BF_ONE, BF_ZERO, BOP_ADD),                            # alpha is SRC: the source is written
+          (BF_ZERO, BF_ONE, BOP_ADD, BF_ZERO, BF_ONE, BOP_ADD)][seed % 4]
+    (sc, dc, co, sa, da, ao) = eq
+    d = Draw(_layers(rng, 6), P4C4, "vs_pos4_col4", "fs_col4", blend=(seed % 4 == 3), srcColor=sc, dstColor=dc, colorOp=co,
+             srcAlpha=sa, dstAlpha=da, alphaOp=ao, depthTest=True, depthWrite=True)
+    return Scene(CELL, CELL, [d], hasDepth=True, clearColor=(0.3, 0.6, 0.2, 0.5), samples=(4 if seed >= 4 else 1))
+
+
 def stencil(seed: int) -> Scene:
     """Stencil compare ops x ops, front/back by winding, masks; with and without depth test (R9)."""
     rng = np.random.default_rng(6000 + seed)
@@ -645,6 +660,7 @@ FAMILIES = {
     "fragtests": (fragtests, 16),
     "texsplit": (texsplit, 12),
     "mixed": (mixed, 24),
+    "blendoff": (blendoff, 6),
 }
 
 
