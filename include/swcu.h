@@ -215,6 +215,7 @@ typedef struct swcu_stats
 	uint64_t primitives;
 	uint64_t h2dBytes;
 	uint64_t d2hBytes;
+	uint64_t pairs;            /* (region, triangle) pairs binned by the draws seen by swcu_sync since create/reset */
 } swcu_stats;
 
 /* ---- lifetime ---- */

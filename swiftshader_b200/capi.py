@@ -94,7 +94,7 @@ class ShaderInfo(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("draws", C.c_uint64), ("kernelLaunches", C.c_uint64), ("primitives", C.c_uint64),
-                ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64)]
+                ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64), ("pairs", C.c_uint64)]
 
 
 EXPORTS = [

@@ -3,10 +3,6 @@
 // sequence that replaces DrawCall::run (Renderer.cpp:551-662).  No torch types, no CPU rendering fallback.
 #include "kernels.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/transform_iterator.h>
-
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -54,15 +50,17 @@ struct swcu_ctx
 	cudaStream_t stream = nullptr, ownStream = nullptr;
 	std::map<uintptr_t, Shadow> mem;
 	std::string err;
-	// Buffers of the setup phase (k_cull, k_setup, pair-offset scan) exist twice: the setup of draw i+1 runs on its own stream
-	// while the tile kernel of draw i is still reading the other set, so the host's wait for the pair count (the one sync of a
-	// binned draw) no longer leaves the GPU idle.
+	// Buffers of the setup phase (k_cull, k_setup, binning) exist twice: the setup of draw i+1 runs on its own stream while the tile
+	// kernel of draw i is still reading the other set.  Nothing of a draw has to reach the host before its tile kernel is launched:
+	// the pair buffer holds 4 pairs per triangle plus a budget for the big triangles (swcu_set_option "big_pair_budget").
 	struct SetupSet
 	{
-		DevBuf triRecords, spans, bigList, tileCount, pairOffset, counters, cullFlags, scanTemp;
-		DrawCounters *hostCounters = nullptr; // pinned
+		DevBuf triRecords, bigList, triRect, binCount, binStart, pairs, counters, cullFlags;
 		cudaEvent_t tileDone = nullptr;       // recorded on the main stream after the last kernel that reads this set
 		bool tileDoneValid = false;
+		cudaEvent_t setupDone = nullptr;      // recorded on the setup stream after the binning of a pipelined draw
+		DrawCounters *hostCounters = nullptr; // pinned: the counters of the last draw that used this set, copied by its k_tile's successor
+		bool countersPending = false;
 	} set[2];
 	int cur = 0;
 	cudaStream_t setupStream = nullptr;
@@ -79,7 +77,9 @@ struct swcu_ctx
 	bool fenceValid[SWCU_MAX_FENCES] = {};
 	int optCopyStreams = 1;
 	int optPipeline = 1;
-	DevBuf keys, vals, keys2, vals2, tileBegin, tileEnd, cubTemp, zeroPage;
+	DevBuf zeroPage;
+	size_t optBigPairBudget = (size_t)16 << 20; // (region, triangle) pairs the big triangles of one draw may occupy
+	int lastOverflow = 0;
 	swcu_stats stats{};
 	cudaEvent_t t0 = nullptr, t1 = nullptr;
 	struct CachedShader { std::vector<uint32_t> words; swcu_shader_info info; };
@@ -170,7 +170,9 @@ extern "C" int swcu_create(swcu_ctx **out, int device_ordinal)
 	for(auto &S : ctx->set)
 	{
 		if((e = cudaMallocHost((void **)&S.hostCounters, sizeof(DrawCounters))) != cudaSuccess) return bail("cudaMallocHost", e);
+		memset(S.hostCounters, 0, sizeof(DrawCounters));
 		if((e = cudaEventCreateWithFlags(&S.tileDone, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+		if((e = cudaEventCreateWithFlags(&S.setupDone, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
 	}
 	*out = ctx;
 	return SWCU_OK;
@@ -191,14 +193,14 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 		if(kv.second.upEvent) cudaEventDestroy(kv.second.upEvent);
 	}
 	if(ctx->setupStream) cudaStreamSynchronize(ctx->setupStream);
-	DevBuf *bufs[] = { &ctx->keys, &ctx->vals, &ctx->keys2, &ctx->vals2, &ctx->tileBegin, &ctx->tileEnd, &ctx->cubTemp, &ctx->zeroPage };
-	for(DevBuf *b : bufs) cudaFree(b->p);
+	cudaFree(ctx->zeroPage.p);
 	for(auto &S : ctx->set)
 	{
-		DevBuf *sb[] = { &S.triRecords, &S.spans, &S.bigList, &S.tileCount, &S.pairOffset, &S.counters, &S.cullFlags, &S.scanTemp };
+		DevBuf *sb[] = { &S.triRecords, &S.bigList, &S.triRect, &S.binCount, &S.binStart, &S.pairs, &S.counters, &S.cullFlags };
 		for(DevBuf *b : sb) cudaFree(b->p);
 		if(S.hostCounters) cudaFreeHost(S.hostCounters);
 		if(S.tileDone) cudaEventDestroy(S.tileDone);
+		if(S.setupDone) cudaEventDestroy(S.setupDone);
 	}
 	if(ctx->evUpload) cudaEventDestroy(ctx->evUpload);
 	if(ctx->evMark) cudaEventDestroy(ctx->evMark);
@@ -443,6 +445,16 @@ extern "C" int swcu_sync(swcu_ctx *ctx)
 	CU(cudaStreamSynchronize(ctx->setupStream));
 	CU(cudaStreamSynchronize(ctx->stream));
 	CU(cudaStreamSynchronize(ctx->d2hStream));
+	// the device is idle: the counters of every finished draw are on the host
+	for(auto &S : ctx->set)
+	{
+		if(!S.countersPending) continue;
+		S.countersPending = false;
+		ctx->stats.pairs += S.hostCounters->pairTotal;
+		if(S.hostCounters->overflow)
+			return fail(ctx, SWCU_E_NOMEM, "a draw had big triangles whose bounding boxes cover more than %zu regions in total (%llu): they were NOT rendered; raise swcu_set_option(\"big_pair_budget\")",
+			            ctx->optBigPairBudget, (unsigned long long)S.hostCounters->bigReserved);
+	}
 	return SWCU_OK;
 }
 
@@ -521,6 +533,7 @@ extern "C" int swcu_set_option(swcu_ctx *ctx, const char *name, int value)
 	else if(!strcmp(name, "tma")) ctx->optTma = value;
 	else if(!strcmp(name, "fast_state")) ctx->optFastState = value;
 	else if(!strcmp(name, "pipeline")) ctx->optPipeline = value;
+	else if(!strcmp(name, "big_pair_budget")) ctx->optBigPairBudget = (size_t)std::max(value, 0);
 	else if(!strcmp(name, "copy_streams"))
 	{
 		// 0: copies on the main stream (needed when something the library cannot see - e.g. an NCCL collective on the caller's
@@ -863,33 +876,29 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	d.tilesY = (d.fbHeight + SWCU_TILE_H - 1) / SWCU_TILE_H;
 	d.tileX0 = d.scX0 / SWCU_TILE_W; d.tileY0 = d.scY0 / SWCU_TILE_H;
 	d.tileX1 = (d.scX1 + SWCU_TILE_W - 1) / SWCU_TILE_W; d.tileY1 = (d.scY1 + SWCU_TILE_H - 1) / SWCU_TILE_H;
-	d.triStride = swcu_tri_stride(d.nslots, d.ms);
+	d.numBins = (uint32_t)(d.tilesX * d.tilesY * 4);
+	d.planeOffset = swcu_plane_offset(d.ms);
+	d.triStride = swcu_tri_stride(d.nslots, d.ms, d.depthTestActive != 0);
 	if(vsrcErr) return vsrcErr;
 	return SWCU_OK;
 }
 
-struct TileRectCount
+// The counters of a draw's setup phase go to the host through its mapped pinned page, written by a kernel (a cudaMemcpyAsync
+// would queue in the device-to-host copy engine behind a frame download).  Nobody waits for them: they are looked at the next
+// time the host has drained the device anyway (swcu_sync), to report a big triangle that did not fit the pair budget.
+__global__ void k_report(const DrawCounters *c, DrawCounters *hostOut)
 {
-	__host__ __device__ uint32_t operator()(uint32_t r) const { return tile_rect_count(r); }
-};
-
-// The totals reach the host through its mapped pinned page, written by the kernel itself: a cudaMemcpyAsync would queue in the
-// device-to-host copy engine behind a frame download that may be in flight there, and the host's one wait of a binned draw would
-// then last as long as that download.
-__global__ void k_pair_total(const uint32_t *pairOffset, const uint32_t *tileCount, uint32_t n, DrawCounters *c, DrawCounters *hostOut)
-{
-	c->pairTotal = (unsigned long long)pairOffset[n - 1] + tile_rect_count(tileCount[n - 1]);
 	*hostOut = *c;
 	__threadfence_system();
 }
 
-// ---- TMA descriptors of the attachments: a 3-D tensor (x, y, sample plane) with a (tile width, tile height, samples) box ----
+// ---- TMA descriptors of the attachments: a 3-D tensor (x, y, sample plane) with a (region width, region height, samples) box ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static bool tma_eligible(const unsigned char *base, int pitchB, int sliceB, int bpp)
 {
-	return base && ((uintptr_t)base % 16 == 0) && pitchB > 0 && sliceB > 0 && (pitchB % 16 == 0) && (sliceB % 16 == 0) && (SWCU_TILE_W * bpp) % 16 == 0;
+	return base && ((uintptr_t)base % 16 == 0) && pitchB > 0 && sliceB > 0 && (pitchB % 16 == 0) && (sliceB % 16 == 0) && (SWCU_REGION_W * bpp) % 16 == 0;
 }
 
 // epp: elements per pixel along x (floating-point colour targets are mapped as 2 or 4 32-bit words per pixel)
@@ -913,7 +922,7 @@ static bool get_tensor_map(swcu_ctx *ctx, CUtensorMap *out, unsigned char *base,
 		CUtensorMap m;
 		const cuuint64_t dims[3] = { (cuuint64_t)w * epp, (cuuint64_t)h, (cuuint64_t)ms };
 		const cuuint64_t strides[2] = { (cuuint64_t)pitchB, (cuuint64_t)sliceB };
-		const cuuint32_t box[3] = { (cuuint32_t)(SWCU_TILE_W * epp), SWCU_TILE_H, (cuuint32_t)ms };
+		const cuuint32_t box[3] = { (cuuint32_t)(SWCU_REGION_W * epp), SWCU_REGION_H, (cuuint32_t)ms }; // one region: what a warp of the tile kernel stages
 		const cuuint32_t estr[3] = { 1, 1, 1 };
 		CUresult r = ((EncodeTiledFn)ctx->encodeTiled)(&m, bpp == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : (bpp == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8), 3, base, dims, strides, box, estr,
 		                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -930,13 +939,14 @@ static void launch_tile4(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps
 {
 	LaunchScope ls(ctx, MS == 4 ? "k_tile<4>" : "k_tile<1>");
 	const int smem = TileLayout<MS, SH>::total(d.depthTestActive != 0, d.stencilActive != 0, FS ? 1 : (int)d.colorEpp);
-	if(MS == 4)
+	static int configured = -1; // per instantiation: the largest dynamic shared-memory size asked for so far
+	if(smem > configured)
 	{
-		// 8 CTAs of 4x MSAA colour + depth tiles need ~224 KB of the SM's shared memory: ask for the largest carve-out
-		static bool once = false;
-		if(!once) { cudaFuncSetAttribute(k_tile<MS, SH, BL, FS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); once = true; }
+		cudaFuncSetAttribute(k_tile<MS, SH, BL, FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+		cudaFuncSetAttribute(k_tile<MS, SH, BL, FS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		configured = smem;
 	}
-	k_tile<MS, SH, BL, FS><<<grid, TILE_THREADS, smem, ctx->stream>>>(d, maps, (const uint32_t *)ctx->tileBegin.p, (const uint32_t *)ctx->tileEnd.p, (const uint32_t *)ctx->vals.p);
+	k_tile<MS, SH, BL, FS><<<grid, TILE_THREADS, smem, ctx->stream>>>(d, maps);
 }
 
 // The common fixed-function state the FS instantiations of k_tile assume (see kernels.cuh); anything else runs the
@@ -1005,8 +1015,8 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	d.direct = (!ctx->optForceBinned && (int)n <= ctx->optDirectMax) ? 1u : 0u;
 	// The setup phase of this draw uses the set the draw before the previous one used.  A binned draw runs it on the setup
 	// stream: it waits only for the inputs (last upload) and for the last reader of this set, not for the tile kernel of the
-	// previous draw, which keeps the GPU busy while the host waits for the pair count.  Direct draws, profiling mode (per-kernel
-	// events) and inputs in caller-owned device memory (whose producers the library cannot see) stay on the main stream.
+	// previous draw.  Direct draws, profiling mode (per-kernel events) and inputs in caller-owned device memory (whose producers
+	// the library cannot see) stay on the main stream.  No step of a draw waits for the host.
 	swcu_ctx::SetupSet &S = ctx->set[ctx->cur];
 	ctx->cur ^= 1;
 	const bool pipelined = !d.direct && ctx->optPipeline && !ctx->profiling && !d.inputsExternal;
@@ -1027,123 +1037,89 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	for(uint32_t t = 0; t < desc->sampledImageCount && t < SWCU_MAX_SAMPLED_IMAGES; t++)
 		for(uint32_t l = 0; l < desc->sampledImage[t].levelCount && l < SWCU_MIPMAP_LEVELS; l++)
 			if((rc = main_touches(ctx, desc->sampledImage[t].level[l].buffer, false))) return rc;
+
+	// ---- work buffers: every capacity follows from the triangle count, nothing is sized by a device-side result ----
+	const size_t scanBlocks = ((size_t)d.numBins + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS);
+	const size_t countersBytes = sizeof(DrawCounters) + 4 * (scanBlocks + 1);
+	const size_t pairCap = d.direct ? 0 : std::min<size_t>((size_t)4 * n + ctx->optBigPairBudget, 0x3FFFFFF0u);
+	if(!d.direct && pairCap < (size_t)4 * n) return fail(ctx, SWCU_E_NOMEM, "%u triangles exceed the pair index space", n);
 	if((rc = ensure(ctx, S.triRecords, (size_t)n * d.triStride))) return rc;
-	if((rc = ensure(ctx, S.tileCount, (size_t)n * 4))) return rc;
-	if((rc = ensure(ctx, S.counters, sizeof(DrawCounters)))) return rc;
+	if((rc = ensure(ctx, S.triRect, (size_t)n * 4))) return rc;
+	if((rc = ensure(ctx, S.bigList, (size_t)n * sizeof(BigTri)))) return rc; // every triangle may be a big one
+	if((rc = ensure(ctx, S.counters, countersBytes))) return rc;
+	if(!d.direct)
+	{
+		const size_t before = S.binCount.cap;
+		if((rc = ensure(ctx, S.binCount, (size_t)d.numBins * 4))) return rc;
+		if(S.binCount.cap != before) CU(cudaMemsetAsync(S.binCount.p, 0, S.binCount.cap, ss)); // k_fill counts every bin back down to zero
+		if((rc = ensure(ctx, S.binStart, ((size_t)d.numBins + 1) * 4))) return rc;
+		if((rc = ensure(ctx, S.pairs, pairCap * 4))) return rc;
+	}
 	if(!ctx->zeroPage.p)
 	{
 		if((rc = ensure(ctx, ctx->zeroPage, 256))) return rc;
 		CU(cudaMemsetAsync(ctx->zeroPage.p, 0, 256, ctx->stream));
 		CU(cudaStreamSynchronize(ctx->stream));
 	}
-	const size_t scRows = (size_t)(d.scY1 - d.scY0);
-	size_t spanWant, bigWant;
-	if(d.direct) { spanWant = (size_t)n * d.ms * scRows; bigWant = n; }
-	else
-	{
-		spanWant = std::max<size_t>(S.spans.cap / 4, std::max<size_t>((size_t)n * d.ms * 8, 1u << 20));
-		bigWant = std::max<size_t>(S.bigList.cap / sizeof(BigTri), 1u << 14);
-	}
+	d.triRecords = (unsigned char *)S.triRecords.p;
+	d.triRect = (uint32_t *)S.triRect.p;
+	d.counters = (DrawCounters *)S.counters.p;
+	d.zeroPage = ctx->zeroPage.p;
+	d.bigList = (BigTri *)S.bigList.p;
+	d.bigCapacity = (uint32_t)std::min<size_t>(S.bigList.cap / sizeof(BigTri), 0x7FFFFFFFu);
+	d.binCount = (uint32_t *)S.binCount.p;
+	d.binStart = (uint32_t *)S.binStart.p;
+	d.pairs = (uint32_t *)S.pairs.p;
+	d.bigBudget = d.direct ? 0 : pairCap - (size_t)4 * n;
 	const dim3 tileGrid((unsigned)(d.tileX1 - d.tileX0), (unsigned)(d.tileY1 - d.tileY0));
-	const uint32_t numTiles = (uint32_t)(d.tilesX * d.tilesY);
 
-	for(int attempt = 0;; attempt++)
+	CU(cudaMemsetAsync(d.counters, 0, countersBytes, ss));
+	// band mode: the scissor / render area keeps less than 3/4 of the framebuffer rows (a rank of a multi-GPU frame)
+	d.cullFlags = nullptr;
+	if(!d.direct && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
 	{
-		if((rc = ensure(ctx, S.spans, spanWant * 4))) return rc;
-		if((rc = ensure(ctx, S.bigList, bigWant * sizeof(BigTri)))) return rc;
-		d.triRecords = (unsigned char *)S.triRecords.p;
-		d.tileCount = (uint32_t *)S.tileCount.p;
-		d.counters = (DrawCounters *)S.counters.p;
-		d.zeroPage = ctx->zeroPage.p;
-		d.spans = (uint32_t *)S.spans.p;
-		d.spanCapacity = std::min<unsigned long long>(S.spans.cap / 4, 0xFFFFFFFFull);
-		d.bigList = (BigTri *)S.bigList.p;
-		d.bigCapacity = (uint32_t)std::min<size_t>(S.bigList.cap / sizeof(BigTri), 0x7FFFFFFFu);
-		CU(cudaMemsetAsync(d.counters, 0, sizeof(DrawCounters), ss));
-		// band mode: the scissor / render area keeps less than 3/4 of the framebuffer rows (a rank of a multi-GPU frame)
-		d.cullFlags = nullptr;
-		if(!d.direct && attempt == 0 && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
-		{
-			if((rc = ensure(ctx, S.cullFlags, n))) return rc;
-			LaunchScope ls(ctx, "k_cull", ss);
-			k_cull<<<(n + 255) / 256, 256, 0, ss>>>(d, (unsigned char *)S.cullFlags.p);
-			d.cullFlags = (const unsigned char *)S.cullFlags.p;
-		}
-		else if(!d.direct && attempt > 0 && S.cullFlags.p && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
-			d.cullFlags = (const unsigned char *)S.cullFlags.p; // flags of the first attempt are still valid
-		{
-			LaunchScope ls(ctx, "k_setup", ss);
-			const size_t scratch = (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4;
-			if(d.ms != 1) k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
-			else k_setup_1x<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
-		}
-		if(d.direct) break;
-
-		// ---- binning: pair offsets, totals back to the host (the one sync of a binned draw) ----
-		if((rc = ensure(ctx, S.pairOffset, (size_t)n * 4))) return rc;
-		size_t tempBytes = 0;
-		thrust::transform_iterator<TileRectCount, const uint32_t *> counts((const uint32_t *)d.tileCount, TileRectCount());
-		CU(cub::DeviceScan::ExclusiveSum(nullptr, tempBytes, counts, (uint32_t *)S.pairOffset.p, (int)n, ss));
-		if((rc = ensure(ctx, S.scanTemp, tempBytes))) return rc;
-		tempBytes = S.scanTemp.cap;
-		CU(cub::DeviceScan::ExclusiveSum(S.scanTemp.p, tempBytes, counts, (uint32_t *)S.pairOffset.p, (int)n, ss));
-		{
-			LaunchScope ls(ctx, "k_pair_total", ss);
-			k_pair_total<<<1, 1, 0, ss>>>((const uint32_t *)S.pairOffset.p, d.tileCount, n, d.counters, S.hostCounters);
-		}
-		CU(cudaStreamSynchronize(ss)); // the setup phase only: the main stream may still be running the previous draw's tiles
-		const DrawCounters hc = *S.hostCounters;
-		if(hc.overflow)
-		{
-			if(attempt >= 2) return fail(ctx, SWCU_E_NOMEM, "work buffers still too small after growing (spans %llu, big %llu)", hc.spanCursor, hc.bigSlots);
-			if(hc.spanCursor > 0xFFFFFFF0ull) return fail(ctx, SWCU_E_NOMEM, "span table of %llu rows exceeds the 32-bit index space", hc.spanCursor);
-			spanWant = std::max<size_t>(spanWant, (size_t)hc.spanCursor + 1024);
-			bigWant = std::max<size_t>(bigWant, (size_t)hc.bigSlots + 64);
-			continue;
-		}
-		if(hc.pairTotal > 0x7FFFFFF0ull) return fail(ctx, SWCU_E_NOMEM, "%llu (tile, triangle) pairs exceed the 31-bit index space", hc.pairTotal);
-		const uint32_t pairs = (uint32_t)hc.pairTotal;
-		if(pairs == 0) return SWCU_OK;
-		if((rc = ensure(ctx, ctx->keys, (size_t)pairs * 4))) return rc;
-		if((rc = ensure(ctx, ctx->vals, (size_t)pairs * 4))) return rc;
-		if((rc = ensure(ctx, ctx->keys2, (size_t)pairs * 4))) return rc;
-		if((rc = ensure(ctx, ctx->vals2, (size_t)pairs * 4))) return rc;
-		if((rc = ensure(ctx, ctx->tileBegin, (size_t)numTiles * 4))) return rc;
-		if((rc = ensure(ctx, ctx->tileEnd, (size_t)numTiles * 4))) return rc;
-		{
-			LaunchScope ls(ctx, "k_emit");
-			k_emit<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d, (const uint32_t *)S.pairOffset.p, (uint32_t *)ctx->keys.p, (uint32_t *)ctx->vals.p);
-		}
-		if(hc.bigSlots)
-		{
-			LaunchScope ls(ctx, "k_big");
-			const unsigned gx = (unsigned)std::min<unsigned long long>(hc.bigSlots, 4096);
-			const unsigned gy = hc.bigSlots < 64 ? 16 : 1;
-			k_big<<<dim3(gx, gy), 256, 0, ctx->stream>>>(d, (const uint32_t *)S.pairOffset.p, (uint32_t *)ctx->keys.p, (uint32_t *)ctx->vals.p);
-		}
-		// stable sort by tile: per-tile lists keep API order
-		int bits = 1;
-		while((1u << bits) <= numTiles) bits++;
-		cub::DoubleBuffer<uint32_t> kb((uint32_t *)ctx->keys.p, (uint32_t *)ctx->keys2.p), vb((uint32_t *)ctx->vals.p, (uint32_t *)ctx->vals2.p);
-		tempBytes = 0;
-		CU(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, kb, vb, (int)pairs, 0, bits, ctx->stream));
-		if((rc = ensure(ctx, ctx->cubTemp, tempBytes))) return rc;
-		tempBytes = ctx->cubTemp.cap;
-		CU(cub::DeviceRadixSort::SortPairs(ctx->cubTemp.p, tempBytes, kb, vb, (int)pairs, 0, bits, ctx->stream));
-		if(kb.Current() != (uint32_t *)ctx->keys.p) { std::swap(ctx->keys, ctx->keys2); }
-		if(vb.Current() != (uint32_t *)ctx->vals.p) { std::swap(ctx->vals, ctx->vals2); }
-		CU(cudaMemsetAsync(ctx->tileBegin.p, 0, (size_t)numTiles * 4, ctx->stream));
-		CU(cudaMemsetAsync(ctx->tileEnd.p, 0, (size_t)numTiles * 4, ctx->stream));
-		{
-			LaunchScope ls(ctx, "k_tile_ranges");
-			k_tile_ranges<<<(pairs + 1023) / 1024, 256, 0, ctx->stream>>>((const uint32_t *)ctx->keys.p, pairs, numTiles, (uint32_t *)ctx->tileBegin.p, (uint32_t *)ctx->tileEnd.p);
-		}
-		break;
+		if((rc = ensure(ctx, S.cullFlags, n))) return rc;
+		LaunchScope ls(ctx, "k_cull", ss);
+		k_cull<<<(n + 255) / 256, 256, 0, ss>>>(d, (unsigned char *)S.cullFlags.p);
+		d.cullFlags = (const unsigned char *)S.cullFlags.p;
 	}
-	if(d.direct)
 	{
-		LaunchScope ls(ctx, "k_big");
-		k_big<<<dim3(std::min<uint32_t>(n, 64u), n <= 4 ? 16 : (n <= 16 ? 4 : 1)), 256, 0, ctx->stream>>>(d, nullptr, nullptr, nullptr);
+		LaunchScope ls(ctx, "k_setup", ss);
+		const size_t scratch = (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4;
+		if(d.ms != 1) k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
+		else k_setup_1x<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
+	}
+	if(!d.direct)
+	{
+		// ---- binning: count (k_setup + k_bigcount), scan, fill, order the long bins; all sized on the host, all asynchronous ----
+		const unsigned bigBlocks = 148; // grid-stride over the big list, whose length only the device knows
+		{
+			LaunchScope ls(ctx, "k_bigcount", ss);
+			k_bigcount<<<bigBlocks, 32 * BIG_WARPS_PER_BLOCK, 0, ss>>>(d);
+		}
+		{
+			LaunchScope ls(ctx, "k_binscan", ss);
+			k_binscan<<<(unsigned)scanBlocks, SCAN_THREADS, 0, ss>>>(d.binCount, d.binStart, d.numBins, (volatile uint32_t *)(d.counters + 1), d.counters);
+		}
+		{
+			LaunchScope ls(ctx, "k_fill", ss);
+			const unsigned smallBlocks = (n + 255) / 256;
+			k_fill<<<smallBlocks + bigBlocks, 256, 0, ss>>>(d, smallBlocks);
+		}
+		{
+			LaunchScope ls(ctx, "k_sortbig", ss);
+			k_sortbig<<<148 * 2, SORTBIG_THREADS, 0, ss>>>(d.binStart, d.pairs, d.numBins);
+		}
+		{
+			LaunchScope ls(ctx, "k_report", ss);
+			k_report<<<1, 1, 0, ss>>>(d.counters, S.hostCounters);
+			S.countersPending = true;
+		}
+		if(pipelined)
+		{
+			CU(cudaEventRecord(S.setupDone, ss));
+			CU(cudaStreamWaitEvent(ctx->stream, S.setupDone, 0));
+		}
 	}
 	// ---- tensor maps of the attachments the tile kernel stages ----
 	TileMaps maps;
@@ -1161,7 +1137,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	}
 	if(d.ms == 4) launch_tile<4>(ctx, d, maps, tileGrid); else launch_tile<1>(ctx, d, maps, tileGrid);
 	CU(cudaGetLastError());
-	CU(cudaEventRecord(S.tileDone, ctx->stream)); // last reader of this set's records / spans / offsets
+	CU(cudaEventRecord(S.tileDone, ctx->stream)); // last reader of this set's records / bins
 	S.tileDoneValid = true;
 	return SWCU_OK;
 }

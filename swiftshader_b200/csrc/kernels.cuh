@@ -361,6 +361,8 @@ __global__ void __launch_bounds__(256) k_cull(const __grid_constant__ DrawConst 
 	flags[tri] = rows_missed(d, y[0], w[0], y[1], w[1], y[2], w[2]) ? 0 : 1;
 }
 
+DEVI uint32_t region_bin(const DrawConst &d, int rx, int ry) { return (uint32_t)(((ry >> 1) * d.tilesX + (rx >> 1)) * 4 + (ry & 1) * 2 + (rx & 1)); }
+
 DEVI int sel3(int i, int a0, int a1, int a2) { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
 DEVI float sel3(int i, float a0, float a1, float a2) { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
 
@@ -376,7 +378,6 @@ DEVI void setup_triangle(const DrawConst &d)
 	const bool live = tri < d.primCount;
 	const int MS = MSC ? MSC : d.ms;
 	const bool msaa = MS > 1;
-	uint32_t nTiles = 0;
 	bool visible = false;
 	uint32_t idx[3] = { 0, 0, 0 };
 	const bool precull = live && d.cullFlags != nullptr && d.cullFlags[tri] == 0; // marked by k_cull: rows outside the band
@@ -470,54 +471,39 @@ DEVI void setup_triangle(const DrawConst &d)
 		} while(0);
 	}
 
-	// ---- span-table and big-list allocation for the big triangles, one atomic per warp ----
+	// ---- classification.  SMALL: the clamped pixel bounds fit an 8 x 8 frame — the spans become bit masks stored in the record,
+	//      and the triangle touches at most 2 x 2 region bins.  BIG: everything else (also clipped-to-garbage polygons whose edges the
+	//      reference walks in wrapped arithmetic): the polygon goes to the big list, the region warps of the tile kernel evaluate
+	//      its spans in closed form (edge_at_row) ----
 	const int rows = visible ? yMax - yMin : 0;
 	bool big = false;
-	uint32_t tileRect = TILE_RECT_NONE; // what k_emit needs to know about this triangle (see tile_rect_count)
-	if(visible)
-	{
-		const int tx0 = pxMin / SWCU_TILE_W, tx1 = (pxMax - 1) / SWCU_TILE_W;
-		const int ty0 = yMin / SWCU_TILE_H, ty1 = (yMax - 1) / SWCU_TILE_H;
-		nTiles = (uint32_t)((tx1 - tx0 + 1) * (ty1 - ty0 + 1));
-		// A polygon with a coordinate outside the screen range (a vertex that projected to INT_MIN because its w was -Inf or NaN,
-		// ...) also goes the big-triangle way: k_big reproduces the reference's wrapping arithmetic for such edges (edge_wrapped),
-		// which keeps that case out of the small-triangle DDA below (whose fast division assumes screen-sized operands).
-		const bool insane = polygon_insane(minXs, maxXs, minYs, maxYs);
-		big = rows > SWCU_SMALL_ROWS || nTiles > SWCU_SMALL_TILES || insane;
-		tileRect = big ? (TILE_RECT_BIG | nTiles) : ((uint32_t)tx0 | ((uint32_t)ty0 << 9) | ((uint32_t)(tx1 - tx0) << 19) | ((uint32_t)(ty1 - ty0) << 22));
-	}
-	const uint32_t count = big ? (uint32_t)(rows * MS) : 0u;
-	unsigned long long base = 0, slot = 0;
-	if(__any_sync(0xFFFFFFFFu, big))
-	{
-		base = warp_alloc(&d.counters->spanCursor, count);
-		slot = warp_alloc(&d.counters->bigSlots, big ? 1u : 0u);
-	}
+	if(visible) big = rows > SWCU_SMALL_ROWS || (pxMax - pxMin) > SWCU_SMALL_COLS || polygon_insane(minXs, maxXs, minYs, maxYs);
+	unsigned long long slot = 0;
+	if(__any_sync(0xFFFFFFFFu, big)) slot = warp_alloc(&d.counters->bigSlots, big ? 1u : 0u);
 	const uint32_t nvis = __popc(__ballot_sync(0xFFFFFFFFu, visible));
 	if((threadIdx.x & 31) == 0 && nvis) atomicAdd(&d.counters->visible, nvis);
 	if(!live) return;
 	unsigned char *rec = d.triRecords + (size_t)tri * d.triStride;
-	if(big && base + count > d.spanCapacity) { atomicOr(&d.counters->overflow, 1u); visible = false; }
 	if(big && slot >= d.bigCapacity) { atomicOr(&d.counters->overflow, 2u); visible = false; }
 	if(!visible)
 	{
-		// empty bounds: never a candidate.  Only the direct mode reads the header of an invisible triangle (every tile CTA walks
-		// the whole list); a binned draw never puts it in a tile list, so the 32-byte sector is not written at all.
-		if(d.direct) *(uint4 *)rec = make_uint4(0, 0, 0, 0);
-		d.tileCount[tri] = TILE_RECT_NONE;
+		// Only the direct mode reads the header of an invisible triangle (every region warp walks the whole list): a small triangle
+		// whose frame lies outside every region.  A binned draw never puts it in a bin, so the 32-byte sector is not written at all.
+		if(d.direct) *(uint4 *)rec = make_uint4(0xFFFFFFFFu, 0, 0, 0);
+		d.triRect[tri] = TRI_RECT_NONE;
 		return;
 	}
-	d.tileCount[tri] = tileRect;
 	// the attributes behind the plane slots (usually the same cache lines as the positions); in flight during the span work
 #pragma unroll
 	for(int a = 0; a < 3; a++)
 #pragma unroll
 		for(int k = 0; k < SWCU_MAXSLOTS; k++) sv[a][k] = k < d.nslots ? vs_operand(d, d.slotSrc[k], idx[a]) : 0.0f;
 
+	uint4 hdr;
 	if(big)
 	{
 		BigTri &b = d.bigList[slot];
-		b.tri = tri; b.spanBase = (uint32_t)base; b.n = n; b.dir = dir;
+		b.tri = tri; b.walk = 0; b.n = n; b.dir = dir;
 		b.yMin = yMin; b.yMax = yMax; b.pxMin = pxMin; b.pxMax = pxMax;
 		if(clipped)
 			for(int i = 0; i < n; i++) { b.X[i] = PX[i]; b.Y[i] = PY[i]; }
@@ -526,13 +512,14 @@ DEVI void setup_triangle(const DrawConst &d)
 			b.X[0] = va.X; b.X[1] = vb.X; b.X[2] = vc.X;
 			b.Y[0] = va.Y; b.Y[1] = vb.Y; b.Y[2] = vc.Y;
 		}
+		d.triRect[tri] = TRI_RECT_BIG | (uint32_t)slot;
+		hdr = make_uint4((uint32_t)pxMin | ((uint32_t)pxMax << 16), (frontFacing ? TRI_FLAG_FRONT : 0u) | TRI_FLAG_BIG, (uint32_t)yMin | ((uint32_t)yMax << 16), (uint32_t)slot);
 	}
 	else
 	{
-		// span rows of the small triangle, built in a shared scratch column and stored inline in its record
+		// span rows of the small triangle, built in a shared scratch column (SetupRoutine::edge writes the left and the right
+		// half of a row from different edges, the last edge that owns a row wins)
 		uint32_t *col = s_rows + threadIdx.x;
-		// every row of the record is written (rows outside the triangle as empty spans): whole 32-byte sectors reach L2, so
-		// evicting them needs no fill from DRAM.
 		// MSAA pre-fill (SetupRoutine.cpp:214-225): left = right = the clamped pixel of the polygon's first vertex — an empty span,
 		// but also what a half keeps when only the other half of a row gets written (degenerate / garbage edges)
 		uint32_t fill = 0;
@@ -558,11 +545,42 @@ DEVI void setup_triangle(const DrawConst &d)
 			else if(msaa) edge_small<4>(d, col, yMin, Xa, Ya, Xb, Yb);
 			else edge_small<1>(d, col, yMin, Xa, Ya, Xb, Yb);
 		}
-		uint32_t *out = (uint32_t *)(rec + d.triStride) - SWCU_SMALL_ROWS * MS;
+		// ---- spans -> coverage masks in the 8 x 8 frame at (pxMin, yMin): pixel x of row y is covered <=> left <= x < right ----
+		auto span_bits = [&](uint32_t v) -> uint32_t {
+			const int a = clampi((int)(v & 0xFFFFu) - pxMin, 0, SWCU_SMALL_COLS), e = clampi((int)(v >> 16) - pxMin, 0, SWCU_SMALL_COLS);
+			return e > a ? ((1u << e) - 1u) & ~((1u << a) - 1u) : 0u;
+		};
+		uint32_t m0 = 0, m1 = 0;
+		if(!msaa)
+		{
 #pragma unroll
-		for(int r = 0; r < SWCU_SMALL_ROWS; r++)
-			if(r < 2 * MS)
-				((uint4 *)out)[r] = make_uint4(col[(4 * r) * SETUP_THREADS], col[(4 * r + 1) * SETUP_THREADS], col[(4 * r + 2) * SETUP_THREADS], col[(4 * r + 3) * SETUP_THREADS]);
+			for(int r = 0; r < SWCU_SMALL_ROWS; r++)
+			{
+				const uint32_t bits = span_bits(col[r * SETUP_THREADS]) << (8 * (r & 3));
+				if(r < 4) m0 |= bits; else m1 |= bits;
+			}
+		}
+		else
+		{
+			uint32_t w[SWCU_SMALL_ROWS];
+#pragma unroll
+			for(int r = 0; r < SWCU_SMALL_ROWS; r++)
+			{
+				w[r] = 0;
+#pragma unroll
+				for(int q = 0; q < 4; q++) w[r] |= span_bits(col[(r * 4 + q) * SETUP_THREADS]) << (8 * q);
+			}
+			((uint4 *)(rec + TRI_HEADER_BYTES))[0] = make_uint4(w[0], w[1], w[2], w[3]);
+			((uint4 *)(rec + TRI_HEADER_BYTES))[1] = make_uint4(w[4], w[5], w[6], w[7]);
+		}
+		hdr = make_uint4((uint32_t)pxMin | ((uint32_t)yMin << 16), frontFacing ? TRI_FLAG_FRONT : 0u, m0, m1);
+		// ---- region bins of the frame: at most 2 x 2 ----
+		const int rx0 = pxMin / SWCU_REGION_W, rx1 = (pxMax - 1) / SWCU_REGION_W;
+		const int ry0 = yMin / SWCU_REGION_H, ry1 = (yMax - 1) / SWCU_REGION_H;
+		d.triRect[tri] = (uint32_t)rx0 | ((uint32_t)ry0 << 9) | ((uint32_t)(rx1 - rx0) << 19) | ((uint32_t)(ry1 - ry0) << 20);
+		if(!d.direct)
+			for(int ry = ry0; ry <= ry1; ry++)
+				for(int rx = rx0; rx <= rx1; rx++) atomicAdd(d.binCount + region_bin(d, rx, ry), 1u);
 	}
 
 	// ---- vertex sort (SetupRoutine.cpp:271-294): only changes float rounding of the planes ----
@@ -601,27 +619,22 @@ DEVI void setup_triangle(const DrawConst &d)
 		M20 = fmul(-y1, A);
 		M21 = fmul(x1, A);
 	}
-	float *f = (float *)(rec + TRI_HEADER_BYTES);
-	float F[TRI_FLOATS_FIXED + 3 * SWCU_MAXSLOTS + 3]; // the plane block, stored with 128-bit writes below
+	float *f = (float *)(rec + d.planeOffset);
+	float F[TRI_FLOATS_FRONT + 3 * SWCU_MAXSLOTS + 4]; // the front block, stored with 128-bit writes below
 #pragma unroll
-	for(int i = 0; i < TRI_FLOATS_FIXED + 3 * SWCU_MAXSLOTS + 3; i++) F[i] = 0.0f;
+	for(int i = 0; i < TRI_FLOATS_FRONT + 3 * SWCU_MAXSLOTS + 4; i++) F[i] = 0.0f;
 	F[0] = x0; F[1] = y0;
-	F[3] = fadd(fadd(M00, M10), M20);
-	F[4] = fadd(fadd(M01, M11), M21);
-	F[5] = fadd(fadd(M02, 0.0f), 0.0f);
-	// The last float of the block is spare for every slot count in use (9 + 3n = 9, 15, 21, 27).  It carries 1/w when the w
-	// plane is constant (wA == wB == 0: MulAdd(x, 0, wC + y * 0) == wC at every pixel, bit for bit), so the tile kernel can
-	// skip the per-fragment division (PixelRoutine.cpp:196-199); 0 = "not constant".
-	float rhwConst = 0.0f;
-	if(F[3] == 0.0f && F[4] == 0.0f && F[5] != 0.0f)
+	F[2] = fadd(fadd(M00, M10), M20);
+	F[3] = fadd(fadd(M01, M11), M21);
+	F[4] = fadd(fadd(M02, 0.0f), 0.0f);
+	// 1/w when the w plane is constant (wA == wB == 0: MulAdd(x, 0, wC + y * 0) == wC at every pixel, bit for bit), so the tile
+	// kernel can skip the per-fragment division (PixelRoutine.cpp:196-199); 0 = "not constant".
+	if(F[2] == 0.0f && F[3] == 0.0f && F[4] != 0.0f)
 	{
-		const float r = fdiv(1.0f, F[5]);
-		if(r != 0.0f && fabsf(r) <= 3.40282347e38f) rhwConst = r;
+		const float r = fdiv(1.0f, F[4]);
+		if(r != 0.0f && fabsf(r) <= 3.40282347e38f) F[5] = r;
 	}
-	const int nf4 = (TRI_FLOATS_FIXED + 3 * d.nslots + 3) >> 2;
-	// 128-bit stores of the block, each issued as soon as its four floats are final (keeps the live range of F short)
-	auto put = [&](int j) { ((float4 *)f)[j] = make_float4(F[4 * j], F[4 * j + 1], F[4 * j + 2], j == nf4 - 1 ? rhwConst : F[4 * j + 3]); };
-	float zBias = 0.0f;
+	const int nf4 = (TRI_FLOATS_FRONT + 3 * d.nslots + 3) >> 2;
 	if(d.depthTestActive)
 	{
 		const float zp0 = sel3(i0, va.zp, vb.zp, vc.zp), zp1 = sel3(i1, va.zp, vb.zp, vc.zp), zp2 = sel3(i2, va.zp, vb.zp, vc.zp);
@@ -632,8 +645,8 @@ DEVI void setup_triangle(const DrawConst &d)
 		const float A = fmul(fsub(fmul(py2, z1), fmul(py1, z2)), D);
 		const float B = fmul(fsub(fmul(px1, z2), fmul(px2, z1)), D);
 		const float C = fadd(fmul(z0, d.depthRange), d.depthNear);
-		F[6] = A; F[7] = B; F[8] = C;
 		const bool applyConst = d.depthBiasConstant != 0.0f, applySlope = d.depthBiasSlope != 0.0f;
+		float zBias = 0.0f;
 		float bias = 0.0f; // SetupRoutine.cpp:417-475, floating-point depth buffer branch
 		if(applyConst)
 		{
@@ -655,16 +668,16 @@ DEVI void setup_triangle(const DrawConst &d)
 			}
 			zBias = bias;
 		}
+		((float4 *)f)[nf4] = make_float4(zBias, A, B, C); // the depth block follows the front block
 	}
-	F[2] = zBias;
+	auto put = [&](int j) { ((float4 *)f)[j] = make_float4(F[4 * j], F[4 * j + 1], F[4 * j + 2], F[4 * j + 3]); };
 	put(0);
-	put(1);
 	// setupGradient, SetupRoutine.cpp:514-548
 #pragma unroll
 	for(int k = 0; k < SWCU_MAXSLOTS; k++)
 	{
 		if(k >= d.nslots) break;
-		float *P = F + TRI_FLOATS_FIXED + 3 * k;
+		float *P = F + TRI_FLOATS_FRONT + 3 * k;
 		const uint32_t mode = d.slotMode[k];
 		if(mode == IM_FLAT)
 		{
@@ -680,20 +693,15 @@ DEVI void setup_triangle(const DrawConst &d)
 			P[1] = fadd(fadd(fmul(a0, M01), fmul(a1, M11)), fmul(a2, M21));
 			P[2] = fadd(fadd(fmul(a0, M02), fmul(a1, 0.0f)), fmul(a2, 0.0f));
 		}
-		// floats up to index 11 + 3k are final: store the float4s this slot completed
+		// floats up to index 8 + 3k are final: store the float4s this slot completed
 #pragma unroll
-		for(int j = 2; j < (TRI_FLOATS_FIXED + 3 * SWCU_MAXSLOTS + 3) / 4; j++)
-			if(4 * j + 3 <= 11 + 3 * k && 4 * j + 3 > 8 + 3 * k) put(j);
+		for(int j = 1; j < (TRI_FLOATS_FRONT + 3 * SWCU_MAXSLOTS + 3) / 4; j++)
+			if(4 * j + 3 <= 8 + 3 * k && 4 * j + 3 > 5 + 3 * k) put(j);
 	}
-	// the float4 that holds the padding (and rhwConst) is still open
+	// the float4 that holds the padding is still open
 #pragma unroll
-	for(int j = 2; j < (TRI_FLOATS_FIXED + 3 * SWCU_MAXSLOTS + 3) / 4; j++)
-		if(j < nf4 && 4 * j + 3 > 8 + 3 * d.nslots) put(j);
-	uint4 hdr;
-	hdr.x = (uint32_t)pxMin | ((uint32_t)pxMax << 16);
-	hdr.y = (uint32_t)yMin | ((uint32_t)yMax << 16);
-	hdr.z = (uint32_t)base;
-	hdr.w = (frontFacing ? 1u : 0u) | (big ? 2u : 0u);
+	for(int j = 1; j < (TRI_FLOATS_FRONT + 3 * SWCU_MAXSLOTS + 3) / 4; j++)
+		if(j < nf4 && 4 * j + 3 > 5 + 3 * d.nslots) put(j);
 	*(uint4 *)rec = hdr;
 }
 
@@ -701,123 +709,240 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_BLOCKS_1X) k_setup_1x(con
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__ DrawConst d) { setup_triangle<0>(d); }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_big: spans (and tile pairs) of the large triangles
+// binning: (region, triangle) pairs without a sort and without a host round trip
+//
+//   k_setup      counts the (at most 2 x 2) region bins of every small triangle           binCount[bin]++
+//   k_bigcount   one warp per big triangle: the regions of its bounding box that an edge does not exclude; a big triangle
+//                whose bounding box does not fit the remaining pair budget is marked `walk` and not binned
+//   k_binscan    exclusive scan of the counts (single pass, decoupled look-back)           binStart[bin]
+//   k_fill       every pair takes a slot of its bin: binStart[bin] + (--binCount[bin]); the counts end at zero again
+//   k_sortbig    bins longer than SWCU_SORT_CAP are put in triangle order here; the tile kernel orders the others itself
+//
+// The slots of a bin are handed out by atomics, i.e. in no particular order; the API order of the triangles (the reference's cluster
+// tickets, Renderer.cpp:573-576) is restored by sorting each bin's few entries by triangle id.  The pair buffer holds 4 pairs per
+// triangle of the draw plus a budget for the big triangles, so no count has to reach the host before the next launch.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_big(const __grid_constant__ DrawConst d, const uint32_t *pairOffset, uint32_t *keys, uint32_t *vals)
+
+// Can a fragment of big triangle b land in region (rx, ry)?  Conservative — the bounding box, minus the regions all of whose pixel
+// centres (widened by the sample offsets) lie strictly outside one edge — and deterministic: k_bigcount and k_fill must agree.
+// sgn: orientation of the polygon, 0 = do not cull geometrically (garbage coordinates the reference walks in wrapped arithmetic).
+DEVI int big_orientation(const BigTri &b)
 {
-	const uint32_t nbig = (uint32_t)min(d.counters->bigSlots, (unsigned long long)d.bigCapacity);
-	for(uint32_t e = blockIdx.x; e < nbig; e += gridDim.x)
+	long long area2 = 0;
+	int loX = b.X[0], hiX = b.X[0], loY = b.Y[0], hiY = b.Y[0];
+	for(int i = 0; i < b.n; i++)
 	{
-		const BigTri &b = d.bigList[e];
-		const int n = b.n, dir = b.dir;
-		const bool msaa = d.ms > 1;
+		const int j = i + 1 == b.n ? 0 : i + 1;
+		area2 += (long long)b.X[i] * b.Y[j] - (long long)b.X[j] * b.Y[i];
+		loX = min(loX, b.X[i]); hiX = max(hiX, b.X[i]); loY = min(loY, b.Y[i]); hiY = max(hiY, b.Y[i]);
+	}
+	return polygon_insane(loX, hiX, loY, hiY) ? 0 : (area2 > 0 ? 1 : (area2 < 0 ? -1 : 0));
+}
+DEVI bool big_touches_region(const DrawConst &d, const BigTri &b, int rx, int ry, int sgn)
+{
+	if(sgn == 0) return true;
+	const int m = d.ms > 1 ? 96 : 0;
+	// pixel centres of the region in 24.8 (centre of pixel x is X = 256x), widened by the sample offsets
+	const long long cx0 = 256ll * max(rx * SWCU_REGION_W, b.pxMin) - m, cx1 = 256ll * (min(rx * SWCU_REGION_W + SWCU_REGION_W, b.pxMax) - 1) + m;
+	const long long cy0 = 256ll * max(ry * SWCU_REGION_H, b.yMin) - m, cy1 = 256ll * (min(ry * SWCU_REGION_H + SWCU_REGION_H, b.yMax) - 1) + m;
+	for(int i = 0; i < b.n; i++)
+	{
+		const int j = i + 1 == b.n ? 0 : i + 1;
+		const long long ex = (long long)b.X[j] - b.X[i], ey = (long long)b.Y[j] - b.Y[i];
+		const long long slack = 4 * (llabs(ex) + llabs(ey)) + 1024; // rounding of re-projected clip vertices
+		// E(P) = ex*(Py - Yi) - ey*(Px - Xi); inside when sgn*E >= 0
+		const long long e00 = sgn * (ex * (cy0 - b.Y[i]) - ey * (cx0 - b.X[i]));
+		const long long e10 = sgn * (ex * (cy0 - b.Y[i]) - ey * (cx1 - b.X[i]));
+		const long long e01 = sgn * (ex * (cy1 - b.Y[i]) - ey * (cx0 - b.X[i]));
+		const long long e11 = sgn * (ex * (cy1 - b.Y[i]) - ey * (cx1 - b.X[i]));
+		if(e00 < -slack && e10 < -slack && e01 < -slack && e11 < -slack) return false;
+	}
+	return true;
+}
+
+// FILL = false: count the regions of every big triangle (k_bigcount); FILL = true: hand out their slots (second part of k_fill)
+template<bool FILL>
+DEVI void big_regions(const DrawConst &d, uint32_t warpIndex, uint32_t warpCount)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t nbig = (uint32_t)min(d.counters->bigSlots, (unsigned long long)d.bigCapacity);
+	for(uint32_t e = warpIndex; e < nbig; e += warpCount)
+	{
+		BigTri &b = d.bigList[e];
+		const int rx0 = b.pxMin / SWCU_REGION_W, rx1 = (b.pxMax - 1) / SWCU_REGION_W;
+		const int ry0 = b.yMin / SWCU_REGION_H, ry1 = (b.yMax - 1) / SWCU_REGION_H;
+		const int w = rx1 - rx0 + 1, total = w * (ry1 - ry0 + 1);
+		uint32_t walk = 0;
+		if(!FILL)
 		{
-			// (row, sample) entries strided over the y-slices of the grid as well: a full-screen triangle gets one row per thread
-			const int total = (b.yMax - b.yMin) * d.ms;
-			for(int r = blockIdx.y * blockDim.x + threadIdx.x; r < total; r += blockDim.x * gridDim.y)
+			// the bounding box must fit what is left of the pair budget; otherwise the triangle is not binned at all
+			if(lane == 0)
 			{
-				const int y = b.yMin + r / d.ms, q = r % d.ms;
-				const int ox = msaa ? c_Xf[q] : 0, oy = msaa ? c_Yf[q] : 0;
-				int L = 0, R = 0;
-				if(msaa) L = R = clampi((int)((uint32_t)b.X[0] + 255u) >> 8, d.scX0, d.scX1); // MSAA pre-fill, SetupRoutine.cpp:214-225
-				for(int i = 0; i < n; i++) // in edge order: the last writer wins, like the reference's span table
-				{
-					const int ia = i + 1 - dir, ib = i + dir;
-					const int a = ia == n ? 0 : ia, bb = ib == n ? 0 : ib;
-					bool right; int x;
-					if(edge_at_row(d, b.X[a] - ox, b.Y[a] - oy, b.X[bb] - ox, b.Y[bb] - oy, y, right, x)) { if(right) R = x; else L = x; }
-				}
-				d.spans[b.spanBase + r] = (uint32_t)L | ((uint32_t)R << 16);
+				const unsigned long long before = atomicAdd(&d.counters->bigReserved, (unsigned long long)total);
+				if(before + (unsigned long long)total > d.bigBudget) { walk = 1; b.walk = 1; atomicOr(&d.counters->overflow, 4u); }
 			}
+			walk = __shfl_sync(0xFFFFFFFFu, walk, 0);
 		}
-		if(keys)
+		else walk = b.walk;
+		if(walk) continue;
+		const int sgn = big_orientation(b);
+		for(int t = lane; t < total; t += 32)
 		{
-			// tiles of the bounding box; a tile all of whose pixel centres lie strictly outside one edge is dropped
-			const int tx0 = b.pxMin / SWCU_TILE_W, tx1 = (b.pxMax - 1) / SWCU_TILE_W;
-			const int ty0 = b.yMin / SWCU_TILE_H, ty1 = (b.yMax - 1) / SWCU_TILE_H;
-			const int tw = tx1 - tx0 + 1, total = tw * (ty1 - ty0 + 1);
-			long long area2 = 0;
-			int loX = b.X[0], hiX = b.X[0], loY = b.Y[0], hiY = b.Y[0];
-			for(int i = 0; i < n; i++)
-			{
-				const int j = i + 1 == n ? 0 : i + 1;
-				area2 += (long long)b.X[i] * b.Y[j] - (long long)b.X[j] * b.Y[i];
-				loX = min(loX, b.X[i]); hiX = max(hiX, b.X[i]); loY = min(loY, b.Y[i]); hiY = max(hiY, b.Y[i]);
-			}
-			// no geometric culling for a polygon whose edges the reference walks in wrapped arithmetic (see k_setup)
-			const long long sgn = polygon_insane(loX, hiX, loY, hiY) ? 0 : (area2 > 0 ? 1 : (area2 < 0 ? -1 : 0));
-			const int m = msaa ? 96 : 0;
-			const uint32_t off = pairOffset[b.tri];
-			for(int t = blockIdx.y * blockDim.x + threadIdx.x; t < total; t += blockDim.x * gridDim.y)
-			{
-				const int tx = tx0 + t % tw, ty = ty0 + t / tw;
-				// pixel centres of the tile in 24.8 (centre of pixel x is X = 256x), widened by the sample offsets
-				const long long cx0 = 256ll * max(tx * SWCU_TILE_W, b.pxMin) - m, cx1 = 256ll * (min(tx * SWCU_TILE_W + SWCU_TILE_W, b.pxMax) - 1) + m;
-				const long long cy0 = 256ll * max(ty * SWCU_TILE_H, b.yMin) - m, cy1 = 256ll * (min(ty * SWCU_TILE_H + SWCU_TILE_H, b.yMax) - 1) + m;
-				bool outside = false;
-				if(sgn != 0)
-					for(int i = 0; i < n && !outside; i++)
-					{
-						const int j = i + 1 == n ? 0 : i + 1;
-						const long long ex = (long long)b.X[j] - b.X[i], ey = (long long)b.Y[j] - b.Y[i];
-						const long long slack = 4 * (llabs(ex) + llabs(ey)) + 1024; // rounding of re-projected clip vertices
-						// E(P) = ex*(Py - Yi) - ey*(Px - Xi); inside when sgn*E >= 0
-						const long long e00 = sgn * (ex * (cy0 - b.Y[i]) - ey * (cx0 - b.X[i]));
-						const long long e10 = sgn * (ex * (cy0 - b.Y[i]) - ey * (cx1 - b.X[i]));
-						const long long e01 = sgn * (ex * (cy1 - b.Y[i]) - ey * (cx0 - b.X[i]));
-						const long long e11 = sgn * (ex * (cy1 - b.Y[i]) - ey * (cx1 - b.X[i]));
-						outside = e00 < -slack && e10 < -slack && e01 < -slack && e11 < -slack;
-					}
-				keys[off + t] = outside ? (uint32_t)(d.tilesX * d.tilesY) : (uint32_t)(ty * d.tilesX + tx); // numTiles = "no tile", sorts last
-				vals[off + t] = b.tri;
-			}
+			const int rx = rx0 + t % w, ry = ry0 + t / w;
+			if(!big_touches_region(d, b, rx, ry, sgn)) continue;
+			const uint32_t bin = region_bin(d, rx, ry);
+			if(!FILL) atomicAdd(d.binCount + bin, 1u);
+			else d.pairs[d.binStart[bin] + (atomicSub(d.binCount + bin, 1u) - 1u)] = b.tri;
 		}
 	}
 }
 
-// (tile, triangle) pairs of the small triangles, from the packed tile rectangle k_setup left for each of them
-__global__ void __launch_bounds__(256) k_emit(const __grid_constant__ DrawConst d, const uint32_t *pairOffset, uint32_t *keys, uint32_t *vals)
+#define BIG_WARPS_PER_BLOCK 8
+__global__ void __launch_bounds__(32 * BIG_WARPS_PER_BLOCK) k_bigcount(const __grid_constant__ DrawConst d)
 {
+	big_regions<false>(d, blockIdx.x * BIG_WARPS_PER_BLOCK + (threadIdx.x >> 5), gridDim.x * BIG_WARPS_PER_BLOCK);
+}
+
+// Exclusive scan of the bin counts in one pass (decoupled look-back: a block publishes its sum, then adds up the sums of its
+// predecessors until it meets one that already knows its prefix).  state[] and the ticket start at zero.
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+__global__ void __launch_bounds__(SCAN_THREADS) k_binscan(const uint32_t *count, uint32_t *start, uint32_t n, volatile uint32_t *state, DrawCounters *c)
+{
+	__shared__ uint32_t s_block, s_warp[SCAN_THREADS / 32], s_prefix;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if(tid == 0) s_block = atomicAdd(&c->scanTicket, 1u); // blocks take their part in the order they start: a predecessor is always running
+	__syncthreads();
+	const uint32_t blk = s_block;
+	const uint32_t base = (blk * SCAN_THREADS + tid) * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS];
+#pragma unroll
+	for(int i = 0; i < SCAN_ITEMS; i++) v[i] = base + i < n ? count[base + i] : 0u;
+	uint32_t sum = 0;
+#pragma unroll
+	for(int i = 0; i < SCAN_ITEMS; i++) sum += v[i];
+	uint32_t incl = sum;
+#pragma unroll
+	for(int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+		if(lane >= o) incl += t;
+	}
+	if(lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	uint32_t warpBase = 0, blockTotal = 0;
+#pragma unroll
+	for(int w = 0; w < SCAN_THREADS / 32; w++)
+	{
+		if(w < warp) warpBase += s_warp[w];
+		blockTotal += s_warp[w];
+	}
+	if(tid == 0)
+	{
+		uint32_t prefix = 0;
+		if(blk == 0) state[0] = 0x80000000u | blockTotal;
+		else
+		{
+			state[blk] = 0x40000000u | blockTotal;
+			__threadfence();
+			for(int j = (int)blk - 1;; j--)
+			{
+				uint32_t sv;
+				do { sv = state[j]; } while((sv & 0xC0000000u) == 0);
+				prefix += sv & 0x3FFFFFFFu;
+				if(sv & 0x80000000u) break;
+			}
+			state[blk] = 0x80000000u | (prefix + blockTotal);
+		}
+		s_prefix = prefix;
+		if((blk + 1) * SCAN_THREADS * SCAN_ITEMS >= n) // the block that holds the last bin
+		{
+			start[n] = prefix + blockTotal;
+			c->pairTotal = prefix + blockTotal;
+		}
+	}
+	__syncthreads();
+	uint32_t run = s_prefix + warpBase + incl - sum;
+#pragma unroll
+	for(int i = 0; i < SCAN_ITEMS; i++)
+	{
+		if(base + i < n) start[base + i] = run;
+		run += v[i];
+	}
+}
+
+// every (region, triangle) pair takes a slot of its bin; blocks [0, smallBlocks) walk the small triangles (one thread each),
+// the blocks after them the big list (one warp per triangle)
+__global__ void __launch_bounds__(256) k_fill(const __grid_constant__ DrawConst d, uint32_t smallBlocks)
+{
+	if(blockIdx.x >= smallBlocks)
+	{
+		big_regions<true>(d, (blockIdx.x - smallBlocks) * BIG_WARPS_PER_BLOCK + (threadIdx.x >> 5), (gridDim.x - smallBlocks) * BIG_WARPS_PER_BLOCK);
+		return;
+	}
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
 	if(tri >= d.primCount) return;
-	const uint32_t r = d.tileCount[tri];
-	if(r & TILE_RECT_BIG) return; // big: k_big emits; invisible: nothing to emit
-	const int tx0 = r & 0x1FF, ty0 = (r >> 9) & 0x3FF, tx1 = tx0 + ((r >> 19) & 7), ty1 = ty0 + ((r >> 22) & 7);
-	uint32_t o = pairOffset[tri];
-	for(int ty = ty0; ty <= ty1; ty++)
-		for(int tx = tx0; tx <= tx1; tx++)
+	const uint32_t r = d.triRect[tri];
+	if(r & TRI_RECT_BIG) return; // big: the blocks behind the small ones; invisible: nothing to do
+	const int rx0 = r & 0x1FF, ry0 = (r >> 9) & 0x3FF, rx1 = rx0 + ((r >> 19) & 1), ry1 = ry0 + ((r >> 20) & 1);
+	for(int ry = ry0; ry <= ry1; ry++)
+		for(int rx = rx0; rx <= rx1; rx++)
 		{
-			keys[o] = (uint32_t)(ty * d.tilesX + tx);
-			vals[o] = tri;
-			o++;
+			const uint32_t bin = region_bin(d, rx, ry);
+			d.pairs[d.binStart[bin] + (atomicSub(d.binCount + bin, 1u) - 1u)] = tri;
 		}
 }
 
-// start/end of every tile's run in the sorted pair array; four keys per thread
-__global__ void k_tile_ranges(const uint32_t *keys, uint32_t n, uint32_t numTiles, uint32_t *tileBegin, uint32_t *tileEnd)
+// Ascending sort of n values with the bitonic network in its "all comparisons point the same way" form (the first step of
+// every merge mirrors the block, the following ones are the usual half-cleaners), so indices >= n simply behave like +infinity and
+// n need not be a power of two.  `sync` separates the steps (warp or CTA barrier), the threads stride over the comparators.
+template<typename Sync>
+DEVI void bitonic_sort_any(uint32_t *a, uint32_t n, uint32_t tid, uint32_t nthreads, Sync sync)
 {
-	const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-	if(i0 >= n) return;
-	uint32_t k[6]; // keys i0 - 1 .. i0 + 4
-	if(i0 + 4 <= n)
+	for(uint32_t k = 2; (k >> 1) < n; k <<= 1)
 	{
-		const uint4 v = *(const uint4 *)(keys + i0);
-		k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+		for(uint32_t j = k >> 1; j > 0; j >>= 1)
+		{
+			const bool mirror = j == (k >> 1);
+			for(uint32_t t = tid; t < (n + 1) / 2 + j; t += nthreads) // comparator t of this step: low index lo, partner hi > lo
+			{
+				const uint32_t lo = ((t / j) * 2 * j) + (t % j);
+				const uint32_t hi = mirror ? (lo ^ (k - 1)) : (lo + j);
+				if(lo < n && hi < n && hi > lo)
+				{
+					const uint32_t x = a[lo], y = a[hi];
+					if(x > y) { a[lo] = y; a[hi] = x; }
+				}
+			}
+			sync();
+		}
 	}
-	else
+}
+
+// bins too long for the tile kernel's own ordering step: one CTA per such bin, in shared memory when it fits
+#define SORTBIG_THREADS 256
+#define SORTBIG_SMEM 8192
+__global__ void __launch_bounds__(SORTBIG_THREADS) k_sortbig(const uint32_t *binStart, uint32_t *pairs, uint32_t numBins)
+{
+	__shared__ uint32_t s_buf[SORTBIG_SMEM];
+	for(uint32_t bin = blockIdx.x; bin < numBins; bin += gridDim.x)
 	{
-#pragma unroll
-		for(int j = 0; j < 4; j++) k[1 + j] = i0 + j < n ? keys[i0 + j] : 0xFFFFFFFFu;
-	}
-	k[0] = i0 > 0 ? keys[i0 - 1] : 0xFFFFFFFFu;
-	k[5] = i0 + 4 < n ? keys[i0 + 4] : 0xFFFFFFFFu;
-#pragma unroll
-	for(int j = 0; j < 4; j++)
-	{
-		const uint32_t i = i0 + j, key = k[1 + j];
-		if(i >= n || key >= numTiles) continue;
-		if(i == 0 || k[j] != key) tileBegin[key] = i;
-		if(i + 1 == n || k[2 + j] != key) tileEnd[key] = i + 1;
+		const uint32_t b0 = binStart[bin], n = binStart[bin + 1] - b0;
+		if(n <= SWCU_SORT_CAP) continue; // (uniform for the CTA)
+		uint32_t *g = pairs + b0;
+		if(n <= SORTBIG_SMEM)
+		{
+			for(uint32_t i = threadIdx.x; i < n; i += SORTBIG_THREADS) s_buf[i] = g[i];
+			__syncthreads();
+			bitonic_sort_any(s_buf, n, threadIdx.x, SORTBIG_THREADS, [] { __syncthreads(); });
+			for(uint32_t i = threadIdx.x; i < n; i += SORTBIG_THREADS) g[i] = s_buf[i];
+			__syncthreads();
+		}
+		else
+		{
+			__syncthreads();
+			bitonic_sort_any(g, n, threadIdx.x, SORTBIG_THREADS, [] { __syncthreads(); });
+		}
 	}
 }
 
@@ -1171,26 +1296,28 @@ DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// k_tile — one CTA per 32x16 screen tile, one warp per 16x8 region of it
+// k_tile — one CTA per 32x16 screen tile = four INDEPENDENT warps, one per 16x8 region (= one triangle bin) of it
 //
-//   * the tile's colour / depth / stencil planes are staged in shared memory by ONE TMA load per attachment
-//     (cp.async.bulk.tensor.3d: x, y, sample plane) that overlaps the first list scan, stay there for the tile's whole
-//     triangle list, and go back with one TMA store per attachment (fallback: cooperative 128-bit copies when the
-//     attachment's pitch / base address do not satisfy the tensor-map alignment rules);
-//   * the four warps are INDEPENDENT inside the list loop (no CTA barriers): each warp scans the tile's list 32 entries
-//     at a time (headers of the next block and list entries of the block after it already in flight), ballots the bounding
-//     boxes against its region and collects a batch of candidates; their plane equations come in with cp.async;
-//   * coverage: one candidate per lane (1x) or lane pair (4x) reads its span rows, clips them to the region's 16 columns and
-//     keeps the non-empty (row, sample) runs in registers; one warp scan places every lane's pairs and first item, the
-//     pair words and one start-mark bit per pair go to shared memory.  Batches of up to 4 (1x) / 1 (4x) candidates — big
-//     triangles — take a one-(candidate, row, sample)-per-lane path instead;
-//   * the covered samples (ITEMS) are consumed 32 at a time, one per lane, so lane utilisation does not depend on triangle
-//     size: the round's mark word maps every lane to its pair.  Items of one sample stay in API order: pairs are in list
-//     order, and when two fragments of a range hit the same sample (tested once per range) the items of a round are
-//     serialised by __match_any_sync rank;
+//   * a warp stages the colour / depth / stencil planes of ITS region in shared memory with one TMA load per attachment
+//     (cp.async.bulk.tensor.3d: x, y, sample plane) behind its own mbarrier, keeps them there for the whole bin and writes them
+//     back with one TMA store per attachment; there is no CTA barrier anywhere, a warp with an empty bin leaves at once
+//     (fallback: lane copies when an attachment does not satisfy the tensor-map alignment rules, or when the scissor rows cut
+//     through the region — a band of a multi-GPU frame must not store rows that belong to another rank);
+//   * the bin's entries come in no particular order (k_fill hands the slots out with atomics): the warp first puts them in
+//     triangle order — the API order of the fragments — in registers (<= 32 entries), in shared memory (<= SWCU_SORT_CAP), or finds
+//     them already sorted by k_sortbig;
+//   * coverage, 32 bin entries at a time, one per lane.  SMALL triangle: the lane clips the coverage masks of the record to
+//     the region (a few logic ops per row) and counts the bits.  BIG triangle: one (row, sample) per lane evaluates the
+//     reference's span in closed form (edge_at_row) from the polygon in the big list;
+//   * a warp scan places every lane's items; the lanes then WRITE their covered samples (`lane | sample | row | x`, 16 bits) into
+//     the warp's item queue in list order — producer-side expansion: no pair lists, no start marks, no search by the consumers;
+//   * the queue is consumed 32 items per round, one covered sample per lane, so lane utilisation does not depend on triangle
+//     size.  Two fragments of one round on the same sample (overlapping triangles) are detected with an owner byte per
+//     sample; only then are the items of the round serialised by __match_any_sync rank (list order);
 //   * specialised on <samples, fragment shader class, blend class, fast state>; everything else is warp-uniform run-time state.
 // ------------------------------------------------------------------------------------------------------------------
 #define TILE_THREADS (SWCU_TILE_WARPS * 32)
+#define REGION_PX (SWCU_REGION_W * SWCU_REGION_H)
 
 template<int SH> struct ShaderSlots { static constexpr int N = SH == SH_CONST ? 0 : SH == SH_VARY ? 4 : SH == SH_TEX ? 2 : 6; };
 
@@ -1217,36 +1344,24 @@ DEVI void tma_store_3d(const CUtensorMap *map, const void *src, int x, int y, in
 DEVI void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 DEVI void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// shared-memory layout of one tile CTA (dynamic shared memory; the host computes the same size)
+// shared-memory layout of one region warp (dynamic shared memory; the host computes the same size)
 template<int MS, int SH>
 struct TileLayout
 {
-	static constexpr int NB = MS == 4 ? 16 : 32;                                   // candidates staged per warp batch
-	static constexpr int NF4 = (TRI_FLOATS_FIXED + 3 * ShaderSlots<SH>::N + 3) / 4; // float4s of plane data per record
-	static constexpr int PLANE_B = SWCU_TILE_W * SWCU_TILE_H * 4 * MS;              // colour or depth tile
-	static constexpr int STENCIL_B = SWCU_TILE_W * SWCU_TILE_H * MS;
-	// A batch is bounded three ways when it is formed: NB candidates, PCAP (candidate, region row, sample) pairs and ICAP
-	// covered samples (both from the bounding boxes, before any span is read), so the per-warp area stays small enough for
-	// 8 CTAs per SM with the 4x MSAA colour + depth tile.
-	static constexpr int PCAP = MS == 4 ? 208 : 256;
-	static constexpr int ICAP = MS == 4 ? 1536 : 2048;
-	// per-warp area
-	static constexpr int W_HDR = 0;                                  // uint4 hdr[NB]: {span rows pointer (lo, hi), yMin | rows << 14 | flags << 28, triangle}
-	static constexpr int W_PLANES = W_HDR + 16 * NB;                 // float4 planes[NB][NF4]
-	static constexpr int W_PAIRS = W_PLANES + 16 * NB * NF4;         // uint32 pairs[PCAP]: start << 18 | cand << 13 | code << 8 | x0 << 4 | (n - 1)
-	static constexpr int W_BITS = W_PAIRS + 4 * PCAP;                // uint32 bits[ICAP / 32]: bit i set <=> a pair starts at item i
-	static constexpr int W_COV = W_BITS + ICAP / 8;                  // uint32 cov[16]: samples of the region covered by the current range (conflict test)
-	static constexpr int W_BYTES = (W_COV + 64 + 15) & ~15;
-	static constexpr int HEAD_B = 128;                               // mbarrier + dirty flag
-	__host__ __device__ static int total(bool depth, bool stencil, int colorEpp = 1)
+	static constexpr int FRONT4 = (TRI_FLOATS_FRONT + 3 * ShaderSlots<SH>::N + 3) / 4; // float4s of the front plane block
+	static constexpr int PLANE_B = REGION_PX * 4 * MS;                                 // one 32-bit-per-sample plane of the region
+	static constexpr int STENCIL_B = REGION_PX * MS;
+	static constexpr int ICAP = MS == 4 ? 512 : 1024;   // items (covered samples) per queue fill; one region holds at most 128 * MS
+	static constexpr int Q_B = 2 * ICAP;                // uint16 queue[ICAP]
+	static constexpr int OWNER_B = REGION_PX * MS;      // uint8 owner[sample of the region]
+	static constexpr int SORT_B = 4 * SWCU_SORT_CAP;    // uint32 sorted[SWCU_SORT_CAP]
+	static constexpr int HEAD_B = 128;                  // the warp's mbarrier
+	__host__ __device__ static int warp_bytes(bool depth, bool stencil, int colorEpp)
 	{
-		return HEAD_B + PLANE_B * colorEpp + (depth ? PLANE_B : 0) + (stencil ? ((STENCIL_B + 127) & ~127) : 0) + SWCU_TILE_WARPS * W_BYTES;
+		return HEAD_B + PLANE_B * colorEpp + (depth ? PLANE_B : 0) + (stencil ? ((STENCIL_B + 127) & ~127) : 0) + Q_B + OWNER_B + SORT_B;
 	}
+	__host__ __device__ static int total(bool depth, bool stencil, int colorEpp = 1) { return SWCU_TILE_WARPS * warp_bytes(depth, stencil, colorEpp); }
 };
-
-DEVI void cp_async16(void *dst, const void *src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory"); }
-DEVI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-DEVI void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // writeColor for the RGBA8 family (PixelRoutine.cpp:1981-1992, :2603-2655): RoundInt(clamp(c, 0, 1) * 255) per channel,
 // packed with saturation.  The float clamp is folded into the integer saturation: values above 1 round to >= 255, negative
@@ -1261,38 +1376,18 @@ DEVI uint32_t pack_unorm8(float b0, float b1, float b2, float b3)
 	return pk;
 }
 
-// cooperative tile <-> framebuffer copy with 128-bit accesses where the layout allows it (TMA-ineligible attachments)
+// region <-> framebuffer copy by the lanes of one warp (TMA-ineligible attachments, regions cut by the scissor rows):
+// rows [y0, y1) of the region only
 template<int MS, typename T, bool STORE>
-DEVI void tile_copy(T *sm, unsigned char *base, int pitchB, int sliceB, int tileX, int tileY, int fbW, int fbH)
+DEVI void region_copy(T *sm, unsigned char *base, int pitchB, int sliceB, int rx, int ry, int fbW, int y0, int y1, int lane)
 {
-	constexpr int ROWB = SWCU_TILE_W * (int)sizeof(T);
-	constexpr int VEC = 16;
-	constexpr int VPR = ROWB / VEC;
-	const bool vecOk = ((size_t)base % VEC == 0) && (pitchB % VEC == 0) && (sliceB % VEC == 0) && ((fbW * (int)sizeof(T)) % VEC == 0);
-	const int x0B = tileX * (int)sizeof(T);
-	if(vecOk)
+	for(int i = lane; i < MS * REGION_PX; i += 32)
 	{
-		for(int i = threadIdx.x; i < MS * SWCU_TILE_H * VPR; i += TILE_THREADS)
-		{
-			const int q = i / (SWCU_TILE_H * VPR), r = (i / VPR) % SWCU_TILE_H, c = i % VPR;
-			const int y = tileY + r, xB = x0B + c * VEC;
-			if(y >= fbH || xB >= fbW * (int)sizeof(T)) continue;
-			uint4 *g = (uint4 *)(base + (size_t)q * sliceB + (size_t)y * pitchB + xB);
-			uint4 *s = (uint4 *)((unsigned char *)(sm + (q * SWCU_TILE_H + r) * SWCU_TILE_W) + c * VEC);
-			if(STORE) *g = *s; else *s = *g;
-		}
-	}
-	else
-	{
-		for(int i = threadIdx.x; i < MS * SWCU_TILE_H * SWCU_TILE_W; i += TILE_THREADS)
-		{
-			const int q = i / (SWCU_TILE_H * SWCU_TILE_W), r = (i / SWCU_TILE_W) % SWCU_TILE_H, c = i % SWCU_TILE_W;
-			const int y = tileY + r, x = tileX + c;
-			if(y >= fbH || x >= fbW) continue;
-			T *g = (T *)(base + (size_t)q * sliceB + (size_t)y * pitchB) + x;
-			T *s = sm + (q * SWCU_TILE_H + r) * SWCU_TILE_W + c;
-			if(STORE) *g = *s; else *s = *g;
-		}
+		const int q = i / REGION_PX, r = (i / SWCU_REGION_W) % SWCU_REGION_H, c = i % SWCU_REGION_W;
+		const int y = ry + r, x = rx + c;
+		if(y < y0 || y >= y1 || x >= fbW) continue;
+		T *g = (T *)(base + (size_t)q * sliceB + (size_t)y * pitchB) + x;
+		if(STORE) *g = sm[i]; else sm[i] = *g;
 	}
 }
 
@@ -1308,647 +1403,576 @@ DEVI float interp_slot(float A, float B, float C, uint32_t mode, float xf, float
 
 struct TileMaps
 {
-	CUtensorMap color, depth, stencil;
+	CUtensorMap color, depth, stencil; // boxes of one region: (16 pixels, 8 rows, all sample planes)
 };
+
+DEVI uint32_t byte_range(int a, int b) { return b > a ? (0xFFFFFFFFu >> (32 - 8 * (b - a))) << (8 * a) : 0u; } // bytes [a, b) of a word, 0 <= a, b <= 4
 
 // FS ("fast state"): the host has checked the common fixed-function state — no stencil, full colour write mask, RGBA byte
 // order, no depth bias, full sample mask, depth test off or LESS / LESS_OR_EQUAL, perspective slots routed one to one —
 // so none of it is decoded per fragment.  FS == false is the same code with every state read at run time.
 template<int MS, int SH, int BL, bool FS>
-__global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __grid_constant__ DrawConst d, const __grid_constant__ TileMaps maps,
-                                                                         const uint32_t *tileBegin, const uint32_t *tileEnd, const uint32_t *triList)
+__global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __grid_constant__ DrawConst d, const __grid_constant__ TileMaps maps)
 {
 	using L = TileLayout<MS, SH>;
-	constexpr int NB = L::NB, NF4 = L::NF4, PCAP = L::PCAP, ICAP = L::ICAP;
-	constexpr int LPC = MS == 4 ? 2 : 1;                 // lanes per candidate in the coverage step
-	constexpr int RPL = SWCU_REGION_H / LPC;              // region rows per lane
-	static_assert(NB * LPC == 32, "one batch fills the warp");
+	constexpr int FRONT4 = L::FRONT4, ICAP = L::ICAP;
 	constexpr bool TEX = SH == SH_TEX || SH == SH_GENERIC;
 	constexpr int UV = SH == SH_TEX ? 0 : 4;
-	constexpr int TP = SWCU_TILE_W * SWCU_TILE_H; // pixels per sample plane of the tile
+	constexpr int BIG_GROUP = MS == 4 ? 1 : 4; // big triangles evaluated together: 8 * MS (row, sample) lanes each
 	extern __shared__ __align__(128) unsigned char smem[];
 
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t laneLt = (1u << lane) - 1u;
 	const int tx = d.tileX0 + blockIdx.x, ty = d.tileY0 + blockIdx.y;
-	const int tileId = ty * d.tilesX + tx;
-	uint32_t begin, end;
-	if(d.direct) { begin = 0; end = d.primCount; }
-	else { begin = tileBegin[tileId]; end = tileEnd[tileId]; }
-	if(begin >= end) return;
+	const uint32_t bin = (uint32_t)(ty * d.tilesX + tx) * 4u + (uint32_t)warp;
+	uint32_t begin = 0, n = d.primCount;
+	if(!d.direct)
+	{
+		begin = d.binStart[bin];
+		n = d.binStart[bin + 1] - begin;
+	}
+	if(n == 0) return;
+	const int rx = tx * SWCU_TILE_W + (warp & 1) * SWCU_REGION_W; // this warp's region
+	const int ry = ty * SWCU_TILE_H + (warp >> 1) * SWCU_REGION_H;
+	const int ryLo = max(ry, d.scY0), ryHi = min(ry + SWCU_REGION_H, d.scY1); // rows of the region inside the scissor
+	if(ryLo >= ryHi || rx >= d.scX1 || rx + SWCU_REGION_W <= d.scX0) return;
 
 	const bool colorOn = FS ? true : (d.colorWriteMask != 0 && d.colorBuf != nullptr);
-	uint64_t *bar = (uint64_t *)smem;
-	int *dirtyFlag = (int *)(smem + 8);
-	uint32_t *smColor = (uint32_t *)(smem + L::HEAD_B);
 	const int colorEpp = FS ? 1 : (int)d.colorEpp; // 32-bit words per colour pixel (floating-point targets: 2 or 4)
-	float *smDepth = (float *)(smem + L::HEAD_B + L::PLANE_B * colorEpp);
-	unsigned char *smStencil = smem + L::HEAD_B + L::PLANE_B * colorEpp + (d.depthTestActive ? L::PLANE_B : 0);
-	unsigned char *warpBase = smStencil + (d.stencilActive ? ((L::STENCIL_B + 127) & ~127) : 0);
+	unsigned char *wa = smem + warp * L::warp_bytes(d.depthTestActive != 0, d.stencilActive != 0, colorEpp);
+	uint64_t *bar = (uint64_t *)wa;
+	uint32_t *smColor = (uint32_t *)(wa + L::HEAD_B);
+	float *smDepth = (float *)(wa + L::HEAD_B + L::PLANE_B * colorEpp);
+	unsigned char *smStencil = wa + L::HEAD_B + L::PLANE_B * colorEpp + (d.depthTestActive ? L::PLANE_B : 0);
+	unsigned short *wQueue = (unsigned short *)(smStencil + (d.stencilActive ? ((L::STENCIL_B + 127) & ~127) : 0));
+	unsigned char *wOwner = (unsigned char *)wQueue + L::Q_B;
+	uint32_t *wSort = (uint32_t *)(wOwner + L::OWNER_B);
 
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t laneLt = (1u << lane) - 1u, laneLe = (2u << lane) - 1u;
-	const int tileX = tx * SWCU_TILE_W, tileY = ty * SWCU_TILE_H;
-	const int rx = tileX + (warp % (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_W; // this warp's region
-	const int ry = tileY + (warp / (SWCU_TILE_W / SWCU_REGION_W)) * SWCU_REGION_H;
-	const int regionPi = (ry - tileY) * SWCU_TILE_W + (rx - tileX); // index of the region's first pixel inside a staged plane
-
-	unsigned char *wa = warpBase + warp * L::W_BYTES;
-	uint4 *wHdr = (uint4 *)(wa + L::W_HDR);
-	float4 *wPlanes = (float4 *)(wa + L::W_PLANES);
-	uint32_t *wPairs = (uint32_t *)(wa + L::W_PAIRS);
-	uint32_t *wBits = (uint32_t *)(wa + L::W_BITS);
-	uint32_t *wCov = (uint32_t *)(wa + L::W_COV);
-
-	// ---- stage the tile: TMA when the attachments allow it ----
-	if(threadIdx.x == 0)
+	// ---- stage the region: TMA when the attachments allow it ----
+	bool tileReady = true;
+	if(d.useTma)
 	{
-		*dirtyFlag = 0;
-		if(d.useTma)
+		if(lane == 0)
 		{
 			mbar_init(bar, 1);
 			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		}
-	}
-	__syncthreads();
-	if(d.useTma)
-	{
-		if(threadIdx.x == 0)
-		{
 			const uint32_t bytes = (colorOn ? L::PLANE_B * colorEpp : 0) + (d.depthTestActive ? (d.depth16 ? L::PLANE_B / 2 : L::PLANE_B) : 0) + (d.stencilActive ? L::STENCIL_B : 0);
 			mbar_expect_tx(bar, bytes);
-			if(colorOn) tma_load_3d(smColor, &maps.color, bar, tileX * colorEpp, tileY, 0); // the map counts 32-bit words along x
-			if(d.depthTestActive) tma_load_3d(smDepth, &maps.depth, bar, tileX, tileY, 0);
-			if(d.stencilActive) tma_load_3d(smStencil, &maps.stencil, bar, tileX, tileY, 0);
+			if(colorOn) tma_load_3d(smColor, &maps.color, bar, rx * colorEpp, ry, 0); // the map counts 32-bit words along x
+			if(d.depthTestActive) tma_load_3d(smDepth, &maps.depth, bar, rx, ry, 0);
+			if(d.stencilActive) tma_load_3d(smStencil, &maps.stencil, bar, rx, ry, 0);
 		}
+		__syncwarp();
+		tileReady = false;
 	}
 	else
 	{
-		if(colorOn && colorEpp == 4) tile_copy<MS, uint4, false>((uint4 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		else if(colorOn && colorEpp == 2) tile_copy<MS, uint2, false>((uint2 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		else if(colorOn) tile_copy<MS, uint32_t, false>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		if(d.depthTestActive && d.depth16) tile_copy<MS, unsigned short, false>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		else if(d.depthTestActive) tile_copy<MS, float, false>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		if(d.stencilActive) tile_copy<MS, unsigned char, false>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		__syncthreads();
+		const int yEnd = min(ry + SWCU_REGION_H, d.fbHeight);
+		if(colorOn && colorEpp == 4) region_copy<MS, uint4, false>((uint4 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+		else if(colorOn && colorEpp == 2) region_copy<MS, uint2, false>((uint2 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+		else if(colorOn) region_copy<MS, uint32_t, false>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+		if(d.depthTestActive && d.depth16) region_copy<MS, unsigned short, false>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+		else if(d.depthTestActive) region_copy<MS, float, false>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+		if(d.stencilActive) region_copy<MS, unsigned char, false>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+		__syncwarp();
 	}
-	bool tileReady = !d.useTma;
 
 	bool dirty = false;
 	const bool biasOn = FS ? false : d.depthBiasEnable != 0;
 	const bool bgr = FS ? false : d.bgr != 0;
 	uint32_t wmask32 = FS ? 0xFFFFFFFFu : 0u; // byte lanes of the packed pixel the draw may write
+	uint32_t sampleBytes = 0xFFFFFFFFu;       // 4x: byte q of a mask word = sample q enabled
 	if(!FS)
 	{
 #pragma unroll
 		for(int ch = 0; ch < 4; ch++)
 			if((d.colorWriteMask >> ch) & 1) wmask32 |= 0xFFu << (8 * ((bgr && ch < 3) ? 2 - ch : ch));
+		if(MS == 4)
+		{
+			sampleBytes = 0;
+#pragma unroll
+			for(int q = 0; q < 4; q++)
+				if((d.sampleMask >> q) & 1) sampleBytes |= 0xFFu << (8 * q);
+		}
 	}
 
-	// ---- list scan with look-ahead: while block b of 32 list entries is used, the record headers of block b + 1 and the list
-	//      entries of block b + 2 are in flight (the header address depends on the list entry) ----
-	uint32_t triN = 0, triNN = 0;
-	uint4 hN = make_uint4(0, 0, 0, 0);
+	// ---- the bin in triangle order ----
+	const uint32_t *list = d.pairs + begin;
+	uint32_t regId = 0xFFFFFFFFu;
+	bool sortedInSmem = false;
+	if(!d.direct)
 	{
-		const uint32_t li = begin + lane;
-		if(li < end)
+		if(n <= 32)
 		{
-			triN = d.direct ? li : __ldg(triList + li);
-			hN = __ldg((const uint4 *)(d.triRecords + (size_t)triN * d.triStride));
-		}
-		if(li + 32 < end) triNN = d.direct ? li + 32 : __ldg(triList + li + 32);
-	}
-	int ns = 0;             // candidates staged so far for the next batch
-	uint32_t pend = 0;      // lanes whose scanned hit is not staged yet
-	uint32_t tri = 0, hy = 0;
-	const unsigned char *hrows = nullptr;
-	for(uint32_t pos = begin;;)
-	{
-		if(!pend && pos < end)
-		{
-			// ---- which of these 32 list entries touch my region? ----
-			bool hit = false;
-			if(pos + lane < end)
-			{
-				const int pxMin = hN.x & 0xFFFF, pxMax = hN.x >> 16, yMin = hN.y & 0xFFFF, yMax = hN.y >> 16;
-				hit = pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ry + SWCU_REGION_H && yMax > ry;
-				if(hit)
+			if((uint32_t)lane < n) regId = __ldg(list + lane);
+#pragma unroll
+			for(int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+				for(int j = k >> 1; j > 0; j >>= 1)
 				{
-					tri = triN;
-					hy = (uint32_t)yMin | ((uint32_t)(yMax - yMin) << 14) | ((hN.w & 3u) << 28);
-					// span rows of the triangle, rebased so that entry (y * MS + q) is row y: the span table for big triangles,
-					// the rows inlined in the record otherwise
-					hrows = (hN.w & 2u) ? (const unsigned char *)(d.spans + hN.z) : d.triRecords + (size_t)triN * d.triStride + TRI_HEADER_BYTES + 16 * NF4;
-					hrows -= (size_t)yMin * (MS * 4);
+					const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, regId, j);
+					const bool keepMin = ((lane & j) == 0) == ((lane & k) == 0);
+					regId = keepMin ? min(regId, o) : max(regId, o);
 				}
-			}
-			pend = __ballot_sync(0xFFFFFFFFu, hit);
-			pos += 32;
-			const uint32_t li = pos + lane;
-			if(li < end)
-			{
-				triN = triNN;
-				hN = __ldg((const uint4 *)(d.triRecords + (size_t)triN * d.triStride));
-			}
-			if(li + 32 < end) triNN = d.direct ? li + 32 : __ldg(triList + li + 32);
 		}
-		if(pend)
+		else if(n <= SWCU_SORT_CAP)
 		{
-			// ---- hits go to the free slots of the batch, in list order; the rest wait for the next batch ----
-			const int rank = __popc(pend & laneLt);
-			const int take = min(__popc(pend), NB - ns);
-			const bool mine = ((pend >> lane) & 1) && rank < take;
-			if(mine) wHdr[ns + rank] = make_uint4((uint32_t)(uintptr_t)hrows, (uint32_t)((uintptr_t)hrows >> 32), hy, tri);
-			pend &= ~__ballot_sync(0xFFFFFFFFu, mine);
-			ns += take;
-		}
-		const bool listDone = pend == 0 && pos >= end;
-		if(ns < NB && !listDone) continue;
-		if(ns == 0) break;
-		{
-			const int nb = ns;
-			ns = 0;
+			for(uint32_t i = lane; i < n; i += 32) wSort[i] = __ldg(list + i);
 			__syncwarp();
-			// ---- plane equations of the batch -> shared memory, asynchronously (needed only when the items are consumed) ----
-			for(int i = lane; i < nb * NF4; i += 32)
-			{
-				const int s = i / NF4, j = i - s * NF4;
-				cp_async16(wPlanes + i, d.triRecords + (size_t)wHdr[s].w * d.triStride + TRI_HEADER_BYTES + 16 * j);
-			}
-			cp_async_commit();
+			bitonic_sort_any(wSort, n, (uint32_t)lane, 32u, [] { __syncwarp(); });
+			sortedInSmem = true;
+		}
+	}
 
-			// ---- coverage (QuadRasterizer.cpp:181-206), one candidate per lane (MS == 1) or per lane pair (MS == 4: rows 0-3 and
-			//      4-7 of the region): the lane reads its rows' spans, clips [left, right) to the region's 16 columns — a run of
-			//      n pixels from x0 — and keeps the non-empty (row, sample) pairs packed in registers.  A warp scan over the lanes
-			//      then places the pairs and their first items, so the lanes write the pair words (and the start marks) directly;
-			//      no per-candidate warp iteration, no second pass over the pairs.  A range [c0, c1) of the batch whose pairs
-			//      and items fit the shared-memory areas is taken at a time (normally the whole batch) ----
-			for(int c0 = 0; c0 < nb;)
+	for(uint32_t pos0 = 0; pos0 < n; pos0 += 32)
+	{
+		// ---- 32 bin entries, one per lane ----
+		const uint32_t li = pos0 + lane;
+		bool valid = li < n;
+		uint32_t id = 0;
+		if(valid) id = d.direct ? li : (n <= 32 ? regId : (sortedInSmem ? wSort[li] : __ldg(list + li)));
+		const unsigned char *rec = d.triRecords + (size_t)id * d.triStride;
+		uint4 h = make_uint4(0, 0, 0, 0);
+		if(valid) h = __ldg((const uint4 *)rec);
+		bool isBig = valid && (h.y & TRI_FLAG_BIG);
+		if(valid)
+		{
+			// does the entry touch my region at all?  (always asked in direct mode; bins are conservative too)
+			if(isBig)
 			{
-			int c1;
-			uint32_t total;
-			bool conflicts = false; // does any sample of the region receive two fragments in this range?
-			if(nb * SWCU_REGION_H * MS <= 32)
-			{
-				// ---- a batch of one (4x) or up to four (1x) candidates — big triangles, direct mode: one (candidate, row, sample)
-				//      per lane, pairs compacted with a ballot, first items from one warp scan ----
-				const int cand = lane / (SWCU_REGION_H * MS), row = (lane / MS) % SWCU_REGION_H, q = lane % MS;
-				uint32_t v = 0;
-				if(cand < nb && (MS == 1 || FS || ((d.sampleMask >> q) & 1)))
-				{
-					const uint4 hh = wHdr[cand];
-					const uint32_t y = (uint32_t)(ry + row);
-					if(y - (hh.z & 0x3FFFu) < ((hh.z >> 14) & 0x3FFFu))
-						v = __ldg((const uint32_t *)(((uintptr_t)hh.y << 32) | hh.x) + y * MS + q);
-				}
-#pragma unroll
-				for(int i = 0; i < (ICAP / 32 + 31) / 32; i++)
-					if(lane + 32 * i < ICAP / 32) wBits[lane + 32 * i] = 0;
-				const int a = clampi((int)(v & 0xFFFF) - rx, 0, 16), e = clampi((int)(v >> 16) - rx, 0, 16);
-				const int n = e - a;
-				const bool has = n > 0;
-				const uint32_t nz = __ballot_sync(0xFFFFFFFFu, has);
-				uint32_t incl = has ? (uint32_t)n : 0u;
-#pragma unroll
-				for(int o = 1; o < 32; o <<= 1)
-				{
-					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-					if(lane >= o) incl += t;
-				}
-				total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-				c1 = nb;
-				if(MS == 1 && nb > 1)
-				{
-					// the other candidates' runs on my row sit 8, 16 and 24 lanes away
-					const uint32_t mask = has ? ((1u << n) - 1u) << a : 0u;
-					const uint32_t others = __shfl_xor_sync(0xFFFFFFFFu, mask, 8) | __shfl_xor_sync(0xFFFFFFFFu, mask, 16) | __shfl_xor_sync(0xFFFFFFFFu, mask, 24);
-					conflicts = __any_sync(0xFFFFFFFFu, (mask & others) != 0);
-				}
-				__syncwarp(); // start marks zeroed
-				if(has)
-				{
-					const uint32_t start = incl - (uint32_t)n;
-					wPairs[__popc(nz & laneLt)] = (start << 18) | ((uint32_t)cand << 13) | ((uint32_t)(row * MS + q) << 8) | ((uint32_t)a << 4) | (uint32_t)(n - 1);
-					atomicOr(wBits + (start >> 5), 1u << (start & 31));
-				}
-				__syncwarp();
+				const int pxMin = h.x & 0xFFFF, pxMax = h.x >> 16, yMin = h.z & 0xFFFF, yMax = h.z >> 16;
+				if(!(pxMin < rx + SWCU_REGION_W && pxMax > rx && yMin < ryHi && yMax > ryLo)) { valid = false; isBig = false; }
 			}
 			else
 			{
-				const int cand = c0 + lane / LPC;
-				const int rowBase = (lane % LPC) * RPL; // first region row of this lane
-				const bool active = cand < nb;
-				uint4 hh = make_uint4(0, 0, 0, 0);
-				if(active) hh = wHdr[cand];
-				const unsigned char *rowsPtr = (const unsigned char *)(((uintptr_t)hh.y << 32) | hh.x);
-				const uint32_t yMin = hh.z & 0x3FFFu, nrows = (hh.z >> 14) & 0x3FFFu;
-				uint32_t sp[RPL][MS];
-#pragma unroll
-				for(int r = 0; r < RPL; r++)
+				const int fx = h.x & 0xFFFF, fy = h.x >> 16;
+				if(!(fx < rx + SWCU_REGION_W && fx + SWCU_SMALL_COLS > rx && fy < ryHi && fy + SWCU_SMALL_ROWS > ryLo)) valid = false;
+			}
+		}
+		const uint32_t bigMask = __ballot_sync(0xFFFFFFFFu, isBig);
+		const int cnt = (int)min(32u, n - pos0);
+		int p = 0;
+		while(p < cnt)
+		{
+			uint32_t total = 0;
+			const uint32_t rest = bigMask >> p;
+			if(rest & 1u)
+			{
+				// ---- BIG: up to BIG_GROUP consecutive big entries; lane -> (entry, row, sample); the span of the row in closed form
+				//      (SetupRoutine::edge as edge_at_row: the last edge that owns the row wins; 4x: pre-filled, SetupRoutine.cpp:214-225) ----
+				int group = 1;
+				if(BIG_GROUP > 1) group = min(BIG_GROUP, rest == 0xFFFFFFFFu ? 32 : (int)__ffs(~rest) - 1);
+				const int c = lane / (SWCU_REGION_H * MS), row = (lane / MS) % SWCU_REGION_H, q = lane % MS;
+				const int src = min(p + c, 31);
+				const uint32_t bslot = __shfl_sync(0xFFFFFFFFu, h.w, src);
+				int a = 0, e = 0;
+				const int y = ry + row;
+				if(c < group && y >= ryLo && y < ryHi && (MS == 1 || FS || ((d.sampleMask >> q) & 1)))
 				{
-					const uint32_t y = (uint32_t)(ry + rowBase + r);
-					const bool in = active && (y - yMin) < nrows;
-					if(MS == 4)
+					const BigTri &b = d.bigList[bslot];
+					if(y >= b.yMin && y < b.yMax)
 					{
-						uint4 v = make_uint4(0, 0, 0, 0); // empty spans outside the triangle's rows
-						if(in) v = __ldg((const uint4 *)(rowsPtr + (size_t)y * 16));
-						sp[r][0] = v.x; sp[r][MS > 1 ? 1 : 0] = v.y; sp[r][MS > 1 ? 2 : 0] = v.z; sp[r][MS > 1 ? 3 : 0] = v.w;
+						const int ox = MS > 1 ? c_Xf[q] : 0, oy = MS > 1 ? c_Yf[q] : 0;
+						int Ls = 0, Rs = 0;
+						if(MS > 1) Ls = Rs = clampi((int)((uint32_t)b.X[0] + 255u) >> 8, d.scX0, d.scX1);
+						const int bn = b.n, bdir = b.dir;
+						for(int i = 0; i < bn; i++)
+						{
+							const int ia = i + 1 - bdir, ib = i + bdir;
+							const int va = ia == bn ? 0 : ia, vb = ib == bn ? 0 : ib;
+							bool right; int x;
+							if(edge_at_row(d, b.X[va] - ox, b.Y[va] - oy, b.X[vb] - ox, b.Y[vb] - oy, y, right, x)) { if(right) Rs = x; else Ls = x; }
+						}
+						a = clampi(Ls - rx, 0, SWCU_REGION_W); e = clampi(Rs - rx, 0, SWCU_REGION_W);
 					}
-					else
-					{
-						sp[r][0] = 0;
-						if(in) sp[r][0] = __ldg((const uint32_t *)(rowsPtr + (size_t)y * 4));
-					}
 				}
-				// zero the start marks while the loads fly (the previous rounds ended with a __syncwarp)
-#pragma unroll
-				for(int i = 0; i < (ICAP / 32 + 31) / 32; i++)
-					if(lane + 32 * i < ICAP / 32) wBits[lane + 32 * i] = 0;
-				if(MS == 4 && lane < 16) wCov[lane] = 0;
-				uint32_t runs[RPL * MS / 4]; // per pair: x0 << 4 | (n - 1), four pairs per register
-				uint32_t valid = 0, items = 0;
-				uint32_t cw[MS == 1 ? RPL / 2 : 1]; // MS == 1: my candidate's coverage of the region, two rows per word
-				if(MS == 1)
-				{
-#pragma unroll
-					for(int i = 0; i < RPL / 2; i++) cw[i] = 0;
-				}
-#pragma unroll
-				for(int j = 0; j < RPL * MS; j++)
-				{
-					const int r = j / MS, q = j % MS;
-					uint32_t v = sp[r][q];
-					if(MS == 4 && !FS && !((d.sampleMask >> q) & 1)) v = 0;
-					const int a = clampi((int)(v & 0xFFFF) - rx, 0, 16), e = clampi((int)(v >> 16) - rx, 0, 16);
-					const int n = e - a;
-					const bool has = n > 0;
-					const uint32_t run = has ? (((uint32_t)a << 4) | (uint32_t)(n - 1)) : 0u;
-					if(j % 4 == 0) runs[j / 4] = run; else runs[j / 4] |= run << (8 * (j % 4));
-					if(has) { valid |= 1u << j; items += (uint32_t)n; }
-					if(MS == 1) cw[j / 2 < RPL / 2 ? j / 2 : 0] |= (has ? ((1u << n) - 1u) << a : 0u) << (16 * (j & 1));
-				}
-				// ---- where do my pairs and items start?  (inclusive scan of pairs << 16 | items over the lanes) ----
-				const uint32_t mineU = ((uint32_t)__popc(valid) << 16) | items;
-				uint32_t incl = mineU;
+				const int nn = e > a ? e - a : 0;
+				uint32_t incl = (uint32_t)nn;
 #pragma unroll
 				for(int o = 1; o < 32; o <<= 1)
 				{
 					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
 					if(lane >= o) incl += t;
 				}
-				// a candidate is taken whole: the sums at its last lane must fit
-				const uint32_t inclC = LPC == 1 ? incl : __shfl_sync(0xFFFFFFFFu, incl, lane | (LPC - 1));
-				const bool fits = active && (inclC >> 16) <= (uint32_t)PCAP && (inclC & 0xFFFFu) <= (uint32_t)ICAP;
-				const uint32_t fitMask = __ballot_sync(0xFFFFFFFFu, fits); // a prefix of the lanes, never empty (one candidate always fits)
-				const int lastLane = 31 - __clz(fitMask);
-				const uint32_t sums = __shfl_sync(0xFFFFFFFFu, incl, lastLane);
-				total = sums & 0xFFFFu;
-				c1 = c0 + (lastLane + 1) / LPC;
-				__syncwarp(); // start marks zeroed
-				if(fits)
+				total = __shfl_sync(0xFFFFFFFFu, incl, 31); // <= 32 runs of <= 16 pixels = ICAP at most
+				uint32_t w = incl - (uint32_t)nn;
+				const uint32_t item = ((uint32_t)(p + c) << 9) | ((uint32_t)q << 7) | ((uint32_t)row << 4);
+				for(int i = 0; i < nn; i++) wQueue[w++] = (unsigned short)(item | (uint32_t)(a + i));
+				p += group;
+			}
+			else
+			{
+				// ---- SMALL: lanes [p, hi) clip the coverage masks of their records to the region and count the bits ----
+				const int hi = rest ? p + (int)__ffs(rest) - 1 : cnt;
+				const bool mine = valid && lane >= p && lane < hi;
+				const int fx = h.x & 0xFFFF, fy = h.x >> 16;
+				uint32_t m[MS == 4 ? 8 : 2];
+				uint32_t count = 0;
+				if(mine)
 				{
-					uint32_t pairIdx = (incl - mineU) >> 16, start = (incl - mineU) & 0xFFFFu;
-					const uint32_t word0 = ((uint32_t)cand << 13) | (MS == 4 ? (uint32_t)rowBase << 10 : 0u);
-#pragma unroll
-					for(int j = 0; j < RPL * MS; j++)
+					const int rlo = clampi(ryLo - fy, 0, SWCU_SMALL_ROWS), rhi = clampi(ryHi - fy, 0, SWCU_SMALL_ROWS);
+					const int clo = clampi(rx - fx, 0, SWCU_SMALL_COLS), chi = clampi(rx + SWCU_REGION_W - fx, 0, SWCU_SMALL_COLS);
+					const uint32_t cm4 = (chi > clo ? (((1u << chi) - 1u) & ~((1u << clo) - 1u)) : 0u) * 0x01010101u;
+					if(MS == 4)
 					{
-						if((valid >> j) & 1)
+						const uint4 wa4 = __ldg((const uint4 *)(rec + TRI_HEADER_BYTES)), wb4 = __ldg((const uint4 *)(rec + TRI_HEADER_BYTES + 16));
+						m[0] = wa4.x; m[1] = wa4.y; m[MS == 4 ? 2 : 0] = wa4.z; m[MS == 4 ? 3 : 0] = wa4.w;
+						m[MS == 4 ? 4 : 0] = wb4.x; m[MS == 4 ? 5 : 0] = wb4.y; m[MS == 4 ? 6 : 0] = wb4.z; m[MS == 4 ? 7 : 0] = wb4.w;
+						const uint32_t keep = cm4 & sampleBytes;
+#pragma unroll
+						for(int r = 0; r < (MS == 4 ? 8 : 0); r++)
 						{
-							const uint32_t run = (runs[j / 4] >> (8 * (j % 4))) & 0xFFu;
-							// code (bits 8-12) = region row << 2 | sample for MS == 4 (j = r * 4 + q, the lane's first row comes in
-							// through word0), region row for MS == 1 (j = r)
-							wPairs[pairIdx] = (start << 18) | (word0 + ((uint32_t)j << 8)) | run;
-							atomicOr(wBits + (start >> 5), 1u << (start & 31));
-							pairIdx++;
-							start += (run & 15u) + 1u;
+							m[r] = (r >= rlo && r < rhi) ? (m[r] & keep) : 0u;
+							count += __popc(m[r]);
 						}
-					}
-				}
-				__syncwarp();
-				// ---- two fragments on one sample?  Every pair ORs its run into a bitmap of the region's samples; a bit that was
-				//      already set means an earlier (or later) pair covers the sample too.  One candidate alone cannot overlap itself ----
-				if(c1 - c0 > 1)
-				{
-					if(MS == 1)
-					{
-						// one candidate per lane, all lanes see the same eight rows: the samples covered by the range are the OR of the
-						// lanes' words; fewer of them than items means some sample is covered twice
-						uint32_t covered = 0;
-#pragma unroll
-						for(int i = 0; i < RPL / 2; i++) covered += __popc(__reduce_or_sync(0xFFFFFFFFu, fits ? cw[i] : 0u));
-						conflicts = covered != total;
 					}
 					else
 					{
-						const uint32_t P = sums >> 16;
-						uint32_t ov = 0;
-#pragma unroll 2
-						for(uint32_t p = lane; p < P; p += 32)
-						{
-							const uint32_t w = wPairs[p];
-							const uint32_t code = (w >> 8) & 31u;
-							const uint32_t m = ((2u << (w & 15u)) - 1u) << (((w >> 4) & 15u) + 16u * (code & 1u));
-							ov |= atomicOr(wCov + (code >> 1), m) & m;
-						}
-						conflicts = __any_sync(0xFFFFFFFFu, ov != 0);
+						m[0] = h.z & cm4 & byte_range(min(rlo, 4), min(rhi, 4));
+						m[1] = h.w & cm4 & byte_range(max(rlo - 4, 0), max(rhi - 4, 0));
+						count = __popc(m[0]) + __popc(m[1]);
 					}
 				}
+				uint32_t incl = count;
+#pragma unroll
+				for(int o = 1; o < 32; o <<= 1)
+				{
+					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+					if(lane >= o) incl += t;
+				}
+				// the lanes whose items still fit the queue: a prefix of [p, hi) (one small triangle always fits)
+				const uint32_t fitMask = __ballot_sync(0xFFFFFFFFu, lane >= p && lane < hi && incl <= (uint32_t)ICAP);
+				const int fitEnd = p + __popc(fitMask);
+				total = __shfl_sync(0xFFFFFFFFu, incl, fitEnd - 1);
+				if(mine && lane < fitEnd && count)
+				{
+					// producer-side expansion: item = lane << 9 | sample << 7 | region row << 4 | region column
+					uint32_t w = incl - count;
+					const uint32_t item0 = (uint32_t)((lane << 9) + (fy - ry) * 16 + (fx - rx));
+					if(MS == 4)
+					{
+#pragma unroll
+						for(int r = 0; r < (MS == 4 ? 8 : 0); r++)
+						{
+							uint32_t bits = m[r];
+							while(bits)
+							{
+								const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+								bits &= bits - 1u;
+								wQueue[w++] = (unsigned short)(item0 + 16u * r + ((b & 0x18u) << 4) + (b & 7u));
+							}
+						}
+					}
+					else
+					{
+#pragma unroll
+						for(int j = 0; j < 2; j++)
+						{
+							uint32_t bits = m[j];
+							while(bits)
+							{
+								const uint32_t b = (uint32_t)__ffs(bits) - 1u;
+								bits &= bits - 1u;
+								wQueue[w++] = (unsigned short)(item0 + 64u * j + ((b & 0x38u) << 1) + (b & 7u));
+							}
+						}
+					}
+				}
+				p = fitEnd;
 			}
-			cp_async_wait_all();
 			__syncwarp();
 			if(total && !tileReady)
 			{
-				while(!mbar_try_wait(bar, 0)) {} // the TMA loads of the tile have landed
+				while(!mbar_try_wait(bar, 0)) {} // the TMA loads of the region have landed
 				tileReady = true;
 			}
-			// ---- consume the items 32 at a time, one per lane ----
+			// ---- consume the items 32 at a time, one covered sample per lane ----
+			for(uint32_t base = 0; base < total; base += 32)
 			{
-				int cursor = 0; // pairs that start before this round
-				for(uint32_t base = 0; base < total; base += 32)
+				const uint32_t g = base + lane;
+				const bool live = g < total;
+				const uint32_t e = live ? (uint32_t)wQueue[g] : 0u;
+				const int k = (int)(e >> 9);
+				const uint32_t idk = __shfl_sync(0xFFFFFFFFu, id, k);
+				const uint32_t flagsk = FS ? 0u : __shfl_sync(0xFFFFFFFFu, h.y, k);
+				const uint32_t skey = e & 0x1FFu; // sample of the region: q << 7 | row << 4 | column
+				// two fragments of this round on one sample?  Every lane signs its sample; a lane that reads back another signature has company
+				if(live) wOwner[skey] = (unsigned char)lane;
+				__syncwarp();
+				const bool shared = live && wOwner[skey] != (unsigned char)lane;
+				int prank = 0, maxRank = 0;
+				if(__any_sync(0xFFFFFFFFu, shared)) // overlapping triangles: same-sample items of a round run in list order
 				{
-					const uint32_t g = base + lane;
-					const bool valid = g < total;
-					const uint32_t starts = wBits[base >> 5];
-					const int myPair = cursor + __popc(starts & laneLe) - 1; // the last pair that starts at or before my item
-					cursor += __popc(starts);
-					const uint32_t e = wPairs[myPair];
-					const int bit = (int)((e >> 4) & 15u) + (int)(g - (e >> 18));
-					const uint32_t code = (e >> 8) & 31u;
-					// items of the same (pixel, sample) in this round run in queue order
-					const uint32_t key = valid ? ((code << 4) | (uint32_t)bit) : (0x200u | lane); // one key per sample of the region
-					int prank = 0, maxRank = 0;
-					if(conflicts) // overlapping triangles in this range: same-sample items of a round run in list order
+					const uint32_t peers = __match_any_sync(0xFFFFFFFFu, live ? skey : (0x200u | (uint32_t)lane));
+					prank = __popc(peers & laneLt);
+					maxRank = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(live ? prank : 0));
+				}
+				for(int rr = 0; rr <= maxRank; rr++)
+				{
+					if(live && prank == rr)
 					{
-						const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-						prank = __popc(peers & laneLt);
-						maxRank = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(valid ? prank : 0));
-					}
-					for(int rr = 0; rr <= maxRank; rr++)
-					{
-						if(valid && prank == rr)
+						const int q = MS == 4 ? (int)((e >> 7) & 3u) : 0;
+						const int row = (int)((e >> 4) & 7u), bit = (int)(e & 15u);
+						const int x = rx + bit, y = ry + row;
+						const int ix = x & 1, iy = y & 1;
+						const int pi = (int)(MS == 4 ? skey : (skey & 0x7Fu)); // index inside the staged planes: q * 128 + row * 16 + column
+						// ---- plane equations of the triangle (through L1: the items of a triangle sit next to each other in the queue) ----
+						const float4 *pl = (const float4 *)(d.triRecords + (size_t)idk * d.triStride + d.planeOffset);
+						float pf[FRONT4 * 4];
+#pragma unroll
+						for(int t = 0; t < FRONT4; t++)
 						{
-							const int k = (e >> 13) & 31;
-							const int q = MS == 4 ? (int)(code & 3) : 0;
-							const int row = MS == 4 ? (int)(code >> 2) : (int)code;
-							const int x = rx + bit, y = ry + row;
-							const int ix = x & 1, iy = y & 1;
-							const int pi = q * TP + regionPi + row * SWCU_TILE_W + bit; // index inside the staged planes
-							// ---- plane equations of the triangle ----
-							float pf[NF4 * 4];
+							const float4 v = __ldg(pl + t);
+							pf[4 * t] = v.x; pf[4 * t + 1] = v.y; pf[4 * t + 2] = v.z; pf[4 * t + 3] = v.w;
+						}
+						const float x0 = pf[0], y0 = pf[1], wA = pf[2], wB = pf[3], wC = pf[4];
+						const float rhwConst = pf[5]; // 1/w of a constant w plane (k_setup), 0 otherwise
+						const float *S = pf + TRI_FLOATS_FRONT; // slot s: S[3s], S[3s+1], S[3s+2]
+						// ---- interpolate + routed fragment shader (PixelRoutine.cpp:196-261, PixelProgram.cpp:138-241) ----
+						const float xf = fsub((float)x, x0), yf = fsub((float)y, y0);
+						float rhw = 1.0f;
+						if(SH != SH_CONST) rhw = rhwConst != 0.0f ? rhwConst : fdiv(1.0f, __fmaf_rn(xf, wA, fadd(wC, fmul(yf, wB))));
+						float texel[4] = { 0, 0, 0, 0 };
+						if(TEX)
+						{
+							// implicit LOD from lanes 0,1,2 of the pixel's quad (helper pixels included), SamplerCore.cpp:1376-1422
+							const uint32_t modeU = FS ? (uint32_t)IM_PERSP : d.slotMode[UV], modeV = FS ? (uint32_t)IM_PERSP : d.slotMode[UV + 1];
+							float uu[3], vv[3];
 #pragma unroll
-							for(int t = 0; t < NF4; t++)
+							for(int t = 0; t < 3; t++)
 							{
-								const float4 v = wPlanes[k * NF4 + t];
-								pf[4 * t] = v.x; pf[4 * t + 1] = v.y; pf[4 * t + 2] = v.z; pf[4 * t + 3] = v.w;
+								const float xk = fsub((float)(x - ix + (t & 1)), x0), yk = fsub((float)(y - iy + (t >> 1)), y0);
+								const float rk = rhwConst != 0.0f ? rhwConst : fdiv(1.0f, __fmaf_rn(xk, wA, fadd(wC, fmul(yk, wB))));
+								uu[t] = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], modeU, xk, yk, rk);
+								vv[t] = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], modeV, xk, yk, rk);
 							}
-							const float x0 = pf[0], y0 = pf[1], zBias = pf[2], wA = pf[3], wB = pf[4], wC = pf[5], zA = pf[6], zB = pf[7], zC = pf[8];
-							const float *S = pf + TRI_FLOATS_FIXED; // slot s: S[3s], S[3s+1], S[3s+2]
-							// ---- interpolate + routed fragment shader (PixelRoutine.cpp:196-261, PixelProgram.cpp:138-241) ----
-							const float xf = fsub((float)x, x0), yf = fsub((float)y, y0);
-							const float rhwConst = pf[NF4 * 4 - 1]; // 1/w of a constant w plane (k_setup), 0 otherwise
-							float rhw = 1.0f;
-							if(SH != SH_CONST) rhw = rhwConst != 0.0f ? rhwConst : fdiv(1.0f, __fmaf_rn(xf, wA, fadd(wC, fmul(yf, wB))));
-							float texel[4] = { 0, 0, 0, 0 };
-							if(TEX)
-							{
-								// implicit LOD from lanes 0,1,2 of the pixel's quad (helper pixels included), SamplerCore.cpp:1376-1422
-								const uint32_t modeU = FS ? (uint32_t)IM_PERSP : d.slotMode[UV], modeV = FS ? (uint32_t)IM_PERSP : d.slotMode[UV + 1];
-								float uu[3], vv[3];
+							const float u = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], modeU, xf, yf, rhw);
+							const float v = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], modeV, xf, yf, rhw);
+							if(d.texFast) sample_texture<true>(d, compute_lod<true>(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]), u, v, texel);
+							else sample_texture<false>(d, compute_lod<false>(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]), u, v, texel);
+						}
+						float rgba[4];
 #pragma unroll
-								for(int t = 0; t < 3; t++)
-								{
-									const float xk = fsub((float)(x - ix + (t & 1)), x0), yk = fsub((float)(y - iy + (t >> 1)), y0);
-									const float rk = rhwConst != 0.0f ? rhwConst : fdiv(1.0f, __fmaf_rn(xk, wA, fadd(wC, fmul(yk, wB))));
-									uu[t] = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], modeU, xk, yk, rk);
-									vv[t] = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], modeV, xk, yk, rk);
-								}
-								const float u = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], modeU, xf, yf, rhw);
-								const float v = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], modeV, xf, yf, rhw);
-								if(d.texFast) sample_texture<true>(d, compute_lod<true>(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]), u, v, texel);
-								else sample_texture<false>(d, compute_lod<false>(d, uu[0], uu[1], uu[2], vv[0], vv[1], vv[2]), u, v, texel);
-							}
-							float rgba[4];
-#pragma unroll
-							for(int ch = 0; ch < 4; ch++)
+						for(int ch = 0; ch < 4; ch++)
+						{
+							float val;
+							if(FS)
 							{
-								float val;
-								if(FS)
-								{
-									// routing checked on the host: constant shader -> constants; texture shader -> texel channel ch;
-									// varying shader -> slot ch, or a constant (e.g. alpha = 1)
-									if(SH == SH_CONST) val = __uint_as_float(d.chanValue[ch]);
-									else if(SH == SH_TEX) val = texel[ch];
-									else
-									{
-										val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], IM_PERSP, xf, yf, rhw);
-										if(d.chanKind[ch] == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
-									}
-								}
+								// routing checked on the host: constant shader -> constants; texture shader -> texel channel ch;
+								// varying shader -> slot ch, or a constant (e.g. alpha = 1)
+								if(SH == SH_CONST) val = __uint_as_float(d.chanValue[ch]);
+								else if(SH == SH_TEX) val = texel[ch];
 								else
 								{
-									const uint32_t kind = d.chanKind[ch];
-									if(kind == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
-									else if(TEX && kind == CK_TEXEL)
-									{
-										const uint32_t t = d.chanValue[ch];
-										val = t == 0 ? texel[0] : t == 1 ? texel[1] : t == 2 ? texel[2] : texel[3];
-									}
-									else if(SH == SH_VARY || SH == SH_GENERIC) val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], d.slotMode[ch], xf, yf, rhw);
-									else val = 0.0f;
+									val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], IM_PERSP, xf, yf, rhw);
+									if(d.chanKind[ch] == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
 								}
-								// PixelProgram::clampColor :286-364 — UNORM targets only ("if the color attachment is floating-point, no clamping occurs")
-								rgba[ch] = (!FS && colorEpp > 1) ? val : sse_min(sse_max(val, 0.0f), 1.0f);
 							}
+							else
+							{
+								const uint32_t kind = d.chanKind[ch];
+								if(kind == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
+								else if(TEX && kind == CK_TEXEL)
+								{
+									const uint32_t t = d.chanValue[ch];
+									val = t == 0 ? texel[0] : t == 1 ? texel[1] : t == 2 ? texel[2] : texel[3];
+								}
+								else if(SH == SH_VARY || SH == SH_GENERIC) val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], d.slotMode[ch], xf, yf, rhw);
+								else val = 0.0f;
+							}
+							// PixelProgram::clampColor :286-364 — UNORM targets only ("if the color attachment is floating-point, no clamping occurs")
+							rgba[ch] = (!FS && colorEpp > 1) ? val : sse_min(sse_max(val, 0.0f), 1.0f);
+						}
 
-							// ---- stencil test, depth test, depth write, blend + colour write, stencil write ----
-							bool sPass = true;
-							uint32_t sValue = 0;
-							const uint32_t frontFacing = FS ? 1u : (wHdr[k].z >> 28) & 1u;
-							if(!FS && d.stencilActive)
+						// ---- stencil test, depth test, depth write, blend + colour write, stencil write ----
+						bool sPass = true;
+						uint32_t sValue = 0;
+						const uint32_t frontFacing = FS ? 1u : (flagsk & TRI_FLAG_FRONT);
+						if(!FS && d.stencilActive)
+						{
+							const KStencilFace &face = frontFacing ? d.front : d.back;
+							sValue = smStencil[pi];
+							sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
+						}
+						// alphaToCoverage (PixelRoutine.cpp:643-658, thresholds Renderer.cpp:391-410): CmpNLT = ordered >=, a NaN alpha loses its coverage; a
+						// sample that loses its coverage leaves every later stage, stencil write included (:319-326)
+						bool alive = true;
+						if(!FS && d.alphaToCoverage) alive = rgba[3] >= (MS == 4 ? (q == 0 ? 0.2f : q == 1 ? 0.4f : q == 2 ? 0.6f : 0.8f) : 0.5f);
+						bool zPass = true;
+						float z = 0.0f;
+						if(d.depthTestActive)
+						{
+							const float4 zv = __ldg(pl + FRONT4); // zBias, zA, zB, zC
+							float yy = yf, xx = xf;
+							if(MS > 1)
 							{
-								const KStencilFace &face = frontFacing ? d.front : d.back;
-								sValue = smStencil[pi];
-								sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
+								// sample position relative to the pixel centre (Constants.cpp:291-297), in eighths: Y = 2q - 3, X = {-1, 3, -3, 1}
+								const float sy = fmul((float)(2 * q - 3), 0.125f);
+								const float sx = fmul((float)(int)(signed char)(0x01FD03FFu >> (8 * q)), 0.125f);
+								yy = fadd(yy, sy);
+								xx = fsub(xx, sx);
 							}
-							// alphaToCoverage (PixelRoutine.cpp:643-658, thresholds Renderer.cpp:391-410): CmpNLT = ordered >=, a NaN alpha loses its coverage; a
-							// sample that loses its coverage leaves every later stage, stencil write included (:319-326)
-							bool alive = true;
-							if(!FS && d.alphaToCoverage) alive = rgba[3] >= (MS == 4 ? (q == 0 ? 0.2f : q == 1 ? 0.4f : q == 2 ? 0.6f : 0.8f) : 0.5f);
-							bool zPass = true;
-							float z = 0.0f;
-							if(d.depthTestActive)
+							z = __fmaf_rn(xx, zv.y, fadd(zv.w, fmul(yy, zv.z)));
+							if(biasOn) z = fadd(z, zv.x);
+							z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
+							if(!FS && d.depth16)
 							{
-								float yy = yf, xx = xf;
-								if(MS > 1)
-								{
-									// sample position relative to the pixel centre (Constants.cpp:291-297), in eighths: Y = 2q - 3, X = {-1, 3, -3, 1}
-									const float sy = fmul((float)(2 * q - 3), 0.125f);
-									const float sx = fmul((float)(int)(signed char)(0x01FD03FFu >> (8 * q)), 0.125f);
-									yy = fadd(yy, sy);
-									xx = fsub(xx, sx);
-								}
-								z = __fmaf_rn(xx, zA, fadd(zC, fmul(yy, zB)));
-								if(biasOn) z = fadd(z, zBias);
-								z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
-								if(!FS && d.depth16)
-								{
-									// D16_UNORM (:466-482, :508-511): Z = Min(Max(Round(z * 0xFFFF), 0), 0xFFFF) against Float(UShort), as floats;
-									// the value written (:687-711, saturating UShort of Round(z * 0xFFFF)) is that same Z
-									z = sse_min(sse_max(rintf(fmul(z, 65535.0f)), 0.0f), 65535.0f);
-									zPass = depth_compare(d.depthCompareOp, (float)((const unsigned short *)smDepth)[pi], z);
-								}
-								else
-								{
-									const float zValue = smDepth[pi];
-									if(FS) zPass = d.depthCompareOp == CMP_LESS ? zValue > z : zValue >= z; // LESS / LESS_OR_EQUAL (:533-553)
-									else zPass = depth_compare(d.depthCompareOp, zValue, z);
-								}
-								if(!FS && d.depthBounds)
-								{
-									// depthBoundsTest :576-641: the STORED depth (read before this fragment's write) against [min, max]; with a depth
-									// test it narrows the depth mask, so the stencil depth-fail op sees it; without one it narrows the coverage
-									const float stored = d.depth16 ? fmul((float)((const unsigned short *)smDepth)[pi], 1.0f / 0xFFFF) : smDepth[pi];
-									const bool inside = d.minDepthBounds <= stored && stored <= d.maxDepthBounds;
-									if(d.depthBounds == 2) alive = alive && inside;
-									else zPass = zPass && inside;
-								}
+								// D16_UNORM (:466-482, :508-511): Z = Min(Max(Round(z * 0xFFFF), 0), 0xFFFF) against Float(UShort), as floats;
+								// the value written (:687-711, saturating UShort of Round(z * 0xFFFF)) is that same Z
+								z = sse_min(sse_max(rintf(fmul(z, 65535.0f)), 0.0f), 65535.0f);
+								zPass = depth_compare(d.depthCompareOp, (float)((const unsigned short *)smDepth)[pi], z);
 							}
-							if(alive && zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
+							else
 							{
-								if(d.depthWriteEnable)
+								const float zValue = smDepth[pi];
+								if(FS) zPass = d.depthCompareOp == CMP_LESS ? zValue > z : zValue >= z; // LESS / LESS_OR_EQUAL (:533-553)
+								else zPass = depth_compare(d.depthCompareOp, zValue, z);
+							}
+							if(!FS && d.depthBounds)
+							{
+								// depthBoundsTest :576-641: the STORED depth (read before this fragment's write) against [min, max]; with a depth
+								// test it narrows the depth mask, so the stencil depth-fail op sees it; without one it narrows the coverage
+								const float stored = d.depth16 ? fmul((float)((const unsigned short *)smDepth)[pi], 1.0f / 0xFFFF) : smDepth[pi];
+								const bool inside = d.minDepthBounds <= stored && stored <= d.maxDepthBounds;
+								if(d.depthBounds == 2) alive = alive && inside;
+								else zPass = zPass && inside;
+							}
+						}
+						if(alive && zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
+						{
+							if(d.depthWriteEnable)
+							{
+								if(!FS && d.depth16) ((unsigned short *)smDepth)[pi] = (unsigned short)z;
+								else smDepth[pi] = z;
+								dirty = true;
+							}
+							if(colorOn)
+							{
+								const bool floatTarget = !FS && colorEpp > 1;
+								const uint32_t px = floatTarget ? 0u : smColor[pi];
+								float o[4] = { rgba[0], rgba[1], rgba[2], rgba[3] };
+								if(BL != BL_OFF)
 								{
-									if(!FS && d.depth16) ((unsigned short *)smDepth)[pi] = (unsigned short)z;
-									else smDepth[pi] = z;
-									dirty = true;
-								}
-								if(colorOn)
-								{
-									const bool floatTarget = !FS && colorEpp > 1;
-									const uint32_t px = floatTarget ? 0u : smColor[pi];
-									float o[4] = { rgba[0], rgba[1], rgba[2], rgba[3] };
-									if(BL != BL_OFF)
-									{
-										float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
-										if(floatTarget)
-										{
-											// floating-point targets: the stored value itself (:1700-1710), or Reactor's Float(Half) (:1782-1801)
-											if(colorEpp == 4)
-											{
-												const float4 t = ((const float4 *)smColor)[pi];
-												dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
-											}
-											else
-											{
-												const uint2 t = ((const uint2 *)smColor)[pi];
-												dst[0] = half_to_float(t.x & 0xFFFFu); dst[1] = half_to_float(t.x >> 16);
-												dst[2] = half_to_float(t.y & 0xFFFFu); dst[3] = half_to_float(t.y >> 16);
-											}
-										}
-										else
-										{
-#pragma unroll
-											for(int ch = 0; ch < 4; ch++)
-											{
-												const uint32_t byte = (bgr && ch < 3) ? 2 - ch : ch;
-												dst[ch] = fmul((float)__byte_perm(px, 0, 0x4400u | byte | (byte << 4)), 1.0f / 0xFFFF); // b * 257 == b << 8 | b
-												if(!FS && d.srgb && ch < 3) dst[ch] = srgb_to_linear(dst[ch]);
-											}
-										}
-										if(BL == BL_SRC_ALPHA)
-										{
-											const float sa = rgba[3], da = fsub(1.0f, rgba[3]);
-#pragma unroll
-											for(int ch = 0; ch < 3; ch++) o[ch] = fadd(fmul(rgba[ch], sa), fmul(dst[ch], da));
-										}
-										else
-										{
-#pragma unroll
-											for(int ch = 0; ch < 3; ch++)
-												o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
-											o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
-										}
-									}
-									if(!FS && d.srgb)
-									{
-#pragma unroll
-										for(int ch = 0; ch < 3; ch++) o[ch] = linear_to_srgb(o[ch]);
-									}
+									float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
 									if(floatTarget)
 									{
-										// masked store of the bits (:2429-2447), or of Reactor's Half(Float) (:2504-2540); no clamp, no rounding of fp32
-										const uint32_t cm = d.colorWriteMask;
+										// floating-point targets: the stored value itself (:1700-1710), or Reactor's Float(Half) (:1782-1801)
 										if(colorEpp == 4)
 										{
-											float *t = (float *)smColor + 4 * pi;
-#pragma unroll
-											for(int ch = 0; ch < 4; ch++)
-												if((cm >> ch) & 1) t[ch] = o[ch];
+											const float4 t = ((const float4 *)smColor)[pi];
+											dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
 										}
 										else
 										{
-											unsigned short *t = (unsigned short *)smColor + 4 * pi;
-#pragma unroll
-											for(int ch = 0; ch < 4; ch++)
-												if((cm >> ch) & 1) t[ch] = (unsigned short)float_to_half(o[ch]);
+											const uint2 t = ((const uint2 *)smColor)[pi];
+											dst[0] = half_to_float(t.x & 0xFFFFu); dst[1] = half_to_float(t.x >> 16);
+											dst[2] = half_to_float(t.y & 0xFFFFu); dst[3] = half_to_float(t.y >> 16);
 										}
 									}
 									else
 									{
-										const uint32_t pk = bgr ? pack_unorm8(o[2], o[1], o[0], o[3]) : pack_unorm8(o[0], o[1], o[2], o[3]);
-										smColor[pi] = (px & ~wmask32) | (pk & wmask32);
+#pragma unroll
+										for(int ch = 0; ch < 4; ch++)
+										{
+											const uint32_t byte = (bgr && ch < 3) ? 2 - ch : ch;
+											dst[ch] = fmul((float)__byte_perm(px, 0, 0x4400u | byte | (byte << 4)), 1.0f / 0xFFFF); // b * 257 == b << 8 | b
+											if(!FS && d.srgb && ch < 3) dst[ch] = srgb_to_linear(dst[ch]);
+										}
 									}
-									dirty = true;
+									if(BL == BL_SRC_ALPHA)
+									{
+										const float sa = rgba[3], da = fsub(1.0f, rgba[3]);
+#pragma unroll
+										for(int ch = 0; ch < 3; ch++) o[ch] = fadd(fmul(rgba[ch], sa), fmul(dst[ch], da));
+									}
+									else
+									{
+#pragma unroll
+										for(int ch = 0; ch < 3; ch++)
+											o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
+										o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
+									}
 								}
-							}
-							if(!FS && d.stencilWrite && alive) // writeStencil :754-817
-							{
-								const KStencilFace &face = frontFacing ? d.front : d.back;
-								const uint32_t ref = face.reference & 0xFF;
-								uint32_t nv;
-								if(!sPass) nv = stencil_op(face.failOp, sValue, ref);
-								else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
-								else nv = stencil_op(face.passOp, sValue, ref);
-								const uint32_t wm = face.writeMask & 0xFF;
-								smStencil[pi] = (unsigned char)((nv & wm) | (sValue & ~wm));
+								if(!FS && d.srgb)
+								{
+#pragma unroll
+									for(int ch = 0; ch < 3; ch++) o[ch] = linear_to_srgb(o[ch]);
+								}
+								if(floatTarget)
+								{
+									// masked store of the bits (:2429-2447), or of Reactor's Half(Float) (:2504-2540); no clamp, no rounding of fp32
+									const uint32_t cm = d.colorWriteMask;
+									if(colorEpp == 4)
+									{
+										float *t = (float *)smColor + 4 * pi;
+#pragma unroll
+										for(int ch = 0; ch < 4; ch++)
+											if((cm >> ch) & 1) t[ch] = o[ch];
+									}
+									else
+									{
+										unsigned short *t = (unsigned short *)smColor + 4 * pi;
+#pragma unroll
+										for(int ch = 0; ch < 4; ch++)
+											if((cm >> ch) & 1) t[ch] = (unsigned short)float_to_half(o[ch]);
+									}
+								}
+								else
+								{
+									const uint32_t pk = bgr ? pack_unorm8(o[2], o[1], o[0], o[3]) : pack_unorm8(o[0], o[1], o[2], o[3]);
+									smColor[pi] = (px & ~wmask32) | (pk & wmask32);
+								}
 								dirty = true;
 							}
 						}
-						__syncwarp();
+						if(!FS && d.stencilWrite && alive) // writeStencil :754-817
+						{
+							const KStencilFace &face = frontFacing ? d.front : d.back;
+							const uint32_t ref = face.reference & 0xFF;
+							uint32_t nv;
+							if(!sPass) nv = stencil_op(face.failOp, sValue, ref);
+							else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
+							else nv = stencil_op(face.passOp, sValue, ref);
+							const uint32_t wm = face.writeMask & 0xFF;
+							smStencil[pi] = (unsigned char)((nv & wm) | (sValue & ~wm));
+							dirty = true;
+						}
 					}
+					__syncwarp();
 				}
-				__syncwarp();
 			}
-			__syncwarp(); // the pair / mark areas are reused by the next range
-			c0 = c1;
-			}
+			__syncwarp(); // the queue is refilled by the next entries
 		}
-		if(listDone) break;
 	}
 
 	if(!tileReady)
 		while(!mbar_try_wait(bar, 0)) {} // never leave with a bulk copy into this CTA's shared memory still in flight
-	if(__any_sync(0xFFFFFFFFu, dirty) && lane == 0) *dirtyFlag = 1;
-	__syncthreads();
-	if(!*dirtyFlag) return;
-	if(d.useTma)
+	if(!__any_sync(0xFFFFFFFFu, dirty)) return;
+	// Only rows inside the scissor go back: the rows of a region that the scissor cuts off may belong to another rank's band of
+	// the same frame (multi-GPU), whose pixels this warp has staged but must not overwrite.
+	const bool whole = ryLo == ry && ryHi == min(ry + SWCU_REGION_H, d.fbHeight);
+	if(d.useTma && whole)
 	{
-		fence_proxy_async(); // generic-proxy writes of the tile -> visible to the async proxy
-		__syncthreads();
-		if(threadIdx.x == 0)
+		fence_proxy_async(); // generic-proxy writes of the region -> visible to the async proxy
+		__syncwarp();
+		if(lane == 0)
 		{
-			if(colorOn) tma_store_3d(&maps.color, smColor, tileX * colorEpp, tileY, 0);
-			if(d.depthWriteEnable) tma_store_3d(&maps.depth, smDepth, tileX, tileY, 0);
-			if(d.stencilWrite) tma_store_3d(&maps.stencil, smStencil, tileX, tileY, 0);
+			if(colorOn) tma_store_3d(&maps.color, smColor, rx * colorEpp, ry, 0);
+			if(d.depthWriteEnable) tma_store_3d(&maps.depth, smDepth, rx, ry, 0);
+			if(d.stencilWrite) tma_store_3d(&maps.stencil, smStencil, rx, ry, 0);
 			tma_commit();
 			tma_wait_read0();
 		}
 	}
 	else
 	{
-		if(colorOn && colorEpp == 4) tile_copy<MS, uint4, true>((uint4 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		else if(colorOn && colorEpp == 2) tile_copy<MS, uint2, true>((uint2 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		else if(colorOn) tile_copy<MS, uint32_t, true>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		if(d.depthWriteEnable && d.depth16) tile_copy<MS, unsigned short, true>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		else if(d.depthWriteEnable) tile_copy<MS, float, true>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
-		if(d.stencilWrite) tile_copy<MS, unsigned char, true>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, tileX, tileY, d.fbWidth, d.fbHeight);
+		__syncwarp();
+		if(colorOn && colorEpp == 4) region_copy<MS, uint4, true>((uint4 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ryLo, ryHi, lane);
+		else if(colorOn && colorEpp == 2) region_copy<MS, uint2, true>((uint2 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ryLo, ryHi, lane);
+		else if(colorOn) region_copy<MS, uint32_t, true>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ryLo, ryHi, lane);
+		if(d.depthWriteEnable && d.depth16) region_copy<MS, unsigned short, true>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, rx, ry, d.fbWidth, ryLo, ryHi, lane);
+		else if(d.depthWriteEnable) region_copy<MS, float, true>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, rx, ry, d.fbWidth, ryLo, ryHi, lane);
+		if(d.stencilWrite) region_copy<MS, unsigned char, true>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, rx, ry, d.fbWidth, ryLo, ryHi, lane);
 	}
 }
 

@@ -54,13 +54,13 @@ enum { CLIP_RIGHT = 1, CLIP_TOP = 2, CLIP_FAR = 4, CLIP_LEFT = 8, CLIP_BOTTOM = 
 #define SWCU_MAXSLOTS 6      // plane-equation slots per triangle: 4 colour channels + (u, v)
 #define SWCU_TILE_W 32       // screen tile staged in shared memory by one CTA
 #define SWCU_TILE_H 16
-#define SWCU_REGION_W 16     // sub-tile owned by one warp: 8x4 quads, one 2x2 quad per lane
+#define SWCU_REGION_W 16     // sub-tile owned by one warp; also the granularity of the triangle bins
 #define SWCU_REGION_H 8
 #define SWCU_TILE_WARPS ((SWCU_TILE_W / SWCU_REGION_W) * (SWCU_TILE_H / SWCU_REGION_H))
-#define SWCU_SMALL_ROWS 8    // triangles up to this many rows carry their span rows inline in the triangle record
-#define SWCU_SMALL_TILES 8   // ... and emit their (tile, triangle) pairs from the emit thread
+#define SWCU_SMALL_ROWS 8    // a SMALL triangle fits an 8 x 8 pixel frame: its coverage travels as bit masks inside its record
+#define SWCU_SMALL_COLS 8
 #define SWCU_POLY_MAX 10     // 3 + 6 clip planes (+1 wrap slot)
-#define SWCU_INVALID_TILE 0xFFFFFFFFu
+#define SWCU_SORT_CAP 256    // bins up to this many entries are put in triangle order by the tile kernel itself (k_sortbig does the others)
 
 // operand kinds after routing (device side)
 enum { OPK_CONST = 0, OPK_INPUT = 1, OPK_TEXEL = 2 };
@@ -101,12 +101,13 @@ struct KStencilFace
 	uint32_t failOp, passOp, depthFailOp, compareOp, compareMask, writeMask, reference, pad;
 };
 
-// One big-triangle work item (triangles taller than SWCU_SMALL_ROWS or wider than SWCU_SMALL_TILES tiles):
-// spans and tile pairs are produced by a CTA instead of the setup thread.
+// One BIG triangle (anything that does not fit the 8 x 8 pixel frame of a small one, clipped polygons, garbage coordinates):
+// the polygon in 24.8 fixed point.  Its spans are evaluated in closed form by the region warps of the tile kernel, its
+// (region, triangle) pairs by k_bigcount / k_fill.
 struct BigTri
 {
 	uint32_t tri;
-	uint32_t spanBase;
+	uint32_t walk;    // 1: its pairs did not fit the pair budget (see DrawConst::bigBudget): not binned
 	int32_t n, dir;
 	int32_t yMin, yMax;
 	int32_t pxMin, pxMax;
@@ -116,11 +117,13 @@ struct BigTri
 // Per-draw device counters (one struct in device memory, zeroed per draw)
 struct DrawCounters
 {
-	unsigned long long spanCursor; // entries allocated from the span table
-	unsigned long long bigSlots;   // entries appended to the big list
-	uint32_t overflow;             // bit0: span table, bit1: big list
-	uint32_t visible;              // triangles that survived setup
-	unsigned long long pairTotal;  // number of (tile, triangle) pairs, written after the scan
+	unsigned long long bigSlots;    // entries appended to the big list
+	unsigned long long bigReserved; // (region, triangle) pairs reserved by big triangles (bounding-box count)
+	unsigned long long pairTotal;   // number of (region, triangle) pairs binned, written by the scan
+	uint32_t overflow;              // bit1: big list full; bit2: a big triangle did not fit the pair budget
+	uint32_t visible;               // triangles that survived setup
+	uint32_t scanTicket;            // k_binscan: block tickets
+	uint32_t pad;
 };
 
 struct DrawConst
@@ -188,43 +191,45 @@ struct DrawConst
 	// ---- work buffers ----
 	unsigned char *triRecords; // primCount records of triStride bytes
 	uint32_t triStride;
-	uint32_t *spans;           // {u16 left, u16 right} per (row, sample)
-	unsigned long long spanCapacity;
+	uint32_t planeOffset;      // bytes from the start of a record to its plane equations (16, or 48 with the 4x masks)
 	BigTri *bigList;
 	uint32_t bigCapacity;
-	uint32_t *tileCount;       // per triangle: packed tile rectangle / pair count (tile_rect_count)
+	uint32_t *triRect;         // per triangle: packed region rectangle of a small triangle / BIG | big-list slot / NONE
+	uint32_t *binCount;        // per region bin: pairs counted by k_setup / k_bigcount, counted back down to zero by k_fill
+	uint32_t *binStart;        // per region bin (+1): exclusive scan of binCount
+	uint32_t *pairs;           // triangle ids, bin after bin
+	unsigned long long bigBudget; // pairs the big triangles of this draw may add (capacity of `pairs` minus 4 per triangle)
 	uint32_t inputsExternal;        // an index / vertex stream lives in caller-owned device memory (host side only)
 	const unsigned char *cullFlags; // band mode: 0 = rows outside the band (k_cull), nullptr when the pass is not run
 	DrawCounters *counters;
 	const void *zeroPage;      // 256 readable bytes: target of the discarded loads of branch-free attribute fetches
 	int32_t tilesX, tilesY;    // tile grid of the framebuffer
 	int32_t tileX0, tileY0, tileX1, tileY1; // tile range touched by the scissor (exclusive upper)
-	uint32_t direct;           // 1: no binning, every tile CTA walks all triangles
+	uint32_t numBins;          // tilesX * tilesY * 4: bin = tile * 4 + (region row & 1) * 2 + (region column & 1)
+	uint32_t direct;           // 1: no binning, every region warp walks all triangles
 	uint32_t blendClass;       // BL_*
 	uint32_t useTma;           // attachments satisfy the tensor-map alignment rules: stage the tile with TMA
 };
 
 // TriRecord layout (triStride bytes, 16-byte aligned):
-//   uint16 pxMin, pxMax, yMin, yMax;   pixel bounds (x exclusive upper, y exclusive upper); yMin>=yMax => invisible
-//   uint32 spanBase;                   big triangles: first entry in the span table, index = spanBase + (y - yMin) * ms + q
-//   uint32 flags;                      bit0 = clockwiseMask (front facing, Primitive.hpp:60); bit1 = big (rows in the span table)
-//   float  x0, y0, zBias, wA, wB, wC, zA, zB, zC;   Primitive::{x0,y0,zBias,w,z}
-//   float  V[nslots][3];               Primitive::V planes {A,B,C} of the routed slots   (padded to a multiple of 16 bytes)
-//   uint32 rows[SWCU_SMALL_ROWS][ms];  small triangles: span {u16 left, u16 right} of row yMin + r, sample q  (Primitive::outline)
+//   small triangle (fits an 8 x 8 pixel frame at (fx, fy)):
+//     uint32 fx | fy << 16;  uint32 flags;  uint32 mask[2]        1x: bit (8 * row + column) = pixel (fx + column, fy + row) covered
+//     uint32 mask[8]                                             4x only: word = row, byte = sample, bit = column
+//   big triangle:
+//     uint32 pxMin | pxMax << 16;  uint32 flags;  uint32 yMin | yMax << 16;  uint32 slot in the big list
+//   flags: bit0 = clockwiseMask (front facing, Primitive.hpp:60); bit1 = big
+//   then the plane equations (Primitive::{x0,y0,w,V,z,zBias}), 128-bit aligned:
+//     float x0, y0, wA, wB, wC, rhwConst;  float V[nslots][3];  (pad to 16 bytes)  float zBias, zA, zB, zC (only with a depth test)
+//   rhwConst = 1/w when the w plane is constant (0 otherwise).
 #define TRI_HEADER_BYTES 16
+#define TRI_FLAG_FRONT 1u
+#define TRI_FLAG_BIG 2u
+#define TRI_FLOATS_FRONT 6
 
-// Per-triangle word k_setup leaves for the binning steps.  Small triangles (<= 8 rows, <= 8 tiles): the tile rectangle
-// tx0 (9 bits) | ty0 << 9 (10 bits) | (tx1 - tx0) << 19 (3 bits) | (ty1 - ty0) << 22 (3 bits) — k_emit needs nothing else.
-// Big triangles: TILE_RECT_BIG | number of tiles of the bounding box (k_big emits them).  Invisible: TILE_RECT_NONE.
-#define TILE_RECT_BIG 0x80000000u
-#define TILE_RECT_NONE 0x80000000u
-#ifdef __CUDACC__
-__host__ __device__
-#endif
-static inline uint32_t tile_rect_count(uint32_t r)
-{
-	return (r & TILE_RECT_BIG) ? (r & 0x7FFFFFFFu) : (((r >> 19) & 7u) + 1u) * (((r >> 22) & 7u) + 1u);
-}
-#define TRI_FLOATS_FIXED 9
-static inline uint32_t swcu_tri_plane_f4(int nslots) { return (uint32_t)((TRI_FLOATS_FIXED + 3 * nslots + 3) / 4); }
-static inline uint32_t swcu_tri_stride(int nslots, int ms) { return TRI_HEADER_BYTES + 16 * swcu_tri_plane_f4(nslots) + 4 * SWCU_SMALL_ROWS * (uint32_t)ms; }
+// Per-triangle word k_setup leaves for the binning steps.  Small: region rectangle rx0 (9 bits) | ry0 << 9 (10 bits) |
+// (rx1 - rx0) << 19 (1 bit) | (ry1 - ry0) << 20 (1 bit); big: TRI_RECT_BIG | slot in the big list; invisible: TRI_RECT_NONE.
+#define TRI_RECT_BIG 0x80000000u
+#define TRI_RECT_NONE 0xFFFFFFFFu
+static inline uint32_t swcu_front_f4(int nslots) { return (uint32_t)((TRI_FLOATS_FRONT + 3 * nslots + 3) / 4); }
+static inline uint32_t swcu_plane_offset(int ms) { return ms > 1 ? TRI_HEADER_BYTES + 32u : TRI_HEADER_BYTES; }
+static inline uint32_t swcu_tri_stride(int nslots, int ms, int depth) { return swcu_plane_offset(ms) + 16u * (swcu_front_f4(nslots) + (depth ? 1u : 0u)); }
