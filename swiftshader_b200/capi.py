@@ -108,7 +108,8 @@ EXPORTS = [
 ]
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_ROOT, "csrc", "libswcuda.so")
+# SWCU_LIB: a differently configured build of the same library (kernel tuning experiments: scripts/gpu_variants.sh)
+LIB_PATH = os.environ.get("SWCU_LIB") or os.path.join(_ROOT, "csrc", "libswcuda.so")
 _lib = None
 
 

@@ -55,7 +55,7 @@ struct swcu_ctx
 	// the pair buffer holds 4 pairs per triangle plus a budget for the big triangles (swcu_set_option "big_pair_budget").
 	struct SetupSet
 	{
-		DevBuf triRecords, bigList, triRect, binCount, binStart, pairs, counters, cullFlags;
+		DevBuf triRecords, bigList, triRect, binCount, binStart, pairs, longBins, counters, cullFlags;
 		cudaEvent_t tileDone = nullptr;       // recorded on the main stream after the last kernel that reads this set
 		bool tileDoneValid = false;
 		cudaEvent_t setupDone = nullptr;      // recorded on the setup stream after the binning of a pipelined draw
@@ -196,7 +196,7 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 	cudaFree(ctx->zeroPage.p);
 	for(auto &S : ctx->set)
 	{
-		DevBuf *sb[] = { &S.triRecords, &S.bigList, &S.triRect, &S.binCount, &S.binStart, &S.pairs, &S.counters, &S.cullFlags };
+		DevBuf *sb[] = { &S.triRecords, &S.bigList, &S.triRect, &S.binCount, &S.binStart, &S.pairs, &S.longBins, &S.counters, &S.cullFlags };
 		for(DevBuf *b : sb) cudaFree(b->p);
 		if(S.hostCounters) cudaFreeHost(S.hostCounters);
 		if(S.tileDone) cudaEventDestroy(S.tileDone);
@@ -1054,6 +1054,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		if(S.binCount.cap != before) CU(cudaMemsetAsync(S.binCount.p, 0, S.binCount.cap, ss)); // k_fill counts every bin back down to zero
 		if((rc = ensure(ctx, S.binStart, ((size_t)d.numBins + 1) * 4))) return rc;
 		if((rc = ensure(ctx, S.pairs, pairCap * 4))) return rc;
+		if((rc = ensure(ctx, S.longBins, (pairCap / SWCU_SORT_CAP + 1) * 4))) return rc; // more bins than that cannot be long
 	}
 	if(!ctx->zeroPage.p)
 	{
@@ -1099,7 +1100,8 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		}
 		{
 			LaunchScope ls(ctx, "k_binscan", ss);
-			k_binscan<<<(unsigned)scanBlocks, SCAN_THREADS, 0, ss>>>(d.binCount, d.binStart, d.numBins, (volatile uint32_t *)(d.counters + 1), d.counters);
+			k_binscan<<<(unsigned)scanBlocks, SCAN_THREADS, 0, ss>>>(d.binCount, d.binStart, d.numBins, (volatile uint32_t *)(d.counters + 1), d.counters,
+			                                                           (uint32_t *)S.longBins.p, (uint32_t)(pairCap / SWCU_SORT_CAP + 1));
 		}
 		{
 			LaunchScope ls(ctx, "k_fill", ss);
@@ -1108,7 +1110,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		}
 		{
 			LaunchScope ls(ctx, "k_sortbig", ss);
-			k_sortbig<<<148 * 2, SORTBIG_THREADS, 0, ss>>>(d.binStart, d.pairs, d.numBins);
+			k_sortbig<<<148, SORTBIG_THREADS, 0, ss>>>(d.binStart, d.pairs, (const uint32_t *)S.longBins.p, (uint32_t)(pairCap / SWCU_SORT_CAP + 1), d.counters);
 		}
 		{
 			LaunchScope ls(ctx, "k_report", ss);

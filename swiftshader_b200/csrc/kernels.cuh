@@ -39,6 +39,7 @@ DEVI float fmul(float a, float b) { return __fmul_rn(a, b); }
 DEVI float fadd(float a, float b) { return __fadd_rn(a, b); }
 DEVI float fsub(float a, float b) { return __fsub_rn(a, b); }
 DEVI float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+DEVI float frcp(float a) { return __frcp_rn(a); } // 1.0f / a, correctly rounded: the same value as fdiv(1.0f, a) in fewer instructions
 DEVI int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __constant__ float c_SampleX[4] = { 0.375f - 0.5f, 0.875f - 0.5f, 0.125f - 0.5f, 0.625f - 0.5f }; // Constants.cpp:291-297
@@ -363,6 +364,27 @@ __global__ void __launch_bounds__(256) k_cull(const __grid_constant__ DrawConst 
 
 DEVI uint32_t region_bin(const DrawConst &d, int rx, int ry) { return (uint32_t)(((ry >> 1) * d.tilesX + (rx >> 1)) * 4 + (ry & 1) * 2 + (rx & 1)); }
 
+// One add per distinct bin of the warp instead of one per lane: neighbouring triangles of a mesh land in the same few region bins,
+// and the L2 atomic unit serialises same-address operations (all 32 lanes must call).
+DEVI void warp_bin_count(uint32_t *binCount, bool has, uint32_t bin)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? bin : (0x80000000u | (uint32_t)lane));
+	if(has && lane == __ffs(peers) - 1) atomicAdd(binCount + bin, (uint32_t)__popc(peers));
+}
+// ... and the slots of the fill pass: the bin's count is taken down by the number of peers, every peer gets one of the slots
+DEVI uint32_t warp_bin_slot(uint32_t *binCount, bool has, uint32_t bin)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? bin : (0x80000000u | (uint32_t)lane));
+	const int leader = __ffs(peers) - 1;
+	const uint32_t cnt = (uint32_t)__popc(peers);
+	uint32_t old = 0;
+	if(has && lane == leader) old = atomicSub(binCount + bin, cnt);
+	old = __shfl_sync(0xFFFFFFFFu, old, leader);
+	return old - cnt + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
 DEVI int sel3(int i, int a0, int a1, int a2) { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
 DEVI float sel3(int i, float a0, float a1, float a2) { return i == 0 ? a0 : (i == 1 ? a1 : a2); }
 
@@ -482,6 +504,22 @@ DEVI void setup_triangle(const DrawConst &d)
 	if(__any_sync(0xFFFFFFFFu, big)) slot = warp_alloc(&d.counters->bigSlots, big ? 1u : 0u);
 	const uint32_t nvis = __popc(__ballot_sync(0xFFFFFFFFu, visible));
 	if((threadIdx.x & 31) == 0 && nvis) atomicAdd(&d.counters->visible, nvis);
+	// ---- region bins of a small triangle's frame: at most 2 x 2, counted here where the warp is still converged ----
+	uint32_t smallRect = TRI_RECT_NONE;
+	{
+		const bool small = visible && !big;
+		const int rx0 = pxMin / SWCU_REGION_W, rx1 = (pxMax - 1) / SWCU_REGION_W;
+		const int ry0 = yMin / SWCU_REGION_H, ry1 = (yMax - 1) / SWCU_REGION_H;
+		if(small) smallRect = (uint32_t)rx0 | ((uint32_t)ry0 << 9) | ((uint32_t)(rx1 - rx0) << 19) | ((uint32_t)(ry1 - ry0) << 20);
+		if(!d.direct)
+		{
+			const bool wide = small && rx1 > rx0, tall = small && ry1 > ry0;
+			warp_bin_count(d.binCount, small, small ? region_bin(d, rx0, ry0) : 0u);
+			if(__any_sync(0xFFFFFFFFu, wide)) warp_bin_count(d.binCount, wide, wide ? region_bin(d, rx1, ry0) : 0u);
+			if(__any_sync(0xFFFFFFFFu, tall)) warp_bin_count(d.binCount, tall, tall ? region_bin(d, rx0, ry1) : 0u);
+			if(__any_sync(0xFFFFFFFFu, wide && tall)) warp_bin_count(d.binCount, wide && tall, (wide && tall) ? region_bin(d, rx1, ry1) : 0u);
+		}
+	}
 	if(!live) return;
 	unsigned char *rec = d.triRecords + (size_t)tri * d.triStride;
 	if(big && slot >= d.bigCapacity) { atomicOr(&d.counters->overflow, 2u); visible = false; }
@@ -574,13 +612,7 @@ DEVI void setup_triangle(const DrawConst &d)
 			((uint4 *)(rec + TRI_HEADER_BYTES))[1] = make_uint4(w[4], w[5], w[6], w[7]);
 		}
 		hdr = make_uint4((uint32_t)pxMin | ((uint32_t)yMin << 16), frontFacing ? TRI_FLAG_FRONT : 0u, m0, m1);
-		// ---- region bins of the frame: at most 2 x 2 ----
-		const int rx0 = pxMin / SWCU_REGION_W, rx1 = (pxMax - 1) / SWCU_REGION_W;
-		const int ry0 = yMin / SWCU_REGION_H, ry1 = (yMax - 1) / SWCU_REGION_H;
-		d.triRect[tri] = (uint32_t)rx0 | ((uint32_t)ry0 << 9) | ((uint32_t)(rx1 - rx0) << 19) | ((uint32_t)(ry1 - ry0) << 20);
-		if(!d.direct)
-			for(int ry = ry0; ry <= ry1; ry++)
-				for(int rx = rx0; rx <= rx1; rx++) atomicAdd(d.binCount + region_bin(d, rx, ry), 1u);
+		d.triRect[tri] = smallRect;
 	}
 
 	// ---- vertex sort (SetupRoutine.cpp:271-294): only changes float rounding of the planes ----
@@ -807,7 +839,7 @@ __global__ void __launch_bounds__(32 * BIG_WARPS_PER_BLOCK) k_bigcount(const __g
 // predecessors until it meets one that already knows its prefix).  state[] and the ticket start at zero.
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 8
-__global__ void __launch_bounds__(SCAN_THREADS) k_binscan(const uint32_t *count, uint32_t *start, uint32_t n, volatile uint32_t *state, DrawCounters *c)
+__global__ void __launch_bounds__(SCAN_THREADS) k_binscan(const uint32_t *count, uint32_t *start, uint32_t n, volatile uint32_t *state, DrawCounters *c, uint32_t *longBins, uint32_t longCap)
 {
 	__shared__ uint32_t s_block, s_warp[SCAN_THREADS / 32], s_prefix;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -820,7 +852,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_binscan(const uint32_t *count,
 	for(int i = 0; i < SCAN_ITEMS; i++) v[i] = base + i < n ? count[base + i] : 0u;
 	uint32_t sum = 0;
 #pragma unroll
-	for(int i = 0; i < SCAN_ITEMS; i++) sum += v[i];
+	for(int i = 0; i < SCAN_ITEMS; i++)
+	{
+		sum += v[i];
+		// bins the tile kernel will not order itself: k_sortbig works through this list (at most longCap = pairs / SWCU_SORT_CAP of them exist)
+		if(v[i] > SWCU_SORT_CAP)
+		{
+			const uint32_t at = atomicAdd(&c->longBins, 1u);
+			if(at < longCap) longBins[at] = base + i;
+		}
+	}
 	uint32_t incl = sum;
 #pragma unroll
 	for(int o = 1; o < 32; o <<= 1)
@@ -881,16 +922,34 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ DrawConst 
 		return;
 	}
 	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
-	if(tri >= d.primCount) return;
-	const uint32_t r = d.triRect[tri];
-	if(r & TRI_RECT_BIG) return; // big: the blocks behind the small ones; invisible: nothing to do
+	const uint32_t r = tri < d.primCount ? d.triRect[tri] : TRI_RECT_NONE;
+	const bool small = !(r & TRI_RECT_BIG); // big: the blocks behind the small ones; invisible: nothing to do
 	const int rx0 = r & 0x1FF, ry0 = (r >> 9) & 0x3FF, rx1 = rx0 + ((r >> 19) & 1), ry1 = ry0 + ((r >> 20) & 1);
-	for(int ry = ry0; ry <= ry1; ry++)
-		for(int rx = rx0; rx <= rx1; rx++)
-		{
-			const uint32_t bin = region_bin(d, rx, ry);
-			d.pairs[d.binStart[bin] + (atomicSub(d.binCount + bin, 1u) - 1u)] = tri;
-		}
+	const bool wide = small && rx1 > rx0, tall = small && ry1 > ry0;
+	// warp-aggregated: one atomic per distinct bin of the warp's triangles
+	{
+		const uint32_t bin = small ? region_bin(d, rx0, ry0) : 0u;
+		const uint32_t slot = warp_bin_slot(d.binCount, small, bin);
+		if(small) d.pairs[d.binStart[bin] + slot] = tri;
+	}
+	if(__any_sync(0xFFFFFFFFu, wide))
+	{
+		const uint32_t bin = wide ? region_bin(d, rx1, ry0) : 0u;
+		const uint32_t slot = warp_bin_slot(d.binCount, wide, bin);
+		if(wide) d.pairs[d.binStart[bin] + slot] = tri;
+	}
+	if(__any_sync(0xFFFFFFFFu, tall))
+	{
+		const uint32_t bin = tall ? region_bin(d, rx0, ry1) : 0u;
+		const uint32_t slot = warp_bin_slot(d.binCount, tall, bin);
+		if(tall) d.pairs[d.binStart[bin] + slot] = tri;
+	}
+	if(__any_sync(0xFFFFFFFFu, wide && tall))
+	{
+		const uint32_t bin = (wide && tall) ? region_bin(d, rx1, ry1) : 0u;
+		const uint32_t slot = warp_bin_slot(d.binCount, wide && tall, bin);
+		if(wide && tall) d.pairs[d.binStart[bin] + slot] = tri;
+	}
 }
 
 // Ascending sort of n values with the bitonic network in its "all comparisons point the same way" form (the first step of
@@ -922,13 +981,14 @@ DEVI void bitonic_sort_any(uint32_t *a, uint32_t n, uint32_t tid, uint32_t nthre
 // bins too long for the tile kernel's own ordering step: one CTA per such bin, in shared memory when it fits
 #define SORTBIG_THREADS 256
 #define SORTBIG_SMEM 8192
-__global__ void __launch_bounds__(SORTBIG_THREADS) k_sortbig(const uint32_t *binStart, uint32_t *pairs, uint32_t numBins)
+__global__ void __launch_bounds__(SORTBIG_THREADS) k_sortbig(const uint32_t *binStart, uint32_t *pairs, const uint32_t *longBins, uint32_t longCap, const DrawCounters *c)
 {
 	__shared__ uint32_t s_buf[SORTBIG_SMEM];
-	for(uint32_t bin = blockIdx.x; bin < numBins; bin += gridDim.x)
+	const uint32_t nlong = min(c->longBins, longCap);
+	for(uint32_t e = blockIdx.x; e < nlong; e += gridDim.x)
 	{
+		const uint32_t bin = longBins[e];
 		const uint32_t b0 = binStart[bin], n = binStart[bin + 1] - b0;
-		if(n <= SWCU_SORT_CAP) continue; // (uniform for the CTA)
 		uint32_t *g = pairs + b0;
 		if(n <= SORTBIG_SMEM)
 		{
@@ -1356,11 +1416,15 @@ struct TileLayout
 	static constexpr int OWNER_B = REGION_PX * MS;      // uint8 owner[sample of the region]
 	static constexpr int SORT_B = 4 * SWCU_SORT_CAP;    // uint32 sorted[SWCU_SORT_CAP]
 	static constexpr int HEAD_B = 128;                  // the warp's mbarrier
-	__host__ __device__ static int warp_bytes(bool depth, bool stencil, int colorEpp)
+	// Per warp, at compile-time offsets: mbarrier | queue | owner | sorted | colour plane (one word per sample).  What depends on the
+	// draw's state — the further colour words of a floating-point target, the depth plane, the stencil plane — lies behind the four
+	// fixed parts, so the hot pointers need no run-time arithmetic (the compiler re-derived them inside the item loop otherwise).
+	static constexpr int FIXED_B = HEAD_B + Q_B + OWNER_B + SORT_B + PLANE_B;
+	__host__ __device__ static int var_bytes(bool depth, bool stencil, int colorEpp)
 	{
-		return HEAD_B + PLANE_B * colorEpp + (depth ? PLANE_B : 0) + (stencil ? ((STENCIL_B + 127) & ~127) : 0) + Q_B + OWNER_B + SORT_B;
+		return (colorEpp > 1 ? PLANE_B * colorEpp : 0) + (depth ? PLANE_B : 0) + (stencil ? ((STENCIL_B + 127) & ~127) : 0);
 	}
-	__host__ __device__ static int total(bool depth, bool stencil, int colorEpp = 1) { return SWCU_TILE_WARPS * warp_bytes(depth, stencil, colorEpp); }
+	__host__ __device__ static int total(bool depth, bool stencil, int colorEpp = 1) { return SWCU_TILE_WARPS * (FIXED_B + var_bytes(depth, stencil, colorEpp)); }
 };
 
 // writeColor for the RGBA8 family (PixelRoutine.cpp:1981-1992, :2603-2655): RoundInt(clamp(c, 0, 1) * 255) per channel,
@@ -1411,8 +1475,14 @@ DEVI uint32_t byte_range(int a, int b) { return b > a ? (0xFFFFFFFFu >> (32 - 8 
 // FS ("fast state"): the host has checked the common fixed-function state — no stencil, full colour write mask, RGBA byte
 // order, no depth bias, full sample mask, depth test off or LESS / LESS_OR_EQUAL, perspective slots routed one to one —
 // so none of it is decoded per fragment.  FS == false is the same code with every state read at run time.
+#ifndef TILE_CTAS_4X
+#define TILE_CTAS_4X 8
+#endif
+#ifndef TILE_CTAS_1X
+#define TILE_CTAS_1X 7
+#endif
 template<int MS, int SH, int BL, bool FS>
-__global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __grid_constant__ DrawConst d, const __grid_constant__ TileMaps maps)
+__global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CTAS_1X) k_tile(const __grid_constant__ DrawConst d, const __grid_constant__ TileMaps maps)
 {
 	using L = TileLayout<MS, SH>;
 	constexpr int FRONT4 = L::FRONT4, ICAP = L::ICAP;
@@ -1439,14 +1509,16 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 
 	const bool colorOn = FS ? true : (d.colorWriteMask != 0 && d.colorBuf != nullptr);
 	const int colorEpp = FS ? 1 : (int)d.colorEpp; // 32-bit words per colour pixel (floating-point targets: 2 or 4)
-	unsigned char *wa = smem + warp * L::warp_bytes(d.depthTestActive != 0, d.stencilActive != 0, colorEpp);
+	unsigned char *wa = smem + warp * L::FIXED_B;
 	uint64_t *bar = (uint64_t *)wa;
-	uint32_t *smColor = (uint32_t *)(wa + L::HEAD_B);
-	float *smDepth = (float *)(wa + L::HEAD_B + L::PLANE_B * colorEpp);
-	unsigned char *smStencil = wa + L::HEAD_B + L::PLANE_B * colorEpp + (d.depthTestActive ? L::PLANE_B : 0);
-	unsigned short *wQueue = (unsigned short *)(smStencil + (d.stencilActive ? ((L::STENCIL_B + 127) & ~127) : 0));
-	unsigned char *wOwner = (unsigned char *)wQueue + L::Q_B;
-	uint32_t *wSort = (uint32_t *)(wOwner + L::OWNER_B);
+	unsigned short *wQueue = (unsigned short *)(wa + L::HEAD_B);
+	unsigned char *wOwner = wa + L::HEAD_B + L::Q_B;
+	uint32_t *wSort = (uint32_t *)(wa + L::HEAD_B + L::Q_B + L::OWNER_B);
+	// the colour plane; a floating-point target (2 or 4 words per pixel, never with FS) lives in the variable part instead
+	unsigned char *wv = smem + SWCU_TILE_WARPS * L::FIXED_B + warp * L::var_bytes(d.depthTestActive != 0, d.stencilActive != 0, colorEpp);
+	uint32_t *smColor = (FS || colorEpp == 1) ? (uint32_t *)(wa + L::HEAD_B + L::Q_B + L::OWNER_B + L::SORT_B) : (uint32_t *)wv;
+	float *smDepth = (float *)(wv + ((FS || colorEpp == 1) ? 0 : L::PLANE_B * colorEpp));
+	unsigned char *smStencil = (unsigned char *)smDepth + (d.depthTestActive ? L::PLANE_B : 0);
 
 	// ---- stage the region: TMA when the attachments allow it ----
 	bool tileReady = true;
@@ -1478,6 +1550,10 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 	}
 
 	bool dirty = false;
+	uint32_t constChan = 0; // colour channels that are shader constants
+#pragma unroll
+	for(int ch = 0; ch < 4; ch++)
+		if(d.chanKind[ch] == CK_CONST) constChan |= 1u << ch;
 	const bool biasOn = FS ? false : d.depthBiasEnable != 0;
 	const bool bgr = FS ? false : d.bgr != 0;
 	uint32_t wmask32 = FS ? 0xFFFFFFFFu : 0u; // byte lanes of the packed pixel the draw may write
@@ -1515,6 +1591,47 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 					regId = keepMin ? min(regId, o) : max(regId, o);
 				}
 		}
+		else if(n <= 128)
+		{
+			// four entries per lane (element 4 * lane + i), bitonic network in registers: partners closer than 4 are in the same lane,
+			// the others one shuffle away; the sorted entries go to the warp's shared-memory list
+			uint32_t v[4];
+#pragma unroll
+			for(int i = 0; i < 4; i++) v[i] = (uint32_t)(4 * lane + i) < n ? __ldg(list + 4 * lane + i) : 0xFFFFFFFFu;
+#pragma unroll
+			for(int k = 2; k <= 128; k <<= 1)
+#pragma unroll
+				for(int j = k >> 1; j > 0; j >>= 1)
+				{
+					if(j >= 4)
+					{
+#pragma unroll
+						for(int i = 0; i < 4; i++)
+						{
+							const int e = 4 * lane + i;
+							const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, v[i], j >> 2);
+							const bool keepMin = ((e & j) == 0) == ((e & k) == 0);
+							v[i] = keepMin ? min(v[i], o) : max(v[i], o);
+						}
+					}
+					else
+					{
+#pragma unroll
+						for(int i = 0; i < 4; i++)
+						{
+							if(i & j) continue; // (i, i | j) is a comparator inside the lane
+							const int e = 4 * lane + i;
+							const bool up = (e & k) == 0;
+							const uint32_t lo = min(v[i], v[i | j]), hi = max(v[i], v[i | j]);
+							v[i] = up ? lo : hi;
+							v[i | j] = up ? hi : lo;
+						}
+					}
+				}
+			*(uint4 *)(wSort + 4 * lane) = make_uint4(v[0], v[1], v[2], v[3]);
+			__syncwarp();
+			sortedInSmem = true;
+		}
 		else if(n <= SWCU_SORT_CAP)
 		{
 			for(uint32_t i = lane; i < n; i += 32) wSort[i] = __ldg(list + i);
@@ -1524,16 +1641,32 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 		}
 	}
 
+	// ---- 32 bin entries at a time, one per lane; the ids and record headers of the next 32 are requested before the current ones
+	//      are used, and the plane equations of every entry are pulled into L2 ahead of the items that will read them ----
+	auto fetch_block = [&](uint32_t pos0, uint32_t &idOut, uint4 &hOut) {
+		const uint32_t li = pos0 + lane;
+		idOut = 0;
+		hOut = make_uint4(0, 0, 0, 0);
+		if(li < n)
+		{
+			idOut = d.direct ? li : (n <= 32 ? regId : (sortedInSmem ? wSort[li] : __ldg(list + li)));
+			const unsigned char *r = d.triRecords + (size_t)idOut * d.triStride;
+			hOut = __ldg((const uint4 *)r);
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(r + d.planeOffset));
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(r + d.triStride - 16));
+		}
+	};
+	uint32_t idN;
+	uint4 hN;
+	fetch_block(0, idN, hN);
 	for(uint32_t pos0 = 0; pos0 < n; pos0 += 32)
 	{
-		// ---- 32 bin entries, one per lane ----
 		const uint32_t li = pos0 + lane;
 		bool valid = li < n;
-		uint32_t id = 0;
-		if(valid) id = d.direct ? li : (n <= 32 ? regId : (sortedInSmem ? wSort[li] : __ldg(list + li)));
+		const uint32_t id = idN;
+		const uint4 h = hN;
+		if(pos0 + 32 < n) fetch_block(pos0 + 32, idN, hN);
 		const unsigned char *rec = d.triRecords + (size_t)id * d.triStride;
-		uint4 h = make_uint4(0, 0, 0, 0);
-		if(valid) h = __ldg((const uint4 *)rec);
 		bool isBig = valid && (h.y & TRI_FLAG_BIG);
 		if(valid)
 		{
@@ -1586,7 +1719,21 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 						a = clampi(Ls - rx, 0, SWCU_REGION_W); e = clampi(Rs - rx, 0, SWCU_REGION_W);
 					}
 				}
-				const int nn = e > a ? e - a : 0;
+				// pixel items: at 4x the four sample lanes of a row exchange their runs; lane q of the row takes the columns [4q, 4q + 4)
+				const uint32_t run = e > a ? ((1u << e) - 1u) & ~((1u << a) - 1u) : 0u; // columns of the region my (row, sample) covers
+				uint32_t cols, sm0 = run, sm1 = 0, sm2 = 0, sm3 = 0;
+				if(MS == 4)
+				{
+					const uint32_t r1 = __shfl_xor_sync(0xFFFFFFFFu, run, 1), r2 = __shfl_xor_sync(0xFFFFFFFFu, run, 2), r3 = __shfl_xor_sync(0xFFFFFFFFu, run, 3);
+					// runs by SAMPLE number: lane q holds sample q, its partner under xor j holds sample q ^ j
+					sm0 = q == 0 ? run : q == 1 ? r1 : q == 2 ? r2 : r3;
+					sm1 = q == 1 ? run : q == 0 ? r1 : q == 3 ? r2 : r3;
+					sm2 = q == 2 ? run : q == 3 ? r1 : q == 0 ? r2 : r3;
+					sm3 = q == 3 ? run : q == 2 ? r1 : q == 1 ? r2 : r3;
+					cols = (sm0 | sm1 | sm2 | sm3) & (0xFu << (4 * q));
+				}
+				else cols = run;
+				const int nn = __popc(cols);
 				uint32_t incl = (uint32_t)nn;
 #pragma unroll
 				for(int o = 1; o < 32; o <<= 1)
@@ -1594,10 +1741,16 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
 					if(lane >= o) incl += t;
 				}
-				total = __shfl_sync(0xFFFFFFFFu, incl, 31); // <= 32 runs of <= 16 pixels = ICAP at most
+				total = __shfl_sync(0xFFFFFFFFu, incl, 31); // <= 128 pixels (4x) / 32 runs of <= 16 pixels (1x): never more than ICAP
 				uint32_t w = incl - (uint32_t)nn;
-				const uint32_t item = ((uint32_t)(p + c) << 9) | ((uint32_t)q << 7) | ((uint32_t)row << 4);
-				for(int i = 0; i < nn; i++) wQueue[w++] = (unsigned short)(item | (uint32_t)(a + i));
+				const uint32_t item = ((uint32_t)(p + c) << 11) | ((uint32_t)row << 4);
+				while(cols)
+				{
+					const uint32_t x = (uint32_t)__ffs(cols) - 1u;
+					cols &= cols - 1u;
+					const uint32_t sm = MS == 4 ? (((sm0 >> x) & 1u) | (((sm1 >> x) & 1u) << 1) | (((sm2 >> x) & 1u) << 2) | (((sm3 >> x) & 1u) << 3)) : 1u;
+					wQueue[w++] = (unsigned short)(item | (sm << 7) | x);
+				}
 				p += group;
 			}
 			else
@@ -1623,7 +1776,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 						for(int r = 0; r < (MS == 4 ? 8 : 0); r++)
 						{
 							m[r] = (r >= rlo && r < rhi) ? (m[r] & keep) : 0u;
-							count += __popc(m[r]);
+							// items are PIXELS: a column counts once however many of its samples are covered
+							count += __popc((m[r] | (m[r] >> 8) | (m[r] >> 16) | (m[r] >> 24)) & 0xFFu);
 						}
 					}
 					else
@@ -1646,20 +1800,23 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 				total = __shfl_sync(0xFFFFFFFFu, incl, fitEnd - 1);
 				if(mine && lane < fitEnd && count)
 				{
-					// producer-side expansion: item = lane << 9 | sample << 7 | region row << 4 | region column
+					// producer-side expansion: item = lane << 11 | sample mask << 7 | region row << 4 | region column
 					uint32_t w = incl - count;
-					const uint32_t item0 = (uint32_t)((lane << 9) + (fy - ry) * 16 + (fx - rx));
+					const uint32_t item0 = (uint32_t)((lane << 11) + (fy - ry) * 16 + (fx - rx));
 					if(MS == 4)
 					{
 #pragma unroll
 						for(int r = 0; r < (MS == 4 ? 8 : 0); r++)
 						{
-							uint32_t bits = m[r];
-							while(bits)
+							const uint32_t mr = m[r];
+							uint32_t cols = (mr | (mr >> 8) | (mr >> 16) | (mr >> 24)) & 0xFFu;
+							while(cols)
 							{
-								const uint32_t b = (uint32_t)__ffs(bits) - 1u;
-								bits &= bits - 1u;
-								wQueue[w++] = (unsigned short)(item0 + 16u * r + ((b & 0x18u) << 4) + (b & 7u));
+								const uint32_t c = (uint32_t)__ffs(cols) - 1u;
+								cols &= cols - 1u;
+								// bit c of the four sample bytes -> a 4-bit sample mask (the partial products of the multiply do not collide)
+								const uint32_t sm = (((mr >> c) & 0x01010101u) * 0x01020408u) >> 24;
+								wQueue[w++] = (unsigned short)(item0 + 16u * r + c + (sm << 7));
 							}
 						}
 					}
@@ -1673,7 +1830,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 							{
 								const uint32_t b = (uint32_t)__ffs(bits) - 1u;
 								bits &= bits - 1u;
-								wQueue[w++] = (unsigned short)(item0 + 64u * j + ((b & 0x38u) << 1) + (b & 7u));
+								wQueue[w++] = (unsigned short)(item0 + (1u << 7) + 64u * j + ((b & 0x38u) << 1) + (b & 7u));
 							}
 						}
 					}
@@ -1686,24 +1843,53 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 				while(!mbar_try_wait(bar, 0)) {} // the TMA loads of the region have landed
 				tileReady = true;
 			}
-			// ---- consume the items 32 at a time, one covered sample per lane ----
+			// ---- consume the items 32 at a time, one covered PIXEL per lane: interpolation and the routed shader run once per pixel
+			//      (PixelRoutine.cpp:196-261), stencil / depth / blend / write once per covered sample of it (:124-148, :262-358) ----
 			for(uint32_t base = 0; base < total; base += 32)
 			{
 				const uint32_t g = base + lane;
 				const bool live = g < total;
 				const uint32_t e = live ? (uint32_t)wQueue[g] : 0u;
-				const int k = (int)(e >> 9);
+				const int k = (int)(e >> 11);
+				const uint32_t smask = MS == 4 ? (e >> 7) & 15u : 1u; // covered samples of the pixel
+				const uint32_t pkey = e & 0x7Fu;                        // pixel of the region: row << 4 | column
 				const uint32_t idk = __shfl_sync(0xFFFFFFFFu, id, k);
 				const uint32_t flagsk = FS ? 0u : __shfl_sync(0xFFFFFFFFu, h.y, k);
-				const uint32_t skey = e & 0x1FFu; // sample of the region: q << 7 | row << 4 | column
-				// two fragments of this round on one sample?  Every lane signs its sample; a lane that reads back another signature has company
-				if(live) wOwner[skey] = (unsigned char)lane;
-				__syncwarp();
-				const bool shared = live && wOwner[skey] != (unsigned char)lane;
-				int prank = 0, maxRank = 0;
-				if(__any_sync(0xFFFFFFFFu, shared)) // overlapping triangles: same-sample items of a round run in list order
+				// ---- plane equations of the item's triangle, requested before the conflict test below (the items of a triangle sit next
+				//      to each other in the queue, so a round reads two or three records) ----
+				const float4 *pl = (const float4 *)(d.triRecords + (size_t)idk * d.triStride + d.planeOffset);
+				float pf[FRONT4 * 4];
+				float4 zv = make_float4(0, 0, 0, 0); // zBias, zA, zB, zC
+				if(live)
 				{
-					const uint32_t peers = __match_any_sync(0xFFFFFFFFu, live ? skey : (0x200u | (uint32_t)lane));
+#pragma unroll
+					for(int t = 0; t < FRONT4; t++)
+					{
+						const float4 v = __ldg(pl + t);
+						pf[4 * t] = v.x; pf[4 * t + 1] = v.y; pf[4 * t + 2] = v.z; pf[4 * t + 3] = v.w;
+					}
+					if(d.depthTestActive) zv = __ldg(pl + FRONT4);
+				}
+				// two fragments of this round on one SAMPLE?  Every lane signs its samples; a lane that reads back another signature has
+				// company.  (Two triangles that share an edge pixel with disjoint samples — every edge of a mesh — are not a conflict.)
+				bool shared = false;
+				if(live)
+				{
+#pragma unroll
+					for(int q = 0; q < MS; q++)
+						if((smask >> q) & 1u) wOwner[q * REGION_PX + pkey] = (unsigned char)lane;
+				}
+				__syncwarp();
+				if(live)
+				{
+#pragma unroll
+					for(int q = 0; q < MS; q++)
+						if(((smask >> q) & 1u) && wOwner[q * REGION_PX + pkey] != (unsigned char)lane) shared = true;
+				}
+				int prank = 0, maxRank = 0;
+				if(__any_sync(0xFFFFFFFFu, shared)) // overlapping triangles: the items of a pixel run in list order
+				{
+					const uint32_t peers = __match_any_sync(0xFFFFFFFFu, live ? pkey : (0x200u | (uint32_t)lane));
 					prank = __popc(peers & laneLt);
 					maxRank = (int)__reduce_max_sync(0xFFFFFFFFu, (uint32_t)(live ? prank : 0));
 				}
@@ -1711,27 +1897,16 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 				{
 					if(live && prank == rr)
 					{
-						const int q = MS == 4 ? (int)((e >> 7) & 3u) : 0;
 						const int row = (int)((e >> 4) & 7u), bit = (int)(e & 15u);
 						const int x = rx + bit, y = ry + row;
 						const int ix = x & 1, iy = y & 1;
-						const int pi = (int)(MS == 4 ? skey : (skey & 0x7Fu)); // index inside the staged planes: q * 128 + row * 16 + column
-						// ---- plane equations of the triangle (through L1: the items of a triangle sit next to each other in the queue) ----
-						const float4 *pl = (const float4 *)(d.triRecords + (size_t)idk * d.triStride + d.planeOffset);
-						float pf[FRONT4 * 4];
-#pragma unroll
-						for(int t = 0; t < FRONT4; t++)
-						{
-							const float4 v = __ldg(pl + t);
-							pf[4 * t] = v.x; pf[4 * t + 1] = v.y; pf[4 * t + 2] = v.z; pf[4 * t + 3] = v.w;
-						}
 						const float x0 = pf[0], y0 = pf[1], wA = pf[2], wB = pf[3], wC = pf[4];
 						const float rhwConst = pf[5]; // 1/w of a constant w plane (k_setup), 0 otherwise
 						const float *S = pf + TRI_FLOATS_FRONT; // slot s: S[3s], S[3s+1], S[3s+2]
 						// ---- interpolate + routed fragment shader (PixelRoutine.cpp:196-261, PixelProgram.cpp:138-241) ----
 						const float xf = fsub((float)x, x0), yf = fsub((float)y, y0);
-						float rhw = 1.0f;
-						if(SH != SH_CONST) rhw = rhwConst != 0.0f ? rhwConst : fdiv(1.0f, __fmaf_rn(xf, wA, fadd(wC, fmul(yf, wB))));
+						float rhw = SH != SH_CONST ? rhwConst : 1.0f;
+						if(SH != SH_CONST && rhwConst == 0.0f) rhw = frcp(__fmaf_rn(xf, wA, fadd(wC, fmul(yf, wB)))); // (a branch: the division is ~10 instructions)
 						float texel[4] = { 0, 0, 0, 0 };
 						if(TEX)
 						{
@@ -1742,7 +1917,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 							for(int t = 0; t < 3; t++)
 							{
 								const float xk = fsub((float)(x - ix + (t & 1)), x0), yk = fsub((float)(y - iy + (t >> 1)), y0);
-								const float rk = rhwConst != 0.0f ? rhwConst : fdiv(1.0f, __fmaf_rn(xk, wA, fadd(wC, fmul(yk, wB))));
+								float rk = rhwConst;
+								if(rhwConst == 0.0f) rk = frcp(__fmaf_rn(xk, wA, fadd(wC, fmul(yk, wB))));
 								uu[t] = interp_slot(S[3 * UV], S[3 * UV + 1], S[3 * UV + 2], modeU, xk, yk, rk);
 								vv[t] = interp_slot(S[3 * UV + 3], S[3 * UV + 4], S[3 * UV + 5], modeV, xk, yk, rk);
 							}
@@ -1764,8 +1940,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 								else if(SH == SH_TEX) val = texel[ch];
 								else
 								{
-									val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], IM_PERSP, xf, yf, rhw);
-									if(d.chanKind[ch] == CK_CONST) val = __uint_as_float(d.chanValue[ch]);
+									if((constChan >> ch) & 1) val = __uint_as_float(d.chanValue[ch]);
+									else val = interp_slot(S[3 * ch], S[3 * ch + 1], S[3 * ch + 2], IM_PERSP, xf, yf, rhw);
 								}
 							}
 							else
@@ -1783,159 +1959,164 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? 8 : 7) k_tile(const __
 							// PixelProgram::clampColor :286-364 — UNORM targets only ("if the color attachment is floating-point, no clamping occurs")
 							rgba[ch] = (!FS && colorEpp > 1) ? val : sse_min(sse_max(val, 0.0f), 1.0f);
 						}
-
-						// ---- stencil test, depth test, depth write, blend + colour write, stencil write ----
-						bool sPass = true;
-						uint32_t sValue = 0;
 						const uint32_t frontFacing = FS ? 1u : (flagsk & TRI_FLAG_FRONT);
-						if(!FS && d.stencilActive)
+
+						// ---- per covered sample: stencil test, depth test, depth write, blend + colour write, stencil write ----
+#pragma unroll 1
+						for(int q = 0; q < MS; q++)
 						{
-							const KStencilFace &face = frontFacing ? d.front : d.back;
-							sValue = smStencil[pi];
-							sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
-						}
-						// alphaToCoverage (PixelRoutine.cpp:643-658, thresholds Renderer.cpp:391-410): CmpNLT = ordered >=, a NaN alpha loses its coverage; a
-						// sample that loses its coverage leaves every later stage, stencil write included (:319-326)
-						bool alive = true;
-						if(!FS && d.alphaToCoverage) alive = rgba[3] >= (MS == 4 ? (q == 0 ? 0.2f : q == 1 ? 0.4f : q == 2 ? 0.6f : 0.8f) : 0.5f);
-						bool zPass = true;
-						float z = 0.0f;
-						if(d.depthTestActive)
-						{
-							const float4 zv = __ldg(pl + FRONT4); // zBias, zA, zB, zC
-							float yy = yf, xx = xf;
-							if(MS > 1)
+							if(!((smask >> q) & 1u)) continue;
+							const int pi = q * REGION_PX + (int)pkey; // index inside the staged planes
+							bool sPass = true;
+							uint32_t sValue = 0;
+							if(!FS && d.stencilActive)
 							{
-								// sample position relative to the pixel centre (Constants.cpp:291-297), in eighths: Y = 2q - 3, X = {-1, 3, -3, 1}
-								const float sy = fmul((float)(2 * q - 3), 0.125f);
-								const float sx = fmul((float)(int)(signed char)(0x01FD03FFu >> (8 * q)), 0.125f);
-								yy = fadd(yy, sy);
-								xx = fsub(xx, sx);
+								const KStencilFace &face = frontFacing ? d.front : d.back;
+								sValue = smStencil[pi];
+								sPass = stencil_compare(face.compareOp, sValue & face.compareMask, face.reference & face.compareMask);
 							}
-							z = __fmaf_rn(xx, zv.y, fadd(zv.w, fmul(yy, zv.z)));
-							if(biasOn) z = fadd(z, zv.x);
-							z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
-							if(!FS && d.depth16)
+							// alphaToCoverage (PixelRoutine.cpp:643-658, thresholds Renderer.cpp:391-410): CmpNLT = ordered >=, a NaN alpha loses its coverage; a
+							// sample that loses its coverage leaves every later stage, stencil write included (:319-326)
+							bool alive = true;
+							if(!FS && d.alphaToCoverage) alive = rgba[3] >= (MS == 4 ? (q == 0 ? 0.2f : q == 1 ? 0.4f : q == 2 ? 0.6f : 0.8f) : 0.5f);
+							bool zPass = true;
+							float z = 0.0f;
+							if(d.depthTestActive)
 							{
-								// D16_UNORM (:466-482, :508-511): Z = Min(Max(Round(z * 0xFFFF), 0), 0xFFFF) against Float(UShort), as floats;
-								// the value written (:687-711, saturating UShort of Round(z * 0xFFFF)) is that same Z
-								z = sse_min(sse_max(rintf(fmul(z, 65535.0f)), 0.0f), 65535.0f);
-								zPass = depth_compare(d.depthCompareOp, (float)((const unsigned short *)smDepth)[pi], z);
-							}
-							else
-							{
-								const float zValue = smDepth[pi];
-								if(FS) zPass = d.depthCompareOp == CMP_LESS ? zValue > z : zValue >= z; // LESS / LESS_OR_EQUAL (:533-553)
-								else zPass = depth_compare(d.depthCompareOp, zValue, z);
-							}
-							if(!FS && d.depthBounds)
-							{
-								// depthBoundsTest :576-641: the STORED depth (read before this fragment's write) against [min, max]; with a depth
-								// test it narrows the depth mask, so the stencil depth-fail op sees it; without one it narrows the coverage
-								const float stored = d.depth16 ? fmul((float)((const unsigned short *)smDepth)[pi], 1.0f / 0xFFFF) : smDepth[pi];
-								const bool inside = d.minDepthBounds <= stored && stored <= d.maxDepthBounds;
-								if(d.depthBounds == 2) alive = alive && inside;
-								else zPass = zPass && inside;
-							}
-						}
-						if(alive && zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
-						{
-							if(d.depthWriteEnable)
-							{
-								if(!FS && d.depth16) ((unsigned short *)smDepth)[pi] = (unsigned short)z;
-								else smDepth[pi] = z;
-								dirty = true;
-							}
-							if(colorOn)
-							{
-								const bool floatTarget = !FS && colorEpp > 1;
-								const uint32_t px = floatTarget ? 0u : smColor[pi];
-								float o[4] = { rgba[0], rgba[1], rgba[2], rgba[3] };
-								if(BL != BL_OFF)
+								float yy = yf, xx = xf;
+								if(MS > 1)
 								{
-									float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
-									if(floatTarget)
-									{
-										// floating-point targets: the stored value itself (:1700-1710), or Reactor's Float(Half) (:1782-1801)
-										if(colorEpp == 4)
-										{
-											const float4 t = ((const float4 *)smColor)[pi];
-											dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
-										}
-										else
-										{
-											const uint2 t = ((const uint2 *)smColor)[pi];
-											dst[0] = half_to_float(t.x & 0xFFFFu); dst[1] = half_to_float(t.x >> 16);
-											dst[2] = half_to_float(t.y & 0xFFFFu); dst[3] = half_to_float(t.y >> 16);
-										}
-									}
-									else
-									{
-#pragma unroll
-										for(int ch = 0; ch < 4; ch++)
-										{
-											const uint32_t byte = (bgr && ch < 3) ? 2 - ch : ch;
-											dst[ch] = fmul((float)__byte_perm(px, 0, 0x4400u | byte | (byte << 4)), 1.0f / 0xFFFF); // b * 257 == b << 8 | b
-											if(!FS && d.srgb && ch < 3) dst[ch] = srgb_to_linear(dst[ch]);
-										}
-									}
-									if(BL == BL_SRC_ALPHA)
-									{
-										const float sa = rgba[3], da = fsub(1.0f, rgba[3]);
-#pragma unroll
-										for(int ch = 0; ch < 3; ch++) o[ch] = fadd(fmul(rgba[ch], sa), fmul(dst[ch], da));
-									}
-									else
-									{
-#pragma unroll
-										for(int ch = 0; ch < 3; ch++)
-											o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
-										o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
-									}
+									// sample position relative to the pixel centre (Constants.cpp:291-297), in eighths: Y = 2q - 3, X = {-1, 3, -3, 1}
+									const float sy = fmul((float)(2 * q - 3), 0.125f);
+									const float sx = fmul((float)(int)(signed char)(0x01FD03FFu >> (8 * q)), 0.125f);
+									yy = fadd(yy, sy);
+									xx = fsub(xx, sx);
 								}
-								if(!FS && d.srgb)
+								z = __fmaf_rn(xx, zv.y, fadd(zv.w, fmul(yy, zv.z)));
+								if(biasOn) z = fadd(z, zv.x);
+								z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
+								if(!FS && d.depth16)
 								{
-#pragma unroll
-									for(int ch = 0; ch < 3; ch++) o[ch] = linear_to_srgb(o[ch]);
-								}
-								if(floatTarget)
-								{
-									// masked store of the bits (:2429-2447), or of Reactor's Half(Float) (:2504-2540); no clamp, no rounding of fp32
-									const uint32_t cm = d.colorWriteMask;
-									if(colorEpp == 4)
-									{
-										float *t = (float *)smColor + 4 * pi;
-#pragma unroll
-										for(int ch = 0; ch < 4; ch++)
-											if((cm >> ch) & 1) t[ch] = o[ch];
-									}
-									else
-									{
-										unsigned short *t = (unsigned short *)smColor + 4 * pi;
-#pragma unroll
-										for(int ch = 0; ch < 4; ch++)
-											if((cm >> ch) & 1) t[ch] = (unsigned short)float_to_half(o[ch]);
-									}
+									// D16_UNORM (:466-482, :508-511): Z = Min(Max(Round(z * 0xFFFF), 0), 0xFFFF) against Float(UShort), as floats;
+									// the value written (:687-711, saturating UShort of Round(z * 0xFFFF)) is that same Z
+									z = sse_min(sse_max(rintf(fmul(z, 65535.0f)), 0.0f), 65535.0f);
+									zPass = depth_compare(d.depthCompareOp, (float)((const unsigned short *)smDepth)[pi], z);
 								}
 								else
 								{
-									const uint32_t pk = bgr ? pack_unorm8(o[2], o[1], o[0], o[3]) : pack_unorm8(o[0], o[1], o[2], o[3]);
-									smColor[pi] = (px & ~wmask32) | (pk & wmask32);
+									const float zValue = smDepth[pi];
+									if(FS) zPass = d.depthCompareOp == CMP_LESS ? zValue > z : zValue >= z; // LESS / LESS_OR_EQUAL (:533-553)
+									else zPass = depth_compare(d.depthCompareOp, zValue, z);
 								}
+								if(!FS && d.depthBounds)
+								{
+									// depthBoundsTest :576-641: the STORED depth (read before this fragment's write) against [min, max]; with a depth
+									// test it narrows the depth mask, so the stencil depth-fail op sees it; without one it narrows the coverage
+									const float stored = d.depth16 ? fmul((float)((const unsigned short *)smDepth)[pi], 1.0f / 0xFFFF) : smDepth[pi];
+									const bool inside = d.minDepthBounds <= stored && stored <= d.maxDepthBounds;
+									if(d.depthBounds == 2) alive = alive && inside;
+									else zPass = zPass && inside;
+								}
+							}
+							if(alive && zPass && sPass) // zMask (& sMask); without a depth test this is cMask & sMask
+							{
+								if(d.depthWriteEnable)
+								{
+									if(!FS && d.depth16) ((unsigned short *)smDepth)[pi] = (unsigned short)z;
+									else smDepth[pi] = z;
+									dirty = true;
+								}
+								if(colorOn)
+								{
+									const bool floatTarget = !FS && colorEpp > 1;
+									const uint32_t px = floatTarget ? 0u : smColor[pi];
+									float o[4] = { rgba[0], rgba[1], rgba[2], rgba[3] };
+									if(BL != BL_OFF)
+									{
+										float dst[4]; // readPixel :1111-1130: b -> b*257 -> float * (1/65535)
+										if(floatTarget)
+										{
+											// floating-point targets: the stored value itself (:1700-1710), or Reactor's Float(Half) (:1782-1801)
+											if(colorEpp == 4)
+											{
+												const float4 t = ((const float4 *)smColor)[pi];
+												dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+											}
+											else
+											{
+												const uint2 t = ((const uint2 *)smColor)[pi];
+												dst[0] = half_to_float(t.x & 0xFFFFu); dst[1] = half_to_float(t.x >> 16);
+												dst[2] = half_to_float(t.y & 0xFFFFu); dst[3] = half_to_float(t.y >> 16);
+											}
+										}
+										else
+										{
+#pragma unroll
+											for(int ch = 0; ch < 4; ch++)
+											{
+												const uint32_t byte = (bgr && ch < 3) ? 2 - ch : ch;
+												dst[ch] = fmul((float)__byte_perm(px, 0, 0x4400u | byte | (byte << 4)), 1.0f / 0xFFFF); // b * 257 == b << 8 | b
+												if(!FS && d.srgb && ch < 3) dst[ch] = srgb_to_linear(dst[ch]);
+											}
+										}
+										if(BL == BL_SRC_ALPHA)
+										{
+											const float sa = rgba[3], da = fsub(1.0f, rgba[3]);
+#pragma unroll
+											for(int ch = 0; ch < 3; ch++) o[ch] = fadd(fmul(rgba[ch], sa), fmul(dst[ch], da));
+										}
+										else
+										{
+#pragma unroll
+											for(int ch = 0; ch < 3; ch++)
+												o[ch] = blend_apply(d.op, rgba[ch], blend_factor_rgb(d, d.srcF, ch, rgba, dst), dst[ch], blend_factor_rgb(d, d.dstF, ch, rgba, dst));
+											o[3] = blend_apply(d.opA, rgba[3], blend_factor_a(d, d.srcFA, rgba, dst), dst[3], blend_factor_a(d, d.dstFA, rgba, dst));
+										}
+									}
+									if(!FS && d.srgb)
+									{
+#pragma unroll
+										for(int ch = 0; ch < 3; ch++) o[ch] = linear_to_srgb(o[ch]);
+									}
+									if(floatTarget)
+									{
+										// masked store of the bits (:2429-2447), or of Reactor's Half(Float) (:2504-2540); no clamp, no rounding of fp32
+										const uint32_t cm = d.colorWriteMask;
+										if(colorEpp == 4)
+										{
+											float *t = (float *)smColor + 4 * pi;
+#pragma unroll
+											for(int ch = 0; ch < 4; ch++)
+												if((cm >> ch) & 1) t[ch] = o[ch];
+										}
+										else
+										{
+											unsigned short *t = (unsigned short *)smColor + 4 * pi;
+#pragma unroll
+											for(int ch = 0; ch < 4; ch++)
+												if((cm >> ch) & 1) t[ch] = (unsigned short)float_to_half(o[ch]);
+										}
+									}
+									else
+									{
+										const uint32_t pk = bgr ? pack_unorm8(o[2], o[1], o[0], o[3]) : pack_unorm8(o[0], o[1], o[2], o[3]);
+										smColor[pi] = (px & ~wmask32) | (pk & wmask32);
+									}
+									dirty = true;
+								}
+							}
+							if(!FS && d.stencilWrite && alive) // writeStencil :754-817
+							{
+								const KStencilFace &face = frontFacing ? d.front : d.back;
+								const uint32_t ref = face.reference & 0xFF;
+								uint32_t nv;
+								if(!sPass) nv = stencil_op(face.failOp, sValue, ref);
+								else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
+								else nv = stencil_op(face.passOp, sValue, ref);
+								const uint32_t wm = face.writeMask & 0xFF;
+								smStencil[pi] = (unsigned char)((nv & wm) | (sValue & ~wm));
 								dirty = true;
 							}
-						}
-						if(!FS && d.stencilWrite && alive) // writeStencil :754-817
-						{
-							const KStencilFace &face = frontFacing ? d.front : d.back;
-							const uint32_t ref = face.reference & 0xFF;
-							uint32_t nv;
-							if(!sPass) nv = stencil_op(face.failOp, sValue, ref);
-							else if(!zPass) nv = stencil_op(face.depthFailOp, sValue, ref);
-							else nv = stencil_op(face.passOp, sValue, ref);
-							const uint32_t wm = face.writeMask & 0xFF;
-							smStencil[pi] = (unsigned char)((nv & wm) | (sValue & ~wm));
-							dirty = true;
 						}
 					}
 					__syncwarp();

@@ -123,7 +123,7 @@ struct DrawCounters
 	uint32_t overflow;              // bit1: big list full; bit2: a big triangle did not fit the pair budget
 	uint32_t visible;               // triangles that survived setup
 	uint32_t scanTicket;            // k_binscan: block tickets
-	uint32_t pad;
+	uint32_t longBins;              // bins longer than SWCU_SORT_CAP (k_binscan lists them for k_sortbig)
 };
 
 struct DrawConst
