@@ -1,16 +1,22 @@
 #!/usr/bin/env python
 """bench.py — the draw hot path on N B200s, one JSON line (see the contract in the task statement / DESIGN.md §Measurement).
 
-A "step" is one frame of the workload: every draw of the scene through swcu_draw (setup -> spans -> binning -> tile
-raster/shade/blend) plus, for the multisampled workload, the end-of-pass resolve; at N > 1 each rank renders its
-screen band (renderArea = band) and the finished bands are all-gathered over NCCL.  Attachments stay resident; the clear
-is outside the timed region, like the reference harness' LOAD pass (oracle/refrender.cpp --time).
+A "step" is one frame of the workload: every draw of the scene through swcu_draw (setup -> binning -> region raster / shade /
+blend) plus, for the multisampled workload, the end-of-pass resolve.  At N > 1 the GPUs form a group (swcu_group_*): every rank
+sets up 1/N of the triangles for the whole frame and stores the records into the owning rank's buffers over NVLink, renders its
+screen band, and the finished bands reach rank 0 by stores over NVLink (default) or an NCCL all-gather (SWCU_GATHER=nccl).
+Attachments stay resident; the clear is outside the timed region, like the reference harness' LOAD pass (oracle/refrender.cpp --time).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl cuda|reference]
+The headline workload is C4 (the largest single-GPU configuration of BASELINE.json); every run additionally measures C5 (the
+multi-GPU configuration: 10 M triangles at 8K) under "secondary", and checks the frame rank 0 holds against the sha256 of the
+reference ICD's own render of the same scene ("frame_hash_ok").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl cuda|reference] [--no-secondary]
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -24,6 +30,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Gpixels/s shaded+blended (also Mtris/s; HBM GB/s vs roofline)"
 DEFAULT_WORKLOAD = "c4"
+SECONDARY = {"c4": "c5"}  # the multi-GPU configuration of BASELINE.json rides along with the headline one
 
 
 def measured_peaks():
@@ -34,6 +41,14 @@ def measured_peaks():
         except Exception:  # noqa: BLE001
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernels_hash() -> str:
+    """sha256 (16 hex digits) of the kernel sources: ties profiles/traffic.json to the code it was captured from."""
+    h = hashlib.sha256()
+    for f in ("kernels.cuh", "draw.cu", "swcu_internal.h"):
+        h.update(open(os.path.join(ROOT, "swiftshader_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -98,14 +113,16 @@ def reference_time(wl, frames: int, warmup: int) -> dict:
     return out["timing"]
 
 
+EST_REF_MS = {"c1": 3, "c2": 4, "c3": 15, "c4": 700, "c5": 4000}
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
     from swiftshader_b200 import workloads
     wl = workloads.WORKLOADS[args.workload]()
     # bounded sample: the reference renders the whole frame K times; K is clamped so the run ends within minutes
-    est_ms = {"c1": 3, "c2": 4, "c3": 15, "c4": 700, "c5": 4000}[args.workload]
-    frames = max(1, min(args.steps, int(120000 / est_ms)))
+    frames = max(1, min(args.steps, int(120000 / EST_REF_MS[args.workload])))
     warm = max(1, min(args.warmup, 3))
     t = reference_time(wl, frames, warm)
     ms = t["mean_ms"]
@@ -122,6 +139,343 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+class _DevArr:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_rank: int, stream, with_e2e: bool = True, sustain_s: float = 1.0) -> dict:
+    """Everything bench.py measures for one workload; returns the pieces of the JSON line (only rank 0's copy is printed)."""
+    import ctypes as C
+    import dataclasses
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from swiftshader_b200 import bands, capi, workloads
+    from swiftshader_b200.scene import Device, Frame
+
+    wl = workloads.WORKLOADS[name]()
+    sc = wl.scene
+    H, W = sc.height, sc.width
+    band = bands.band_rows(H, N, rank)
+    area = bands.render_area(W, H, N, rank)
+    pitch = W * 4
+    H2 = sc.padded_height()
+    dev_s = f"cuda:{local_rank}"
+
+    dev = Device(local_rank)
+    dev.set_stream(stream.cuda_stream)
+    # N > 1: the group shards the setup of every draw by triangle range (SWCU_GROUP=0: every rank sets all triangles up itself)
+    group = None
+    if N > 1 and os.environ.get("SWCU_GROUP", "1") != "0":
+        group = bands.Group(dev, sc, N, rank, max(d.primitive_count() for d in sc.draws), 6, sc.samples)
+    frame = Frame(dev, sc, render_area=area)
+    frame.upload_inputs()
+    frame.clear()
+
+    # resolve only my band: attachments re-based to the band's first row
+    def band_att(host_arr, slice_b):
+        return capi.Attachment(host_arr.ctypes.data + band[0] * pitch, sc.colorFormat, pitch, slice_b, W, band[1] - band[0], 0)
+
+    src_b = band_att(frame.att["color"], H2 * pitch)
+    # The presentable 1x frames: a ring of three (MSAA: resolve targets; 1x at N > 1: copy targets on rank 0), so that frame i can
+    # still be on its way to the host while frame i + 1 is rendered into the next slot.  1x at N = 1: the colour attachment itself.
+    ring_n = 3 if (sc.samples > 1 or N > 1) else 1
+    finals = []
+    if sc.samples > 1:
+        finals.append(frame.resolved)
+    elif N > 1 and rank == 0:
+        finals.append(np.zeros((1, H2, W, 4), dtype=np.uint8))
+        dev.register(finals[0], upload=False)
+    while finals and len(finals) < ring_n and (rank == 0 or N == 1):
+        extra = np.zeros_like(finals[0])
+        dev.register(extra, upload=False)
+        finals.append(extra)
+    final_imgs = [f[0] for f in finals] if finals else [frame.att["color"][0]]
+    final_atts = [band_att(f, H2 * pitch) for f in finals]
+
+    # N > 1: how the finished bands reach rank 0.  "peer" (default): the end-of-pass resolve (4x) / a band copy (1x) of every
+    # rank stores straight into rank 0's frame of the current ring slot over NVLink (CUDA IPC mapping), ordered by flags — no
+    # collective on the data path.  "nccl": in-place NCCL all-gather of the bands (SWCU_GATHER=nccl).
+    gather = os.environ.get("SWCU_GATHER", "peer") if N > 1 else "none"
+    pg, full = None, None
+    if gather == "peer":
+        try:
+            pg = bands.PeerGather(dev, final_imgs if rank == 0 else [None] * ring_n, H, pitch, N, rank)
+            ok = 1
+        except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC not permitted in this container)
+            print(f"[bench] rank {rank}: peer delivery unavailable ({e}); falling back to the NCCL all-gather", file=sys.stderr)
+            pg, ok = None, 0
+        t_ok = torch.tensor([ok], device=dev_s)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        if int(t_ok.item()) == 0:
+            pg, gather = None, "nccl"
+    if gather == "nccl":
+        if sc.samples == 1 and N > 1:  # every rank needs a whole-frame buffer to gather into
+            if not finals:
+                finals.append(np.zeros((1, H2, W, 4), dtype=np.uint8))
+                dev.register(finals[0], upload=False)
+                final_imgs, final_atts = [finals[0][0]], [band_att(finals[0], H2 * pitch)]
+        full = torch.as_tensor(_DevArr(dev.device_ptr(final_imgs[0]), H * pitch), device=dev_s)
+        dev.set_option("copy_streams", 0)  # the all-gather writes the frame on the caller's stream, unseen by the library
+
+    state = {"i": 0}
+
+    def step(present=None, descs=None):
+        """One frame: draws, end-of-pass resolve / band copy into the presentable frame of the current slot, delivery to rank 0."""
+        i = state["i"]
+        state["i"] += 1
+        for d_ in (descs if descs is not None else frame.descs):
+            dev.draw(d_)
+        k = i % len(final_imgs)
+        if pg is not None:
+            pg.begin_frame()  # (ranks > 0: the frame that was in this slot must have been consumed)
+            dst = pg.band_destination(sc.colorFormat, W) if rank != 0 else final_atts[pg.slot]
+            if sc.samples > 1:
+                dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(dst)))
+            else:
+                dev.check(dev.lib.swcu_copy_image(dev.ctx, C.byref(src_b), C.byref(dst)))
+            pg.band_done()  # ranks > 0: announce; rank 0: the stream waits for the other ranks' bands
+            if rank == 0:
+                if present is not None:
+                    present(final_imgs[pg.slot])
+                pg.frame_consumed()
+            return
+        if sc.samples > 1:
+            dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(final_atts[0 if gather == "nccl" else k])))
+        elif gather == "nccl":
+            dev.check(dev.lib.swcu_copy_image(dev.ctx, C.byref(src_b), C.byref(final_atts[0])))
+        if gather == "nccl":
+            bands.gather_bands(full, H, pitch, N, rank)  # NCCL all-gather, in place: my band is already at its slot
+        if present is not None and rank == 0:
+            present(final_imgs[0 if gather == "nccl" else k])
+
+    def barrier():
+        if N > 1:
+            dist.barrier()
+
+    out = {"wl": wl, "band_rows": band[1] - band[0], "gather": gather, "group": group is not None}
+    with torch.cuda.stream(stream):
+        # ---- correctness first: ONE frame from cleared attachments, assembled on rank 0, against the reference ICD's own render ----
+        got = {}
+        step(present=lambda img: (dev.download(img), got.setdefault("img", img)))
+        dev.sync()
+        torch.cuda.synchronize()
+        barrier()
+        if rank == 0:
+            try:
+                want = json.load(open(os.path.join(ROOT, "tests", "golden", "workload_hashes.json")))[name]["hashes"]["color"]
+                out["frame_hash_ok"] = hashlib.sha256(np.ascontiguousarray(got["img"][:H]).tobytes()).hexdigest() == want
+            except (OSError, KeyError):
+                out["frame_hash_ok"] = None
+
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        dev.reset_stats()
+        # one event per frame boundary: the contract's value is total / K; the per-frame spread (p10 / p50 / p90) is reported too
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        torch.cuda.synchronize()
+        marks[0].record(stream)
+        for i in range(steps):
+            step()
+            marks[i + 1].record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms_total = marks[0].elapsed_time(marks[-1])
+        per_frame = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(steps))
+        pct = lambda q: per_frame[min(len(per_frame) - 1, int(q * len(per_frame)))]  # noqa: E731
+        out["frame_spread"] = {"p10": pct(0.10), "p50": pct(0.50), "p90": pct(0.90)}
+        out["stats"] = dev.stats()
+        t = torch.tensor([ms_total], device=dev_s)
+        if N > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["ms_step"] = float(t.item()) / steps
+        out["clocks"] = clocks.stop() if rank == 0 else None
+
+        # ---- the same loop sustained for >= 1 s: the burst above runs at boost clock, an issue-bound kernel follows the SM clock ----
+        if sustain_s > 0:
+            n_s = max(steps, int(sustain_s * 1e3 / max(out["ms_step"], 1e-3)) + 1)
+            sclk = ClockSampler(local_rank)
+            if rank == 0:
+                sclk.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(n_s):
+                step()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev_s)
+            if N > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ck = sclk.stop() if rank == 0 else None
+            out["sustained"] = {"ms_per_step": float(t.item()) / n_s, "steps": n_s, "seconds": float(t.item()) * 1e-3, "clocks": ck}
+
+        # ---- end to end through the C-ABI with HOST buffers: H2D of the step's inputs and D2H of the frame inside the timed region.
+        #      A render loop with several frames in flight, bounded by a fence per frame (a Vulkan application's per-frame vk::Fence):
+        #      the library's copy streams bring frame i+1's inputs up and frame i-1's pixels down while frame i renders.  At N > 1
+        #      every rank uploads 1/N of each input buffer over its own PCIe link and the slices are all-gathered over NVLink (NCCL);
+        #      rank 0 downloads the assembled frame from the ring ----
+        if with_e2e:
+            e2e_steps = max(6, min(steps, 30))
+            alt_inputs, alt_keep = [], []
+            alt_descs = [sc.build_desc(dataclasses.replace(dr, vertices=np.array(dr.vertices, dtype=np.float32, copy=True),
+                                                           indices=None if dr.indices is None else dr.indices.copy()),
+                                       frame.att, alt_keep, area, alt_inputs) for dr in sc.draws]
+            for b in alt_inputs:
+                dev.register(b, upload=False)
+            in_sets = [(frame.inputs, frame.descs), (alt_inputs, alt_descs)]
+            sharded_upload = N > 1 and os.environ.get("SWCU_SHARD_UPLOAD", "1") != "0"
+            if sharded_upload and gather != "nccl":
+                dev.set_option("copy_streams", 0)  # the input all-gather writes the shadows on the caller's stream
+            up_bytes = [0]
+
+            def upload_set(k):
+                for b in in_sets[k][0]:
+                    if not sharded_upload:
+                        dev.upload(b)
+                        up_bytes[0] += b.nbytes
+                        continue
+                    # my 1/N over PCIe, the rest over NVLink: all-gather of the 16-byte-aligned bulk, every rank uploads the small tail
+                    flat = b.reshape(-1).view(np.uint8)
+                    chunk = (flat.nbytes // N) & ~15
+                    if chunk:
+                        dev.check(dev.lib.swcu_mem_upload(dev.ctx, flat.ctypes.data + rank * chunk, chunk))
+                        whole = torch.as_tensor(_DevArr(dev.device_ptr(b), chunk * N), device=dev_s)
+                        dist.all_gather_into_tensor(whole, whole[rank * chunk:(rank + 1) * chunk])
+                    tail = flat.nbytes - chunk * N
+                    if tail:
+                        dev.check(dev.lib.swcu_mem_upload(dev.ctx, flat.ctypes.data + chunk * N, tail))
+                    up_bytes[0] += chunk + tail
+
+            F = len(final_imgs) if (rank == 0 or N == 1) else 2
+            state["i"] = 0
+            if pg is not None:  # the e2e loop starts on a slot boundary of the ring
+                while pg.frame_no % pg.slots:
+                    step()
+                dev.sync()
+                barrier()
+
+            def e2e_frame(i):
+                upload_set((i + 1) % 2)  # next frame's inputs, behind this frame's on the upload stream
+                if F == 1 and i >= 1 and rank == 0:
+                    dev.fence_wait((i - 1) % 2)  # the one host image: frame i-1 is consumed before frame i may land in it
+                step(present=lambda img: dev.download(img), descs=in_sets[i % 2][1])
+                dev.fence_signal(i % max(F, 2))
+                if F > 1 and i >= F - 1:
+                    dev.fence_wait((i - (F - 1)) % F)  # frame i - (F - 1) is on the host now
+
+            def e2e_run(n):
+                upload_set(0)  # frame 0's inputs; every frame of the loop uploads one set, so n frames move n sets
+                for i in range(n):
+                    e2e_frame(i)
+                dev.sync()
+
+            e2e_run(3)
+            barrier()
+            torch.cuda.synchronize()
+            up_bytes[0] = 0
+            t0 = time.perf_counter()
+            e2e_run(e2e_steps)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], device=dev_s)
+            if N > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out["e2e"] = {"ms_per_step": float(t.item()) * 1e3 / e2e_steps, "steps": e2e_steps, "frames_in_flight": max(F, 2),
+                          "h2d_bytes_per_step": int(up_bytes[0] / (e2e_steps + 1)) * N,  # all ranks together
+                          "h2d_bytes_per_step_per_gpu": int(up_bytes[0] / (e2e_steps + 1)),
+                          "d2h_bytes_per_step": H * pitch,
+                          "inputs": "1/N per rank over PCIe + NCCL all-gather over NVLink" if sharded_upload else "every rank uploads everything" if N > 1 else "uploaded"}
+            if sharded_upload and gather != "nccl":
+                dev.set_option("copy_streams", 1)
+
+        # ---- per-kernel device times (events around every launch) for the roofline of the dominant kernel ----
+        dev.set_profiling(True)
+        per = {}
+        for _ in range(5):
+            for d_ in frame.descs:
+                dev.draw(d_)
+                for kname, ms in dev.last_draw_kernels():
+                    per.setdefault(kname, []).append(ms)
+        dev.set_profiling(False)
+        dev.sync()
+        torch.cuda.synchronize()
+        barrier()
+    out["kernels"] = {k: statistics.mean(v) for k, v in per.items()}
+    if pg is not None:
+        pg.close()
+    frame.close()
+    for f in finals:
+        if f is not frame.resolved:
+            dev.unregister(f)
+    if group is not None:
+        group.close()
+    dev.close()
+    return out
+
+
+def workload_line(name: str, r: dict, N: int, steps: int, warmup: int) -> dict:
+    """The JSON pieces of one measured workload."""
+    wl = r["wl"]
+    sc = wl.scene
+    ms_step = r["ms_step"]
+    peak, peak_src = measured_peaks()
+    tile_name = "k_tile<4>" if sc.samples == 4 else "k_tile<1>"
+    tile_ms = r["kernels"].get(tile_name)
+    tile_bytes = wl.tile_bytes / N
+    achieved = tile_bytes / (tile_ms * 1e-3) / 1e9 if tile_ms else None
+    frame_bytes = wl.algorithmic_bytes if N == 1 else None
+    # DRAM bytes of the dominant kernel per launch, from the committed ncu capture of this workload — only while the kernel sources
+    # are the ones the capture was taken from (profiles/traffic.json carries their hash)
+    traffic, traffic_note = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if N == 1 and wl.name in tj and tj[wl.name]["kernel"] == tile_name:
+            if tj[wl.name].get("kernels_sha16") == kernels_hash():
+                traffic = tj[wl.name]["bytes"]
+                traffic_note = tj[wl.name].get("source")
+            else:
+                traffic_note = "stale: the kernel sources changed after the committed capture"
+    except (OSError, ValueError, KeyError):
+        pass
+    line = {
+        "value": wl.covered_pixels / (ms_step * 1e-3) / 1e9, "unit": "Gpixels/s", "ms_per_step": ms_step, "ms_per_step_spread": r["frame_spread"],
+        "mtris_per_s": wl.triangles / (ms_step * 1e-3) / 1e6,
+        "frame_hash_ok": r.get("frame_hash_ok"),
+        "config": {"workload": wl.name, "description": wl.description, "bands": N, "band_rows": r["band_rows"],
+                   "l2": "inputs larger than L2 (framebuffer + mesh + per-triangle records > 126 MB)" if wl.algorithmic_bytes > 200e6 else "working set fits L2; steady-state frames",
+                   "step": "draw (+ resolve)" + ("" if N == 1 else (" with the setup sharded by triangle range (records stored into the owning rank's buffers over NVLink)" if r["group"] else " with replicated setup")
+                                                 + (" + bands stored into rank 0's frame over NVLink (CUDA IPC) + flags" if r["gather"] == "peer" else " + NCCL all-gather of bands")),
+                   "gather": r["gather"], "group": r["group"]},
+        "clocks": r["clocks"],
+        "gpu_launches": int(r["stats"].kernelLaunches),
+        "gpu_launches_note": "kernels of libswcuda.so launched in the timed region (every kernel of the draw path is the library's own)",
+        "kernels_ms": r["kernels"],
+        "roofline": {"bound": "hbm", "kernel": tile_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": tile_bytes,
+                     "frame_algorithmic_bytes": frame_bytes,
+                     "frame_achieved": (frame_bytes / (ms_step * 1e-3) / 1e9) if frame_bytes else None,
+                     "frame_frac": (frame_bytes / (ms_step * 1e-3) / 1e9 / peak) if frame_bytes else None},
+    }
+    if "sustained" in r:
+        s = r["sustained"]
+        line["sustained"] = {"value": wl.covered_pixels / (s["ms_per_step"] * 1e-3) / 1e9, "unit": "Gpixels/s", "ms_per_step": s["ms_per_step"],
+                             "steps": s["steps"], "seconds": s["seconds"], "clocks": s["clocks"]}
+    if "e2e" in r:
+        e = r["e2e"]
+        line["e2e"] = {"value": wl.covered_pixels / (e["ms_per_step"] * 1e-3) / 1e9, "unit": "Gpixels/s", **e}
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -130,6 +484,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -143,13 +498,8 @@ def main():
     if args.steps is None:  # the 1080p-4K single triangles are launch-bound -> steady state over many back-to-back frames
         args.steps = 256 if args.workload in ("c1", "c2", "c3") else 50
 
-    import numpy as np
     import torch
     import torch.distributed as dist
-    from swiftshader_b200 import bands, workloads
-    from swiftshader_b200.scene import Device, Frame
-    from swiftshader_b200 import capi
-    import ctypes as C
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the draw path has no CPU fallback")
@@ -158,252 +508,29 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     N = world
-
-    wl = workloads.WORKLOADS[args.workload]()
-    sc = wl.scene
-    H, W = sc.height, sc.width
-    band = bands.band_rows(H, N, rank)
-    area = bands.render_area(W, H, N, rank)
-
-    dev = Device(local_rank)
     stream = torch.cuda.Stream()
-    dev.set_stream(stream.cuda_stream)
-    frame = Frame(dev, sc, render_area=area)
-    frame.upload_inputs()
-    frame.clear()
-    H2 = sc.padded_height()
-    pitch = W * 4
 
-    # resolve only my band: attachments re-based to the band's first row
-    def band_att(host_arr, slice_b):
-        return capi.Attachment(host_arr.ctypes.data + band[0] * pitch, sc.colorFormat, pitch, slice_b, W, band[1] - band[0], 0)
-
-    src_b = band_att(frame.att["color"], H2 * pitch)
-    dst_b = band_att(frame.resolved, H2 * pitch) if frame.resolved is not None else None
-
-    class _DevArr:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-    # N > 1: how the finished bands reach rank 0.  "peer" (default): the end-of-pass resolve (4x) / a band copy (1x) of every
-    # other rank stores straight into rank 0's frame over NVLink (CUDA IPC mapping), ordered by flags — no collective on the
-    # data path.  "nccl": in-place NCCL all-gather of the bands (SWCU_GATHER=nccl).
-    gather = os.environ.get("SWCU_GATHER", "peer") if N > 1 else "none"
-    full = None
-    pg = None
-    if gather == "nccl":
-        full = torch.as_tensor(_DevArr(frame.final_device_ptr(), H * pitch), device=f"cuda:{local_rank}")
-    elif gather == "peer":
-        try:
-            pg = bands.PeerGather(dev, frame.final_image(), H, pitch, N, rank)
-            ok = 1
-        except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC not permitted in this container)
-            print(f"[bench] rank {rank}: peer delivery unavailable ({e}); falling back to the NCCL all-gather", file=sys.stderr)
-            pg, ok = None, 0
-        t_ok = torch.tensor([ok], device=f"cuda:{local_rank}")
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        if int(t_ok.item()) == 0:
-            pg, gather = None, "nccl"
-            full = torch.as_tensor(_DevArr(frame.final_device_ptr(), H * pitch), device=f"cuda:{local_rank}")
-        elif rank != 0:
-            peer_dst = pg.band_destination(sc.colorFormat, W)
-
-    def step(present=None, descs=None):
-        for d_ in (descs if descs is not None else frame.descs):
-            dev.draw(d_)
-        if pg is not None and rank != 0:
-            pg.begin_frame()  # rank 0 must be done with the previous frame before its rows are overwritten
-            if dst_b is not None:
-                dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(peer_dst)))
-            else:
-                dev.check(dev.lib.swcu_copy_image(dev.ctx, C.byref(src_b), C.byref(peer_dst)))
-            pg.band_done()
-            return
-        if dst_b is not None:
-            dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(dst_b)))
-        if pg is not None:
-            pg.begin_frame()
-            pg.band_done()  # the stream waits for the other ranks' bands
-            if present is not None:
-                present()
-            pg.frame_consumed()
-            return
-        if gather == "nccl":
-            bands.gather_bands(full, H, pitch, N, rank)  # NCCL all-gather, in place: my band is already at its slot
-        if present is not None:
-            present()
-
-    def barrier():
-        if N > 1:
-            dist.barrier()
-
-    with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step()
-        torch.cuda.synchronize()
-        clocks = ClockSampler(local_rank)
-        if rank == 0:
-            clocks.start()
-        dev.reset_stats()
-        # one event per frame boundary: the contract's value is total / K; the per-frame spread (p10 / p50 / p90) is reported too
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        barrier()
-        torch.cuda.synchronize()
-        marks[0].record(stream)
-        for i in range(args.steps):
-            step()
-            marks[i + 1].record(stream)
-        torch.cuda.synchronize()
-        barrier()
-        ms_total = marks[0].elapsed_time(marks[-1])
-        per_frame = sorted(marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps))
-        pct = lambda q: per_frame[min(len(per_frame) - 1, int(q * len(per_frame)))]  # noqa: E731
-        frame_spread = {"p10": pct(0.10), "p50": pct(0.50), "p90": pct(0.90)}
-        st = dev.stats()
-        clock_info = clocks.stop() if rank == 0 else None
-        t = torch.tensor([ms_total], device=f"cuda:{local_rank}")
-        if N > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step = float(t.item()) / args.steps
-
-        # ---- end to end through the C-ABI with HOST buffers: H2D of the step's inputs and D2H of the frame inside the timed region.
-        #      A render loop with several frames in flight, bounded by a fence per frame (a Vulkan application's per-frame vk::Fence):
-        #      the library's copy streams bring frame i+1's inputs up and frame i-1's pixels down while frame i renders ----
-        e2e_steps = max(6, min(args.steps, 30))
-        if gather == "nccl":
-            dev.set_option("copy_streams", 0)  # the all-gather writes the frame on the caller's stream, unseen by the library
-        # Three stages overlap - frame i+1's inputs going up, frame i rendering, frame i-1 coming down - so the loop holds two
-        # sets of input buffers (per-frame dynamic vertex data, as an application double-buffers it) and, at N = 1 with MSAA,
-        # three resolve targets; a fence per frame bounds the frames in flight.
-        import dataclasses
-        alt_inputs, alt_keep = [], []
-        alt_descs = [sc.build_desc(dataclasses.replace(dr, vertices=np.array(dr.vertices, dtype=np.float32, copy=True),
-                                                       indices=None if dr.indices is None else dr.indices.copy()),
-                                   frame.att, alt_keep, area, alt_inputs) for dr in sc.draws]
-        for b in alt_inputs:
-            dev.register(b, upload=False)
-        in_sets = [(frame.inputs, frame.descs), (alt_inputs, alt_descs)]
-        skip = set(filter(None, os.environ.get("SWCU_E2E_SKIP", "").split(",")))  # diagnosis only: the reported e2e runs with nothing skipped
-
-        def upload_set(k):
-            for b in in_sets[k][0]:
-                dev.upload(b)
-
-        if N == 1:
-            outs, dsts = [frame.final_image()], [dst_b]
-            if dst_b is not None:
-                for _ in range(2):
-                    extra = np.zeros_like(frame.resolved)
-                    dev.register(extra, upload=False)
-                    outs.append(extra[0])
-                    dsts.append(band_att(extra, H2 * pitch))
-            F = len(outs)  # frames in flight (1x: the colour attachment itself is the only host-visible image)
-
-            def e2e_frame(i):
-                upload_set((i + 1) % 2)  # next frame's inputs, behind this frame's on the upload stream
-                for d_ in in_sets[i % 2][1]:
-                    dev.draw(d_)
-                k = i % F
-                if dsts[k] is not None:
-                    dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(dsts[k])))
-                if F == 1 and i >= 1:
-                    dev.fence_wait((i - 1) % 2)  # the one host image: frame i-1 is consumed before frame i may land in it
-                if "download" not in skip:
-                    dev.download(outs[k])
-                dev.fence_signal(i % max(F, 2))
-                if F > 1 and i >= F - 1:
-                    dev.fence_wait((i - (F - 1)) % F)  # frame i-2 is on the host now
-            frames_in_flight = max(F, 2)
-        else:
-            # rank 0's frame is the one host-visible image (the other ranks store their bands into it): frame i-1 is consumed
-            # before frame i comes down; the consumed flag leaves rank 0 from its download stream, so its next draw is not held back
-            def present(i):
-                if i >= 1:
-                    dev.fence_wait((i - 1) % 2)
-                frame.download_final()
-
-            def e2e_frame(i):
-                upload_set((i + 1) % 2)
-                step((lambda: present(i)) if rank == 0 else None, in_sets[i % 2][1])
-                dev.fence_signal(i % 2)
-                if rank != 0 and i >= 1:
-                    dev.fence_wait((i - 1) % 2)
-            frames_in_flight = 2
-
-        def e2e_run(n):
-            upload_set(0)  # frame 0's inputs; every frame of the loop uploads one set, so n frames move n sets
-            for i in range(n):
-                e2e_frame(i)
-            dev.sync()
-
-        e2e_run(3)
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_run(e2e_steps)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], device=f"cuda:{local_rank}")
-        if N > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item()) * 1e3 / e2e_steps
-        h2d = frame.input_bytes()
-        d2h = H * pitch
-
-        # ---- per-kernel device times (events around every launch) for the roofline of the dominant kernel ----
-        dev.set_profiling(True)
-        per = {}
-        prof_steps = 5
-        for _ in range(prof_steps):
-            frame.draw()
-            for name, ms in dev.last_draw_kernels():
-                per.setdefault(name, []).append(ms)
-        dev.set_profiling(False)
-        torch.cuda.synchronize()
-
-    kernels = {k: statistics.mean(v) for k, v in per.items()}
-    peak, peak_src = measured_peaks()
-    tile_name = "k_tile<4>" if sc.samples == 4 else "k_tile<1>"
-    tile_ms = kernels.get(tile_name)
-    tile_bytes = wl.tile_bytes / N
-    achieved = tile_bytes / (tile_ms * 1e-3) / 1e9 if tile_ms else None
-    frame_bytes = wl.algorithmic_bytes if N == 1 else None
-    traffic = None  # DRAM bytes of the dominant kernel per launch, from the committed ncu capture of this workload (if any)
-    try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")))
-        if N == 1 and wl.name in tj and tj[wl.name]["kernel"] == tile_name:
-            traffic = tj[wl.name]["bytes"]
-    except (OSError, ValueError, KeyError):
-        pass
+    primary = run_workload(args.workload, args.steps, args.warmup, rank, N, local_rank, stream)
+    secondary = None
+    sec_name = None if args.no_secondary else SECONDARY.get(args.workload)
+    if sec_name:
+        sec_steps = max(5, min(args.steps, 20))
+        secondary = run_workload(sec_name, sec_steps, args.warmup, rank, N, local_rank, stream, sustain_s=0.0)
 
     if rank == 0:
-        gpix = wl.covered_pixels / (ms_step * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": gpix, "unit": "Gpixels/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "ms_per_step_spread": frame_spread, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+u8 (fp32 setup/interpolation/blend, 24.8 fixed-point coverage, u16 sampler)",
-            "data": "synthetic",
-            "mtris_per_s": wl.triangles / (ms_step * 1e-3) / 1e6,
-            "config": {"workload": wl.name, "description": wl.description, "bands": N, "band_rows": band[1] - band[0],
-                       "l2": "inputs larger than L2 (framebuffer + mesh + per-triangle records > 126 MB)" if wl.algorithmic_bytes > 200e6 else "working set fits L2; steady-state frames",
-                       "step": "draw (+ resolve)" + ("" if N == 1 else " + bands stored into rank 0's frame over NVLink (CUDA IPC) + flags" if gather == "peer" else " + NCCL all-gather of bands"),
-                       "gather": gather},
-            "clocks": clock_info,
-            "e2e": {"value": wl.covered_pixels / (e2e_ms * 1e-3) / 1e9, "unit": "Gpixels/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "frames_in_flight": frames_in_flight},
-            "gpu_launches": int(st.kernelLaunches),
-            "gpu_launches_note": "kernels of libswcuda.so launched in the timed region (excludes the CUB scan/sort kernels between them)",
-            "kernels_ms": kernels,
-            "roofline": {"bound": "hbm", "kernel": tile_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": tile_bytes,
-                         "frame_algorithmic_bytes": frame_bytes,
-                         "frame_achieved": (frame_bytes / (ms_step * 1e-3) / 1e9) if frame_bytes else None,
-                         "frame_frac": (frame_bytes / (ms_step * 1e-3) / 1e9 / peak) if frame_bytes else None},
-        }
+        wl = primary["wl"]
+        body = workload_line(args.workload, primary, N, args.steps, args.warmup)
+        line = {"metric": METRIC, "value": body.pop("value"), "unit": body.pop("unit"), "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": body.pop("ms_per_step"), "ms_per_step_spread": body.pop("ms_per_step_spread"), "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32+u8 (fp32 setup/interpolation/blend, 24.8 fixed-point coverage, u16 sampler)", "data": "synthetic"}
+        line.update(body)
+        if secondary is not None:
+            sb = workload_line(sec_name, secondary, N, sec_steps, args.warmup)
+            sb["steps"] = sec_steps
+            line["secondary"] = sb
         if N == 1 and not args.no_cpu_baseline:
             try:
-                est_ms = {"c1": 3, "c2": 4, "c3": 15, "c4": 700, "c5": 4000}[args.workload]
-                frames = max(3, min(40, int(15000 / est_ms)))
+                frames = max(3, min(40, int(15000 / EST_REF_MS[args.workload])))
                 tm = reference_time(wl, frames, 1)
                 line["cpu_baseline"] = {"value": wl.covered_pixels / (tm["median_ms"] * 1e-3) / 1e9, "unit": "Gpixels/s", "cores": host_threads(),
                                         "kind": "reference", "ms_per_step": tm["median_ms"],
@@ -411,10 +538,6 @@ def main():
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "unit": "Gpixels/s", "cores": host_threads(), "kind": "reference", "sample": f"unavailable: {e}"}
         print(json.dumps(line), flush=True)
-    if pg is not None:
-        pg.close()
-    frame.close()
-    dev.close()
     if N > 1:
         dist.destroy_process_group()
 

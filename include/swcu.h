@@ -43,6 +43,7 @@ extern "C" {
 #define SWCU_MAX_SAMPLED_IMAGES 4  /* combined image samplers visible to the fragment shader */
 #define SWCU_MIPMAP_LEVELS 15      /* sw::MIPMAP_LEVELS, src/Device/Config.hpp */
 #define SWCU_MAX_VARYING_COMPONENTS 16
+#define SWCU_MAX_GROUP 8           /* GPUs of one box that share a frame (swcu_group_*) */
 
 typedef struct swcu_ctx swcu_ctx;
 
@@ -269,6 +270,29 @@ int swcu_copy_image(swcu_ctx *ctx, const swcu_attachment *src, const swcu_attach
 int swcu_signal(swcu_ctx *ctx, void *flag, uint32_t value);
 /* the stream waits until flags[first .. first+count) >= value (wrap-around compare), count <= 64 */
 int swcu_wait_flags(swcu_ctx *ctx, const void *flags, uint32_t first, uint32_t count, uint32_t value);
+
+/* ---- groups: the GPUs of one box render ONE frame — the setup of every draw is sharded by triangle range, the pixels by screen band ----
+ * Without a group, a rank that renders a band (renderArea = band) still fetches and projects every triangle of the draw.  In a group
+ * rank r sets up triangles [r n / world, (r + 1) n / world) for the WHOLE frame and stores each record, its bin counts and its big-list
+ * entry straight into the memory of the rank(s) whose band the triangle touches (CUDA IPC mappings of the peers' work buffers, NVLink
+ * stores and atomics); one flag barrier later every rank bins and rasterises what has arrived for its band.  All O(triangles) work
+ * is divided by the number of GPUs, and the only collective step of a draw is that barrier.
+ * Every rank: swcu_group_reserve (sizes its work buffers once, returns an IPC handle), exchange the handles (torch.distributed /
+ * MPI / a pipe: not this library's business), swcu_group_attach with all of them, in rank order.  From then on every BINNED swcu_draw
+ * must be issued by all ranks, in the same order, with renderArea = the rank's band of fbHeight / world rows and otherwise equal
+ * state; swcu_group_detach (after swcu_sync) ends it. */
+typedef struct swcu_group_desc
+{
+	uint32_t structSize;
+	uint32_t rank, world;        /* world <= SWCU_MAX_GROUP */
+	uint32_t maxPrimitives;      /* largest primitiveCount a group draw will have */
+	uint32_t maxSlots;           /* interpolated scalars the fragment shaders consume at most (0..6); sizes the triangle records */
+	uint32_t maxSamples;         /* 1 or 4 */
+	uint32_t fbWidth, fbHeight;  /* framebuffer extent of the group draws (the bins are laid out for it) */
+} swcu_group_desc;
+int swcu_group_reserve(swcu_ctx *ctx, const swcu_group_desc *desc, void *handle64 /* 64 bytes out */);
+int swcu_group_attach(swcu_ctx *ctx, const void *handles /* world * 64 bytes, rank order */);
+int swcu_group_detach(swcu_ctx *ctx);
 
 /* ---- narrow SPIR-V translator (host-only, no GPU needed) ---- */
 int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_shader_info *out, char *err, size_t errlen);

@@ -97,6 +97,11 @@ class Stats(C.Structure):
                 ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64), ("pairs", C.c_uint64)]
 
 
+class GroupDesc(C.Structure):
+    _fields_ = [("structSize", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32), ("maxPrimitives", C.c_uint32),
+                ("maxSlots", C.c_uint32), ("maxSamples", C.c_uint32), ("fbWidth", C.c_uint32), ("fbHeight", C.c_uint32)]
+
+
 EXPORTS = [
     "swcu_create", "swcu_destroy", "swcu_last_error",
     "swcu_mem_register", "swcu_mem_register_device", "swcu_mem_unregister", "swcu_mem_upload", "swcu_mem_download", "swcu_mem_device_ptr",
@@ -105,6 +110,7 @@ EXPORTS = [
     "swcu_set_profiling", "swcu_last_draw_kernels", "swcu_set_option", "swcu_version",
     "swcu_ipc_export", "swcu_ipc_open", "swcu_ipc_close", "swcu_copy_image", "swcu_signal", "swcu_wait_flags",
     "swcu_fence_signal", "swcu_fence_wait",
+    "swcu_group_reserve", "swcu_group_attach", "swcu_group_detach",
 ]
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -156,6 +162,9 @@ def lib() -> C.CDLL:
     L.swcu_wait_flags.argtypes = [vp, vp, u32, u32, u32]
     L.swcu_fence_signal.argtypes = [vp, u32]
     L.swcu_fence_wait.argtypes = [vp, u32]
+    L.swcu_group_reserve.argtypes = [vp, C.POINTER(GroupDesc), vp]
+    L.swcu_group_attach.argtypes = [vp, vp]
+    L.swcu_group_detach.argtypes = [vp]
     L.swcu_version.argtypes = []
     L.swcu_version.restype = C.c_char_p
     for name in EXPORTS:

@@ -78,6 +78,18 @@ struct swcu_ctx
 	int optCopyStreams = 1;
 	int optPipeline = 1;
 	DevBuf zeroPage;
+	// ---- group (swcu_group_*): the work buffers peers write into live in ONE allocation exported over CUDA IPC ----
+	struct Group
+	{
+		bool reserved = false, attached = false;
+		uint32_t rank = 0, world = 1, maxPrims = 0, stride = 0, fbW = 0, fbH = 0, numBins = 0;
+		size_t countersBytes = 0;
+		unsigned char *arena = nullptr;
+		size_t arenaBytes = 0;
+		size_t offRecords[2], offRect[2], offBig[2], offBinCount[2], offCounters[2], offFlags[2];
+		unsigned char *peer[SWCU_MAX_GROUP] = {}; // mapped arenas, [rank] = my own
+		uint32_t epoch[2] = { 0, 0 };
+	} group;
 	size_t optBigPairBudget = (size_t)16 << 20; // (region, triangle) pairs the big triangles of one draw may occupy
 	int lastOverflow = 0;
 	swcu_stats stats{};
@@ -193,6 +205,7 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 		if(kv.second.upEvent) cudaEventDestroy(kv.second.upEvent);
 	}
 	if(ctx->setupStream) cudaStreamSynchronize(ctx->setupStream);
+	swcu_group_detach(ctx);
 	cudaFree(ctx->zeroPage.p);
 	for(auto &S : ctx->set)
 	{
@@ -691,6 +704,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		d.scX1 = clampi_h(desc->scissor.x + (int)desc->scissor.width, x0, x1);
 		d.scY0 = clampi_h(desc->scissor.y, y0, y1);
 		d.scY1 = clampi_h(desc->scissor.y + (int)desc->scissor.height, y0, y1);
+		d.suY0 = d.scY0; d.suY1 = d.scY1; // (a group draw widens these to the scissor rows of the whole frame, see swcu_draw)
 	}
 	d.ms = (int)desc->sampleCount;
 	d.sampleMask = desc->sampleMask & (d.ms > 1 ? 0xFu : 0x1u); // Context.cpp:527: bit 0 counts at one sample per pixel too
@@ -871,6 +885,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	if((rc = att(desc->stencil, 1, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, "stencil"))) return rc;
 	d.scX0 = clampi_h(d.scX0, 0, d.fbWidth); d.scX1 = clampi_h(d.scX1, 0, d.fbWidth);
 	d.scY0 = clampi_h(d.scY0, 0, d.fbHeight); d.scY1 = clampi_h(d.scY1, 0, d.fbHeight);
+	d.suY0 = d.scY0; d.suY1 = d.scY1;
 
 	d.tilesX = (d.fbWidth + SWCU_TILE_W - 1) / SWCU_TILE_W;
 	d.tilesY = (d.fbHeight + SWCU_TILE_H - 1) / SWCU_TILE_H;
@@ -881,15 +896,6 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	d.triStride = swcu_tri_stride(d.nslots, d.ms, d.depthTestActive != 0);
 	if(vsrcErr) return vsrcErr;
 	return SWCU_OK;
-}
-
-// The counters of a draw's setup phase go to the host through its mapped pinned page, written by a kernel (a cudaMemcpyAsync
-// would queue in the device-to-host copy engine behind a frame download).  Nobody waits for them: they are looked at the next
-// time the host has drained the device anyway (swcu_sync), to report a big triangle that did not fit the pair budget.
-__global__ void k_report(const DrawCounters *c, DrawCounters *hostOut)
-{
-	*hostOut = *c;
-	__threadfence_system();
 }
 
 // ---- TMA descriptors of the attachments: a 3-D tensor (x, y, sample plane) with a (region width, region height, samples) box ----
@@ -1008,18 +1014,24 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	ctx->stats.draws++;
 	ctx->stats.primitives += d.primCount;
 	if(ctx->profiling) { ctx->lastKernels.clear(); ctx->eventsUsed = 0; }
-	if(d.primCount == 0 || d.scX0 >= d.scX1 || d.scY0 >= d.scY1 || d.sampleMask == 0) return SWCU_OK; // no sample enabled: PixelRoutine.cpp:104-111
+	if(d.primCount == 0 || d.sampleMask == 0) return SWCU_OK; // no sample enabled: PixelRoutine.cpp:104-111
+	// (an empty render area ends the draw here too — unless this rank is a member of a group: its share of the setup and the barrier of the draw are still due)
+	if((d.scX0 >= d.scX1 || d.scY0 >= d.scY1) && !(ctx->group.attached && (ctx->optForceBinned || (int)d.primCount > ctx->optDirectMax))) return SWCU_OK;
 	if((unsigned long long)d.primCount * d.triStride > (1ull << 36)) return fail(ctx, SWCU_E_NOMEM, "draw too large");
 
 	const uint32_t n = d.primCount;
 	d.direct = (!ctx->optForceBinned && (int)n <= ctx->optDirectMax) ? 1u : 0u;
+	swcu_ctx::Group &G = ctx->group;
+	const bool grouped = G.attached && !d.direct;
 	// The setup phase of this draw uses the set the draw before the previous one used.  A binned draw runs it on the setup
 	// stream: it waits only for the inputs (last upload) and for the last reader of this set, not for the tile kernel of the
-	// previous draw.  Direct draws, profiling mode (per-kernel events) and inputs in caller-owned device memory (whose producers
-	// the library cannot see) stay on the main stream.  No step of a draw waits for the host.
-	swcu_ctx::SetupSet &S = ctx->set[ctx->cur];
+	// previous draw.  Direct draws, group draws (whose buffers the PEERS write: everything stays in one stream's order), profiling
+	// mode (per-kernel events) and inputs in caller-owned device memory (whose producers the library cannot see) stay on the main
+	// stream.  No step of a draw waits for the host.
+	const int setIndex = ctx->cur;
+	swcu_ctx::SetupSet &S = ctx->set[setIndex];
 	ctx->cur ^= 1;
-	const bool pipelined = !d.direct && ctx->optPipeline && !ctx->profiling && !d.inputsExternal;
+	const bool pipelined = !d.direct && !grouped && ctx->optPipeline && !ctx->profiling && !d.inputsExternal;
 	const cudaStream_t ss = pipelined ? ctx->setupStream : ctx->stream;
 	if(pipelined)
 	{
@@ -1043,15 +1055,60 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	const size_t countersBytes = sizeof(DrawCounters) + 4 * (scanBlocks + 1);
 	const size_t pairCap = d.direct ? 0 : std::min<size_t>((size_t)4 * n + ctx->optBigPairBudget, 0x3FFFFFF0u);
 	if(!d.direct && pairCap < (size_t)4 * n) return fail(ctx, SWCU_E_NOMEM, "%u triangles exceed the pair index space", n);
-	if((rc = ensure(ctx, S.triRecords, (size_t)n * d.triStride))) return rc;
-	if((rc = ensure(ctx, S.triRect, (size_t)n * 4))) return rc;
-	if((rc = ensure(ctx, S.bigList, (size_t)n * sizeof(BigTri)))) return rc; // every triangle may be a big one
-	if((rc = ensure(ctx, S.counters, countersBytes))) return rc;
+	d.world = 1; d.rank = 0; d.triLo = 0; d.triHi = n; d.bandRows = d.fbHeight;
+	if(grouped)
+	{
+		// the buffers the peers write lie in the exported arena; this rank sets up its share of the triangles for the whole frame
+		if(n > G.maxPrims || d.triStride > G.stride || (uint32_t)d.fbWidth != G.fbW || (uint32_t)d.fbHeight != G.fbH || countersBytes > G.countersBytes)
+			return fail(ctx, SWCU_E_INVALID, "group draw outside what swcu_group_reserve sized (%u triangles of %u bytes, %dx%d)", n, d.triStride, d.fbWidth, d.fbHeight);
+		if(d.fbHeight % (int)G.world) return fail(ctx, SWCU_E_INVALID, "framebuffer height %d does not split into %u bands", d.fbHeight, G.world);
+		d.world = G.world; d.rank = G.rank; d.bandRows = d.fbHeight / (int)G.world;
+		if(d.bandRows < 2 * SWCU_REGION_H) return fail(ctx, SWCU_E_UNSUPPORTED, "bands of %d rows are too small for a group", d.bandRows);
+		d.triLo = (uint32_t)((unsigned long long)n * G.rank / G.world);
+		d.triHi = (uint32_t)((unsigned long long)n * (G.rank + 1) / G.world);
+		d.suY0 = clampi_h(desc->scissor.y, 0, d.fbHeight);
+		d.suY1 = clampi_h(desc->scissor.y + (int)desc->scissor.height, 0, d.fbHeight);
+		// my rows: my band of the scissor (NOT the render area the caller passed, which must be that band)
+		d.scY0 = clampi_h(d.suY0, (int)G.rank * d.bandRows, (int)(G.rank + 1) * d.bandRows);
+		d.scY1 = clampi_h(d.suY1, (int)G.rank * d.bandRows, (int)(G.rank + 1) * d.bandRows);
+		d.tileY0 = d.scY0 / SWCU_TILE_H; d.tileY1 = (d.scY1 + SWCU_TILE_H - 1) / SWCU_TILE_H;
+		for(uint32_t p = 0; p < G.world; p++)
+		{
+			d.peerRecords[p] = G.peer[p] + G.offRecords[setIndex];
+			d.peerRect[p] = (uint32_t *)(G.peer[p] + G.offRect[setIndex]);
+			d.peerBig[p] = (BigTri *)(G.peer[p] + G.offBig[setIndex]);
+			d.peerBinCount[p] = (uint32_t *)(G.peer[p] + G.offBinCount[setIndex]);
+			d.peerCounters[p] = (DrawCounters *)(G.peer[p] + G.offCounters[setIndex]);
+		}
+		d.triRecords = d.peerRecords[G.rank];
+		d.triRect = d.peerRect[G.rank];
+		d.bigList = d.peerBig[G.rank];
+		d.bigCapacity = G.maxPrims;
+		d.binCount = d.peerBinCount[G.rank];
+		d.counters = d.peerCounters[G.rank];
+	}
+	else
+	{
+		if((rc = ensure(ctx, S.triRecords, (size_t)n * d.triStride))) return rc;
+		if((rc = ensure(ctx, S.triRect, (size_t)n * 4))) return rc;
+		if((rc = ensure(ctx, S.bigList, (size_t)n * sizeof(BigTri)))) return rc; // every triangle may be a big one
+		if((rc = ensure(ctx, S.counters, countersBytes))) return rc;
+		if(!d.direct)
+		{
+			const size_t before = S.binCount.cap;
+			if((rc = ensure(ctx, S.binCount, (size_t)d.numBins * 4))) return rc;
+			if(S.binCount.cap != before) CU(cudaMemsetAsync(S.binCount.p, 0, S.binCount.cap, ss)); // k_fill counts every bin back down to zero
+		}
+		d.triRecords = (unsigned char *)S.triRecords.p;
+		d.triRect = (uint32_t *)S.triRect.p;
+		d.counters = (DrawCounters *)S.counters.p;
+		d.bigList = (BigTri *)S.bigList.p;
+		d.bigCapacity = (uint32_t)std::min<size_t>(S.bigList.cap / sizeof(BigTri), 0x7FFFFFFFu);
+		d.binCount = (uint32_t *)S.binCount.p;
+		d.peerRecords[0] = d.triRecords; d.peerRect[0] = d.triRect; d.peerBig[0] = d.bigList; d.peerBinCount[0] = d.binCount; d.peerCounters[0] = d.counters;
+	}
 	if(!d.direct)
 	{
-		const size_t before = S.binCount.cap;
-		if((rc = ensure(ctx, S.binCount, (size_t)d.numBins * 4))) return rc;
-		if(S.binCount.cap != before) CU(cudaMemsetAsync(S.binCount.p, 0, S.binCount.cap, ss)); // k_fill counts every bin back down to zero
 		if((rc = ensure(ctx, S.binStart, ((size_t)d.numBins + 1) * 4))) return rc;
 		if((rc = ensure(ctx, S.pairs, pairCap * 4))) return rc;
 		if((rc = ensure(ctx, S.longBins, (pairCap / SWCU_SORT_CAP + 1) * 4))) return rc; // more bins than that cannot be long
@@ -1062,34 +1119,41 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		CU(cudaMemsetAsync(ctx->zeroPage.p, 0, 256, ctx->stream));
 		CU(cudaStreamSynchronize(ctx->stream));
 	}
-	d.triRecords = (unsigned char *)S.triRecords.p;
-	d.triRect = (uint32_t *)S.triRect.p;
-	d.counters = (DrawCounters *)S.counters.p;
 	d.zeroPage = ctx->zeroPage.p;
-	d.bigList = (BigTri *)S.bigList.p;
-	d.bigCapacity = (uint32_t)std::min<size_t>(S.bigList.cap / sizeof(BigTri), 0x7FFFFFFFu);
-	d.binCount = (uint32_t *)S.binCount.p;
 	d.binStart = (uint32_t *)S.binStart.p;
 	d.pairs = (uint32_t *)S.pairs.p;
 	d.bigBudget = d.direct ? 0 : pairCap - (size_t)4 * n;
-	const dim3 tileGrid((unsigned)(d.tileX1 - d.tileX0), (unsigned)(d.tileY1 - d.tileY0));
+	const dim3 tileGrid((unsigned)std::max(d.tileX1 - d.tileX0, 0), (unsigned)std::max(d.tileY1 - d.tileY0, 0));
 
-	CU(cudaMemsetAsync(d.counters, 0, countersBytes, ss));
-	// band mode: the scissor / render area keeps less than 3/4 of the framebuffer rows (a rank of a multi-GPU frame)
+	// (a group member's counters and rectangles were reset behind the last draw that used this set: peers may be writing already)
+	if(!grouped) CU(cudaMemsetAsync(d.counters, 0, countersBytes, ss));
+	// band mode without a group: the scissor / render area keeps less than 3/4 of the framebuffer rows
 	d.cullFlags = nullptr;
-	if(!d.direct && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
+	if(!d.direct && !grouped && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
 	{
 		if((rc = ensure(ctx, S.cullFlags, n))) return rc;
 		LaunchScope ls(ctx, "k_cull", ss);
 		k_cull<<<(n + 255) / 256, 256, 0, ss>>>(d, (unsigned char *)S.cullFlags.p);
 		d.cullFlags = (const unsigned char *)S.cullFlags.p;
 	}
+	if(d.triHi > d.triLo)
 	{
 		LaunchScope ls(ctx, "k_setup", ss);
+		const uint32_t share = d.triHi - d.triLo;
 		const size_t scratch = (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4;
-		if(d.ms != 1) k_setup<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
-		else k_setup_1x<<<(n + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
+		if(d.ms != 1) k_setup<<<(share + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
+		else k_setup_1x<<<(share + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
 	}
+	if(grouped)
+	{
+		// every rank's share has to be in my buffers before I bin: the one collective step of a group draw
+		GroupFlags gf;
+		memset(&gf, 0, sizeof(gf));
+		for(uint32_t p = 0; p < G.world; p++) gf.flags[p] = (uint32_t *)(G.peer[p] + G.offFlags[setIndex]);
+		LaunchScope ls(ctx, "k_xbarrier", ss);
+		k_xbarrier<<<1, 32, 0, ss>>>(gf, G.world, G.rank, ++G.epoch[setIndex]);
+	}
+	const bool nothingToDraw = d.scX0 >= d.scX1 || d.scY0 >= d.scY1; // (only a group member gets here with an empty band)
 	if(!d.direct)
 	{
 		// ---- binning: count (k_setup + k_bigcount), scan, fill, order the long bins; all sized on the host, all asynchronous ----
@@ -1110,11 +1174,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		}
 		{
 			LaunchScope ls(ctx, "k_sortbig", ss);
-			k_sortbig<<<148, SORTBIG_THREADS, 0, ss>>>(d.binStart, d.pairs, (const uint32_t *)S.longBins.p, (uint32_t)(pairCap / SWCU_SORT_CAP + 1), d.counters);
-		}
-		{
-			LaunchScope ls(ctx, "k_report", ss);
-			k_report<<<1, 1, 0, ss>>>(d.counters, S.hostCounters);
+			k_sortbig<<<148, SORTBIG_THREADS, 0, ss>>>(d.binStart, d.pairs, (const uint32_t *)S.longBins.p, (uint32_t)(pairCap / SWCU_SORT_CAP + 1), d.counters, S.hostCounters);
 			S.countersPending = true;
 		}
 		if(pipelined)
@@ -1137,11 +1197,102 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		if(ok && d.stencilActive) ok = get_tensor_map(ctx, &maps.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, d.fbWidth, d.fbHeight, d.ms, 1);
 		d.useTma = ok ? 1u : 0u;
 	}
-	if(d.ms == 4) launch_tile<4>(ctx, d, maps, tileGrid); else launch_tile<1>(ctx, d, maps, tileGrid);
+	if(!nothingToDraw) { if(d.ms == 4) launch_tile<4>(ctx, d, maps, tileGrid); else launch_tile<1>(ctx, d, maps, tileGrid); }
 	CU(cudaGetLastError());
+	if(grouped)
+	{
+		// reset what the peers will write into two draws from now: their next share arrives behind the barrier of the draw in between
+		CU(cudaMemsetAsync(d.counters, 0, G.countersBytes, ctx->stream));
+		CU(cudaMemsetAsync(d.triRect, 0xFF, (size_t)n * 4, ctx->stream));
+	}
 	CU(cudaEventRecord(S.tileDone, ctx->stream)); // last reader of this set's records / bins
 	S.tileDoneValid = true;
 	return SWCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// groups: work buffers in one IPC-exported allocation per rank, mapped by every peer
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int swcu_group_reserve(swcu_ctx *ctx, const swcu_group_desc *g, void *handle64)
+{
+	if(!ctx || !g || !handle64 || g->structSize != sizeof(swcu_group_desc)) return fail(ctx, SWCU_E_INVALID, "swcu_group_reserve: bad argument");
+	if(g->world < 1 || g->world > SWCU_MAX_GROUP || g->rank >= g->world) return fail(ctx, SWCU_E_INVALID, "swcu_group_reserve: rank %u of %u", g->rank, g->world);
+	if(g->maxSlots > SWCU_MAXSLOTS || (g->maxSamples != 1 && g->maxSamples != 4) || !g->maxPrimitives || !g->fbWidth || !g->fbHeight || g->fbWidth > 8192 || g->fbHeight > 8192)
+		return fail(ctx, SWCU_E_INVALID, "swcu_group_reserve: bad sizes");
+	swcu_ctx::Group &G = ctx->group;
+	if(G.reserved) return fail(ctx, SWCU_E_INVALID, "swcu_group_reserve: a group is already reserved on this context");
+	CU(cudaSetDevice(ctx->device));
+	G.rank = g->rank; G.world = g->world; G.maxPrims = g->maxPrimitives; G.fbW = g->fbWidth; G.fbH = g->fbHeight;
+	G.stride = swcu_tri_stride((int)g->maxSlots, (int)g->maxSamples, 1);
+	const uint32_t tilesX = (G.fbW + SWCU_TILE_W - 1) / SWCU_TILE_W, tilesY = (G.fbH + SWCU_TILE_H - 1) / SWCU_TILE_H;
+	G.numBins = tilesX * tilesY * 4;
+	const size_t scanBlocks = ((size_t)G.numBins + SCAN_THREADS * SCAN_ITEMS - 1) / (SCAN_THREADS * SCAN_ITEMS);
+	G.countersBytes = (sizeof(DrawCounters) + 4 * (scanBlocks + 1) + 255) & ~(size_t)255;
+	size_t off = 0;
+	auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+	for(int k = 0; k < 2; k++)
+	{
+		G.offRecords[k] = take((size_t)G.maxPrims * G.stride);
+		G.offRect[k] = take((size_t)G.maxPrims * 4);
+		G.offBig[k] = take((size_t)G.maxPrims * sizeof(BigTri));
+		G.offBinCount[k] = take((size_t)G.numBins * 4);
+		G.offCounters[k] = take(G.countersBytes);
+		G.offFlags[k] = take(SWCU_MAX_GROUP * 4);
+	}
+	G.arenaBytes = off;
+	cudaError_t e = cudaMalloc((void **)&G.arena, G.arenaBytes);
+	if(e != cudaSuccess) { cudaGetLastError(); return fail(ctx, SWCU_E_NOMEM, "cudaMalloc(%zu) for the group arena failed: %s", G.arenaBytes, cudaGetErrorString(e)); }
+	CU(cudaMemsetAsync(G.arena, 0, G.arenaBytes, ctx->stream));
+	for(int k = 0; k < 2; k++) CU(cudaMemsetAsync(G.arena + G.offRect[k], 0xFF, (size_t)G.maxPrims * 4, ctx->stream)); // TRI_RECT_NONE
+	CU(cudaStreamSynchronize(ctx->stream));
+	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, G.arena));
+	G.reserved = true;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_group_attach(swcu_ctx *ctx, const void *handles)
+{
+	if(!ctx || !handles) return fail(ctx, SWCU_E_INVALID, "swcu_group_attach: null argument");
+	swcu_ctx::Group &G = ctx->group;
+	if(!G.reserved || G.attached) return fail(ctx, SWCU_E_INVALID, "swcu_group_attach: reserve first, attach once");
+	CU(cudaSetDevice(ctx->device));
+	int rc = swcu_sync(ctx);
+	if(rc) return rc;
+	for(uint32_t p = 0; p < G.world; p++)
+	{
+		if(p == G.rank) { G.peer[p] = G.arena; continue; }
+		cudaIpcMemHandle_t h;
+		memcpy(&h, (const unsigned char *)handles + 64 * (size_t)p, sizeof(h));
+		void *base = nullptr;
+		cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+		if(e != cudaSuccess)
+		{
+			cudaGetLastError();
+			for(uint32_t q = 0; q < p; q++)
+				if(q != G.rank && G.peer[q]) { cudaIpcCloseMemHandle(G.peer[q]); G.peer[q] = nullptr; }
+			return fail(ctx, SWCU_E_CUDA, "cudaIpcOpenMemHandle of rank %u's work buffers failed: %s", p, cudaGetErrorString(e));
+		}
+		G.peer[p] = (unsigned char *)base;
+	}
+	G.epoch[0] = G.epoch[1] = 0;
+	ctx->cur = 0; // every rank starts the group with the same buffer set
+	G.attached = true;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_group_detach(swcu_ctx *ctx)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	swcu_ctx::Group &G = ctx->group;
+	if(!G.reserved) return SWCU_OK;
+	CU(cudaSetDevice(ctx->device));
+	int rc = swcu_sync(ctx);
+	for(uint32_t p = 0; p < G.world; p++)
+		if(G.attached && p != G.rank && G.peer[p]) cudaIpcCloseMemHandle(G.peer[p]);
+	cudaFree(G.arena);
+	cudaGetLastError();
+	G = swcu_ctx::Group();
+	return rc;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

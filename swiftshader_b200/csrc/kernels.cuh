@@ -267,7 +267,7 @@ DEVI void edge_small(const DrawConst &d, uint32_t *rows, int rowMin, int Xa, int
 	{
 		const int X1q = X1 - (MS > 1 ? c_Xf[q] : 0), Y1q = Y1 - (MS > 1 ? c_Yf[q] : 0), Y2q = Y2 - (MS > 1 ? c_Yf[q] : 0);
 		const int y1 = (Y1q + 255) >> 8, y2 = (Y2q + 255) >> 8;
-		const int yMin = max(y1, d.scY0), yMax = min(y2, d.scY1);
+		const int yMin = max(y1, d.suY0), yMax = min(y2, d.suY1);
 		if(!(yMin < yMax)) continue;
 		// x(y1) = (X1 >> 8) + ceil(N / FDY), dd = N - ceil * FDY in (-FDY, 0]
 		const int N = DX * ((y1 << 8) - Y1q) + (X1q & 255) * DY;
@@ -340,7 +340,7 @@ DEVI bool rows_missed(const DrawConst &d, float y0, float w0, float y1, float w1
 	const float y1a = __fmaf_rn(__fdividef(y1, w1), d.HxF, d.Y0xF);
 	const float y2a = __fmaf_rn(__fdividef(y2, w2), d.HxF, d.Y0xF);
 	const float ylo = fminf(fminf(y0a, y1a), y2a), yhi = fmaxf(fmaxf(y0a, y1a), y2a);
-	return yhi + 1024.0f < (float)(d.scY0 << 8) || ylo - 1024.0f > (float)(d.scY1 << 8);
+	return yhi + 1024.0f < (float)(d.suY0 << 8) || ylo - 1024.0f > (float)(d.suY1 << 8);
 }
 
 // Band mode (the render area covers only part of the framebuffer rows — a rank of a multi-GPU frame): a light first pass,
@@ -372,6 +372,14 @@ DEVI void warp_bin_count(uint32_t *binCount, bool has, uint32_t bin)
 	const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? bin : (0x80000000u | (uint32_t)lane));
 	if(has && lane == __ffs(peers) - 1) atomicAdd(binCount + bin, (uint32_t)__popc(peers));
 }
+// group: the rank whose band holds row y, and the count of bin `bin` AT that rank (a peer's memory over NVLink, or my own)
+DEVI int band_of(const DrawConst &d, int y) { return min(y / d.bandRows, (int)d.world - 1); }
+DEVI void warp_bin_count_at(const DrawConst &d, bool has, int owner, uint32_t bin)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t peers = __match_any_sync(0xFFFFFFFFu, has ? (bin | ((uint32_t)owner << 24)) : (0x80000000u | (uint32_t)lane));
+	if(has && lane == __ffs(peers) - 1) atomicAdd(d.peerBinCount[owner] + bin, (uint32_t)__popc(peers));
+}
 // ... and the slots of the fill pass: the bin's count is taken down by the number of peers, every peer gets one of the slots
 DEVI uint32_t warp_bin_slot(uint32_t *binCount, bool has, uint32_t bin)
 {
@@ -396,8 +404,8 @@ template<int MSC>
 DEVI void setup_triangle(const DrawConst &d)
 {
 	extern __shared__ uint32_t s_rows[]; // [SWCU_SMALL_ROWS * ms][SETUP_THREADS]: one scratch column of span rows per thread
-	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x; // grid is padded to whole warps; inactive lanes just allocate 0
-	const bool live = tri < d.primCount;
+	const uint32_t tri = d.triLo + blockIdx.x * blockDim.x + threadIdx.x; // my share of the draw; the grid is padded to whole warps
+	const bool live = tri < d.triHi;
 	const int MS = MSC ? MSC : d.ms;
 	const bool msaa = MS > 1;
 	bool visible = false;
@@ -477,8 +485,8 @@ DEVI void setup_triangle(const DrawConst &d)
 			// value 2147483520 (RoundIntClamped), the sum wraps negative and the triangle ends here, as it does in the reference
 			yMin = (int)((uint32_t)minY + (msaa ? 159u : 255u)) >> 8;
 			yMax = (int)((uint32_t)maxY + (msaa ? 351u : 255u)) >> 8;
-			yMin = max(yMin, d.scY0);
-			yMax = min(yMax, d.scY1);
+			yMin = max(yMin, d.suY0);
+			yMax = min(yMax, d.suY1);
 			if(yMin >= yMax) break;
 			// conservative pixel-x bounds of the spans (left = ceil of an edge x >= minX; right <= ceil(maxX))
 			const int margin = msaa ? 96 : 0;
@@ -500,35 +508,59 @@ DEVI void setup_triangle(const DrawConst &d)
 	const int rows = visible ? yMax - yMin : 0;
 	bool big = false;
 	if(visible) big = rows > SWCU_SMALL_ROWS || (pxMax - pxMin) > SWCU_SMALL_COLS || polygon_insane(minXs, maxXs, minYs, maxYs);
+	// ---- owners: the ranks whose bands hold rows of the triangle's regions (one rank, everything local, outside a group).  The rule
+	//      only looks at the region rows, so that the owner's k_fill can apply it to the rectangle alone ----
+	const int ry0 = visible ? yMin / SWCU_REGION_H : 0, ry1 = visible ? (yMax - 1) / SWCU_REGION_H : 0;
+	int o0 = 0, o1 = 0;
+	if(visible && d.world > 1)
+	{
+		o0 = band_of(d, max(ry0 * SWCU_REGION_H, d.suY0));
+		o1 = band_of(d, min(ry1 * SWCU_REGION_H + SWCU_REGION_H, d.suY1) - 1);
+	}
 	unsigned long long slot = 0;
-	if(__any_sync(0xFFFFFFFFu, big)) slot = warp_alloc(&d.counters->bigSlots, big ? 1u : 0u);
+	if(d.world == 1)
+	{
+		if(__any_sync(0xFFFFFFFFu, big)) slot = warp_alloc(&d.counters->bigSlots, big ? 1u : 0u);
+	}
+	else if(big) slot = atomicAdd(&d.peerCounters[o0]->bigSlots, 1ull);
 	const uint32_t nvis = __popc(__ballot_sync(0xFFFFFFFFu, visible));
 	if((threadIdx.x & 31) == 0 && nvis) atomicAdd(&d.counters->visible, nvis);
-	// ---- region bins of a small triangle's frame: at most 2 x 2, counted here where the warp is still converged ----
+	// ---- region bins of a small triangle's frame: at most 2 x 2, counted here where the warp is still converged; a region row that
+	//      straddles two bands counts at both owners ----
 	uint32_t smallRect = TRI_RECT_NONE;
 	{
 		const bool small = visible && !big;
 		const int rx0 = pxMin / SWCU_REGION_W, rx1 = (pxMax - 1) / SWCU_REGION_W;
-		const int ry0 = yMin / SWCU_REGION_H, ry1 = (yMax - 1) / SWCU_REGION_H;
 		if(small) smallRect = (uint32_t)rx0 | ((uint32_t)ry0 << 9) | ((uint32_t)(rx1 - rx0) << 19) | ((uint32_t)(ry1 - ry0) << 20);
 		if(!d.direct)
 		{
-			const bool wide = small && rx1 > rx0, tall = small && ry1 > ry0;
-			warp_bin_count(d.binCount, small, small ? region_bin(d, rx0, ry0) : 0u);
-			if(__any_sync(0xFFFFFFFFu, wide)) warp_bin_count(d.binCount, wide, wide ? region_bin(d, rx1, ry0) : 0u);
-			if(__any_sync(0xFFFFFFFFu, tall)) warp_bin_count(d.binCount, tall, tall ? region_bin(d, rx0, ry1) : 0u);
-			if(__any_sync(0xFFFFFFFFu, wide && tall)) warp_bin_count(d.binCount, wide && tall, (wide && tall) ? region_bin(d, rx1, ry1) : 0u);
+#pragma unroll
+			for(int cell = 0; cell < 4; cell++)
+			{
+				const int cx = (cell & 1) ? rx1 : rx0, cy = (cell & 2) ? ry1 : ry0;
+				const bool has = small && (!(cell & 1) || rx1 > rx0) && (!(cell & 2) || ry1 > ry0);
+				if(cell && !__any_sync(0xFFFFFFFFu, has)) continue;
+				const uint32_t bin = has ? region_bin(d, cx, cy) : 0u;
+				int oA = 0, oB = 0;
+				if(has && d.world > 1)
+				{
+					oA = band_of(d, max(cy * SWCU_REGION_H, d.suY0));
+					oB = band_of(d, min(cy * SWCU_REGION_H + SWCU_REGION_H, d.suY1) - 1);
+				}
+				warp_bin_count_at(d, has, oA, bin);
+				if(__any_sync(0xFFFFFFFFu, has && oB != oA)) warp_bin_count_at(d, has && oB != oA, oB, bin);
+			}
 		}
 	}
 	if(!live) return;
-	unsigned char *rec = d.triRecords + (size_t)tri * d.triStride;
+	unsigned char *rec = d.peerRecords[o0] + (size_t)tri * d.triStride;
 	if(big && slot >= d.bigCapacity) { atomicOr(&d.counters->overflow, 2u); visible = false; }
 	if(!visible)
 	{
 		// Only the direct mode reads the header of an invisible triangle (every region warp walks the whole list): a small triangle
 		// whose frame lies outside every region.  A binned draw never puts it in a bin, so the 32-byte sector is not written at all.
 		if(d.direct) *(uint4 *)rec = make_uint4(0xFFFFFFFFu, 0, 0, 0);
-		d.triRect[tri] = TRI_RECT_NONE;
+		if(d.world == 1) d.triRect[tri] = TRI_RECT_NONE; // (the rectangles of a group member are cleared ahead of the draw: most come from peers)
 		return;
 	}
 	// the attributes behind the plane slots (usually the same cache lines as the positions); in flight during the span work
@@ -540,7 +572,7 @@ DEVI void setup_triangle(const DrawConst &d)
 	uint4 hdr;
 	if(big)
 	{
-		BigTri &b = d.bigList[slot];
+		BigTri &b = d.peerBig[o0][slot];
 		b.tri = tri; b.walk = 0; b.n = n; b.dir = dir;
 		b.yMin = yMin; b.yMax = yMax; b.pxMin = pxMin; b.pxMax = pxMax;
 		if(clipped)
@@ -550,7 +582,7 @@ DEVI void setup_triangle(const DrawConst &d)
 			b.X[0] = va.X; b.X[1] = vb.X; b.X[2] = vc.X;
 			b.Y[0] = va.Y; b.Y[1] = vb.Y; b.Y[2] = vc.Y;
 		}
-		d.triRect[tri] = TRI_RECT_BIG | (uint32_t)slot;
+		d.peerRect[o0][tri] = TRI_RECT_BIG | (uint32_t)slot;
 		hdr = make_uint4((uint32_t)pxMin | ((uint32_t)pxMax << 16), (frontFacing ? TRI_FLAG_FRONT : 0u) | TRI_FLAG_BIG, (uint32_t)yMin | ((uint32_t)yMax << 16), (uint32_t)slot);
 	}
 	else
@@ -612,7 +644,7 @@ DEVI void setup_triangle(const DrawConst &d)
 			((uint4 *)(rec + TRI_HEADER_BYTES))[1] = make_uint4(w[4], w[5], w[6], w[7]);
 		}
 		hdr = make_uint4((uint32_t)pxMin | ((uint32_t)yMin << 16), frontFacing ? TRI_FLAG_FRONT : 0u, m0, m1);
-		d.triRect[tri] = smallRect;
+		d.peerRect[o0][tri] = smallRect;
 	}
 
 	// ---- vertex sort (SetupRoutine.cpp:271-294): only changes float rounding of the planes ----
@@ -735,6 +767,24 @@ DEVI void setup_triangle(const DrawConst &d)
 	for(int j = 1; j < (TRI_FLOATS_FRONT + 3 * SWCU_MAXSLOTS + 3) / 4; j++)
 		if(j < nf4 && 4 * j + 3 > 5 + 3 * d.nslots) put(j);
 	*(uint4 *)rec = hdr;
+	// ---- a triangle whose regions reach into further bands: the same record (read back) for each further owner; a big triangle
+	//      gets a slot in that owner's big list ----
+	for(int o = o0 + 1; o <= o1; o++)
+	{
+		unsigned char *rec2 = d.peerRecords[o] + (size_t)tri * d.triStride;
+		for(uint32_t i = 16; i < d.triStride; i += 16) *(uint4 *)(rec2 + i) = *(const uint4 *)(rec + i);
+		uint4 h2 = hdr;
+		if(big)
+		{
+			const unsigned long long slot2 = atomicAdd(&d.peerCounters[o]->bigSlots, 1ull);
+			if(slot2 >= d.bigCapacity) { atomicOr(&d.peerCounters[o]->overflow, 2u); continue; }
+			d.peerBig[o][slot2] = d.peerBig[o0][slot];
+			h2.w = (uint32_t)slot2;
+			d.peerRect[o][tri] = TRI_RECT_BIG | (uint32_t)slot2;
+		}
+		else d.peerRect[o][tri] = smallRect;
+		*(uint4 *)rec2 = h2;
+	}
 }
 
 __global__ void __launch_bounds__(SETUP_THREADS, SETUP_BLOCKS_1X) k_setup_1x(const __grid_constant__ DrawConst d) { setup_triangle<1>(d); }
@@ -802,7 +852,9 @@ DEVI void big_regions(const DrawConst &d, uint32_t warpIndex, uint32_t warpCount
 	{
 		BigTri &b = d.bigList[e];
 		const int rx0 = b.pxMin / SWCU_REGION_W, rx1 = (b.pxMax - 1) / SWCU_REGION_W;
-		const int ry0 = b.yMin / SWCU_REGION_H, ry1 = (b.yMax - 1) / SWCU_REGION_H;
+		// the region rows of the triangle that hold rows of MY part of the frame (a member of a group: its band)
+		const int ry0 = max(b.yMin, d.scY0) / SWCU_REGION_H, ry1 = (min(b.yMax, d.scY1) - 1) / SWCU_REGION_H;
+		if(ry1 < ry0) continue;
 		const int w = rx1 - rx0 + 1, total = w * (ry1 - ry0 + 1);
 		uint32_t walk = 0;
 		if(!FILL)
@@ -925,30 +977,18 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ DrawConst 
 	const uint32_t r = tri < d.primCount ? d.triRect[tri] : TRI_RECT_NONE;
 	const bool small = !(r & TRI_RECT_BIG); // big: the blocks behind the small ones; invisible: nothing to do
 	const int rx0 = r & 0x1FF, ry0 = (r >> 9) & 0x3FF, rx1 = rx0 + ((r >> 19) & 1), ry1 = ry0 + ((r >> 20) & 1);
-	const bool wide = small && rx1 > rx0, tall = small && ry1 > ry0;
-	// warp-aggregated: one atomic per distinct bin of the warp's triangles
+	// warp-aggregated: one atomic per distinct bin of the warp's triangles.  A cell counts here if its region row holds rows of MY
+	// part of the frame — the rule k_setup (possibly on another rank) counted it by
+#pragma unroll
+	for(int cell = 0; cell < 4; cell++)
 	{
-		const uint32_t bin = small ? region_bin(d, rx0, ry0) : 0u;
-		const uint32_t slot = warp_bin_slot(d.binCount, small, bin);
-		if(small) d.pairs[d.binStart[bin] + slot] = tri;
-	}
-	if(__any_sync(0xFFFFFFFFu, wide))
-	{
-		const uint32_t bin = wide ? region_bin(d, rx1, ry0) : 0u;
-		const uint32_t slot = warp_bin_slot(d.binCount, wide, bin);
-		if(wide) d.pairs[d.binStart[bin] + slot] = tri;
-	}
-	if(__any_sync(0xFFFFFFFFu, tall))
-	{
-		const uint32_t bin = tall ? region_bin(d, rx0, ry1) : 0u;
-		const uint32_t slot = warp_bin_slot(d.binCount, tall, bin);
-		if(tall) d.pairs[d.binStart[bin] + slot] = tri;
-	}
-	if(__any_sync(0xFFFFFFFFu, wide && tall))
-	{
-		const uint32_t bin = (wide && tall) ? region_bin(d, rx1, ry1) : 0u;
-		const uint32_t slot = warp_bin_slot(d.binCount, wide && tall, bin);
-		if(wide && tall) d.pairs[d.binStart[bin] + slot] = tri;
+		const int cx = (cell & 1) ? rx1 : rx0, cy = (cell & 2) ? ry1 : ry0;
+		const bool has = small && (!(cell & 1) || rx1 > rx0) && (!(cell & 2) || ry1 > ry0) &&
+		                 max(cy * SWCU_REGION_H, d.scY0) < min(cy * SWCU_REGION_H + SWCU_REGION_H, d.scY1);
+		if(!__any_sync(0xFFFFFFFFu, has)) continue;
+		const uint32_t bin = has ? region_bin(d, cx, cy) : 0u;
+		const uint32_t slot = warp_bin_slot(d.binCount, has, bin);
+		if(has) d.pairs[d.binStart[bin] + slot] = tri;
 	}
 }
 
@@ -981,9 +1021,16 @@ DEVI void bitonic_sort_any(uint32_t *a, uint32_t n, uint32_t tid, uint32_t nthre
 // bins too long for the tile kernel's own ordering step: one CTA per such bin, in shared memory when it fits
 #define SORTBIG_THREADS 256
 #define SORTBIG_SMEM 8192
-__global__ void __launch_bounds__(SORTBIG_THREADS) k_sortbig(const uint32_t *binStart, uint32_t *pairs, const uint32_t *longBins, uint32_t longCap, const DrawCounters *c)
+// Block 0 also hands the counters of the draw's setup phase to the host through its mapped pinned page (a cudaMemcpyAsync would queue
+// in the device-to-host copy engine behind a frame download).  Nobody waits for them: swcu_sync looks at them once the device is idle.
+__global__ void __launch_bounds__(SORTBIG_THREADS) k_sortbig(const uint32_t *binStart, uint32_t *pairs, const uint32_t *longBins, uint32_t longCap, const DrawCounters *c, DrawCounters *hostOut)
 {
 	__shared__ uint32_t s_buf[SORTBIG_SMEM];
+	if(blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		*hostOut = *c;
+		__threadfence_system();
+	}
 	const uint32_t nlong = min(c->longBins, longCap);
 	for(uint32_t e = blockIdx.x; e < nlong; e += gridDim.x)
 	{
@@ -2211,6 +2258,23 @@ __global__ void k_copy_rows(const unsigned char *src, int srcPitchB, unsigned ch
 		const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
 		if(i < rowBytes) *(uint32_t *)(t + i) = *(const uint32_t *)(s + i);
 	}
+}
+
+// Group barrier of the setup phase: tell every rank that my share of the draw has been delivered (my stores and atomics into its
+// memory are visible system-wide), then wait until every rank has told me the same.  flags[p]: rank p's flag row of this buffer set.
+struct GroupFlags
+{
+	uint32_t *flags[SWCU_MAX_GROUP];
+};
+__global__ void k_xbarrier(const GroupFlags g, uint32_t world, uint32_t rank, uint32_t epoch)
+{
+	const uint32_t lane = threadIdx.x;
+	__threadfence_system();
+	if(lane < world) *(volatile uint32_t *)(g.flags[lane] + rank) = epoch;
+	if(lane < world)
+		while((int32_t)(*(volatile const uint32_t *)(g.flags[rank] + lane) - epoch) < 0) __nanosleep(64);
+	__syncwarp();
+	__threadfence_system();
 }
 
 // flag <- value, after everything this stream wrote before (the kernels ahead of this one) is visible system-wide

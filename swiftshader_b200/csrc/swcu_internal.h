@@ -130,7 +130,9 @@ struct DrawConst
 {
 	// ---- DrawData scalars (Renderer.hpp:58-113, Renderer.cpp:300-345) ----
 	float WxF, HxF, X0xF, Y0xF, depthRange, depthNear;
-	int32_t scX0, scX1, scY0, scY1;
+	int32_t scX0, scX1, scY0, scY1; // scissor ∩ render area: what the tile phase renders (a rank of a group: its band)
+	int32_t suY0, suY1;             // rows the SETUP clamps against: the same, except in a group, where every rank sets its share of
+	                                // the triangles up for the whole frame (scissor ∩ framebuffer) and the owners clip to their bands
 	int32_t ms; // 1 or 4
 	uint32_t sampleMask;
 
@@ -206,6 +208,16 @@ struct DrawConst
 	int32_t tilesX, tilesY;    // tile grid of the framebuffer
 	int32_t tileX0, tileY0, tileX1, tileY1; // tile range touched by the scissor (exclusive upper)
 	uint32_t numBins;          // tilesX * tilesY * 4: bin = tile * 4 + (region row & 1) * 2 + (region column & 1)
+	// ---- group (multi-GPU): this rank sets up triangles [triLo, triHi) and delivers record, rectangle, big-list entry and bin
+	//      counts of each to the rank(s) whose band of bandRows rows the triangle touches, over NVLink.  world == 1: everything local ----
+	uint32_t triLo, triHi;
+	uint32_t world, rank;
+	int32_t bandRows;
+	unsigned char *peerRecords[SWCU_MAX_GROUP];
+	uint32_t *peerRect[SWCU_MAX_GROUP];
+	uint32_t *peerBinCount[SWCU_MAX_GROUP];
+	BigTri *peerBig[SWCU_MAX_GROUP];
+	DrawCounters *peerCounters[SWCU_MAX_GROUP];
 	uint32_t direct;           // 1: no binning, every region warp walks all triangles
 	uint32_t blendClass;       // BL_*
 	uint32_t useTma;           // attachments satisfy the tensor-map alignment rules: stage the tile with TMA

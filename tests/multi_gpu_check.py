@@ -39,7 +39,13 @@ def main():
         H, W = sc.height, sc.width
         if H % (2 * world):
             continue
-        for mode in ("nccl", "peer"):
+        for mode in ("nccl", "peer", "group"):
+            # "group": the setup of every binned draw is sharded by triangle range as well (swcu_group_*: records, bin counts and big-list
+            # entries stored into the owning rank's work buffers over NVLink); the bands are delivered like in "peer"
+            grp = None
+            if mode == "group":
+                grp = bands.Group(dev, sc, world, rank, max(d.primitive_count() for d in sc.draws), 6, sc.samples)
+                dev.set_option("force_binned", 1)  # the single triangles too: a share can be empty, a big triangle spans every band
             fr = Frame(dev, sc, render_area=bands.render_area(W, H, world, rank))
             y0, y1 = bands.band_rows(H, world, rank)
             pitch = W * 4
@@ -55,7 +61,7 @@ def main():
                     # two frames, so the "previous frame consumed" handshake is exercised as well
                     pg = bands.PeerGather(dev, fr.final_image(), H, pitch, world, rank)
                     H2 = sc.padded_height()
-                    for _ in range(2):
+                    for _ in range(3 if mode == "group" else 2):
                         if sc.samples > 1:
                             fr.clear()  # the blended 4x scene is not idempotent; its 4x attachments are private to the rank
                         fr.draw()
@@ -81,6 +87,9 @@ def main():
                     got = fr.final_image()[:H].copy()
                     pg.close()
             fr.close()
+            if grp is not None:
+                grp.close()
+                dev.set_option("force_binned", 0)
             if rank == 0:
                 want = swref.render_oracle(sc)
                 ref = swref.resolve_oracle(sc, want) if sc.samples > 1 else want["color"][0]
