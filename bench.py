@@ -333,8 +333,6 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
                 dev.register(b, upload=False)
             in_sets = [(frame.inputs, frame.descs), (alt_inputs, alt_descs)]
             sharded_upload = N > 1 and os.environ.get("SWCU_SHARD_UPLOAD", "1") != "0"
-            if sharded_upload and gather != "nccl":
-                dev.set_option("copy_streams", 0)  # the input all-gather writes the shadows on the caller's stream
             up_bytes = [0]
 
             def upload_set(k):
@@ -346,13 +344,17 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
                     # my 1/N over PCIe, the rest over NVLink: all-gather of the 16-byte-aligned bulk, every rank uploads the small tail
                     flat = b.reshape(-1).view(np.uint8)
                     chunk = (flat.nbytes // N) & ~15
+                    tail = flat.nbytes - chunk * N
                     if chunk:
                         dev.check(dev.lib.swcu_mem_upload(dev.ctx, flat.ctypes.data + rank * chunk, chunk))
-                        whole = torch.as_tensor(_DevArr(dev.device_ptr(b), chunk * N), device=dev_s)
-                        dist.all_gather_into_tensor(whole, whole[rank * chunk:(rank + 1) * chunk])
-                    tail = flat.nbytes - chunk * N
                     if tail:
                         dev.check(dev.lib.swcu_mem_upload(dev.ctx, flat.ctypes.data + chunk * N, tail))
+                    if chunk:
+                        # the collective runs on the caller's stream: it waits for my slice's upload, later uploads wait for it
+                        dev.check(dev.lib.swcu_mem_acquire(dev.ctx, flat.ctypes.data))
+                        whole = torch.as_tensor(_DevArr(dev.device_ptr(b), chunk * N), device=dev_s)
+                        dist.all_gather_into_tensor(whole, whole[rank * chunk:(rank + 1) * chunk])
+                        dev.check(dev.lib.swcu_mem_release(dev.ctx, flat.ctypes.data))
                     up_bytes[0] += chunk + tail
 
             F = len(final_imgs) if (rank == 0 or N == 1) else 2
@@ -394,8 +396,6 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
                           "h2d_bytes_per_step_per_gpu": int(up_bytes[0] / (e2e_steps + 1)),
                           "d2h_bytes_per_step": H * pitch,
                           "inputs": "1/N per rank over PCIe + NCCL all-gather over NVLink" if sharded_upload else "every rank uploads everything" if N > 1 else "uploaded"}
-            if sharded_upload and gather != "nccl":
-                dev.set_option("copy_streams", 1)
 
         # ---- per-kernel device times (events around every launch) for the roofline of the dominant kernel ----
         dev.set_profiling(True)

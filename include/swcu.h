@@ -294,6 +294,14 @@ int swcu_group_reserve(swcu_ctx *ctx, const swcu_group_desc *desc, void *handle6
 int swcu_group_attach(swcu_ctx *ctx, const void *handles /* world * 64 bytes, rank order */);
 int swcu_group_detach(swcu_ctx *ctx);
 
+/* The caller's stream (swcu_set_stream) is about to read or write the shadow of host_ptr itself — a collective over
+ * swcu_mem_device_ptr, a kernel of its own: the stream waits for the last upload into the shadow (and for a download of it still in
+ * flight), and uploads issued later wait for what the stream has been given up to their call. */
+int swcu_mem_acquire(swcu_ctx *ctx, const void *host_ptr);
+/* ... and once that work has been enqueued on the stream: whatever reads the shadow from now on (the setup phase of a draw runs on
+ * a stream of its own) waits for it, as it would for an upload. */
+int swcu_mem_release(swcu_ctx *ctx, const void *host_ptr);
+
 /* ---- narrow SPIR-V translator (host-only, no GPU needed) ---- */
 int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_shader_info *out, char *err, size_t errlen);
 

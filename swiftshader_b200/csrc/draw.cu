@@ -44,6 +44,8 @@ struct KernelTime
 	cudaEvent_t e0, e1;
 };
 
+#define SWCU_SETS 3 // buffer sets of the setup phase: in a group the peers write set d + 1 while this rank may still read sets d and d - 1
+
 struct swcu_ctx
 {
 	int device = 0;
@@ -55,13 +57,13 @@ struct swcu_ctx
 	// the pair buffer holds 4 pairs per triangle plus a budget for the big triangles (swcu_set_option "big_pair_budget").
 	struct SetupSet
 	{
-		DevBuf triRecords, bigList, triRect, binCount, binStart, pairs, longBins, counters, cullFlags;
+		DevBuf triRecords, bigList, triRect, binCount, binStart, pairs, counters, cullFlags;
 		cudaEvent_t tileDone = nullptr;       // recorded on the main stream after the last kernel that reads this set
 		bool tileDoneValid = false;
 		cudaEvent_t setupDone = nullptr;      // recorded on the setup stream after the binning of a pipelined draw
 		DrawCounters *hostCounters = nullptr; // pinned: the counters of the last draw that used this set, copied by its k_tile's successor
 		bool countersPending = false;
-	} set[2];
+	} set[SWCU_SETS];
 	int cur = 0;
 	cudaStream_t setupStream = nullptr;
 	// Host<->device copies run on their own two streams (one per DMA direction), so the upload of the next frame's inputs and
@@ -86,9 +88,9 @@ struct swcu_ctx
 		size_t countersBytes = 0;
 		unsigned char *arena = nullptr;
 		size_t arenaBytes = 0;
-		size_t offRecords[2], offRect[2], offBig[2], offBinCount[2], offCounters[2], offFlags[2];
+		size_t offRecords[SWCU_SETS], offRect[SWCU_SETS], offBig[SWCU_SETS], offBinCount[SWCU_SETS], offCounters[SWCU_SETS], offFlags[SWCU_SETS];
 		unsigned char *peer[SWCU_MAX_GROUP] = {}; // mapped arenas, [rank] = my own
-		uint32_t epoch[2] = { 0, 0 };
+		uint32_t epoch[SWCU_SETS] = {};
 	} group;
 	size_t optBigPairBudget = (size_t)16 << 20; // (region, triangle) pairs the big triangles of one draw may occupy
 	int lastOverflow = 0;
@@ -209,7 +211,7 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 	cudaFree(ctx->zeroPage.p);
 	for(auto &S : ctx->set)
 	{
-		DevBuf *sb[] = { &S.triRecords, &S.bigList, &S.triRect, &S.binCount, &S.binStart, &S.pairs, &S.longBins, &S.counters, &S.cullFlags };
+		DevBuf *sb[] = { &S.triRecords, &S.bigList, &S.triRect, &S.binCount, &S.binStart, &S.pairs, &S.counters, &S.cullFlags };
 		for(DevBuf *b : sb) cudaFree(b->p);
 		if(S.hostCounters) cudaFreeHost(S.hostCounters);
 		if(S.tileDone) cudaEventDestroy(S.tileDone);
@@ -442,6 +444,31 @@ extern "C" int swcu_fence_wait(swcu_ctx *ctx, uint32_t slot)
 	if(!ctx->fenceValid[slot]) return SWCU_OK;
 	CU(cudaSetDevice(ctx->device));
 	CU(cudaEventSynchronize(ctx->fence[slot]));
+	return SWCU_OK;
+}
+
+extern "C" int swcu_mem_acquire(swcu_ctx *ctx, const void *host_ptr)
+{
+	if(!ctx || !host_ptr) return fail(ctx, SWCU_E_INVALID, "swcu_mem_acquire: null argument");
+	if(!find_shadow(ctx, host_ptr, 1)) return fail(ctx, SWCU_E_INVALID, "swcu_mem_acquire: %p is not inside a registered range", host_ptr);
+	CU(cudaSetDevice(ctx->device));
+	return main_touches(ctx, host_ptr, true);
+}
+
+extern "C" int swcu_mem_release(swcu_ctx *ctx, const void *host_ptr)
+{
+	if(!ctx || !host_ptr) return fail(ctx, SWCU_E_INVALID, "swcu_mem_release: null argument");
+	Shadow *s = find_shadow(ctx, host_ptr, 1);
+	if(!s) return fail(ctx, SWCU_E_INVALID, "swcu_mem_release: %p is not inside a registered range", host_ptr);
+	CU(cudaSetDevice(ctx->device));
+	// The caller's work counts as the newest "upload" of the shadow.  Readers assume that having waited for upload number n they
+	// have seen all earlier ones, so the stream first catches up with every upload issued so far.
+	int rc = see_uploads(ctx, ctx->stream, ctx->mainSawUpload);
+	if(rc) return rc;
+	if(!s->upEvent) CU(cudaEventCreateWithFlags(&s->upEvent, cudaEventDisableTiming));
+	CU(cudaEventRecord(s->upEvent, ctx->stream));
+	s->upSeq = ++ctx->uploadSeq;
+	ctx->mainSawUpload = s->upSeq;
 	return SWCU_OK;
 }
 
@@ -1025,13 +1052,12 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	const bool grouped = G.attached && !d.direct;
 	// The setup phase of this draw uses the set the draw before the previous one used.  A binned draw runs it on the setup
 	// stream: it waits only for the inputs (last upload) and for the last reader of this set, not for the tile kernel of the
-	// previous draw.  Direct draws, group draws (whose buffers the PEERS write: everything stays in one stream's order), profiling
-	// mode (per-kernel events) and inputs in caller-owned device memory (whose producers the library cannot see) stay on the main
-	// stream.  No step of a draw waits for the host.
+	// previous draw.  Direct draws, profiling mode (per-kernel events) and inputs in caller-owned device memory (whose producers the
+	// library cannot see) stay on the main stream.  No step of a draw waits for the host.
 	const int setIndex = ctx->cur;
 	swcu_ctx::SetupSet &S = ctx->set[setIndex];
-	ctx->cur ^= 1;
-	const bool pipelined = !d.direct && !grouped && ctx->optPipeline && !ctx->profiling && !d.inputsExternal;
+	ctx->cur = (ctx->cur + 1) % SWCU_SETS;
+	const bool pipelined = !d.direct && ctx->optPipeline && !ctx->profiling && !d.inputsExternal;
 	const cudaStream_t ss = pipelined ? ctx->setupStream : ctx->stream;
 	if(pipelined)
 	{
@@ -1111,7 +1137,6 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	{
 		if((rc = ensure(ctx, S.binStart, ((size_t)d.numBins + 1) * 4))) return rc;
 		if((rc = ensure(ctx, S.pairs, pairCap * 4))) return rc;
-		if((rc = ensure(ctx, S.longBins, (pairCap / SWCU_SORT_CAP + 1) * 4))) return rc; // more bins than that cannot be long
 	}
 	if(!ctx->zeroPage.p)
 	{
@@ -1120,6 +1145,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		CU(cudaStreamSynchronize(ctx->stream));
 	}
 	d.zeroPage = ctx->zeroPage.p;
+	d.hostCounters = d.direct ? nullptr : S.hostCounters;
 	d.binStart = (uint32_t *)S.binStart.p;
 	d.pairs = (uint32_t *)S.pairs.p;
 	d.bigBudget = d.direct ? 0 : pairCap - (size_t)4 * n;
@@ -1146,7 +1172,11 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	}
 	if(grouped)
 	{
-		// every rank's share has to be in my buffers before I bin: the one collective step of a group draw
+		// Every rank's share has to be in my buffers before I bin: the one collective step of a group draw.  Passing this barrier also
+		// lets the peers start on the NEXT draw, i.e. write into my next buffer set — so its last reader (the tile kernel of the draw
+		// before the previous one) and the reset behind it must be done before I check in.
+		swcu_ctx::SetupSet &next = ctx->set[ctx->cur];
+		if(pipelined && next.tileDoneValid) CU(cudaStreamWaitEvent(ss, next.tileDone, 0));
 		GroupFlags gf;
 		memset(&gf, 0, sizeof(gf));
 		for(uint32_t p = 0; p < G.world; p++) gf.flags[p] = (uint32_t *)(G.peer[p] + G.offFlags[setIndex]);
@@ -1156,27 +1186,18 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	const bool nothingToDraw = d.scX0 >= d.scX1 || d.scY0 >= d.scY1; // (only a group member gets here with an empty band)
 	if(!d.direct)
 	{
-		// ---- binning: count (k_setup + k_bigcount), scan, fill, order the long bins; all sized on the host, all asynchronous ----
+		// ---- binning: count (k_setup + the first blocks of k_binscan), scan, fill; all sized on the host, all asynchronous ----
 		const unsigned bigBlocks = 148; // grid-stride over the big list, whose length only the device knows
 		{
-			LaunchScope ls(ctx, "k_bigcount", ss);
-			k_bigcount<<<bigBlocks, 32 * BIG_WARPS_PER_BLOCK, 0, ss>>>(d);
-		}
-		{
 			LaunchScope ls(ctx, "k_binscan", ss);
-			k_binscan<<<(unsigned)scanBlocks, SCAN_THREADS, 0, ss>>>(d.binCount, d.binStart, d.numBins, (volatile uint32_t *)(d.counters + 1), d.counters,
-			                                                           (uint32_t *)S.longBins.p, (uint32_t)(pairCap / SWCU_SORT_CAP + 1));
+			k_binscan<<<bigBlocks + (unsigned)scanBlocks, SCAN_THREADS, 0, ss>>>(d, bigBlocks);
 		}
 		{
 			LaunchScope ls(ctx, "k_fill", ss);
 			const unsigned smallBlocks = (n + 255) / 256;
 			k_fill<<<smallBlocks + bigBlocks, 256, 0, ss>>>(d, smallBlocks);
 		}
-		{
-			LaunchScope ls(ctx, "k_sortbig", ss);
-			k_sortbig<<<148, SORTBIG_THREADS, 0, ss>>>(d.binStart, d.pairs, (const uint32_t *)S.longBins.p, (uint32_t)(pairCap / SWCU_SORT_CAP + 1), d.counters, S.hostCounters);
-			S.countersPending = true;
-		}
+		S.countersPending = true;
 		if(pipelined)
 		{
 			CU(cudaEventRecord(S.setupDone, ss));
@@ -1230,7 +1251,7 @@ extern "C" int swcu_group_reserve(swcu_ctx *ctx, const swcu_group_desc *g, void 
 	G.countersBytes = (sizeof(DrawCounters) + 4 * (scanBlocks + 1) + 255) & ~(size_t)255;
 	size_t off = 0;
 	auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
-	for(int k = 0; k < 2; k++)
+	for(int k = 0; k < SWCU_SETS; k++)
 	{
 		G.offRecords[k] = take((size_t)G.maxPrims * G.stride);
 		G.offRect[k] = take((size_t)G.maxPrims * 4);
@@ -1243,7 +1264,7 @@ extern "C" int swcu_group_reserve(swcu_ctx *ctx, const swcu_group_desc *g, void 
 	cudaError_t e = cudaMalloc((void **)&G.arena, G.arenaBytes);
 	if(e != cudaSuccess) { cudaGetLastError(); return fail(ctx, SWCU_E_NOMEM, "cudaMalloc(%zu) for the group arena failed: %s", G.arenaBytes, cudaGetErrorString(e)); }
 	CU(cudaMemsetAsync(G.arena, 0, G.arenaBytes, ctx->stream));
-	for(int k = 0; k < 2; k++) CU(cudaMemsetAsync(G.arena + G.offRect[k], 0xFF, (size_t)G.maxPrims * 4, ctx->stream)); // TRI_RECT_NONE
+	for(int k = 0; k < SWCU_SETS; k++) CU(cudaMemsetAsync(G.arena + G.offRect[k], 0xFF, (size_t)G.maxPrims * 4, ctx->stream)); // TRI_RECT_NONE
 	CU(cudaStreamSynchronize(ctx->stream));
 	CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, G.arena));
 	G.reserved = true;
@@ -1274,7 +1295,7 @@ extern "C" int swcu_group_attach(swcu_ctx *ctx, const void *handles)
 		}
 		G.peer[p] = (unsigned char *)base;
 	}
-	G.epoch[0] = G.epoch[1] = 0;
+	for(auto &e : G.epoch) e = 0;
 	ctx->cur = 0; // every rank starts the group with the same buffer set
 	G.attached = true;
 	return SWCU_OK;

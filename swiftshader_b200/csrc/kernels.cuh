@@ -794,11 +794,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 // binning: (region, triangle) pairs without a sort and without a host round trip
 //
 //   k_setup      counts the (at most 2 x 2) region bins of every small triangle           binCount[bin]++
-//   k_bigcount   one warp per big triangle: the regions of its bounding box that an edge does not exclude; a big triangle
-//                whose bounding box does not fit the remaining pair budget is marked `walk` and not binned
-//   k_binscan    exclusive scan of the counts (single pass, decoupled look-back)           binStart[bin]
+//   k_binscan    its first blocks count the regions of the big triangles (one warp per triangle: the regions of its bounding box that
+//                an edge does not exclude; a big triangle whose bounding box does not fit the remaining pair budget is marked `walk`
+//                and not binned), the others then scan the counts (single pass, decoupled look-back)         binStart[bin]
 //   k_fill       every pair takes a slot of its bin: binStart[bin] + (--binCount[bin]); the counts end at zero again
-//   k_sortbig    bins longer than SWCU_SORT_CAP are put in triangle order here; the tile kernel orders the others itself
 //
 // The slots of a bin are handed out by atomics, i.e. in no particular order; the API order of the triangles (the reference's cluster
 // tickets, Renderer.cpp:573-576) is restored by sorting each bin's few entries by triangle id.  The pair buffer holds 4 pairs per
@@ -806,7 +805,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_setup(const __grid_constant__
 // ------------------------------------------------------------------------------------------------------------------
 
 // Can a fragment of big triangle b land in region (rx, ry)?  Conservative — the bounding box, minus the regions all of whose pixel
-// centres (widened by the sample offsets) lie strictly outside one edge — and deterministic: k_bigcount and k_fill must agree.
+// centres (widened by the sample offsets) lie strictly outside one edge — and deterministic: the count (k_binscan) and the fill (k_fill) must agree.
 // sgn: orientation of the polygon, 0 = do not cull geometrically (garbage coordinates the reference walks in wrapped arithmetic).
 DEVI int big_orientation(const BigTri &b)
 {
@@ -842,7 +841,7 @@ DEVI bool big_touches_region(const DrawConst &d, const BigTri &b, int rx, int ry
 	return true;
 }
 
-// FILL = false: count the regions of every big triangle (k_bigcount); FILL = true: hand out their slots (second part of k_fill)
+// FILL = false: count the regions of every big triangle (first blocks of k_binscan); FILL = true: hand out their slots (second part of k_fill)
 template<bool FILL>
 DEVI void big_regions(const DrawConst &d, uint32_t warpIndex, uint32_t warpCount)
 {
@@ -882,20 +881,35 @@ DEVI void big_regions(const DrawConst &d, uint32_t warpIndex, uint32_t warpCount
 }
 
 #define BIG_WARPS_PER_BLOCK 8
-__global__ void __launch_bounds__(32 * BIG_WARPS_PER_BLOCK) k_bigcount(const __grid_constant__ DrawConst d)
-{
-	big_regions<false>(d, blockIdx.x * BIG_WARPS_PER_BLOCK + (threadIdx.x >> 5), gridDim.x * BIG_WARPS_PER_BLOCK);
-}
-
 // Exclusive scan of the bin counts in one pass (decoupled look-back: a block publishes its sum, then adds up the sums of its
 // predecessors until it meets one that already knows its prefix).  state[] and the ticket start at zero.
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 8
-__global__ void __launch_bounds__(SCAN_THREADS) k_binscan(const uint32_t *count, uint32_t *start, uint32_t n, volatile uint32_t *state, DrawCounters *c, uint32_t *longBins, uint32_t longCap)
+// The first bigBlocks blocks of the grid count the regions of the big triangles (k_setup has counted the small ones) and check in;
+// the scan blocks wait for them — all blocks of this small grid are resident together — unless the draw has no big triangle at all.
+__global__ void __launch_bounds__(SCAN_THREADS) k_binscan(const __grid_constant__ DrawConst d, uint32_t bigBlocks)
 {
 	__shared__ uint32_t s_block, s_warp[SCAN_THREADS / 32], s_prefix;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	if(tid == 0) s_block = atomicAdd(&c->scanTicket, 1u); // blocks take their part in the order they start: a predecessor is always running
+	DrawCounters *c = d.counters;
+	const uint32_t *count = d.binCount;
+	uint32_t *start = d.binStart;
+	const uint32_t n = d.numBins;
+	volatile uint32_t *state = (volatile uint32_t *)(d.counters + 1);
+	if(blockIdx.x < bigBlocks)
+	{
+		big_regions<false>(d, blockIdx.x * BIG_WARPS_PER_BLOCK + (threadIdx.x >> 5), bigBlocks * BIG_WARPS_PER_BLOCK);
+		__syncthreads();
+		if(tid == 0) { __threadfence(); atomicAdd(&c->bigDone, 1u); }
+		return;
+	}
+	if(tid == 0)
+	{
+		if(c->bigSlots != 0)
+			while(*(volatile uint32_t *)&c->bigDone < bigBlocks) __nanosleep(32);
+		__threadfence();
+		s_block = atomicAdd(&c->scanTicket, 1u); // blocks take their part in the order they start: a predecessor is always running
+	}
 	__syncthreads();
 	const uint32_t blk = s_block;
 	const uint32_t base = (blk * SCAN_THREADS + tid) * SCAN_ITEMS;
@@ -904,16 +918,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_binscan(const uint32_t *count,
 	for(int i = 0; i < SCAN_ITEMS; i++) v[i] = base + i < n ? count[base + i] : 0u;
 	uint32_t sum = 0;
 #pragma unroll
-	for(int i = 0; i < SCAN_ITEMS; i++)
-	{
-		sum += v[i];
-		// bins the tile kernel will not order itself: k_sortbig works through this list (at most longCap = pairs / SWCU_SORT_CAP of them exist)
-		if(v[i] > SWCU_SORT_CAP)
-		{
-			const uint32_t at = atomicAdd(&c->longBins, 1u);
-			if(at < longCap) longBins[at] = base + i;
-		}
-	}
+	for(int i = 0; i < SCAN_ITEMS; i++) sum += v[i];
 	uint32_t incl = sum;
 #pragma unroll
 	for(int o = 1; o < 32; o <<= 1)
@@ -1014,41 +1019,6 @@ DEVI void bitonic_sort_any(uint32_t *a, uint32_t n, uint32_t tid, uint32_t nthre
 				}
 			}
 			sync();
-		}
-	}
-}
-
-// bins too long for the tile kernel's own ordering step: one CTA per such bin, in shared memory when it fits
-#define SORTBIG_THREADS 256
-#define SORTBIG_SMEM 8192
-// Block 0 also hands the counters of the draw's setup phase to the host through its mapped pinned page (a cudaMemcpyAsync would queue
-// in the device-to-host copy engine behind a frame download).  Nobody waits for them: swcu_sync looks at them once the device is idle.
-__global__ void __launch_bounds__(SORTBIG_THREADS) k_sortbig(const uint32_t *binStart, uint32_t *pairs, const uint32_t *longBins, uint32_t longCap, const DrawCounters *c, DrawCounters *hostOut)
-{
-	__shared__ uint32_t s_buf[SORTBIG_SMEM];
-	if(blockIdx.x == 0 && threadIdx.x == 0)
-	{
-		*hostOut = *c;
-		__threadfence_system();
-	}
-	const uint32_t nlong = min(c->longBins, longCap);
-	for(uint32_t e = blockIdx.x; e < nlong; e += gridDim.x)
-	{
-		const uint32_t bin = longBins[e];
-		const uint32_t b0 = binStart[bin], n = binStart[bin + 1] - b0;
-		uint32_t *g = pairs + b0;
-		if(n <= SORTBIG_SMEM)
-		{
-			for(uint32_t i = threadIdx.x; i < n; i += SORTBIG_THREADS) s_buf[i] = g[i];
-			__syncthreads();
-			bitonic_sort_any(s_buf, n, threadIdx.x, SORTBIG_THREADS, [] { __syncthreads(); });
-			for(uint32_t i = threadIdx.x; i < n; i += SORTBIG_THREADS) g[i] = s_buf[i];
-			__syncthreads();
-		}
-		else
-		{
-			__syncthreads();
-			bitonic_sort_any(g, n, threadIdx.x, SORTBIG_THREADS, [] { __syncthreads(); });
 		}
 	}
 }
@@ -1411,8 +1381,8 @@ DEVI float blend_apply(uint32_t op, float s, float sf, float dd, float df) // :1
 //     (fallback: lane copies when an attachment does not satisfy the tensor-map alignment rules, or when the scissor rows cut
 //     through the region — a band of a multi-GPU frame must not store rows that belong to another rank);
 //   * the bin's entries come in no particular order (k_fill hands the slots out with atomics): the warp first puts them in
-//     triangle order — the API order of the fragments — in registers (<= 32 entries), in shared memory (<= SWCU_SORT_CAP), or finds
-//     them already sorted by k_sortbig;
+//     triangle order — the API order of the fragments — in registers (<= 128 entries), in shared memory (<= SWCU_SORT_CAP) or, a long
+//     bin, in place in global memory;
 //   * coverage, 32 bin entries at a time, one per lane.  SMALL triangle: the lane clips the coverage masks of the record to
 //     the region (a few logic ops per row) and counts the bits.  BIG triangle: one (row, sample) per lane evaluates the
 //     reference's span in closed form (edge_at_row) from the polygon in the big list;
@@ -1540,6 +1510,13 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t laneLt = (1u << lane) - 1u;
+	if(blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && d.hostCounters)
+	{
+		// the counters of the draw's setup phase, for swcu_sync to look at (through the mapped page: a cudaMemcpyAsync would queue in the
+		// device-to-host copy engine behind a frame download)
+		*d.hostCounters = *d.counters;
+		__threadfence_system();
+	}
 	const int tx = d.tileX0 + blockIdx.x, ty = d.tileY0 + blockIdx.y;
 	const uint32_t bin = (uint32_t)(ty * d.tilesX + tx) * 4u + (uint32_t)warp;
 	uint32_t begin = 0, n = d.primCount;
@@ -1622,7 +1599,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 	// ---- the bin in triangle order ----
 	const uint32_t *list = d.pairs + begin;
 	uint32_t regId = 0xFFFFFFFFu;
-	bool sortedInSmem = false;
+	bool sortedInSmem = false, listInPlace = false;
 	if(!d.direct)
 	{
 		if(n <= 32)
@@ -1686,6 +1663,12 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 			bitonic_sort_any(wSort, n, (uint32_t)lane, 32u, [] { __syncwarp(); });
 			sortedInSmem = true;
 		}
+		else
+		{
+			// a long bin (heavy overdraw): ordered in place in global memory — the segment belongs to this warp alone
+			bitonic_sort_any(d.pairs + begin, n, (uint32_t)lane, 32u, [] { __syncwarp(); });
+			listInPlace = true;
+		}
 	}
 
 	// ---- 32 bin entries at a time, one per lane; the ids and record headers of the next 32 are requested before the current ones
@@ -1696,7 +1679,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 		hOut = make_uint4(0, 0, 0, 0);
 		if(li < n)
 		{
-			idOut = d.direct ? li : (n <= 32 ? regId : (sortedInSmem ? wSort[li] : __ldg(list + li)));
+			idOut = d.direct ? li : (n <= 32 ? regId : (sortedInSmem ? wSort[li] : (listInPlace ? d.pairs[begin + li] : __ldg(list + li))));
 			const unsigned char *r = d.triRecords + (size_t)idOut * d.triStride;
 			hOut = __ldg((const uint4 *)r);
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(r + d.planeOffset));

@@ -60,7 +60,7 @@ enum { CLIP_RIGHT = 1, CLIP_TOP = 2, CLIP_FAR = 4, CLIP_LEFT = 8, CLIP_BOTTOM = 
 #define SWCU_SMALL_ROWS 8    // a SMALL triangle fits an 8 x 8 pixel frame: its coverage travels as bit masks inside its record
 #define SWCU_SMALL_COLS 8
 #define SWCU_POLY_MAX 10     // 3 + 6 clip planes (+1 wrap slot)
-#define SWCU_SORT_CAP 256    // bins up to this many entries are put in triangle order by the tile kernel itself (k_sortbig does the others)
+#define SWCU_SORT_CAP 256    // bins up to this many entries are put in triangle order in shared memory (longer ones in place, in global memory)
 
 // operand kinds after routing (device side)
 enum { OPK_CONST = 0, OPK_INPUT = 1, OPK_TEXEL = 2 };
@@ -123,7 +123,7 @@ struct DrawCounters
 	uint32_t overflow;              // bit1: big list full; bit2: a big triangle did not fit the pair budget
 	uint32_t visible;               // triangles that survived setup
 	uint32_t scanTicket;            // k_binscan: block tickets
-	uint32_t longBins;              // bins longer than SWCU_SORT_CAP (k_binscan lists them for k_sortbig)
+	uint32_t bigDone;               // k_binscan: blocks that have finished counting the big triangles' regions
 };
 
 struct DrawConst
@@ -204,6 +204,7 @@ struct DrawConst
 	uint32_t inputsExternal;        // an index / vertex stream lives in caller-owned device memory (host side only)
 	const unsigned char *cullFlags; // band mode: 0 = rows outside the band (k_cull), nullptr when the pass is not run
 	DrawCounters *counters;
+	DrawCounters *hostCounters; // mapped pinned page: the tile kernel leaves the counters of the draw there (nobody waits for them)
 	const void *zeroPage;      // 256 readable bytes: target of the discarded loads of branch-free attribute fetches
 	int32_t tilesX, tilesY;    // tile grid of the framebuffer
 	int32_t tileX0, tileY0, tileX1, tileY1; // tile range touched by the scissor (exclusive upper)
