@@ -26,6 +26,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libswref.so")
 REF_ICD = os.path.join(_HERE, "_ref", "libvk_swiftshader.so")
 REFRENDER = os.path.join(_HERE, "_ref", "refrender")
+# the same ICD with the CUDA draw path wired in behind sw::Renderer::draw (oracle/build_cuda_icd.sh, icd/): product, not oracle —
+# it is only DRIVEN from here, by the harness that also drives the reference
+CUDA_ICD = os.path.join(_HERE, "_cuda", "libvk_swiftshader_cuda.so")
 _lib = None
 
 
@@ -156,10 +159,15 @@ def reference_available() -> bool:
     return os.path.exists(REF_ICD) and os.path.exists(REFRENDER)
 
 
-def render_reference(scene: Scene, time_frames: int = 0, threads: int | None = None, warmup: int = 1) -> dict:
-    """Render the scene with the REFERENCE ICD (oracle/_ref).  Returns colour (resolved when multisampled),
-    depth/stencil when single-sampled, and the timing JSON when time_frames > 0."""
-    if not reference_available():
+def cuda_icd_available() -> bool:
+    return os.path.exists(CUDA_ICD) and os.path.exists(REFRENDER)
+
+
+def render_reference(scene: Scene, time_frames: int = 0, threads: int | None = None, warmup: int = 1, icd: str | None = None, env: dict | None = None) -> dict:
+    """Render the scene through the Vulkan API of an ICD — by default the REFERENCE ICD (oracle/_ref); `icd` = CUDA_ICD drives the
+    patched ICD instead.  Returns colour (resolved when multisampled), depth/stencil when single-sampled, and the timing JSON when
+    time_frames > 0."""
+    if icd is None and not reference_available():
         raise RuntimeError("reference ICD not built (oracle/build_ref.sh); only available where /root/reference is")
     with tempfile.TemporaryDirectory() as td:
         sp, op = os.path.join(td, "scene.bin"), os.path.join(td, "out.bin")
@@ -167,10 +175,10 @@ def render_reference(scene: Scene, time_frames: int = 0, threads: int | None = N
         if threads is not None:  # docs/RuntimeConfiguration.md:9-22 — SwiftShader.ini is read from the CWD
             with open(os.path.join(td, "SwiftShader.ini"), "w") as f:
                 f.write(f"[Processor]\nThreadCount={threads}\n")
-        cmd = [REFRENDER, REF_ICD, sp, op]
+        cmd = [REFRENDER, icd or REF_ICD, sp, op]
         if time_frames:
             cmd += ["--time", str(time_frames), "--warmup", str(warmup)]
-        res = subprocess.run(cmd, cwd=td, capture_output=True, text=True)
+        res = subprocess.run(cmd, cwd=td, capture_output=True, text=True, env=None if env is None else {**os.environ, **env})
         if res.returncode != 0:
             raise RuntimeError(f"refrender failed ({res.returncode}): {res.stderr[-2000:]}")
         raw = open(op, "rb").read()
