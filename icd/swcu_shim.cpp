@@ -35,6 +35,7 @@ struct Api
 	int (*mem_download)(swcu_ctx *, void *, size_t);
 	int (*draw)(swcu_ctx *, const swcu_draw_desc *);
 	int (*sync)(swcu_ctx *);
+	int (*resolve)(swcu_ctx *, const swcu_attachment *, uint32_t, const swcu_attachment *);
 	int (*shader_translate)(const uint32_t *, uint32_t, swcu_shader_info *, char *, size_t);
 };
 
@@ -50,6 +51,7 @@ struct State
 	Api api{};
 	swcu_ctx *ctx = nullptr;
 	std::map<uintptr_t, size_t> allocations;  // registered host ranges (base -> bytes)
+	std::map<uintptr_t, bool> mapped;         // allocations the application holds a pointer into (vkMapMemory)
 	std::vector<Range> deviceNewer;           // attachment ranges the device has drawn to since their last download
 };
 
@@ -100,6 +102,7 @@ bool start()
 	SYM(mem_download, "swcu_mem_download");
 	SYM(draw, "swcu_draw");
 	SYM(sync, "swcu_sync");
+	SYM(resolve, "swcu_resolve");
 	SYM(shader_translate, "swcu_shader_translate");
 #undef SYM
 	const char *ord = getenv("SWCU_DEVICE");
@@ -126,10 +129,13 @@ bool findAllocation(uintptr_t p, uintptr_t &base, size_t &bytes)
 	return true;
 }
 
+bool deviceIsNewer(uintptr_t lo, uintptr_t hi);
+
 // host -> device for [p, p + bytes), clipped to the allocation that holds p
 void uploadRange(const void *p, size_t bytes)
 {
 	if(!p || !bytes) return;
+	if(deviceIsNewer((uintptr_t)p, (uintptr_t)p + bytes)) return;  // (a render target read as an input: the device copy IS the current one)
 	uintptr_t base;
 	size_t size;
 	if(!findAllocation((uintptr_t)p, base, size)) die("a draw reads host memory that is not a vk::DeviceMemory allocation", "");
@@ -153,6 +159,27 @@ void acquireAttachment(const void *p, size_t bytes)
 	if(deviceIsNewer(lo, hi)) return;
 	uploadRange(p, bytes);
 	S().deviceNewer.push_back({ lo, hi });
+}
+
+thread_local int tl_drawScope = 0;
+
+// device -> host for what the device has drawn inside [lo, hi); with the lock held
+void makeHostCurrent(uintptr_t lo, uintptr_t hi)
+{
+	State &s = S();
+	bool any = false;
+	for(size_t i = 0; i < s.deviceNewer.size();)
+	{
+		const Range r = s.deviceNewer[i];
+		if(r.lo < hi && r.hi > lo)
+		{
+			check(s.api.mem_download(s.ctx, (void *)r.lo, r.hi - r.lo), "swcu_mem_download");
+			s.deviceNewer.erase(s.deviceNewer.begin() + i);
+			any = true;
+		}
+		else i++;
+	}
+	if(any) check(s.api.sync(s.ctx), "swcu_sync");
 }
 
 swcu_attachment attachment(vk::ImageView *view, VkImageAspectFlagBits aspect, int layer, int samples)
@@ -203,10 +230,57 @@ void onFree(void *base)
 	}
 	check(s.api.mem_unregister(s.ctx, base), "swcu_mem_unregister");
 	s.allocations.erase(it);
+	s.mapped.erase((uintptr_t)base);
+}
+
+DrawScope::DrawScope() { tl_drawScope++; }
+DrawScope::~DrawScope() { tl_drawScope--; }
+
+void hostAccess(const void *base, size_t bytes)
+{
+	if(tl_drawScope > 0 || !base) return;
+	std::lock_guard<std::mutex> lock(S().mutex);
+	if(!S().on || S().deviceNewer.empty()) return;
+	makeHostCurrent((uintptr_t)base, (uintptr_t)base + bytes);
+}
+
+void onMap(const void *base)
+{
+	std::lock_guard<std::mutex> lock(S().mutex);
+	if(S().on && base) S().mapped[(uintptr_t)base] = true;
+}
+
+bool resolve(vk::ImageView *src, vk::ImageView *dst)
+{
+	DrawScope scope;
+	std::lock_guard<std::mutex> lock(S().mutex);
+	State &s = S();
+	if(!s.on || !src || !dst) return false;
+	const VkFormat fs = (VkFormat)src->getFormat(VK_IMAGE_ASPECT_COLOR_BIT), fd = (VkFormat)dst->getFormat(VK_IMAGE_ASPECT_COLOR_BIT);
+	if(fs != fd || (fs != VK_FORMAT_R8G8B8A8_UNORM && fs != VK_FORMAT_B8G8R8A8_UNORM)) return false;
+	if(src->getSampleCount() != 4 || dst->getSampleCount() != 1) return false;
+	if(src->getSubresourceRange().layerCount != 1 || dst->getSubresourceRange().layerCount != 1) return false;
+	const VkExtent2D es = src->getMipLevelExtent(0), ed = dst->getMipLevelExtent(0);
+	if(es.width != ed.width || es.height != ed.height) return false;
+	swcu_attachment a = {}, b = {};
+	a.buffer = src->getOffsetPointer({ 0, 0, 0 }, VK_IMAGE_ASPECT_COLOR_BIT, 0, 0);
+	a.format = (uint32_t)fs; a.pitchB = src->rowPitchBytes(VK_IMAGE_ASPECT_COLOR_BIT, 0); a.sliceB = src->slicePitchBytes(VK_IMAGE_ASPECT_COLOR_BIT, 0);
+	a.width = es.width; a.height = es.height;
+	b.buffer = dst->getOffsetPointer({ 0, 0, 0 }, VK_IMAGE_ASPECT_COLOR_BIT, 0, 0);
+	b.format = (uint32_t)fd; b.pitchB = dst->rowPitchBytes(VK_IMAGE_ASPECT_COLOR_BIT, 0); b.sliceB = dst->slicePitchBytes(VK_IMAGE_ASPECT_COLOR_BIT, 0);
+	b.width = ed.width; b.height = ed.height;
+	const size_t srcBytes = (size_t)a.sliceB * 4, dstBytes = (size_t)b.pitchB * b.height;
+	if(!deviceIsNewer((uintptr_t)a.buffer, (uintptr_t)a.buffer + srcBytes)) uploadRange(a.buffer, srcBytes);  // (the source was last written on the host)
+	check(s.api.resolve(s.ctx, &a, 4, &b), "swcu_resolve");
+	// every pixel of the target is written: the device copy is the current one from here on
+	const uintptr_t lo = (uintptr_t)b.buffer, hi = lo + dstBytes;
+	if(!deviceIsNewer(lo, hi)) s.deviceNewer.push_back({ lo, hi });
+	return true;
 }
 
 void draw(const DrawArgs &args)
 {
+	DrawScope scope;
 	std::lock_guard<std::mutex> lock(S().mutex);
 	State &s = S();
 	const vk::GraphicsState &state = *args.state;
@@ -329,9 +403,20 @@ void synchronize()
 	std::lock_guard<std::mutex> lock(S().mutex);
 	State &s = S();
 	if(!s.on) return;
-	// whoever touches the attachments on the host next (Framebuffer::resolve, a copy command, a mapped read) finds them current
-	for(const Range &r : s.deviceNewer) check(s.api.mem_download(s.ctx, (void *)r.lo, r.hi - r.lo), "swcu_mem_download");
-	s.deviceNewer.clear();
+	// an application reads a mapped allocation through its own pointer once the fence has signalled: those come down here; every
+	// other attachment stays on the device until somebody asks for a host pointer into its allocation (hostAccess)
+	for(size_t i = 0; i < s.deviceNewer.size();)
+	{
+		const Range r = s.deviceNewer[i];
+		uintptr_t base;
+		size_t bytes;
+		if(findAllocation(r.lo, base, bytes) && s.mapped.count(base))
+		{
+			check(s.api.mem_download(s.ctx, (void *)r.lo, r.hi - r.lo), "swcu_mem_download");
+			s.deviceNewer.erase(s.deviceNewer.begin() + i);
+		}
+		else i++;
+	}
 	check(s.api.sync(s.ctx), "swcu_sync");
 }
 

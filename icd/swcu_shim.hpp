@@ -5,6 +5,9 @@
 //   * DrawCall::run at the end of Renderer::draw (Renderer.cpp:489)            -> swcu_shim::draw      -> swcu_draw
 //   * Renderer::synchronize (Renderer.cpp:664-671)                             -> swcu_shim::synchronize -> downloads + swcu_sync
 //   * DeviceMemory::allocateBuffer / freeBuffer (src/Vulkan/VkDeviceMemory.cpp:340-356) -> swcu_mem_register / _unregister
+//   * DeviceMemory::getOffsetPointer / map (VkDeviceMemory.cpp:293-309): whoever asks for a host pointer into an allocation gets
+//     host memory that is current — attachments the device has drawn to come down first (and only then)
+//   * ImageView::resolve (src/Vulkan/VkImageView.cpp:284-312), the end-of-pass multisample resolve    -> swcu_resolve on the shadows
 // libswcuda.so is loaded with dlopen at the first use (SWCU_LIB, or next to the ICD): the ICD has no link-time CUDA dependency.
 // SWCU_ICD=0 leaves the reference's own routines in charge (one binary, A/B by environment, never a silent fallback: a draw the
 // CUDA path rejects aborts with its error text).
@@ -17,6 +20,7 @@
 
 namespace vk {
 class Device;
+class ImageView;
 class GraphicsPipeline;
 class GraphicsState;
 struct Inputs;
@@ -50,7 +54,22 @@ struct DrawArgs
 };
 void draw(const DrawArgs &args);
 
-// Renderer::synchronize: everything drawn so far is in host memory again when this returns
+// Renderer::synchronize: every draw issued so far has finished; attachments in host-MAPPED allocations are current in host memory
+// (an application reads those through its own pointer).  Other attachments stay resident on the device until somebody asks for a
+// pointer into their allocation (hostAccess).
 void synchronize();
+
+// DeviceMemory::getOffsetPointer: the caller is about to read or write [base, base + bytes) on the host
+void hostAccess(const void *base, size_t bytes);
+void onMap(const void *base);
+// while one is alive on this thread, hostAccess does nothing: the pointers Renderer::draw gathers are handed to the device, not read
+struct DrawScope
+{
+	DrawScope();
+	~DrawScope();
+};
+
+// ImageView::resolve: true if the 4x -> 1x resolve has been done on the device shadows (Blitter::fastResolve's arithmetic)
+bool resolve(vk::ImageView *src, vk::ImageView *dst);
 
 }  // namespace swcu_shim

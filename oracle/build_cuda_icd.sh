@@ -1,9 +1,9 @@
 #!/bin/bash
 # Builds the reference ICD WITH the CUDA draw path wired in behind sw::Renderer::draw:
 #   oracle/_cuda/libvk_swiftshader_cuda.so  =  the object files of the unmodified ICD build (oracle/build_ref.sh, $SS_BUILD_DIR)
-#                                            with Renderer.cpp and VkDeviceMemory.cpp replaced by patched copies (icd/swiftshader_cuda.patch)
+#                                            with Renderer.cpp, VkDeviceMemory.cpp and VkImageView.cpp replaced by patched copies (icd/swiftshader_cuda.patch)
 #                                            plus icd/swcu_shim.cpp.
-# Nothing is written under /root/reference and no reference source is copied into this repository: the two files are copied to a
+# Nothing is written under /root/reference and no reference source is copied into this repository: the three files are copied to a
 # scratch directory, patched there, compiled with the very command lines of the reference's own build (ninja -t commands) and linked
 # with the reference's own link line.  libswcuda.so is NOT linked: the shim dlopens it (SWCU_LIB, or ../../swiftshader_b200/csrc/).
 set -euo pipefail
@@ -18,6 +18,7 @@ if [ ! -f "$BUILD/build.ninja" ]; then echo "no ICD build tree at $BUILD: run or
 mkdir -p "$OUT" "$SCRATCH/src/Device" "$SCRATCH/src/Vulkan" "$SCRATCH/obj"
 cp "$REF/src/Device/Renderer.cpp" "$SCRATCH/src/Device/Renderer.cpp"
 cp "$REF/src/Vulkan/VkDeviceMemory.cpp" "$SCRATCH/src/Vulkan/VkDeviceMemory.cpp"
+cp "$REF/src/Vulkan/VkImageView.cpp" "$SCRATCH/src/Vulkan/VkImageView.cpp"
 (cd "$SCRATCH" && patch -s -p1 < "$REPO/icd/swiftshader_cuda.patch")
 cd "$BUILD"
 ninja -t commands vk_swiftshader > "$SCRATCH/commands.txt"
@@ -33,6 +34,7 @@ compile() { # <like: source path in the reference> <source to compile> <object o
 }
 compile "$REF/src/Device/Renderer.cpp" "$SCRATCH/src/Device/Renderer.cpp" "$SCRATCH/obj/Renderer.cpp.o" "$REF/src/Device"
 compile "$REF/src/Vulkan/VkDeviceMemory.cpp" "$SCRATCH/src/Vulkan/VkDeviceMemory.cpp" "$SCRATCH/obj/VkDeviceMemory.cpp.o" "$REF/src/Vulkan"
+compile "$REF/src/Vulkan/VkImageView.cpp" "$SCRATCH/src/Vulkan/VkImageView.cpp" "$SCRATCH/obj/VkImageView.cpp.o" "$REF/src/Vulkan"
 compile "$REF/src/Vulkan/VkDeviceMemory.cpp" "$REPO/icd/swcu_shim.cpp" "$SCRATCH/obj/swcu_shim.cpp.o" "$REF/src/Vulkan"
 # libvk_device.a with the patched Renderer
 cp "$BUILD/src/Device/libvk_device.a" "$SCRATCH/obj/libvk_device_cuda.a"
@@ -44,6 +46,7 @@ link="${link#: && }"
 link="${link%% && cd *}"   # (what follows only copies the library around the build tree)
 link="${link//-o libvk_swiftshader.so/-o $OUT/libvk_swiftshader_cuda.so}"
 link="${link//src\/Vulkan\/CMakeFiles\/vk_swiftshader.dir\/VkDeviceMemory.cpp.o/$SCRATCH/obj/VkDeviceMemory.cpp.o $SCRATCH/obj/swcu_shim.cpp.o}"
+link="${link//src\/Vulkan\/CMakeFiles\/vk_swiftshader.dir\/VkImageView.cpp.o/$SCRATCH/obj/VkImageView.cpp.o}"
 link="${link//src\/Device\/libvk_device.a/$SCRATCH/obj/libvk_device_cuda.a}"
 link="$(echo "$link" | sed -E 's# -Wl,--dependency-file=[^ ]+##')"
 eval "$link -ldl"
