@@ -1544,34 +1544,42 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 	float *smDepth = (float *)(wv + ((FS || colorEpp == 1) ? 0 : L::PLANE_B * colorEpp));
 	unsigned char *smStencil = (unsigned char *)smDepth + (d.depthTestActive ? L::PLANE_B : 0);
 
-	// ---- stage the region: TMA when the attachments allow it ----
+	// ---- stage the region: TMA when the attachments allow it.  (A second time if the optimistic pass below has to be redone:
+	//      nothing has been stored by then, the attachments still hold what they held.) ----
 	bool tileReady = true;
-	if(d.useTma)
-	{
-		if(lane == 0)
+	uint32_t tmaPhase = 0;
+	auto stage_region = [&](bool first) {
+		if(d.useTma)
 		{
-			mbar_init(bar, 1);
-			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-			const uint32_t bytes = (colorOn ? L::PLANE_B * colorEpp : 0) + (d.depthTestActive ? (d.depth16 ? L::PLANE_B / 2 : L::PLANE_B) : 0) + (d.stencilActive ? L::STENCIL_B : 0);
-			mbar_expect_tx(bar, bytes);
-			if(colorOn) tma_load_3d(smColor, &maps.color, bar, rx * colorEpp, ry, 0); // the map counts 32-bit words along x
-			if(d.depthTestActive) tma_load_3d(smDepth, &maps.depth, bar, rx, ry, 0);
-			if(d.stencilActive) tma_load_3d(smStencil, &maps.stencil, bar, rx, ry, 0);
+			if(lane == 0)
+			{
+				if(first)
+				{
+					mbar_init(bar, 1);
+					asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+				}
+				const uint32_t bytes = (colorOn ? L::PLANE_B * colorEpp : 0) + (d.depthTestActive ? (d.depth16 ? L::PLANE_B / 2 : L::PLANE_B) : 0) + (d.stencilActive ? L::STENCIL_B : 0);
+				mbar_expect_tx(bar, bytes);
+				if(colorOn) tma_load_3d(smColor, &maps.color, bar, rx * colorEpp, ry, 0); // the map counts 32-bit words along x
+				if(d.depthTestActive) tma_load_3d(smDepth, &maps.depth, bar, rx, ry, 0);
+				if(d.stencilActive) tma_load_3d(smStencil, &maps.stencil, bar, rx, ry, 0);
+			}
+			__syncwarp();
+			tileReady = false;
 		}
-		__syncwarp();
-		tileReady = false;
-	}
-	else
-	{
-		const int yEnd = min(ry + SWCU_REGION_H, d.fbHeight);
-		if(colorOn && colorEpp == 4) region_copy<MS, uint4, false>((uint4 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
-		else if(colorOn && colorEpp == 2) region_copy<MS, uint2, false>((uint2 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
-		else if(colorOn) region_copy<MS, uint32_t, false>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
-		if(d.depthTestActive && d.depth16) region_copy<MS, unsigned short, false>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
-		else if(d.depthTestActive) region_copy<MS, float, false>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
-		if(d.stencilActive) region_copy<MS, unsigned char, false>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
-		__syncwarp();
-	}
+		else
+		{
+			const int yEnd = min(ry + SWCU_REGION_H, d.fbHeight);
+			if(colorOn && colorEpp == 4) region_copy<MS, uint4, false>((uint4 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+			else if(colorOn && colorEpp == 2) region_copy<MS, uint2, false>((uint2 *)smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+			else if(colorOn) region_copy<MS, uint32_t, false>(smColor, d.colorBuf, d.colorPitchB, d.colorSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+			if(d.depthTestActive && d.depth16) region_copy<MS, unsigned short, false>((unsigned short *)smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+			else if(d.depthTestActive) region_copy<MS, float, false>(smDepth, d.depthBuf, d.depthPitchB, d.depthSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+			if(d.stencilActive) region_copy<MS, unsigned char, false>(smStencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, rx, ry, d.fbWidth, ry, yEnd, lane);
+			__syncwarp();
+		}
+	};
+	stage_region(true);
 
 	bool dirty = false;
 	uint32_t constChan = 0; // colour channels that are shader constants
@@ -1596,11 +1604,34 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 		}
 	}
 
-	// ---- the bin in triangle order ----
+	// ---- the bin in triangle order — or, 1x, optimistically NOT: the order of the fragments only matters where two of them land on
+	//      the same sample.  A bin of a mesh without overdraw is walked as k_fill left it, every sample signing the owner array
+	//      as it is written; the first sample found signed already (or signed twice in one round) abandons the pass: the region is
+	//      staged again — nothing has been stored — and the bin is walked once more, sorted.  Order-free bins skip the sort; bins
+	//      with overdraw pay for the part of the first pass they got through ----
 	const uint32_t *list = d.pairs + begin;
 	uint32_t regId = 0xFFFFFFFFu;
 	bool sortedInSmem = false, listInPlace = false;
-	if(!d.direct)
+	const bool optimisticBin = MS == 1 && !d.direct && n > 32 && n <= SWCU_SORT_CAP;
+	bool redo = false;
+	for(int pass = 0; pass < 2; pass++)
+	{
+	const bool optimistic = optimisticBin && pass == 0;
+	if(pass == 1)
+	{
+		if(!tileReady)
+			while(!mbar_try_wait(bar, tmaPhase)) {}
+		tmaPhase ^= 1u;
+		stage_region(false);
+		dirty = false;
+		redo = false;
+	}
+	if(optimistic)
+	{
+		((uint32_t *)wOwner)[lane] = 0xFFFFFFFFu; // 128 samples, nobody has signed yet
+		__syncwarp();
+	}
+	if(!d.direct && !optimistic)
 	{
 		if(n <= 32)
 		{
@@ -1689,7 +1720,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 	uint32_t idN;
 	uint4 hN;
 	fetch_block(0, idN, hN);
-	for(uint32_t pos0 = 0; pos0 < n; pos0 += 32)
+	for(uint32_t pos0 = 0; pos0 < n && !redo; pos0 += 32)
 	{
 		const uint32_t li = pos0 + lane;
 		bool valid = li < n;
@@ -1715,7 +1746,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 		const uint32_t bigMask = __ballot_sync(0xFFFFFFFFu, isBig);
 		const int cnt = (int)min(32u, n - pos0);
 		int p = 0;
-		while(p < cnt)
+		while(p < cnt && !redo)
 		{
 			uint32_t total = 0;
 			const uint32_t rest = bigMask >> p;
@@ -1870,12 +1901,12 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 			__syncwarp();
 			if(total && !tileReady)
 			{
-				while(!mbar_try_wait(bar, 0)) {} // the TMA loads of the region have landed
+				while(!mbar_try_wait(bar, tmaPhase)) {} // the TMA loads of the region have landed
 				tileReady = true;
 			}
 			// ---- consume the items 32 at a time, one covered PIXEL per lane: interpolation and the routed shader run once per pixel
 			//      (PixelRoutine.cpp:196-261), stencil / depth / blend / write once per covered sample of it (:124-148, :262-358) ----
-			for(uint32_t base = 0; base < total; base += 32)
+			for(uint32_t base = 0; base < total && !redo; base += 32)
 			{
 				const uint32_t g = base + lane;
 				const bool live = g < total;
@@ -1903,6 +1934,12 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 				// two fragments of this round on one SAMPLE?  Every lane signs its samples; a lane that reads back another signature has
 				// company.  (Two triangles that share an edge pixel with disjoint samples — every edge of a mesh — are not a conflict.)
 				bool shared = false;
+				if(MS == 1 && optimistic)
+				{
+					// signed in an earlier round of this pass?  Then two fragments meet on the sample and the walk needs the order
+					if(live && wOwner[pkey] != 0xFFu) shared = true;
+					__syncwarp();
+				}
 				if(live)
 				{
 #pragma unroll
@@ -1917,7 +1954,13 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 						if(((smask >> q) & 1u) && wOwner[q * REGION_PX + pkey] != (unsigned char)lane) shared = true;
 				}
 				int prank = 0, maxRank = 0;
-				if(__any_sync(0xFFFFFFFFu, shared)) // overlapping triangles: the items of a pixel run in list order
+				const bool anyShared = __any_sync(0xFFFFFFFFu, shared);
+				if(MS == 1 && optimistic && anyShared)
+				{
+					redo = true; // (warp-uniform) nothing of this round has been applied
+					break;
+				}
+				if(anyShared) // overlapping triangles: the items of a pixel run in list order
 				{
 					const uint32_t peers = __match_any_sync(0xFFFFFFFFu, live ? pkey : (0x200u | (uint32_t)lane));
 					prank = __popc(peers & laneLt);
@@ -1990,10 +2033,20 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 							rgba[ch] = (!FS && colorEpp > 1) ? val : sse_min(sse_max(val, 0.0f), 1.0f);
 						}
 						const uint32_t frontFacing = FS ? 1u : (flagsk & TRI_FLAG_FRONT);
+						float premul[3] = { 0, 0, 0 }; // source colour times source alpha: the first product of the SRC_ALPHA blend, the same for every sample
+						if(BL == BL_SRC_ALPHA)
+						{
+#pragma unroll
+							for(int ch = 0; ch < 3; ch++) premul[ch] = fmul(rgba[ch], rgba[3]);
+						}
 
 						// ---- per covered sample: stencil test, depth test, depth write, blend + colour write, stencil write ----
+#ifdef TILE_SAMPLE_LOOP_ROLLED
 #pragma unroll 1
-						for(int q = 0; q < MS; q++)
+#else
+#pragma unroll
+#endif
+						for(int q = 0; q < MS; q++) // (unrolled: the sample offsets and plane strides of each copy are constants)
 						{
 							if(!((smask >> q) & 1u)) continue;
 							const int pi = q * REGION_PX + (int)pkey; // index inside the staged planes
@@ -2091,9 +2144,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 										}
 										if(BL == BL_SRC_ALPHA)
 										{
-											const float sa = rgba[3], da = fsub(1.0f, rgba[3]);
+											const float da = fsub(1.0f, rgba[3]);
 #pragma unroll
-											for(int ch = 0; ch < 3; ch++) o[ch] = fadd(fmul(rgba[ch], sa), fmul(dst[ch], da));
+											for(int ch = 0; ch < 3; ch++) o[ch] = fadd(premul[ch], fmul(dst[ch], da));
 										}
 										else
 										{
@@ -2156,8 +2209,11 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 		}
 	}
 
+	if(!redo) break;
+	} // pass
+
 	if(!tileReady)
-		while(!mbar_try_wait(bar, 0)) {} // never leave with a bulk copy into this CTA's shared memory still in flight
+		while(!mbar_try_wait(bar, tmaPhase)) {} // never leave with a bulk copy into this CTA's shared memory still in flight
 	if(!__any_sync(0xFFFFFFFFu, dirty)) return;
 	// Only rows inside the scissor go back: the rows of a region that the scissor cuts off may belong to another rank's band of
 	// the same frame (multi-GPU), whose pixels this warp has staged but must not overwrite.
