@@ -299,8 +299,13 @@ DEVI bool edge_at_row(const DrawConst &d, int Xa, int Ya, int Xb, int Yb, int y,
 	const long long DX = X2 - X1, DY = Y2 - Y1;
 	const long long N = DX * (256ll * y - Y1) + (long long)(X1 & 255) * DY;
 	const long long D = 256ll * DY;
-	long long qv = N / D;
-	if(N % D > 0) qv += 1; // ceiling
+	// ceil(N / D), exactly: a double-precision estimate of the quotient (|N| < 2^46, 0 < D < 2^31, so it is off by one at most),
+	// put right with the integer remainder — a 64-bit integer division costs several times as many instructions
+	long long qv = __double2ll_rd(__ddiv_rn((double)N, (double)D));
+	long long rem = N - qv * D;
+	while(rem < 0) { rem += D; qv -= 1; }
+	while(rem >= D) { rem -= D; qv += 1; }
+	if(rem > 0) qv += 1; // ceiling
 	xo = clampi((X1 >> 8) + (int)qv, d.scX0, d.scX1);
 	right = swap;
 	return true;
@@ -1749,70 +1754,123 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 		while(p < cnt && !redo)
 		{
 			uint32_t total = 0;
+			bool oneCandidate = false; // the queue holds the pixels of a single triangle: no two of them on the same sample
 			const uint32_t rest = bigMask >> p;
 			if(rest & 1u)
 			{
-				// ---- BIG: up to BIG_GROUP consecutive big entries; lane -> (entry, row, sample); the span of the row in closed form
-				//      (SetupRoutine::edge as edge_at_row: the last edge that owns the row wins; 4x: pre-filled, SetupRoutine.cpp:214-225) ----
-				int group = 1;
-				if(BIG_GROUP > 1) group = min(BIG_GROUP, rest == 0xFFFFFFFFu ? 32 : (int)__ffs(~rest) - 1);
-				const int c = lane / (SWCU_REGION_H * MS), row = (lane / MS) % SWCU_REGION_H, q = lane % MS;
-				const int src = min(p + c, 31);
-				const uint32_t bslot = __shfl_sync(0xFFFFFFFFu, h.w, src);
-				int a = 0, e = 0;
-				const int y = ry + row;
-				if(c < group && y >= ryLo && y < ryHi && (MS == 1 || FS || ((d.sampleMask >> q) & 1)))
+				if(MS == 1)
 				{
-					const BigTri &b = d.bigList[bslot];
-					if(y >= b.yMin && y < b.yMax)
+					// ---- BIG, 1x: one entry; lane -> (row, edge slot): the four lanes of a row evaluate the polygon's edges 4 at a time in
+					//      closed form (SetupRoutine::edge as edge_at_row) and keep, for the left and the right end of the span, the hit
+					//      of the LAST edge that owns the row (the reference's span table is written edge after edge) ----
+					const int row = lane >> 2, es = lane & 3;
+					const uint32_t bslot = __shfl_sync(0xFFFFFFFFu, h.w, p);
+					const int y = ry + row;
+					int Lx = 0, Li = -1, Rx = 0, Ri = -1;
+					if(y >= ryLo && y < ryHi)
 					{
-						const int ox = MS > 1 ? c_Xf[q] : 0, oy = MS > 1 ? c_Yf[q] : 0;
-						int Ls = 0, Rs = 0;
-						if(MS > 1) Ls = Rs = clampi((int)((uint32_t)b.X[0] + 255u) >> 8, d.scX0, d.scX1);
-						const int bn = b.n, bdir = b.dir;
-						for(int i = 0; i < bn; i++)
+						const BigTri &b = d.bigList[bslot];
+						if(y >= b.yMin && y < b.yMax)
 						{
-							const int ia = i + 1 - bdir, ib = i + bdir;
-							const int va = ia == bn ? 0 : ia, vb = ib == bn ? 0 : ib;
-							bool right; int x;
-							if(edge_at_row(d, b.X[va] - ox, b.Y[va] - oy, b.X[vb] - ox, b.Y[vb] - oy, y, right, x)) { if(right) Rs = x; else Ls = x; }
+							const int bn = b.n, bdir = b.dir;
+							for(int i = es; i < bn; i += 4)
+							{
+								const int ia = i + 1 - bdir, ib = i + bdir;
+								const int va = ia == bn ? 0 : ia, vb = ib == bn ? 0 : ib;
+								bool right; int x;
+								if(edge_at_row(d, b.X[va], b.Y[va], b.X[vb], b.Y[vb], y, right, x)) { if(right) { Rx = x; Ri = i; } else { Lx = x; Li = i; } }
+							}
 						}
-						a = clampi(Ls - rx, 0, SWCU_REGION_W); e = clampi(Rs - rx, 0, SWCU_REGION_W);
 					}
-				}
-				// pixel items: at 4x the four sample lanes of a row exchange their runs; lane q of the row takes the columns [4q, 4q + 4)
-				const uint32_t run = e > a ? ((1u << e) - 1u) & ~((1u << a) - 1u) : 0u; // columns of the region my (row, sample) covers
-				uint32_t cols, sm0 = run, sm1 = 0, sm2 = 0, sm3 = 0;
-				if(MS == 4)
-				{
-					const uint32_t r1 = __shfl_xor_sync(0xFFFFFFFFu, run, 1), r2 = __shfl_xor_sync(0xFFFFFFFFu, run, 2), r3 = __shfl_xor_sync(0xFFFFFFFFu, run, 3);
-					// runs by SAMPLE number: lane q holds sample q, its partner under xor j holds sample q ^ j
-					sm0 = q == 0 ? run : q == 1 ? r1 : q == 2 ? r2 : r3;
-					sm1 = q == 1 ? run : q == 0 ? r1 : q == 3 ? r2 : r3;
-					sm2 = q == 2 ? run : q == 3 ? r1 : q == 0 ? r2 : r3;
-					sm3 = q == 3 ? run : q == 2 ? r1 : q == 1 ? r2 : r3;
-					cols = (sm0 | sm1 | sm2 | sm3) & (0xFu << (4 * q));
-				}
-				else cols = run;
-				const int nn = __popc(cols);
-				uint32_t incl = (uint32_t)nn;
 #pragma unroll
-				for(int o = 1; o < 32; o <<= 1)
-				{
-					const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-					if(lane >= o) incl += t;
+					for(int o = 1; o <= 2; o <<= 1)
+					{
+						const int oLx = __shfl_xor_sync(0xFFFFFFFFu, Lx, o), oLi = __shfl_xor_sync(0xFFFFFFFFu, Li, o);
+						const int oRx = __shfl_xor_sync(0xFFFFFFFFu, Rx, o), oRi = __shfl_xor_sync(0xFFFFFFFFu, Ri, o);
+						if(oLi > Li) { Li = oLi; Lx = oLx; }
+						if(oRi > Ri) { Ri = oRi; Rx = oRx; }
+					}
+					// (a side no edge owns keeps 0, the value the reference's cleared span entry holds)
+					const int a = clampi(Lx - rx, 0, SWCU_REGION_W), e = clampi(Rx - rx, 0, SWCU_REGION_W);
+					const int nrow = e > a ? e - a : 0;       // the same in the four lanes of the row
+					uint32_t incl = es == 0 ? (uint32_t)nrow : 0u;
+#pragma unroll
+					for(int o = 1; o < 32; o <<= 1)
+					{
+						const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+						if(lane >= o) incl += t;
+					}
+					total = __shfl_sync(0xFFFFFFFFu, incl, 31); // <= 128
+					const uint32_t start = __shfl_sync(0xFFFFFFFFu, incl, lane & ~3) - (uint32_t)nrow; // first item of my row
+					const uint32_t item = ((uint32_t)p << 11) | (1u << 7) | ((uint32_t)row << 4);
+					for(int i = es; i < nrow; i += 4) wQueue[start + i] = (unsigned short)(item | (uint32_t)(a + i)); // every fourth pixel of the run
+					p += 1;
+					oneCandidate = true;
 				}
-				total = __shfl_sync(0xFFFFFFFFu, incl, 31); // <= 128 pixels (4x) / 32 runs of <= 16 pixels (1x): never more than ICAP
-				uint32_t w = incl - (uint32_t)nn;
-				const uint32_t item = ((uint32_t)(p + c) << 11) | ((uint32_t)row << 4);
-				while(cols)
+				else
 				{
-					const uint32_t x = (uint32_t)__ffs(cols) - 1u;
-					cols &= cols - 1u;
-					const uint32_t sm = MS == 4 ? (((sm0 >> x) & 1u) | (((sm1 >> x) & 1u) << 1) | (((sm2 >> x) & 1u) << 2) | (((sm3 >> x) & 1u) << 3)) : 1u;
-					wQueue[w++] = (unsigned short)(item | (sm << 7) | x);
-				}
+					// ---- BIG: up to BIG_GROUP consecutive big entries; lane -> (entry, row, sample); the span of the row in closed form
+					//      (SetupRoutine::edge as edge_at_row: the last edge that owns the row wins; 4x: pre-filled, SetupRoutine.cpp:214-225) ----
+					int group = 1;
+					if(BIG_GROUP > 1) group = min(BIG_GROUP, rest == 0xFFFFFFFFu ? 32 : (int)__ffs(~rest) - 1);
+					const int c = lane / (SWCU_REGION_H * MS), row = (lane / MS) % SWCU_REGION_H, q = lane % MS;
+					const int src = min(p + c, 31);
+					const uint32_t bslot = __shfl_sync(0xFFFFFFFFu, h.w, src);
+					int a = 0, e = 0;
+					const int y = ry + row;
+					if(c < group && y >= ryLo && y < ryHi && (MS == 1 || FS || ((d.sampleMask >> q) & 1)))
+					{
+						const BigTri &b = d.bigList[bslot];
+						if(y >= b.yMin && y < b.yMax)
+						{
+							const int ox = MS > 1 ? c_Xf[q] : 0, oy = MS > 1 ? c_Yf[q] : 0;
+							int Ls = 0, Rs = 0;
+							if(MS > 1) Ls = Rs = clampi((int)((uint32_t)b.X[0] + 255u) >> 8, d.scX0, d.scX1);
+							const int bn = b.n, bdir = b.dir;
+							for(int i = 0; i < bn; i++)
+							{
+								const int ia = i + 1 - bdir, ib = i + bdir;
+								const int va = ia == bn ? 0 : ia, vb = ib == bn ? 0 : ib;
+								bool right; int x;
+								if(edge_at_row(d, b.X[va] - ox, b.Y[va] - oy, b.X[vb] - ox, b.Y[vb] - oy, y, right, x)) { if(right) Rs = x; else Ls = x; }
+							}
+							a = clampi(Ls - rx, 0, SWCU_REGION_W); e = clampi(Rs - rx, 0, SWCU_REGION_W);
+						}
+					}
+					// pixel items: at 4x the four sample lanes of a row exchange their runs; lane q of the row takes the columns [4q, 4q + 4)
+					const uint32_t run = e > a ? ((1u << e) - 1u) & ~((1u << a) - 1u) : 0u; // columns of the region my (row, sample) covers
+					uint32_t cols, sm0 = run, sm1 = 0, sm2 = 0, sm3 = 0;
+					if(MS == 4)
+					{
+						const uint32_t r1 = __shfl_xor_sync(0xFFFFFFFFu, run, 1), r2 = __shfl_xor_sync(0xFFFFFFFFu, run, 2), r3 = __shfl_xor_sync(0xFFFFFFFFu, run, 3);
+						// runs by SAMPLE number: lane q holds sample q, its partner under xor j holds sample q ^ j
+						sm0 = q == 0 ? run : q == 1 ? r1 : q == 2 ? r2 : r3;
+						sm1 = q == 1 ? run : q == 0 ? r1 : q == 3 ? r2 : r3;
+						sm2 = q == 2 ? run : q == 3 ? r1 : q == 0 ? r2 : r3;
+						sm3 = q == 3 ? run : q == 2 ? r1 : q == 1 ? r2 : r3;
+						cols = (sm0 | sm1 | sm2 | sm3) & (0xFu << (4 * q));
+					}
+					else cols = run;
+					const int nn = __popc(cols);
+					uint32_t incl = (uint32_t)nn;
+	#pragma unroll
+					for(int o = 1; o < 32; o <<= 1)
+					{
+						const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+						if(lane >= o) incl += t;
+					}
+					total = __shfl_sync(0xFFFFFFFFu, incl, 31); // <= 128 pixels (4x) / 32 runs of <= 16 pixels (1x): never more than ICAP
+					uint32_t w = incl - (uint32_t)nn;
+					const uint32_t item = ((uint32_t)(p + c) << 11) | ((uint32_t)row << 4);
+					while(cols)
+					{
+						const uint32_t x = (uint32_t)__ffs(cols) - 1u;
+						cols &= cols - 1u;
+						const uint32_t sm = MS == 4 ? (((sm0 >> x) & 1u) | (((sm1 >> x) & 1u) << 1) | (((sm2 >> x) & 1u) << 2) | (((sm3 >> x) & 1u) << 3)) : 1u;
+						wQueue[w++] = (unsigned short)(item | (sm << 7) | x);
+					}
 				p += group;
+				}
 			}
 			else
 			{
@@ -1934,6 +1992,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 				// two fragments of this round on one SAMPLE?  Every lane signs its samples; a lane that reads back another signature has
 				// company.  (Two triangles that share an edge pixel with disjoint samples — every edge of a mesh — are not a conflict.)
 				bool shared = false;
+				const bool noCheck = oneCandidate && !optimistic; // (an optimistic pass still has to sign the samples for the rounds to come)
+				if(!noCheck)
+				{
 				if(MS == 1 && optimistic)
 				{
 					// signed in an earlier round of this pass?  Then two fragments meet on the sample and the walk needs the order
@@ -1953,8 +2014,9 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 					for(int q = 0; q < MS; q++)
 						if(((smask >> q) & 1u) && wOwner[q * REGION_PX + pkey] != (unsigned char)lane) shared = true;
 				}
+				}
 				int prank = 0, maxRank = 0;
-				const bool anyShared = __any_sync(0xFFFFFFFFu, shared);
+				const bool anyShared = !noCheck && __any_sync(0xFFFFFFFFu, shared);
 				if(MS == 1 && optimistic && anyShared)
 				{
 					redo = true; // (warp-uniform) nothing of this round has been applied
