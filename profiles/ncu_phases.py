@@ -7,21 +7,26 @@ import sys
 
 MARKERS = [  # (phase, substring of the first line of the phase), in file order
     ("helpers", "small helpers (Reactor semantics"),
+    ("vertex+clip", "DEVI uint32_t fetch_index"),
+    ("spans", "SetupRoutine::edge (SetupRoutine.cpp:550-621), row-stepping form"),
+    ("setup", "DEVI void rot1("),
+    ("binning", "Can a fragment of big triangle b land in region"),
     ("sampler", "DEVI uint32_t mulhi16"),
     ("pixhelp", "DEVI bool stencil_compare"),
     ("tile-prolog", "FS (\"fast state\")"),
-    ("scan", "list scan with look-ahead"),
-    ("admit", "hits join the batch in list order"),
-    ("planes-stage", "plane equations of the batch -> shared memory"),
-    ("coverage-L", "coverage (QuadRasterizer.cpp:181-206), one candidate per lane"),
-    ("scan-place", "where do my pairs and items start"),
-    ("coverage", "coverage (QuadRasterizer.cpp:181-206)"),
-    ("psum", "first item of each pair"),
-    ("item-find", "consume the items 32 at a time"),
-    ("item-planes", "plane equations of the triangle ----"),
+    ("bin-order", "the bin in triangle order"),
+    ("fetch", "32 bin entries at a time, one per lane; the ids"),
+    ("cover-big1x", "BIG, 1x: one entry"),
+    ("cover-big", "BIG: up to BIG_GROUP"),
+    ("cover-small", "SMALL: lanes [p, hi) clip"),
+    ("expand", "producer-side expansion: item ="),
+    ("queue-wait", "the TMA loads of the region have landed"),
+    ("item-fetch", "consume the items 32 at a time"),
+    ("item-planes", "plane equations of the item's triangle"),
+    ("conflict", "two fragments of this round on one SAMPLE"),
     ("item-shade", "interpolate + routed fragment shader"),
-    ("item-tests", "stencil test, depth test, depth write"),
-    ("item-blend", "const uint32_t px = smColor[pi];"),
+    ("item-tests", "per covered sample: stencil test"),
+    ("item-blend", "const uint32_t px = floatTarget"),
     ("item-stencilw", "writeStencil :754-817"),
     ("tile-epilog", "never leave with a bulk copy"),
     ("after", "the steps either side of the draw"),

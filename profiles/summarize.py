@@ -38,9 +38,8 @@ def launch_table(path):
     return "\n".join(out)
 
 
-def raw_metrics(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(txt)))
+def raw_metrics(rawcsv):
+    rows = list(csv.reader(open(rawcsv)))
     if len(rows) < 3:
         return "(no rows)"
     hdr, units = rows[0], rows[1]
@@ -60,11 +59,27 @@ def raw_metrics(rep):
     return "\n".join(out)
 
 
-def hot_lines(rep, kernel_regex, skip, top=25):
+def hot_lines(srccsv, kernel, top=25):
+    """the hottest CUDA lines of the first function of the source-page export whose name contains `kernel`"""
+    rows = list(csv.reader(open(srccsv)))
+    out, keep, fn, taken = [], False, None, False
+    pend = []
+    for r in rows:
+        if r and r[0] == "File Path":
+            pend = [r]
+            keep = False
+            continue
+        if r and r[0] == "Function Name":
+            fn = r[1]
+            keep = (kernel in fn.split("(")[0]) and pend and pend[0][1].endswith("kernels.cuh")
+            if keep:
+                out += pend
+            pend = []
+        if keep:
+            out.append(r)
     tmp = "/tmp/_src_page.csv"
-    with open(tmp, "w") as f:
-        subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", f"regex:{kernel_regex}",
-                        "--launch-skip", str(skip), "--launch-count", "1"], stdout=f, stderr=subprocess.DEVNULL)
+    with open(tmp, "w", newline="") as f:
+        csv.writer(f).writerows(out)
     res = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "ncu_lines.py"), tmp, str(top)], capture_output=True, text=True)
     return res.stdout if res.returncode == 0 else f"(source page unavailable: {res.stderr[-200:]})"
 
@@ -103,18 +118,17 @@ def main():
     for p in sorted(glob.glob(os.path.join(src, "launches_*.csv"))):
         shutil.copy(p, dst)
         md += [f"## ncu launch list `{os.path.basename(p)}` (cold-cache, serialised: shares only)", "", launch_table(p), ""]
-    for p in sorted(glob.glob(os.path.join(src, "prof_*.ncu-rep"))):
-        name = os.path.basename(p)
-        md += [f"## `ncu --set full` {name} (the .ncu-rep itself stays in gpurun_out/: too large for the history)", "", raw_metrics(p), ""]
-        wl = name[len("prof_"):-len(".ncu-rep")]
+    for p in sorted(glob.glob(os.path.join(src, "raw_c*.csv"))):
+        wl = os.path.basename(p)[len("raw_"):-len(".csv")]
+        md += [f"## `ncu --set full` of the tile and setup kernels, workload {wl} (raw page)", "", raw_metrics(p), ""]
         srccsv = os.path.join(src, f"source_{wl}.csv")
         if os.path.exists(srccsv):
             warps = {"c4": 64800, "c5": 259200}.get(wl, 0)
             res = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "ncu_phases.py"), srccsv, "k_tile"] + ([str(warps)] if warps else []), capture_output=True, text=True)
             md += ["Tile kernel by phase (warp instructions, stall samples; SASS rows de-duplicated; profiles/ncu_phases.py):", "", "```", res.stdout.strip(), "```", ""]
-        md += ["Hottest CUDA lines of the tile kernel (share of warp instructions / of stall samples, top stall reasons):", "", "```",
-               hot_lines(p, "^k_tile$", 0).strip(), "```", ""]
-        md += ["Hottest CUDA lines of k_setup:", "", "```", hot_lines(p, "^k_setup(_1x)?$", 0, 15).strip(), "```", ""]
+            md += ["Hottest CUDA lines of the tile kernel (share of warp instructions / of stall samples, top stall reasons):", "", "```",
+                   hot_lines(srccsv, "k_tile").strip(), "```", ""]
+            md += ["Hottest CUDA lines of k_setup:", "", "```", hot_lines(srccsv, "k_setup", 15).strip(), "```", ""]
     open(os.path.join(dst, "SUMMARY.md"), "w").write("\n".join(md))
     print(f"wrote {dst}/SUMMARY.md")
 

@@ -27,11 +27,13 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'^(
   python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_full.log" 2>&1
 ncu -i "$OUT/prof_c4.ncu-rep" --page source --print-source cuda,sass --csv > "$OUT/source_c4.csv" 2>/dev/null
 ncu -i "$OUT/prof_c4.ncu-rep" --page raw --csv > "$OUT/raw_c4.csv" 2>/dev/null
+rm -f "$OUT/prof_c4.ncu-rep"   # (gpurun brings back at most 64 MiB: the CSV exports are what profiles/summarize.py reads)
 if [ "$MODE" != "quick" ]; then
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'^(k_tile|k_setup|k_setup_1x)$' -s 4 -c 2 -f -o "$OUT/prof_c5" \
   python bench.py --workload c5 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_full_c5.log" 2>&1
 ncu -i "$OUT/prof_c5.ncu-rep" --page source --print-source cuda,sass --csv > "$OUT/source_c5.csv" 2>/dev/null
 ncu -i "$OUT/prof_c5.ncu-rep" --page raw --csv > "$OUT/raw_c5.csv" 2>/dev/null
+rm -f "$OUT/prof_c5.ncu-rep"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches_c5.csv" \
   python bench.py --workload c5 --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/ncu_launch_c5.log" 2>&1
 fi
