@@ -304,7 +304,16 @@ void draw(const DrawArgs &args)
 	d.baseVertex = args.baseVertex;
 	if(args.indexBuffer)
 	{
-		const size_t n = vii.getTopology() == VK_PRIMITIVE_TOPOLOGY_TRIANGLE_LIST ? (size_t)args.count * 3 : (size_t)args.count + 2;
+		const size_t c = args.count;
+		size_t n;
+		switch(vii.getTopology())  // indices the draw fetches (setBatchIndices, Renderer.cpp:50-145)
+		{
+		case VK_PRIMITIVE_TOPOLOGY_POINT_LIST: n = c; break;
+		case VK_PRIMITIVE_TOPOLOGY_LINE_LIST: n = c * 2; break;
+		case VK_PRIMITIVE_TOPOLOGY_LINE_STRIP: n = c + 1; break;
+		case VK_PRIMITIVE_TOPOLOGY_TRIANGLE_LIST: n = c * 3; break;
+		default: n = c + 2; break;
+		}
 		uploadRange(args.indexBuffer, n * d.indexType);
 	}
 	for(int i = 0; i < SWCU_MAX_INPUTS; i++)  // DrawData::input / stride / robustnessSize (Renderer.cpp:282-288)
@@ -317,6 +326,10 @@ void draw(const DrawArgs &args)
 		d.input[i].format = (uint32_t)st.format;
 		uploadRange(st.buffer, st.robustnessSize);
 	}
+	// push constants as Renderer::draw copied them for this draw (Renderer.cpp:484-486), the line width of the pipeline (:276)
+	d.pushConstants = &args.data->pushConstants;
+	d.pushConstantBytes = (uint32_t)sizeof(args.data->pushConstants);
+	d.lineWidth = args.data->lineWidth;
 	d.vertexShader = vs->insns.data();    // SpirvShader.hpp:164 — what the pipeline holds after spirv-opt (VkPipeline.cpp:42-107)
 	d.vertexShaderWords = (uint32_t)vs->insns.size();
 	d.fragmentShader = fs->insns.data();

@@ -127,11 +127,11 @@ typedef struct swcu_draw_desc
 	uint32_t structSize; /* sizeof(swcu_draw_desc), ABI check */
 
 	/* --- input assembly: Renderer::draw(count, baseVertex, indexBuffer), DrawCall::processVertices (Renderer.cpp:600-628) */
-	uint32_t topology;            /* VkPrimitiveTopology */
+	uint32_t topology;            /* VkPrimitiveTopology: POINT_LIST 0, LINE_LIST 1, LINE_STRIP 2, TRIANGLE_LIST 3, TRIANGLE_STRIP 4, TRIANGLE_FAN 5 */
 	uint32_t provokingVertexMode; /* VkProvokingVertexModeEXT (0 = FIRST, reference default Context.hpp:329) */
 	uint32_t indexType;           /* 0 = non-indexed, 2 = uint16, 4 = uint32 (bytes per index) */
 	const void *indexBuffer;      /* host address of the first index of this draw (NULL when non-indexed) */
-	uint32_t primitiveCount;      /* number of triangles (Renderer::draw `count`) */
+	uint32_t primitiveCount;      /* number of primitives: triangles, lines or points (Renderer::draw `count`) */
 	int32_t baseVertex;           /* added to every index (firstVertex for non-indexed draws) */
 	swcu_vertex_input input[SWCU_MAX_INPUTS];
 
@@ -178,6 +178,13 @@ typedef struct swcu_draw_desc
 	swcu_attachment depth;
 	swcu_attachment stencil;
 
+	/* --- push constants of the draw (DrawData::pushConstants, Renderer.cpp:484-486): copied by swcu_draw */
+	const void *pushConstants;
+	uint32_t pushConstantBytes; /* <= 4 * SWCU_MAX_PUSH_WORDS */
+	/* --- lines (DrawData::lineWidth, Renderer.cpp:276; rectangle lines of DrawCall::setupLine, Renderer.cpp:920-1000 — the reference's
+	 *     default line rasterization mode; 0 is read as 1.0).  Points take their size from the vertex shader (gl_PointSize). */
+	float lineWidth;
+
 	/* --- descriptors visible to the fragment shader */
 	uint32_t sampledImageCount;
 	uint32_t reserved0;
@@ -188,11 +195,29 @@ typedef struct swcu_draw_desc
 #define SWCU_SRC_INPUT 0 /* value = location*4 + component of a stage input */
 #define SWCU_SRC_CONST 1 /* value = IEEE-754 bits of a float constant */
 #define SWCU_SRC_TEXEL 2 /* fragment only: value = component of the OpImageSampleImplicitLod result */
+#define SWCU_SRC_PUSH 3  /* vertex only: value = 32-bit word of the push-constant block (sw::DrawData::pushConstants, Renderer.hpp:110) */
+#define SWCU_SRC_TEMP 4  /* vertex only: value = index of the program step that computes it */
+/* The arithmetic a vertex shader does on its way from the inputs to gl_Position / the varyings (an MVP from push constants), lowered
+ * to straight-line steps with the reference's rounding: MUL / ADD / SUB / NEG are single IEEE operations (SpirvShaderArithmetic.cpp),
+ * FMA is Reactor's MulAdd — what OpMatrixTimesVector accumulates with (fused on every host with FMA, LLVMReactor.cpp:3082-3092). */
+#define SWCU_OP_MUL 0
+#define SWCU_OP_ADD 1
+#define SWCU_OP_SUB 2
+#define SWCU_OP_FMA 3 /* a * b + c, one rounding */
+#define SWCU_OP_NEG 4
+#define SWCU_MAX_PROGRAM 48
+#define SWCU_MAX_PUSH_WORDS 32 /* 128 bytes: vk::MAX_PUSH_CONSTANT_SIZE (src/Vulkan/VkConfig.hpp) */
 typedef struct swcu_shader_operand
 {
 	uint32_t kind;
 	uint32_t value;
 } swcu_shader_operand;
+
+typedef struct swcu_shader_op
+{
+	uint32_t op; /* SWCU_OP_* */
+	swcu_shader_operand a, b, c;
+} swcu_shader_op;
 
 typedef struct swcu_shader_info
 {
@@ -206,6 +231,10 @@ typedef struct swcu_shader_info
 	uint32_t usesTexture;          /* fragment: 1 if a combined image sampler is sampled */
 	uint32_t textureSet, textureBinding;
 	swcu_shader_operand texCoord[2]; /* fragment: u, v operands of the sample */
+	uint32_t programLength;          /* vertex: steps of the arithmetic program; step i defines SWCU_SRC_TEMP i */
+	swcu_shader_op program[SWCU_MAX_PROGRAM];
+	uint32_t writesPointSize;        /* vertex: gl_PointSize is stored (VertexRoutine.cpp:641-650); read by point draws only */
+	swcu_shader_operand pointSize;
 } swcu_shader_info;
 
 /* Counters for bench / tests. */

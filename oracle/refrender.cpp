@@ -40,7 +40,7 @@
 	X(vkGetBufferMemoryRequirements) X(vkBindBufferMemory) X(vkMapMemory) X(vkCreateShaderModule) X(vkCreatePipelineLayout)         \
 	X(vkCreateGraphicsPipelines) X(vkCreateCommandPool) X(vkAllocateCommandBuffers) X(vkBeginCommandBuffer) X(vkEndCommandBuffer)   \
 	X(vkCmdBeginRenderPass) X(vkCmdEndRenderPass) X(vkCmdBindPipeline) X(vkCmdBindVertexBuffers) X(vkCmdBindIndexBuffer)            \
-	X(vkCmdDraw) X(vkCmdDrawIndexed) X(vkCmdCopyImageToBuffer) X(vkQueueSubmit) X(vkQueueWaitIdle) X(vkCmdPipelineBarrier)          \
+	X(vkCmdDraw) X(vkCmdDrawIndexed) X(vkCmdPushConstants) X(vkCmdCopyImageToBuffer) X(vkQueueSubmit) X(vkQueueWaitIdle) X(vkCmdPipelineBarrier)          \
 	X(vkCreateSampler) X(vkCreateDescriptorSetLayout) X(vkCreateDescriptorPool) X(vkAllocateDescriptorSets)                         \
 	X(vkUpdateDescriptorSets) X(vkCmdBindDescriptorSets) X(vkCmdCopyBufferToImage) X(vkGetPhysicalDeviceProperties)
 #define DECL(n) static PFN_##n n;
@@ -339,6 +339,8 @@ int main(int argc, char **argv)
 		}
 		VkPipelineLayoutCreateInfo pli{ VK_STRUCTURE_TYPE_PIPELINE_LAYOUT_CREATE_INFO };
 		if(dsl) { pli.setLayoutCount = 1; pli.pSetLayouts = &dsl; }
+		VkPushConstantRange pcr{ VK_SHADER_STAGE_VERTEX_BIT, 0, d.pushConstantBytes };
+		if(d.pushConstantBytes) { pli.pushConstantRangeCount = 1; pli.pPushConstantRanges = &pcr; }
 		CHECK(vkCreatePipelineLayout(dev, &pli, nullptr, &o.layout));
 
 		VkShaderModule vsm, fsm;
@@ -371,7 +373,7 @@ int main(int argc, char **argv)
 		rs.polygonMode = VK_POLYGON_MODE_FILL;
 		rs.cullMode = d.cullMode;
 		rs.frontFace = (VkFrontFace)d.frontFace;
-		rs.lineWidth = 1;
+		rs.lineWidth = d.lineWidth != 0.0f ? d.lineWidth : 1.0f;
 		rs.depthBiasEnable = d.depthBiasEnable;
 		rs.depthBiasConstantFactor = d.depthBiasConstant;
 		rs.depthBiasClamp = d.depthBiasClamp;
@@ -449,6 +451,7 @@ int main(int argc, char **argv)
 			DrawObjects &o = objs[di];
 			vkCmdBindPipeline(c, VK_PIPELINE_BIND_POINT_GRAPHICS, o.pipeline[pass]);
 			if(o.dset) vkCmdBindDescriptorSets(c, VK_PIPELINE_BIND_POINT_GRAPHICS, o.layout, d.texSet, 1, &o.dset, 0, nullptr);
+			if(d.pushConstantBytes) vkCmdPushConstants(c, o.layout, VK_SHADER_STAGE_VERTEX_BIT, 0, d.pushConstantBytes, d.pushConstants);
 			VkDeviceSize off = 0;
 			vkCmdBindVertexBuffers(c, 0, 1, &o.vb, &off);
 			if(d.indexType)

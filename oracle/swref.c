@@ -43,7 +43,7 @@ enum
 	FMT_D32_SFLOAT = 126,
 	FMT_S8_UINT = 127,
 };
-enum { TOPO_TRIANGLE_LIST = 3, TOPO_TRIANGLE_STRIP = 4, TOPO_TRIANGLE_FAN = 5 };
+enum { TOPO_POINT_LIST = 0, TOPO_LINE_LIST = 1, TOPO_LINE_STRIP = 2, TOPO_TRIANGLE_LIST = 3, TOPO_TRIANGLE_STRIP = 4, TOPO_TRIANGLE_FAN = 5 };
 enum { CMP_NEVER, CMP_LESS, CMP_EQUAL, CMP_LESS_OR_EQUAL, CMP_GREATER, CMP_NOT_EQUAL, CMP_GREATER_OR_EQUAL, CMP_ALWAYS };
 enum { SOP_KEEP, SOP_ZERO, SOP_REPLACE, SOP_INC_CLAMP, SOP_DEC_CLAMP, SOP_INVERT, SOP_INC_WRAP, SOP_DEC_WRAP };
 enum
@@ -64,6 +64,17 @@ enum { ADDR_REPEAT = 0, ADDR_MIRRORED_REPEAT = 1, ADDR_CLAMP_TO_EDGE = 2 };
 /* Device/Clipper.hpp:28-41 */
 enum { CLIP_RIGHT = 1, CLIP_TOP = 2, CLIP_FAR = 4, CLIP_LEFT = 8, CLIP_BOTTOM = 16, CLIP_NEAR = 32, CLIP_FINITE = 128 };
 #define CLIP_FRUSTUM (CLIP_RIGHT | CLIP_TOP | CLIP_FAR | CLIP_LEFT | CLIP_BOTTOM | CLIP_NEAR)
+#define CLIP_SIDES (CLIP_LEFT | CLIP_RIGHT | CLIP_TOP | CLIP_BOTTOM) /* Clipper.hpp:41 */
+/* `lineWidth * 0.5f / sqrt(dx * dx + dy * dy)` of Renderer.cpp:965.  <cmath>'s unqualified sqrt on a float argument: which overload the
+ * reference build picks decides whether the quotient is formed in float or in double; pinned against the reference ICD's line goldens. */
+#ifndef SWREF_LINE_SQRT_DOUBLE
+#define SWREF_LINE_SQRT_DOUBLE 0
+#endif
+#if SWREF_LINE_SQRT_DOUBLE
+#define LINE_SCALE(lw, dx, dy) ((float)((double)((lw) * 0.5f) / sqrt((double)((dx) * (dx) + (dy) * (dy)))))
+#else
+#define LINE_SCALE(lw, dx, dy) ((lw) * 0.5f / sqrtf((dx) * (dx) + (dy) * (dy)))
+#endif
 
 #define OUTLINE_RESOLUTION 8192 /* Device/Config.hpp:20 */
 #define SUBPIX_B 8              /* Vulkan/VkConfig.hpp:101 (CMake build) */
@@ -88,6 +99,7 @@ typedef struct
 	int clipFlags;
 	int X, Y;     /* projected.x/.y, 24.8 fixed point */
 	float pz, pw; /* projected.z, projected.w (= rhw) */
+	float pointSize; /* gl_PointSize (VertexRoutine.cpp:641-650); 1.0 when the shader does not store it (the reference leaves it unset) */
 	float v[SWCU_MAX_VARYING_COMPONENTS];
 } Vertex;
 
@@ -119,6 +131,8 @@ typedef struct
 	int floatTarget, colorBpp; /* R32G32B32A32_SFLOAT / R16G16B16A16_SFLOAT colour attachment; bytes per pixel */
 	int numVaryings; /* packed interpolants = set bits of fs->inputMask */
 	int interpolateZ, interpolateW;
+	int prim; /* 0 = triangles, 1 = lines, 2 = points (SetupProcessor.cpp:71-73 isDrawTriangle / isDrawLine / isDrawPoint) */
+	float lineWidth, halfPixelX, halfPixelY; /* Renderer.cpp:276,317-318 */
 } Draw;
 
 /* x86 conversions used by Reactor: RoundInt = cvtps2dq, Int(float) = cvttps2dq (Reactor/LLVMReactor.cpp:135-138,2694-2703) */
@@ -160,10 +174,40 @@ static void read_stream(const swcu_vertex_input *in, uint32_t index, int baseVer
 	for(int i = 0; i < n; i++) out[i] = src[i];
 }
 
-static float operand(const swcu_shader_operand *op, float inputs[SWCU_MAX_INPUTS][4])
+/* One operand of the vertex stage: constant, input component, word of the push-constant block (DrawData::pushConstants, words the
+ * application never pushed read 0 here) or the result of an earlier step of the arithmetic program. */
+static float operand(const Draw *dr, const swcu_shader_operand *op, float inputs[SWCU_MAX_INPUTS][4], const float *temps)
 {
 	if(op->kind == SWCU_SRC_CONST) return as_float(op->value);
+	if(op->kind == SWCU_SRC_TEMP) return temps[op->value];
+	if(op->kind == SWCU_SRC_PUSH)
+	{
+		uint32_t w = 0;
+		if(4 * op->value + 4 <= dr->d->pushConstantBytes) memcpy(&w, (const char *)dr->d->pushConstants + 4 * op->value, 4);
+		return as_float(w);
+	}
 	return inputs[op->value >> 2][op->value & 3];
+}
+
+/* The straight-line arithmetic of the vertex stage (an MVP transform): SpirvShaderArithmetic.cpp:39-75,449-457,611-621.  MUL / ADD /
+ * SUB are single operations; FMA is Reactor's MulAdd = llvm.fmuladd, one rounding on a host with FMA units (LLVMReactor.cpp:4425-4429;
+ * this file is compiled with -mfma -ffp-contract=off, so fmaf() is the fused instruction and nothing else is contracted). */
+static void run_program(const Draw *dr, float inputs[SWCU_MAX_INPUTS][4], float *temps)
+{
+	const swcu_shader_info *vs = dr->vs;
+	for(uint32_t i = 0; i < vs->programLength && i < SWCU_MAX_PROGRAM; i++)
+	{
+		const swcu_shader_op *st = &vs->program[i];
+		float a = operand(dr, &st->a, inputs, temps);
+		switch(st->op)
+		{
+		case SWCU_OP_MUL: temps[i] = a * operand(dr, &st->b, inputs, temps); break;
+		case SWCU_OP_ADD: temps[i] = a + operand(dr, &st->b, inputs, temps); break;
+		case SWCU_OP_SUB: temps[i] = a - operand(dr, &st->b, inputs, temps); break;
+		case SWCU_OP_FMA: temps[i] = fmaf(a, operand(dr, &st->b, inputs, temps), operand(dr, &st->c, inputs, temps)); break;
+		default: temps[i] = as_float(as_uint(a) ^ 0x80000000u); break; /* SWCU_OP_NEG: LLVM fneg */
+		}
+	}
 }
 
 static void process_vertex(const Draw *dr, uint32_t index, Vertex *v)
@@ -175,11 +219,14 @@ static void process_vertex(const Draw *dr, uint32_t index, Vertex *v)
 		if(dr->vs->inputMask & (0xFu << (4 * l)) ) read_stream(&d->input[l], index, d->baseVertex, inputs[l]);
 		else { inputs[l][0] = inputs[l][1] = inputs[l][2] = 0; inputs[l][3] = 1; }
 	}
-	float px = operand(&dr->vs->position[0], inputs), py = operand(&dr->vs->position[1], inputs);
-	float pz = operand(&dr->vs->position[2], inputs), pw = operand(&dr->vs->position[3], inputs);
+	float temps[SWCU_MAX_PROGRAM];
+	run_program(dr, inputs, temps);
+	float px = operand(dr, &dr->vs->position[0], inputs, temps), py = operand(dr, &dr->vs->position[1], inputs, temps);
+	float pz = operand(dr, &dr->vs->position[2], inputs, temps), pw = operand(dr, &dr->vs->position[3], inputs, temps);
 	v->position.x = px; v->position.y = py; v->position.z = pz; v->position.w = pw;
 	for(int i = 0; i < SWCU_MAX_VARYING_COMPONENTS; i++)
-		v->v[i] = (dr->vs->outputMask >> i) & 1 ? operand(&dr->vs->output[i], inputs) : 0.0f;
+		v->v[i] = (dr->vs->outputMask >> i) & 1 ? operand(dr, &dr->vs->output[i], inputs, temps) : 0.0f;
+	v->pointSize = dr->vs->writesPointSize ? operand(dr, &dr->vs->pointSize, inputs, temps) : 1.0f;
 
 	/* computeClipFlags, VertexRoutine.cpp:128-152.  Reactor's CmpNLE / CmpNLT / CmpNEQ are ORDERED compares in the LLVM backend
 	 * (FCmpOGT / FCmpOGE / FCmpONE, LLVMReactor.cpp:3161-3180,4479-4495), not the x86 cmpnleps they are named after: a NaN w sets
@@ -342,7 +389,8 @@ static int setup_triangle(const Draw *dr, Primitive *prim, const Vertex *tv0, co
 	Y[0] = tv0->Y; Y[1] = tv1->Y; Y[2] = tv2->Y;
 
 	int dir = 1;
-	int clockwise;
+	int clockwise = 1; /* lines and points: clockwiseMask = 0xFF, no culling, winding as given (SetupRoutine.cpp:110-114) */
+	if(dr->prim == 0)
 	{ /* SetupRoutine.cpp:73-115 culling */
 		float x0 = (float)X[0], x1 = (float)X[1], x2 = (float)X[2];
 		float y0 = (float)Y[0], y1 = (float)Y[1], y2 = (float)Y[2];
@@ -357,7 +405,7 @@ static int setup_triangle(const Draw *dr, Primitive *prim, const Vertex *tv0, co
 	}
 
 	int n = poly->n;
-	if(poly->i != 0) /* clipped: reproject, SetupRoutine.cpp:125-145 */
+	if(poly->i != 0 || dr->prim != 0) /* clipped, or the quad of a line / point: reproject, SetupRoutine.cpp:120-145 */
 	{
 		for(int i = 0; i < n; i++)
 		{
@@ -410,14 +458,16 @@ static int setup_triangle(const Draw *dr, Primitive *prim, const Vertex *tv0, co
 	prim->yMax = yMax;
 	prim->clockwise = clockwise;
 
-	/* vertex sort, SetupRoutine.cpp:271-294 */
+	/* vertex sort, SetupRoutine.cpp:271-294 (triangles only) */
 	const Vertex *v0 = tv0, *v1 = tv1, *v2 = tv2;
+	if(dr->prim == 0)
 	{
 		float y0 = v0->position.y, y1 = v1->position.y, y2 = v2->position.y;
 		float ym = sse_min(sse_min(y0, y1), y2);
 		rotate1(ym == y1, &v0, &v1, &v2);
 		rotate2(ym == y2, &v0, &v1, &v2);
 	}
+	if(dr->prim == 0)
 	{
 		float w0 = v0->position.w, w1 = v1->position.w, w2 = v2->position.w;
 		float wm = sse_max(sse_max(w0, w1), w2);
@@ -429,6 +479,11 @@ static int setup_triangle(const Draw *dr, Primitive *prim, const Vertex *tv0, co
 	float w012[3] = { w0, w1, w2 };
 	float rhw0 = v0->pw;
 	int X0 = v0->X, X1 = v1->X, X2 = v2->X, Y0 = v0->Y, Y1 = v1->Y, Y2 = v2->Y;
+	if(dr->prim == 1) /* line: the third point of the plane equations is the second end point turned by 90 degrees, SetupRoutine.cpp:317-321 */
+	{
+		X2 = (int)((uint32_t)X1 + (uint32_t)Y1 - (uint32_t)Y0);
+		Y2 = (int)((uint32_t)Y1 + (uint32_t)X0 - (uint32_t)X1);
+	}
 	const float rsub = 1.0f / 256.0f;
 	float x0 = (float)X0 * rsub, y0 = (float)Y0 * rsub;
 	prim->x0 = x0; prim->y0 = y0;
@@ -464,11 +519,13 @@ static int setup_triangle(const Draw *dr, Primitive *prim, const Vertex *tv0, co
 		float D = dr->depthRange / (px1 * py2 - px2 * py1);
 		float A = (py2 * z1 - py1 * z2) * D;
 		float B = (px1 * z2 - px2 * z1) * D;
+		if(dr->prim == 2) { A = 0.0f; B = 0.0f; } /* point: constant depth, SetupRoutine.cpp:405-409 */
 		float C = z0 * dr->depthRange + dr->depthNear;
 		prim->z.A = A; prim->z.B = B; prim->z.C = C;
 		/* depth bias, SetupRoutine.cpp:417-475 (floating-point depth buffer branch) */
 		float bias = 0.0f;
 		int applyConst = d->depthBiasConstant != 0.0f, applySlope = d->depthBiasSlope != 0.0f;
+		if(dr->prim != 0) applyConst = applySlope = 0; /* SetupProcessor.cpp:75-77: isDrawTriangle(false, polygonMode) */
 		if(applyConst)
 		{
 			float r;
@@ -1223,6 +1280,19 @@ static void triangle_indices(const swcu_draw_desc *d, uint32_t i, uint32_t idx[3
 		idx[1] = fetch_index(d, i + (i & 1) + (pf ? 1 : 0));
 		idx[2] = fetch_index(d, i + (~i & 1) + (pf ? 1 : 0));
 		break;
+	case TOPO_POINT_LIST: /* Renderer.cpp:57-73 + VertexRoutine.cpp:74: the one vertex stands for all three */
+		idx[0] = idx[1] = idx[2] = fetch_index(d, i);
+		break;
+	case TOPO_LINE_LIST: /* Renderer.cpp:74-86 */
+		idx[0] = fetch_index(d, 2 * i + (pf ? 0 : 1));
+		idx[1] = fetch_index(d, 2 * i + (pf ? 1 : 0));
+		idx[2] = fetch_index(d, 2 * i + 1);
+		break;
+	case TOPO_LINE_STRIP: /* Renderer.cpp:87-99 */
+		idx[0] = fetch_index(d, i + (pf ? 0 : 1));
+		idx[1] = fetch_index(d, i + (pf ? 1 : 0));
+		idx[2] = fetch_index(d, i + 1);
+		break;
 	case TOPO_TRIANGLE_FAN:
 		idx[pf ? 0 : 2] = fetch_index(d, i + 1);
 		idx[pf ? 1 : 0] = fetch_index(d, i + 2);
@@ -1272,6 +1342,9 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 		dr.scissorY0 = CLAMPI(d->scissor.y, y0, y1);
 		dr.scissorY1 = CLAMPI(d->scissor.y + (int)d->scissor.height, y0, y1);
 	}
+	dr.prim = d->topology == TOPO_POINT_LIST ? 2 : ((d->topology == TOPO_LINE_LIST || d->topology == TOPO_LINE_STRIP) ? 1 : 0);
+	dr.lineWidth = d->lineWidth == 0.0f ? 1.0f : d->lineWidth;
+	dr.halfPixelX = 0.5f / (0.5f * d->viewportWidth); dr.halfPixelY = 0.5f / (0.5f * d->viewportHeight);
 	dr.ms = (int)d->sampleCount;
 	dr.enableMultiSampling = dr.ms > 1;
 	dr.depthTestActive = d->depthTestEnable && d->depth.buffer;
@@ -1306,14 +1379,52 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 		Vertex v[3];
 		for(int k = 0; k < 3; k++) process_vertex(&dr, idx[k], &v[k]);
 
+		Polygon poly;
+		if(dr.prim == 1)
+		{
+			/* DrawCall::setupLine, Renderer.cpp:920-1000: rectangle centred on the segment (the default line rasterization mode);
+			 * host C++ there, plain float operations here in the same order */
+			const f4 P0 = v[0].position, P1 = v[1].position;
+			if(P0.w <= 0 && P1.w <= 0) continue;
+			const float W = dr.WxF * (1.0f / 256.0f), H = dr.HxF * (1.0f / 256.0f);
+			float dx = W * (P1.x / P1.w - P0.x / P0.w);
+			float dy = H * (P1.y / P1.w - P0.y / P0.w);
+			if(dx == 0 && dy == 0) continue;
+			float scale = LINE_SCALE(dr.lineWidth, dx, dy);
+			dx *= scale; dy *= scale;
+			float dx0h = dx * P0.w / H, dy0w = dy * P0.w / W;
+			float dx1h = dx * P1.w / H, dy1w = dy * P1.w / W;
+			poly.P[0] = P0; poly.P[1] = P1; poly.P[2] = P1; poly.P[3] = P0;
+			poly.P[0].x += -dy0w; poly.P[0].y += +dx0h;
+			poly.P[1].x += -dy1w; poly.P[1].y += +dx1h;
+			poly.P[2].x += +dy1w; poly.P[2].y += -dx1h;
+			poly.P[3].x += +dy0w; poly.P[3].y += -dx0h;
+			poly.n = 4; poly.i = 0;
+			if(!clip_polygon(&poly, d->depthClipEnable ? CLIP_FRUSTUM : CLIP_SIDES)) continue;
+		}
+		else if(dr.prim == 2)
+		{
+			/* DrawCall::setupPoint, Renderer.cpp:1137-1185: a square of gl_PointSize pixels around the vertex */
+			const float pSize = v[0].pointSize < 1.0f ? 1.0f : (v[0].pointSize > 1023.0f ? 1023.0f : v[0].pointSize); /* clamp(): NaN passes through */
+			const float X = pSize * v[0].position.w * dr.halfPixelX, Y = pSize * v[0].position.w * dr.halfPixelY;
+			for(int k = 0; k < 4; k++) poly.P[k] = v[0].position;
+			poly.P[0].x -= X; poly.P[0].y += Y;
+			poly.P[1].x += X; poly.P[1].y += Y;
+			poly.P[2].x += X; poly.P[2].y -= Y;
+			poly.P[3].x -= X; poly.P[3].y -= Y;
+			poly.n = 4; poly.i = 0;
+			if(!clip_polygon(&poly, d->depthClipEnable ? CLIP_FRUSTUM : CLIP_SIDES)) continue;
+		}
+		else
+		{
 		/* setupSolidTriangles, Renderer.cpp:733-776 */
 		if((v[0].clipFlags & v[1].clipFlags & v[2].clipFlags) != CLIP_FINITE) continue;
-		Polygon poly;
 		poly.P[0] = v[0].position; poly.P[1] = v[1].position; poly.P[2] = v[2].position;
 		poly.n = 3; poly.i = 0;
 		int flagsOr = v[0].clipFlags | v[1].clipFlags | v[2].clipFlags;
 		if(flagsOr != CLIP_FINITE)
 			if(!clip_polygon(&poly, flagsOr)) continue;
+		}
 		if(!setup_triangle(&dr, prim, &v[0], &v[1], &v[2], &poly)) continue;
 		for(int q = 1; q < dr.ms; q++) /* planes live in the first Primitive only; copy what rasterize() reads */
 		{

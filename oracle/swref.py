@@ -66,7 +66,47 @@ def _texel(c: int):
     return (capi.SRC_TEXEL, c)
 
 
-def _vs(position, outputs: dict) -> capi.ShaderInfo:
+def _push(word: int):
+    return (capi.SRC_PUSH, word)
+
+
+def _temp(step: int):
+    return (capi.SRC_TEMP, step)
+
+
+class _Program:
+    """The scalar steps of a vertex shader's arithmetic, written down by hand in the reference's evaluation order."""
+
+    def __init__(self):
+        self.steps = []
+
+    def op(self, op, a, b=None, c=None):
+        z = _const(0.0)
+        self.steps.append((op, a, b or z, c or z))
+        return _temp(len(self.steps) - 1)
+
+    def mul(self, a, b):
+        return self.op(capi.OP_MUL, a, b)
+
+    def add(self, a, b):
+        return self.op(capi.OP_ADD, a, b)
+
+    def fma(self, a, b, c):
+        return self.op(capi.OP_FMA, a, b, c)
+
+    def mat4_times_vec4(self, first_word: int, v):
+        """OpMatrixTimesVector on a column-major mat4 at push-constant word `first_word` (SpirvShaderArithmetic.cpp:39-55):
+        row i = M[i,0] * v0, then MulAdd(M[i,j], vj, .) for j = 1..3"""
+        out = []
+        for i in range(4):
+            acc = self.mul(_push(first_word + i), v[0])
+            for j in range(1, 4):
+                acc = self.fma(_push(first_word + 4 * j + i), v[j], acc)
+            out.append(acc)
+        return out
+
+
+def _vs(position, outputs: dict, program: _Program | None = None, point_size=None) -> capi.ShaderInfo:
     s = capi.ShaderInfo()
     s.stage = 0
     inmask = 0
@@ -79,8 +119,36 @@ def _vs(position, outputs: dict) -> capi.ShaderInfo:
         s.outputMask |= 1 << comp
         if k == capi.SRC_INPUT:
             inmask |= 1 << v
+    if program is not None:
+        s.programLength = len(program.steps)
+        for i, (op, a, b, c) in enumerate(program.steps):
+            s.program[i] = capi.ShaderOp(op, capi.ShaderOperand(*a), capi.ShaderOperand(*b), capi.ShaderOperand(*c))
+            for (k, v) in (a, b, c):
+                if k == capi.SRC_INPUT:
+                    inmask |= 1 << v
+    if point_size is not None:
+        s.writesPointSize = 1
+        s.pointSize = capi.ShaderOperand(*point_size)
+        if point_size[0] == capi.SRC_INPUT:
+            inmask |= 1 << point_size[1]
     s.inputMask = inmask
     return s
+
+
+def _vs_mvp():
+    # gl_Position = pc.mvp * vec4(inPos, 1.0); outColor = inColor
+    p = _Program()
+    pos = p.mat4_times_vec4(0, [_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)])
+    return _vs(pos, {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2), 3: _inp(1, 3)}, p)
+
+
+def _vs_xform():
+    # p = inPos * pc.scale.xyz + pc.offset.xyz; gl_Position = vec4(p, pc.offset.w); outColor = inColor * pc.tint
+    p = _Program()
+    m = [p.mul(_inp(0, c), _push(c)) for c in range(3)]
+    q = [p.add(m[c], _push(4 + c)) for c in range(3)]
+    col = [p.mul(_inp(1, c), _push(8 + c)) for c in range(4)]
+    return _vs(q + [_push(7)], {c: col[c] for c in range(4)}, p)
 
 
 def _fs(colour, tex=None) -> capi.ShaderInfo:
@@ -118,6 +186,13 @@ SHADER_SPECS = {
     # gl_Position = inPos (vec4); outCol = inCol (vec4)
     "vs_pos4_col4": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _inp(0, 3)],
                                 {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2), 3: _inp(1, 3)}),
+    # gl_Position = pc.mvp * vec4(inPos, 1.0) with a mat4 in the push-constant block
+    "vs_mvp_pos3_col4": _vs_mvp,
+    # component-wise scale / offset / tint from the push-constant block
+    "vs_xform_pos3_col4": _vs_xform,
+    # gl_Position = inPos; gl_PointSize = inSize (loc 2); outColor = inColor
+    "vs_point_pos4_col4": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _inp(0, 3)],
+                                      {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2), 3: _inp(1, 3)}, point_size=_inp(2, 0)),
     "fs_white": lambda: _fs([_const(1.0)] * 4),
     "fs_col3": lambda: _fs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)]),
     "fs_col4": lambda: _fs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _inp(0, 3)]),

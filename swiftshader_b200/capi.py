@@ -72,6 +72,7 @@ class DrawDesc(C.Structure):
         ("srcAlphaBlendFactor", C.c_uint32), ("dstAlphaBlendFactor", C.c_uint32), ("alphaBlendOp", C.c_uint32),
         ("colorWriteMask", C.c_uint32), ("blendConstants", C.c_float * 4),
         ("color", Attachment), ("depth", Attachment), ("stencil", Attachment),
+        ("pushConstants", C.c_void_p), ("pushConstantBytes", C.c_uint32), ("lineWidth", C.c_float),
         ("sampledImageCount", C.c_uint32), ("reserved0", C.c_uint32),
         ("sampledImage", SampledImage * MAX_SAMPLED_IMAGES),
     ]
@@ -81,7 +82,14 @@ class ShaderOperand(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("value", C.c_uint32)]
 
 
-SRC_INPUT, SRC_CONST, SRC_TEXEL = 0, 1, 2
+SRC_INPUT, SRC_CONST, SRC_TEXEL, SRC_PUSH, SRC_TEMP = 0, 1, 2, 3, 4
+OP_MUL, OP_ADD, OP_SUB, OP_FMA, OP_NEG = 0, 1, 2, 3, 4
+MAX_PROGRAM = 48
+
+
+class ShaderOp(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("a", ShaderOperand), ("b", ShaderOperand), ("c", ShaderOperand)]
+
 
 
 class ShaderInfo(C.Structure):
@@ -89,7 +97,9 @@ class ShaderInfo(C.Structure):
                 ("position", ShaderOperand * 4), ("output", ShaderOperand * MAX_VARYING_COMPONENTS),
                 ("inputMask", C.c_uint32), ("flatMask", C.c_uint32), ("noPerspectiveMask", C.c_uint32),
                 ("usesTexture", C.c_uint32), ("textureSet", C.c_uint32), ("textureBinding", C.c_uint32),
-                ("texCoord", ShaderOperand * 2)]
+                ("texCoord", ShaderOperand * 2),
+                ("programLength", C.c_uint32), ("program", ShaderOp * MAX_PROGRAM),
+                ("writesPointSize", C.c_uint32), ("pointSize", ShaderOperand)]
 
 
 class Stats(C.Structure):

@@ -690,8 +690,8 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 {
 	memset(&d, 0, sizeof(d));
 	if(desc->structSize != sizeof(swcu_draw_desc)) return fail(ctx, SWCU_E_INVALID, "swcu_draw_desc.structSize %u != %zu", desc->structSize, sizeof(swcu_draw_desc));
-	if(desc->topology != TOPO_TRIANGLE_LIST && desc->topology != TOPO_TRIANGLE_STRIP && desc->topology != TOPO_TRIANGLE_FAN)
-		return fail(ctx, SWCU_E_UNSUPPORTED, "topology %u outside the subset (triangle list/strip/fan)", desc->topology);
+	if(desc->topology > TOPO_TRIANGLE_FAN)
+		return fail(ctx, SWCU_E_UNSUPPORTED, "topology %u outside the subset (point list, line list/strip, triangle list/strip/fan)", desc->topology);
 	if(desc->sampleCount != 1 && desc->sampleCount != 4) return fail(ctx, SWCU_E_UNSUPPORTED, "sample count %u unsupported (1 or 4)", desc->sampleCount);
 	if(desc->indexType != 0 && desc->indexType != 2 && desc->indexType != 4) return fail(ctx, SWCU_E_UNSUPPORTED, "index type %u unsupported", desc->indexType);
 	if(desc->provokingVertexMode > 1) return fail(ctx, SWCU_E_INVALID, "bad provoking vertex mode");
@@ -746,17 +746,30 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	{
 		// every index the draw fetches must lie inside the registered range: the kernels do no bounds checks on the index stream
 		// (the reference reads whatever follows an index buffer that is too short; a device library must not)
-		const size_t nIdx = desc->topology == TOPO_TRIANGLE_LIST ? (size_t)desc->primitiveCount * 3 : (size_t)desc->primitiveCount + 2;
+		const size_t pc = desc->primitiveCount;
+		const size_t nIdx = desc->topology == TOPO_TRIANGLE_LIST ? pc * 3 : desc->topology == TOPO_LINE_LIST ? pc * 2 : desc->topology == TOPO_LINE_STRIP ? pc + 1 :
+		                    desc->topology == TOPO_POINT_LIST ? pc : pc + 2;
 		d.indexBuffer = desc->primitiveCount ? dev_ptr(ctx, desc->indexBuffer, nIdx * desc->indexType) : dev_ptr(ctx, desc->indexBuffer);
 		if(!d.indexBuffer) return fail(ctx, SWCU_E_INVALID, "index buffer [%p, +%zu) is not inside a registered range", desc->indexBuffer, nIdx * desc->indexType);
 		if(find_shadow(ctx, desc->indexBuffer, 1)->external) d.inputsExternal = 1;
 	}
 	// vertex-stage scalars: component c of stream l, or a constant (VertexRoutine::readStream, VertexRoutine.cpp:173-245)
 	int vsrcErr = SWCU_OK;
+	// a 32-bit word of the draw's push-constant block (DrawData::pushConstants, Renderer.cpp:484-486); words the application never
+	// pushed read 0
+	if(desc->pushConstantBytes > 4 * SWCU_MAX_PUSH_WORDS || (desc->pushConstantBytes && !desc->pushConstants))
+		return fail(ctx, SWCU_E_INVALID, "bad push-constant block (%u bytes)", desc->pushConstantBytes);
+	auto push_word = [&](uint32_t w) -> uint32_t {
+		uint32_t v = 0;
+		if(4 * w + 4 <= desc->pushConstantBytes) memcpy(&v, (const unsigned char *)desc->pushConstants + 4 * w, 4);
+		return v;
+	};
 	auto vsrc = [&](const swcu_shader_operand &o) -> KVSrc {
 		KVSrc k;
 		k.ptr = nullptr; k.stride = 0; k.limit = 0xFFFFFFFFu; k.constant = 0.0f; k.pad = 0;
 		if(o.kind == SWCU_SRC_CONST) { memcpy(&k.constant, &o.value, 4); return k; }
+		if(o.kind == SWCU_SRC_PUSH) { const uint32_t v = push_word(o.value); memcpy(&k.constant, &v, 4); return k; }
+		if(o.kind == SWCU_SRC_TEMP) return k; // (the caller routes the step's result: posTemp / slotTemp)
 		const uint32_t l = o.value >> 2, c = o.value & 3;
 		const swcu_vertex_input &in = desc->input[l];
 		uint32_t ncomp;
@@ -780,14 +793,66 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		return k;
 	};
 
+	// ---- vertex-stage arithmetic: the translator's steps with their operands resolved for this draw ----
+	d.vsProgLen = vs.programLength;
+	if(vs.programLength > SWCU_MAX_PROGRAM) return fail(ctx, SWCU_E_INVALID, "vertex program too long");
+	{
+		uint32_t inKey[SWCU_VS_INPUTS], nIn = 0;
+		for(uint32_t i = 0; i < vs.programLength; i++)
+		{
+			const swcu_shader_operand *src[3] = { &vs.program[i].a, &vs.program[i].b, &vs.program[i].c };
+			KVsOperand *dst[3] = { &d.vsProg[i].a, &d.vsProg[i].b, &d.vsProg[i].c };
+			d.vsProg[i].op = vs.program[i].op;
+			for(int k = 0; k < 3; k++)
+			{
+				const swcu_shader_operand &o = *src[k];
+				if(o.kind == SWCU_SRC_CONST) *dst[k] = { VK_CONST, o.value };
+				else if(o.kind == SWCU_SRC_PUSH) *dst[k] = { VK_CONST, push_word(o.value) };
+				else if(o.kind == SWCU_SRC_TEMP)
+				{
+					if(o.value >= i) return fail(ctx, SWCU_E_INVALID, "vertex program step %u reads a later step", i);
+					*dst[k] = { VK_TEMP, o.value };
+				}
+				else
+				{
+					uint32_t j = 0;
+					while(j < nIn && inKey[j] != o.value) j++;
+					if(j == nIn)
+					{
+						if(nIn == SWCU_VS_INPUTS) return fail(ctx, SWCU_E_UNSUPPORTED, "vertex program reads more than %d attribute components", SWCU_VS_INPUTS);
+						inKey[nIn] = o.value;
+						d.vsIn[nIn++] = vsrc(o);
+					}
+					*dst[k] = { VK_INPUT, j };
+				}
+			}
+		}
+	}
+	auto temp_of = [](const swcu_shader_operand &o) -> int32_t { return o.kind == SWCU_SRC_TEMP ? (int32_t)o.value : -1; };
+
 	// ---- shader routing ----
-	for(int k = 0; k < 4; k++) d.vsPos[k] = vsrc(vs.position[k]);
+	for(int k = 0; k < 4; k++) { d.vsPos[k] = vsrc(vs.position[k]); d.posTemp[k] = temp_of(vs.position[k]); }
+	for(int k = 0; k < SWCU_MAXSLOTS; k++) d.slotTemp[k] = -1;
+	// ---- lines and points ----
+	d.primKind = desc->topology == TOPO_POINT_LIST ? PRIM_POINT : ((desc->topology == TOPO_LINE_LIST || desc->topology == TOPO_LINE_STRIP) ? PRIM_LINE : PRIM_TRIANGLE);
+	d.lineWidth = desc->lineWidth == 0.0f ? 1.0f : desc->lineWidth;
+	d.halfPixelX = 0.5f / (0.5f * desc->viewportWidth); d.halfPixelY = 0.5f / (0.5f * desc->viewportHeight);
+	{
+		const float one = 1.0f;
+		swcu_shader_operand opOne = { SWCU_SRC_CONST, 0 };
+		memcpy(&opOne.value, &one, 4);
+		d.pointSizeSrc = vsrc(vs.writesPointSize ? vs.pointSize : opOne);
+		d.pointSizeTemp = vs.writesPointSize ? temp_of(vs.pointSize) : -1;
+	}
 	const swcu_shader_operand opZero = { SWCU_SRC_CONST, 0 };
 	// a fragment-stage operand that reads an interpolated input becomes a plane slot fed by the vertex stage
 	auto slot_from = [&](const swcu_shader_operand &o, int slot) {
+		d.slotTemp[slot] = -1;
 		if(o.kind == SWCU_SRC_CONST) { d.slotSrc[slot] = vsrc(o); d.slotMode[slot] = IM_FLAT; return; }
 		const uint32_t c = o.value; // location*4 + component of the fragment input
-		d.slotSrc[slot] = vsrc(((vs.outputMask >> c) & 1) ? vs.output[c] : opZero); // never written by the vertex stage: 0
+		const swcu_shader_operand &vo = ((vs.outputMask >> c) & 1) ? vs.output[c] : opZero; // never written by the vertex stage: 0
+		d.slotSrc[slot] = vsrc(vo);
+		d.slotTemp[slot] = temp_of(vo);
 		d.slotMode[slot] = ((fs.flatMask >> c) & 1) ? IM_FLAT : (((fs.noPerspectiveMask >> c) & 1) ? IM_NOPERSP : IM_PERSP);
 	};
 	bool anySlot = false;
@@ -841,6 +906,11 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	d.cullMode = desc->cullMode; d.frontFace = desc->frontFace; d.depthClipEnable = desc->depthClipEnable;
 	d.depthBiasConstant = desc->depthBiasConstant; d.depthBiasSlope = desc->depthBiasSlope; d.depthBiasClamp = desc->depthBiasClamp;
 	d.depthBiasEnable = desc->depthBiasConstant != 0.0f || desc->depthBiasSlope != 0.0f;
+	if(d.primKind != PRIM_TRIANGLE) // SetupProcessor.cpp:75-77: depth bias applies to triangles only
+	{
+		d.depthBiasConstant = d.depthBiasSlope = d.depthBiasClamp = 0.0f;
+		d.depthBiasEnable = 0;
+	}
 
 	// ---- pixel state ----
 	d.depthTestActive = desc->depthTestEnable && desc->depth.buffer;
@@ -1155,7 +1225,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	if(!grouped) CU(cudaMemsetAsync(d.counters, 0, countersBytes, ss));
 	// band mode without a group: the scissor / render area keeps less than 3/4 of the framebuffer rows
 	d.cullFlags = nullptr;
-	if(!d.direct && !grouped && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
+	if(!d.direct && !grouped && !d.vsProgLen && d.primKind == PRIM_TRIANGLE && n >= 4096 && (long long)(d.scY1 - d.scY0) * 4 < (long long)d.fbHeight * 3)
 	{
 		if((rc = ensure(ctx, S.cullFlags, n))) return rc;
 		LaunchScope ls(ctx, "k_cull", ss);
@@ -1167,7 +1237,8 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		LaunchScope ls(ctx, "k_setup", ss);
 		const uint32_t share = d.triHi - d.triLo;
 		const size_t scratch = (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4;
-		if(d.ms != 1) k_setup<<<(share + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
+		if(d.vsProgLen || d.primKind != PRIM_TRIANGLE) k_setup_prog<<<(share + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d); // the vertex stage has arithmetic, or the primitives are lines / points
+		else if(d.ms != 1) k_setup<<<(share + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
 		else k_setup_1x<<<(share + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
 	}
 	if(grouped)

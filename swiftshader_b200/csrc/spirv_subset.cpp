@@ -3,7 +3,11 @@
 // Stands in for sw::SpirvShader's analysis of the two graphics stages (reference:
 // src/Pipeline/SpirvShader.cpp:947-961 interface slots, src/Pipeline/SpirvShader.hpp:761-782 decorations,
 // src/Pipeline/VertexProgram.cpp:75-94, src/Pipeline/PixelProgram.cpp:138-241) for the benchmark subset ONLY:
-//   vertex:   gl_Position and user varyings are copies / swizzles of vertex inputs and float constants;
+//   vertex:   gl_Position and user varyings are built from vertex inputs, float constants and the push-constant block with copies /
+//             swizzles and straight-line float arithmetic (OpFAdd / OpFSub / OpFMul / OpFNegate / OpVectorTimesScalar /
+//             OpMatrixTimesVector / OpVectorTimesMatrix / OpMatrixTimesScalar / OpDot): an MVP transform.  The arithmetic is lowered to
+//             a list of scalar steps with the reference's rounding (SpirvShaderArithmetic.cpp:39-75,449-457,611-621: products and
+//             sums are single operations, matrix and dot products accumulate with MulAdd);
 //   fragment: colour output 0 is built from interpolated inputs, float constants and at most one
 //             OpImageSampleImplicitLod of a combined image sampler whose coordinate is again such a value.
 // The result is an operand-routing table (swcu_shader_info); the kernels in kernels.cuh are specialised on it, so the
@@ -23,23 +27,24 @@ enum Op : uint32_t
 {
 	OpNop = 0, OpSourceContinued = 2, OpSource = 3, OpSourceExtension = 4, OpName = 5, OpMemberName = 6, OpString = 7, OpLine = 8,
 	OpExtension = 10, OpExtInstImport = 11, OpMemoryModel = 14, OpEntryPoint = 15, OpExecutionMode = 16, OpCapability = 17,
-	OpTypeVoid = 19, OpTypeBool = 20, OpTypeInt = 21, OpTypeFloat = 22, OpTypeVector = 23, OpTypeImage = 25, OpTypeSampler = 26,
+	OpTypeVoid = 19, OpTypeBool = 20, OpTypeInt = 21, OpTypeFloat = 22, OpTypeVector = 23, OpTypeMatrix = 24, OpTypeImage = 25, OpTypeSampler = 26,
 	OpTypeSampledImage = 27, OpTypeArray = 28, OpTypeStruct = 30, OpTypePointer = 32, OpTypeFunction = 33,
 	OpConstant = 43, OpConstantComposite = 44, OpFunction = 54, OpFunctionEnd = 56, OpVariable = 59, OpLoad = 61, OpStore = 62,
 	OpAccessChain = 65, OpInBoundsAccessChain = 66, OpDecorate = 71, OpMemberDecorate = 72, OpVectorShuffle = 79,
 	OpCompositeConstruct = 80, OpCompositeExtract = 81, OpCompositeInsert = 82, OpCopyObject = 83,
-	OpImageSampleImplicitLod = 87, OpLabel = 248, OpReturn = 253, OpNoLine = 317, OpModuleProcessed = 330,
+	OpImageSampleImplicitLod = 87, OpFNegate = 127, OpFAdd = 129, OpFSub = 131, OpFMul = 133, OpVectorTimesScalar = 142,
+	OpMatrixTimesScalar = 143, OpVectorTimesMatrix = 144, OpMatrixTimesVector = 145, OpDot = 148, OpLabel = 248, OpReturn = 253, OpNoLine = 317, OpModuleProcessed = 330,
 };
-enum { DecBlock = 2, DecBuiltIn = 11, DecNoPerspective = 13, DecFlat = 14, DecLocation = 30, DecComponent = 31, DecBinding = 33,
-	   DecDescriptorSet = 34, DecRelaxedPrecision = 0 };
+enum { DecBlock = 2, DecRowMajor = 4, DecColMajor = 5, DecMatrixStride = 7, DecBuiltIn = 11, DecNoPerspective = 13, DecFlat = 14, DecLocation = 30, DecComponent = 31, DecBinding = 33,
+	   DecDescriptorSet = 34, DecOffset = 35, DecRelaxedPrecision = 0 };
 enum { BuiltInPosition = 0, BuiltInPointSize = 1, BuiltInClipDistance = 3, BuiltInCullDistance = 4 };
-enum { SCUniformConstant = 0, SCInput = 1, SCOutput = 3 };
+enum { SCUniformConstant = 0, SCInput = 1, SCOutput = 3, SCPushConstant = 9 };
 
 struct Type
 {
-	enum Kind { None, Void, Float, Int, Vector, Struct, Pointer, Image, SampledImage, Function, Array } kind = None;
+	enum Kind { None, Void, Float, Int, Vector, Matrix, Struct, Pointer, Image, SampledImage, Function, Array } kind = None;
 	uint32_t elem = 0;  // vector/array/pointer/sampledimage: element / pointee / image type id
-	uint32_t count = 0; // vector: components
+	uint32_t count = 0; // vector: components; matrix: columns
 	uint32_t storage = 0;
 	std::vector<uint32_t> members;
 	bool image2D = false;
@@ -50,15 +55,20 @@ struct Deco
 	int location = -1, builtin = -1, binding = -1, set = -1, component = 0;
 	bool flat = false, noPersp = false, block = false;
 	std::map<uint32_t, int> memberBuiltin;
+	std::map<uint32_t, uint32_t> memberOffset, memberStride; // push-constant block members: Offset, MatrixStride
+	std::map<uint32_t, bool> memberRowMajor;
 };
 
 struct Value
 {
 	enum Kind { None, Vec, Pointer, SampledImage, IntConst } kind = None;
 	int n = 0;
-	swcu_shader_operand c[4];
+	swcu_shader_operand c[16]; // a matrix is held column by column: element (column j, row i) = c[j * rows + i]
+	int rows = 0;              // matrix: components per column (0 = not a matrix)
 	// pointer
 	uint32_t var = 0;
+	uint32_t pcType = 0, pcOffset = 0, pcStride = 0; // pointer into the push-constant block: pointee type, byte offset, stride between
+	bool pcRowMajor = false;                         //   the columns (ColMajor) / rows (RowMajor) of the matrix it points into
 	int member = -1;    // struct member index (gl_PerVertex)
 	int component = -1; // vector component selected by an access chain
 	uint32_t ival = 0;
@@ -166,6 +176,10 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			NEED(3);
 			ID(a[0]);
 			if(a[2] == DecBuiltIn) { NEED(4); decos[a[0]].memberBuiltin[a[1]] = (int)a[3]; }
+			else if(a[2] == DecOffset) { NEED(4); decos[a[0]].memberOffset[a[1]] = a[3]; }
+			else if(a[2] == DecMatrixStride) { NEED(4); decos[a[0]].memberStride[a[1]] = a[3]; }
+			else if(a[2] == DecColMajor) decos[a[0]].memberRowMajor[a[1]] = false;
+			else if(a[2] == DecRowMajor) decos[a[0]].memberRowMajor[a[1]] = true;
 			else if(a[2] != DecRelaxedPrecision) return fail("member decoration %u outside the subset", a[2]);
 			break;
 		case OpTypeVoid: NEED(1); ID(a[0]); types[a[0]].kind = Type::Void; break;
@@ -183,6 +197,11 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			NEED(3); ID(a[0]); ID(a[1]);
 			if(types[a[1]].kind != Type::Float || a[2] < 2 || a[2] > 4) return fail("only float vectors of 2..4 components are supported");
 			types[a[0]].kind = Type::Vector; types[a[0]].elem = a[1]; types[a[0]].count = a[2];
+			break;
+		case OpTypeMatrix:
+			NEED(3); ID(a[0]); ID(a[1]);
+			if(types[a[1]].kind != Type::Vector || a[2] < 2 || a[2] > 4) return fail("only float matrices of 2..4 columns are supported");
+			types[a[0]].kind = Type::Matrix; types[a[0]].elem = a[1]; types[a[0]].count = a[2];
 			break;
 		case OpTypeArray:
 			NEED(3); ID(a[0]); ID(a[1]);
@@ -238,10 +257,17 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			NEED(3); ID(a[0]); ID(a[1]);
 			if(na > 3) return fail("variable initialisers unsupported");
 			if(types[a[0]].kind != Type::Pointer) return fail("variable type is not a pointer");
-			if(a[2] != SCInput && a[2] != SCOutput && a[2] != SCUniformConstant) return fail("storage class %u outside the subset", a[2]);
+			if(a[2] != SCInput && a[2] != SCOutput && a[2] != SCUniformConstant && a[2] != SCPushConstant) return fail("storage class %u outside the subset", a[2]);
 			varType[a[1]] = a[0];
 			Value &v = values[a[1]];
 			v.kind = Value::Pointer; v.var = a[1];
+			if(a[2] == SCPushConstant)
+			{
+				// the push-constant block (sw::DrawData::pushConstants, Renderer.hpp:110): a Block struct of float scalars / vectors / matrices
+				if(model != 0) return fail("push constants are only supported in the vertex stage");
+				if(types[types[a[0]].elem].kind != Type::Struct) return fail("push-constant variable must be a Block struct");
+				v.pcType = types[a[0]].elem;
+			}
 			break;
 		}
 		case OpFunction:
@@ -262,6 +288,51 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 		{
 			NEED(4); ID(a[0]); ID(a[1]); ID(a[2]);
 			const Value &base = values[a[2]];
+			if(base.kind == Value::Pointer && base.pcType)
+			{
+				// into the push-constant block: member [, column [, row]] / member [, component], every index a constant
+				Value v = base;
+				for(uint32_t i = 3; i < na; i++)
+				{
+					ID(a[i]);
+					if(values[a[i]].kind != Value::IntConst) return fail("push-constant access chain index must be an integer constant");
+					const uint32_t idx = values[a[i]].ival;
+					const Type &t = types[v.pcType];
+					if(t.kind == Type::Struct)
+					{
+						if(idx >= t.members.size()) return fail("push-constant member index out of range");
+						const Deco &sd = decos[v.pcType];
+						auto off = sd.memberOffset.find(idx);
+						if(off == sd.memberOffset.end()) return fail("push-constant member without Offset");
+						v.pcOffset += off->second;
+						v.pcType = t.members[idx];
+						if(types[v.pcType].kind == Type::Matrix)
+						{
+							auto st = sd.memberStride.find(idx);
+							if(st == sd.memberStride.end()) return fail("matrix member without MatrixStride");
+							auto rm = sd.memberRowMajor.find(idx);
+							v.pcStride = st->second;
+							v.pcRowMajor = rm != sd.memberRowMajor.end() && rm->second;
+						}
+					}
+					else if(t.kind == Type::Matrix)
+					{
+						if(idx >= t.count) return fail("matrix column index out of range");
+						v.pcOffset += v.pcRowMajor ? 4 * idx : v.pcStride * idx; // column idx: its rows lie pcStride apart when RowMajor
+						v.pcType = t.elem;
+						if(!v.pcRowMajor) v.pcStride = 4;
+					}
+					else if(t.kind == Type::Vector)
+					{
+						if(idx >= t.count) return fail("component index out of range");
+						v.pcOffset += (v.pcStride ? v.pcStride : 4) * idx;
+						v.pcType = t.elem;
+					}
+					else return fail("push-constant access chain into an unsupported type");
+				}
+				values[a[1]] = v;
+				break;
+			}
 			if(base.kind != Value::Pointer || base.member >= 0 || base.component >= 0) return fail("access chain on an unsupported base");
 			if(na != 4) return fail("only single-index access chains are supported");
 			ID(a[3]);
@@ -285,6 +356,33 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			if(na > 3) return fail("memory access operands unsupported");
 			const Value &p = values[a[2]];
 			if(p.kind != Value::Pointer) return fail("load from a non-pointer");
+			if(p.pcType)
+			{
+				// scalar / vector / matrix of the push-constant block: one SWCU_SRC_PUSH operand per 32-bit word
+				const Type &t = types[p.pcType];
+				Value v; v.kind = Value::Vec;
+				auto word = [&](uint32_t byteOffset) -> swcu_shader_operand { return { SWCU_SRC_PUSH, byteOffset / 4 }; };
+				bool bad = false;
+				auto check = [&](uint32_t byteOffset) { if((byteOffset & 3) || byteOffset / 4 >= SWCU_MAX_PUSH_WORDS) bad = true; return byteOffset; };
+				if(t.kind == Type::Float) { v.n = 1; v.c[0] = word(check(p.pcOffset)); }
+				else if(t.kind == Type::Vector)
+				{
+					v.n = (int)t.count;
+					for(int i = 0; i < v.n; i++) v.c[i] = word(check(p.pcOffset + (p.pcStride ? p.pcStride : 4) * i));
+				}
+				else if(t.kind == Type::Matrix)
+				{
+					const int rows = (int)types[t.elem].count, cols = (int)t.count;
+					v.n = rows * cols; v.rows = rows;
+					for(int j = 0; j < cols; j++)
+						for(int i = 0; i < rows; i++)
+							v.c[j * rows + i] = word(check(p.pcOffset + (p.pcRowMajor ? p.pcStride * i + 4 * j : p.pcStride * j + 4 * i)));
+				}
+				else return fail("load of an unsupported push-constant type");
+				if(bad) return fail("push-constant access beyond %d bytes or unaligned", 4 * SWCU_MAX_PUSH_WORDS);
+				values[a[1]] = v;
+				break;
+			}
 			const Type &pt = types[varType[p.var]];
 			const Type &obj = types[pt.elem];
 			const Deco &d = decos[p.var];
@@ -327,7 +425,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			{
 				ID(a[i]);
 				const Value &e = values[a[i]];
-				if(e.kind != Value::Vec) return fail("composite construct from a non-value");
+				if(e.kind != Value::Vec || e.rows) return fail("composite construct from a non-value");
 				for(int k = 0; k < e.n; k++) { if(v.n >= 4) return fail("vector too long"); v.c[v.n++] = e.c[k]; }
 			}
 			if(v.n != (int)types[a[0]].count) return fail("composite construct arity mismatch");
@@ -338,6 +436,16 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 		{
 			NEED(4); ID(a[1]); ID(a[2]);
 			const Value &s = values[a[2]];
+			if(s.kind == Value::Vec && s.rows) // column (and row) of a matrix
+			{
+				const uint32_t cols = (uint32_t)(s.n / s.rows);
+				if((na != 4 && na != 5) || a[3] >= cols || (na == 5 && a[4] >= (uint32_t)s.rows)) return fail("unsupported matrix extract");
+				Value v; v.kind = Value::Vec;
+				if(na == 5) { v.n = 1; v.c[0] = s.c[a[3] * s.rows + a[4]]; }
+				else { v.n = s.rows; for(int i = 0; i < s.rows; i++) v.c[i] = s.c[a[3] * s.rows + i]; }
+				values[a[1]] = v;
+				break;
+			}
 			if(s.kind != Value::Vec || na != 4 || a[3] >= (uint32_t)s.n) return fail("unsupported composite extract");
 			Value v; v.kind = Value::Vec; v.n = 1; v.c[0] = s.c[a[3]];
 			values[a[1]] = v;
@@ -348,7 +456,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			NEED(5); ID(a[1]); ID(a[2]); ID(a[3]);
 			const Value &obj = values[a[2]];
 			Value v = values[a[3]];
-			if(obj.kind != Value::Vec || obj.n != 1 || v.kind != Value::Vec || na != 5 || a[4] >= (uint32_t)v.n) return fail("unsupported composite insert");
+			if(obj.kind != Value::Vec || obj.n != 1 || v.kind != Value::Vec || v.rows || na != 5 || a[4] >= (uint32_t)v.n) return fail("unsupported composite insert");
 			v.c[a[4]] = obj.c[0];
 			values[a[1]] = v;
 			break;
@@ -357,7 +465,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 		{
 			NEED(4); ID(a[1]); ID(a[2]); ID(a[3]);
 			const Value &x = values[a[2]], &y = values[a[3]];
-			if(x.kind != Value::Vec || y.kind != Value::Vec || na - 4 > 4 || na - 4 < 2) return fail("unsupported vector shuffle");
+			if(x.kind != Value::Vec || y.kind != Value::Vec || x.rows || y.rows || na - 4 > 4 || na - 4 < 2) return fail("unsupported vector shuffle");
 			Value v; v.kind = Value::Vec;
 			for(uint32_t i = 4; i < na; i++)
 			{
@@ -367,6 +475,80 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 				else if(s < (uint32_t)(x.n + y.n)) v.c[v.n++] = y.c[s - x.n];
 				else return fail("shuffle index out of range");
 			}
+			values[a[1]] = v;
+			break;
+		}
+		case OpFNegate: case OpFAdd: case OpFSub: case OpFMul: case OpVectorTimesScalar: case OpMatrixTimesScalar:
+		case OpMatrixTimesVector: case OpVectorTimesMatrix: case OpDot:
+		{
+			// straight-line float arithmetic of the vertex stage -> scalar program steps (SpirvShaderArithmetic.cpp)
+			NEED(3); ID(a[0]); ID(a[1]); ID(a[2]);
+			if(model != 0) return fail("arithmetic in the fragment stage is outside the subset (opcode %u)", op);
+			const bool unary = op == OpFNegate;
+			if(!unary) { NEED(4); ID(a[3]); }
+			const Value &x = values[a[2]];
+			const Value &y = unary ? x : values[a[3]];
+			if(x.kind != Value::Vec || y.kind != Value::Vec) return fail("arithmetic on a non-value (opcode %u)", op);
+			bool full = false;
+			auto emit = [&](uint32_t o, swcu_shader_operand p0, swcu_shader_operand p1, swcu_shader_operand p2) -> swcu_shader_operand {
+				if(out->programLength >= SWCU_MAX_PROGRAM) { full = true; return { SWCU_SRC_CONST, 0 }; }
+				swcu_shader_op &st = out->program[out->programLength];
+				st.op = o; st.a = p0; st.b = p1; st.c = p2;
+				return { SWCU_SRC_TEMP, out->programLength++ };
+			};
+			const swcu_shader_operand none = { SWCU_SRC_CONST, 0 };
+			Value v; v.kind = Value::Vec;
+			switch(op)
+			{
+			case OpFNegate:
+				if(x.rows) return fail("matrix negate outside the subset");
+				v.n = x.n;
+				for(int i = 0; i < x.n; i++) v.c[i] = emit(SWCU_OP_NEG, x.c[i], none, none);
+				break;
+			case OpFAdd: case OpFSub: case OpFMul:
+				if(x.rows || y.rows || x.n != y.n || x.n > 4) return fail("component-wise arithmetic on mismatched or matrix operands");
+				v.n = x.n;
+				for(int i = 0; i < x.n; i++) v.c[i] = emit(op == OpFAdd ? SWCU_OP_ADD : op == OpFSub ? SWCU_OP_SUB : SWCU_OP_MUL, x.c[i], y.c[i], none);
+				break;
+			case OpVectorTimesScalar: case OpMatrixTimesScalar: // :57-75 pattern: lhs.Float(i) * rhs.Float(0)
+				if(y.n != 1 || (op == OpVectorTimesScalar && x.rows) || (op == OpMatrixTimesScalar && !x.rows)) return fail("bad operands of a times-scalar product");
+				v.n = x.n; v.rows = x.rows;
+				for(int i = 0; i < x.n; i++) v.c[i] = emit(SWCU_OP_MUL, x.c[i], y.c[0], none);
+				break;
+			case OpMatrixTimesVector: // :39-55: v_i = M[i,0] * x_0, then v_i = MulAdd(M[i,j], x_j, v_i)
+			{
+				if(!x.rows || y.rows || y.n != x.n / x.rows) return fail("bad operands of OpMatrixTimesVector");
+				v.n = x.rows;
+				for(int i = 0; i < x.rows; i++)
+				{
+					swcu_shader_operand acc = emit(SWCU_OP_MUL, x.c[i], y.c[0], none);
+					for(int j = 1; j < y.n; j++) acc = emit(SWCU_OP_FMA, x.c[i + x.rows * j], y.c[j], acc);
+					v.c[i] = acc;
+				}
+				break;
+			}
+			case OpVectorTimesMatrix: // :57-73: v_i = x_0 * M[0,i], then v_i = MulAdd(x_j, M[j,i], v_i)
+			{
+				if(x.rows || !y.rows || x.n != y.rows) return fail("bad operands of OpVectorTimesMatrix");
+				v.n = y.n / y.rows;
+				for(int i = 0; i < v.n; i++)
+				{
+					swcu_shader_operand acc = emit(SWCU_OP_MUL, x.c[0], y.c[i * y.rows], none);
+					for(int j = 1; j < x.n; j++) acc = emit(SWCU_OP_FMA, x.c[j], y.c[i * y.rows + j], acc);
+					v.c[i] = acc;
+				}
+				break;
+			}
+			default: // OpDot, :611-621: d = x_0 * y_0, then d = MulAdd(x_i, y_i, d)
+			{
+				if(x.rows || y.rows || x.n != y.n || x.n < 2 || x.n > 4) return fail("bad operands of OpDot");
+				swcu_shader_operand acc = emit(SWCU_OP_MUL, x.c[0], y.c[0], none);
+				for(int i = 1; i < x.n; i++) acc = emit(SWCU_OP_FMA, x.c[i], y.c[i], acc);
+				v.n = 1; v.c[0] = acc;
+				break;
+			}
+			}
+			if(full) return fail("vertex shader arithmetic exceeds %d scalar steps", SWCU_MAX_PROGRAM);
 			values[a[1]] = v;
 			break;
 		}
@@ -397,7 +579,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			NEED(2); ID(a[0]); ID(a[1]);
 			if(na > 2) return fail("memory access operands unsupported");
 			const Value &p = values[a[0]], &v = values[a[1]];
-			if(p.kind != Value::Pointer || v.kind != Value::Vec) return fail("unsupported store");
+			if(p.kind != Value::Pointer || v.kind != Value::Vec || v.rows || p.pcType) return fail("unsupported store");
 			const Type &pt = types[varType[p.var]];
 			if(pt.storage != SCOutput) return fail("store to a non-output variable");
 			const Type &obj = types[pt.elem];
@@ -413,7 +595,13 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			if(builtin >= 0)
 			{
 				if(model != 0) return fail("built-in output in the fragment stage outside the subset (FragDepth etc.)");
-				if(builtin == BuiltInPointSize) break; // irrelevant for triangles
+				if(builtin == BuiltInPointSize) // read by point draws only (DrawCall::setupPoint, Renderer.cpp:1151)
+				{
+					if(v.n != 1 || v.c[0].kind == SWCU_SRC_TEXEL) return fail("gl_PointSize must be stored as a float");
+					out->pointSize = v.c[0];
+					out->writesPointSize = 1;
+					break;
+				}
 				if(builtin != BuiltInPosition) return fail("built-in output %d outside the subset", builtin);
 				if(v.n != 4) return fail("gl_Position must be stored as a vec4");
 				for(int k = 0; k < 4; k++) out->position[k] = v.c[k];
@@ -465,6 +653,8 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 		}
 		for(int k = 0; k < SWCU_MAX_VARYING_COMPONENTS; k++)
 			if(out->outputMask >> k & 1) use(out->output[k]);
+		for(uint32_t i = 0; i < out->programLength; i++) { use(out->program[i].a); use(out->program[i].b); use(out->program[i].c); }
+		if(out->writesPointSize) use(out->pointSize);
 	}
 	else
 	{

@@ -27,7 +27,8 @@ enum
 	VKF_D32_SFLOAT = 126,
 	VKF_S8_UINT = 127,
 };
-enum { TOPO_TRIANGLE_LIST = 3, TOPO_TRIANGLE_STRIP = 4, TOPO_TRIANGLE_FAN = 5 };
+enum { TOPO_POINT_LIST = 0, TOPO_LINE_LIST = 1, TOPO_LINE_STRIP = 2, TOPO_TRIANGLE_LIST = 3, TOPO_TRIANGLE_STRIP = 4, TOPO_TRIANGLE_FAN = 5 };
+enum { PRIM_TRIANGLE = 0, PRIM_LINE = 1, PRIM_POINT = 2 }; // SetupProcessor.cpp:71-73
 enum { CMP_NEVER, CMP_LESS, CMP_EQUAL, CMP_LESS_OR_EQUAL, CMP_GREATER, CMP_NOT_EQUAL, CMP_GREATER_OR_EQUAL, CMP_ALWAYS };
 enum { SOP_KEEP, SOP_ZERO, SOP_REPLACE, SOP_INC_CLAMP, SOP_DEC_CLAMP, SOP_INVERT, SOP_INC_WRAP, SOP_DEC_WRAP };
 enum
@@ -50,6 +51,7 @@ enum { ADDR_REPEAT = 0, ADDR_MIRRORED_REPEAT = 1, ADDR_CLAMP_TO_EDGE = 2 };
 // Device/Clipper.hpp:28-41
 enum { CLIP_RIGHT = 1, CLIP_TOP = 2, CLIP_FAR = 4, CLIP_LEFT = 8, CLIP_BOTTOM = 16, CLIP_NEAR = 32, CLIP_FINITE = 128 };
 #define CLIP_FRUSTUM (CLIP_RIGHT | CLIP_TOP | CLIP_FAR | CLIP_LEFT | CLIP_BOTTOM | CLIP_NEAR)
+#define CLIP_SIDES (CLIP_LEFT | CLIP_RIGHT | CLIP_TOP | CLIP_BOTTOM)
 
 #define SWCU_MAXSLOTS 6      // plane-equation slots per triangle: 4 colour channels + (u, v)
 #define SWCU_TILE_W 32       // screen tile staged in shared memory by one CTA
@@ -88,6 +90,22 @@ struct KVSrc
 	float constant;           // value when ptr == nullptr (shader constant, or the (0,0,0,1) default of a short format)
 	uint32_t pad;
 };
+
+// One scalar step of the vertex stage's arithmetic (an MVP transform).  The translator lowers OpMatrixTimesVector & co.
+// to SWCU_OP_* steps; the host resolves their operands per draw: push-constant words become constants (DrawData::pushConstants is
+// fixed for the draw), inputs become entries of DrawConst::vsIn.
+enum { VK_CONST = 0, VK_INPUT = 1, VK_TEMP = 2 };
+struct KVsOperand
+{
+	uint32_t kind;  // VK_*
+	uint32_t value; // CONST: float bits; INPUT: index into DrawConst::vsIn; TEMP: index of the step that computed it
+};
+struct KVsStep
+{
+	uint32_t op; // SWCU_OP_*
+	KVsOperand a, b, c;
+};
+#define SWCU_VS_INPUTS 16 // distinct attribute components a vertex program may read
 
 struct KMip
 {
@@ -154,6 +172,18 @@ struct DrawConst
 	uint32_t chanValue[4];       // CK_CONST: float bits; CK_SLOT: slot index; CK_TEXEL: texel component
 	uint32_t usesTexture;
 	int32_t uvSlot;              // first of the two texcoord slots
+	// lines and points (DrawCall::setupLine / setupPoint, Renderer.cpp:920-1185): the primitive becomes a clipped quad in k_setup_prog
+	uint32_t primKind;            // PRIM_*
+	float lineWidth, halfPixelX, halfPixelY; // Renderer.cpp:276,317-318
+	KVSrc pointSizeSrc;           // gl_PointSize (constant 1 when the shader does not store it)
+	int32_t pointSizeTemp;
+	// vertex-stage arithmetic: when vsProgLen > 0, k_setup_prog runs the steps for each of the three vertices first; a position
+	// component / slot source with a non-negative *Temp index takes the result of that step instead of its KVSrc
+	uint32_t vsProgLen;
+	int32_t posTemp[4];
+	int32_t slotTemp[SWCU_MAXSLOTS];
+	KVSrc vsIn[SWCU_VS_INPUTS];
+	KVsStep vsProg[SWCU_MAX_PROGRAM];
 
 	// ---- setup state ----
 	uint32_t cullMode, frontFace, depthClipEnable;

@@ -28,6 +28,7 @@ FMT_D32_SFLOAT = 126
 FMT_D16_UNORM = 124
 FMT_S8_UINT = 127
 FLOAT_FORMATS = {1: FMT_R32_SFLOAT, 2: FMT_R32G32_SFLOAT, 3: FMT_R32G32B32_SFLOAT, 4: FMT_R32G32B32A32_SFLOAT}
+TOPO_POINT_LIST, TOPO_LINE_LIST, TOPO_LINE_STRIP = 0, 1, 2
 TOPO_TRIANGLE_LIST, TOPO_TRIANGLE_STRIP, TOPO_TRIANGLE_FAN = 3, 4, 5
 CMP_NEVER, CMP_LESS, CMP_EQUAL, CMP_LESS_OR_EQUAL, CMP_GREATER, CMP_NOT_EQUAL, CMP_GREATER_OR_EQUAL, CMP_ALWAYS = range(8)
 SOP_KEEP, SOP_ZERO, SOP_REPLACE, SOP_INC_CLAMP, SOP_DEC_CLAMP, SOP_INVERT, SOP_INC_WRAP, SOP_DEC_WRAP = range(8)
@@ -132,6 +133,8 @@ class Draw:
     alphaToCoverage: bool = False
     depthBounds: Optional[tuple] = None  # (min, max) enables the depth bounds test
     texture: Optional[Texture] = None
+    pushConstants: Optional[np.ndarray] = None  # float32 / uint32 words pushed for the vertex stage (<= 32)
+    lineWidth: float = 1.0
 
     def vertex_count(self) -> int:
         if self.count is not None:
@@ -142,6 +145,12 @@ class Draw:
         n = self.vertex_count()
         if self.topology == TOPO_TRIANGLE_LIST:
             return n // 3
+        if self.topology == TOPO_POINT_LIST:
+            return n
+        if self.topology == TOPO_LINE_LIST:
+            return n // 2
+        if self.topology == TOPO_LINE_STRIP:
+            return max(0, n - 1)
         return max(0, n - 2)
 
 
@@ -225,10 +234,12 @@ class Scene:
             d.indexType = 0
             d.indexBuffer = None
             d.baseVertex = draw.first
-        if draw.topology == TOPO_TRIANGLE_LIST:
-            d.primitiveCount = nverts // 3
-        else:
-            d.primitiveCount = max(0, nverts - 2)
+        d.primitiveCount = draw.primitive_count()
+        d.lineWidth = draw.lineWidth
+        if draw.pushConstants is not None:
+            pc = np.ascontiguousarray(draw.pushConstants).view(np.uint32).ravel().copy()
+            keep.append(pc)
+            d.pushConstants, d.pushConstantBytes = pc.ctypes.data, pc.nbytes
         for (loc, comps, off) in draw.attribs:
             vi = d.input[loc]
             vi.buffer = verts.ctypes.data + off * 4
@@ -329,8 +340,15 @@ class Scene:
             else:
                 r += struct.pack("<5I5I3f2I", 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0, 0)
             r += struct.pack("<IIff", int(dr.alphaToCoverage), int(dr.depthBounds is not None), *(dr.depthBounds or (0.0, 1.0)))
+            pc = np.zeros(32, dtype=np.uint32)
+            npc = 0
+            if dr.pushConstants is not None:
+                w = np.ascontiguousarray(dr.pushConstants).view(np.uint32).ravel()
+                npc = len(w)
+                pc[:npc] = w
+            r += struct.pack("<fI", dr.lineWidth, 4 * npc) + pc.tobytes()
             recs.append(r)
-        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 3, self.width, self.height, self.samples, self.colorFormat,
+        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 4, self.width, self.height, self.samples, self.colorFormat,
                           (2 if self.depthFormat == FMT_D16_UNORM else 1) if self.hasDepth else 0, int(self.hasStencil), *self.clearColor, self.clearDepth, self.clearStencil,
                           len(recs), len(blobs))
         off = len(hdr) + sum(len(r) for r in recs) + 16 * len(blobs)

@@ -30,7 +30,7 @@ ENUMS = {
     "Dim": {"1D": 0, "2D": 1, "3D": 2, "Cube": 3},
     "ImageFormat": {"Unknown": 0, "Rgba8": 4},
     "FunctionControl": {"None": 0},
-    "Decoration": {"RelaxedPrecision": 0, "Block": 2, "BuiltIn": 11, "NoPerspective": 13, "Flat": 14,
+    "Decoration": {"RelaxedPrecision": 0, "Block": 2, "RowMajor": 4, "ColMajor": 5, "MatrixStride": 7, "BuiltIn": 11, "NoPerspective": 13, "Flat": 14,
                    "Centroid": 16, "Location": 30, "Component": 31, "Binding": 33, "DescriptorSet": 34, "Offset": 35},
     "BuiltIn": {"Position": 0, "PointSize": 1, "ClipDistance": 3, "CullDistance": 4, "FragCoord": 15,
                 "FrontFacing": 17, "FragDepth": 22},
@@ -86,7 +86,10 @@ OPS = {
     "OpFSub": (131, True, True, ["id", "id"]),
     "OpFMul": (133, True, True, ["id", "id"]),
     "OpVectorTimesScalar": (142, True, True, ["id", "id"]),
+    "OpMatrixTimesScalar": (143, True, True, ["id", "id"]),
+    "OpVectorTimesMatrix": (144, True, True, ["id", "id"]),
     "OpMatrixTimesVector": (145, True, True, ["id", "id"]),
+    "OpDot": (148, True, True, ["id", "id"]),
     "OpLabel": (248, False, True, []),
     "OpKill": (252, False, False, []),
     "OpReturn": (253, False, False, []),

@@ -639,6 +639,111 @@ def mixed(seed: int):
 
 
 
+# ------------------------------------------------------------------ f4: a transform in the vertex stage, lines, points ----
+P3C4 = [(0, 3, 0), (1, 4, 3)]
+
+
+def _perspective(rng):
+    """A model-view-projection matrix (row-major numpy; the block stores it column-major like a GLSL mat4)."""
+    a, b, c = rng.uniform(-0.6, 0.6, 3)
+    ca, sa, cb, sb, cc, sc = np.cos(a), np.sin(a), np.cos(b), np.sin(b), np.cos(c), np.sin(c)
+    rx = np.array([[1, 0, 0, 0], [0, ca, -sa, 0], [0, sa, ca, 0], [0, 0, 0, 1]])
+    ry = np.array([[cb, 0, sb, 0], [0, 1, 0, 0], [-sb, 0, cb, 0], [0, 0, 0, 1]])
+    rz = np.array([[cc, -sc, 0, 0], [sc, cc, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    t = np.eye(4)
+    t[:3, 3] = (rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), rng.uniform(2.0, 3.5))
+    f, n_, fa = 1.0 / np.tan(rng.uniform(0.5, 0.9) / 2), 0.5, 8.0
+    proj = np.array([[f, 0, 0, 0], [0, f, 0, 0], [0, 0, fa / (fa - n_), -fa * n_ / (fa - n_)], [0, 0, 1, 0]])
+    return (proj @ t @ rz @ ry @ rx).astype(np.float32)
+
+
+def mvp(seed: int) -> Scene:
+    """A transform in the vertex stage from the push-constant block: OpMatrixTimesVector (MulAdd accumulation) on a tessellated
+    object-space patch, or component-wise scale / offset / tint; depth-tested, some of it clipped by the frustum."""
+    rng = np.random.default_rng(21000 + seed)
+    g = 6 + seed % 5
+    u, v = np.meshgrid(np.linspace(-1, 1, g + 1), np.linspace(-1, 1, g + 1))
+    z = 0.35 * np.sin(2.5 * u + seed) * np.cos(2.0 * v)
+    verts = np.zeros(((g + 1) * (g + 1), 7), dtype=np.float32)
+    verts[:, 0], verts[:, 1], verts[:, 2] = u.ravel(), v.ravel(), z.ravel()
+    verts[:, 3:7] = rng.uniform(0, 1, (len(verts), 4))
+    idx = []
+    for j in range(g):
+        for i in range(g):
+            a = j * (g + 1) + i
+            idx += [a, a + 1, a + g + 1, a + 1, a + g + 2, a + g + 1]
+    idx = np.array(idx, dtype=np.uint16 if seed % 2 else np.uint32)
+    if seed % 3 == 2:
+        pc = np.concatenate([rng.uniform(0.4, 1.3, 3), [0.0], rng.uniform(-0.4, 0.4, 2), [rng.uniform(0.2, 0.8)], [rng.uniform(0.8, 1.6)],
+                             rng.uniform(0.3, 1.0, 4)]).astype(np.float32)
+        vs = "vs_xform_pos3_col4"
+    else:
+        m = _perspective(rng)
+        if seed % 4 == 1:
+            m = m * np.float32(rng.uniform(0.8, 1.9))  # pushes part of the patch across the frustum planes
+        pc = np.ascontiguousarray(m.T).ravel()
+        vs = "vs_mvp_pos3_col4"
+    d = Draw(verts, P3C4, vs, "fs_col4", indices=idx, depthTest=True, depthWrite=True, pushConstants=pc,
+             cullMode=[CULL_NONE, CULL_FRONT, CULL_NONE][seed % 3], blend=(seed % 4 == 3))
+    return Scene(2 * CELL, 2 * CELL, [d], samples=4 if seed % 5 == 4 else 1, hasDepth=True, clearColor=(0.1, 0.1, 0.1, 1.0))
+
+
+def lines(seed: int) -> Scene:
+    """Line lists and strips (DrawCall::setupLine, Renderer.cpp:920-1000: the rectangle of the default rasterization mode), with
+    perspective, end points outside the frustum, u16 indices, 1x and 4x, with and without a depth test."""
+    rng = np.random.default_rng(22000 + seed)
+    n = 24
+    w = rng.uniform(0.5, 2.0, n) if seed % 2 else np.ones(n)
+    span = 1.5 if seed % 3 == 0 else 0.95
+    v = np.zeros((n, 8), dtype=np.float32)
+    v[:, 0] = rng.uniform(-span, span, n) * w
+    v[:, 1] = rng.uniform(-span, span, n) * w
+    v[:, 2] = rng.uniform(0.1, 0.9, n) * w
+    v[:, 3] = w
+    v[:, 4:8] = rng.uniform(0, 1, (n, 4))
+    if seed % 8 == 5:
+        v[3, 3] = -0.4  # an end point behind the eye
+        v[7, 0:2] = v[6, 0:2] / v[6, 3] * v[7, 3]  # a segment of zero length on screen
+    kind = seed % 4
+    kw = {}
+    if kind == 0:
+        idx, topo = None, TOPO_LINE_LIST
+    elif kind == 1:
+        idx, topo = None, TOPO_LINE_STRIP
+    elif kind == 2:
+        idx, topo = rng.integers(0, n, 20).astype(np.uint16), TOPO_LINE_LIST
+    else:
+        idx, topo = rng.integers(0, n, 14).astype(np.uint32), TOPO_LINE_STRIP
+        kw = dict(first=2, count=11)
+    d = Draw(v, P4C4, "vs_pos4_col4", "fs_col4", indices=idx, topology=topo, depthTest=(seed % 3 == 1), depthWrite=True,
+             lineWidth=[1.0, 1.0, 3.0, 1.0, 2.5][seed % 5], depthBias=(2.0, 0.0, 1.5) if seed % 6 == 4 else (0.0, 0.0, 0.0), **kw)
+    return Scene(2 * CELL, 2 * CELL, [d], samples=4 if seed % 4 == 3 else 1, hasDepth=True, clearColor=(0.0, 0.0, 0.0, 1.0))
+
+
+P4C4S1 = [(0, 4, 0), (1, 4, 4), (2, 1, 8)]
+
+
+def points(seed: int) -> Scene:
+    """Point lists (DrawCall::setupPoint, Renderer.cpp:1137-1185): gl_PointSize from an attribute, clamped to [1, 1023], squares that
+    reach over the frustum sides, perspective w, overlapping points with a depth test or blending, 1x and 4x."""
+    rng = np.random.default_rng(23000 + seed)
+    n = 40
+    w = rng.uniform(0.5, 2.0, n) if seed % 2 else np.ones(n)
+    v = np.zeros((n, 9), dtype=np.float32)
+    v[:, 0] = rng.uniform(-1.05, 1.05, n) * w
+    v[:, 1] = rng.uniform(-1.05, 1.05, n) * w
+    v[:, 2] = rng.uniform(0.1, 0.9, n) * w
+    v[:, 3] = w
+    v[:, 4:8] = rng.uniform(0, 1, (n, 4))
+    v[:, 8] = rng.choice([0.25, 1.0, 1.5, 2.0, 3.0, 4.5, 7.0, 12.0, 30.0], n)
+    if seed % 6 == 3:
+        v[5, 8] = 2000.0  # beyond MAX_POINT_SIZE
+    idx = rng.integers(0, n, 25).astype(np.uint16) if seed % 3 == 2 else None
+    d = Draw(v, P4C4S1, "vs_point_pos4_col4", "fs_col4", indices=idx, topology=TOPO_POINT_LIST, depthTest=(seed % 2 == 0), depthWrite=True,
+             blend=(seed % 4 == 1))
+    return Scene(2 * CELL, 2 * CELL, [d], samples=4 if seed % 4 == 2 else 1, hasDepth=True, clearColor=(0.0, 0.0, 0.0, 1.0))
+
+
 FAMILIES = {
     # name: (generator, number of seeds)
     "coverage": (coverage, 40),
@@ -661,6 +766,9 @@ FAMILIES = {
     "texsplit": (texsplit, 12),
     "mixed": (mixed, 24),
     "blendoff": (blendoff, 6),
+    "mvp": (mvp, 12),
+    "lines": (lines, 16),
+    "points": (points, 12),
 }
 
 

@@ -42,12 +42,30 @@ int main(){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(swcu_draw_desc), sizeof(s
 def _dump(i):
     return dict(stage=i.stage, outputMask=i.outputMask, position=[(o.kind, o.value) for o in i.position],
                 output=[(o.kind, o.value) for o in i.output], inputMask=i.inputMask, flat=i.flatMask, nopersp=i.noPerspectiveMask,
-                tex=(i.usesTexture, i.textureSet, i.textureBinding), tc=[(o.kind, o.value) for o in i.texCoord])
+                tex=(i.usesTexture, i.textureSet, i.textureBinding), tc=[(o.kind, o.value) for o in i.texCoord],
+                program=[(s.op, (s.a.kind, s.a.value), (s.b.kind, s.b.value), (s.c.kind, s.c.value)) for s in i.program[:i.programLength]],
+                pointSize=(i.writesPointSize, i.pointSize.kind, i.pointSize.value))
 
 
 @pytest.mark.parametrize("name", sorted(swref.SHADER_SPECS))
 def test_translator_matches_hand_written_meaning(name):
     assert _dump(capi.translate_shader(spirv.shader(name))) == _dump(swref.shader_spec(name))
+
+
+@pytest.mark.parametrize("name", sorted(swref.SHADER_SPECS))
+def test_translator_on_the_post_spirv_opt_form(name):
+    """The shim hands over SpirvShader::insns, i.e. the module AFTER spirv-opt (VkPipeline.cpp:36-107); the committed fixtures are the
+    fixture shaders run through the reference's own pass list (tests/golden/gen_spv_postopt.py).  Same meaning either way."""
+    words = np.fromfile(os.path.join(ROOT, "tests", "golden", "spv_postopt", name + ".spv"), dtype=np.uint32)
+    assert _dump(capi.translate_shader(words)) == _dump(swref.shader_spec(name))
+
+
+def test_translator_vertex_arithmetic_limits():
+    """a push-constant access beyond 128 bytes, and arithmetic in the fragment stage, are outside the subset"""
+    src = spirv.shader_source("vs_mvp_pos3_col4").replace("OpMemberDecorate %PC 0 Offset 0", "OpMemberDecorate %PC 0 Offset 96")
+    with pytest.raises(capi.SwcuError) as e:
+        capi.translate_shader(spirv.assemble(src))
+    assert e.value.code == capi.E_UNSUPPORTED and "push-constant access beyond" in str(e.value)
 
 
 FS_HEAD = """OpCapability Shader
