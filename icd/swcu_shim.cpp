@@ -343,6 +343,7 @@ void draw(const DrawArgs &args)
 	d.cullMode = (uint32_t)pre.getCullMode();
 	d.frontFace = (uint32_t)pre.getFrontFace();
 	d.depthClipEnable = pre.getDepthClipEnable() ? 1u : 0u;
+	d.depthClampEnable = pre.getDepthClampEnable() ? 1u : 0u;
 	d.depthBiasConstant = pre.getConstantDepthBias();
 	d.depthBiasSlope = pre.getSlopeDepthBias();
 	d.depthBiasClamp = pre.getDepthBiasClamp();

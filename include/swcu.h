@@ -148,6 +148,8 @@ typedef struct swcu_draw_desc
 	uint32_t cullMode;  /* VkCullModeFlags */
 	uint32_t frontFace; /* VkFrontFace */
 	uint32_t depthClipEnable; /* reference default true */
+	uint32_t depthClampEnable; /* VkPipelineRasterizationStateCreateInfo::depthClampEnable: fragment depth is clamped to the viewport's depth range
+	                              instead of [0, 1] (PixelProcessor.cpp:121-136); the API ties depthClipEnable = !depthClampEnable (Context.cpp:647-648) */
 	float depthBiasConstant, depthBiasSlope, depthBiasClamp;
 
 	/* --- multisampling */

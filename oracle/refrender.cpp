@@ -161,6 +161,7 @@ int main(int argc, char **argv)
 	dci.pQueueCreateInfos = &qci;
 	VkPhysicalDeviceFeatures feat{};
 	feat.depthBounds = VK_TRUE;
+	feat.depthClamp = VK_TRUE;
 	dci.pEnabledFeatures = &feat;
 	CHECK(vkCreateDevice(pd, &dci, nullptr, &dev));
 	VkQueue queue;
@@ -374,6 +375,7 @@ int main(int argc, char **argv)
 		rs.cullMode = d.cullMode;
 		rs.frontFace = (VkFrontFace)d.frontFace;
 		rs.lineWidth = d.lineWidth != 0.0f ? d.lineWidth : 1.0f;
+		rs.depthClampEnable = d.depthClampEnable ? VK_TRUE : VK_FALSE;
 		rs.depthBiasEnable = d.depthBiasEnable;
 		rs.depthBiasConstantFactor = d.depthBiasConstant;
 		rs.depthBiasClamp = d.depthBiasClamp;

@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define SCENE_MAGIC 0x43535753u /* "SWSC" */
-#define SCENE_VERSION 4u
+#define SCENE_VERSION 5u
 #define SCENE_MAX_ATTRIBS 8
 
 #pragma pack(push, 4)
@@ -61,6 +61,7 @@ typedef struct SceneDraw
 	float lineWidth;            /* VkPipelineRasterizationStateCreateInfo::lineWidth (0 is read as 1) */
 	uint32_t pushConstantBytes; /* vkCmdPushConstants(VERTEX, 0, bytes) ahead of the draw; 0 = no push-constant range */
 	uint32_t pushConstants[32];
+	uint32_t depthClampEnable;  /* VkPipelineRasterizationStateCreateInfo::depthClampEnable */
 } SceneDraw;
 
 typedef struct SceneBlob { uint64_t offset, size; } SceneBlob;

@@ -133,6 +133,7 @@ typedef struct
 	int interpolateZ, interpolateW;
 	int prim; /* 0 = triangles, 1 = lines, 2 = points (SetupProcessor.cpp:71-73 isDrawTriangle / isDrawLine / isDrawPoint) */
 	float lineWidth, halfPixelX, halfPixelY; /* Renderer.cpp:276,317-318 */
+	float minDepthClamp, maxDepthClamp;      /* PixelProcessor.cpp:121-136 */
 } Draw;
 
 /* x86 conversions used by Reactor: RoundInt = cvtps2dq, Int(float) = cvttps2dq (Reactor/LLVMReactor.cpp:135-138,2694-2703) */
@@ -1119,7 +1120,7 @@ static void rasterize(const Draw *dr, const Primitive *prim)
 					for(int i = 0; i < 4; i++)
 					{
 						/* clampDepth :484-492: fixed point, or D32F without VK_EXT_depth_range_unrestricted => [0,1] (PixelProcessor.cpp:121-136) */
-						z[q][i] = sse_min(sse_max(z[q][i], 0.0f), 1.0f);
+						z[q][i] = sse_min(sse_max(z[q][i], dr->minDepthClamp), dr->maxDepthClamp);
 						float Z = z[q][i];
 						float zValue;
 						if(d16)
@@ -1345,6 +1346,12 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 	dr.prim = d->topology == TOPO_POINT_LIST ? 2 : ((d->topology == TOPO_LINE_LIST || d->topology == TOPO_LINE_STRIP) ? 1 : 0);
 	dr.lineWidth = d->lineWidth == 0.0f ? 1.0f : d->lineWidth;
 	dr.halfPixelX = 0.5f / (0.5f * d->viewportWidth); dr.halfPixelY = 0.5f / (0.5f * d->viewportHeight);
+	dr.minDepthClamp = 0.0f; dr.maxDepthClamp = 1.0f; /* no VK_EXT_depth_range_unrestricted: always clamped */
+	if(d->depthClampEnable)
+	{
+		dr.minDepthClamp = d->viewportMinDepth < d->viewportMaxDepth ? d->viewportMinDepth : d->viewportMaxDepth;
+		dr.maxDepthClamp = d->viewportMinDepth < d->viewportMaxDepth ? d->viewportMaxDepth : d->viewportMinDepth;
+	}
 	dr.ms = (int)d->sampleCount;
 	dr.enableMultiSampling = dr.ms > 1;
 	dr.depthTestActive = d->depthTestEnable && d->depth.buffer;

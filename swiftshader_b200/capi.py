@@ -61,7 +61,7 @@ class DrawDesc(C.Structure):
         ("viewportX", C.c_float), ("viewportY", C.c_float), ("viewportWidth", C.c_float), ("viewportHeight", C.c_float),
         ("viewportMinDepth", C.c_float), ("viewportMaxDepth", C.c_float),
         ("scissor", Rect), ("renderArea", Rect),
-        ("cullMode", C.c_uint32), ("frontFace", C.c_uint32), ("depthClipEnable", C.c_uint32),
+        ("cullMode", C.c_uint32), ("frontFace", C.c_uint32), ("depthClipEnable", C.c_uint32), ("depthClampEnable", C.c_uint32),
         ("depthBiasConstant", C.c_float), ("depthBiasSlope", C.c_float), ("depthBiasClamp", C.c_float),
         ("sampleCount", C.c_uint32), ("sampleMask", C.c_uint32), ("alphaToCoverageEnable", C.c_uint32),
         ("depthTestEnable", C.c_uint32), ("depthWriteEnable", C.c_uint32), ("depthCompareOp", C.c_uint32),

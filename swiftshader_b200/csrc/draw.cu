@@ -904,6 +904,12 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 
 	// ---- setup state ----
 	d.cullMode = desc->cullMode; d.frontFace = desc->frontFace; d.depthClipEnable = desc->depthClipEnable;
+	d.minDepthClamp = 0.0f; d.maxDepthClamp = 1.0f; // PixelProcessor.cpp:121-136 (no VK_EXT_depth_range_unrestricted: always clamped)
+	if(desc->depthClampEnable)
+	{
+		d.minDepthClamp = std::min(desc->viewportMinDepth, desc->viewportMaxDepth);
+		d.maxDepthClamp = std::max(desc->viewportMinDepth, desc->viewportMaxDepth);
+	}
 	d.depthBiasConstant = desc->depthBiasConstant; d.depthBiasSlope = desc->depthBiasSlope; d.depthBiasClamp = desc->depthBiasClamp;
 	d.depthBiasEnable = desc->depthBiasConstant != 0.0f || desc->depthBiasSlope != 0.0f;
 	if(d.primKind != PRIM_TRIANGLE) // SetupProcessor.cpp:75-77: depth bias applies to triangles only
@@ -1057,7 +1063,7 @@ static void launch_tile4(swcu_ctx *ctx, const DrawConst &d, const TileMaps &maps
 static bool fast_state(const swcu_ctx *ctx, const DrawConst &d)
 {
 	if(!ctx->optFastState) return false;
-	if(d.alphaToCoverage || d.depthBounds) return false;
+	if(d.alphaToCoverage || d.depthBounds || d.minDepthClamp != 0.0f || d.maxDepthClamp != 1.0f) return false;
 	if(d.stencilActive || d.stencilWrite || !d.colorBuf || d.colorWriteMask != 0xFu || d.bgr || d.srgb || d.colorEpp != 1 || d.depthBiasEnable || d.depth16) return false;
 	if(d.depthTestActive && d.depthCompareOp != CMP_LESS && d.depthCompareOp != CMP_LESS_OR_EQUAL) return false;
 	if(d.ms == 4 && (d.sampleMask & 0xFu) != 0xFu) return false;

@@ -1616,11 +1616,18 @@ DEVI uint32_t byte_range(int a, int b) { return b > a ? (0xFFFFFFFFu >> (32 - 8 
 // order, no depth bias, full sample mask, depth test off or LESS / LESS_OR_EQUAL, perspective slots routed one to one —
 // so none of it is decoded per fragment.  FS == false is the same code with every state read at run time.
 #ifndef TILE_CTAS_4X
-#define TILE_CTAS_4X 7 // 72 registers: measured 0.368 ms on C4 against 0.382 ms with 8 CTAs of 64 (spills and re-derived addresses in the item loop)
+#define TILE_CTAS_4X 7 // 72 registers: measured 0.357 ms on C4 against 0.385 ms with 8 CTAs of 64 (spills and re-derived addresses in the item loop)
 #endif
 #ifndef TILE_CTAS_1X
 #define TILE_CTAS_1X 7
 #endif
+#ifndef TILE_MAP_1X
+#define TILE_MAP_1X 0
+#endif
+#ifndef TILE_MAP_4X
+#define TILE_MAP_4X 1
+#endif
+
 template<int MS, int SH, int BL, bool FS>
 __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CTAS_1X) k_tile(const __grid_constant__ DrawConst d, const __grid_constant__ TileMaps maps)
 {
@@ -1660,6 +1667,14 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 	uint64_t *bar = (uint64_t *)wa;
 	unsigned short *wQueue = (unsigned short *)(wa + L::HEAD_B);
 	unsigned char *wOwner = wa + L::HEAD_B + L::Q_B;
+	// The first words of the owner array double as the COVERAGE MAP of a queue fill: one bit per sample of the region (word 2 * row:
+	// samples 0 | 1 << 16, word 2 * row + 1: samples 2 | 3 << 16, a bit per column; 1x: word row / 2, half row & 1).  Every producer ORs
+	// its clipped masks in; a bit found set already means two fragments of the fill meet on a sample.  Only then do the rounds of the
+	// fill run the exact per-round test (owner bytes, below) — a mesh without overdraw never does.
+	uint32_t *wBits = (uint32_t *)wOwner;
+	// (1x: measured slower than signing the owner bytes round by round — 32 lanes meet on the 4 words of the map — so one sample per
+	// pixel keeps the per-round test, and its optimistic pass the signatures)
+	constexpr bool USE_MAP = MS == 4 ? TILE_MAP_4X : TILE_MAP_1X;
 	uint32_t *wSort = (uint32_t *)(wa + L::HEAD_B + L::Q_B + L::OWNER_B);
 	// the colour plane; a floating-point target (2 or 4 words per pixel, never with FS) lives in the variable part instead
 	unsigned char *wv = smem + SWCU_TILE_WARPS * L::FIXED_B + warp * L::var_bytes(d.depthTestActive != 0, d.stencilActive != 0, colorEpp);
@@ -1751,7 +1766,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 	}
 	if(optimistic)
 	{
-		((uint32_t *)wOwner)[lane] = 0xFFFFFFFFu; // 128 samples, nobody has signed yet
+		if(USE_MAP) { if(lane < 4) wBits[lane] = 0u; } // the pass keeps ONE map of the samples written so far: 8 rows x 16 columns
+		else ((uint32_t *)wOwner)[lane] = 0xFFFFFFFFu; // 128 samples, nobody has signed yet
 		__syncwarp();
 	}
 	if(!d.direct && !optimistic)
@@ -1872,7 +1888,8 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 		while(p < cnt && !redo)
 		{
 			uint32_t total = 0;
-			bool oneCandidate = false; // the queue holds the pixels of a single triangle: no two of them on the same sample
+			bool oneCandidate = false; // no two items of this queue fill can lie on the same sample (one triangle, or the coverage map says so)
+			bool mapHit = false;       // optimistic pass: an item of this fill lands on a sample an earlier fragment of the pass has written
 			const uint32_t rest = bigMask >> p;
 			if(rest & 1u)
 			{
@@ -1922,6 +1939,11 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 					const uint32_t start = __shfl_sync(0xFFFFFFFFu, incl, lane & ~3) - (uint32_t)nrow; // first item of my row
 					const uint32_t item = ((uint32_t)p << 11) | (1u << 7) | ((uint32_t)row << 4);
 					for(int i = es; i < nrow; i += 4) wQueue[start + i] = (unsigned short)(item | (uint32_t)(a + i)); // every fourth pixel of the run
+					if(USE_MAP && optimistic && es == 0 && nrow)
+					{
+						const uint32_t v = ((0xFFFFu >> (16 - nrow)) << a) << (16 * (row & 1));
+						if(atomicOr(wBits + (row >> 1), v) & v) mapHit = true;
+					}
 					p += 1;
 					oneCandidate = true;
 				}
@@ -1988,6 +2010,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 						wQueue[w++] = (unsigned short)(item | (sm << 7) | x);
 					}
 				p += group;
+				oneCandidate = group == 1;
 				}
 			}
 			else
@@ -2072,9 +2095,61 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 						}
 					}
 				}
+				// ---- coverage map of the fill: do two of its fragments meet on a sample?  (Not asked when the fill holds one triangle.) ----
+				if(fitEnd - p == 1 && !optimistic) oneCandidate = true;
+				else if(USE_MAP)
+				{
+					if(!optimistic)
+					{
+						if(lane < (MS == 4 ? 16 : 4)) wBits[lane] = 0u;
+						__syncwarp();
+					}
+					bool hit = false;
+					if(mine && lane < fitEnd && count)
+					{
+						const int dx = fx - rx, dy = fy - ry;
+						const int sl = max(dx, 0), sr = max(-dx, 0); // (columns left of the region are clipped away: nothing is shifted out)
+						if(MS == 4)
+						{
+#pragma unroll
+							for(int r = 0; r < (MS == 4 ? 8 : 0); r++)
+							{
+								const uint32_t mr = m[r];
+								if(mr)
+								{
+									const uint32_t lo = (__byte_perm(mr, 0, 0x4140) << sl) >> sr, hi2 = (__byte_perm(mr, 0, 0x4342) << sl) >> sr;
+									uint32_t *w = wBits + 2 * (dy + r);
+									if(lo && (atomicOr(w, lo) & lo)) hit = true;
+									if(hi2 && (atomicOr(w + 1, hi2) & hi2)) hit = true;
+								}
+							}
+						}
+						else
+						{
+#pragma unroll
+							for(int r = 0; r < 8; r++)
+							{
+								const uint32_t byte = (m[r >> 2] >> (8 * (r & 3))) & 0xFFu;
+								if(byte)
+								{
+									const int R = dy + r;
+									const uint32_t v = ((byte << sl) >> sr) << (16 * (R & 1));
+									if(atomicOr(wBits + (R >> 1), v) & v) hit = true;
+								}
+							}
+						}
+					}
+					if(optimistic) mapHit = hit;
+					else oneCandidate = !__any_sync(0xFFFFFFFFu, hit);
+				}
 				p = fitEnd;
 			}
 			__syncwarp();
+			if(USE_MAP && optimistic && __any_sync(0xFFFFFFFFu, mapHit))
+			{
+				redo = true; // (warp-uniform) nothing of this fill has been applied: the region is staged again and the bin walked in order
+				break;
+			}
 			if(total && !tileReady)
 			{
 				while(!mbar_try_wait(bar, tmaPhase)) {} // the TMA loads of the region have landed
@@ -2110,10 +2185,11 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 				// two fragments of this round on one SAMPLE?  Every lane signs its samples; a lane that reads back another signature has
 				// company.  (Two triangles that share an edge pixel with disjoint samples — every edge of a mesh — are not a conflict.)
 				bool shared = false;
-				const bool noCheck = oneCandidate && !optimistic; // (an optimistic pass still has to sign the samples for the rounds to come)
+				// (an optimistic pass with the map has asked it about the whole pass; one without still has to sign the samples for the rounds to come)
+				const bool noCheck = USE_MAP ? (oneCandidate || optimistic) : (oneCandidate && !optimistic);
 				if(!noCheck)
 				{
-				if(MS == 1 && optimistic)
+				if(!USE_MAP && MS == 1 && optimistic)
 				{
 					// signed in an earlier round of this pass?  Then two fragments meet on the sample and the walk needs the order
 					if(live && wOwner[pkey] != 0xFFu) shared = true;
@@ -2135,7 +2211,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 				}
 				int prank = 0, maxRank = 0;
 				const bool anyShared = !noCheck && __any_sync(0xFFFFFFFFu, shared);
-				if(MS == 1 && optimistic && anyShared)
+				if(!USE_MAP && MS == 1 && optimistic && anyShared)
 				{
 					redo = true; // (warp-uniform) nothing of this round has been applied
 					break;
@@ -2221,11 +2297,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 						}
 
 						// ---- per covered sample: stencil test, depth test, depth write, blend + colour write, stencil write ----
-#ifdef TILE_SAMPLE_LOOP_ROLLED
-#pragma unroll 1
-#else
 #pragma unroll
-#endif
 						for(int q = 0; q < MS; q++) // (unrolled: the sample offsets and plane strides of each copy are constants)
 						{
 							if(!((smask >> q) & 1u)) continue;
@@ -2257,7 +2329,7 @@ __global__ void __launch_bounds__(TILE_THREADS, MS == 4 ? TILE_CTAS_4X : TILE_CT
 								}
 								z = __fmaf_rn(xx, zv.y, fadd(zv.w, fmul(yy, zv.z)));
 								if(biasOn) z = fadd(z, zv.x);
-								z = sse_min(sse_max(z, 0.0f), 1.0f); // clampDepth :484-492
+								z = FS ? sse_min(sse_max(z, 0.0f), 1.0f) : sse_min(sse_max(z, d.minDepthClamp), d.maxDepthClamp); // clampDepth :484-492
 								if(!FS && d.depth16)
 								{
 									// D16_UNORM (:466-482, :508-511): Z = Min(Max(Round(z * 0xFFFF), 0), 0xFFFF) against Float(UShort), as floats;

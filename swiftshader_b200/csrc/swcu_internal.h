@@ -192,6 +192,7 @@ struct DrawConst
 
 	// ---- pixel state (PixelProcessor.cpp:74-140, Context.cpp:1090-1312 folded) ----
 	uint32_t depthTestActive, depthWriteEnable, depthCompareOp;
+	float minDepthClamp, maxDepthClamp; // clampDepth (PixelRoutine.cpp:484-492): [0, 1], or the viewport's depth range with depthClampEnable
 	uint32_t depth16; // D16_UNORM depth buffer: quantised compare / saturating write (PixelRoutine.cpp:466-482,508-511,687-711)
 	uint32_t stencilActive, stencilWrite;
 	uint32_t alphaToCoverage; // c[0].w against the per-sample thresholds of Renderer.cpp:391-410 (PixelRoutine.cpp:643-658)

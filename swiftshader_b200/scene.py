@@ -135,6 +135,7 @@ class Draw:
     texture: Optional[Texture] = None
     pushConstants: Optional[np.ndarray] = None  # float32 / uint32 words pushed for the vertex stage (<= 32)
     lineWidth: float = 1.0
+    depthClamp: bool = False  # depthClampEnable: no near / far clipping, fragment depth clamped to the viewport's depth range
 
     def vertex_count(self) -> int:
         if self.count is not None:
@@ -255,7 +256,8 @@ class Scene:
         sc = draw.scissor or (0, 0, self.width, self.height)
         d.scissor = capi.Rect(*sc)
         d.renderArea = capi.Rect(*(render_area or (0, 0, self.width, self.height)))
-        d.cullMode, d.frontFace, d.depthClipEnable = draw.cullMode, draw.frontFace, 1
+        d.cullMode, d.frontFace = draw.cullMode, draw.frontFace
+        d.depthClampEnable, d.depthClipEnable = int(draw.depthClamp), int(not draw.depthClamp)  # Context.cpp:647-648
         d.depthBiasConstant, d.depthBiasClamp, d.depthBiasSlope = draw.depthBias
         d.sampleCount, d.sampleMask = self.samples, draw.sampleMask & ((1 << self.samples) - 1)
         d.alphaToCoverageEnable = int(draw.alphaToCoverage)
@@ -347,8 +349,9 @@ class Scene:
                 npc = len(w)
                 pc[:npc] = w
             r += struct.pack("<fI", dr.lineWidth, 4 * npc) + pc.tobytes()
+            r += struct.pack("<I", int(dr.depthClamp))
             recs.append(r)
-        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 4, self.width, self.height, self.samples, self.colorFormat,
+        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 5, self.width, self.height, self.samples, self.colorFormat,
                           (2 if self.depthFormat == FMT_D16_UNORM else 1) if self.hasDepth else 0, int(self.hasStencil), *self.clearColor, self.clearDepth, self.clearStencil,
                           len(recs), len(blobs))
         off = len(hdr) + sum(len(r) for r in recs) + 16 * len(blobs)

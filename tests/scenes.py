@@ -88,6 +88,27 @@ def zclip(seed: int) -> Scene:
     return _grid_scene(mk, hasDepth=True, clearDepth=1.0)
 
 
+def zclamp(seed: int) -> Scene:
+    """depthClampEnable: no near / far clipping (Context.cpp:647-648), fragment depth clamped to the viewport's depth range instead of
+    [0, 1] (PixelProcessor.cpp:121-136) — narrowed and reversed ranges, triangles that cross z < 0 and z > w, two layers per cell."""
+    rng = np.random.default_rng(24000 + seed)
+    ranges = [(0.2, 0.7), (0.8, 0.3), (0.0, 1.0), (0.45, 0.55)]
+    g, draws = 3, []
+    for i in range(g * g):
+        vx, vy = (i % g) * CELL, (i // g) * CELL
+        lo, hi = ranges[(seed + i) % 4]
+        for layer in range(2):
+            p = _tri_kind(rng, 5 if (i + layer) % 2 else 0)
+            z = rng.uniform(-0.6, 1.6, 3)
+            d = Draw(_verts(rng, p, persp=(i % 2 == 0), colour=rng.uniform(0, 1, (3, 4)), z=z), P4C4, "vs_pos4_col4", "fs_col4",
+                     depthTest=True, depthWrite=True, depthClamp=(layer == 0 or seed % 2 == 0),
+                     depthCompareOp=[CMP_LESS_OR_EQUAL, CMP_LESS, CMP_GREATER, CMP_ALWAYS][(seed // 2 + layer) % 4])
+            d.viewport = (float(vx), float(vy), float(CELL), float(CELL), lo, hi)
+            d.scissor = (vx, vy, CELL, CELL)
+            draws.append(d)
+    return Scene(g * CELL, g * CELL, draws, samples=4 if seed % 4 == 3 else 1, hasDepth=True, clearDepth=[1.0, 0.5][seed % 2])
+
+
 def cull(seed: int) -> Scene:
     rng = np.random.default_rng(3000 + seed)
     mode = [CULL_NONE, CULL_FRONT, CULL_BACK, CULL_FRONT | CULL_BACK][seed % 4]
@@ -769,6 +790,7 @@ FAMILIES = {
     "mvp": (mvp, 12),
     "lines": (lines, 16),
     "points": (points, 12),
+    "zclamp": (zclamp, 8),
 }
 
 
