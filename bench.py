@@ -333,6 +333,7 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
                 dev.register(b, upload=False)
             in_sets = [(frame.inputs, frame.descs), (alt_inputs, alt_descs)]
             sharded_upload = N > 1 and os.environ.get("SWCU_SHARD_UPLOAD", "1") != "0"
+            gather_stream = torch.cuda.Stream() if sharded_upload else None
             up_bytes = [0]
 
             def upload_set(k):
@@ -350,11 +351,13 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
                     if tail:
                         dev.check(dev.lib.swcu_mem_upload(dev.ctx, flat.ctypes.data + chunk * N, tail))
                     if chunk:
-                        # the collective runs on the caller's stream: it waits for my slice's upload, later uploads wait for it
-                        dev.check(dev.lib.swcu_mem_acquire(dev.ctx, flat.ctypes.data))
+                        # the collective runs on a stream of its own, beside the frame that is rendering: it waits for my slice's upload,
+                        # the draw that reads the buffer waits for it
+                        dev.check(dev.lib.swcu_mem_acquire_on(dev.ctx, flat.ctypes.data, gather_stream.cuda_stream))
                         whole = torch.as_tensor(_DevArr(dev.device_ptr(b), chunk * N), device=dev_s)
-                        dist.all_gather_into_tensor(whole, whole[rank * chunk:(rank + 1) * chunk])
-                        dev.check(dev.lib.swcu_mem_release(dev.ctx, flat.ctypes.data))
+                        with torch.cuda.stream(gather_stream):
+                            dist.all_gather_into_tensor(whole, whole[rank * chunk:(rank + 1) * chunk])
+                        dev.check(dev.lib.swcu_mem_release_on(dev.ctx, flat.ctypes.data, gather_stream.cuda_stream))
                     up_bytes[0] += chunk + tail
 
             F = len(final_imgs) if (rank == 0 or N == 1) else 2

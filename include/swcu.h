@@ -332,6 +332,11 @@ int swcu_mem_acquire(swcu_ctx *ctx, const void *host_ptr);
 /* ... and once that work has been enqueued on the stream: whatever reads the shadow from now on (the setup phase of a draw runs on
  * a stream of its own) waits for it, as it would for an upload. */
 int swcu_mem_release(swcu_ctx *ctx, const void *host_ptr);
+/* The same pair for work the caller runs on a stream of ITS OWN (a collective that assembles the shadow from the ranks' slices while
+ * the library's stream renders the previous frame): `cuda_stream` waits for the last upload into the shadow; after release whatever
+ * reads the shadow waits for what that stream had been given.  The library's own stream is not held up. */
+int swcu_mem_acquire_on(swcu_ctx *ctx, const void *host_ptr, void *cuda_stream);
+int swcu_mem_release_on(swcu_ctx *ctx, const void *host_ptr, void *cuda_stream);
 
 /* ---- narrow SPIR-V translator (host-only, no GPU needed) ---- */
 int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_shader_info *out, char *err, size_t errlen);

@@ -120,7 +120,7 @@ EXPORTS = [
     "swcu_set_profiling", "swcu_last_draw_kernels", "swcu_set_option", "swcu_version",
     "swcu_ipc_export", "swcu_ipc_open", "swcu_ipc_close", "swcu_copy_image", "swcu_signal", "swcu_wait_flags",
     "swcu_fence_signal", "swcu_fence_wait",
-    "swcu_group_reserve", "swcu_group_attach", "swcu_group_detach", "swcu_mem_acquire", "swcu_mem_release",
+    "swcu_group_reserve", "swcu_group_attach", "swcu_group_detach", "swcu_mem_acquire", "swcu_mem_release", "swcu_mem_acquire_on", "swcu_mem_release_on",
 ]
 
 _ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -177,6 +177,8 @@ def lib() -> C.CDLL:
     L.swcu_group_detach.argtypes = [vp]
     L.swcu_mem_acquire.argtypes = [vp, vp]
     L.swcu_mem_release.argtypes = [vp, vp]
+    L.swcu_mem_acquire_on.argtypes = [vp, vp, vp]
+    L.swcu_mem_release_on.argtypes = [vp, vp, vp]
     L.swcu_version.argtypes = []
     L.swcu_version.restype = C.c_char_p
     for name in EXPORTS:

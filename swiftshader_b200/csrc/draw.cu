@@ -472,6 +472,38 @@ extern "C" int swcu_mem_release(swcu_ctx *ctx, const void *host_ptr)
 	return SWCU_OK;
 }
 
+extern "C" int swcu_mem_acquire_on(swcu_ctx *ctx, const void *host_ptr, void *cuda_stream)
+{
+	if(!ctx || !host_ptr || !cuda_stream) return fail(ctx, SWCU_E_INVALID, "swcu_mem_acquire_on: null argument");
+	Shadow *s = find_shadow(ctx, host_ptr, 1);
+	if(!s) return fail(ctx, SWCU_E_INVALID, "swcu_mem_acquire_on: %p is not inside a registered range", host_ptr);
+	CU(cudaSetDevice(ctx->device));
+	// the caller's stream sees the last upload into the shadow (the upload itself has waited for the draws that read the shadow
+	// before it), and a download of it still in flight
+	if(s->upEvent && s->upSeq) CU(cudaStreamWaitEvent((cudaStream_t)cuda_stream, s->upEvent, 0));
+	if(s->dlPendingMain) CU(cudaStreamWaitEvent((cudaStream_t)cuda_stream, s->dlEvent, 0));
+	return SWCU_OK;
+}
+
+extern "C" int swcu_mem_release_on(swcu_ctx *ctx, const void *host_ptr, void *cuda_stream)
+{
+	if(!ctx || !host_ptr || !cuda_stream) return fail(ctx, SWCU_E_INVALID, "swcu_mem_release_on: null argument");
+	Shadow *s = find_shadow(ctx, host_ptr, 1);
+	if(!s) return fail(ctx, SWCU_E_INVALID, "swcu_mem_release_on: %p is not inside a registered range", host_ptr);
+	CU(cudaSetDevice(ctx->device));
+	// The caller's work counts as the newest "upload" of the shadow.  Readers assume that having waited for upload number n they have
+	// seen all earlier ones, so the caller's stream first catches up with every upload issued so far.
+	if(ctx->uploadSeq) CU(cudaStreamWaitEvent((cudaStream_t)cuda_stream, ctx->evUpload, 0));
+	if(!s->upEvent) CU(cudaEventCreateWithFlags(&s->upEvent, cudaEventDisableTiming));
+	CU(cudaEventRecord(s->upEvent, (cudaStream_t)cuda_stream));
+	// "the last upload" now ends on the caller's stream; the copy stream queues behind it, so that waiting for any later upload
+	// still means having seen this one
+	CU(cudaEventRecord(ctx->evUpload, (cudaStream_t)cuda_stream));
+	if(ctx->optCopyStreams) CU(cudaStreamWaitEvent(ctx->h2dStream, s->upEvent, 0));
+	s->upSeq = ++ctx->uploadSeq;
+	return SWCU_OK;
+}
+
 extern "C" void *swcu_mem_device_ptr(swcu_ctx *ctx, const void *host_ptr) { return ctx ? dev_ptr(ctx, host_ptr) : nullptr; }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -1058,28 +1058,36 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_binscan(const __grid_constant_
 		if(w < warp) warpBase += s_warp[w];
 		blockTotal += s_warp[w];
 	}
-	if(tid == 0)
+	if(warp == 0)
 	{
+		// look-back by the whole warp: lane l reads the state of predecessor blk - 1 - l (32 at a time, one trip to L2 per window
+		// instead of one per predecessor), the lanes up to the nearest predecessor that already knows its prefix add up
 		uint32_t prefix = 0;
-		if(blk == 0) state[0] = 0x80000000u | blockTotal;
+		if(blk == 0) { if(lane == 0) state[0] = 0x80000000u | blockTotal; }
 		else
 		{
-			state[blk] = 0x40000000u | blockTotal;
-			__threadfence();
-			for(int j = (int)blk - 1;; j--)
+			if(lane == 0) { state[blk] = 0x40000000u | blockTotal; __threadfence(); }
+			for(int hi = (int)blk - 1; hi >= 0; hi -= 32)
 			{
-				uint32_t sv;
-				do { sv = state[j]; } while((sv & 0xC0000000u) == 0);
-				prefix += sv & 0x3FFFFFFFu;
-				if(sv & 0x80000000u) break;
+				const int j = hi - lane;
+				uint32_t sv = 0x80000000u; // (lanes past block 0 contribute nothing and end the walk)
+				if(j >= 0)
+					do { sv = state[j]; } while((sv & 0xC0000000u) == 0);
+				const uint32_t done = __ballot_sync(0xFFFFFFFFu, (sv & 0x80000000u) != 0);
+				const int last = done ? __ffs(done) - 1 : 31; // nearest predecessor with an inclusive prefix
+				prefix += __reduce_add_sync(0xFFFFFFFFu, (lane <= last && j >= 0) ? (sv & 0x3FFFFFFFu) : 0u);
+				if(done) break;
 			}
-			state[blk] = 0x80000000u | (prefix + blockTotal);
+			if(lane == 0) state[blk] = 0x80000000u | (prefix + blockTotal);
 		}
-		s_prefix = prefix;
-		if((blk + 1) * SCAN_THREADS * SCAN_ITEMS >= n) // the block that holds the last bin
+		if(lane == 0)
 		{
-			start[n] = prefix + blockTotal;
-			c->pairTotal = prefix + blockTotal;
+			s_prefix = prefix;
+			if((blk + 1) * SCAN_THREADS * SCAN_ITEMS >= n) // the block that holds the last bin
+			{
+				start[n] = prefix + blockTotal;
+				c->pairTotal = prefix + blockTotal;
+			}
 		}
 	}
 	__syncthreads();
