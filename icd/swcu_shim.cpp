@@ -257,7 +257,9 @@ bool resolve(vk::ImageView *src, vk::ImageView *dst)
 	State &s = S();
 	if(!s.on || !src || !dst) return false;
 	const VkFormat fs = (VkFormat)src->getFormat(VK_IMAGE_ASPECT_COLOR_BIT), fd = (VkFormat)dst->getFormat(VK_IMAGE_ASPECT_COLOR_BIT);
-	if(fs != fd || (fs != VK_FORMAT_R8G8B8A8_UNORM && fs != VK_FORMAT_B8G8R8A8_UNORM)) return false;
+	// Blitter::fastResolve's formats, and the ones whose resolve is the generic blit (swcu_resolve restates both)
+	if(fs != fd || (fs != VK_FORMAT_R8G8B8A8_UNORM && fs != VK_FORMAT_B8G8R8A8_UNORM && fs != VK_FORMAT_R8G8B8A8_SRGB && fs != VK_FORMAT_B8G8R8A8_SRGB &&
+	                fs != VK_FORMAT_R16G16B16A16_SFLOAT && fs != VK_FORMAT_R32G32B32A32_SFLOAT)) return false;
 	if(src->getSampleCount() != 4 || dst->getSampleCount() != 1) return false;
 	if(src->getSubresourceRange().layerCount != 1 || dst->getSubresourceRange().layerCount != 1) return false;
 	const VkExtent2D es = src->getMipLevelExtent(0), ed = dst->getMipLevelExtent(0);

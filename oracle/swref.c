@@ -1314,9 +1314,6 @@ int swref_draw(const swcu_draw_desc *d, const swcu_shader_info *vs, const swcu_s
 	const int floatTarget = d->color.buffer && (d->color.format == FMT_R32G32B32A32_SFLOAT || d->color.format == FMT_R16G16B16A16_SFLOAT);
 	if(d->color.buffer && !floatTarget && d->color.format != FMT_R8G8B8A8_UNORM && d->color.format != FMT_B8G8R8A8_UNORM &&
 	   d->color.format != FMT_R8G8B8A8_SRGB && d->color.format != FMT_B8G8R8A8_SRGB) return SWCU_E_UNSUPPORTED;
-	if(floatTarget && d->sampleCount > 1) return SWCU_E_UNSUPPORTED; /* no Blitter::fastResolve for float formats: outside the subset */
-	if(d->color.buffer && (d->color.format == FMT_R8G8B8A8_SRGB || d->color.format == FMT_B8G8R8A8_SRGB) && d->sampleCount > 1)
-		return SWCU_E_UNSUPPORTED; /* the sRGB resolve is not Blitter::fastResolve: outside the subset */
 	if(d->depth.buffer && d->depth.format != FMT_D32_SFLOAT && d->depth.format != FMT_D16_UNORM) return SWCU_E_UNSUPPORTED;
 	if(d->depth.buffer && d->depth.format == FMT_D16_UNORM && d->stencil.buffer) return SWCU_E_UNSUPPORTED; /* D16_UNORM_S8_UINT: not in the subset */
 
@@ -1461,6 +1458,59 @@ int swref_clear(const swcu_attachment *att, uint32_t samples, const swcu_rect *a
 int swref_resolve(const swcu_attachment *src, uint32_t samples, const swcu_attachment *dst)
 {
 	if(samples != 4) return SWCU_E_UNSUPPORTED;
+	if(src->format == FMT_R8G8B8A8_SRGB || src->format == FMT_B8G8R8A8_SRGB || src->format == FMT_R16G16B16A16_SFLOAT || src->format == FMT_R32G32B32A32_SFLOAT)
+	{
+		/* Not Blitter::fastResolve (its format switch, Blitter.cpp:2142-2200, knows RGBA8 / BGRA8 UNORM only): Blitter::resolve falls
+		 * back to the generic blit (:2053-2071), whose routine reads every sample as floats (readFloat4 :368-452), brings sRGB samples
+		 * to linear light (ApplyScaleAndClamp :1459-1465: * 1/255, sRGBtoLinear on rgb, * 255), adds them up in sample order, scales by
+		 * 1 / samples (:1524-1545), takes the result back through the same function (pre-scaled: * 1/255, linearToSRGB, * 255) and
+		 * writes it (:640-745: RoundShort4 + unsigned saturation for the 8-bit formats, Reactor's Half() for R16G16B16A16_SFLOAT). */
+		unsigned int csr = _mm_getcsr();
+		_mm_setcsr(csr | 0x8040);
+		const int bpp = src->format == FMT_R32G32B32A32_SFLOAT ? 16 : (src->format == FMT_R16G16B16A16_SFLOAT ? 8 : 4);
+		const int srgb = bpp == 4;
+		for(uint32_t y = 0; y < dst->height; y++)
+			for(uint32_t x = 0; x < dst->width; x++)
+			{
+				float accum[4] = { 0, 0, 0, 0 };
+				for(int q = 0; q < 4; q++)
+				{
+					const uint8_t *s = (const uint8_t *)src->buffer + (size_t)q * src->sliceB + (size_t)y * src->pitchB + (size_t)x * bpp;
+					for(int ch = 0; ch < 4; ch++)
+					{
+						float c;
+						if(bpp == 16) c = ((const float *)s)[ch];
+						else if(bpp == 8) c = half_to_float(((const uint16_t *)s)[ch]);
+						else
+						{
+							c = (float)s[ch] * (1.0f / 255.0f);
+							if(ch < 3) c = srgb_to_linear(c); /* (byte order does not matter: the three colour bytes are treated alike) */
+							c = c * 255.0f;
+						}
+						accum[ch] = q == 0 ? c : accum[ch] + c;
+					}
+				}
+				uint8_t *t = (uint8_t *)dst->buffer + (size_t)y * dst->pitchB + (size_t)x * bpp;
+				for(int ch = 0; ch < 4; ch++)
+				{
+					float c = accum[ch] * 0.25f;
+					if(bpp == 16) ((float *)t)[ch] = c;
+					else if(bpp == 8) ((uint16_t *)t)[ch] = float_to_half(c);
+					else
+					{
+						c = c * (1.0f / 255.0f);
+						if(ch < 3) c = linear_to_srgb(c);
+						c = c * 255.0f;
+						int i = round_int(c); /* RoundShort4: cvtps2dq, packssdw; then packuswb */
+						i = i < -32768 ? -32768 : (i > 32767 ? 32767 : i);
+						t[ch] = (uint8_t)(i < 0 ? 0 : (i > 255 ? 255 : i));
+					}
+				}
+			}
+		_mm_setcsr(csr);
+		(void)srgb;
+		return SWCU_OK;
+	}
 	for(uint32_t y = 0; y < dst->height; y++)
 		for(uint32_t x = 0; x < dst->width * 4; x++)
 		{

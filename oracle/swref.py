@@ -221,9 +221,10 @@ def render_oracle(scene: Scene, att: dict | None = None, render_area=None) -> di
 
 def resolve_oracle(scene: Scene, att: dict) -> np.ndarray:
     H2, W = scene.padded_height(), scene.width
-    out = np.zeros((H2, W, 4), dtype=np.uint8)
-    src = capi.Attachment(att["color"].ctypes.data, scene.colorFormat, W * 4, H2 * W * 4, W, scene.height, 0)
-    dst = capi.Attachment(out.ctypes.data, scene.colorFormat, W * 4, H2 * W * 4, W, scene.height, 0)
+    out = np.zeros((H2, W, 4), dtype=scene.color_dtype())
+    bpp = scene.color_bpp()
+    src = capi.Attachment(att["color"].ctypes.data, scene.colorFormat, W * bpp, H2 * W * bpp, W, scene.height, 0)
+    dst = capi.Attachment(out.ctypes.data, scene.colorFormat, W * bpp, H2 * W * bpp, W, scene.height, 0)
     rc = lib().swref_resolve(C.byref(src), scene.samples, C.byref(dst))
     if rc != 0:
         raise RuntimeError(f"swref_resolve failed: {rc}")

@@ -728,9 +728,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	if(desc->indexType != 0 && desc->indexType != 2 && desc->indexType != 4) return fail(ctx, SWCU_E_UNSUPPORTED, "index type %u unsupported", desc->indexType);
 	if(desc->provokingVertexMode > 1) return fail(ctx, SWCU_E_INVALID, "bad provoking vertex mode");
 	const bool srgbTarget = desc->color.buffer && (desc->color.format == VKF_R8G8B8A8_SRGB || desc->color.format == VKF_B8G8R8A8_SRGB);
-	if(srgbTarget && desc->sampleCount > 1) return fail(ctx, SWCU_E_UNSUPPORTED, "multisampled sRGB colour targets are outside the subset (their resolve is not Blitter::fastResolve)");
 	const bool floatTarget = desc->color.buffer && (desc->color.format == VKF_R32G32B32A32_SFLOAT || desc->color.format == VKF_R16G16B16A16_SFLOAT);
-	if(floatTarget && desc->sampleCount > 1) return fail(ctx, SWCU_E_UNSUPPORTED, "multisampled floating-point colour targets are outside the subset (no Blitter::fastResolve)");
 	if(desc->color.buffer && !srgbTarget && !floatTarget && desc->color.format != VKF_R8G8B8A8_UNORM && desc->color.format != VKF_B8G8R8A8_UNORM)
 		return fail(ctx, SWCU_E_UNSUPPORTED, "colour format %u unsupported (R8G8B8A8 / B8G8R8A8 UNORM or SRGB, R16G16B16A16_SFLOAT, R32G32B32A32_SFLOAT)", desc->color.format);
 	d.colorEpp = desc->color.format == VKF_R32G32B32A32_SFLOAT ? 4u : (desc->color.format == VKF_R16G16B16A16_SFLOAT ? 2u : 1u);
@@ -1552,16 +1550,20 @@ extern "C" int swcu_resolve(swcu_ctx *ctx, const swcu_attachment *src, uint32_t 
 {
 	if(!ctx || !src || !dst || !src->buffer || !dst->buffer) return fail(ctx, SWCU_E_INVALID, "swcu_resolve: null argument");
 	if(samples != 4) return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_resolve: only 4x -> 1x");
-	if(src->format != dst->format || (src->format != VKF_R8G8B8A8_UNORM && src->format != VKF_B8G8R8A8_UNORM)) return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_resolve: format unsupported");
+	const bool fast = src->format == VKF_R8G8B8A8_UNORM || src->format == VKF_B8G8R8A8_UNORM; // Blitter::fastResolve; everything else: the generic blit
+	const int epp = src->format == VKF_R32G32B32A32_SFLOAT ? 4 : (src->format == VKF_R16G16B16A16_SFLOAT ? 2 : 1);
+	if(src->format != dst->format || (!fast && epp == 1 && src->format != VKF_R8G8B8A8_SRGB && src->format != VKF_B8G8R8A8_SRGB))
+		return fail(ctx, SWCU_E_UNSUPPORTED, "swcu_resolve: format unsupported (RGBA8 / BGRA8 UNORM or SRGB, R16G16B16A16_SFLOAT, R32G32B32A32_SFLOAT)");
 	if(src->width != dst->width || src->height != dst->height) return fail(ctx, SWCU_E_INVALID, "swcu_resolve: extent mismatch");
 	CU(cudaSetDevice(ctx->device));
-	unsigned char *s = dev_ptr(ctx, src->buffer, (size_t)3 * src->sliceB + (size_t)(src->height - 1) * src->pitchB + (size_t)src->width * 4);
-	unsigned char *t = dev_ptr(ctx, dst->buffer, (size_t)(dst->height - 1) * dst->pitchB + (size_t)dst->width * 4);
+	unsigned char *s = dev_ptr(ctx, src->buffer, (size_t)3 * src->sliceB + (size_t)(src->height - 1) * src->pitchB + (size_t)src->width * 4 * epp);
+	unsigned char *t = dev_ptr(ctx, dst->buffer, (size_t)(dst->height - 1) * dst->pitchB + (size_t)dst->width * 4 * epp);
 	if(!s || !t) return fail(ctx, SWCU_E_INVALID, "swcu_resolve: attachment is not inside a registered range");
 	int rc;
 	if((rc = main_touches(ctx, src->buffer, false)) || (rc = main_touches(ctx, dst->buffer, true))) return rc;
-	LaunchScope ls(ctx, "k_resolve4");
-	k_resolve4<<<dim3((src->width + 255) / 256, src->height), 256, 0, ctx->stream>>>(s, src->pitchB, src->sliceB, t, dst->pitchB, (int)src->width, (int)src->height);
+	LaunchScope ls(ctx, fast ? "k_resolve4" : "k_resolve4_generic");
+	if(fast) k_resolve4<<<dim3((src->width + 255) / 256, src->height), 256, 0, ctx->stream>>>(s, src->pitchB, src->sliceB, t, dst->pitchB, (int)src->width, (int)src->height);
+	else k_resolve4_generic<<<dim3((src->width + 127) / 128, src->height), 128, 0, ctx->stream>>>(s, src->pitchB, src->sliceB, t, dst->pitchB, (int)src->width, (int)src->height, epp);
 	CU(cudaGetLastError());
 	return SWCU_OK;
 }

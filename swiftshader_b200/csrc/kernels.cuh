@@ -2537,6 +2537,70 @@ __global__ void k_resolve4(const unsigned char *src, int srcPitchB, int srcSlice
 	*(uint32_t *)(dst + (size_t)y * dstPitchB + 4 * (size_t)x) = pavgb4(pavgb4(s0, s1), pavgb4(s2, s3));
 }
 
+// Blitter::resolve for the formats fastResolve does not know (its switch, Blitter.cpp:2142-2200, has RGBA8 / BGRA8 UNORM only): the
+// generic blit routine (:2053-2071).  Every sample is read as floats (readFloat4 :368-452); sRGB samples go to linear light
+// (ApplyScaleAndClamp :1459-1465: * 1/255, sRGBtoLinear on rgb, * 255); the samples are added in order and scaled by 1/4 (:1524-1545);
+// the result comes back through the same function (pre-scaled: * 1/255, linearToSRGB, * 255) and is written (:640-745: RoundShort4 +
+// unsigned saturation for the 8-bit formats, Reactor's Half() for R16G16B16A16_SFLOAT, the floats themselves for R32G32B32A32_SFLOAT).
+// epp = 32-bit words per pixel: 1 (sRGB8), 2 (RGBA16F), 4 (RGBA32F).
+__global__ void k_resolve4_generic(const unsigned char *src, int srcPitchB, int srcSliceB, unsigned char *dst, int dstPitchB, int w, int h, int epp)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if(x >= w || y >= h) return;
+	const size_t o = (size_t)y * srcPitchB + 4 * (size_t)epp * x;
+	float acc[4] = { 0, 0, 0, 0 };
+#pragma unroll
+	for(int q = 0; q < 4; q++)
+	{
+		const unsigned char *s = src + o + (size_t)q * srcSliceB;
+		float c[4];
+		if(epp == 4)
+		{
+			const float4 v = *(const float4 *)s;
+			c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+		}
+		else if(epp == 2)
+		{
+			const uint2 v = *(const uint2 *)s;
+			c[0] = half_to_float(v.x & 0xFFFFu); c[1] = half_to_float(v.x >> 16); c[2] = half_to_float(v.y & 0xFFFFu); c[3] = half_to_float(v.y >> 16);
+		}
+		else
+		{
+			const uint32_t v = *(const uint32_t *)s;
+#pragma unroll
+			for(int ch = 0; ch < 4; ch++)
+			{
+				float t = fmul((float)((v >> (8 * ch)) & 0xFFu), 1.0f / 255.0f);
+				if(ch < 3) t = srgb_to_linear(t); // (the three colour bytes are treated alike: RGBA or BGRA order does not matter)
+				c[ch] = fmul(t, 255.0f);
+			}
+		}
+#pragma unroll
+		for(int ch = 0; ch < 4; ch++) acc[ch] = q == 0 ? c[ch] : fadd(acc[ch], c[ch]);
+	}
+	unsigned char *t = dst + (size_t)y * dstPitchB + 4 * (size_t)epp * x;
+	float r[4];
+#pragma unroll
+	for(int ch = 0; ch < 4; ch++) r[ch] = fmul(acc[ch], 0.25f);
+	if(epp == 4) *(float4 *)t = make_float4(r[0], r[1], r[2], r[3]);
+	else if(epp == 2) *(uint2 *)t = make_uint2(float_to_half(r[0]) | (float_to_half(r[1]) << 16), float_to_half(r[2]) | (float_to_half(r[3]) << 16));
+	else
+	{
+		uint32_t pk = 0;
+#pragma unroll
+		for(int ch = 0; ch < 4; ch++)
+		{
+			float v = fmul(r[ch], 1.0f / 255.0f);
+			if(ch < 3) v = linear_to_srgb(v);
+			v = fmul(v, 255.0f);
+			const int i = clampi(round_int(v), -32768, 32767); // RoundShort4: cvtps2dq + packssdw; then packuswb
+			pk |= (uint32_t)clampi(i, 0, 255) << (8 * ch);
+		}
+		*(uint32_t *)t = pk;
+	}
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // multi-GPU: finished bands go to the presenting GPU by stores over NVLink into its (IPC-mapped) frame, not by a collective
 // ------------------------------------------------------------------------------------------------------------------

@@ -469,10 +469,11 @@ class Device:
     def resolve(self, scene: Scene, att: dict) -> np.ndarray:
         """Blitter::fastResolve on the device shadows; returns the 1x image."""
         H2, W = scene.padded_height(), scene.width
-        out = np.zeros((1, H2, W, 4), dtype=np.uint8)
+        out = np.zeros((1, H2, W, 4), dtype=scene.color_dtype())
+        bpp = scene.color_bpp()
         self.register(out, upload=True)
-        src = capi.Attachment(att["color"].ctypes.data, scene.colorFormat, W * 4, H2 * W * 4, W, scene.height, 0)
-        dst = capi.Attachment(out.ctypes.data, scene.colorFormat, W * 4, H2 * W * 4, W, scene.height, 0)
+        src = capi.Attachment(att["color"].ctypes.data, scene.colorFormat, W * bpp, H2 * W * bpp, W, scene.height, 0)
+        dst = capi.Attachment(out.ctypes.data, scene.colorFormat, W * bpp, H2 * W * bpp, W, scene.height, 0)
         self.check(self.lib.swcu_resolve(self.ctx, C.byref(src), scene.samples, C.byref(dst)))
         self.download(out)
         self.sync()
@@ -512,7 +513,7 @@ class Frame:
         self.dev, self.scene = dev, scene
         self.att = scene.alloc_attachments()
         H2, W = scene.padded_height(), scene.width
-        self.resolved = np.zeros((1, H2, W, 4), dtype=np.uint8) if scene.samples > 1 else None
+        self.resolved = np.zeros((1, H2, W, 4), dtype=scene.color_dtype()) if scene.samples > 1 else None
         self.keep: list = []
         self.inputs: list = []
         self.descs = [scene.build_desc(dr, self.att, self.keep, render_area, self.inputs) for dr in scene.draws]
@@ -544,7 +545,7 @@ class Frame:
             return capi.Attachment(self.att["depth"].ctypes.data, sc.depthFormat, W * zb, H2 * W * zb, W, sc.height, 0)
         if key == "stencil":
             return capi.Attachment(self.att["stencil"].ctypes.data, FMT_S8_UINT, W, H2 * W, W, sc.height, 0)
-        return capi.Attachment(self.resolved.ctypes.data, sc.colorFormat, W * 4, H2 * W * 4, W, sc.height, 0)
+        return capi.Attachment(self.resolved.ctypes.data, sc.colorFormat, W * cb, H2 * W * cb, W, sc.height, 0)
 
     def clear(self):
         """Attachment load-op CLEAR on the device (Blitter::fastClear), whole framebuffer."""

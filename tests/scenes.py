@@ -765,6 +765,21 @@ def points(seed: int) -> Scene:
     return Scene(2 * CELL, 2 * CELL, [d], samples=4 if seed % 4 == 2 else 1, hasDepth=True, clearColor=(0.0, 0.0, 0.0, 1.0))
 
 
+def msaafmt(seed: int) -> Scene:
+    """4x MSAA on the colour formats whose resolve is NOT Blitter::fastResolve but the generic blit (Blitter.cpp:2053-2071, :1524-1545):
+    sRGB8 (decode per sample, average in linear light, encode), R16G16B16A16_SFLOAT, R32G32B32A32_SFLOAT — opaque, blended and
+    depth-tested layers, colours outside [0, 1] on the float targets."""
+    rng = np.random.default_rng(25000 + seed)
+    fmt = [FMT_R8G8B8A8_SRGB, FMT_R16G16B16A16_SFLOAT, FMT_R32G32B32A32_SFLOAT, FMT_B8G8R8A8_SRGB][seed % 4]
+    fl = fmt in (FMT_R16G16B16A16_SFLOAT, FMT_R32G32B32A32_SFLOAT)
+    clear = (0.25, 0.5, 0.125, 1.0) if fl else [(0.0, 0.0, 0.0, 1.0), (1.0, 1.0, 1.0, 0.0)][(seed // 4) % 2]
+    lo, hi = (-0.75, 2.5) if fl else (0.0, 1.0)
+    tris = [_verts(rng, _tri_kind(rng, (5, 0, 1, 4)[i % 4]), persp=(i % 2 == 0), colour=rng.uniform(lo, hi, (3, 4))) for i in range(10)]
+    mode = (seed // 4) % 3
+    d = Draw(np.concatenate(tris), P4C4, "vs_pos4_col4", "fs_col4", blend=(mode == 1), depthTest=(mode == 2), depthWrite=(mode == 2))
+    return Scene(CELL, CELL, [d], samples=4, colorFormat=fmt, clearColor=clear, hasDepth=(mode == 2))
+
+
 FAMILIES = {
     # name: (generator, number of seeds)
     "coverage": (coverage, 40),
@@ -791,6 +806,7 @@ FAMILIES = {
     "lines": (lines, 16),
     "points": (points, 12),
     "zclamp": (zclamp, 8),
+    "msaafmt": (msaafmt, 12),
 }
 
 

@@ -25,7 +25,9 @@ NAMES = ["benchmark_0_720p", "benchmark_1_720p", "benchmark_2_720p", "benchmark_
          "coverage_0", "coverage_7", "zclip_1", "cull_3", "depth_ops_5", "blend_4", "blend_17", "stencil_3", "stencil_10", "texture_2", "texture_9",
          "msaa_1", "msaa_4", "topology_1", "topology_4", "scissor_2", "depth16_3", "srgb_2", "floatrt_5", "fragtests_6", "texsplit_3", "blendoff_0",
          # f4: a transform from push constants in the vertex stage (vkCmdPushConstants -> DrawData::pushConstants), lines, points
-         "mvp_0", "mvp_2", "mvp_4", "lines_1", "lines_2", "lines_3", "points_0", "points_2", "points_5"]
+         "mvp_0", "mvp_2", "mvp_4", "lines_1", "lines_2", "lines_3", "points_0", "points_2", "points_5",
+         # depthClampEnable; 4x MSAA on the formats whose resolve is the generic blit
+         "zclamp_1", "zclamp_3", "msaafmt_0", "msaafmt_1", "msaafmt_2", "msaafmt_3", "msaafmt_5"]
 
 
 def _sha(a):
