@@ -334,6 +334,7 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
             in_sets = [(frame.inputs, frame.descs), (alt_inputs, alt_descs)]
             sharded_upload = N > 1 and os.environ.get("SWCU_SHARD_UPLOAD", "1") != "0"
             gather_stream = torch.cuda.Stream() if sharded_upload else None
+            gather_views = {}
             up_bytes = [0]
 
             def upload_set(k):
@@ -354,7 +355,10 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
                         # the collective runs on a stream of its own, beside the frame that is rendering: it waits for my slice's upload,
                         # the draw that reads the buffer waits for it
                         dev.check(dev.lib.swcu_mem_acquire_on(dev.ctx, flat.ctypes.data, gather_stream.cuda_stream))
-                        whole = torch.as_tensor(_DevArr(dev.device_ptr(b), chunk * N), device=dev_s)
+                        key = (b.ctypes.data, chunk)
+                        if key not in gather_views:  # (wrapping the shadow in a tensor costs more host time than the collective's launch)
+                            gather_views[key] = torch.as_tensor(_DevArr(dev.device_ptr(b), chunk * N), device=dev_s)
+                        whole = gather_views[key]
                         with torch.cuda.stream(gather_stream):
                             dist.all_gather_into_tensor(whole, whole[rank * chunk:(rank + 1) * chunk])
                         dev.check(dev.lib.swcu_mem_release_on(dev.ctx, flat.ctypes.data, gather_stream.cuda_stream))

@@ -100,7 +100,7 @@ struct DrawObjects
 	VkPipeline pipeline[2]; // [0] for the clearing pass, [1] for the LOAD pass (render-pass compatible, but keep it explicit)
 	VkPipelineLayout layout;
 	VkDescriptorSet dset = VK_NULL_HANDLE;
-	VkBuffer vb, ib = VK_NULL_HANDLE;
+	VkBuffer vb, ib = VK_NULL_HANDLE, instb = VK_NULL_HANDLE;
 };
 
 int main(int argc, char **argv)
@@ -273,6 +273,11 @@ int main(int argc, char **argv)
 			mkBuffer(blobSize(d.indexBlob), VK_BUFFER_USAGE_INDEX_BUFFER_BIT, o.ib, p);
 			memcpy(p, blobPtr(d.indexBlob), blobSize(d.indexBlob));
 		}
+		if(d.numInstanceAttribs)
+		{
+			mkBuffer(blobSize(d.instanceBlob), VK_BUFFER_USAGE_VERTEX_BUFFER_BIT, o.instb, p);
+			memcpy(p, blobPtr(d.instanceBlob), blobSize(d.instanceBlob));
+		}
 		VkDescriptorSetLayout dsl = VK_NULL_HANDLE;
 		if(d.hasTexture)
 		{
@@ -356,13 +361,15 @@ int main(int argc, char **argv)
 		st[0].sType = st[1].sType = VK_STRUCTURE_TYPE_PIPELINE_SHADER_STAGE_CREATE_INFO;
 		st[0].stage = VK_SHADER_STAGE_VERTEX_BIT; st[0].module = vsm; st[0].pName = "main";
 		st[1].stage = VK_SHADER_STAGE_FRAGMENT_BIT; st[1].module = fsm; st[1].pName = "main";
-		VkVertexInputBindingDescription vbd{ 0, d.stride, VK_VERTEX_INPUT_RATE_VERTEX };
-		VkVertexInputAttributeDescription vad[SCENE_MAX_ATTRIBS];
-		for(uint32_t a = 0; a < d.numAttribs; a++) vad[a] = { d.attrib[a].location, 0, (VkFormat)d.attrib[a].format, d.attrib[a].offset };
+		VkVertexInputBindingDescription vbd[2] = { { 0, d.stride, VK_VERTEX_INPUT_RATE_VERTEX }, { 1, d.instanceStride, VK_VERTEX_INPUT_RATE_INSTANCE } };
+		VkVertexInputAttributeDescription vad[SCENE_MAX_ATTRIBS + 4];
+		uint32_t nvad = 0;
+		for(uint32_t a = 0; a < d.numAttribs; a++) vad[nvad++] = { d.attrib[a].location, 0, (VkFormat)d.attrib[a].format, d.attrib[a].offset };
+		for(uint32_t a = 0; a < d.numInstanceAttribs && a < 4; a++) vad[nvad++] = { d.instanceAttrib[a].location, 1, (VkFormat)d.instanceAttrib[a].format, d.instanceAttrib[a].offset };
 		VkPipelineVertexInputStateCreateInfo vis{ VK_STRUCTURE_TYPE_PIPELINE_VERTEX_INPUT_STATE_CREATE_INFO };
-		vis.vertexBindingDescriptionCount = 1;
-		vis.pVertexBindingDescriptions = &vbd;
-		vis.vertexAttributeDescriptionCount = d.numAttribs;
+		vis.vertexBindingDescriptionCount = d.numInstanceAttribs ? 2 : 1;
+		vis.pVertexBindingDescriptions = vbd;
+		vis.vertexAttributeDescriptionCount = nvad;
 		vis.pVertexAttributeDescriptions = vad;
 		VkPipelineInputAssemblyStateCreateInfo ias{ VK_STRUCTURE_TYPE_PIPELINE_INPUT_ASSEMBLY_STATE_CREATE_INFO };
 		ias.topology = (VkPrimitiveTopology)d.topology;
@@ -456,12 +463,14 @@ int main(int argc, char **argv)
 			if(d.pushConstantBytes) vkCmdPushConstants(c, o.layout, VK_SHADER_STAGE_VERTEX_BIT, 0, d.pushConstantBytes, d.pushConstants);
 			VkDeviceSize off = 0;
 			vkCmdBindVertexBuffers(c, 0, 1, &o.vb, &off);
+			if(d.numInstanceAttribs) vkCmdBindVertexBuffers(c, 1, 1, &o.instb, &off);
+			const uint32_t instances = d.instanceCount ? d.instanceCount : 1;
 			if(d.indexType)
 			{
 				vkCmdBindIndexBuffer(c, o.ib, 0, d.indexType == 2 ? VK_INDEX_TYPE_UINT16 : VK_INDEX_TYPE_UINT32);
-				vkCmdDrawIndexed(c, d.count, 1, d.firstIndex, d.vertexOffset, 0);
+				vkCmdDrawIndexed(c, d.count, instances, d.firstIndex, d.vertexOffset, 0);
 			}
-			else vkCmdDraw(c, d.count, 1, d.firstIndex, 0);
+			else vkCmdDraw(c, d.count, instances, d.firstIndex, 0);
 		}
 		vkCmdEndRenderPass(c);
 		if(copy)

@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define SCENE_MAGIC 0x43535753u /* "SWSC" */
-#define SCENE_VERSION 5u
+#define SCENE_VERSION 6u
 #define SCENE_MAX_ATTRIBS 8
 
 #pragma pack(push, 4)
@@ -62,6 +62,10 @@ typedef struct SceneDraw
 	uint32_t pushConstantBytes; /* vkCmdPushConstants(VERTEX, 0, bytes) ahead of the draw; 0 = no push-constant range */
 	uint32_t pushConstants[32];
 	uint32_t depthClampEnable;  /* VkPipelineRasterizationStateCreateInfo::depthClampEnable */
+	/* instancing: vkCmdDraw*(…, instanceCount, …); attributes of vertex binding 1 (VK_VERTEX_INPUT_RATE_INSTANCE) */
+	uint32_t instanceCount;     /* >= 1 */
+	uint32_t instanceBlob, instanceStride, numInstanceAttribs;
+	struct { uint32_t location, format, offset; } instanceAttrib[4];
 } SceneDraw;
 
 typedef struct SceneBlob { uint64_t offset, size; } SceneBlob;

@@ -142,6 +142,12 @@ def _vs_mvp():
     return _vs(pos, {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2), 3: _inp(1, 3)}, p)
 
 
+def _vs_inst():
+    p = _Program()
+    q = [p.add(_inp(0, c), _inp(2, c)) for c in range(4)]
+    return _vs(q, {c: _inp(1, c) for c in range(4)}, p)
+
+
 def _vs_xform():
     # p = inPos * pc.scale.xyz + pc.offset.xyz; gl_Position = vec4(p, pc.offset.w); outColor = inColor * pc.tint
     p = _Program()
@@ -193,6 +199,8 @@ SHADER_SPECS = {
     # gl_Position = inPos; gl_PointSize = inSize (loc 2); outColor = inColor
     "vs_point_pos4_col4": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _inp(0, 3)],
                                       {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2), 3: _inp(1, 3)}, point_size=_inp(2, 0)),
+    # gl_Position = inPos + instOffset (loc 2, per instance); outColor = instColor (loc 1, per instance)
+    "vs_inst_pos4_col4": _vs_inst,
     "fs_white": lambda: _fs([_const(1.0)] * 4),
     "fs_col3": lambda: _fs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)]),
     "fs_col4": lambda: _fs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _inp(0, 3)]),
@@ -209,7 +217,7 @@ def render_oracle(scene: Scene, att: dict | None = None, render_area=None) -> di
     """Render every draw of the scene with the C restatement, in order, into host numpy attachments."""
     L = lib()
     att = att if att is not None else scene.alloc_attachments()
-    for dr in scene.draws:
+    for dr in scene.flat_draws():
         keep: list = []
         d = scene.build_desc(dr, att, keep, render_area)
         vs, fs = shader_spec(dr.vs), shader_spec(dr.fs)

@@ -9,6 +9,7 @@ Nothing here computes pixels.  ``Scene.write_ref_scene`` serialises the same inp
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 import struct
 from dataclasses import dataclass, field
 from typing import Optional
@@ -136,6 +137,11 @@ class Draw:
     pushConstants: Optional[np.ndarray] = None  # float32 / uint32 words pushed for the vertex stage (<= 32)
     lineWidth: float = 1.0
     depthClamp: bool = False  # depthClampEnable: no near / far clipping, fragment depth clamped to the viewport's depth range
+    # instancing (CmdDrawBase::draw, VkCommandBuffer.cpp:987-1010): one Renderer::draw per instance, the streams of the instance-rate
+    # binding moved on by its stride in between (Inputs::advanceInstanceAttributes, Context.cpp:447-461); the vertices see stride 0
+    instances: Optional[np.ndarray] = None  # (instanceCount, k) float32: the instance-rate vertex buffer (binding 1)
+    instanceAttribs: list = field(default_factory=list)  # [(location, components, float_offset)] inside a row of `instances`
+    instanceRow: Optional[int] = None  # set on the per-instance copies Scene.flat_draws() hands out
 
     def vertex_count(self) -> int:
         if self.count is not None:
@@ -208,6 +214,16 @@ class Scene:
             att["stencil"] = np.full((S, H2, W), self.clearStencil & 0xFF, dtype=np.uint8)
         return att
 
+    def flat_draws(self) -> list:
+        """The draws as sw::Renderer::draw sees them: an instanced draw is one draw per instance."""
+        out = []
+        for dr in self.draws:
+            if dr.instances is None:
+                out.append(dr)
+            else:
+                out += [dataclasses.replace(dr, instanceRow=i) for i in range(dr.instances.shape[0])]
+        return out
+
     # ---- flattening into the C-ABI descriptor ----
     def build_desc(self, draw: Draw, att: dict, keep: list, render_area: Optional[tuple] = None,
                    dev: Optional[list] = None) -> capi.DrawDesc:
@@ -247,6 +263,18 @@ class Scene:
             vi.robustnessSize = max(0, verts.nbytes - off * 4)
             vi.vertexStride = stride
             vi.format = FLOAT_FORMATS[comps]
+        if draw.instances is not None:
+            inst = np.ascontiguousarray(draw.instances, dtype=np.float32)
+            keep.append(inst)
+            dev.append(inst)
+            row = draw.instanceRow or 0
+            for (loc, comps, off) in draw.instanceAttribs:
+                vi = d.input[loc]
+                start = (row * inst.shape[1] + off) * 4
+                vi.buffer = inst.ctypes.data + start
+                vi.robustnessSize = max(0, inst.nbytes - start)
+                vi.vertexStride = 0
+                vi.format = FLOAT_FORMATS[comps]
         vs, fs = spirv.shader(draw.vs), spirv.shader(draw.fs)
         keep += [vs, fs]
         d.vertexShader, d.vertexShaderWords = vs.ctypes.data, len(vs)
@@ -350,8 +378,20 @@ class Scene:
                 pc[:npc] = w
             r += struct.pack("<fI", dr.lineWidth, 4 * npc) + pc.tobytes()
             r += struct.pack("<I", int(dr.depthClamp))
+            # instancing: the instance-rate buffer (binding 1) and its attributes
+            if dr.instances is not None:
+                inst = np.ascontiguousarray(dr.instances, dtype=np.float32)
+                r += struct.pack("<IIII", inst.shape[0], blob(inst), inst.shape[1] * 4, len(dr.instanceAttribs))
+                for i in range(4):
+                    if i < len(dr.instanceAttribs):
+                        loc, comps, off = dr.instanceAttribs[i]
+                        r += struct.pack("<III", loc, FLOAT_FORMATS[comps], off * 4)
+                    else:
+                        r += struct.pack("<III", 0, 0, 0)
+            else:
+                r += struct.pack("<IIII", 1, 0, 0, 0) + struct.pack("<III", 0, 0, 0) * 4
             recs.append(r)
-        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 5, self.width, self.height, self.samples, self.colorFormat,
+        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 6, self.width, self.height, self.samples, self.colorFormat,
                           (2 if self.depthFormat == FMT_D16_UNORM else 1) if self.hasDepth else 0, int(self.hasStencil), *self.clearColor, self.clearDepth, self.clearStencil,
                           len(recs), len(blobs))
         off = len(hdr) + sum(len(r) for r in recs) + 16 * len(blobs)
@@ -485,7 +525,7 @@ class Device:
         att = att if att is not None else scene.alloc_attachments()
         keep: list = []
         dev: list = []
-        descs = [scene.build_desc(dr, att, keep, render_area, dev) for dr in scene.draws]
+        descs = [scene.build_desc(dr, att, keep, render_area, dev) for dr in scene.flat_draws()]
         bufs, seen = [], set()
         for b in list(att.values()) + dev:
             if b.ctypes.data not in seen:
@@ -516,7 +556,7 @@ class Frame:
         self.resolved = np.zeros((1, H2, W, 4), dtype=scene.color_dtype()) if scene.samples > 1 else None
         self.keep: list = []
         self.inputs: list = []
-        self.descs = [scene.build_desc(dr, self.att, self.keep, render_area, self.inputs) for dr in scene.draws]
+        self.descs = [scene.build_desc(dr, self.att, self.keep, render_area, self.inputs) for dr in scene.flat_draws()]
         seen = set()
         self.inputs = [b for b in self.inputs if not (b.ctypes.data in seen or seen.add(b.ctypes.data))]
         self.bufs = list(self.att.values()) + self.inputs + ([self.resolved] if self.resolved is not None else [])

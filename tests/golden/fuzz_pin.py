@@ -1,7 +1,7 @@
 """Extra pinning run of the CPU oracle against the REFERENCE ICD on scenes that are NOT in the golden set: every scene family
 of tests/scenes.py at seeds beyond the committed range (the families draw their geometry from the seed, their state from
 seed % k).  Nothing is written; mismatches are listed.  Runs only where oracle/_ref holds the reference build.
-usage: python tests/golden/fuzz_pin.py [first_seed] [seeds_per_family]   |   python tests/golden/fuzz_pin.py mixed <first_seed> <count>"""
+usage: python tests/golden/fuzz_pin.py [first_seed] [seeds_per_family] [family,family,...]   |   python tests/golden/fuzz_pin.py mixed <first_seed> <count>"""
 import os
 import sys
 
@@ -50,8 +50,11 @@ def main():
 
     first = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     count = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    only = sys.argv[3].split(",") if len(sys.argv) > 3 else None
     bad = total = 0
     for fam, (gen, _) in scenes.FAMILIES.items():
+        if only and fam not in only:
+            continue
         for s in range(first, first + count):
             try:
                 scene = gen(s)

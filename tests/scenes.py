@@ -780,6 +780,22 @@ def msaafmt(seed: int) -> Scene:
     return Scene(CELL, CELL, [d], samples=4, colorFormat=fmt, clearColor=clear, hasDepth=(mode == 2))
 
 
+def instanced(seed: int) -> Scene:
+    """Instanced draws (CmdDrawBase::draw, VkCommandBuffer.cpp:987-1010: one sw::Renderer::draw per instance, the instance-rate
+    streams moved on by Inputs::advanceInstanceAttributes in between): per-instance colour and offset from vertex binding 1."""
+    rng = np.random.default_rng(26000 + seed)
+    n_inst = 3 + seed % 6
+    tris = np.concatenate([_verts(rng, _tri_kind(rng, (1, 5, 4)[i % 3]) * 0.5, persp=(i % 2 == 0)) for i in range(6)])[:, :4].copy()
+    inst = np.zeros((n_inst, 8), dtype=np.float32)
+    inst[:, 0:4] = rng.uniform(0, 1, (n_inst, 4))
+    inst[:, 4:6] = rng.uniform(-0.5, 0.5, (n_inst, 2))
+    inst[:, 6] = rng.uniform(-0.1, 0.1, n_inst)
+    idx = rng.integers(0, len(tris), 12).astype(np.uint16) if seed % 3 == 1 else None
+    d = Draw(tris, [(0, 4, 0)], "vs_inst_pos4_col4", "fs_col4", indices=idx, instances=inst, instanceAttribs=[(1, 4, 0), (2, 4, 4)],
+             depthTest=(seed % 2 == 0), depthWrite=True, blend=(seed % 2 == 1))
+    return Scene(CELL, CELL, [d], samples=4 if seed % 4 == 3 else 1, hasDepth=True, clearColor=(0.0, 0.0, 0.0, 1.0))
+
+
 FAMILIES = {
     # name: (generator, number of seeds)
     "coverage": (coverage, 40),
@@ -807,6 +823,7 @@ FAMILIES = {
     "points": (points, 12),
     "zclamp": (zclamp, 8),
     "msaafmt": (msaafmt, 12),
+    "instanced": (instanced, 8),
 }
 
 

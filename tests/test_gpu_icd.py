@@ -27,7 +27,9 @@ NAMES = ["benchmark_0_720p", "benchmark_1_720p", "benchmark_2_720p", "benchmark_
          # f4: a transform from push constants in the vertex stage (vkCmdPushConstants -> DrawData::pushConstants), lines, points
          "mvp_0", "mvp_2", "mvp_4", "lines_1", "lines_2", "lines_3", "points_0", "points_2", "points_5",
          # depthClampEnable; 4x MSAA on the formats whose resolve is the generic blit
-         "zclamp_1", "zclamp_3", "msaafmt_0", "msaafmt_1", "msaafmt_2", "msaafmt_3", "msaafmt_5"]
+         "zclamp_1", "zclamp_3", "msaafmt_0", "msaafmt_1", "msaafmt_2", "msaafmt_3", "msaafmt_5",
+         # instanced draws: the reference's own loop over the instances (CmdDrawBase::draw) calls the CUDA path once per instance
+         "instanced_0", "instanced_1", "instanced_3"]
 
 
 def _sha(a):
