@@ -173,7 +173,16 @@ extern "C" int swcu_create(swcu_ctx **out, int device_ordinal)
 	ctx->stream = ctx->ownStream;
 	if((e = cudaEventCreate(&ctx->t0)) != cudaSuccess) return bail("cudaEventCreate", e);
 	if((e = cudaEventCreate(&ctx->t1)) != cudaSuccess) return bail("cudaEventCreate", e);
-	if((e = cudaStreamCreateWithFlags(&ctx->setupStream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+	{
+		// The setup phase of draw i+1 (set-up, group barrier, scan, fill: mostly short, latency-bound launches) runs beside the tile kernel
+		// of draw i, which fills the machine: with a higher stream priority its blocks are placed ahead of the tile kernel's remaining
+		// ones instead of behind them, so the chain is over when the tile kernel drains.  SWCU_SETUP_PRIORITY=0 keeps the default.
+		int least = 0, greatest = 0;
+		cudaDeviceGetStreamPriorityRange(&least, &greatest);
+		const char *pe = getenv("SWCU_SETUP_PRIORITY");
+		const int prio = (pe && pe[0] == '0') ? least : greatest;
+		if((e = cudaStreamCreateWithPriority(&ctx->setupStream, cudaStreamNonBlocking, prio)) != cudaSuccess) return bail("cudaStreamCreate", e);
+	}
 	if((e = cudaEventCreateWithFlags(&ctx->evUpload, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
 	if((e = cudaEventCreateWithFlags(&ctx->evMark, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
 	if((e = cudaEventCreateWithFlags(&ctx->evDownload, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
