@@ -34,17 +34,26 @@ def main():
     bad = 0
     import ctypes as C
     from swiftshader_b200 import capi
-    for name in ("c4", "c5", "c2"):
-        sc = workloads.small(name).scene
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import scenes
+    wl_hashes = json.load(open(os.path.join(ROOT, "tests", "golden", "workload_hashes.json")))
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_hashes.json")))
+    cases = [(n, workloads.small(n).scene, wl_hashes[f"small_{n}"]["hashes"]["color"], ("nccl", "peer", "group")) for n in ("c4", "c5", "c2")]
+    # the general set-up kernel in a group (a transform in the vertex stage, lines, points: quads that are always clipped and
+    # re-projected, delivered to the owners of their rows like any other record), instanced draws = several draws per frame
+    for n, gen, seed in (("mvp_0", scenes.mvp, 0), ("mvp_4", scenes.mvp, 4), ("lines_1", scenes.lines, 1), ("lines_3", scenes.lines, 3),
+                         ("points_0", scenes.points, 0), ("points_2", scenes.points, 2), ("instanced_0", scenes.instanced, 0)):
+        cases.append((n, gen(seed), gold[n]["color"], ("group",)))
+    for name, sc, want_sha, modes in cases:
         H, W = sc.height, sc.width
         if H % (2 * world):
             continue
-        for mode in ("nccl", "peer", "group"):
+        for mode in modes:
             # "group": the setup of every binned draw is sharded by triangle range as well (swcu_group_*: records, bin counts and big-list
             # entries stored into the owning rank's work buffers over NVLink); the bands are delivered like in "peer"
             grp = None
             if mode == "group":
-                grp = bands.Group(dev, sc, world, rank, max(d.primitive_count() for d in sc.draws), 6, sc.samples)
+                grp = bands.Group(dev, sc, world, rank, max(d.primitive_count() for d in sc.flat_draws()), 6, sc.samples)
                 dev.set_option("force_binned", 1)  # the single triangles too: a share can be empty, a big triangle spans every band
             fr = Frame(dev, sc, render_area=bands.render_area(W, H, world, rank))
             y0, y1 = bands.band_rows(H, world, rank)
@@ -95,7 +104,6 @@ def main():
                 ref = swref.resolve_oracle(sc, want) if sc.samples > 1 else want["color"][0]
                 ok = np.array_equal(got, ref[:H])
                 # ... and with what the unmodified reference ICD rendered for the same scene (tests/golden/gen_workload_hashes.py)
-                want_sha = json.load(open(os.path.join(ROOT, "tests", "golden", "workload_hashes.json")))[f"small_{name}"]["hashes"]["color"]
                 ok = ok and hashlib.sha256(np.ascontiguousarray(got).tobytes()).hexdigest() == want_sha
                 print(f"multi_gpu_check {name} world={world} gather={mode}: {'ok' if ok else 'MISMATCH'}", flush=True)
                 bad += 0 if ok else 1
