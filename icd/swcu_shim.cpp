@@ -411,6 +411,29 @@ void draw(const DrawArgs &args)
 		si.mipLodBias = sampler->mipLodBias; si.minLod = sampler->minLod; si.maxLod = sampler->maxLod;
 		si.anisotropyEnable = sampler->anisotropyEnable; si.compareEnable = sampler->compareEnable; si.unnormalizedCoordinates = sampler->unnormalizedCoordinates;
 	}
+	// the uniform buffers the vertex shader reads: the vk::BufferDescriptor { ptr, sizeInBytes } at the binding's offset in the bound
+	// set (VkDescriptorSetLayout.hpp:75-82; a dynamic one moved on by its dynamic offset, SpirvShaderMemory.cpp / EmitDescriptor*).
+	// Host memory the application wrote: the library reads the words the vertex program uses during swcu_draw.
+	swcu_shader_info vinfo;
+	if(s.api.shader_translate(vs->insns.data(), (uint32_t)vs->insns.size(), &vinfo, err, sizeof(err)) != SWCU_OK) die("vertex shader outside the subset", err);
+	for(uint32_t u = 0; u < vinfo.uniformCount && u < SWCU_MAX_UNIFORM_BUFFERS; u++)
+	{
+		const vk::PipelineLayout *layout = pre.getPipelineLayout();
+		const uint32_t set = vinfo.uniformSet[u], binding = vinfo.uniformBinding[u];
+		if(set >= layout->getDescriptorSetCount() || binding >= layout->getBindingCount(set)) die("swcu_draw", "the vertex shader's uniform block is not in the pipeline layout");
+		const VkDescriptorType type = layout->getDescriptorType(set, binding);
+		if(type != VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER && type != VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC) die("swcu_draw", "the vertex shader's uniform block is not bound as a uniform buffer");
+		const uint8_t *setData = args.data->descriptorSets[set];
+		if(!setData) die("swcu_draw", "unbound descriptor set");
+		const vk::BufferDescriptor *bd = (const vk::BufferDescriptor *)(setData + layout->getBindingOffset(set, binding));
+		uint32_t dynamic = 0;
+		if(type == VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER_DYNAMIC) dynamic = args.data->descriptorDynamicOffsets[layout->getDynamicOffsetIndex(set, binding)];
+		swcu_uniform_buffer &ub = d.uniformBuffer[d.uniformBufferCount++];
+		ub.set = set;
+		ub.binding = binding;
+		ub.data = bd->ptr ? (const uint8_t *)bd->ptr + dynamic : nullptr;
+		ub.bytes = (uint32_t)(bd->sizeInBytes > 0 ? bd->sizeInBytes : 0);
+	}
 	check(s.api.draw(s.ctx, &d), "swcu_draw");
 }
 

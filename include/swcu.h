@@ -41,6 +41,7 @@ extern "C" {
 
 #define SWCU_MAX_INPUTS 16         /* vertex input locations (reference: MAX_INTERFACE_COMPONENTS/4 = 32) */
 #define SWCU_MAX_SAMPLED_IMAGES 4  /* combined image samplers visible to the fragment shader */
+#define SWCU_MAX_UNIFORM_BUFFERS 4 /* uniform-buffer descriptors the vertex stage reads */
 #define SWCU_MIPMAP_LEVELS 15      /* sw::MIPMAP_LEVELS, src/Device/Config.hpp */
 #define SWCU_MAX_VARYING_COMPONENTS 16
 #define SWCU_MAX_GROUP 8           /* GPUs of one box that share a frame (swcu_group_*) */
@@ -122,6 +123,14 @@ typedef struct swcu_rect
 } swcu_rect;
 
 /* Flattened arguments + gathered state of sw::Renderer::draw (Renderer.cpp:183-490). */
+typedef struct swcu_uniform_buffer
+{
+	uint32_t set, binding;
+	const void *data; /* host pointer: BufferDescriptor::ptr (offset of the descriptor and, for a dynamic one, the dynamic offset applied) */
+	uint32_t bytes;   /* BufferDescriptor::sizeInBytes; words past it read 0 */
+	uint32_t reserved0;
+} swcu_uniform_buffer;
+
 typedef struct swcu_draw_desc
 {
 	uint32_t structSize; /* sizeof(swcu_draw_desc), ABI check */
@@ -189,8 +198,13 @@ typedef struct swcu_draw_desc
 
 	/* --- descriptors visible to the fragment shader */
 	uint32_t sampledImageCount;
-	uint32_t reserved0;
+	/* --- uniform buffers the vertex stage reads (VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER: the vk::BufferDescriptor { ptr, sizeInBytes } at
+	 *     the binding's offset in DrawData::descriptorSets[set], VkDescriptorSetLayout.cpp:574-600; what the shader's OpLoad through
+	 *     an access chain into the Block reads, SpirvShaderMemory.cpp).  HOST memory: swcu_draw reads the words the vertex program
+	 *     uses and folds them into the program like the push constants; nothing of it goes to the device. */
+	uint32_t uniformBufferCount;
 	swcu_sampled_image sampledImage[SWCU_MAX_SAMPLED_IMAGES];
+	swcu_uniform_buffer uniformBuffer[SWCU_MAX_UNIFORM_BUFFERS];
 } swcu_draw_desc;
 
 /* What the narrow SPIR-V translator extracted from one module (for tests and caching). */
@@ -199,6 +213,7 @@ typedef struct swcu_draw_desc
 #define SWCU_SRC_TEXEL 2 /* fragment only: value = component of the OpImageSampleImplicitLod result */
 #define SWCU_SRC_PUSH 3  /* vertex only: value = 32-bit word of the push-constant block (sw::DrawData::pushConstants, Renderer.hpp:110) */
 #define SWCU_SRC_TEMP 4  /* vertex only: value = index of the program step that computes it */
+#define SWCU_SRC_UNIFORM 5 /* vertex only: value = slot << 16 | 32-bit word of the uniform block `slot` (uniformSet / uniformBinding of the shader info) */
 /* The arithmetic a vertex shader does on its way from the inputs to gl_Position / the varyings (an MVP from push constants), lowered
  * to straight-line steps with the reference's rounding: MUL / ADD / SUB / NEG are single IEEE operations (SpirvShaderArithmetic.cpp),
  * FMA is Reactor's MulAdd — what OpMatrixTimesVector accumulates with (fused on every host with FMA, LLVMReactor.cpp:3082-3092). */
@@ -237,6 +252,8 @@ typedef struct swcu_shader_info
 	swcu_shader_op program[SWCU_MAX_PROGRAM];
 	uint32_t writesPointSize;        /* vertex: gl_PointSize is stored (VertexRoutine.cpp:641-650); read by point draws only */
 	swcu_shader_operand pointSize;
+	uint32_t uniformCount;           /* vertex: uniform blocks (Uniform storage class, Block-decorated) the program reads */
+	uint32_t uniformSet[SWCU_MAX_UNIFORM_BUFFERS], uniformBinding[SWCU_MAX_UNIFORM_BUFFERS];
 } swcu_shader_info;
 
 /* Counters for bench / tests. */

@@ -253,11 +253,11 @@ int main(int argc, char **argv)
 	// ---- per-draw objects ----
 	std::vector<DrawObjects> objs(hdr->numDraws);
 	CHECK(vkBeginCommandBuffer(cmd[2], &cbi));
-	VkDescriptorPoolSize psz{ VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, hdr->numDraws + 1 };
+	VkDescriptorPoolSize psz[2] = { { VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, hdr->numDraws + 1 }, { VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, hdr->numDraws + 1 } };
 	VkDescriptorPoolCreateInfo dpi{ VK_STRUCTURE_TYPE_DESCRIPTOR_POOL_CREATE_INFO };
 	dpi.maxSets = hdr->numDraws + 1;
-	dpi.poolSizeCount = 1;
-	dpi.pPoolSizes = &psz;
+	dpi.poolSizeCount = 2;
+	dpi.pPoolSizes = psz;
 	VkDescriptorPool dpool;
 	CHECK(vkCreateDescriptorPool(dev, &dpi, nullptr, &dpool));
 
@@ -279,6 +279,18 @@ int main(int argc, char **argv)
 			memcpy(p, blobPtr(d.instanceBlob), blobSize(d.instanceBlob));
 		}
 		VkDescriptorSetLayout dsl = VK_NULL_HANDLE;
+		// the bindings of descriptor set 0: the fragment shader's combined image sampler and / or the vertex shader's uniform buffer
+		std::vector<VkDescriptorSetLayoutBinding> lbs;
+		VkDescriptorImageInfo dii{};
+		VkDescriptorBufferInfo dbi{};
+		if(d.hasUbo)
+		{
+			VkBuffer ub;
+			mkBuffer(blobSize(d.uboBlob), VK_BUFFER_USAGE_UNIFORM_BUFFER_BIT, ub, p);
+			memcpy(p, blobPtr(d.uboBlob), blobSize(d.uboBlob));
+			dbi = { ub, 0, VK_WHOLE_SIZE };
+			lbs.push_back({ d.uboBinding, VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER, 1, VK_SHADER_STAGE_VERTEX_BIT, nullptr });
+		}
 		if(d.hasTexture)
 		{
 			VkBuffer sb;
@@ -324,24 +336,31 @@ int main(int argc, char **argv)
 			sci.maxLod = d.maxLod;
 			VkSampler smp;
 			CHECK(vkCreateSampler(dev, &sci, nullptr, &smp));
-			VkDescriptorSetLayoutBinding lb{ d.texBinding, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 1, VK_SHADER_STAGE_FRAGMENT_BIT, nullptr };
+			lbs.push_back({ d.texBinding, VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER, 1, VK_SHADER_STAGE_FRAGMENT_BIT, nullptr });
+			dii = { smp, tview, VK_IMAGE_LAYOUT_SHADER_READ_ONLY_OPTIMAL };
+		}
+		if(!lbs.empty())
+		{
 			VkDescriptorSetLayoutCreateInfo li{ VK_STRUCTURE_TYPE_DESCRIPTOR_SET_LAYOUT_CREATE_INFO };
-			li.bindingCount = 1;
-			li.pBindings = &lb;
+			li.bindingCount = (uint32_t)lbs.size();
+			li.pBindings = lbs.data();
 			CHECK(vkCreateDescriptorSetLayout(dev, &li, nullptr, &dsl));
 			VkDescriptorSetAllocateInfo dai{ VK_STRUCTURE_TYPE_DESCRIPTOR_SET_ALLOCATE_INFO };
 			dai.descriptorPool = dpool;
 			dai.descriptorSetCount = 1;
 			dai.pSetLayouts = &dsl;
 			CHECK(vkAllocateDescriptorSets(dev, &dai, &o.dset));
-			VkDescriptorImageInfo dii{ smp, tview, VK_IMAGE_LAYOUT_SHADER_READ_ONLY_OPTIMAL };
-			VkWriteDescriptorSet wd{ VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET };
-			wd.dstSet = o.dset;
-			wd.dstBinding = d.texBinding;
-			wd.descriptorCount = 1;
-			wd.descriptorType = VK_DESCRIPTOR_TYPE_COMBINED_IMAGE_SAMPLER;
-			wd.pImageInfo = &dii;
-			vkUpdateDescriptorSets(dev, 1, &wd, 0, nullptr);
+			for(const VkDescriptorSetLayoutBinding &lb : lbs)
+			{
+				VkWriteDescriptorSet wd{ VK_STRUCTURE_TYPE_WRITE_DESCRIPTOR_SET };
+				wd.dstSet = o.dset;
+				wd.dstBinding = lb.binding;
+				wd.descriptorCount = 1;
+				wd.descriptorType = lb.descriptorType;
+				if(lb.descriptorType == VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER) wd.pBufferInfo = &dbi;
+				else wd.pImageInfo = &dii;
+				vkUpdateDescriptorSets(dev, 1, &wd, 0, nullptr);
+			}
 		}
 		VkPipelineLayoutCreateInfo pli{ VK_STRUCTURE_TYPE_PIPELINE_LAYOUT_CREATE_INFO };
 		if(dsl) { pli.setLayoutCount = 1; pli.pSetLayouts = &dsl; }
@@ -459,7 +478,7 @@ int main(int argc, char **argv)
 			const SceneDraw &d = draws[di];
 			DrawObjects &o = objs[di];
 			vkCmdBindPipeline(c, VK_PIPELINE_BIND_POINT_GRAPHICS, o.pipeline[pass]);
-			if(o.dset) vkCmdBindDescriptorSets(c, VK_PIPELINE_BIND_POINT_GRAPHICS, o.layout, d.texSet, 1, &o.dset, 0, nullptr);
+			if(o.dset) vkCmdBindDescriptorSets(c, VK_PIPELINE_BIND_POINT_GRAPHICS, o.layout, d.hasTexture ? d.texSet : d.uboSet, 1, &o.dset, 0, nullptr);
 			if(d.pushConstantBytes) vkCmdPushConstants(c, o.layout, VK_SHADER_STAGE_VERTEX_BIT, 0, d.pushConstantBytes, d.pushConstants);
 			VkDeviceSize off = 0;
 			vkCmdBindVertexBuffers(c, 0, 1, &o.vb, &off);

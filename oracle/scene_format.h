@@ -12,7 +12,7 @@
 #include <stdint.h>
 
 #define SCENE_MAGIC 0x43535753u /* "SWSC" */
-#define SCENE_VERSION 6u
+#define SCENE_VERSION 7u
 #define SCENE_MAX_ATTRIBS 8
 
 #pragma pack(push, 4)
@@ -66,6 +66,8 @@ typedef struct SceneDraw
 	uint32_t instanceCount;     /* >= 1 */
 	uint32_t instanceBlob, instanceStride, numInstanceAttribs;
 	struct { uint32_t location, format, offset; } instanceAttrib[4];
+	/* a uniform buffer for the vertex stage (VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER at (uboSet, uboBinding)); set 0 only */
+	uint32_t hasUbo, uboBlob, uboSet, uboBinding;
 } SceneDraw;
 
 typedef struct SceneBlob { uint64_t offset, size; } SceneBlob;

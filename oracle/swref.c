@@ -187,6 +187,22 @@ static float operand(const Draw *dr, const swcu_shader_operand *op, float inputs
 		if(4 * op->value + 4 <= dr->d->pushConstantBytes) memcpy(&w, (const char *)dr->d->pushConstants + 4 * op->value, 4);
 		return as_float(w);
 	}
+	if(op->kind == SWCU_SRC_UNIFORM)
+	{
+		/* word of the uniform block behind the BufferDescriptor bound at the block's (set, binding): the Load through the access chain
+		 * into the Block (SpirvShaderMemory.cpp), the descriptor's ptr / sizeInBytes (VkDescriptorSetLayout.cpp:574-600) */
+		const uint32_t slot = op->value >> 16, wi = op->value & 0xFFFFu;
+		uint32_t w = 0;
+		if(slot < dr->vs->uniformCount)
+			for(uint32_t i = 0; i < dr->d->uniformBufferCount && i < SWCU_MAX_UNIFORM_BUFFERS; i++)
+			{
+				const swcu_uniform_buffer *u = &dr->d->uniformBuffer[i];
+				if(u->set != dr->vs->uniformSet[slot] || u->binding != dr->vs->uniformBinding[slot]) continue;
+				if(u->data && (size_t)4 * wi + 4 <= u->bytes) memcpy(&w, (const char *)u->data + 4 * wi, 4);
+				break;
+			}
+		return as_float(w);
+	}
 	return inputs[op->value >> 2][op->value & 3];
 }
 

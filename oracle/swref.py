@@ -70,6 +70,10 @@ def _push(word: int):
     return (capi.SRC_PUSH, word)
 
 
+def _ubo(slot: int, word: int):
+    return (capi.SRC_UNIFORM, (slot << 16) | word)
+
+
 def _temp(step: int):
     return (capi.SRC_TEMP, step)
 
@@ -94,14 +98,16 @@ class _Program:
     def fma(self, a, b, c):
         return self.op(capi.OP_FMA, a, b, c)
 
-    def mat4_times_vec4(self, first_word: int, v):
+    def mat4_times_vec4(self, first_word: int, v, elem=None):
         """OpMatrixTimesVector on a column-major mat4 at push-constant word `first_word` (SpirvShaderArithmetic.cpp:39-55):
-        row i = M[i,0] * v0, then MulAdd(M[i,j], vj, .) for j = 1..3"""
+        row i = M[i,0] * v0, then MulAdd(M[i,j], vj, .) for j = 1..3.  `elem(row, column)` names the operand that holds an element
+        when the matrix lives somewhere else (a uniform block, a row-major layout)."""
+        elem = elem or (lambda i, j: _push(first_word + 4 * j + i))
         out = []
         for i in range(4):
-            acc = self.mul(_push(first_word + i), v[0])
+            acc = self.mul(elem(i, 0), v[0])
             for j in range(1, 4):
-                acc = self.fma(_push(first_word + 4 * j + i), v[j], acc)
+                acc = self.fma(elem(i, j), v[j], acc)
             out.append(acc)
         return out
 
@@ -140,6 +146,18 @@ def _vs_mvp():
     p = _Program()
     pos = p.mat4_times_vec4(0, [_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)])
     return _vs(pos, {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2), 3: _inp(1, 3)}, p)
+
+
+def _vs_ubo():
+    # layout(set = 0, binding = 1) uniform UBO { mat4 model (ColMajor, offset 0); row_major mat4 viewProj (offset 64); vec4 tint (offset 128); } u;
+    # gl_Position = u.viewProj * (u.model * vec4(inPos, 1.0)); outColor = inColor * u.tint
+    p = _Program()
+    world = p.mat4_times_vec4(0, [_inp(0, 0), _inp(0, 1), _inp(0, 2), _const(1.0)], elem=lambda i, j: _ubo(0, 4 * j + i))
+    clip = p.mat4_times_vec4(0, world, elem=lambda i, j: _ubo(0, 16 + 4 * i + j))  # row-major: the rows lie MatrixStride apart
+    col = [p.mul(_inp(1, c), _ubo(0, 32 + c)) for c in range(4)]
+    s = _vs(clip, {c: col[c] for c in range(4)}, p)
+    s.uniformCount, s.uniformSet[0], s.uniformBinding[0] = 1, 0, 1
+    return s
 
 
 def _vs_inst():
@@ -196,6 +214,8 @@ SHADER_SPECS = {
     "vs_mvp_pos3_col4": _vs_mvp,
     # component-wise scale / offset / tint from the push-constant block
     "vs_xform_pos3_col4": _vs_xform,
+    # two matrices (one row-major) and a tint from a uniform buffer at (set 0, binding 1)
+    "vs_ubo_pos3_col4": _vs_ubo,
     # gl_Position = inPos; gl_PointSize = inSize (loc 2); outColor = inColor
     "vs_point_pos4_col4": lambda: _vs([_inp(0, 0), _inp(0, 1), _inp(0, 2), _inp(0, 3)],
                                       {0: _inp(1, 0), 1: _inp(1, 1), 2: _inp(1, 2), 3: _inp(1, 3)}, point_size=_inp(2, 0)),

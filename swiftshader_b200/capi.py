@@ -50,6 +50,13 @@ class Rect(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32)]
 
 
+MAX_UNIFORM_BUFFERS = 4
+
+
+class UniformBuffer(C.Structure):
+    _fields_ = [("set", C.c_uint32), ("binding", C.c_uint32), ("data", C.c_void_p), ("bytes", C.c_uint32), ("reserved0", C.c_uint32)]
+
+
 class DrawDesc(C.Structure):
     _fields_ = [
         ("structSize", C.c_uint32),
@@ -73,8 +80,9 @@ class DrawDesc(C.Structure):
         ("colorWriteMask", C.c_uint32), ("blendConstants", C.c_float * 4),
         ("color", Attachment), ("depth", Attachment), ("stencil", Attachment),
         ("pushConstants", C.c_void_p), ("pushConstantBytes", C.c_uint32), ("lineWidth", C.c_float),
-        ("sampledImageCount", C.c_uint32), ("reserved0", C.c_uint32),
+        ("sampledImageCount", C.c_uint32), ("uniformBufferCount", C.c_uint32),
         ("sampledImage", SampledImage * MAX_SAMPLED_IMAGES),
+        ("uniformBuffer", UniformBuffer * MAX_UNIFORM_BUFFERS),
     ]
 
 
@@ -82,7 +90,7 @@ class ShaderOperand(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("value", C.c_uint32)]
 
 
-SRC_INPUT, SRC_CONST, SRC_TEXEL, SRC_PUSH, SRC_TEMP = 0, 1, 2, 3, 4
+SRC_INPUT, SRC_CONST, SRC_TEXEL, SRC_PUSH, SRC_TEMP, SRC_UNIFORM = 0, 1, 2, 3, 4, 5
 OP_MUL, OP_ADD, OP_SUB, OP_FMA, OP_NEG = 0, 1, 2, 3, 4
 MAX_PROGRAM = 48
 
@@ -99,7 +107,8 @@ class ShaderInfo(C.Structure):
                 ("usesTexture", C.c_uint32), ("textureSet", C.c_uint32), ("textureBinding", C.c_uint32),
                 ("texCoord", ShaderOperand * 2),
                 ("programLength", C.c_uint32), ("program", ShaderOp * MAX_PROGRAM),
-                ("writesPointSize", C.c_uint32), ("pointSize", ShaderOperand)]
+                ("writesPointSize", C.c_uint32), ("pointSize", ShaderOperand),
+                ("uniformCount", C.c_uint32), ("uniformSet", C.c_uint32 * MAX_UNIFORM_BUFFERS), ("uniformBinding", C.c_uint32 * MAX_UNIFORM_BUFFERS)]
 
 
 class Stats(C.Structure):

@@ -105,6 +105,7 @@ struct swcu_ctx
 	size_t eventsUsed = 0;
 	int optTma = 1;
 	int optFastState = 1;
+	int optWriteOnly = 1;
 	void *encodeTiled = nullptr; // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda link dependency)
 	std::map<std::vector<uint64_t>, CUtensorMap> mapCache;
 };
@@ -624,6 +625,7 @@ extern "C" int swcu_set_option(swcu_ctx *ctx, const char *name, int value)
 	else if(!strcmp(name, "pin_host")) ctx->optPinHost = value;
 	else if(!strcmp(name, "tma")) ctx->optTma = value;
 	else if(!strcmp(name, "fast_state")) ctx->optFastState = value;
+	else if(!strcmp(name, "write_only")) ctx->optWriteOnly = value;
 	else if(!strcmp(name, "pipeline")) ctx->optPipeline = value;
 	else if(!strcmp(name, "big_pair_budget")) ctx->optBigPairBudget = (size_t)std::max(value, 0);
 	else if(!strcmp(name, "copy_streams"))
@@ -814,11 +816,30 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 		if(4 * w + 4 <= desc->pushConstantBytes) memcpy(&v, (const unsigned char *)desc->pushConstants + 4 * w, 4);
 		return v;
 	};
+	// a 32-bit word of uniform block `slot` of the vertex shader: read from the host memory behind the descriptor the draw binds at
+	// the block's (set, binding) — BufferDescriptor::ptr / sizeInBytes; words past the end read 0 (robust buffer access)
+	if(desc->uniformBufferCount > SWCU_MAX_UNIFORM_BUFFERS) return fail(ctx, SWCU_E_INVALID, "more than %d uniform buffers", SWCU_MAX_UNIFORM_BUFFERS);
+	int uboErr = SWCU_OK;
+	auto uniform_word = [&](uint32_t value) -> uint32_t {
+		const uint32_t slot = value >> 16, w = value & 0xFFFFu;
+		if(slot >= vs.uniformCount) { uboErr = fail(ctx, SWCU_E_INVALID, "vertex program reads uniform block %u of %u", slot, vs.uniformCount); return 0; }
+		for(uint32_t i = 0; i < desc->uniformBufferCount; i++)
+		{
+			const swcu_uniform_buffer &u = desc->uniformBuffer[i];
+			if(u.set != vs.uniformSet[slot] || u.binding != vs.uniformBinding[slot]) continue;
+			uint32_t v = 0;
+			if(u.data && (size_t)4 * w + 4 <= u.bytes) memcpy(&v, (const unsigned char *)u.data + 4 * w, 4);
+			return v;
+		}
+		uboErr = fail(ctx, SWCU_E_INVALID, "no uniform buffer bound at set %u, binding %u", vs.uniformSet[slot], vs.uniformBinding[slot]);
+		return 0;
+	};
 	auto vsrc = [&](const swcu_shader_operand &o) -> KVSrc {
 		KVSrc k;
 		k.ptr = nullptr; k.stride = 0; k.limit = 0xFFFFFFFFu; k.constant = 0.0f; k.pad = 0;
 		if(o.kind == SWCU_SRC_CONST) { memcpy(&k.constant, &o.value, 4); return k; }
 		if(o.kind == SWCU_SRC_PUSH) { const uint32_t v = push_word(o.value); memcpy(&k.constant, &v, 4); return k; }
+		if(o.kind == SWCU_SRC_UNIFORM) { const uint32_t v = uniform_word(o.value); memcpy(&k.constant, &v, 4); return k; }
 		if(o.kind == SWCU_SRC_TEMP) return k; // (the caller routes the step's result: posTemp / slotTemp)
 		const uint32_t l = o.value >> 2, c = o.value & 3;
 		const swcu_vertex_input &in = desc->input[l];
@@ -858,6 +879,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 				const swcu_shader_operand &o = *src[k];
 				if(o.kind == SWCU_SRC_CONST) *dst[k] = { VK_CONST, o.value };
 				else if(o.kind == SWCU_SRC_PUSH) *dst[k] = { VK_CONST, push_word(o.value) };
+				else if(o.kind == SWCU_SRC_UNIFORM) *dst[k] = { VK_CONST, uniform_word(o.value) };
 				else if(o.kind == SWCU_SRC_TEMP)
 				{
 					if(o.value >= i) return fail(ctx, SWCU_E_INVALID, "vertex program step %u reads a later step", i);
@@ -1048,6 +1070,7 @@ static int build_const(swcu_ctx *ctx, const swcu_draw_desc *desc, DrawConst &d)
 	d.planeOffset = swcu_plane_offset(d.ms);
 	d.triStride = swcu_tri_stride(d.nslots, d.ms, d.depthTestActive != 0);
 	if(vsrcErr) return vsrcErr;
+	if(uboErr) return uboErr;
 	return SWCU_OK;
 }
 
@@ -1345,6 +1368,8 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		if(ok && d.stencilActive) ok = get_tensor_map(ctx, &maps.stencil, d.stencilBuf, d.stencilPitchB, d.stencilSliceB, d.fbWidth, d.fbHeight, d.ms, 1);
 		d.useTma = ok ? 1u : 0u;
 	}
+	// No attachment is read: the region warps store the colour of a fragment straight into the framebuffer (no staging, no write-back)
+	d.writeOnly = (ctx->optWriteOnly && d.blendClass == BL_OFF && !d.depthTestActive && d.shaderClass != SH_GENERIC && fast_state(ctx, d)) ? 1u : 0u;
 	if(!nothingToDraw) { if(d.ms == 4) launch_tile<4>(ctx, d, maps, tileGrid); else launch_tile<1>(ctx, d, maps, tileGrid); }
 	CU(cudaGetLastError());
 	if(grouped)

@@ -38,7 +38,7 @@ enum Op : uint32_t
 enum { DecBlock = 2, DecRowMajor = 4, DecColMajor = 5, DecMatrixStride = 7, DecBuiltIn = 11, DecNoPerspective = 13, DecFlat = 14, DecLocation = 30, DecComponent = 31, DecBinding = 33,
 	   DecDescriptorSet = 34, DecOffset = 35, DecRelaxedPrecision = 0 };
 enum { BuiltInPosition = 0, BuiltInPointSize = 1, BuiltInClipDistance = 3, BuiltInCullDistance = 4 };
-enum { SCUniformConstant = 0, SCInput = 1, SCOutput = 3, SCPushConstant = 9 };
+enum { SCUniformConstant = 0, SCInput = 1, SCUniform = 2, SCOutput = 3, SCPushConstant = 9 };
 
 struct Type
 {
@@ -69,6 +69,7 @@ struct Value
 	uint32_t var = 0;
 	uint32_t pcType = 0, pcOffset = 0, pcStride = 0; // pointer into the push-constant block: pointee type, byte offset, stride between
 	bool pcRowMajor = false;                         //   the columns (ColMajor) / rows (RowMajor) of the matrix it points into
+	int ubo = -1;       // the block is uniform block `ubo` of the module (swcu_shader_info::uniformSet / uniformBinding), not the push constants
 	int member = -1;    // struct member index (gl_PerVertex)
 	int component = -1; // vector component selected by an access chain
 	uint32_t ival = 0;
@@ -257,7 +258,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			NEED(3); ID(a[0]); ID(a[1]);
 			if(na > 3) return fail("variable initialisers unsupported");
 			if(types[a[0]].kind != Type::Pointer) return fail("variable type is not a pointer");
-			if(a[2] != SCInput && a[2] != SCOutput && a[2] != SCUniformConstant && a[2] != SCPushConstant) return fail("storage class %u outside the subset", a[2]);
+			if(a[2] != SCInput && a[2] != SCOutput && a[2] != SCUniformConstant && a[2] != SCPushConstant && a[2] != SCUniform) return fail("storage class %u outside the subset", a[2]);
 			varType[a[1]] = a[0];
 			Value &v = values[a[1]];
 			v.kind = Value::Pointer; v.var = a[1];
@@ -267,6 +268,22 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 				if(model != 0) return fail("push constants are only supported in the vertex stage");
 				if(types[types[a[0]].elem].kind != Type::Struct) return fail("push-constant variable must be a Block struct");
 				v.pcType = types[a[0]].elem;
+			}
+			else if(a[2] == SCUniform)
+			{
+				// a uniform buffer (VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER): a Block struct of float scalars / vectors / matrices behind the
+				// BufferDescriptor of (DescriptorSet, Binding); addressed like the push-constant block
+				if(model != 0) return fail("uniform buffers are only supported in the vertex stage");
+				const uint32_t st = types[a[0]].elem;
+				if(types[st].kind != Type::Struct || !decos[st].block) return fail("uniform variable must be a Block struct");
+				const Deco &vd = decos[a[1]];
+				if(vd.set < 0 || vd.binding < 0) return fail("uniform buffer without DescriptorSet/Binding");
+				if(out->uniformCount >= SWCU_MAX_UNIFORM_BUFFERS) return fail("more than %d uniform buffers", SWCU_MAX_UNIFORM_BUFFERS);
+				v.ubo = (int)out->uniformCount;
+				out->uniformSet[out->uniformCount] = (uint32_t)vd.set;
+				out->uniformBinding[out->uniformCount] = (uint32_t)vd.binding;
+				out->uniformCount++;
+				v.pcType = st;
 			}
 			break;
 		}
@@ -361,9 +378,14 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 				// scalar / vector / matrix of the push-constant block: one SWCU_SRC_PUSH operand per 32-bit word
 				const Type &t = types[p.pcType];
 				Value v; v.kind = Value::Vec;
-				auto word = [&](uint32_t byteOffset) -> swcu_shader_operand { return { SWCU_SRC_PUSH, byteOffset / 4 }; };
+				const int ubo = p.ubo;
+				auto word = [&](uint32_t byteOffset) -> swcu_shader_operand {
+					if(ubo >= 0) return { SWCU_SRC_UNIFORM, ((uint32_t)ubo << 16) | (byteOffset / 4) };
+					return { SWCU_SRC_PUSH, byteOffset / 4 };
+				};
 				bool bad = false;
-				auto check = [&](uint32_t byteOffset) { if((byteOffset & 3) || byteOffset / 4 >= SWCU_MAX_PUSH_WORDS) bad = true; return byteOffset; };
+				// (a uniform block: words below 64 KiB, maxUniformBufferRange of the reference is 65536 bytes)
+				auto check = [&](uint32_t byteOffset) { if((byteOffset & 3) || byteOffset / 4 >= (ubo >= 0 ? 16384u : (uint32_t)SWCU_MAX_PUSH_WORDS)) bad = true; return byteOffset; };
 				if(t.kind == Type::Float) { v.n = 1; v.c[0] = word(check(p.pcOffset)); }
 				else if(t.kind == Type::Vector)
 				{
@@ -379,7 +401,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 							v.c[j * rows + i] = word(check(p.pcOffset + (p.pcRowMajor ? p.pcStride * i + 4 * j : p.pcStride * j + 4 * i)));
 				}
 				else return fail("load of an unsupported push-constant type");
-				if(bad) return fail("push-constant access beyond %d bytes or unaligned", 4 * SWCU_MAX_PUSH_WORDS);
+				if(bad) return fail("%s access beyond %d bytes or unaligned", ubo >= 0 ? "uniform-buffer" : "push-constant", ubo >= 0 ? 65536 : 4 * SWCU_MAX_PUSH_WORDS);
 				values[a[1]] = v;
 				break;
 			}

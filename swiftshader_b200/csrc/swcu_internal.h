@@ -253,6 +253,7 @@ struct DrawConst
 	uint32_t direct;           // 1: no binning, every region warp walks all triangles
 	uint32_t blendClass;       // BL_*
 	uint32_t useTma;           // attachments satisfy the tensor-map alignment rules: stage the tile with TMA
+	uint32_t writeOnly;        // fast state, no blending, no depth / stencil: no attachment is read, the colour goes straight to the framebuffer
 };
 
 // TriRecord layout (triStride bytes, 16-byte aligned):

@@ -135,6 +135,8 @@ class Draw:
     depthBounds: Optional[tuple] = None  # (min, max) enables the depth bounds test
     texture: Optional[Texture] = None
     pushConstants: Optional[np.ndarray] = None  # float32 / uint32 words pushed for the vertex stage (<= 32)
+    # uniform buffer the vertex stage reads: (set, binding, float32 / uint32 words) — VK_DESCRIPTOR_TYPE_UNIFORM_BUFFER
+    uniformBuffer: Optional[tuple] = None
     lineWidth: float = 1.0
     depthClamp: bool = False  # depthClampEnable: no near / far clipping, fragment depth clamped to the viewport's depth range
     # instancing (CmdDrawBase::draw, VkCommandBuffer.cpp:987-1010): one Renderer::draw per instance, the streams of the instance-rate
@@ -257,6 +259,12 @@ class Scene:
             pc = np.ascontiguousarray(draw.pushConstants).view(np.uint32).ravel().copy()
             keep.append(pc)
             d.pushConstants, d.pushConstantBytes = pc.ctypes.data, pc.nbytes
+        if draw.uniformBuffer is not None:
+            (uset, ubinding, uwords) = draw.uniformBuffer
+            ub = np.ascontiguousarray(uwords).view(np.uint32).ravel().copy()
+            keep.append(ub)  # host memory: swcu_draw folds the words the vertex program reads (no shadow)
+            d.uniformBufferCount = 1
+            d.uniformBuffer[0] = capi.UniformBuffer(uset, ubinding, ub.ctypes.data, ub.nbytes, 0)
         for (loc, comps, off) in draw.attribs:
             vi = d.input[loc]
             vi.buffer = verts.ctypes.data + off * 4
@@ -390,8 +398,13 @@ class Scene:
                         r += struct.pack("<III", 0, 0, 0)
             else:
                 r += struct.pack("<IIII", 1, 0, 0, 0) + struct.pack("<III", 0, 0, 0) * 4
+            if dr.uniformBuffer is not None:
+                (uset, ubinding, uwords) = dr.uniformBuffer
+                r += struct.pack("<IIII", 1, blob(np.ascontiguousarray(uwords).view(np.uint32).ravel()), uset, ubinding)
+            else:
+                r += struct.pack("<IIII", 0, 0, 0, 0)
             recs.append(r)
-        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 6, self.width, self.height, self.samples, self.colorFormat,
+        hdr = struct.pack("<IIIIIIII4ffIII", 0x43535753, 7, self.width, self.height, self.samples, self.colorFormat,
                           (2 if self.depthFormat == FMT_D16_UNORM else 1) if self.hasDepth else 0, int(self.hasStencil), *self.clearColor, self.clearDepth, self.clearStencil,
                           len(recs), len(blobs))
         off = len(hdr) + sum(len(r) for r in recs) + 16 * len(blobs)

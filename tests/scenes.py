@@ -709,6 +709,44 @@ def mvp(seed: int) -> Scene:
     return Scene(2 * CELL, 2 * CELL, [d], samples=4 if seed % 5 == 4 else 1, hasDepth=True, clearColor=(0.1, 0.1, 0.1, 1.0))
 
 
+def ubo(seed: int) -> Scene:
+    """A transform in the vertex stage from a UNIFORM BUFFER (set 0, binding 1): a column-major model matrix, a row-major
+    view-projection matrix (two OpMatrixTimesVector, 32 MulAdd steps) and a tint; 1x and 4x, depth-tested, culled, blended, part of
+    the patch across the frustum planes; with a texture in the fragment stage the set holds both descriptors."""
+    rng = np.random.default_rng(27000 + seed)
+    g = 5 + seed % 4
+    u, v = np.meshgrid(np.linspace(-1, 1, g + 1), np.linspace(-1, 1, g + 1))
+    z = 0.3 * np.cos(2.0 * u - seed) * np.sin(2.5 * v + 0.5 * seed)
+    textured = seed % 4 == 2
+    verts = np.zeros(((g + 1) * (g + 1), 7), dtype=np.float32)
+    verts[:, 0], verts[:, 1], verts[:, 2] = u.ravel(), v.ravel(), z.ravel()
+    verts[:, 3:7] = rng.uniform(0, 1, (len(verts), 4))
+    idx = []
+    for j in range(g):
+        for i in range(g):
+            a = j * (g + 1) + i
+            idx += [a, a + 1, a + g + 1, a + 1, a + g + 2, a + g + 1]
+    idx = np.array(idx, dtype=np.uint32 if seed % 2 else np.uint16)
+    model = np.eye(4)
+    model[:3, :3] *= rng.uniform(0.45, 0.95, 3)
+    model[:3, 3] = rng.uniform(-0.2, 0.2, 3)
+    vp = _perspective(rng)
+    if seed % 3 == 1:
+        vp = vp * np.float32(rng.uniform(0.9, 1.8))  # part of the patch leaves the frustum
+    words = np.concatenate([np.ascontiguousarray(model.astype(np.float32).T).ravel(),  # column-major
+                            np.ascontiguousarray(vp.astype(np.float32)).ravel(),           # row-major
+                            rng.uniform(0.3, 1.0, 4).astype(np.float32),
+                            np.zeros(seed % 3 * 4, dtype=np.float32)])                      # (a buffer longer than the block)
+    kw = {}
+    fs = "fs_col4"
+    if textured:
+        fs = "fs_tex_col4"
+        kw["texture"] = Texture(_rand_tex(rng, 32, 32, 4), maxLod=3.0)
+    d = Draw(verts, P3C4, "vs_ubo_pos3_col4", fs, indices=idx, depthTest=True, depthWrite=True, uniformBuffer=(0, 1, words),
+             cullMode=[CULL_NONE, CULL_FRONT, CULL_NONE][seed % 3], blend=(seed % 4 == 3), **kw)
+    return Scene(2 * CELL, 2 * CELL, [d], samples=4 if seed % 5 == 3 else 1, hasDepth=True, clearColor=(0.05, 0.1, 0.15, 1.0))
+
+
 def lines(seed: int) -> Scene:
     """Line lists and strips (DrawCall::setupLine, Renderer.cpp:920-1000: the rectangle of the default rasterization mode), with
     perspective, end points outside the frustum, u16 indices, 1x and 4x, with and without a depth test."""
@@ -824,6 +862,7 @@ FAMILIES = {
     "zclamp": (zclamp, 8),
     "msaafmt": (msaafmt, 12),
     "instanced": (instanced, 8),
+    "ubo": (ubo, 10),
 }
 
 

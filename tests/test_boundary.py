@@ -44,7 +44,8 @@ def _dump(i):
                 output=[(o.kind, o.value) for o in i.output], inputMask=i.inputMask, flat=i.flatMask, nopersp=i.noPerspectiveMask,
                 tex=(i.usesTexture, i.textureSet, i.textureBinding), tc=[(o.kind, o.value) for o in i.texCoord],
                 program=[(s.op, (s.a.kind, s.a.value), (s.b.kind, s.b.value), (s.c.kind, s.c.value)) for s in i.program[:i.programLength]],
-                pointSize=(i.writesPointSize, i.pointSize.kind, i.pointSize.value))
+                pointSize=(i.writesPointSize, i.pointSize.kind, i.pointSize.value),
+                uniforms=[(i.uniformSet[k], i.uniformBinding[k]) for k in range(i.uniformCount)])
 
 
 @pytest.mark.parametrize("name", sorted(swref.SHADER_SPECS))
@@ -66,6 +67,21 @@ def test_translator_vertex_arithmetic_limits():
     with pytest.raises(capi.SwcuError) as e:
         capi.translate_shader(spirv.assemble(src))
     assert e.value.code == capi.E_UNSUPPORTED and "push-constant access beyond" in str(e.value)
+
+
+def test_translator_uniform_buffer_limits():
+    """a uniform block needs DescriptorSet / Binding and the Block decoration; words past 64 KiB are outside the subset"""
+    src = spirv.shader_source("vs_ubo_pos3_col4")
+    info = capi.translate_shader(spirv.assemble(src))
+    assert info.uniformCount == 1 and (info.uniformSet[0], info.uniformBinding[0]) == (0, 1)
+    assert info.program[16].a.kind == capi.SRC_UNIFORM and info.program[16].a.value == 16  # row-major viewProj: element (0, 0) at byte 64
+    assert info.program[17].a.value == 17 and info.program[20].a.value == 20              # (0, 1) 4 bytes on, (1, 0) one MatrixStride on
+    for bad, what in ((src.replace("OpDecorate %u Binding 1\n", ""), "without DescriptorSet/Binding"),
+                      (src.replace("OpDecorate %UBO Block\n", ""), "must be a Block struct"),
+                      (src.replace("OpMemberDecorate %UBO 2 Offset 128", "OpMemberDecorate %UBO 2 Offset 65536"), "uniform-buffer access beyond")):
+        with pytest.raises(capi.SwcuError) as e:
+            capi.translate_shader(spirv.assemble(bad))
+        assert e.value.code == capi.E_UNSUPPORTED and what in str(e.value)
 
 
 FS_HEAD = """OpCapability Shader

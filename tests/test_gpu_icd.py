@@ -29,7 +29,9 @@ NAMES = ["benchmark_0_720p", "benchmark_1_720p", "benchmark_2_720p", "benchmark_
          # depthClampEnable; 4x MSAA on the formats whose resolve is the generic blit
          "zclamp_1", "zclamp_3", "msaafmt_0", "msaafmt_1", "msaafmt_2", "msaafmt_3", "msaafmt_5",
          # instanced draws: the reference's own loop over the instances (CmdDrawBase::draw) calls the CUDA path once per instance
-         "instanced_0", "instanced_1", "instanced_3"]
+         "instanced_0", "instanced_1", "instanced_3",
+         # a transform from a uniform buffer: the shim hands over the vk::BufferDescriptor of the vertex shader's block (with a texture: both descriptors of the set)
+         "ubo_0", "ubo_1", "ubo_2", "ubo_3"]
 
 
 def _sha(a):
