@@ -219,6 +219,25 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
         full = torch.as_tensor(_DevArr(dev.device_ptr(final_imgs[0]), H * pitch), device=dev_s)
         dev.set_option("copy_streams", 0)  # the all-gather writes the frame on the caller's stream, unseen by the library
 
+    # Peer delivery runs on the library's hand-over stream (SWCU_HANDOVER=0: on the main stream, between the frames): a rank resolves /
+    # copies its band into a LOCAL 1x band buffer (two of them, used in turn) and goes on with the next frame; the wait for the ring
+    # slot, the copy of the band into rank 0's frame over NVLink and the signal follow on the second stream.  Rank 0 likewise waits
+    # for the other ranks' bands (and downloads / releases the frame) beside its next frame.
+    handover = pg is not None and os.environ.get("SWCU_HANDOVER", "1") != "0"
+    local_atts = []
+    if handover and rank != 0:
+        for _ in range(2):
+            lb = np.zeros((band[1] - band[0], W, 4), dtype=np.uint8)
+            dev.register(lb, upload=False)
+            finals.append(lb)  # (kept alive)
+            local_atts.append(capi.Attachment(lb.ctypes.data, sc.colorFormat, pitch, 0, W, band[1] - band[0], 0))
+
+    def side_join():
+        """The main stream catches up with the hand-over stream (before a time stamp that is to cover whole frames)."""
+        if handover:
+            for k_ in range(2):
+                dev.check(dev.lib.swcu_side_wait(dev.ctx, k_))
+
     state = {"i": 0}
 
     def step(present=None, descs=None):
@@ -228,6 +247,33 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
         for d_ in (descs if descs is not None else frame.descs):
             dev.draw(d_)
         k = i % len(final_imgs)
+        if pg is not None and handover:
+            k2 = i & 1
+            if rank != 0:
+                dev.check(dev.lib.swcu_side_wait(dev.ctx, k2))  # the delivery of frame i - 2 has read this band buffer
+                if sc.samples > 1:
+                    dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(local_atts[k2])))
+                else:
+                    dev.check(dev.lib.swcu_copy_image(dev.ctx, C.byref(src_b), C.byref(local_atts[k2])))
+                dev.check(dev.lib.swcu_side_begin(dev.ctx))
+                pg.begin_frame()  # the frame that was in this ring slot must have been consumed
+                dev.check(dev.lib.swcu_copy_image(dev.ctx, C.byref(local_atts[k2]), C.byref(pg.band_destination(sc.colorFormat, W))))
+                pg.band_done()    # announce the band
+                dev.check(dev.lib.swcu_side_end(dev.ctx, k2))
+            else:
+                pg.begin_frame()
+                dst = final_atts[pg.slot]
+                if sc.samples > 1:
+                    dev.check(dev.lib.swcu_resolve(dev.ctx, C.byref(src_b), sc.samples, C.byref(dst)))
+                else:
+                    dev.check(dev.lib.swcu_copy_image(dev.ctx, C.byref(src_b), C.byref(dst)))
+                dev.check(dev.lib.swcu_side_begin(dev.ctx))
+                pg.band_done()    # the hand-over stream waits for the other ranks' bands
+                if present is not None:
+                    present(final_imgs[pg.slot])
+                pg.frame_consumed()
+                dev.check(dev.lib.swcu_side_end(dev.ctx, k2))
+            return
         if pg is not None:
             pg.begin_frame()  # (ranks > 0: the frame that was in this slot must have been consumed)
             dst = pg.band_destination(sc.colorFormat, W) if rank != 0 else final_atts[pg.slot]
@@ -281,9 +327,14 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
         barrier()
         torch.cuda.synchronize()
         marks[0].record(stream)
+        t_host0 = time.perf_counter()
         for i in range(steps):
             step()
+            if i == steps - 1:
+                side_join()  # the last time stamp covers the delivery of every frame
             marks[i + 1].record(stream)
+        # what the host needs to ENQUEUE a frame (the calls are asynchronous): a frame cannot be faster than this
+        out["host_enqueue_ms_step"] = (time.perf_counter() - t_host0) * 1e3 / steps
         torch.cuda.synchronize()
         barrier()
         ms_total = marks[0].elapsed_time(marks[-1])
@@ -309,6 +360,7 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
             e0.record(stream)
             for _ in range(n_s):
                 step()
+            side_join()
             e1.record(stream)
             torch.cuda.synchronize()
             barrier()
@@ -317,6 +369,21 @@ def run_workload(name: str, steps: int, warmup: int, rank: int, N: int, local_ra
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ck = sclk.stop() if rank == 0 else None
             out["sustained"] = {"ms_per_step": float(t.item()) / n_s, "steps": n_s, "seconds": float(t.item()) * 1e-3, "clocks": ck}
+
+        # ---- diagnostics (SWCU_TIMELINE=<frames>): where every kernel of a few pipelined frames really ran, per rank, written to
+        #      gpurun_out/timeline_<workload>_n<N>_r<rank>.json (times in ms since the first kernel of the rank's timeline) ----
+        tl_frames = int(os.environ.get("SWCU_TIMELINE", "0"))
+        if tl_frames > 0:
+            barrier()
+            dev.set_profiling(2)
+            for _ in range(tl_frames):
+                step()
+            tl = dev.timeline()
+            dev.set_profiling(0)
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", f"timeline_{name}_n{N}_r{rank}.json"), "w") as f:
+                json.dump(tl, f)
+            barrier()
 
         # ---- end to end through the C-ABI with HOST buffers: H2D of the step's inputs and D2H of the frame inside the timed region.
         #      A render loop with several frames in flight, bounded by a fence per frame (a Vulkan application's per-frame vk::Fence):
@@ -455,7 +522,7 @@ def workload_line(name: str, r: dict, N: int, steps: int, warmup: int) -> dict:
         pass
     line = {
         "value": wl.covered_pixels / (ms_step * 1e-3) / 1e9, "unit": "Gpixels/s", "ms_per_step": ms_step, "ms_per_step_spread": r["frame_spread"],
-        "mtris_per_s": wl.triangles / (ms_step * 1e-3) / 1e6,
+        "mtris_per_s": wl.triangles / (ms_step * 1e-3) / 1e6, "host_enqueue_ms_per_step": r.get("host_enqueue_ms_step"),
         "frame_hash_ok": r.get("frame_hash_ok"),
         "config": {"workload": wl.name, "description": wl.description, "bands": N, "band_rows": r["band_rows"],
                    "l2": "inputs larger than L2 (framebuffer + mesh + per-triangle records > 126 MB)" if wl.algorithmic_bytes > 200e6 else "working set fits L2; steady-state frames",

@@ -318,6 +318,16 @@ int swcu_copy_image(swcu_ctx *ctx, const swcu_attachment *src, const swcu_attach
 int swcu_signal(swcu_ctx *ctx, void *flag, uint32_t value);
 /* the stream waits until flags[first .. first+count) >= value (wrap-around compare), count <= 64 */
 int swcu_wait_flags(swcu_ctx *ctx, const void *flags, uint32_t first, uint32_t count, uint32_t value);
+/* The hand-over stream: between swcu_side_begin and swcu_side_end the calls that pass a finished frame on — swcu_wait_flags,
+ * swcu_copy_image, swcu_signal, swcu_mem_download — are issued on a second stream that has waited for everything issued before
+ * swcu_side_begin; the main stream goes on with the next frame's draws meanwhile (the reference's counterpart: presenting a frame is
+ * not part of the render loop either — vkQueuePresentKHR waits on the frame's semaphore, the next submission does not wait for it).
+ * swcu_side_end(slot) marks the end of that work; swcu_side_wait(slot) makes the MAIN stream wait for the mark of `slot` — to be
+ * called before something the hand-over read is overwritten (a band buffer of a two-deep ring: slot = frame & 1). */
+#define SWCU_SIDE_SLOTS 4
+int swcu_side_begin(swcu_ctx *ctx);
+int swcu_side_end(swcu_ctx *ctx, uint32_t slot);
+int swcu_side_wait(swcu_ctx *ctx, uint32_t slot);
 
 /* ---- groups: the GPUs of one box render ONE frame — the setup of every draw is sharded by triangle range, the pixels by screen band ----
  * Without a group, a rank that renders a band (renderArea = band) still fetches and projects every triangle of the draw.  In a group
@@ -366,7 +376,10 @@ int swcu_get_stats(swcu_ctx *ctx, swcu_stats *out);
 int swcu_reset_stats(swcu_ctx *ctx);
 /* Per-kernel device time of the LAST swcu_draw when profiling is on (events around every launch).
  * names/ms arrays of capacity n; returns number of kernels written. */
-int swcu_set_profiling(swcu_ctx *ctx, int enable);
+int swcu_set_profiling(swcu_ctx *ctx, int enable); /* 1: per-kernel times of the last draw (the draw runs on one stream); 2: timeline (below) */
+/* Diagnostics: begin / end (ms since the first one) of every kernel of the library issued since swcu_set_profiling(ctx, 2), measured by
+ * events on the streams the kernels really run on (the draws stay pipelined); returns the count, at most n, and starts a new timeline. */
+int swcu_timeline(swcu_ctx *ctx, const char **names, float *begin_ms, float *end_ms, int n);
 int swcu_last_draw_kernels(swcu_ctx *ctx, const char **names, float *ms, int n);
 /* Tuning knob for tests: force the binned path even for tiny draws (default: direct mode below a threshold). */
 int swcu_set_option(swcu_ctx *ctx, const char *name, int value);

@@ -126,7 +126,7 @@ EXPORTS = [
     "swcu_mem_register", "swcu_mem_register_device", "swcu_mem_unregister", "swcu_mem_upload", "swcu_mem_download", "swcu_mem_device_ptr",
     "swcu_draw", "swcu_sync", "swcu_clear", "swcu_resolve", "swcu_shader_translate",
     "swcu_set_stream", "swcu_timer_begin", "swcu_timer_end", "swcu_get_stats", "swcu_reset_stats",
-    "swcu_set_profiling", "swcu_last_draw_kernels", "swcu_set_option", "swcu_version",
+    "swcu_set_profiling", "swcu_last_draw_kernels", "swcu_timeline", "swcu_side_begin", "swcu_side_end", "swcu_side_wait", "swcu_set_option", "swcu_version",
     "swcu_ipc_export", "swcu_ipc_open", "swcu_ipc_close", "swcu_copy_image", "swcu_signal", "swcu_wait_flags",
     "swcu_fence_signal", "swcu_fence_wait",
     "swcu_group_reserve", "swcu_group_attach", "swcu_group_detach", "swcu_mem_acquire", "swcu_mem_release", "swcu_mem_acquire_on", "swcu_mem_release_on",
@@ -173,12 +173,16 @@ def lib() -> C.CDLL:
     L.swcu_set_profiling.argtypes = [vp, i32]
     L.swcu_last_draw_kernels.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), i32]
     L.swcu_set_option.argtypes = [vp, C.c_char_p, i32]
+    L.swcu_timeline.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_float), i32]
     L.swcu_ipc_export.argtypes = [vp, vp, vp, C.POINTER(C.c_uint64)]
     L.swcu_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
     L.swcu_ipc_close.argtypes = [vp, vp]
     L.swcu_copy_image.argtypes = [vp, C.POINTER(Attachment), C.POINTER(Attachment)]
     L.swcu_signal.argtypes = [vp, vp, u32]
     L.swcu_wait_flags.argtypes = [vp, vp, u32, u32, u32]
+    L.swcu_side_begin.argtypes = [vp]
+    L.swcu_side_end.argtypes = [vp, u32]
+    L.swcu_side_wait.argtypes = [vp, u32]
     L.swcu_fence_signal.argtypes = [vp, u32]
     L.swcu_fence_wait.argtypes = [vp, u32]
     L.swcu_group_reserve.argtypes = [vp, C.POINTER(GroupDesc), vp]

@@ -65,12 +65,29 @@ struct swcu_ctx
 		bool countersPending = false;
 	} set[SWCU_SETS];
 	int cur = 0;
-	cudaStream_t setupStream = nullptr;
+	// The setup streams.  A lone context uses [0] for every pipelined draw.  A group member uses one PER SET: its chain of a draw
+	// (set-up -> group barrier -> scan -> fill) is a string of short, latency-bound launches that takes longer than the tile
+	// kernel of a band, so on one stream the chains themselves would set the frame rate; on three streams the set-up of draw i+1
+	// starts as soon as the barrier of draw i has been passed (evBarrier) and runs beside the scan / fill of draw i.
+	cudaStream_t setupStream[SWCU_SETS] = {};
+	// The hand-over stream (swcu_side_begin / _end / _wait): what follows a frame's last kernel on its way to whoever presents it —
+	// waiting for the flags of a ring slot, the copy of a band into a peer's frame over NVLink, the signal, the download — runs
+	// beside the next frame's kernels instead of between them.
+	cudaStream_t sideStream = nullptr;
+	bool sideActive = false;
+	cudaEvent_t evSideBegin = nullptr;
+	cudaEvent_t sideDone[SWCU_SIDE_SLOTS] = {};
+	bool sideDoneValid[SWCU_SIDE_SLOTS] = {};
+	cudaStream_t handover() const { return sideActive ? sideStream : stream; } // where hand-over calls are issued
+	cudaEvent_t evBarrier = nullptr;   // group: recorded behind the k_xbarrier of the last grouped draw
+	bool evBarrierValid = false;
+	cudaEvent_t evSetupMark[SWCU_SETS] = {}; // scratch: "this setup stream up to here" (uploads wait for the readers of the old contents)
+	bool setupReadsInputs[SWCU_SETS] = {};   // a setup phase ran on this setup stream since the last upload looked
 	// Host<->device copies run on their own two streams (one per DMA direction), so the upload of the next frame's inputs and
 	// the download of the previous frame overlap the kernels of the current one; events order them against the kernels:
 	cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
 	cudaEvent_t evUpload = nullptr;  // after the last swcu_mem_upload
-	uint64_t uploadSeq = 0, mainSawUpload = 0, setupSawUpload = 0, d2hSawUpload = 0;
+	uint64_t uploadSeq = 0, mainSawUpload = 0, setupSawUpload[SWCU_SETS] = {}, d2hSawUpload = 0;
 	cudaEvent_t evMark = nullptr;    // scratch: "the main stream up to here"
 	cudaEvent_t evDownload = nullptr; // after the last swcu_mem_download
 	uint64_t downloadSeq = 0, mainSawDownload = 0;
@@ -106,6 +123,8 @@ struct swcu_ctx
 	int optTma = 1;
 	int optFastState = 1;
 	int optWriteOnly = 1;
+	int optSetupWide = 1;
+	int smCount = 148;
 	void *encodeTiled = nullptr; // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda link dependency)
 	std::map<std::vector<uint64_t>, CUtensorMap> mapCache;
 };
@@ -136,7 +155,8 @@ static int ensure(swcu_ctx *ctx, DevBuf &b, size_t bytes)
 	if(b.p)
 	{
 		CU(cudaStreamSynchronize(ctx->stream)); // earlier launches may still read the old block
-		if(ctx->setupStream) CU(cudaStreamSynchronize(ctx->setupStream));
+		for(cudaStream_t ss : ctx->setupStream)
+			if(ss) CU(cudaStreamSynchronize(ss));
 		CU(cudaFree(b.p));
 		b.p = nullptr;
 		b.cap = 0;
@@ -157,17 +177,25 @@ static int ensure(swcu_ctx *ctx, DevBuf &b, size_t bytes)
 // SWCU_SETUP_PRIORITY=0 / 1 forces it off / on.
 static cudaError_t make_setup_stream(swcu_ctx *ctx, bool grouped)
 {
-	if(ctx->setupStream)
-	{
-		cudaStreamSynchronize(ctx->setupStream);
-		cudaStreamDestroy(ctx->setupStream);
-		ctx->setupStream = nullptr;
-	}
 	int least = 0, greatest = 0;
 	cudaDeviceGetStreamPriorityRange(&least, &greatest);
 	const char *pe = getenv("SWCU_SETUP_PRIORITY");
 	const bool high = pe ? pe[0] != '0' : grouped;
-	return cudaStreamCreateWithPriority(&ctx->setupStream, cudaStreamNonBlocking, high ? greatest : least);
+	for(int i = 0; i < SWCU_SETS; i++)
+	{
+		if(ctx->setupStream[i])
+		{
+			cudaStreamSynchronize(ctx->setupStream[i]);
+			cudaStreamDestroy(ctx->setupStream[i]);
+			ctx->setupStream[i] = nullptr;
+		}
+		cudaError_t e = cudaStreamCreateWithPriority(&ctx->setupStream[i], cudaStreamNonBlocking, high ? greatest : least);
+		if(e != cudaSuccess) return e;
+		ctx->setupSawUpload[i] = 0; // (a new stream has waited for nothing yet)
+		ctx->setupReadsInputs[i] = false;
+	}
+	ctx->evBarrierValid = false;
+	return cudaSuccess;
 }
 
 extern "C" int swcu_create(swcu_ctx **out, int device_ordinal)
@@ -190,6 +218,7 @@ extern "C" int swcu_create(swcu_ctx **out, int device_ordinal)
 		return rc;
 	};
 	if((e = cudaSetDevice(device_ordinal)) != cudaSuccess) return bail("cudaSetDevice", e);
+	cudaDeviceGetAttribute(&ctx->smCount, cudaDevAttrMultiProcessorCount, device_ordinal);
 	if((e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
 	ctx->stream = ctx->ownStream;
 	if((e = cudaEventCreate(&ctx->t0)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -227,7 +256,8 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 		if(kv.second.dlEvent) cudaEventDestroy(kv.second.dlEvent);
 		if(kv.second.upEvent) cudaEventDestroy(kv.second.upEvent);
 	}
-	if(ctx->setupStream) cudaStreamSynchronize(ctx->setupStream);
+	for(cudaStream_t ss : ctx->setupStream)
+		if(ss) cudaStreamSynchronize(ss);
 	swcu_group_detach(ctx);
 	cudaFree(ctx->zeroPage.p);
 	for(auto &S : ctx->set)
@@ -245,7 +275,15 @@ extern "C" void swcu_destroy(swcu_ctx *ctx)
 		if(f) cudaEventDestroy(f);
 	if(ctx->h2dStream) cudaStreamDestroy(ctx->h2dStream);
 	if(ctx->d2hStream) cudaStreamDestroy(ctx->d2hStream);
-	if(ctx->setupStream) cudaStreamDestroy(ctx->setupStream);
+	for(cudaStream_t ss : ctx->setupStream)
+		if(ss) cudaStreamDestroy(ss);
+	for(cudaEvent_t ev : ctx->evSetupMark)
+		if(ev) cudaEventDestroy(ev);
+	if(ctx->evBarrier) cudaEventDestroy(ctx->evBarrier);
+	if(ctx->sideStream) { cudaStreamSynchronize(ctx->sideStream); cudaStreamDestroy(ctx->sideStream); }
+	if(ctx->evSideBegin) cudaEventDestroy(ctx->evSideBegin);
+	for(cudaEvent_t ev : ctx->sideDone)
+		if(ev) cudaEventDestroy(ev);
 	for(cudaEvent_t ev : ctx->eventPool) cudaEventDestroy(ev);
 	if(ctx->t0) cudaEventDestroy(ctx->t0);
 	if(ctx->t1) cudaEventDestroy(ctx->t1);
@@ -329,8 +367,9 @@ extern "C" int swcu_mem_unregister(swcu_ctx *ctx, const void *host_base)
 	if(it == ctx->mem.end()) return fail(ctx, SWCU_E_INVALID, "swcu_mem_unregister: %p is not a registered base", host_base);
 	CU(cudaSetDevice(ctx->device));
 	CU(cudaStreamSynchronize(ctx->h2dStream));
-	CU(cudaStreamSynchronize(ctx->setupStream));
+	for(cudaStream_t ss : ctx->setupStream) CU(cudaStreamSynchronize(ss));
 	CU(cudaStreamSynchronize(ctx->stream));
+	if(ctx->sideStream) CU(cudaStreamSynchronize(ctx->sideStream));
 	CU(cudaStreamSynchronize(ctx->d2hStream));
 	if(it->second.pinned) cudaHostUnregister((void *)it->second.host);
 	if(!it->second.external) cudaFree(it->second.dev);
@@ -390,13 +429,21 @@ extern "C" int swcu_mem_upload(swcu_ctx *ctx, const void *host_ptr, size_t bytes
 	const cudaStream_t st = ctx->optCopyStreams ? ctx->h2dStream : ctx->stream;
 	if(ctx->optCopyStreams)
 	{
-		// Readers of the old contents.  The setup phase of a pipelined draw has been waited for by the host (swcu_draw's one
-		// sync), so plain vertex / index streams need nothing; kernels of the main stream do.
+		// Readers of the old contents: kernels of the main stream, and the setup phases of pipelined draws on the setup streams
+		// (they read the vertex / index streams)
 		if(s->mainTouched || ctx->mainReadsInputs)
 		{
 			CU(cudaEventRecord(ctx->evMark, ctx->stream));
 			CU(cudaStreamWaitEvent(st, ctx->evMark, 0));
 			ctx->mainReadsInputs = false;
+		}
+		for(int i = 0; i < SWCU_SETS; i++)
+		{
+			if(!ctx->setupReadsInputs[i]) continue;
+			if(!ctx->evSetupMark[i]) CU(cudaEventCreateWithFlags(&ctx->evSetupMark[i], cudaEventDisableTiming));
+			CU(cudaEventRecord(ctx->evSetupMark[i], ctx->setupStream[i]));
+			CU(cudaStreamWaitEvent(st, ctx->evSetupMark[i], 0));
+			ctx->setupReadsInputs[i] = false;
 		}
 		if(s->dlPendingUpload)
 		{
@@ -430,7 +477,7 @@ extern "C" int swcu_mem_download(swcu_ctx *ctx, void *host_ptr, size_t bytes)
 		return SWCU_OK;
 	}
 	const cudaStream_t st = ctx->d2hStream;
-	CU(cudaEventRecord(ctx->evMark, ctx->stream)); // everything issued on the main stream so far has produced its pixels
+	CU(cudaEventRecord(ctx->evMark, ctx->handover())); // everything issued so far (main stream; hand-over stream: what it waits for) has produced its pixels
 	CU(cudaStreamWaitEvent(st, ctx->evMark, 0));
 	int rc = see_upload(ctx, s, st, ctx->d2hSawUpload);
 	if(rc) return rc;
@@ -452,6 +499,11 @@ extern "C" int swcu_fence_signal(swcu_ctx *ctx, uint32_t slot)
 	const cudaStream_t st = ctx->d2hStream; // downloads are the tail of a frame: join the other streams here
 	CU(cudaEventRecord(ctx->evMark, ctx->stream));
 	CU(cudaStreamWaitEvent(st, ctx->evMark, 0));
+	if(ctx->sideStream)
+	{
+		CU(cudaEventRecord(ctx->evMark, ctx->sideStream));
+		CU(cudaStreamWaitEvent(st, ctx->evMark, 0));
+	}
 	int rc = see_uploads(ctx, st, ctx->d2hSawUpload);
 	if(rc) return rc;
 	CU(cudaEventRecord(ctx->fence[slot], st));
@@ -535,8 +587,9 @@ extern "C" int swcu_sync(swcu_ctx *ctx)
 	if(!ctx) return SWCU_E_INVALID;
 	CU(cudaSetDevice(ctx->device));
 	CU(cudaStreamSynchronize(ctx->h2dStream));
-	CU(cudaStreamSynchronize(ctx->setupStream));
+	for(cudaStream_t ss : ctx->setupStream) CU(cudaStreamSynchronize(ss));
 	CU(cudaStreamSynchronize(ctx->stream));
+	if(ctx->sideStream) CU(cudaStreamSynchronize(ctx->sideStream));
 	CU(cudaStreamSynchronize(ctx->d2hStream));
 	// the device is idle: the counters of every finished draw are on the host
 	for(auto &S : ctx->set)
@@ -604,6 +657,7 @@ extern "C" int swcu_last_draw_kernels(swcu_ctx *ctx, const char **names, float *
 	if(!ctx) return SWCU_E_INVALID;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	if(ctx->sideStream) cudaStreamSynchronize(ctx->sideStream);
 	int k = 0;
 	for(const KernelTime &t : ctx->lastKernels)
 	{
@@ -617,6 +671,32 @@ extern "C" int swcu_last_draw_kernels(swcu_ctx *ctx, const char **names, float *
 	return k;
 }
 
+// Diagnostics (no counterpart in the reference): with swcu_set_profiling(ctx, 2) the draws stay pipelined over their streams and every
+// kernel of the library is bracketed by events on the stream it really runs on; this returns the begin / end of each one in
+// milliseconds since the first of them — the timeline of the frames issued since the mode was switched on — and starts a new one.
+extern "C" int swcu_timeline(swcu_ctx *ctx, const char **names, float *begin_ms, float *end_ms, int n)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	cudaSetDevice(ctx->device);
+	int rc = swcu_sync(ctx);
+	if(rc) return rc;
+	int k = 0;
+	for(const KernelTime &t : ctx->lastKernels)
+	{
+		if(k >= n) break;
+		float a = 0, b = 0;
+		cudaEventElapsedTime(&a, ctx->lastKernels[0].e0, t.e0);
+		cudaEventElapsedTime(&b, ctx->lastKernels[0].e0, t.e1);
+		names[k] = t.name;
+		begin_ms[k] = a;
+		end_ms[k] = b;
+		k++;
+	}
+	ctx->lastKernels.clear();
+	ctx->eventsUsed = 0;
+	return k;
+}
+
 extern "C" int swcu_set_option(swcu_ctx *ctx, const char *name, int value)
 {
 	if(!ctx || !name) return SWCU_E_INVALID;
@@ -626,6 +706,7 @@ extern "C" int swcu_set_option(swcu_ctx *ctx, const char *name, int value)
 	else if(!strcmp(name, "tma")) ctx->optTma = value;
 	else if(!strcmp(name, "fast_state")) ctx->optFastState = value;
 	else if(!strcmp(name, "write_only")) ctx->optWriteOnly = value;
+	else if(!strcmp(name, "setup_wide")) ctx->optSetupWide = value;
 	else if(!strcmp(name, "pipeline")) ctx->optPipeline = value;
 	else if(!strcmp(name, "big_pair_budget")) ctx->optBigPairBudget = (size_t)std::max(value, 0);
 	else if(!strcmp(name, "copy_streams"))
@@ -1189,7 +1270,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	if(rc) return rc;
 	ctx->stats.draws++;
 	ctx->stats.primitives += d.primCount;
-	if(ctx->profiling) { ctx->lastKernels.clear(); ctx->eventsUsed = 0; }
+	if(ctx->profiling == 1) { ctx->lastKernels.clear(); ctx->eventsUsed = 0; } // (2: the timeline keeps growing until swcu_timeline reads it)
 	if(d.primCount == 0 || d.sampleMask == 0) return SWCU_OK; // no sample enabled: PixelRoutine.cpp:104-111
 	// (an empty render area ends the draw here too — unless this rank is a member of a group: its share of the setup and the barrier of the draw are still due)
 	if((d.scX0 >= d.scX1 || d.scY0 >= d.scY1) && !(ctx->group.attached && (ctx->optForceBinned || (int)d.primCount > ctx->optDirectMax))) return SWCU_OK;
@@ -1206,16 +1287,21 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	const int setIndex = ctx->cur;
 	swcu_ctx::SetupSet &S = ctx->set[setIndex];
 	ctx->cur = (ctx->cur + 1) % SWCU_SETS;
-	const bool pipelined = !d.direct && ctx->optPipeline && !ctx->profiling && !d.inputsExternal;
-	const cudaStream_t ss = pipelined ? ctx->setupStream : ctx->stream;
+	const bool pipelined = !d.direct && ctx->optPipeline && ctx->profiling != 1 && !d.inputsExternal;
+	const int ssIndex = grouped ? setIndex : 0; // a group member: one setup stream per set (see swcu_ctx::setupStream)
+	const cudaStream_t ss = pipelined ? ctx->setupStream[ssIndex] : ctx->stream;
 	if(pipelined)
 	{
 		if(S.tileDoneValid) CU(cudaStreamWaitEvent(ss, S.tileDone, 0));
+		// The peers' buffers of this draw's set may be written once the barrier of the previous draw has been passed: every rank checks
+		// in there only when the last reader of ITS copy of the set has finished (see below).  On one stream the order was implicit.
+		if(grouped && ctx->evBarrierValid) CU(cudaStreamWaitEvent(ss, ctx->evBarrier, 0));
+		ctx->setupReadsInputs[ssIndex] = true;
 	}
 	else ctx->mainReadsInputs = true; // the setup phase reads the vertex / index streams on the main stream, asynchronously
 	{
 		// the vertex / index streams the setup phase reads: wait for THEIR uploads only
-		uint64_t &seen = pipelined ? ctx->setupSawUpload : ctx->mainSawUpload;
+		uint64_t &seen = pipelined ? ctx->setupSawUpload[ssIndex] : ctx->mainSawUpload;
 		for(int i = 0; i < SWCU_MAX_INPUTS; i++)
 			if(desc->input[i].buffer && (rc = see_upload(ctx, find_shadow(ctx, desc->input[i].buffer, 1), ss, seen))) return rc;
 		if(desc->indexBuffer && (rc = see_upload(ctx, find_shadow(ctx, desc->indexBuffer, 1), ss, seen))) return rc;
@@ -1317,7 +1403,14 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		const uint32_t share = d.triHi - d.triLo;
 		const size_t scratch = (size_t)SWCU_SMALL_ROWS * d.ms * SETUP_THREADS * 4;
 		if(d.vsProgLen || d.primKind != PRIM_TRIANGLE) k_setup_prog<<<(share + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d); // the vertex stage has arithmetic, or the primitives are lines / points
-		else if(d.ms != 1) k_setup<<<(share + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
+		else if(d.ms != 1)
+		{
+			// wave quantisation (see k_setup_wide): the variant with more resident CTAs when it saves enough waves to pay for its slower ones
+			const unsigned blocks = (share + SETUP_THREADS - 1) / SETUP_THREADS, sms = (unsigned)std::max(ctx->smCount, 1);
+			const unsigned w6 = (blocks + sms * SETUP_BLOCKS_4X - 1) / (sms * SETUP_BLOCKS_4X), w7 = (blocks + sms * SETUP_BLOCKS_WIDE - 1) / (sms * SETUP_BLOCKS_WIDE);
+			if(ctx->optSetupWide == 2 /* forced: parity tests */ || (ctx->optSetupWide && w7 * 1.24f < w6 * 0.9f)) k_setup_wide<<<blocks, SETUP_THREADS, scratch, ss>>>(d);
+			else k_setup<<<blocks, SETUP_THREADS, scratch, ss>>>(d);
+		}
 		else k_setup_1x<<<(share + SETUP_THREADS - 1) / SETUP_THREADS, SETUP_THREADS, scratch, ss>>>(d);
 	}
 	if(grouped)
@@ -1332,6 +1425,12 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		for(uint32_t p = 0; p < G.world; p++) gf.flags[p] = (uint32_t *)(G.peer[p] + G.offFlags[setIndex]);
 		LaunchScope ls(ctx, "k_xbarrier", ss);
 		k_xbarrier<<<1, 32, 0, ss>>>(gf, G.world, G.rank, ++G.epoch[setIndex]);
+		if(pipelined)
+		{
+			if(!ctx->evBarrier) CU(cudaEventCreateWithFlags(&ctx->evBarrier, cudaEventDisableTiming));
+			CU(cudaEventRecord(ctx->evBarrier, ss));
+			ctx->evBarrierValid = true;
+		}
 	}
 	const bool nothingToDraw = d.scX0 >= d.scX1 || d.scY0 >= d.scY1; // (only a group member gets here with an empty band)
 	if(!d.direct)
@@ -1344,7 +1443,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 		}
 		{
 			LaunchScope ls(ctx, "k_fill", ss);
-			const unsigned smallBlocks = (n + 255) / 256;
+			const unsigned smallBlocks = (n + 256 * FILL_TRIS - 1) / (256 * FILL_TRIS);
 			k_fill<<<smallBlocks + bigBlocks, 256, 0, ss>>>(d, smallBlocks);
 		}
 		S.countersPending = true;
@@ -1376,7 +1475,7 @@ extern "C" int swcu_draw(swcu_ctx *ctx, const swcu_draw_desc *desc)
 	{
 		// reset what the peers will write into two draws from now: their next share arrives behind the barrier of the draw in between
 		CU(cudaMemsetAsync(d.counters, 0, G.countersBytes, ctx->stream));
-		CU(cudaMemsetAsync(d.triRect, 0xFF, (size_t)n * 4, ctx->stream));
+		// (the rectangles are put back to "none" by k_fill as it reads them)
 	}
 	CU(cudaEventRecord(S.tileDone, ctx->stream)); // last reader of this set's records / bins
 	S.tileDoneValid = true;
@@ -1466,7 +1565,7 @@ extern "C" int swcu_group_detach(swcu_ctx *ctx)
 	cudaFree(G.arena);
 	cudaGetLastError();
 	G = swcu_ctx::Group();
-	if(ctx->setupStream) make_setup_stream(ctx, false); // (not while the context is being torn down)
+	if(ctx->setupStream[0]) make_setup_stream(ctx, false); // (not while the context is being torn down)
 	return rc;
 }
 
@@ -1517,9 +1616,22 @@ extern "C" int swcu_copy_image(swcu_ctx *ctx, const swcu_attachment *src, const 
 	const int vec = ((uintptr_t)s % 16 == 0) && ((uintptr_t)t % 16 == 0) && (src->pitchB % 16 == 0) && (dst->pitchB % 16 == 0) && (rowB % 16 == 0);
 	const int per = vec ? 16 : 4;
 	int rc;
-	if((rc = main_touches(ctx, src->buffer, false)) || (rc = main_touches(ctx, dst->buffer, true))) return rc;
-	LaunchScope ls(ctx, "k_copy_rows");
-	k_copy_rows<<<dim3((unsigned)((rowB / per + 255) / 256), src->height), 256, 0, ctx->stream>>>(s, src->pitchB, t, dst->pitchB, (int)rowB, (int)src->height, vec);
+	const cudaStream_t st = ctx->handover();
+	if(ctx->sideActive)
+	{
+		// on the hand-over stream: it has waited for the main stream at swcu_side_begin; what is left are copies in flight on the two
+		// images (the bookkeeping of the main stream is not touched: it has not seen these waits)
+		const swcu_attachment *both[2] = { src, dst };
+		for(int i = 0; i < 2; i++)
+		{
+			Shadow *sh = find_shadow(ctx, both[i]->buffer, 1);
+			if(sh && sh->upEvent && sh->upSeq) CU(cudaStreamWaitEvent(st, sh->upEvent, 0));
+			if(sh && i == 1 && sh->dlEvent && (sh->dlPendingMain || sh->dlPendingUpload)) CU(cudaStreamWaitEvent(st, sh->dlEvent, 0));
+		}
+	}
+	else if((rc = main_touches(ctx, src->buffer, false)) || (rc = main_touches(ctx, dst->buffer, true))) return rc;
+	LaunchScope ls(ctx, "k_copy_rows", st);
+	k_copy_rows<<<dim3((unsigned)((rowB / per + 255) / 256), src->height), 256, 0, st>>>(s, src->pitchB, t, dst->pitchB, (int)rowB, (int)src->height, vec);
 	CU(cudaGetLastError());
 	return SWCU_OK;
 }
@@ -1533,11 +1645,11 @@ extern "C" int swcu_signal(swcu_ctx *ctx, void *flag, uint32_t value)
 	// A flag tells a peer that this rank's frame may be overwritten, so downloads still in flight come first.  The flag is then
 	// written from the download stream, behind them (and behind everything issued on the main stream so far): the main stream
 	// itself is not held back and goes on with the next frame's draw.
-	cudaStream_t st = ctx->stream;
+	cudaStream_t st = ctx->handover();
 	if(ctx->optCopyStreams && ctx->mainSawDownload != ctx->downloadSeq)
 	{
+		CU(cudaEventRecord(ctx->evMark, st));
 		st = ctx->d2hStream;
-		CU(cudaEventRecord(ctx->evMark, ctx->stream));
 		CU(cudaStreamWaitEvent(st, ctx->evMark, 0));
 		ctx->mainSawDownload = ctx->downloadSeq;
 	}
@@ -1554,9 +1666,47 @@ extern "C" int swcu_wait_flags(swcu_ctx *ctx, const void *flags, uint32_t first,
 	CU(cudaSetDevice(ctx->device));
 	unsigned char *f = dev_ptr(ctx, flags, (size_t)(first + count) * 4);
 	if(!f) return fail(ctx, SWCU_E_INVALID, "swcu_wait_flags: flags are not inside a registered range");
-	LaunchScope ls(ctx, "k_wait_flags");
-	k_wait_flags<<<1, 64, 0, ctx->stream>>>((const uint32_t *)f, (int)first, (int)count, value);
+	LaunchScope ls(ctx, "k_wait_flags", ctx->handover());
+	k_wait_flags<<<1, 64, 0, ctx->handover()>>>((const uint32_t *)f, (int)first, (int)count, value);
 	CU(cudaGetLastError());
+	return SWCU_OK;
+}
+
+// ---- the hand-over stream ----
+extern "C" int swcu_side_begin(swcu_ctx *ctx)
+{
+	if(!ctx) return SWCU_E_INVALID;
+	if(ctx->sideActive) return fail(ctx, SWCU_E_INVALID, "swcu_side_begin: already begun");
+	CU(cudaSetDevice(ctx->device));
+	if(!ctx->sideStream)
+	{
+		CU(cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&ctx->evSideBegin, cudaEventDisableTiming));
+	}
+	CU(cudaEventRecord(ctx->evSideBegin, ctx->stream));
+	CU(cudaStreamWaitEvent(ctx->sideStream, ctx->evSideBegin, 0));
+	ctx->sideActive = true;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_side_end(swcu_ctx *ctx, uint32_t slot)
+{
+	if(!ctx || slot >= SWCU_SIDE_SLOTS) return fail(ctx, SWCU_E_INVALID, "swcu_side_end: bad slot");
+	if(!ctx->sideActive) return fail(ctx, SWCU_E_INVALID, "swcu_side_end without swcu_side_begin");
+	CU(cudaSetDevice(ctx->device));
+	if(!ctx->sideDone[slot]) CU(cudaEventCreateWithFlags(&ctx->sideDone[slot], cudaEventDisableTiming));
+	CU(cudaEventRecord(ctx->sideDone[slot], ctx->sideStream));
+	ctx->sideDoneValid[slot] = true;
+	ctx->sideActive = false;
+	return SWCU_OK;
+}
+
+extern "C" int swcu_side_wait(swcu_ctx *ctx, uint32_t slot)
+{
+	if(!ctx || slot >= SWCU_SIDE_SLOTS) return fail(ctx, SWCU_E_INVALID, "swcu_side_wait: bad slot");
+	if(!ctx->sideDoneValid[slot]) return SWCU_OK;
+	CU(cudaSetDevice(ctx->device));
+	CU(cudaStreamWaitEvent(ctx->stream, ctx->sideDone[slot], 0));
 	return SWCU_OK;
 }
 

@@ -914,6 +914,11 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_BLOCKS_1X) k_setup_1x(con
 #define SETUP_BLOCKS_4X 6 // 80 registers, no spills: C4 set-up 0.183 -> 0.175 ms (5 CTAs of 96 registers before; 7 CTAs of 72 spill and take 0.186 ms)
 #endif
 __global__ void __launch_bounds__(SETUP_THREADS, SETUP_BLOCKS_4X) k_setup(const __grid_constant__ DrawConst d) { setup_triangle<0>(d); }
+// The same kernel capped at 72 registers (7 CTAs per SM; it spills a little and a wave of it takes ~1.24x as long): launched when the
+// draw — a rank's share of a group draw — then fits in fewer waves.  Every thread is one triangle's serial chain, so a wave costs its
+// full latency however empty it is: 125 k triangles are 1.1 waves of k_setup (two wave times) but one wave of this one.
+#define SETUP_BLOCKS_WIDE 7
+__global__ void __launch_bounds__(SETUP_THREADS, SETUP_BLOCKS_WIDE) k_setup_wide(const __grid_constant__ DrawConst d) { setup_triangle<0>(d); }
 __global__ void __launch_bounds__(SETUP_THREADS) k_setup_prog(const __grid_constant__ DrawConst d) { setup_triangle<0, true>(d); }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1105,6 +1110,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_binscan(const __grid_constant_
 
 // every (region, triangle) pair takes a slot of its bin; blocks [0, smallBlocks) walk the small triangles (one thread each),
 // the blocks after them the big list (one warp per triangle)
+#define FILL_TRIS 4
 __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ DrawConst d, uint32_t smallBlocks)
 {
 	if(blockIdx.x >= smallBlocks)
@@ -1112,22 +1118,39 @@ __global__ void __launch_bounds__(256) k_fill(const __grid_constant__ DrawConst 
 		big_regions<true>(d, (blockIdx.x - smallBlocks) * BIG_WARPS_PER_BLOCK + (threadIdx.x >> 5), (gridDim.x - smallBlocks) * BIG_WARPS_PER_BLOCK);
 		return;
 	}
-	const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t r = tri < d.primCount ? d.triRect[tri] : TRI_RECT_NONE;
-	const bool small = !(r & TRI_RECT_BIG); // big: the blocks behind the small ones; invisible: nothing to do
-	const int rx0 = r & 0x1FF, ry0 = (r >> 9) & 0x3FF, rx1 = rx0 + ((r >> 19) & 1), ry1 = ry0 + ((r >> 20) & 1);
-	// warp-aggregated: one atomic per distinct bin of the warp's triangles.  A cell counts here if its region row holds rows of MY
-	// part of the frame — the rule k_setup (possibly on another rank) counted it by
+	// FILL_TRIS triangles per thread — a warp walks 32 * FILL_TRIS consecutive triangles, 32 consecutive ones per step (neighbours of
+	// a mesh share their bins: one atomic per distinct bin of a step), all rectangles requested up front.  A block of one-triangle
+	// threads lived for one trip to memory, and the pass over a big mesh — of which a rank of a group owns only its band — was bound
+	// by the turnover of such blocks (10 M triangles: 54 us however few of them were the rank's).
+	const uint32_t warpBase = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32u * FILL_TRIS) + (threadIdx.x & 31);
+	uint32_t rr[FILL_TRIS];
 #pragma unroll
-	for(int cell = 0; cell < 4; cell++)
+	for(int k = 0; k < FILL_TRIS; k++) rr[k] = warpBase + 32u * k < d.primCount ? d.triRect[warpBase + 32u * k] : TRI_RECT_NONE;
+	// (a thread of invisible / big / foreign triangles has nothing to do; a warp of them leaves here)
+	if(!__any_sync(0xFFFFFFFFu, !(rr[0] & rr[1] & rr[2] & rr[3] & TRI_RECT_BIG))) return;
+#pragma unroll
+	for(int k = 0; k < FILL_TRIS; k++)
 	{
-		const int cx = (cell & 1) ? rx1 : rx0, cy = (cell & 2) ? ry1 : ry0;
-		const bool has = small && (!(cell & 1) || rx1 > rx0) && (!(cell & 2) || ry1 > ry0) &&
-		                 max(cy * SWCU_REGION_H, d.scY0) < min(cy * SWCU_REGION_H + SWCU_REGION_H, d.scY1);
-		if(!__any_sync(0xFFFFFFFFu, has)) continue;
-		const uint32_t bin = has ? region_bin(d, cx, cy) : 0u;
-		const uint32_t slot = warp_bin_slot(d.binCount, has, bin);
-		if(has) d.pairs[d.binStart[bin] + slot] = tri;
+		const uint32_t tri = warpBase + 32u * k, r = rr[k];
+		// a member of a group: the rectangles come from the peers (only those of visible triangles are stored), so every entry that has
+		// been read goes back to "none" for the draw that uses this set next — no pass over the whole array in between
+		if(d.world > 1 && r != TRI_RECT_NONE) d.triRect[tri] = TRI_RECT_NONE;
+		const bool small = !(r & TRI_RECT_BIG); // big: the blocks behind the small ones; invisible: nothing to do
+		if(!__any_sync(0xFFFFFFFFu, small)) continue;
+		const int rx0 = r & 0x1FF, ry0 = (r >> 9) & 0x3FF, rx1 = rx0 + ((r >> 19) & 1), ry1 = ry0 + ((r >> 20) & 1);
+		// warp-aggregated: one atomic per distinct bin of the warp's triangles.  A cell counts here if its region row holds rows of MY
+		// part of the frame — the rule k_setup (possibly on another rank) counted it by
+#pragma unroll
+		for(int cell = 0; cell < 4; cell++)
+		{
+			const int cx = (cell & 1) ? rx1 : rx0, cy = (cell & 2) ? ry1 : ry0;
+			const bool has = small && (!(cell & 1) || rx1 > rx0) && (!(cell & 2) || ry1 > ry0) &&
+			                 max(cy * SWCU_REGION_H, d.scY0) < min(cy * SWCU_REGION_H + SWCU_REGION_H, d.scY1);
+			if(!__any_sync(0xFFFFFFFFu, has)) continue;
+			const uint32_t bin = has ? region_bin(d, cx, cy) : 0u;
+			const uint32_t slot = warp_bin_slot(d.binCount, has, bin);
+			if(has) d.pairs[d.binStart[bin] + slot] = tri;
+		}
 	}
 }
 

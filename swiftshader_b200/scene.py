@@ -502,7 +502,7 @@ class Device:
     def reset_stats(self):
         self.check(self.lib.swcu_reset_stats(self.ctx))
 
-    def set_profiling(self, on: bool):
+    def set_profiling(self, on):
         self.check(self.lib.swcu_set_profiling(self.ctx, int(on)))
 
     def last_draw_kernels(self) -> list:
@@ -510,6 +510,14 @@ class Device:
         ms = (C.c_float * 64)()
         n = self.lib.swcu_last_draw_kernels(self.ctx, names, ms, 64)
         return [(names[i].decode(), float(ms[i])) for i in range(max(n, 0))]
+
+    def timeline(self, cap: int = 4096) -> list:
+        """(name, begin ms, end ms) of every kernel issued since set_profiling(2), on the streams they really ran on."""
+        names = (C.c_char_p * cap)()
+        t0 = (C.c_float * cap)()
+        t1 = (C.c_float * cap)()
+        n = self.lib.swcu_timeline(self.ctx, names, t0, t1, cap)
+        return [(names[i].decode(), float(t0[i]), float(t1[i])) for i in range(max(n, 0))]
 
     def set_option(self, name: str, value: int):
         self.check(self.lib.swcu_set_option(self.ctx, name.encode(), value))

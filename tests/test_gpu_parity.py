@@ -71,3 +71,22 @@ def test_cuda_matches_reference_golden_and_oracle(device, name, mode):
         want = swref.render_oracle(scene)
         for k in want:
             assert np.array_equal(att[k].view(np.uint8), want[k].view(np.uint8)), f"{name}/{k}: sample planes differ from the oracle"
+
+
+MSAA_CASES = sorted(n for n, sc in CASES.items() if sc.samples > 1)
+
+
+@pytest.mark.parametrize("name", MSAA_CASES)
+def test_wide_setup_variant_matches_the_goldens(device, name):
+    """k_setup_wide (the 72-register build of the 4x set-up kernel, picked by wave count for a rank's share of a group draw) forced on
+    every multisampled golden scene, binned: same bytes."""
+    scene = CASES[name]
+    device.set_option("force_binned", 1)
+    device.set_option("setup_wide", 2)
+    try:
+        att, out = cuda_outputs(device, scene)
+    finally:
+        device.set_option("force_binned", 0)
+        device.set_option("setup_wide", 1)
+    for k, h in HASHES[name].items():
+        assert sha(out[k]) == h, f"{name}/{k}: k_setup_wide differs from the reference golden"
