@@ -307,20 +307,20 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 			const Value &base = values[a[2]];
 			if(base.kind == Value::Pointer && base.pcType)
 			{
-				// into the push-constant block: member [, column [, row]] / member [, component], every index a constant
+				// into the push-constant block or a uniform block: member [, column [, row]] / member [, component], every index a constant
 				Value v = base;
 				for(uint32_t i = 3; i < na; i++)
 				{
 					ID(a[i]);
-					if(values[a[i]].kind != Value::IntConst) return fail("push-constant access chain index must be an integer constant");
+					if(values[a[i]].kind != Value::IntConst) return fail("access chain index into a push-constant / uniform block must be an integer constant");
 					const uint32_t idx = values[a[i]].ival;
 					const Type &t = types[v.pcType];
 					if(t.kind == Type::Struct)
 					{
-						if(idx >= t.members.size()) return fail("push-constant member index out of range");
+						if(idx >= t.members.size()) return fail("block member index out of range");
 						const Deco &sd = decos[v.pcType];
 						auto off = sd.memberOffset.find(idx);
-						if(off == sd.memberOffset.end()) return fail("push-constant member without Offset");
+						if(off == sd.memberOffset.end()) return fail("block member without Offset");
 						v.pcOffset += off->second;
 						v.pcType = t.members[idx];
 						if(types[v.pcType].kind == Type::Matrix)
@@ -345,7 +345,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 						v.pcOffset += (v.pcStride ? v.pcStride : 4) * idx;
 						v.pcType = t.elem;
 					}
-					else return fail("push-constant access chain into an unsupported type");
+					else return fail("access chain into an unsupported type of a push-constant / uniform block");
 				}
 				values[a[1]] = v;
 				break;
@@ -400,7 +400,7 @@ extern "C" int swcu_shader_translate(const uint32_t *code, uint32_t words, swcu_
 						for(int i = 0; i < rows; i++)
 							v.c[j * rows + i] = word(check(p.pcOffset + (p.pcRowMajor ? p.pcStride * i + 4 * j : p.pcStride * j + 4 * i)));
 				}
-				else return fail("load of an unsupported push-constant type");
+				else return fail("load of an unsupported type from a push-constant / uniform block");
 				if(bad) return fail("%s access beyond %d bytes or unaligned", ubo >= 0 ? "uniform-buffer" : "push-constant", ubo >= 0 ? 65536 : 4 * SWCU_MAX_PUSH_WORDS);
 				values[a[1]] = v;
 				break;
